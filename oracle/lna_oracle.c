@@ -1,0 +1,867 @@
+/*
+ * lna_oracle.c -- CPU ORACLE (test infrastructure; see lna_oracle.h for the rules of use).
+ *
+ * A literal scalar restatement of the reference's arithmetic for the hot path, INCLUDING its
+ * quirks: the non-standard "RK4" whose k4 uses dt/2, explicit-Euler
+ * fundamental matrix / covariance, the 1e-8 Cholesky jitter, the -1e7 sentinels, the
+ * logOrigin that drops its last row in one sampler only, ...
+ * Compile with `-O2 -ffp-contract=off` (no FMA contraction, like a default R package build).
+ *
+ * Every function cites the reference file:line (under /root/reference/) it restates.
+ */
+#include "lna_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_PI 3.14159265358979323846264338327950288 /* src/LNA_functional.h:6 */
+#define MAXP 3
+
+/* ---------------------------------------------------------------- small dense helpers (col-major) */
+static void mat_mul(const double *A, const double *B, int p, double *C) { /* C = A*B */
+    for (int c = 0; c < p; c++)
+        for (int r = 0; r < p; r++) {
+            double s = A[r] * B[c * p];
+            for (int k = 1; k < p; k++) s += A[r + k * p] * B[k + c * p];
+            C[r + c * p] = s;
+        }
+}
+static void mat_mul_bt(const double *A, const double *B, int p, double *C) { /* C = A*B^T */
+    for (int c = 0; c < p; c++)
+        for (int r = 0; r < p; r++) {
+            double s = A[r] * B[c];
+            for (int k = 1; k < p; k++) s += A[r + k * p] * B[c + k * p];
+            C[r + c * p] = s;
+        }
+}
+/* arma::accu / sum() of a vector: two interleaved accumulators (arrayops::accumulate). */
+static double accu2(const double *x, int n) {
+    double a1 = 0.0, a2 = 0.0;
+    int i, j;
+    for (i = 0, j = 1; j < n; i += 2, j += 2) {
+        a1 += x[i];
+        a2 += x[j];
+    }
+    if (i < n) a1 += x[i];
+    return a1 + a2;
+}
+
+/* ---------------------------------------------------------------- change-point transmission rate */
+
+/* betaTs: LNA_functional.cpp:31-58.  Single sweep over sorted times. */
+void orc_betaTs(const double *param, const double *times, int m, const double *x_r, const int *x_i,
+                double *betas) {
+    double R0 = param[x_i[2]];
+    int i = 0, nch = x_i[0];
+    for (int j = 0; j < m; j++) {
+        if (i < nch) {
+            while (x_r[i + 1] <= times[j]) {
+                R0 *= param[x_i[1] + i];
+                i++;
+                if (i == nch) break;
+            }
+        }
+        betas[j] = R0 * param[x_i[3]] / x_r[0];
+    }
+}
+
+/* param_transform: LNA_functional.cpp:63-86.  Rescans from scratch; only entry 0 changes. */
+void orc_param_transform(double t, const double *param, int nparam_total, const double *x_r,
+                         const int *x_i, double *param2) {
+    memcpy(param2, param, sizeof(double) * (size_t)nparam_total);
+    double R0 = param[x_i[2]];
+    int i = 0, nch = x_i[0];
+    if (nch > 0) {
+        while (x_r[i + 1] <= t) {
+            R0 *= param[x_i[1] + i];
+            if (i == nch - 1) break;
+            i++;
+        }
+    }
+    param2[0] = R0 * param[x_i[3]] / x_r[0];
+}
+
+/* Only thetas[0..2] are ever read by rhs / F / h, so the transform is applied on a 3-vector view. */
+static void thetas3(const orc_cfg *c, double t, const double *param, double *th) {
+    double R0 = param[c->x_i[2]];
+    int i = 0, nch = c->x_i[0];
+    if (nch > 0) {
+        while (c->x_r[i + 1] <= t) {
+            R0 *= param[c->x_i[1] + i];
+            if (i == nch - 1) break;
+            i++;
+        }
+    }
+    th[0] = R0 * param[c->x_i[3]] / c->x_r[0];
+    th[1] = c->nparam_total > 1 ? param[1] : 0.0;
+    th[2] = c->nparam_total > 2 ? param[2] : 0.0;
+}
+
+/* ---------------------------------------------------------------- model rhs / Jacobian / hazards */
+
+/* ODE_SIR_one :107-127, ODE_SEIR2_one :130-153, ODE_SEIR_one :156-198. */
+void orc_ode_one(const orc_cfg *c, const double *x, const double *param, double t, double *res) {
+    double th[3];
+    thetas3(c, t, param, th);
+    if (c->model == ORC_SIR) {
+        if (c->transX == ORC_STANDARD) {
+            res[0] = -th[0] * x[0] * x[1];
+            res[1] = th[0] * x[0] * x[1] - th[1] * x[1];
+        } else {
+            res[0] = -th[0] * exp(x[1]) - th[0] * exp(x[1] - x[0]) / 2;
+            res[1] = th[0] * exp(x[0]) - th[1] - th[0] * exp(x[0] - x[1]) / 2 - th[1] * exp(-x[1]) / 2;
+        }
+    } else if (c->model == ORC_SEIR2) {
+        double N = c->x_r[0];
+        res[0] = th[0] * N * x[1] - th[1] * x[0];
+        res[1] = th[1] * x[0] - th[2] * x[1];
+    } else { /* SEIR */
+        if (c->transX == ORC_STANDARD) {
+            res[0] = -th[0] * x[0] * x[2];
+            res[1] = th[0] * x[0] * x[2] - th[1] * x[1];
+            res[2] = th[1] * x[1] - th[2] * x[2];
+        } else {
+            res[0] = -th[0] * exp(x[2]) - th[0] * exp(x[2] - x[0]) / 2;
+            res[1] = th[0] * exp(x[0] + x[2] - x[1]) - th[1] - th[0] * exp(x[0] + x[2] - 2 * x[1]) / 2 -
+                     th[1] * exp(-x[1]) / 2;
+            res[2] = th[1] * exp(x[1] - x[2]) - th[2] - th[2] * exp(-x[2]) / 2 -
+                     th[1] * exp(x[1] - 2 * x[2]) / 2;
+        }
+    }
+}
+
+/* SIR_F :248-261, SEIR2_F :265-271, SEIR_F :276-296.  F is p x p column-major. */
+void orc_F(const orc_cfg *c, const double *x, const double *th, double *F) {
+    if (c->model == ORC_SIR) {
+        if (c->transX == ORC_STANDARD) {
+            F[0] = -th[0] * x[1];            F[2] = -th[0] * x[0];
+            F[1] = th[0] * x[1];             F[3] = th[0] * x[0] - th[1];
+        } else {
+            F[0] = th[0] * exp(x[1] - x[0]) / 2;
+            F[2] = -th[0] * exp(x[1]) - th[0] / 2 * exp(x[1] - x[0]);
+            F[1] = th[0] * exp(x[0]) - th[0] * exp(x[0] - x[1]) / 2;
+            F[3] = th[0] * exp(x[0] - x[1]) / 2 + th[1] / 2 * exp(-x[1]);
+        }
+    } else if (c->model == ORC_SEIR2) {
+        double N = 1000000; /* hard-coded in the reference (:267) */
+        F[0] = -th[1];  F[2] = th[0] * N;
+        F[1] = th[1];   F[3] = -th[2];
+    } else {
+        if (c->transX == ORC_STANDARD) {
+            F[0] = -th[0] * x[2];  F[3] = 0;       F[6] = -th[0] * x[0];
+            F[1] = th[0] * x[2];   F[4] = -th[1];  F[7] = th[0] * x[0];
+            F[2] = 0;              F[5] = th[1];   F[8] = -th[2];
+        } else {
+            F[0] = th[0] * exp(x[2] - x[0]) / 2;
+            F[3] = 0;
+            F[6] = -th[0] * exp(x[2]) - th[0] / 2 * exp(x[2] - x[0]);
+            F[1] = th[0] * exp(x[0] + x[2] - x[1]) - th[0] * exp(x[0] + x[2] - 2 * x[1]) / 2;
+            F[4] = -th[0] * exp(x[0] + x[2] - x[1]) + th[1] * exp(-x[1]) / 2 +
+                   th[0] * exp(x[0] + x[2] - 2 * x[1]);
+            F[7] = th[0] * exp(x[0] + x[2] - x[1]) - th[0] * exp(-x[0] + x[2] - 2 * x[1]);
+            F[2] = 0;
+            F[5] = th[1] * exp(x[1] - x[2]) - th[1] * exp(x[1] - 2 * x[2]) / 2;
+            F[8] = -th[1] * exp(x[1] - x[2]) + th[2] * exp(-x[2]) / 2 + th[1] * exp(x[1] - 2 * x[2]);
+        }
+    }
+}
+
+/* SIR_h :301-314, SEIR2_h :317-324, SEIR_h :328-344 (log branch keeps the states(1) quirk, A.16).
+ * Returns the number of reactions m. */
+int orc_h(const orc_cfg *c, const double *x, const double *th, double *h) {
+    if (c->model == ORC_SIR) {
+        if (c->transX == ORC_STANDARD) {
+            h[0] = th[0] * x[0] * x[1];
+            h[1] = th[1] * x[1];
+        } else {
+            h[0] = th[0] * exp(x[0]) * exp(x[1]);
+            h[1] = th[1] * exp(x[1]);
+        }
+        return 2;
+    }
+    if (c->model == ORC_SEIR2) {
+        double N = 1000000;
+        h[0] = th[0] * N * x[1];
+        h[1] = th[1] * x[0];
+        h[2] = th[2] * x[1];
+        return 3;
+    }
+    if (c->transX == ORC_STANDARD) {
+        h[0] = th[0] * x[0] * x[2];
+        h[1] = th[1] * x[1];
+        h[2] = th[2] * x[2];
+    } else {
+        h[0] = th[0] * exp(x[0]) * exp(x[1]);
+        h[1] = th[1] * exp(x[1]);
+        h[2] = th[2] * exp(x[2]);
+    }
+    return 3;
+}
+
+/* Stoichiometry A (m x p, rows = reactions), SigmaF :558-564.  Column-major m x p. */
+static int stoich(const orc_cfg *c, double *A) {
+    if (c->model == ORC_SIR) {
+        /* [-1 1; 0 -1] */
+        A[0] = -1; A[2] = 1;
+        A[1] = 0;  A[3] = -1;
+        return 2;
+    }
+    if (c->model == ORC_SEIR) {
+        /* [-1 1 0; 0 -1 1; 0 0 -1] */
+        A[0] = -1; A[3] = 1;  A[6] = 0;
+        A[1] = 0;  A[4] = -1; A[7] = 1;
+        A[2] = 0;  A[5] = 0;  A[8] = -1;
+        return 3;
+    }
+    /* SEIR2: 3 reactions x 2 states: [1 0; -1 1; 0 -1] */
+    A[0] = 1;  A[3] = 0;
+    A[1] = -1; A[4] = 1;
+    A[2] = 0;  A[5] = -1;
+    return 3;
+}
+
+/* ---------------------------------------------------------------- integrator */
+
+/* ODE_rk45: LNA_functional.cpp:455-491.  NOT a textbook RK4: all four stages at t[i-1] and k4 is
+ * evaluated at X0 + k3*dt/2.  `(k*dt)/2`, `(k1/6+k2/3+k3/3+k4/6)*dt` as written. */
+void orc_ode_rk45(const orc_cfg *c, const double *initial, const double *t, int n, const double *param,
+                  double *OdeTraj) {
+    int p = c->p;
+    double dt = t[1] - t[0];
+    double X0[MAXP], X1[MAXP], k1[MAXP], k2[MAXP], k3[MAXP], k4[MAXP], xs[MAXP];
+    for (int i = 0; i < n; i++) OdeTraj[i] = t[i];
+    for (int j = 0; j < p; j++) {
+        OdeTraj[(size_t)(j + 1) * n] = initial[j];
+        X1[j] = initial[j];
+    }
+    for (int i = 1; i < n; i++) {
+        for (int j = 0; j < p; j++) X0[j] = X1[j];
+        orc_ode_one(c, X0, param, t[i - 1], k1);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k1[j] * dt / 2;
+        orc_ode_one(c, xs, param, t[i - 1], k2);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k2[j] * dt / 2;
+        orc_ode_one(c, xs, param, t[i - 1], k3);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k3[j] * dt / 2;
+        orc_ode_one(c, xs, param, t[i - 1], k4);
+        for (int j = 0; j < p; j++) {
+            X1[j] = X0[j] + (k1[j] / 6 + k2[j] / 3 + k3[j] / 3 + k4[j] / 6) * dt;
+            OdeTraj[i + (size_t)(j + 1) * n] = X1[j];
+        }
+    }
+}
+
+/* ODE_rk45_stop: LNA_functional.cpp:495-530. */
+double orc_ode_rk45_stop(const orc_cfg *c, const double *initial, const double *t, int n,
+                         const double *param, double tol) {
+    int p = c->p;
+    double dt = t[1] - t[0];
+    double X0[MAXP], X1[MAXP], k1[MAXP], k2[MAXP], k3[MAXP], k4[MAXP], xs[MAXP];
+    for (int j = 0; j < p; j++) X1[j] = initial[j];
+    int i = 1;
+    for (; i < n; i++) {
+        for (int j = 0; j < p; j++) X0[j] = X1[j];
+        orc_ode_one(c, X0, param, t[i - 1], k1);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k1[j] * dt / 2;
+        orc_ode_one(c, xs, param, t[i - 1], k2);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k2[j] * dt / 2;
+        orc_ode_one(c, xs, param, t[i - 1], k3);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k3[j] * dt / 2;
+        orc_ode_one(c, xs, param, t[i - 1], k4);
+        for (int j = 0; j < p; j++) X1[j] = X0[j] + (k1[j] / 6 + k2[j] / 3 + k3[j] / 3 + k4[j] / 6) * dt;
+        if (X1[c->x_i[3]] < tol) return t[i];
+    }
+    return t[i - 1] + 0.1;
+}
+
+/* SigmaF: LNA_functional.cpp:536-599.  Traj_par = `nrow` rows of a (ld x (p+1)) col-major matrix.
+ * Explicit Euler at the rows' left endpoints; dt = row1.time - row0.time of THIS block (A.3). */
+void orc_sigmaF(const orc_cfg *c, const double *Traj_par, int nrow, int ld, const double *param,
+                double *expF, double *Sigma) {
+    int p = c->p;
+    double Q[MAXP * MAXP] = {0}, F0[MAXP * MAXP] = {0}, Sg[MAXP * MAXP] = {0};
+    double A[9], At[9], F[MAXP * MAXP], h[3], state[MAXP], th[3];
+    double T1[9], T2[9], M2[9], M3[9], M4[9], FF0[9];
+    for (int j = 0; j < p; j++) Q[j + j * p] = 1.0, F0[j + j * p] = 1.0;
+    int m = stoich(c, A); /* m x p */
+    double dt = Traj_par[1] - Traj_par[0];
+    for (int i = 0; i < nrow; i++) {
+        double t = Traj_par[i];
+        thetas3(c, t, param, th);
+        for (int j = 0; j < p; j++) {
+            state[j] = Traj_par[i + (size_t)(j + 1) * ld];
+            if (c->transX == ORC_LOG) Q[j + j * p] = exp(-state[j]);
+        }
+        orc_h(c, state, th, h);
+        orc_F(c, state, th, F);
+        /* F0 = F0 + (F*F0)*dt */
+        mat_mul(F, F0, p, FF0);
+        for (int e = 0; e < p * p; e++) F0[e] = F0[e] + FF0[e] * dt;
+        /* Sigma = Sigma + (Sigma*F' + F*Sigma + Q*A'*H*A*Q)*dt ; the 5-factor product left to right */
+        mat_mul_bt(Sg, F, p, T1);
+        mat_mul(F, Sg, p, T2);
+        /* M1 = Q*A' (p x m) */
+        for (int r = 0; r < p; r++)
+            for (int q = 0; q < m; q++) {
+                double s = 0.0;
+                for (int k = 0; k < p; k++) s += Q[r + k * p] * A[q + k * m];
+                At[r + q * p] = s;
+            }
+        /* M2 = M1*H (p x m), H = diag(h) */
+        for (int r = 0; r < p; r++)
+            for (int q = 0; q < m; q++) M2[r + q * p] = At[r + q * p] * h[q];
+        /* M3 = M2*A (p x p) */
+        for (int r = 0; r < p; r++)
+            for (int q = 0; q < p; q++) {
+                double s = M2[r] * A[q * m];
+                for (int k = 1; k < m; k++) s += M2[r + k * p] * A[k + q * m];
+                M3[r + q * p] = s;
+            }
+        mat_mul(M3, Q, p, M4);
+        for (int e = 0; e < p * p; e++) Sg[e] = Sg[e] + ((T1[e] + T2[e]) + M4[e]) * dt;
+    }
+    memcpy(expF, F0, sizeof(double) * (size_t)(p * p));
+    memcpy(Sigma, Sg, sizeof(double) * (size_t)(p * p));
+}
+
+/* KF_param: LNA_functional.cpp:603-634 (centred: Sigma itself). */
+void orc_kf_param(const orc_cfg *c, const double *OdeTraj, int nrow, const double *param, int gridsize,
+                  double *Acube, double *Scube) {
+    int p = c->p, k = (nrow - 1) / gridsize;
+    for (int i = 0; i < k; i++)
+        orc_sigmaF(c, OdeTraj + (size_t)i * gridsize, gridsize, nrow, param, Acube + (size_t)i * p * p,
+                   Scube + (size_t)i * p * p);
+}
+
+/* chol(S + jitter*I)^T (lower), as LAPACK dpotrf('U') would compute it on the upper triangle:
+ * LNA_functional.cpp:661.  Returns 0 on success, 1 when a pivot is <= 0 or NaN (dpotrf info>0). */
+int orc_chol_lower(const double *S, int p, double jitter, double *L) {
+    double U[MAXP * MAXP] = {0};
+    for (int j = 0; j < p; j++) {
+        double ajj = S[j + j * p] + jitter;
+        for (int k = 0; k < j; k++) ajj -= U[k + j * p] * U[k + j * p];
+        if (!(ajj > 0.0)) return 1;
+        ajj = sqrt(ajj);
+        U[j + j * p] = ajj;
+        for (int q = j + 1; q < p; q++) {
+            double s = S[j + q * p];
+            for (int k = 0; k < j; k++) s -= U[k + j * p] * U[k + q * p];
+            U[j + q * p] = s / ajj;
+        }
+    }
+    for (int r = 0; r < p; r++)
+        for (int q = 0; q < p; q++) L[r + q * p] = U[q + r * p];
+    return 0;
+}
+
+/* KF_param_chol: LNA_functional.cpp:638-670.  The "Sigma" slot holds L (A.4). */
+int orc_kf_param_chol(const orc_cfg *c, const double *OdeTraj, int nrow, const double *param,
+                      int gridsize, double *Acube, double *Lcube) {
+    int p = c->p, k = (nrow - 1) / gridsize;
+    double Sg[MAXP * MAXP];
+    for (int i = 0; i < k; i++) {
+        orc_sigmaF(c, OdeTraj + (size_t)i * gridsize, gridsize, nrow, param, Acube + (size_t)i * p * p, Sg);
+        if (orc_chol_lower(Sg, p, 0.00000001, Lcube + (size_t)i * p * p)) return ORC_CHOL_FAIL;
+    }
+    return ORC_OK;
+}
+
+/* Ode_Coarse_Slicer: LNA_functional.cpp:1179-1188. */
+void orc_ode_coarse_slicer(const double *Ode_thin, int nrow, int ncol, int gridsize, double *Ode_coarse) {
+    int d = nrow / gridsize + 1;
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < ncol; j++) Ode_coarse[i + (size_t)j * d] = Ode_thin[(size_t)i * gridsize + (size_t)j * nrow];
+}
+
+/* New_Param_List: LNA_functional.cpp:1191-1208. */
+int orc_new_param_list(const orc_cfg *c, const double *param, const double *initial, int gridsize,
+                       const double *t, int nt, double *Acube, double *Lcube, double *Ode_coarse,
+                       double *betaN) {
+    int p = c->p;
+    double *thin = (double *)malloc(sizeof(double) * (size_t)nt * (size_t)(p + 1));
+    orc_ode_rk45(c, initial, t, nt, param, thin);
+    int st = orc_kf_param_chol(c, thin, nt, param, gridsize, Acube, Lcube);
+    if (st == ORC_OK) {
+        orc_ode_coarse_slicer(thin, nt, p + 1, gridsize, Ode_coarse);
+        orc_betaTs(param, Ode_coarse, nt / gridsize + 1, c->x_r, c->x_i, betaN);
+    }
+    free(thin);
+    return st;
+}
+
+/* ---------------------------------------------------------------- non-centred trajectory */
+
+/* TransformTraj: LNA_functional.cpp:877-900.  X1 = A_i X0 + L_i eps_i ; traj = ODE + X. */
+void orc_transform_traj(const double *OdeTraj, int nrow, int p, const double *OriginLatent, int k,
+                        const double *Acube, const double *Lcube, double *LNA_traj) {
+    double X0[MAXP] = {0}, X1[MAXP];
+    memcpy(LNA_traj, OdeTraj, sizeof(double) * (size_t)nrow * (size_t)(p + 1));
+    for (int i = 0; i < k; i++) {
+        const double *A = Acube + (size_t)i * p * p, *L = Lcube + (size_t)i * p * p;
+        for (int r = 0; r < p; r++) {
+            double ax = A[r] * X0[0], le = L[r] * OriginLatent[i];
+            for (int q = 1; q < p; q++) {
+                ax += A[r + q * p] * X0[q];
+                le += L[r + q * p] * OriginLatent[i + (size_t)q * k];
+            }
+            X1[r] = ax + le;
+        }
+        for (int r = 0; r < p; r++) {
+            LNA_traj[(i + 1) + (size_t)(r + 1) * nrow] = X1[r] + LNA_traj[(i + 1) + (size_t)(r + 1) * nrow];
+            X0[r] = X1[r];
+        }
+    }
+}
+
+static double det_small(const double *M, int p) {
+    if (p == 2) return M[0] * M[3] - M[2] * M[1];
+    return M[0] * (M[4] * M[8] - M[7] * M[5]) - M[3] * (M[1] * M[8] - M[7] * M[2]) +
+           M[6] * (M[1] * M[5] - M[4] * M[2]);
+}
+
+/* Traj_sim_general_noncentral: LNA_functional.cpp:824-872, eps supplied (k*p normals, step-major:
+ * step i consumes normals[i*p .. i*p+p-1]).  OriginLatent is k x p column-major. */
+void orc_traj_sim_noncentral(const double *OdeTraj, int nrow, int p, const double *Acube,
+                             const double *Lcube, double t_correct, const double *normals,
+                             double *LNA_traj, double *OriginLatent, double *logMultiNorm,
+                             double *logOrigin) {
+    int k = nrow - 1;
+    double X0[MAXP] = {0}, X1[MAXP], loglike = 0.0, logTraj = 0.0;
+    memcpy(LNA_traj, OdeTraj, sizeof(double) * (size_t)nrow * (size_t)(p + 1));
+    for (int i = 0; i < k; i++) {
+        const double *eps = normals + (size_t)i * p;
+        const double *A = Acube + (size_t)i * p * p, *L = Lcube + (size_t)i * p * p;
+        for (int q = 0; q < p; q++) OriginLatent[i + (size_t)q * k] = eps[q];
+        for (int r = 0; r < p; r++) {
+            double ax = A[r] * X0[0], le = L[r] * eps[0];
+            for (int q = 1; q < p; q++) {
+                ax += A[r + q * p] * X0[q];
+                le += L[r + q * p] * eps[q];
+            }
+            X1[r] = ax + le;
+        }
+        for (int r = 0; r < p; r++) {
+            LNA_traj[(i + 1) + (size_t)(r + 1) * nrow] = X1[r] + LNA_traj[(i + 1) + (size_t)(r + 1) * nrow];
+            X0[r] = X1[r];
+        }
+        if (OdeTraj[i + 1] <= t_correct) {
+            double ee = eps[0] * eps[0];
+            for (int q = 1; q < p; q++) ee += eps[q] * eps[q];
+            loglike += -log(det_small(L, p));
+            logTraj += (-0.5) * ee;
+        }
+    }
+    *logMultiNorm = loglike;
+    *logOrigin = logTraj;
+}
+
+/* log_like_traj_general2: LNA_functional.cpp:675-722 (centred Gaussian transition density; used by
+ * the reference's "Test SIR model" identity).  solve(S, v) by explicit small inverse. */
+double orc_log_like_traj_general2(const double *SdeTraj, const double *OdeTraj, int nrow, int p,
+                                  const double *Acube, const double *Scube, double t_correct) {
+    int k = nrow - 1;
+    double loglik = 0.0, Xd0[MAXP], Xd1[MAXP], v[MAXP], w[MAXP];
+    for (int j = 0; j < p; j++) Xd1[j] = SdeTraj[(size_t)(j + 1) * nrow] - OdeTraj[(size_t)(j + 1) * nrow];
+    for (int i = 0; i < k; i++) {
+        const double *A = Acube + (size_t)i * p * p, *S = Scube + (size_t)i * p * p;
+        for (int j = 0; j < p; j++) Xd0[j] = Xd1[j];
+        for (int j = 0; j < p; j++)
+            Xd1[j] = SdeTraj[(i + 1) + (size_t)(j + 1) * nrow] - OdeTraj[(i + 1) + (size_t)(j + 1) * nrow];
+        if (SdeTraj[i + 1] <= t_correct) {
+            for (int r = 0; r < p; r++) {
+                double ax = 0.0;
+                for (int q = 0; q < p; q++) ax += A[r + q * p] * Xd0[q];
+                v[r] = Xd1[r] - ax;
+            }
+            double d = det_small(S, p);
+            if (p == 2) {
+                w[0] = (S[3] * v[0] - S[2] * v[1]) / d;
+                w[1] = (-S[1] * v[0] + S[0] * v[1]) / d;
+            } else {
+                /* Cramer via cofactors */
+                double C[9];
+                C[0] = S[4] * S[8] - S[7] * S[5]; C[3] = -(S[3] * S[8] - S[6] * S[5]); C[6] = S[3] * S[7] - S[6] * S[4];
+                C[1] = -(S[1] * S[8] - S[7] * S[2]); C[4] = S[0] * S[8] - S[6] * S[2]; C[7] = -(S[0] * S[7] - S[6] * S[1]);
+                C[2] = S[1] * S[5] - S[4] * S[2]; C[5] = -(S[0] * S[5] - S[3] * S[2]); C[8] = S[0] * S[4] - S[3] * S[1];
+                for (int r = 0; r < 3; r++) w[r] = (C[r] * v[0] + C[r + 3] * v[1] + C[r + 6] * v[2]) / d;
+            }
+            double q = 0.0;
+            for (int r = 0; r < p; r++) q += v[r] * w[r];
+            loglik += -log(d) / 2.0 - 0.5 * q;
+        }
+    }
+    return loglik;
+}
+
+/* ---------------------------------------------------------------- coalescent likelihoods */
+
+static double volz_core(const orc_init *init, const double *f1, int nrow, int p, const double *betaN,
+                        double t_correct, const int *index, int transX, int nan_guard) {
+    /* volz_loglik_nh2: LNA_functional.cpp:1119-1176 (nh3 :1058-1113 = same without the NaN guard) */
+    int n2 = nrow, n0 = init->ng - 1, L = 0;
+    while (f1[L] < t_correct) {
+        L++;
+        if (L == n2 - 1) break;
+    }
+    for (int j = 1; j <= p; j++)
+        for (int r = 0; r <= n0; r++)
+            if (f1[r + (size_t)j * nrow] < 0) return ORC_SENTINEL;
+    int E = init->E;
+    double *ll = (double *)malloc(sizeof(double) * (size_t)(E > 0 ? E : 1));
+    int start = 0, has_nan = 0;
+    for (int i = 0; i < n0; i++) {
+        int row = L - i; /* f2(n0-i-1,.) = f1(L-i,.)  (A.9) */
+        int reps = (int)init->gridrep[i];
+        for (int j = 0; j < reps; j++) {
+            double f, s, b = betaN[row];
+            if (transX == ORC_STANDARD) {
+                f = log(f1[row + (size_t)(index[1] + 1) * nrow]);
+                s = log(f1[row + (size_t)(index[0] + 1) * nrow]);
+            } else {
+                f = f1[row + (size_t)(index[1] + 1) * nrow];
+                s = f1[row + (size_t)(index[0] + 1) * nrow];
+            }
+            double v = -2 * (init->C[start] * init->D[start] * b * exp(-f) * exp(s)) +
+                       init->y[start] * (log(b) - f + s);
+            if (v != v) has_nan = 1;
+            ll[start++] = v;
+        }
+    }
+    double res;
+    if (nan_guard && has_nan) res = ORC_SENTINEL;
+    else res = accu2(ll, start);
+    free(ll);
+    return res;
+}
+
+double orc_volz_loglik_nh2(const orc_init *init, const double *f1, int nrow, int p, const double *betaN,
+                           double t_correct, const int *index, int transX) {
+    return volz_core(init, f1, nrow, p, betaN, t_correct, index, transX, 1);
+}
+double orc_volz_loglik_nh3(const orc_init *init, const double *f1, int nrow, int p, const double *betaN,
+                           double t_correct, const int *index, int transX) {
+    return volz_core(init, f1, nrow, p, betaN, t_correct, index, transX, 0);
+}
+
+static double kingman_core(const orc_init *init, const double *f1, int nrow, int col, double t_correct,
+                           double lambda, int take_log) {
+    int n0 = 0;
+    while (f1[n0] < t_correct) n0++;
+    int E = init->E, start = 0;
+    double *ll = (double *)malloc(sizeof(double) * (size_t)(E > 0 ? E : 1));
+    /* f2(n0-i) = [log] f1(i,col), i = n0..1 ; cell c = n0-i uses row n0-c */
+    for (int c = 0; c < n0 && c < init->ng; c++) {
+        int row = n0 - c, reps = (int)init->gridrep[c];
+        double f = f1[row + (size_t)col * nrow];
+        if (take_log) f = log(f);
+        for (int j = 0; j < reps; j++) {
+            ll[start] = -lambda * (init->C[start] * init->D[start] * exp(-f)) + init->y[start] * (log(lambda) - f);
+            start++;
+        }
+    }
+    (void)nrow;
+    double res = accu2(ll, start);
+    free(ll);
+    return res;
+}
+
+/* coal_loglik3: LNA_functional.cpp:1016-1054 (Kingman with scale lambda; Index = 0-based state col). */
+double orc_coal_loglik3(const orc_init *init, const double *f1, int nrow, int p, double t_correct,
+                        double lambda, int Index, int transX) {
+    (void)p;
+    return kingman_core(init, f1, nrow, Index + 1, t_correct, lambda, transX == ORC_STANDARD);
+}
+
+/* coal_loglik: SIR_phylodyn.cpp:436-468 (column 2 of f1 already holds log I). */
+double orc_coal_loglik(const orc_init *init, const double *f1, int nrow, int p, double t_correct,
+                       double lambda) {
+    (void)p;
+    return kingman_core(init, f1, nrow, 2, t_correct, lambda, 0);
+}
+
+/* ---------------------------------------------------------------- FULL evaluation + MH step */
+
+int orc_full_loglik(const orc_cfg *c, const orc_init *init, const double *param, const double *initial,
+                    const double *t, int nt, int gridsize, const double *OriginTraj, double t_correct,
+                    double *Acube, double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj,
+                    double *coalLog) {
+    int p = c->p, nrow = nt / gridsize + 1, k = (nt - 1) / gridsize;
+    int st = orc_new_param_list(c, param, initial, gridsize, t, nt, Acube, Lcube, Ode_coarse, betaN);
+    if (st != ORC_OK) {
+        *coalLog = ORC_SENTINEL;
+        return st;
+    }
+    orc_transform_traj(Ode_coarse, nrow, p, OriginTraj, k, Acube, Lcube, LatentTraj);
+    *coalLog = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, &c->x_i[2], c->transX);
+    return ORC_OK;
+}
+
+/* Update_Param: LNA_functional.cpp:1212-1243.  One uniform; accept iff log(u) < a. */
+int orc_update_param(const orc_cfg *c, const orc_init *init, const double *param, const double *initial,
+                     const double *t, int nt, const double *OriginTraj, int gridsize, double coal_log,
+                     double prior_proposal_offset, double t_correct, double unif, int *accept,
+                     double *Acube, double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj,
+                     double *coalLog_new) {
+    int st = orc_full_loglik(c, init, param, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
+                             Ode_coarse, betaN, LatentTraj, coalLog_new);
+    if (st != ORC_OK) { /* the reference throws here (-> R tryCatch keeps the old state) */
+        *accept = 0;
+        return st;
+    }
+    double a = *coalLog_new - coal_log + prior_proposal_offset;
+    *accept = (log(unif) < a) ? 1 : 0;
+    return ORC_OK;
+}
+
+/* ---------------------------------------------------------------- ESS rotations */
+
+/* Param_Slice_update: LNA_functional.cpp:1246-1253. */
+void orc_param_slice_update(const double *param, int nparam_total, const int *x_i, double theta,
+                            const double *newChs, double *param_new) {
+    memcpy(param_new, param, sizeof(double) * (size_t)nparam_total);
+    for (int j = 0; j < x_i[0]; j++) {
+        double od = log(param[x_i[1] + j]);
+        param_new[x_i[1] + j] = exp(od * cos(theta) + newChs[j] * sin(theta));
+    }
+}
+
+/* Param_Slice_update_all2: LNA_functional.cpp:1268-1314 (hard-wired p=2). */
+void orc_param_slice_update_all2(const double *par_old, int npar, const int *x_i, double theta,
+                                 const double *newChs, const int *ESS_vec, const double *pr,
+                                 double *par_new) {
+    int nz = x_i[1] + x_i[0] + 2; /* length of par_old.subvec(1, x_i1+x_i0+2) */
+    int ih = x_i[0] + x_i[1] + 1; /* hyper inside OdeChs */
+    double *z = (double *)malloc(sizeof(double) * (size_t)nz);
+    double *zp = (double *)malloc(sizeof(double) * (size_t)nz);
+    memcpy(par_new, par_old, sizeof(double) * (size_t)npar);
+    for (int i = 0; i < nz; i++) z[i] = log(par_old[1 + i]);
+    for (int i = 0; i < 3; i++) z[i] = (z[i] - pr[2 * i]) / pr[2 * i + 1];
+    z[ih] = (z[ih] - pr[6]) / pr[7];
+    for (int i = 3; i <= 2 + x_i[0]; i++) z[i] = z[i] * par_new[x_i[0] + x_i[1] + 2];
+    double ct = cos(theta), sn = sin(theta);
+    for (int i = 0; i < nz; i++) zp[i] = z[i] * ct + newChs[i] * sn;
+    for (int i = 0; i < 3; i++)
+        if (ESS_vec[i] != 0) par_new[1 + i] = exp(zp[i] * pr[2 * i + 1] + pr[2 * i]);
+    if (ESS_vec[4] != 0) par_new[x_i[0] + x_i[1] + 2] = exp(zp[ih] * pr[7] + pr[6]);
+    if (ESS_vec[5] != 0)
+        for (int i = 3; i <= x_i[0] + x_i[1]; i++) par_new[1 + i] = exp(zp[i] / par_new[x_i[0] + x_i[1] + 2]);
+    free(z);
+    free(zp);
+}
+
+/* R::runif(a,b) = a + (b-a)*unif_rand()  (R nmath/runif.c) */
+static double runif_ab(double a, double b, double u) { return a + (b - a) * u; }
+
+/* ESlice_par_General: LNA_functional.cpp:1532-1688.
+ * normals: npar-1 (then k*p more, discarded, iff ESS_vec[6]==1); uniforms: u, theta_1, one per shrink. */
+int orc_eslice_par_general(const orc_cfg *c, const orc_init *init, const double *par_old, int npar,
+                           const double *t, int nt, const double *OriginTraj, const double *pr8,
+                           int gridsize, const int *ESS_vec, double coal_log, double t_correct,
+                           const double *normals, const double *uniforms, int *n_norm, int *n_unif,
+                           int *n_evals, double *par_new, double *Acube, double *Lcube,
+                           double *Ode_coarse, double *betaN, double *LatentTraj,
+                           double *OriginTraj_new, double *CoalLog, double *logOrigin) {
+    int p = 2, k = (nt - 1) / gridsize, nrow = nt / gridsize + 1;
+    int u_param = npar - 1, in = 0, iu = 0, evals = 0, status = 0;
+    const double *new_par_raw = normals;
+    in += u_param;
+    if (ESS_vec[6] == 1) in += k * p; /* drawn into a block-scoped variable and discarded (:1576-1578) */
+    memcpy(OriginTraj_new, OriginTraj, sizeof(double) * (size_t)k * p);
+    double u = uniforms[iu++];
+    double logy = coal_log + log(u);
+    double theta = 2 * ORC_PI, theta_min = 0, theta_max = 2 * ORC_PI, loglike = 0.0;
+    memcpy(par_new, par_old, sizeof(double) * (size_t)npar);
+    int i = 0;
+    do {
+        i += 1;
+        if (i > 20) {
+            theta = 0;
+            memcpy(par_new, par_old, sizeof(double) * (size_t)npar);
+            memcpy(OriginTraj_new, OriginTraj, sizeof(double) * (size_t)k * p);
+            int st = orc_full_loglik(c, init, par_new + 2, par_new, t, nt, gridsize, OriginTraj_new, t_correct,
+                                     Acube, Lcube, Ode_coarse, betaN, LatentTraj, &loglike);
+            evals++;
+            status |= ORC_CAP_HIT | st; /* a chol failure here propagates as an exception in the reference */
+            break;
+        }
+        if (i == 1) {
+            theta = runif_ab(0, 2 * ORC_PI, uniforms[iu++]);
+            theta_min = theta - 2 * ORC_PI;
+            theta_max = theta;
+        } else {
+            if (theta < 0) theta_min = theta;
+            else theta_max = theta;
+            theta = runif_ab(theta_min, theta_max, uniforms[iu++]);
+        }
+        orc_param_slice_update_all2(par_old, npar, c->x_i, theta, new_par_raw, ESS_vec, pr8, par_new);
+        evals++;
+        int st = orc_new_param_list(c, par_new + 2, par_new, gridsize, t, nt, Acube, Lcube, Ode_coarse, betaN);
+        if (st != ORC_OK) { /* try/catch(...) -> loglike = -1e7 ; continue (:1641-1651) */
+            loglike = ORC_SENTINEL;
+            continue;
+        }
+        if (ESS_vec[6] == 1) { /* mixes OriginTraj with (the running) itself, :1660-1662 */
+            double ct = cos(theta), sn = sin(theta);
+            for (int e = 0; e < k * p; e++) OriginTraj_new[e] = OriginTraj[e] * ct + OriginTraj_new[e] * sn;
+        }
+        orc_transform_traj(Ode_coarse, nrow, p, OriginTraj_new, k, Acube, Lcube, LatentTraj);
+        loglike = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, &c->x_i[2], c->transX);
+    } while (loglike <= logy);
+    double lo = 0.0;
+    for (int j = 0; j < k; j++)
+        for (int q = 0; q < p; q++) lo -= 0.5 * OriginTraj_new[j + (size_t)q * k] * OriginTraj_new[j + (size_t)q * k];
+    *logOrigin = lo;
+    *CoalLog = loglike;
+    *n_norm = in;
+    *n_unif = iu;
+    *n_evals = evals;
+    return status;
+}
+
+/* ESlice_general_NC: LNA_functional.cpp:1690-1778.
+ * normals: k*p (column-major k x p); uniforms: u, theta_1, one per shrink (<= 20). */
+int orc_eslice_general_nc(const orc_init *init, const double *f_cur, int k, int p, const double *OdeTraj,
+                          const double *Acube, const double *Lcube, const double *betaN, double t_correct,
+                          double lambda, double coal_log, int volz, const int *Index, int transX,
+                          const double *normals, const double *uniforms, int *n_norm, int *n_unif,
+                          int *n_evals, double *LatentTraj, double *OriginTraj_new, double *logOrigin,
+                          double *CoalLog) {
+    int nrow = k + 1, iu = 0, evals = 0, status = 0;
+    const double *v_traj = normals;
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)nrow * (p + 1));
+    double u = uniforms[iu++], logy;
+    (void)lambda;
+    if (!volz) { /* Kingman branch needs LogTraj(), which the reference never defines in C++ */
+        free(tmp);
+        return -1;
+    }
+    if (coal_log != -99999999) {
+        logy = coal_log + log(u);
+    } else {
+        orc_transform_traj(OdeTraj, nrow, p, f_cur, k, Acube, Lcube, tmp);
+        logy = orc_volz_loglik_nh2(init, tmp, nrow, p, betaN, t_correct, Index, transX) + log(u);
+        evals++;
+    }
+    double theta = runif_ab(0, 2 * ORC_PI, uniforms[iu++]);
+    double theta_min = theta - 2 * ORC_PI, theta_max = theta;
+    double *f_prime = OriginTraj_new;
+    double ct = cos(theta), sn = sin(theta);
+    for (int e = 0; e < k * p; e++) f_prime[e] = f_cur[e] * ct + v_traj[e] * sn;
+    orc_transform_traj(OdeTraj, nrow, p, f_prime, k, Acube, Lcube, LatentTraj);
+    double loglike = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, Index, transX);
+    evals++;
+    int i = 0;
+    for (;;) {
+        double mn = LatentTraj[nrow];
+        for (int e = nrow; e < nrow * (p + 1); e++)
+            if (LatentTraj[e] < mn) mn = LatentTraj[e];
+        if (!(mn < 0 || loglike <= logy)) break;
+        i += 1;
+        if (i > 20) {
+            orc_transform_traj(OdeTraj, nrow, p, f_cur, k, Acube, Lcube, LatentTraj);
+            loglike = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, Index, transX);
+            evals++;
+            memcpy(f_prime, f_cur, sizeof(double) * (size_t)k * p);
+            status |= ORC_CAP_HIT;
+            break;
+        }
+        if (theta < 0) theta_min = theta;
+        else theta_max = theta;
+        theta = runif_ab(theta_min, theta_max, uniforms[iu++]);
+        ct = cos(theta);
+        sn = sin(theta);
+        for (int e = 0; e < k * p; e++) f_prime[e] = f_cur[e] * ct + v_traj[e] * sn;
+        orc_transform_traj(OdeTraj, nrow, p, f_prime, k, Acube, Lcube, LatentTraj);
+        loglike = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, Index, transX);
+        evals++;
+    }
+    double lo = 0.0;
+    for (int j = 0; j < k - 1; j++) /* omits the LAST row (:1768) */
+        for (int q = 0; q < p; q++) lo -= 0.5 * f_prime[j + (size_t)q * k] * f_prime[j + (size_t)q * k];
+    *logOrigin = lo;
+    *CoalLog = loglike;
+    *n_norm = k * p;
+    *n_unif = iu;
+    *n_evals = evals;
+    free(tmp);
+    return status;
+}
+
+/* ESlice_change_points: LNA_functional.cpp:1317-1409.
+ * uniforms: u, theta_1 FIRST; then normals: nch (divided by hyper); then one uniform per shrink. */
+int orc_eslice_change_points(const orc_cfg *c, const orc_init *init, const double *param,
+                             const double *initial, const double *t, int nt, const double *OriginTraj,
+                             int gridsize, double coal_log, double t_correct, const double *normals,
+                             const double *uniforms, int *n_norm, int *n_unif, int *n_evals,
+                             double *param_new, double *Acube, double *Lcube, double *Ode_coarse,
+                             double *betaN, double *LatentTraj, double *CoalLog, double *LogChProb) {
+    int nch = c->x_i[0], npt = c->nparam_total, iu = 0, evals = 0, status = 0;
+    double u = uniforms[iu++];
+    double logy = coal_log + log(u);
+    double theta = runif_ab(0, 2 * ORC_PI, uniforms[iu++]);
+    double theta_min = theta - 2 * ORC_PI, theta_max = theta;
+    double *newChs = (double *)malloc(sizeof(double) * (size_t)(nch > 0 ? nch : 1));
+    for (int j = 0; j < nch; j++) newChs[j] = normals[j] / param[c->x_i[0] + c->x_i[1]];
+    orc_param_slice_update(param, npt, c->x_i, theta, newChs, param_new);
+    double loglike;
+    int st = orc_full_loglik(c, init, param_new, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
+                             Ode_coarse, betaN, LatentTraj, &loglike);
+    evals++;
+    status |= st; /* uncaught exception in the reference */
+    int i = 0;
+    while (st == ORC_OK && loglike <= logy) {
+        i += 1;
+        if (i > 20) {
+            theta = 0;
+            memcpy(param_new, param, sizeof(double) * (size_t)npt);
+            st = orc_full_loglik(c, init, param, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
+                                 Ode_coarse, betaN, LatentTraj, &loglike);
+            evals++;
+            status |= ORC_CAP_HIT | st;
+            break;
+        }
+        if (theta < 0) theta_min = theta;
+        else theta_max = theta;
+        theta = runif_ab(theta_min, theta_max, uniforms[iu++]);
+        orc_param_slice_update(param, npt, c->x_i, theta, newChs, param_new);
+        st = orc_full_loglik(c, init, param_new, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
+                             Ode_coarse, betaN, LatentTraj, &loglike);
+        evals++;
+        status |= st;
+    }
+    double lcp = 0.0;
+    for (int j = 0; j < nch; j++) {
+        double d = log(param_new[c->x_i[1] + j]) * param_new[c->x_i[0] + c->x_i[1]];
+        lcp += -0.5 * d * d;
+    }
+    *LogChProb = lcp;
+    *CoalLog = loglike;
+    *n_norm = nch;
+    *n_unif = iu;
+    *n_evals = evals;
+    free(newChs);
+    return status;
+}
+
+/* ---------------------------------------------------------------- basic_util.cpp */
+
+/* inv2: basic_util.cpp:5-14 */
+void orc_inv2(const double *a, double *res) {
+    double r00 = a[3], r11 = a[0], r10 = -a[1], r01 = -a[2];
+    double D = r00 * r11 - r10 * r01;
+    res[0] = r00 * (1 / D);
+    res[1] = r10 * (1 / D);
+    res[2] = r01 * (1 / D);
+    res[3] = r11 * (1 / D);
+}
+
+/* chols: basic_util.cpp:17-25 (hand 2x2 Cholesky, returns lower) */
+void orc_chols(const double *S, double *L) {
+    double r00 = sqrt(S[0]);
+    double r01 = S[1] / r00;
+    double r11 = sqrt(S[3] - r01 * r01);
+    L[0] = r00;
+    L[1] = r01;
+    L[2] = 0;
+    L[3] = r11;
+}

@@ -1,0 +1,382 @@
+"""ctypes binding of the CPU oracle (oracle/liblna_oracle.so).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/lna_oracle.h.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / `--impl reference` legs may import this module.  The function names
+mirror the reference's Rcpp exports (R/RcppExports.R) so that tests read like the reference's.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblna_oracle.so")
+
+MODELS = {"SIR": 0, "SEIR": 1, "SEIR2": 2}
+MODEL_P = {"SIR": 2, "SEIR": 3, "SEIR2": 2}
+TRANSX = {"standard": 0, "log": 1}
+SENTINEL = -10000000.0
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("model", C.c_int), ("transX", C.c_int), ("p", C.c_int), ("nparam_total", C.c_int),
+                ("x_r", _dp), ("x_i", C.c_int * 4)]
+
+
+class _Init(C.Structure):
+    _fields_ = [("E", C.c_int), ("ng", C.c_int), ("C", _dp), ("D", _dp), ("y", _dp), ("gridrep", _dp)]
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("lna_oracle.c", "lna_oracle.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "liblna_oracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        for name in ("orc_volz_loglik_nh2", "orc_volz_loglik_nh3", "orc_coal_loglik3", "orc_coal_loglik",
+                     "orc_log_like_traj_general2", "orc_ode_rk45_stop"):
+            getattr(_lib, name).restype = C.c_double
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _f(a):
+    """column-major double copy"""
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _ints(a):
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64).round().astype(np.int32))
+    return arr, arr.ctypes.data_as(_ip)
+
+
+class Cfg:
+    """(model, transX, x_r, x_i) pack; keeps the numpy buffers alive."""
+
+    def __init__(self, x_r, x_i, nparam_total, model="SIR", transX="standard"):
+        self.x_r = _d(x_r)
+        self.x_i = [int(round(float(v))) for v in np.asarray(x_i).ravel()]
+        self.model, self.transX = model, transX
+        self.p = MODEL_P[model]
+        self.nparam_total = int(nparam_total)
+        self.c = _Cfg(MODELS[model], TRANSX[transX], self.p, self.nparam_total, _p(self.x_r),
+                      (C.c_int * 4)(*self.x_i))
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+
+class Init:
+    """Positional view of coal_lik_init()'s list: needs C, D, y, gridrep, ng."""
+
+    def __init__(self, init):
+        g = (lambda k: init[k]) if not hasattr(init, "files") else (lambda k: init[k])
+        self.C, self.D, self.y = _d(g("C")), _d(g("D")), _d(g("y"))
+        self.gridrep = _d(g("gridrep"))
+        self.ng = int(np.asarray(g("ng")).ravel()[0])
+        self.E = len(self.C)
+        self.c = _Init(self.E, self.ng, _p(self.C), _p(self.D), _p(self.y), _p(self.gridrep))
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+
+# ----------------------------------------------------------------------------- Rcpp-named wrappers
+
+def betaTs(param, times, x_r, x_i):
+    param, times, x_r = _d(param), _d(times), _d(x_r)
+    xi, xip = _ints(x_i)
+    out = np.empty(len(times))
+    lib().orc_betaTs(_p(param), _p(times), len(times), _p(x_r), xip, _p(out))
+    return out
+
+
+def param_transform(t, param, x_r, x_i):
+    param, x_r = _d(param), _d(x_r)
+    xi, xip = _ints(x_i)
+    out = np.empty(len(param))
+    lib().orc_param_transform(C.c_double(t), _p(param), len(param), _p(x_r), xip, _p(out))
+    return out
+
+
+def ODE_rk45(initial, t, param, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    initial, t, param = _d(initial), _d(t), _d(param)
+    out = np.empty((len(t), cfg.p + 1), order="F")
+    lib().orc_ode_rk45(cfg.ref, _p(initial), _p(t), len(t), _p(param), _p(out))
+    return out
+
+
+def SigmaF(Traj_par, param, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    T, param = _f(Traj_par), _d(param)
+    p = cfg.p
+    eF, S = np.empty((p, p), order="F"), np.empty((p, p), order="F")
+    lib().orc_sigmaF(cfg.ref, _p(T), T.shape[0], T.shape[0], _p(param), _p(eF), _p(S))
+    return {"expF": eF, "Sigma": S}
+
+
+def _cubes(p, k):
+    return np.empty((p, p, k), order="F"), np.empty((p, p, k), order="F")
+
+
+def KF_param(OdeTraj, param, gridsize, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    O, param = _f(OdeTraj), _d(param)
+    k = (O.shape[0] - 1) // gridsize
+    A, S = _cubes(cfg.p, k)
+    lib().orc_kf_param(cfg.ref, _p(O), O.shape[0], _p(param), int(gridsize), _p(A), _p(S))
+    return {"A": A, "Sigma": S}
+
+
+def KF_param_chol(OdeTraj, param, gridsize, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    O, param = _f(OdeTraj), _d(param)
+    k = (O.shape[0] - 1) // gridsize
+    A, L = _cubes(cfg.p, k)
+    st = lib().orc_kf_param_chol(cfg.ref, _p(O), O.shape[0], _p(param), int(gridsize), _p(A), _p(L))
+    if st:
+        raise ValueError("Invalid input for cholesky decomposition., parametrization fails")
+    return {"A": A, "Sigma": L}
+
+
+def Ode_Coarse_Slicer(Ode_thin, gridsize):
+    O = _f(Ode_thin)
+    d = O.shape[0] // gridsize + 1
+    out = np.empty((d, O.shape[1]), order="F")
+    lib().orc_ode_coarse_slicer(_p(O), O.shape[0], O.shape[1], int(gridsize), _p(out))
+    return out
+
+
+def New_Param_List(param, initial, gridsize, t, x_r, x_i, transP="changepoint", model="SIR",
+                   transX="standard"):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    param, initial, t = _d(param), _d(initial), _d(t)
+    nt, p = len(t), cfg.p
+    k, nrow = (nt - 1) // gridsize, nt // gridsize + 1
+    A, L = _cubes(p, k)
+    ode, betaN = np.empty((nrow, p + 1), order="F"), np.empty(nrow)
+    st = lib().orc_new_param_list(cfg.ref, _p(param), _p(initial), int(gridsize), _p(t), nt, _p(A), _p(L),
+                                  _p(ode), _p(betaN))
+    if st:
+        raise ValueError("Invalid input for cholesky decomposition., parametrization fails")
+    return {"FT": {"A": A, "Sigma": L}, "Ode": ode, "betaN": betaN}
+
+
+def TransformTraj(OdeTraj, OriginLatent, Filter_NC):
+    O, eps = _f(OdeTraj), _f(OriginLatent)
+    A, L = _f(Filter_NC["A"]), _f(Filter_NC["Sigma"])
+    out = np.empty_like(O, order="F")
+    lib().orc_transform_traj(_p(O), O.shape[0], O.shape[1] - 1, _p(eps), eps.shape[0], _p(A), _p(L), _p(out))
+    return out
+
+
+def Traj_sim_general_noncentral(OdeTraj, Filter_NC, t_correct, normals):
+    """`normals`: k*p pre-drawn N(0,1), step-major (step i uses normals[i*p:(i+1)*p])."""
+    O = _f(OdeTraj)
+    A, L = _f(Filter_NC["A"]), _f(Filter_NC["Sigma"])
+    nrow, p = O.shape[0], O.shape[1] - 1
+    nrm = _d(normals)
+    traj, origin = np.empty_like(O, order="F"), np.empty((nrow - 1, p), order="F")
+    lm, lo = C.c_double(), C.c_double()
+    lib().orc_traj_sim_noncentral(_p(O), nrow, p, _p(A), _p(L), C.c_double(t_correct), _p(nrm), _p(traj),
+                                  _p(origin), C.byref(lm), C.byref(lo))
+    return {"SimuTraj": traj, "OriginTraj": origin, "logMultiNorm": lm.value, "logOrigin": lo.value}
+
+
+def log_like_traj_general2(SdeTraj, OdeTraj, Filter, gridsize, t_correct):
+    S, O = _f(SdeTraj), _f(OdeTraj)
+    A, Sg = _f(Filter["A"]), _f(Filter["Sigma"])
+    return lib().orc_log_like_traj_general2(_p(S), _p(O), S.shape[0], S.shape[1] - 1, _p(A), _p(Sg),
+                                            C.c_double(t_correct))
+
+
+def volz_loglik_nh2(init, f1, betaN, t_correct, index, transX="standard", _fn="orc_volz_loglik_nh2"):
+    ini = init if isinstance(init, Init) else Init(init)
+    F, b = _f(f1), _d(betaN)
+    ix, ixp = _ints(index)
+    return getattr(lib(), _fn)(ini.ref, _p(F), F.shape[0], F.shape[1] - 1, _p(b), C.c_double(t_correct), ixp,
+                               TRANSX[transX])
+
+
+def volz_loglik_nh3(init, f1, betaN, t_correct, index, transX="standard"):
+    return volz_loglik_nh2(init, f1, betaN, t_correct, index, transX, _fn="orc_volz_loglik_nh3")
+
+
+def coal_loglik3(init, f1, t_correct, lam, Index, transX="standard"):
+    ini = init if isinstance(init, Init) else Init(init)
+    F = _f(f1)
+    return lib().orc_coal_loglik3(ini.ref, _p(F), F.shape[0], F.shape[1] - 1, C.c_double(t_correct),
+                                  C.c_double(lam), int(Index), TRANSX[transX])
+
+
+def coal_loglik(init, f1, t_correct, lam, gridsize=1, transX="standard"):
+    ini = init if isinstance(init, Init) else Init(init)
+    F = _f(f1)
+    return lib().orc_coal_loglik(ini.ref, _p(F), F.shape[0], F.shape[1] - 1, C.c_double(t_correct),
+                                 C.c_double(lam))
+
+
+def full_loglik(cfg, ini, param, initial, t, gridsize, OriginTraj, t_correct):
+    """One FULL evaluation (New_Param_List -> TransformTraj -> volz_loglik_nh2). Returns dict + status."""
+    param, initial, t, eps = _d(param), _d(initial), _d(t), _f(OriginTraj)
+    nt, p = len(t), cfg.p
+    k, nrow = (nt - 1) // gridsize, nt // gridsize + 1
+    A, L = _cubes(p, k)
+    ode, betaN, lat = np.empty((nrow, p + 1), order="F"), np.empty(nrow), np.empty((nrow, p + 1), order="F")
+    cl = C.c_double()
+    st = lib().orc_full_loglik(cfg.ref, ini.ref, _p(param), _p(initial), _p(t), nt, int(gridsize), _p(eps),
+                               C.c_double(t_correct), _p(A), _p(L), _p(ode), _p(betaN), _p(lat), C.byref(cl))
+    return {"status": st, "FT": {"A": A, "Sigma": L}, "Ode": ode, "betaN": betaN, "LatentTraj": lat,
+            "coalLog": cl.value}
+
+
+def Update_Param(param, initial, t, OriginTraj, x_r, x_i, init, gridsize, coal_log=0.0,
+                 prior_proposal_offset=0.0, t_correct=0.0, transP="changepoint", model="SIR",
+                 transX="standard", volz=True, *, unif):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    ini = init if isinstance(init, Init) else Init(init)
+    param, initial, t, eps = _d(param), _d(initial), _d(t), _f(OriginTraj)
+    nt, p = len(t), cfg.p
+    k, nrow = (nt - 1) // gridsize, nt // gridsize + 1
+    A, L = _cubes(p, k)
+    ode, betaN, lat = np.empty((nrow, p + 1), order="F"), np.empty(nrow), np.empty((nrow, p + 1), order="F")
+    cl, acc = C.c_double(), C.c_int()
+    st = lib().orc_update_param(cfg.ref, ini.ref, _p(param), _p(initial), _p(t), nt, _p(eps), int(gridsize),
+                                C.c_double(coal_log), C.c_double(prior_proposal_offset), C.c_double(t_correct),
+                                C.c_double(unif), C.byref(acc), _p(A), _p(L), _p(ode), _p(betaN), _p(lat),
+                                C.byref(cl))
+    if st:
+        raise ValueError("Invalid input for cholesky decomposition., parametrization fails")
+    if not acc.value:
+        return {"accept": False, "coalLog_proposed": cl.value}
+    return {"accept": True, "FT": {"A": A, "Sigma": L}, "Ode": ode, "betaN": betaN, "coalLog": cl.value,
+            "LatentTraj": lat}
+
+
+def Param_Slice_update(param, x_r, x_i, theta, newChs, rho=1):
+    param, newChs = _d(param), _d(newChs)
+    xi, xip = _ints(x_i)
+    out = np.empty(len(param))
+    lib().orc_param_slice_update(_p(param), len(param), xip, C.c_double(theta), _p(newChs), _p(out))
+    return out
+
+
+def _pr8(priorList):
+    return _d(np.concatenate([np.asarray(v, dtype=np.float64).ravel()[:2] for v in priorList]))
+
+
+def Param_Slice_update_all2(par_old, x_r, x_i, theta, newChs, ESS_vec, priorList):
+    par_old, newChs = _d(par_old), _d(newChs)
+    xi, xip = _ints(x_i)
+    ev, evp = _ints(ESS_vec)
+    pr = _pr8(priorList)
+    out = np.empty(len(par_old))
+    lib().orc_param_slice_update_all2(_p(par_old), len(par_old), xip, C.c_double(theta), _p(newChs), evp,
+                                      _p(pr), _p(out))
+    return out
+
+
+def ESlice_par_General(par_old, t, OriginTraj, priorList, x_r, x_i, init, gridsize, ESS_vec, coal_log=0.0,
+                       t_correct=0.0, transP="changepoint", model="SIR", transX="standard", volz=True, *,
+                       normals, uniforms):
+    par_old, t, eps = _d(par_old), _d(t), _f(OriginTraj)
+    cfg = Cfg(x_r, x_i, len(par_old) - 2, model, transX)
+    ini = init if isinstance(init, Init) else Init(init)
+    ev, evp = _ints(ESS_vec)
+    pr, nrm, unf = _pr8(priorList), _d(normals), _d(uniforms)
+    nt, p = len(t), 2
+    k, nrow = (nt - 1) // gridsize, nt // gridsize + 1
+    A, L = _cubes(p, k)
+    ode, betaN, lat = np.empty((nrow, p + 1), order="F"), np.empty(nrow), np.empty((nrow, p + 1), order="F")
+    par_new, eps_new = np.empty(len(par_old)), np.empty((k, p), order="F")
+    cl, lo = C.c_double(), C.c_double()
+    nn, nu, ne = C.c_int(), C.c_int(), C.c_int()
+    st = lib().orc_eslice_par_general(cfg.ref, ini.ref, _p(par_old), len(par_old), _p(t), nt, _p(eps), _p(pr),
+                                      int(gridsize), evp, C.c_double(coal_log), C.c_double(t_correct),
+                                      _p(nrm), _p(unf), C.byref(nn), C.byref(nu), C.byref(ne), _p(par_new),
+                                      _p(A), _p(L), _p(ode), _p(betaN), _p(lat), _p(eps_new), C.byref(cl),
+                                      C.byref(lo))
+    return {"betaN": betaN, "FT": {"A": A, "Sigma": L}, "OdeTraj": ode, "par": par_new, "LatentTraj": lat,
+            "CoalLog": cl.value, "OriginTraj": eps_new, "logOrigin": lo.value,
+            "status": st, "n_normals": nn.value, "n_uniforms": nu.value, "n_evals": ne.value}
+
+
+def ESlice_general_NC(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, coal_log=-99999999.0,
+                      gridsize=100, volz=False, model="SIR", transX="standard", *, normals, uniforms):
+    f, O = _f(f_cur), _f(OdeTraj)
+    A, L = _f(FTs["A"]), _f(FTs["Sigma"])
+    ini = init if isinstance(init, Init) else Init(init)
+    b, nrm, unf = _d(betaN), _d(normals), _d(uniforms)
+    k, p = f.shape
+    Index = (C.c_int * 2)(0, 1 if model == "SIR" else 2)
+    lat, eps_new = np.empty((k + 1, p + 1), order="F"), np.empty((k, p), order="F")
+    cl, lo = C.c_double(), C.c_double()
+    nn, nu, ne = C.c_int(), C.c_int(), C.c_int()
+    st = lib().orc_eslice_general_nc(ini.ref, _p(f), k, p, _p(O), _p(A), _p(L), _p(b), C.c_double(t_correct),
+                                     C.c_double(lam), C.c_double(coal_log), int(bool(volz)), Index,
+                                     TRANSX[transX], _p(nrm), _p(unf), C.byref(nn), C.byref(nu), C.byref(ne),
+                                     _p(lat), _p(eps_new), C.byref(lo), C.byref(cl))
+    if st < 0:
+        raise NotImplementedError("ESlice_general_NC(volz=False): LogTraj() is not defined in the reference's C++")
+    return {"LatentTraj": lat, "OriginTraj": eps_new, "logOrigin": lo.value, "CoalLog": cl.value,
+            "status": st, "n_normals": nn.value, "n_uniforms": nu.value, "n_evals": ne.value}
+
+
+def ESlice_change_points(param, initial, t, OriginTraj, x_r, x_i, init, gridsize, coal_log=0.0, t_correct=0.0,
+                         transP="changepoint", model="SIR", transX="standard", volz=True, *, normals, uniforms):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    ini = init if isinstance(init, Init) else Init(init)
+    param, initial, t, eps = _d(param), _d(initial), _d(t), _f(OriginTraj)
+    nrm, unf = _d(normals), _d(uniforms)
+    nt, p = len(t), cfg.p
+    k, nrow = (nt - 1) // gridsize, nt // gridsize + 1
+    A, L = _cubes(p, k)
+    ode, betaN, lat = np.empty((nrow, p + 1), order="F"), np.empty(nrow), np.empty((nrow, p + 1), order="F")
+    param_new = np.empty(len(param))
+    cl, lcp = C.c_double(), C.c_double()
+    nn, nu, ne = C.c_int(), C.c_int(), C.c_int()
+    st = lib().orc_eslice_change_points(cfg.ref, ini.ref, _p(param), _p(initial), _p(t), nt, _p(eps),
+                                        int(gridsize), C.c_double(coal_log), C.c_double(t_correct), _p(nrm),
+                                        _p(unf), C.byref(nn), C.byref(nu), C.byref(ne), _p(param_new), _p(A),
+                                        _p(L), _p(ode), _p(betaN), _p(lat), C.byref(cl), C.byref(lcp))
+    return {"betaN": betaN, "FT": {"A": A, "Sigma": L}, "OdeTraj": ode, "param": param_new, "LatentTraj": lat,
+            "CoalLog": cl.value, "LogChProb": lcp.value,
+            "status": st, "n_normals": nn.value, "n_uniforms": nu.value, "n_evals": ne.value}
+
+
+def chols(S):
+    S = _f(S)
+    out = np.empty((2, 2), order="F")
+    lib().orc_chols(_p(S), _p(out))
+    return out
+
+
+def inv2(a):
+    a = _f(a)
+    out = np.empty((2, 2), order="F")
+    lib().orc_inv2(_p(a), _p(out))
+    return out
