@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- LNA+coalescent log-likelihood evaluations/sec (and ESlice chain-iterations/sec).
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N>1) prints ONE JSON
+line on rank 0.  Workload = BASELINE.json configs[1] (Changpoint_sim vignette: SIR LNA, N=1e6,
+2000 fine steps, gridsize 50, 39 R0 change points, the vignette's cached 342-tip genealogy E=376),
+4096 chains.  One "step" of the likelihood leg = one batch of B FULL evaluations
+(param, initial, OriginTraj) -> coalLog per GPU, B = 4096 chains x 16 slice proposals by default.
+
+  value      : FULL evaluations/s, inputs already resident in HBM, CUDA-event timed on the launch stream
+  e2e        : the same through the host-buffer C ABI call (pinned host inputs, H2D + kernel + D2H)
+  eslice     : chain-iterations/s of the batched General_MCMC_with_ESlice iteration (when built)
+  roofline   : algorithmic FP64 flops (113/fine step + 21/interval + 10/cell)
+               over the measured independent-DFMA peak of this GPU
+  cpu_baseline: the CPU oracle (restated reference algorithm) on the host cores, bounded sample
+
+`--impl reference` times only the CPU oracle (the reference cannot be built here: no R/Rcpp/Armadillo).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "LNA+coalescent loglik evals/sec (FULL evaluations, batched chains)"
+UNIT = "evals/s"
+
+
+def load_workload():
+    from conftest import Golden
+    return Golden("changepoint_sim")
+
+
+def synth_inputs(g, B, seed):
+    """Synthetic draws of the vignette's shape: parameters around the cached chain state, fresh
+    N(0,1) latent increments.  Natural layouts: par (B,44), eps (B,k,p)."""
+    rng = np.random.default_rng(seed)
+    par = np.tile(g.final["par"].ravel(), (B, 1))
+    par[:, 2] *= np.exp(0.05 * rng.standard_normal(B))
+    par[:, 3] *= np.exp(0.05 * rng.standard_normal(B))
+    par[:, 4:43] *= np.exp(0.02 * rng.standard_normal((B, 39)))
+    eps = rng.standard_normal((B, 40, 2))
+    return par, eps
+
+
+def algorithmic_flops(g):
+    n = len(g.times) - 1
+    k = n // g.gridsize
+    ng = int(g.init["ng"][0])
+    return 113.0 * n + 21.0 * k + 10.0 * (ng - 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def time_oracle(g, n_per_thread, threads, seed=123):
+    from oracle import oracle as orc
+    cfg, ini = orc.Cfg(g.x_r, g.x_i, 42), orc.Init(g.init)
+    par, eps = synth_inputs(g, n_per_thread * threads, seed)
+    chunks = [(par[i * n_per_thread:(i + 1) * n_per_thread], eps[i * n_per_thread:(i + 1) * n_per_thread])
+              for i in range(threads)]
+    outs = [None] * threads
+
+    def work(i):
+        outs[i] = orc.full_loglik_batch(cfg, ini, chunks[i][0][:, 2:], chunks[i][0][:, :2], g.times, g.gridsize,
+                                        chunks[i][1], g.t_correct)
+
+    orc.lib()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return n_per_thread * threads / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = load_workload()
+    cores = os.cpu_count() or 1
+    per = max(16, int(args.ref_evals_per_core))
+    for _ in range(args.warmup):
+        time_oracle(g, 16, cores)
+    tot_t, tot_n = 0.0, 0
+    for s in range(args.steps):
+        rate, dt = time_oracle(g, per, cores, seed=1000 + s)
+        tot_t += dt
+        tot_n += per * cores
+    val = tot_n / tot_t
+    sample = f"{per} FULL evals per core per step x {cores} threads (Changpoint_sim shape), CPU oracle -O2 -ffp-contract=off"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Changpoint_sim vignette shape: SIR LNA N=1e6, 2000 fine steps, gridsize 50, "
+                               "39 change points, E=376 genealogy; FULL loglik evaluations"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=4096, help="concurrent chains per GPU")
+    ap.add_argument("--proposals", type=int, default=16, help="slice proposals per chain in one likelihood batch")
+    ap.add_argument("--ref-evals-per-core", type=int, default=1024)
+    ap.add_argument("--cpu-evals-per-core", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eslice", action="store_true")
+    ap.add_argument("--eslice-iters", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from lnaphylodyn_b200 import _lib, api
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = _lib.lib()
+    g = load_workload()
+    B = args.chains * args.proposals
+    pb = api.Problem(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init, device=local_rank)
+    stream = torch.cuda.current_stream(dev)
+    _lib.check(L.lna_problem_set_stream(pb.h, C.c_void_p(stream.cuda_stream)), "set_stream")
+
+    # ---- inputs: NBUF distinct batches resident in HBM (this rank's shard of the global batch) ----
+    NBUF = 4
+    bufs = []
+    host = []
+    for i in range(NBUF):
+        par, eps = synth_inputs(g, B, seed=10_000 * (rank + 1) + i)
+        param_h = torch.from_numpy(np.ascontiguousarray(par[:, 2:])).pin_memory()
+        init_h = torch.from_numpy(np.ascontiguousarray(par[:, :2])).pin_memory()
+        eps_h = torch.from_numpy(np.ascontiguousarray(np.transpose(eps, (0, 2, 1)))).pin_memory()  # item = k x p col-major
+        host.append((param_h, init_h, eps_h))
+        bufs.append(tuple(t.to(dev) for t in (param_h, init_h, eps_h)))
+    coal_d = torch.empty(B, dtype=torch.float64, device=dev)
+    st_d = torch.empty(B, dtype=torch.int32, device=dev)
+    coal_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    st_h = torch.empty(B, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+
+    def step_dev(i):
+        p_, i_, e_ = bufs[i % NBUF]
+        _lib.check(L.lna_full_loglik_dev(pb.h, B, p_.data_ptr(), i_.data_ptr(), e_.data_ptr(), coal_d.data_ptr(),
+                                         st_d.data_ptr(), None, None, None, None, None), "lna_full_loglik_dev")
+
+    def step_host(i):
+        p_, i_, e_ = host[i % NBUF]
+        _lib.check(L.lna_full_loglik(pb.h, B, p_.data_ptr(), i_.data_ptr(), e_.data_ptr(), coal_h.data_ptr(),
+                                     st_h.data_ptr(), None, None, None, None, None), "lna_full_loglik")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    fp64_peak = L.lna_measure_fp64_peak(local_rank, 20000) if rank == 0 else 0.0
+
+    for i in range(args.warmup):
+        step_dev(i)
+        step_host(i)
+    torch.cuda.synchronize(dev)
+    # sanity: device-resident and host-buffer paths agree
+    step_dev(0)
+    step_host(0)
+    torch.cuda.synchronize(dev)
+    assert torch.equal(coal_d.cpu(), coal_h), "device-resident and host-buffer results differ"
+    n_sentinel = int((coal_h == -10000000.0).sum())
+
+    clocks = Clocks(local_rank)
+    launches0 = pb.launch_count()
+    barrier()
+    clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (not timed)
+        evs[i][0].record(stream)
+        step_dev(i)
+        evs[i][1].record(stream)
+    barrier()
+    clk = clocks.stop()
+    launches = pb.launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the reference-facing C ABI call, copies inside the timed region ----
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * args.steps / float(t.item())
+    h2d = sum(x.numel() * x.element_size() for x in host[0])
+    d2h = coal_h.numel() * 8 + st_h.numel() * 4
+
+    # ---- ESlice leg (batched General_MCMC_with_ESlice iterations), when the chain driver is built ----
+    eslice = None
+    if not args.no_eslice:
+        try:
+            from lnaphylodyn_b200 import chains as chains_mod
+            eslice = chains_mod.bench_eslice(pb, g, args.chains, args.eslice_iters, rank, world, dev)
+        except Exception as e:  # noqa: BLE001
+            eslice = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+    if rank == 0:
+        W = algorithmic_flops(g)
+        achieved = (value / world) * W / 1e12
+        peak = fp64_peak / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1] Changpoint_sim vignette: SIR LNA N=1e6, 2000 fine steps, gridsize 50, "
+                                   "39 R0 change points, cached 342-tip genealogy (E=376)",
+                       "chains_per_gpu": args.chains, "proposals_per_chain": args.proposals, "evals_per_step_per_gpu": B,
+                       "l2": "256 MB flush write between timed iterations", "sentinel_evals_in_batch": n_sentinel},
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                         "flops_per_eval": W,
+                         "peak_source": "measured here: independent-DFMA microbenchmark (lna_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "hbm_algorithmic_GBps": (value / world) * (h2d + d2h) / B / 1e9},
+        }
+        if eslice is not None:
+            line["eslice"] = eslice
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate1, dt1 = time_oracle(g, max(64, args.cpu_evals_per_core // 2), 1)
+            rateN, dtN = time_oracle(g, args.cpu_evals_per_core, cores)
+            line["cpu_baseline"] = {"value": rateN, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "value_1core": rate1,
+                                    "sample": f"{args.cpu_evals_per_core} FULL evals/core x {cores} threads "
+                                              f"({dtN:.1f}s) + {max(64, args.cpu_evals_per_core // 2)} on 1 core ({dt1:.1f}s); "
+                                              "CPU oracle = literal restatement of the reference algorithm"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,246 @@
+/*
+ * lnaphylodyn_b200.h -- C ABI of the B200-native LNA + coalescent likelihood / elliptical-slice path.
+ *
+ * This is the drop-in boundary (DESIGN.md section "Boundary"): the reference's Rcpp glue
+ * (src/RcppExports.cpp, R/RcppExports.R) would forward its `.Call("_LNAPhyloDyn_<fn>")` entry
+ * points for this path to the functions below (INTEGRATION.md shows the shim).  Plain C: pointers,
+ * sizes and two small structs; no C++/torch types.  All `file:line` citations are into the
+ * reference tree (MingweiWilliamTang/LNAphyloDyn).
+ *
+ * Conventions
+ *  - Every entry point is BATCHED: `B` independent items (chains / proposals / parameter draws).
+ *    B = 1 reproduces the single-call Rcpp semantics.  Item b of an array with per-item length n
+ *    lives at `ptr + b*n`; inside one item the layout is exactly Armadillo's (column-major
+ *    matrices, p x p x k cubes slice-major, trajectories nrow x (p+1) with column 0 = time).
+ *  - Functions without suffix take HOST pointers (copies happen inside); `_dev` variants take
+ *    DEVICE pointers on the problem's device and are asynchronous on the problem's stream.
+ *  - Random numbers are never drawn here: samplers take PRE-DRAWN standard normals / uniforms and
+ *    consume them in the reference's order, so chains are replayable.
+ *  - Return value: 0 on success, -1 on error (message via lna_last_error()).  Numerical failure is
+ *    reported per item in `status` (LNA_ST_* bits) and, like the reference, in-band as -1e7.
+ *  - There is NO CPU fallback: without a CUDA device every compute call fails with -1.
+ */
+#ifndef LNAPHYLODYN_B200_H_
+#define LNAPHYLODYN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNA_ABI_VERSION 1
+
+/* model strings of the reference ("SIR","SEIR": LNA_functional.cpp:390-443) become enums */
+enum { LNA_MODEL_SIR = 0, LNA_MODEL_SEIR = 1 };
+/* transX: only "standard" is on the GPU path ("log" is legacy) */
+enum { LNA_TRANSX_STANDARD = 0 };
+
+/* per-item status bits (reference failure channels) */
+enum {
+    LNA_ST_OK = 0,
+    LNA_ST_CHOL_FAIL = 1, /* arma::chol threw in KF_param_chol (LNA_functional.cpp:660-664)      */
+    LNA_ST_NEG_STATE = 2, /* state < 0 in rows 0..ng-1 -> -1e7 (LNA_functional.cpp:1130-1132)     */
+    LNA_ST_NAN = 4,       /* NaN among the per-event terms -> -1e7 (LNA_functional.cpp:1172-1174) */
+    LNA_ST_CAP_HIT = 8    /* 20-shrink cap -> reverted to the current state (:1609-1622,1741-1747) */
+};
+
+#define LNA_SENTINEL (-10000000.0)
+
+/* Replaces (model, transP, transX, x_r, x_i, t, gridsize, t_correct): the arguments every
+ * hot-path export repeats (e.g. New_Param_List, LNA_functional.cpp:1191-1193). */
+typedef struct lna_cfg {
+    int model;          /* LNA_MODEL_*                                                        */
+    int transX;         /* LNA_TRANSX_STANDARD                                                */
+    int nch;            /* x_i[0]: number of R0 change points                                 */
+    int nparam;         /* x_i[1]: number of model parameters before the change ratios        */
+    int iR0;            /* x_i[2]: index of R0 in `param`; also the S column for volz         */
+    int iGamma;         /* x_i[3]: index of gamma in `param`; also the I column for volz      */
+    int gridsize;       /* fine steps per LNA interval                                        */
+    int nt;             /* length(times)                                                      */
+    const double *times;/* fine time grid, length nt (uniform in every reference config)      */
+    const double *x_r;  /* (N, cht_1..cht_nch), length nch+1                                  */
+    double t_correct;   /* forward time of the most recent sample                             */
+} lna_cfg;
+
+/* Positional view of coal_lik_init()'s list (R/coal_simulation.R:204-277): the entries the
+ * coalescent likelihoods read (init[2],[3],[4],[6],[9]; LNA_functional.cpp:1124,1146,1169). */
+typedef struct lna_init {
+    int E;                 /* length(C) = length(D) = length(y) = sum(gridrep)             */
+    int ng;                /* Init$ng                                                         */
+    const double *C;       /* Init$C  = l(l-1)/2 per interval                                */
+    const double *D;       /* Init$D  = interval lengths                                     */
+    const double *y;       /* Init$y  = 1 if the interval ends in a coalescence              */
+    const double *gridrep; /* Init$gridrep (R numeric), length ng                            */
+} lna_init;
+
+typedef struct lna_problem lna_problem; /* opaque: device copy of cfg + genealogy, stream, scratch */
+
+/* ---- runtime ---------------------------------------------------------------------------------- */
+int lna_abi_version(void);
+const char *lna_last_error(void);
+int lna_device_count(void);
+/* contiguous shard [*begin,*end) of B items owned by `rank` of `nranks` */
+int lna_shard(int64_t B, int rank, int nranks, int64_t *begin, int64_t *end);
+
+/* Build the per-genealogy device state.  `init` may be NULL for ODE/LNA-only use.  The per-cell
+ * sums  sum_{e in cell} C_e D_e  and  sum y_e  are reduced on the device here (segmented reduction
+ * over the sorted events) so that each likelihood evaluation is O(ng) instead of O(E). */
+lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *init, int device);
+void lna_problem_destroy(lna_problem *pb);
+int lna_problem_sync(lna_problem *pb);               /* cudaStreamSynchronize on the problem stream */
+void *lna_problem_stream(lna_problem *pb);           /* cudaStream_t */
+int lna_problem_set_stream(lna_problem *pb, void *cuda_stream);
+/* dimensions derived from cfg: p, k = (nt-1)/gridsize, nrow = nt/gridsize + 1, npt = nparam+nch+1 */
+int lna_problem_dims(const lna_problem *pb, int *p, int *k, int *nrow, int *npt);
+/* number of kernel launches issued through this problem so far (bench.py "gpu_launches") */
+int64_t lna_problem_launch_count(const lna_problem *pb);
+/* per-cell sums computed at create time (host copies), each of length ng-1 */
+int lna_problem_cell_sums(const lna_problem *pb, double *cellCD, double *cellY, double *cellCnt);
+
+/* ---- helpers of the integrator --------------------------------------------------------------- */
+/* betaTs (LNA_functional.cpp:31-58): beta at `m` sorted times, per item.  betas: B x m. */
+int lna_betaTs(lna_problem *pb, int64_t B, const double *param, const double *times, int m, double *betas);
+/* param_transform (:63-86): theta at time t[b] per item; param2: B x npt. */
+int lna_param_transform(lna_problem *pb, int64_t B, const double *t, const double *param, double *param2);
+/* ODE_rk45 (:455-491): fine mean trajectory, OdeTraj: B x (nt x (p+1)). */
+int lna_ode_rk45(lna_problem *pb, int64_t B, const double *initial, const double *param, double *OdeTraj);
+/* KF_param_chol / KF_param (:638-670 / :603-634) from a given fine trajectory.
+ * Acube, Scube: B x (p*p*k).  chol != 0: Scube holds L = chol(Sigma+1e-8 I)^T and status gets
+ * LNA_ST_CHOL_FAIL where the reference would throw; chol == 0: Scube holds Sigma. */
+int lna_kf_param(lna_problem *pb, int64_t B, const double *OdeTraj, const double *param, int chol,
+                 double *Acube, double *Scube, int32_t *status);
+/* Ode_Coarse_Slicer (:1179-1188). Ode_coarse: B x (nrow x (p+1)). */
+int lna_ode_coarse_slicer(lna_problem *pb, int64_t B, const double *OdeTraj, double *Ode_coarse);
+/* New_Param_List (:1191-1208): ODE -> FT (A, L) -> coarse ODE -> betaN, fused in one kernel. */
+int lna_new_param_list(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                       double *Acube, double *Lcube, double *Ode_coarse, double *betaN, int32_t *status);
+
+/* ---- non-centred trajectory ------------------------------------------------------------------ */
+/* TransformTraj (:877-900).  OriginLatent: B x (k x p); LNA_traj: B x (nrow x (p+1)). */
+int lna_transform_traj(lna_problem *pb, int64_t B, const double *Ode_coarse, const double *OriginLatent,
+                       const double *Acube, const double *Lcube, double *LNA_traj);
+/* Traj_sim_general_noncentral (:824-872) with supplied normals (B x k*p, step-major: step i uses
+ * normals[i*p..i*p+p-1]).  Also returns OriginLatent (k x p col-major), logMultiNorm, logOrigin. */
+int lna_traj_sim_noncentral(lna_problem *pb, int64_t B, const double *Ode_coarse, const double *Acube,
+                            const double *Lcube, const double *normals, double *LNA_traj,
+                            double *OriginLatent, double *logMultiNorm, double *logOrigin);
+
+/* ---- coalescent likelihoods ------------------------------------------------------------------ */
+/* volz_loglik_nh2 (:1119-1176) on given trajectories (B x nrow x (p+1)) and betaN (B x nrow). */
+int lna_volz_loglik_nh2(lna_problem *pb, int64_t B, const double *traj, const double *betaN,
+                        double *loglik, int32_t *status);
+/* coal_loglik3 (:1016-1054) / coal_loglik (SIR_phylodyn.cpp:436-468): Kingman with scale lambda[b].
+ * take_log != 0: column `col` (1-based state column of traj) holds counts (coal_loglik3, transX
+ * "standard"); take_log == 0: it already holds log-counts (coal_loglik uses col = 2). */
+int lna_coal_loglik(lna_problem *pb, int64_t B, const double *traj, const double *lambda, int col,
+                    int take_log, double *loglik);
+
+/* ---- the hot path: one FULL evaluation per item ---------------------------------------------- */
+/* (param, initial, OriginTraj) -> coalLog = volz_loglik_nh2(TransformTraj(New_Param_List(...)))
+ * i.e. the body of Update_Param (:1217-1226) and of every ESlice iteration, fused in one kernel,
+ * one thread per item, all state in registers.  Optional outputs may be NULL. */
+int lna_full_loglik(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                    const double *OriginTraj, double *coalLog, int32_t *status,
+                    double *Acube, double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj);
+int lna_full_loglik_dev(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                        const double *OriginTraj, double *coalLog, int32_t *status,
+                        double *Acube, double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj);
+
+/* Update_Param (:1212-1243): FULL evaluation + MH test  log(unif[b]) < coalLog_new - coal_log[b] +
+ * prior_proposal_offset[b].  accept[b] in {0,1}; outputs are written for every item (the caller
+ * keeps them only where accept[b] == 1, like the R wrapper LNA_chpt_slice.R:254-262). */
+int lna_update_param(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                     const double *OriginTraj, const double *coal_log, const double *prior_proposal_offset,
+                     const double *unif, int32_t *accept, double *coalLog_new, int32_t *status,
+                     double *Acube, double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj);
+
+/* ---- elliptical slice sampling --------------------------------------------------------------- */
+/* Param_Slice_update (:1246-1253) and Param_Slice_update_all2 (:1268-1314), per item. */
+int lna_param_slice_update(lna_problem *pb, int64_t B, const double *param, const double *theta,
+                           const double *newChs, double *param_new);
+int lna_param_slice_update_all2(lna_problem *pb, int64_t B, const double *par_old, const double *theta,
+                                const double *newChs, const int32_t *ESS_vec7, const double *prior8,
+                                double *par_new);
+
+/* Number of uniforms an ESlice call may consume: u, theta_1 and one per shrink. */
+#define LNA_ESLICE_MAX_UNIF 22
+
+/* ESlice_par_General (:1532-1688), SIR (p = 2) only like the reference.  par_old: B x npar
+ * (npar = 2 + npt); normals: B x (npar-1); uniforms: B x LNA_ESLICE_MAX_UNIF (u, theta draws).
+ * prior8 = (priorList[[1]][1:2], ..., priorList[[4]][1:2]); ESS_vec7[6] must be 0.
+ * The candidates theta_1..theta_20 depend only on the uniforms, so they are evaluated
+ * speculatively, `spec_width` (1,2,4,8,16,32; 0 = auto) per wave, and the first one with
+ * loglike > logy is taken: identical to the sequential loop.  n_evals[b] = evaluations the
+ * sequential loop would have made (1 + shrinks). */
+int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *par_old, const double *OriginTraj,
+                           const double *prior8, const int32_t *ESS_vec7, const double *coal_log,
+                           const double *normals, const double *uniforms, int spec_width,
+                           double *par_new, double *Acube, double *Lcube, double *Ode_coarse,
+                           double *betaN, double *LatentTraj, double *CoalLog, double *logOrigin,
+                           int32_t *n_evals, int32_t *status);
+
+/* ESlice_general_NC (:1690-1778), volz likelihood.  f_cur: B x (k x p); normals: B x (k*p)
+ * (column-major k x p like arma::randn(k,p)); uniforms: B x LNA_ESLICE_MAX_UNIF.
+ * coal_log[b] == -99999999 recomputes the current likelihood like the reference. */
+int lna_eslice_general_nc(lna_problem *pb, int64_t B, const double *f_cur, const double *Ode_coarse,
+                          const double *Acube, const double *Lcube, const double *betaN,
+                          const double *coal_log, const double *normals, const double *uniforms,
+                          double *LatentTraj, double *OriginTraj_new, double *logOrigin, double *CoalLog,
+                          int32_t *n_evals, int32_t *status);
+
+/* ESlice_change_points (:1317-1409).  param: B x npt; normals: B x nch; uniforms: B x 22. */
+int lna_eslice_change_points(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                             const double *OriginTraj, const double *coal_log, const double *normals,
+                             const double *uniforms, int spec_width, double *param_new, double *Acube,
+                             double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj,
+                             double *CoalLog, double *LogChProb, int32_t *n_evals, int32_t *status);
+
+/* ---- resident chain batches: the MCMC driver loop on the device -------------------------------- */
+/* State of B chains kept in HBM between iterations (par, OriginTraj, FT, coarse ODE, betaN,
+ * LatentTraj, coalLog, logOrigin): the batched equivalent of the R list MCMC_obj
+ * (R/general_change_point.R:558-561). */
+typedef struct lna_chains lna_chains;
+
+/* Settings of General_MCMC_with_ESlice's iteration body (R/LNA_chpt_slice.R:775-847) as used by
+ * the Changpoint_sim / Ebola vignettes: MH on log(gamma) + the no-op hyper MH,
+ * parameter ESS, trajectory ESS. */
+typedef struct lna_mcmc_opts {
+    double prior8[8];     /* (pop_pr[1:2], R0_pr, prior[[3]], hyper_pr) as passed to ESlice_par_General */
+    double gamma_prior[2];/* MCMC_setting$prior[[priorId]] for the gamma MH step                     */
+    double gamma_prop;    /* MCMC_setting$proposal[[proposeId]]: half-width of the uniform RW        */
+    int32_t ESS_vec[7];
+    int32_t update_traj;  /* 1: run updateTraj_general_NC (i >= burn1); 0: skip (i < burn1)          */
+    int32_t hyper_noop_mh;/* 1: also run the no-op hyper MH entry (parIdlist d)         */
+    int32_t spec_width;   /* speculative candidates per wave for the parameter ESS (0 = auto)        */
+} lna_mcmc_opts;
+
+/* uniforms per chain-iteration: gamma RW draw, MH accept, hyper MH accept, ESS-par (22), ESS-traj (22) */
+#define LNA_ITER_UNIF (3 + 2 * LNA_ESLICE_MAX_UNIF)
+
+lna_chains *lna_chains_create(lna_problem *pb, int64_t B);
+void lna_chains_destroy(lna_chains *ch);
+/* Initialise from (par, OriginTraj) per chain: New_Param_List + TransformTraj + volz_loglik_nh2
+ * (MCMC_initialize_general, R/general_change_point.R:507-536).  Host pointers. */
+int lna_chains_init(lna_chains *ch, const double *par, const double *OriginTraj);
+/* One MCMC iteration for all chains.  normals: B x (npar-1 + k*p); uniforms: B x LNA_ITER_UNIF.
+ * `_dev`: streams already in HBM.  Host variant copies them in first. */
+int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *opts, const double *normals, const double *uniforms);
+int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *opts, const double *normals, const double *uniforms);
+/* Read the state back (any pointer may be NULL).  counters: B x 4 int32 = (n_full_evals,
+ * n_cheap_evals, n_mh_accept, status OR). */
+int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
+                   double *logOrigin, int32_t *counters);
+/* Device pointer to the B x 4 summary block (coalLog, logOrigin, n_full_evals, status) that is
+ * all-gathered across GPUs; valid until the next step. */
+const double *lna_chains_summary_dev(lna_chains *ch);
+
+/* ---- measurement helper ---------------------------------------------------------------------- */
+/* Independent-DFMA microbenchmark: returns achieved FP64 FLOP/s of the device (2 flops per FMA),
+ * used as the measured denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 entry). */
+double lna_measure_fp64_peak(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LNAPHYLODYN_B200_H_ */

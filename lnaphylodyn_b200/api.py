@@ -1,0 +1,408 @@
+"""Host-side mirror of the reference's Rcpp-exported operator API for the hot path.
+
+R is not available in this image, so this Python layer plays the role of R/RcppExports.R: the
+function names, argument order/meaning and error behaviour follow the reference
+(R/RcppExports.R:27-181; src/LNA_functional.h:15-120), and every call goes through the C ABI of
+liblnaphylodyn_b200.so (include/lnaphylodyn_b200.h) into hand-written sm_100a kernels.
+Differences from the reference, all forced by the batched/replayable design:
+  * every function also accepts a leading batch dimension (param of shape (B, npt), ...);
+  * samplers take pre-drawn `normals=` / `uniforms=` instead of calling an RNG;
+  * Lists become dicts; arma::cube (p,p,k) becomes an ndarray of shape (p,p,k) (Fortran order).
+No CPU fallback: importing works anywhere, calling needs a CUDA device.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import LnaCfg, LnaInit, LnaError, check
+
+MODELS = {"SIR": 0, "SEIR": 1}
+MODEL_P = {"SIR": 2, "SEIR": 3}
+SENTINEL = -10000000.0
+ST_CHOL_FAIL, ST_NEG_STATE, ST_NAN, ST_CAP_HIT = 1, 2, 4, 8
+ESLICE_MAX_UNIF = 22
+CHOL_MSG = "Invalid input for cholesky decomposition., parametrization fails"  # LNA_functional.cpp:663
+
+
+def _d(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _xi(x_i):
+    return [int(round(float(v))) for v in np.asarray(x_i).ravel()]
+
+
+class Problem:
+    """Device-resident (config + genealogy) handle: wraps lna_problem (lna_problem_create)."""
+
+    def __init__(self, times, x_r, x_i, gridsize, t_correct=0.0, init=None, model="SIR", transX="standard",
+                 device=0):
+        if model not in MODELS:
+            raise LnaError(f"model {model!r} is not on the GPU path (SIR, SEIR)")
+        if transX != "standard":
+            raise LnaError('only transX="standard" is on the GPU path')
+        self.times, self.x_r = _d(times), _d(x_r)
+        self.x_i = _xi(x_i)
+        self.model, self.gridsize, self.t_correct, self.device = model, int(gridsize), float(t_correct), int(device)
+        cfg = LnaCfg(MODELS[model], 0, self.x_i[0], self.x_i[1], self.x_i[2], self.x_i[3], self.gridsize,
+                     len(self.times), self.times.ctypes.data_as(_lib._dp), self.x_r.ctypes.data_as(_lib._dp),
+                     self.t_correct)
+        ini_ref = None
+        if init is not None:
+            g = init
+            self._C, self._D, self._y = _d(g["C"]), _d(g["D"]), _d(g["y"])
+            self._gridrep = _d(g["gridrep"])
+            ng = int(np.asarray(g["ng"]).ravel()[0])
+            self._ini = LnaInit(len(self._C), ng, self._C.ctypes.data_as(_lib._dp), self._D.ctypes.data_as(_lib._dp),
+                                self._y.ctypes.data_as(_lib._dp), self._gridrep.ctypes.data_as(_lib._dp))
+            ini_ref = C.byref(self._ini)
+        L = _lib.lib()
+        self.h = L.lna_problem_create(C.byref(cfg), ini_ref, self.device)
+        if not self.h:
+            raise LnaError("lna_problem_create: " + L.lna_last_error().decode())
+        p, k, nrow, npt = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(L.lna_problem_dims(self.h, C.byref(p), C.byref(k), C.byref(nrow), C.byref(npt)))
+        self.p, self.k, self.nrow, self.npt = p.value, k.value, nrow.value, npt.value
+        self.has_init = init is not None
+        self._fin = weakref.finalize(self, L.lna_problem_destroy, self.h)
+
+    # -- helpers -----------------------------------------------------------------------------
+    def launch_count(self):
+        return int(_lib.lib().lna_problem_launch_count(self.h))
+
+    def sync(self):
+        check(_lib.lib().lna_problem_sync(self.h), "lna_problem_sync")
+
+    def cell_sums(self):
+        n0 = self._ini.ng - 1
+        cd, yy, cnt = np.empty(n0), np.empty(n0), np.empty(n0)
+        check(_lib.lib().lna_problem_cell_sums(self.h, _ptr(cd), _ptr(yy), _ptr(cnt)), "lna_problem_cell_sums")
+        return cd, yy, cnt
+
+    def _batch(self, a, per):
+        """-> (array of shape (B, per) C-contiguous, was_single)."""
+        a = _d(a)
+        single = a.ndim == 1 or (a.ndim >= 1 and a.size == per and a.ndim <= 2 and a.shape != (1, per) and a.ndim != 2)
+        if a.size == per and a.ndim <= 1:
+            return a.reshape(1, per), True
+        return a.reshape(-1, per), False
+
+    def _mats(self, a, shape):
+        """item matrices given in natural (row, col[, slice]) indexing -> (B, prod) in column-major item layout."""
+        a = np.asarray(a, dtype=np.float64)
+        nd = len(shape)
+        single = a.ndim == nd
+        if single:
+            a = a[None]
+        assert a.shape[1:] == tuple(shape), (a.shape, shape)
+        B = a.shape[0]
+        flat = np.ascontiguousarray(np.transpose(a, (0,) + tuple(range(nd, 0, -1)))).reshape(B, -1)
+        return flat, single
+
+    def _unmats(self, flat, shape, single):
+        nd = len(shape)
+        a = flat.reshape((flat.shape[0],) + tuple(shape[::-1]))
+        a = np.transpose(a, (0,) + tuple(range(nd, 0, -1)))
+        return a[0] if single else a
+
+    # -- batched operators -------------------------------------------------------------------
+    def full_loglik(self, param, initial, OriginTraj=None, want=("coalLog",)):
+        """FULL evaluation(s).  `want` subset of coalLog, FT, Ode, betaN, LatentTraj."""
+        P, single = self._batch(param, self.npt)
+        I, _ = self._batch(initial, self.p)
+        B = P.shape[0]
+        if I.shape[0] == 1 and B > 1:
+            I = np.ascontiguousarray(np.broadcast_to(I, (B, self.p)))
+        E = None
+        if OriginTraj is not None:
+            E, _ = self._mats(OriginTraj, (self.k, self.p))
+            if E.shape[0] == 1 and B > 1:
+                E = np.ascontiguousarray(np.broadcast_to(E, (B, E.shape[1])))
+        p, k, nrow = self.p, self.k, self.nrow
+        cl = np.empty(B) if "coalLog" in want else None
+        st = np.zeros(B, dtype=np.int32)
+        A = np.empty((B, p * p * k)) if "FT" in want else None
+        Lc = np.empty((B, p * p * k)) if "FT" in want else None
+        ode = np.empty((B, nrow * (p + 1))) if "Ode" in want else None
+        bn = np.empty((B, nrow)) if "betaN" in want else None
+        lat = np.empty((B, nrow * (p + 1))) if "LatentTraj" in want else None
+        check(_lib.lib().lna_full_loglik(self.h, B, _ptr(P), _ptr(I), _ptr(E), _ptr(cl), _ptr(st), _ptr(A), _ptr(Lc),
+                                         _ptr(ode), _ptr(bn), _ptr(lat)), "lna_full_loglik")
+        out = {"status": st[0] if single else st}
+        if cl is not None:
+            out["coalLog"] = float(cl[0]) if single else cl
+        if A is not None:
+            out["FT"] = {"A": self._unmats(A, (p, p, k), single), "Sigma": self._unmats(Lc, (p, p, k), single)}
+        if ode is not None:
+            out["Ode"] = self._unmats(ode, (nrow, p + 1), single)
+        if bn is not None:
+            out["betaN"] = bn[0] if single else bn
+        if lat is not None:
+            out["LatentTraj"] = self._unmats(lat, (nrow, p + 1), single)
+        return out
+
+
+_cache = {}
+
+
+def problem_for(times, x_r, x_i, gridsize, t_correct=0.0, init=None, model="SIR", transX="standard", device=0):
+    """Problem handles are cached by value so that the Rcpp-style free functions stay cheap."""
+    times, x_r = _d(times), _d(x_r)
+    ini_key = None
+    if init is not None:
+        ini_key = (_d(init["C"]).tobytes(), _d(init["D"]).tobytes(), _d(init["y"]).tobytes(),
+                   _d(init["gridrep"]).tobytes(), int(np.asarray(init["ng"]).ravel()[0]))
+    key = (times.tobytes(), x_r.tobytes(), tuple(_xi(x_i)), int(gridsize), float(t_correct), ini_key, model, transX,
+           device)
+    pb = _cache.get(key)
+    if pb is None:
+        if len(_cache) > 32:
+            _cache.clear()
+        pb = _cache[key] = Problem(times, x_r, x_i, gridsize, t_correct, init, model, transX, device)
+    return pb
+
+
+def _grid_problem(times_like, x_r, x_i, model, transX, nt_min=2):
+    """Problem for calls that carry no time grid of their own (betaTs, param_transform)."""
+    t = np.array([0.0, 1.0]) if times_like is None else _d(times_like)
+    return problem_for(t, x_r, x_i, 1, 0.0, None, model, transX)
+
+
+# ------------------------------------------------------------------------------------------------
+# Rcpp-named functions (R/RcppExports.R).  Single-item calls return the reference's shapes.
+# ------------------------------------------------------------------------------------------------
+
+def betaTs(param, times, x_r, x_i):
+    """LNA_functional.cpp:31-58"""
+    param = _d(param)
+    xi = _xi(x_i)
+    pb = problem_for(np.array([0.0, 1.0]), x_r, [xi[0], max(xi[1], 2), xi[2], xi[3]], 1)
+    P = np.zeros((1, pb.npt))
+    P[0, :min(pb.npt, param.size)] = param[:pb.npt]
+    times = _d(times)
+    out = np.empty((1, len(times)))
+    check(_lib.lib().lna_betaTs(pb.h, 1, _ptr(P), _ptr(times), len(times), _ptr(out)), "lna_betaTs")
+    return out[0]
+
+
+def param_transform(t, param, x_r, x_i):
+    """LNA_functional.cpp:63-86"""
+    param = _d(param)
+    xi = _xi(x_i)
+    pb = problem_for(np.array([0.0, 1.0]), x_r, [xi[0], max(xi[1], 2), xi[2], xi[3]], 1)
+    P = np.zeros((1, pb.npt))
+    P[0, :min(pb.npt, param.size)] = param[:pb.npt]
+    tt = np.array([float(t)])
+    out = np.empty((1, pb.npt))
+    check(_lib.lib().lna_param_transform(pb.h, 1, _ptr(tt), _ptr(P), _ptr(out)), "lna_param_transform")
+    res = param.copy()
+    res[0] = out[0, 0]
+    return res
+
+
+def _pad_param(pb, param):
+    """The reference tolerates extra trailing params (testthat 'Test SIR model' (a)): only the first
+    nparam+nch entries are read by the integrator."""
+    param = _d(param)
+    if param.ndim == 1:
+        param = param[None]
+    B = param.shape[0]
+    P = np.zeros((B, pb.npt))
+    n = min(pb.npt, param.shape[1])
+    P[:, :n] = param[:, :n]
+    if param.shape[1] < pb.npt - 1:
+        raise LnaError(f"param has {param.shape[1]} entries, need at least nparam+nch = {pb.npt - 1}")
+    return P
+
+
+def ODE_rk45(initial, t, param, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    """LNA_functional.cpp:455-491 -> (n x (p+1)) matrix, column 0 = t."""
+    pb = problem_for(t, x_r, x_i, 1, 0.0, None, model, transX)
+    P = _pad_param(pb, param)
+    I = _d(initial).reshape(-1, pb.p)
+    B = P.shape[0]
+    out = np.empty((B, len(pb.times) * (pb.p + 1)))
+    check(_lib.lib().lna_ode_rk45(pb.h, B, _ptr(I), _ptr(P), _ptr(out)), "lna_ode_rk45")
+    res = pb._unmats(out, (len(pb.times), pb.p + 1), np.asarray(param).ndim == 1)
+    return res
+
+
+def _kf(OdeTraj, param, gridsize, x_r, x_i, model, transX, chol):
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    times = O[:, 0] if single else O[0, :, 0]
+    pb = problem_for(times, x_r, x_i, gridsize, 0.0, None, model, transX)
+    Of, _ = pb._mats(O, (len(times), pb.p + 1))
+    P = _pad_param(pb, param)
+    B = Of.shape[0]
+    cube = pb.p * pb.p * pb.k
+    A, S, st = np.empty((B, cube)), np.empty((B, cube)), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_kf_param(pb.h, B, _ptr(Of), _ptr(P), int(chol), _ptr(A), _ptr(S), _ptr(st)), "lna_kf_param")
+    if chol and np.any(st & ST_CHOL_FAIL):
+        raise ValueError(CHOL_MSG)
+    return {"A": pb._unmats(A, (pb.p, pb.p, pb.k), single), "Sigma": pb._unmats(S, (pb.p, pb.p, pb.k), single)}
+
+
+def KF_param(OdeTraj, param, gridsize, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    """LNA_functional.cpp:603-634"""
+    return _kf(OdeTraj, param, gridsize, x_r, x_i, model, transX, 0)
+
+
+def KF_param_chol(OdeTraj, param, gridsize, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    """LNA_functional.cpp:638-670 (the `Sigma` slot holds L)."""
+    return _kf(OdeTraj, param, gridsize, x_r, x_i, model, transX, 1)
+
+
+def SigmaF(Traj_par, param, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    """LNA_functional.cpp:536-599: one LNA interval = KF_param with gridsize = nrow(Traj_par).
+    The rows' own times are used (a virtual closing row is appended, it is never read)."""
+    T = np.asarray(Traj_par, dtype=np.float64)
+    g = T.shape[0]
+    last = T[-1].copy()
+    last[0] = T[-1, 0] + (T[1, 0] - T[0, 0])
+    res = _kf(np.vstack([T, last]), param, g, x_r, x_i, model, transX, 0)
+    return {"expF": res["A"][:, :, 0], "Sigma": res["Sigma"][:, :, 0]}
+
+
+def Ode_Coarse_Slicer(Ode_thin, gridsize):
+    """LNA_functional.cpp:1179-1188"""
+    O = np.asarray(Ode_thin, dtype=np.float64)
+    p = O.shape[1] - 1
+    model = "SIR" if p == 2 else "SEIR"
+    pb = problem_for(O[:, 0], [1.0], [0, 2 if p == 2 else 3, 0, 1], gridsize, 0.0, None, model)
+    Of, _ = pb._mats(O, (O.shape[0], p + 1))
+    out = np.empty((1, pb.nrow * (p + 1)))
+    check(_lib.lib().lna_ode_coarse_slicer(pb.h, 1, _ptr(Of), _ptr(out)), "lna_ode_coarse_slicer")
+    return pb._unmats(out, (pb.nrow, p + 1), True)
+
+
+def New_Param_List(param, initial, gridsize, t, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
+    """LNA_functional.cpp:1191-1208 -> {FT:{A,Sigma(=L)}, Ode, betaN}; raises on Cholesky failure."""
+    pb = problem_for(t, x_r, x_i, gridsize, 0.0, None, model, transX)
+    res = pb.full_loglik(_pad_param(pb, param) if np.asarray(param).ndim > 1 else _pad_param(pb, param)[0], initial,
+                         None, want=("FT", "Ode", "betaN"))
+    if np.any(np.asarray(res["status"]) & ST_CHOL_FAIL):
+        raise ValueError(CHOL_MSG)
+    return {"FT": res["FT"], "Ode": res["Ode"], "betaN": res["betaN"]}
+
+
+def _traj_problem(OdeTraj, p):
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    times = O[:, 0] if O.ndim == 2 else O[0, :, 0]
+    model = "SIR" if p == 2 else "SEIR"
+    return problem_for(times, [1.0], [0, 2 if p == 2 else 3, 0, 1], 1, 0.0, None, model)
+
+
+def TransformTraj(OdeTraj, OriginLatent, Filter_NC):
+    """LNA_functional.cpp:877-900"""
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    p = O.shape[-1] - 1
+    pb = _traj_problem(O, p)
+    nrow = O.shape[-2]
+    Of, _ = pb._mats(O, (nrow, p + 1))
+    Ef, _ = pb._mats(OriginLatent, (nrow - 1, p))
+    Af, _ = pb._mats(Filter_NC["A"], (p, p, nrow - 1))
+    Lf, _ = pb._mats(Filter_NC["Sigma"], (p, p, nrow - 1))
+    out = np.empty_like(Of)
+    check(_lib.lib().lna_transform_traj(pb.h, Of.shape[0], _ptr(Of), _ptr(Ef), _ptr(Af), _ptr(Lf), _ptr(out)),
+          "lna_transform_traj")
+    return pb._unmats(out, (nrow, p + 1), single)
+
+
+def Traj_sim_general_noncentral(OdeTraj, Filter_NC, t_correct, *, normals):
+    """LNA_functional.cpp:824-872 with supplied normals (k*p, step-major)."""
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    p, nrow = O.shape[-1] - 1, O.shape[-2]
+    model = "SIR" if p == 2 else "SEIR"
+    pb = problem_for(O[:, 0], [1.0], [0, 2 if p == 2 else 3, 0, 1], 1, t_correct, None, model)
+    Of, _ = pb._mats(O, (nrow, p + 1))
+    Af, _ = pb._mats(Filter_NC["A"], (p, p, nrow - 1))
+    Lf, _ = pb._mats(Filter_NC["Sigma"], (p, p, nrow - 1))
+    nrm = _d(normals).reshape(1, -1)
+    traj, origin = np.empty_like(Of), np.empty((1, (nrow - 1) * p))
+    lm, lo = np.empty(1), np.empty(1)
+    check(_lib.lib().lna_traj_sim_noncentral(pb.h, 1, _ptr(Of), _ptr(Af), _ptr(Lf), _ptr(nrm), _ptr(traj), _ptr(origin),
+                                             _ptr(lm), _ptr(lo)), "lna_traj_sim_noncentral")
+    return {"SimuTraj": pb._unmats(traj, (nrow, p + 1), True), "OriginTraj": pb._unmats(origin, (nrow - 1, p), True),
+            "logMultiNorm": float(lm[0]), "logOrigin": float(lo[0])}
+
+
+def volz_loglik_nh2(init, f1, betaN, t_correct, index, transX="standard"):
+    """LNA_functional.cpp:1119-1176 (literal per-event kernel)."""
+    F = np.asarray(f1, dtype=np.float64)
+    single = F.ndim == 2
+    p, nrow = F.shape[-1] - 1, F.shape[-2]
+    times = F[:, 0] if single else F[0, :, 0]
+    ix = _xi(index)
+    model = "SIR" if p == 2 else "SEIR"
+    pb = problem_for(times, [1.0], [0, 2 if p == 2 else 3, ix[0], ix[1]], 1, t_correct, init, model, transX)
+    Ff, _ = pb._mats(F, (nrow, p + 1))
+    b = _d(betaN).reshape(Ff.shape[0], nrow)
+    ll, st = np.empty(Ff.shape[0]), np.zeros(Ff.shape[0], dtype=np.int32)
+    check(_lib.lib().lna_volz_loglik_nh2(pb.h, Ff.shape[0], _ptr(Ff), _ptr(b), _ptr(ll), _ptr(st)),
+          "lna_volz_loglik_nh2")
+    return float(ll[0]) if single else ll
+
+
+def _kingman(init, f1, t_correct, lam, col, take_log):
+    F = np.asarray(f1, dtype=np.float64)
+    single = F.ndim == 2
+    p, nrow = F.shape[-1] - 1, F.shape[-2]
+    times = F[:, 0] if single else F[0, :, 0]
+    model = "SIR" if p == 2 else "SEIR"
+    pb = problem_for(times, [1.0], [0, 2 if p == 2 else 3, 0, 1], 1, t_correct, init, model)
+    Ff, _ = pb._mats(F, (nrow, p + 1))
+    lamv = np.ascontiguousarray(np.broadcast_to(_d(lam).ravel(), (Ff.shape[0],)))
+    ll = np.empty(Ff.shape[0])
+    check(_lib.lib().lna_coal_loglik(pb.h, Ff.shape[0], _ptr(Ff), _ptr(lamv), int(col), int(take_log), _ptr(ll)),
+          "lna_coal_loglik")
+    return float(ll[0]) if single else ll
+
+
+def coal_loglik3(init, f1, t_correct, lam, Index, transX="standard"):
+    """LNA_functional.cpp:1016-1054"""
+    return _kingman(init, f1, t_correct, lam, Index + 1, transX == "standard")
+
+
+def coal_loglik(init, f1, t_correct, lam, gridsize=1, transX="standard"):
+    """SIR_phylodyn.cpp:436-468 (f1[,3] already holds log I)"""
+    return _kingman(init, f1, t_correct, lam, 2, False)
+
+
+def Update_Param(param, initial, t, OriginTraj, x_r, x_i, init, gridsize, coal_log=0.0, prior_proposal_offset=0.0,
+                 t_correct=0.0, transP="changepoint", model="SIR", transX="standard", volz=True, *, unif):
+    """LNA_functional.cpp:1212-1243; `unif` replaces the single R::runif(0,1) draw."""
+    pb = problem_for(t, x_r, x_i, gridsize, t_correct, init, model, transX)
+    P, single = pb._batch(param, pb.npt)
+    B = P.shape[0]
+    I, _ = pb._batch(initial, pb.p)
+    E, _ = pb._mats(OriginTraj, (pb.k, pb.p))
+    bc = lambda a, n: np.ascontiguousarray(np.broadcast_to(_d(a).reshape(-1, n) if n > 1 else _d(a).ravel(),
+                                                           (B, n) if n > 1 else (B,)))
+    I, E = bc(I, pb.p), bc(E, pb.k * pb.p)
+    cl0, off, u = bc(coal_log, 1), bc(prior_proposal_offset, 1), bc(unif, 1)
+    p, k, nrow = pb.p, pb.k, pb.nrow
+    acc, cl, st = np.zeros(B, dtype=np.int32), np.empty(B), np.zeros(B, dtype=np.int32)
+    A, Lc = np.empty((B, p * p * k)), np.empty((B, p * p * k))
+    ode, bn, lat = np.empty((B, nrow * (p + 1))), np.empty((B, nrow)), np.empty((B, nrow * (p + 1)))
+    check(_lib.lib().lna_update_param(pb.h, B, _ptr(P), _ptr(I), _ptr(E), _ptr(cl0), _ptr(off), _ptr(u), _ptr(acc),
+                                      _ptr(cl), _ptr(st), _ptr(A), _ptr(Lc), _ptr(ode), _ptr(bn), _ptr(lat)),
+          "lna_update_param")
+    if single:
+        if st[0] & ST_CHOL_FAIL:
+            raise ValueError(CHOL_MSG)
+        if not acc[0]:
+            return {"accept": False, "coalLog_proposed": float(cl[0])}
+        return {"accept": True, "FT": {"A": pb._unmats(A, (p, p, k), True), "Sigma": pb._unmats(Lc, (p, p, k), True)},
+                "Ode": pb._unmats(ode, (nrow, p + 1), True), "betaN": bn[0], "coalLog": float(cl[0]),
+                "LatentTraj": pb._unmats(lat, (nrow, p + 1), True)}
+    return {"accept": acc.astype(bool), "status": st, "coalLog": cl,
+            "FT": {"A": pb._unmats(A, (p, p, k), False), "Sigma": pb._unmats(Lc, (p, p, k), False)},
+            "Ode": pb._unmats(ode, (nrow, p + 1), False), "betaN": bn, "LatentTraj": pb._unmats(lat, (nrow, p + 1), False)}

@@ -1,0 +1,714 @@
+// lna_capi.cu -- host library + C ABI (include/lnaphylodyn_b200.h) over the sm_100a kernels.
+//
+// The host side mirrors the reference's Rcpp layer for the hot path (src/RcppExports.cpp): each
+// entry point validates its arguments, stages host buffers into HBM when given host pointers,
+// launches the kernels on the problem's stream and reports errors through lna_last_error()
+// instead of C++ exceptions (BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:11-19).
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lnaphylodyn_b200.h"
+#include "lna_kernels.cuh"
+#include "lna_eslice.cuh"
+
+using namespace lna;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CKP(call)                                                                            \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));        \
+            return nullptr;                                                                  \
+        }                                                                                    \
+    } while (0)
+
+// grow-only device scratch slots used by the host-pointer entry points
+struct Scratch {
+    std::vector<void *> ptr;
+    std::vector<size_t> cap;
+    void *get(size_t slot, size_t bytes) {
+        if (slot >= ptr.size()) {
+            ptr.resize(slot + 1, nullptr);
+            cap.resize(slot + 1, 0);
+        }
+        if (cap[slot] < bytes) {
+            if (ptr[slot]) cudaFree(ptr[slot]);
+            ptr[slot] = nullptr;
+            size_t want = std::max(bytes, cap[slot] * 2);
+            if (cudaMalloc(&ptr[slot], want) != cudaSuccess) {
+                cap[slot] = 0;
+                return nullptr;
+            }
+            cap[slot] = want;
+        }
+        return ptr[slot];
+    }
+    void release() {
+        for (void *p : ptr)
+            if (p) cudaFree(p);
+        ptr.clear();
+        cap.clear();
+    }
+};
+
+struct lna_problem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevProb dp{};
+    int sm_count = 0;
+    std::vector<double> times, x_r;
+    std::vector<int> chidx;
+    std::vector<double> dt_seg, cellCD, cellY;
+    std::vector<int> cellCnt, evStart;
+    std::vector<void *> owned;
+    Scratch scratch;
+    int64_t launches = 0;
+    size_t tab_bytes = 0;
+};
+
+template <class T>
+static T *dev_upload(lna_problem *pb, const T *h, size_t n) {
+    T *d = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) return nullptr;
+    pb->owned.push_back(d);
+    if (h && cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return d;
+}
+
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int lna_abi_version(void) { return LNA_ABI_VERSION; }
+extern "C" const char *lna_last_error(void) { return g_err.c_str(); }
+
+extern "C" int lna_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int lna_shard(int64_t B, int rank, int nranks, int64_t *begin, int64_t *end) {
+    if (nranks <= 0 || rank < 0 || rank >= nranks || B < 0) return fail("lna_shard: bad arguments");
+    const int64_t q = B / nranks, r = B % nranks;
+    *begin = rank * q + std::min<int64_t>(rank, r);
+    *end = *begin + q + (rank < r ? 1 : 0);
+    return 0;
+}
+
+extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *init, int device) {
+    if (!cfg || !cfg->times || !cfg->x_r) {
+        fail("lna_problem_create: null cfg/times/x_r");
+        return nullptr;
+    }
+    if (cfg->model != LNA_MODEL_SIR && cfg->model != LNA_MODEL_SEIR) {
+        fail("lna_problem_create: unsupported model %d (SIR=0, SEIR=1)", cfg->model);
+        return nullptr;
+    }
+    if (cfg->transX != LNA_TRANSX_STANDARD) {
+        fail("lna_problem_create: only transX=\"standard\" is implemented on the GPU path");
+        return nullptr;
+    }
+    if (cfg->nt < 2 || cfg->gridsize < 1 || cfg->nch < 0 || cfg->nparam < 2) {
+        fail("lna_problem_create: bad sizes (nt=%d gridsize=%d nch=%d nparam=%d)", cfg->nt, cfg->gridsize, cfg->nch,
+             cfg->nparam);
+        return nullptr;
+    }
+    int ndev = lna_device_count();
+    if (ndev <= 0) {
+        fail("lna_problem_create: no CUDA device available (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail("lna_problem_create: device %d out of range (%d devices)", device, ndev);
+        return nullptr;
+    }
+    CKP(cudaSetDevice(device));
+    lna_problem *pb = new lna_problem();
+    pb->device = device;
+    cudaDeviceGetAttribute(&pb->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&pb->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail("cudaStreamCreate failed");
+        delete pb;
+        return nullptr;
+    }
+    pb->own_stream = true;
+    DevProb &P = pb->dp;
+    P.model = cfg->model;
+    P.p = cfg->model == LNA_MODEL_SIR ? 2 : 3;
+    P.nch = cfg->nch;
+    P.nparam = cfg->nparam;
+    P.iR0 = cfg->iR0;
+    P.iGamma = cfg->iGamma;
+    P.idxS = cfg->iR0;
+    P.idxI = cfg->iGamma;
+    P.g = cfg->gridsize;
+    P.nt = cfg->nt;
+    P.k = (cfg->nt - 1) / cfg->gridsize;
+    P.nrow = cfg->nt / cfg->gridsize + 1;
+    P.npt = cfg->nparam + cfg->nch + 1;
+    P.N = cfg->x_r[0];
+    P.t_correct = cfg->t_correct;
+    pb->times.assign(cfg->times, cfg->times + cfg->nt);
+    pb->x_r.assign(cfg->x_r, cfg->x_r + cfg->nch + 1);
+    P.dt_ode = pb->times[1] - pb->times[0];
+    if (P.nrow != P.k + 1) {
+        fail("lna_problem_create: (nt-1) must be a multiple of gridsize (nt=%d, gridsize=%d)", cfg->nt, cfg->gridsize);
+        lna_problem_destroy(pb);
+        return nullptr;
+    }
+    // change point j applies from the first fine index whose time is >= cht_j; the reference's scan
+    // stops at the first cht_j > t, hence the running max (param_transform, LNA_functional.cpp:77-83)
+    pb->chidx.resize(P.nch);
+    int run = 0;
+    for (int j = 0; j < P.nch; ++j) {
+        const double c = pb->x_r[j + 1];
+        int idx = (int)(std::lower_bound(pb->times.begin(), pb->times.end(), c) - pb->times.begin());
+        run = std::max(run, idx);
+        pb->chidx[j] = run;
+    }
+    pb->dt_seg.resize(P.k);
+    for (int i = 0; i < P.k; ++i) pb->dt_seg[i] = pb->times[(size_t)i * P.g + 1] - pb->times[(size_t)i * P.g];
+    // Lrow: first coarse row with time >= t_correct, capped (volz_loglik_nh2, LNA_functional.cpp:1125-1129)
+    int L = 0;
+    while (pb->times[(size_t)L * P.g] < P.t_correct) {
+        L++;
+        if (L == P.nrow - 1) break;
+    }
+    P.Lrow = L;
+    P.has_init = 0;
+    P.n0 = 0;
+    P.E = 0;
+    if (init) {
+        if (init->ng < 1 || !init->C || !init->D || !init->y || !init->gridrep) {
+            fail("lna_problem_create: incomplete lna_init");
+            lna_problem_destroy(pb);
+            return nullptr;
+        }
+        P.n0 = init->ng - 1;
+        P.E = init->E;
+        pb->cellCnt.resize(P.n0);
+        pb->evStart.assign(P.n0 + 1, 0);
+        for (int i = 0; i < P.n0; ++i) {
+            pb->cellCnt[i] = (int)std::llround(init->gridrep[i]);
+            pb->evStart[i + 1] = pb->evStart[i] + pb->cellCnt[i];
+        }
+        if (pb->evStart[P.n0] > init->E) {
+            fail("lna_problem_create: sum(gridrep[0..ng-2]) = %d exceeds E = %d", pb->evStart[P.n0], init->E);
+            lna_problem_destroy(pb);
+            return nullptr;
+        }
+        if (P.Lrow - P.n0 + 1 < 0 || P.n0 > P.nrow - 1) {
+            fail("lna_problem_create: genealogy needs %d grid cells before t_correct but only %d coarse rows exist",
+                 P.n0, P.Lrow + 1);
+            lna_problem_destroy(pb);
+            return nullptr;
+        }
+        P.has_init = 1;
+    }
+    P.chidx = dev_upload(pb, pb->chidx.data(), pb->chidx.size());
+    P.dt_seg = dev_upload(pb, pb->dt_seg.data(), pb->dt_seg.size());
+    P.times = dev_upload(pb, pb->times.data(), pb->times.size());
+    P.cht = dev_upload(pb, pb->x_r.data() + 1, (size_t)P.nch);
+    if (!P.chidx || !P.dt_seg || !P.times || !P.cht) {
+        fail("lna_problem_create: device allocation failed");
+        lna_problem_destroy(pb);
+        return nullptr;
+    }
+    if (P.has_init) {
+        P.evC = dev_upload(pb, init->C, (size_t)init->E);
+        P.evD = dev_upload(pb, init->D, (size_t)init->E);
+        P.evY = dev_upload(pb, init->y, (size_t)init->E);
+        P.evStart = dev_upload(pb, pb->evStart.data(), pb->evStart.size());
+        P.cellCnt = dev_upload(pb, pb->cellCnt.data(), pb->cellCnt.size());
+        double *cd = dev_upload<double>(pb, nullptr, (size_t)P.n0), *yy = dev_upload<double>(pb, nullptr, (size_t)P.n0);
+        if (!P.evC || !P.evD || !P.evY || !P.evStart || !P.cellCnt || !cd || !yy) {
+            fail("lna_problem_create: device allocation failed");
+            lna_problem_destroy(pb);
+            return nullptr;
+        }
+        if (P.n0 > 0) {
+            k_cell_sums<<<nblk((long long)P.n0 * 32, 128), 128, 0, pb->stream>>>(P.n0, P.evStart, P.evC, P.evD, P.evY, cd,
+                                                                                   yy);
+            pb->launches++;
+        }
+        pb->cellCD.resize(P.n0);
+        pb->cellY.resize(P.n0);
+        cudaError_t e = cudaStreamSynchronize(pb->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(pb->cellCD.data(), cd, sizeof(double) * P.n0, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(pb->cellY.data(), yy, sizeof(double) * P.n0, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            fail("lna_problem_create: cell-sum kernel failed: %s", cudaGetErrorString(e));
+            lna_problem_destroy(pb);
+            return nullptr;
+        }
+        P.cellCD = cd;
+        P.cellY = yy;
+    }
+    pb->tab_bytes = tables_bytes(P.nch, P.k, P.n0);
+    return pb;
+}
+
+extern "C" void lna_problem_destroy(lna_problem *pb) {
+    if (!pb) return;
+    cudaSetDevice(pb->device);
+    if (pb->stream) cudaStreamSynchronize(pb->stream);
+    for (void *p : pb->owned) cudaFree(p);
+    pb->scratch.release();
+    if (pb->own_stream && pb->stream) cudaStreamDestroy(pb->stream);
+    delete pb;
+}
+
+extern "C" int lna_problem_sync(lna_problem *pb) {
+    if (!pb) return fail("null problem");
+    CK(cudaStreamSynchronize(pb->stream));
+    return 0;
+}
+extern "C" void *lna_problem_stream(lna_problem *pb) { return pb ? (void *)pb->stream : nullptr; }
+extern "C" int lna_problem_set_stream(lna_problem *pb, void *s) {
+    if (!pb) return fail("null problem");
+    if (pb->own_stream && pb->stream) {
+        cudaStreamSynchronize(pb->stream);
+        cudaStreamDestroy(pb->stream);
+    }
+    pb->stream = (cudaStream_t)s;
+    pb->own_stream = false;
+    return 0;
+}
+extern "C" int lna_problem_dims(const lna_problem *pb, int *p, int *k, int *nrow, int *npt) {
+    if (!pb) return fail("null problem");
+    if (p) *p = pb->dp.p;
+    if (k) *k = pb->dp.k;
+    if (nrow) *nrow = pb->dp.nrow;
+    if (npt) *npt = pb->dp.npt;
+    return 0;
+}
+extern "C" int64_t lna_problem_launch_count(const lna_problem *pb) { return pb ? pb->launches : 0; }
+extern "C" int lna_problem_cell_sums(const lna_problem *pb, double *cd, double *yy, double *cnt) {
+    if (!pb || !pb->dp.has_init) return fail("lna_problem_cell_sums: problem has no genealogy");
+    for (int i = 0; i < pb->dp.n0; ++i) {
+        if (cd) cd[i] = pb->cellCD[i];
+        if (yy) yy[i] = pb->cellY[i];
+        if (cnt) cnt[i] = pb->cellCnt[i];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// staging helpers for the host-pointer entry points
+// ------------------------------------------------------------------------------------------------
+struct Stage {
+    lna_problem *pb;
+    size_t slot = 0;
+    bool ok = true;
+    explicit Stage(lna_problem *p) : pb(p) { cudaSetDevice(p->device); }
+    template <class T>
+    T *in(const T *h, size_t n) {  // upload (nullptr stays nullptr)
+        if (!h) return nullptr;
+        T *d = (T *)pb->scratch.get(slot++, std::max<size_t>(n, 1) * sizeof(T));
+        if (!d || cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, pb->stream) != cudaSuccess) ok = false;
+        return d;
+    }
+    template <class T>
+    T *out(const T *h, size_t n) {  // device buffer for an output the caller asked for
+        if (!h) return nullptr;
+        T *d = (T *)pb->scratch.get(slot++, std::max<size_t>(n, 1) * sizeof(T));
+        if (!d) ok = false;
+        return d;
+    }
+    template <class T>
+    T *tmp(size_t n) {
+        T *d = (T *)pb->scratch.get(slot++, std::max<size_t>(n, 1) * sizeof(T));
+        if (!d) ok = false;
+        return d;
+    }
+    template <class T>
+    void back(T *h, const T *d, size_t n) {
+        if (!h || !d) return;
+        if (cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, pb->stream) != cudaSuccess) ok = false;
+    }
+    int finish(const char *what) {
+        cudaError_t e = cudaStreamSynchronize(pb->stream);
+        if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+        if (!ok) {
+            cudaError_t l = cudaGetLastError();
+            return fail("%s: device staging failed (%s)", what, cudaGetErrorString(l));
+        }
+        return 0;
+    }
+};
+
+static int launch_check(lna_problem *pb, const char *what) {
+    pb->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+static View item_view(const double *d, long long n) { return View{d, n, 1}; }
+static OutView item_out(double *d, long long n) { return OutView{d, n, 1}; }
+
+// Pick the block size so that small batches still spread over all SMs.
+static int pick_block(const lna_problem *pb, long long B) {
+    const long long per_sm = (B + pb->sm_count - 1) / std::max(pb->sm_count, 1);
+    if (per_sm >= 256) return 128;
+    if (per_sm >= 64) return 64;
+    return 32;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FULL evaluation
+// ------------------------------------------------------------------------------------------------
+static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                                const double *origin, double *coalLog, int32_t *status, double *A, double *L,
+                                double *ode, double *betaN, double *latent) {
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    if (!param || !initial) return fail("lna_full_loglik: param/initial must not be null");
+    if (coalLog && !P.has_init) return fail("lna_full_loglik: problem was created without a genealogy");
+    const int p = P.p;
+    FullOut out{item_out(A, (long long)p * p * P.k), item_out(L, (long long)p * p * P.k),
+                item_out(ode, (long long)P.nrow * (p + 1)), item_out(betaN, P.nrow),
+                item_out(latent, (long long)P.nrow * (p + 1))};
+    const bool store = A || L || ode || betaN || latent;
+    const int block = pick_block(pb, B);
+    const unsigned grid = nblk(B, block);
+    const View vp = item_view(param, P.npt), vi = item_view(initial, p), vo = item_view(origin, (long long)P.k * p);
+#define LAUNCH(MODEL, STORE)                                                                                     \
+    k_full_loglik<MODEL, STORE><<<grid, block, pb->tab_bytes, pb->stream>>>(P, B, vp, vi, vo, out, coalLog, status)
+    if (P.model == LNA_MODEL_SIR) {
+        if (store) LAUNCH(0, true);
+        else LAUNCH(0, false);
+    } else {
+        if (store) LAUNCH(1, true);
+        else LAUNCH(1, false);
+    }
+#undef LAUNCH
+    return launch_check(pb, "k_full_loglik");
+}
+
+extern "C" int lna_full_loglik_dev(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                                   const double *OriginTraj, double *coalLog, int32_t *status, double *Acube,
+                                   double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj) {
+    if (!pb) return fail("null problem");
+    cudaSetDevice(pb->device);
+    return full_loglik_dev_impl(pb, B, param, initial, OriginTraj, coalLog, status, Acube, Lcube, Ode_coarse, betaN,
+                                LatentTraj);
+}
+
+extern "C" int lna_full_loglik(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                               const double *OriginTraj, double *coalLog, int32_t *status, double *Acube,
+                               double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t p = P.p, k = P.k, nrow = P.nrow, nB = (size_t)B;
+    Stage s(pb);
+    const double *dpar = s.in(param, nB * P.npt), *dini = s.in(initial, nB * p), *dor = s.in(OriginTraj, nB * k * p);
+    double *dcl = s.out(coalLog, nB);
+    int32_t *dst = s.out(status, nB);
+    double *dA = s.out(Acube, nB * p * p * k), *dL = s.out(Lcube, nB * p * p * k);
+    double *dode = s.out(Ode_coarse, nB * nrow * (p + 1)), *dbn = s.out(betaN, nB * nrow);
+    double *dlat = s.out(LatentTraj, nB * nrow * (p + 1));
+    if (!s.ok) return fail("lna_full_loglik: device staging failed");
+    if (full_loglik_dev_impl(pb, B, dpar, dini, dor, dcl, dst, dA, dL, dode, dbn, dlat)) return -1;
+    s.back(coalLog, dcl, nB);
+    s.back(status, dst, nB);
+    s.back(Acube, dA, nB * p * p * k);
+    s.back(Lcube, dL, nB * p * p * k);
+    s.back(Ode_coarse, dode, nB * nrow * (p + 1));
+    s.back(betaN, dbn, nB * nrow);
+    s.back(LatentTraj, dlat, nB * nrow * (p + 1));
+    return s.finish("lna_full_loglik");
+}
+
+extern "C" int lna_new_param_list(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                                  double *Acube, double *Lcube, double *Ode_coarse, double *betaN, int32_t *status) {
+    return lna_full_loglik(pb, B, param, initial, nullptr, nullptr, status, Acube, Lcube, Ode_coarse, betaN, nullptr);
+}
+
+extern "C" int lna_update_param(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                                const double *OriginTraj, const double *coal_log, const double *offset,
+                                const double *unif, int32_t *accept, double *coalLog_new, int32_t *status,
+                                double *Acube, double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (!coal_log || !unif || !accept) return fail("lna_update_param: coal_log/unif/accept must not be null");
+    const DevProb &P = pb->dp;
+    const size_t p = P.p, k = P.k, nrow = P.nrow, nB = (size_t)B;
+    Stage s(pb);
+    const double *dpar = s.in(param, nB * P.npt), *dini = s.in(initial, nB * p), *dor = s.in(OriginTraj, nB * k * p);
+    const double *dcl0 = s.in(coal_log, nB), *doff = s.in(offset, nB), *du = s.in(unif, nB);
+    double *dcl = s.tmp<double>(nB);
+    int32_t *dst = s.tmp<int32_t>(nB), *dacc = s.tmp<int32_t>(nB);
+    double *dA = s.out(Acube, nB * p * p * k), *dL = s.out(Lcube, nB * p * p * k);
+    double *dode = s.out(Ode_coarse, nB * nrow * (p + 1)), *dbn = s.out(betaN, nB * nrow);
+    double *dlat = s.out(LatentTraj, nB * nrow * (p + 1));
+    if (!s.ok) return fail("lna_update_param: device staging failed");
+    if (full_loglik_dev_impl(pb, B, dpar, dini, dor, dcl, dst, dA, dL, dode, dbn, dlat)) return -1;
+    k_mh_accept<<<nblk(B, 128), 128, 0, pb->stream>>>(B, dcl, dcl0, doff, du, dst, dacc);
+    if (launch_check(pb, "k_mh_accept")) return -1;
+    s.back(accept, dacc, nB);
+    s.back(coalLog_new, dcl, nB);
+    s.back(status, dst, nB);
+    s.back(Acube, dA, nB * p * p * k);
+    s.back(Lcube, dL, nB * p * p * k);
+    s.back(Ode_coarse, dode, nB * nrow * (p + 1));
+    s.back(betaN, dbn, nB * nrow);
+    s.back(LatentTraj, dlat, nB * nrow * (p + 1));
+    return s.finish("lna_update_param");
+}
+
+// ------------------------------------------------------------------------------------------------
+// mirrors of the individual exports
+// ------------------------------------------------------------------------------------------------
+extern "C" int lna_betaTs(lna_problem *pb, int64_t B, const double *param, const double *times, int m,
+                          double *betas) {
+    if (!pb) return fail("null problem");
+    if (B <= 0 || m <= 0) return 0;
+    const size_t nB = (size_t)B;
+    Stage s(pb);
+    const double *dpar = s.in(param, nB * pb->dp.npt), *dt = s.in(times, (size_t)m);
+    double *db = s.out(betas, nB * m);
+    if (!s.ok || !dpar || !dt || !db) return fail("lna_betaTs: bad arguments / staging failed");
+    k_betaTs<<<nblk(B, 128), 128, 0, pb->stream>>>(pb->dp, B, item_view(dpar, pb->dp.npt), dt, m, db);
+    if (launch_check(pb, "k_betaTs")) return -1;
+    s.back(betas, db, nB * m);
+    return s.finish("lna_betaTs");
+}
+
+extern "C" int lna_param_transform(lna_problem *pb, int64_t B, const double *t, const double *param,
+                                   double *param2) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const size_t nB = (size_t)B, npt = pb->dp.npt;
+    Stage s(pb);
+    const double *dt = s.in(t, nB), *dpar = s.in(param, nB * npt);
+    double *d2 = s.out(param2, nB * npt);
+    if (!s.ok || !dt || !dpar || !d2) return fail("lna_param_transform: bad arguments / staging failed");
+    k_param_transform<<<nblk(B, 128), 128, 0, pb->stream>>>(pb->dp, B, dt, item_view(dpar, npt), d2);
+    if (launch_check(pb, "k_param_transform")) return -1;
+    s.back(param2, d2, nB * npt);
+    return s.finish("lna_param_transform");
+}
+
+extern "C" int lna_ode_rk45(lna_problem *pb, int64_t B, const double *initial, const double *param,
+                            double *OdeTraj) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, p = P.p, per = (size_t)P.nt * (p + 1);
+    Stage s(pb);
+    const double *dini = s.in(initial, nB * p), *dpar = s.in(param, nB * P.npt);
+    double *dout = s.out(OdeTraj, nB * per);
+    if (!s.ok || !dini || !dpar || !dout) return fail("lna_ode_rk45: bad arguments / staging failed");
+    if (P.model == LNA_MODEL_SIR)
+        k_ode_rk45<0><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
+    else
+        k_ode_rk45<1><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
+    if (launch_check(pb, "k_ode_rk45")) return -1;
+    s.back(OdeTraj, dout, nB * per);
+    return s.finish("lna_ode_rk45");
+}
+
+extern "C" int lna_kf_param(lna_problem *pb, int64_t B, const double *OdeTraj, const double *param, int chol,
+                            double *Acube, double *Scube, int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, p = P.p, per = (size_t)P.nt * (p + 1), cube = p * p * P.k;
+    Stage s(pb);
+    const double *dtr = s.in(OdeTraj, nB * per), *dpar = s.in(param, nB * P.npt);
+    double *dA = s.tmp<double>(nB * cube), *dS = s.tmp<double>(nB * cube);
+    int32_t *dst = s.tmp<int32_t>(nB);
+    if (!s.ok || !dtr || !dpar) return fail("lna_kf_param: bad arguments / staging failed");
+    CK(cudaMemsetAsync(dst, 0, nB * sizeof(int32_t), pb->stream));
+    const long long n = (long long)B * P.k;
+    if (P.model == LNA_MODEL_SIR)
+        k_kf_param<0><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);
+    else
+        k_kf_param<1><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);
+    if (launch_check(pb, "k_kf_param")) return -1;
+    s.back(Acube, dA, nB * cube);
+    s.back(Scube, dS, nB * cube);
+    s.back(status, dst, nB);
+    return s.finish("lna_kf_param");
+}
+
+extern "C" int lna_ode_coarse_slicer(lna_problem *pb, int64_t B, const double *OdeTraj, double *Ode_coarse) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, ncol = P.p + 1;
+    Stage s(pb);
+    const double *dtr = s.in(OdeTraj, nB * P.nt * ncol);
+    double *dc = s.out(Ode_coarse, nB * P.nrow * ncol);
+    if (!s.ok || !dtr || !dc) return fail("lna_ode_coarse_slicer: bad arguments / staging failed");
+    const long long n = (long long)B * P.nrow * ncol;
+    k_coarse_slicer<<<nblk(n, 256), 256, 0, pb->stream>>>(P.nt, (int)ncol, P.g, P.nrow, B, dtr, dc);
+    if (launch_check(pb, "k_coarse_slicer")) return -1;
+    s.back(Ode_coarse, dc, nB * P.nrow * ncol);
+    return s.finish("lna_ode_coarse_slicer");
+}
+
+static int transform_impl(lna_problem *pb, int64_t B, const double *Ode, const double *eps, const double *A,
+                          const double *L, int step_major, double *traj, double *origin, double *lm, double *lo,
+                          const char *what) {
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, p = P.p, k = P.k, per = (size_t)P.nrow * (p + 1), cube = p * p * k;
+    Stage s(pb);
+    const double *dO = s.in(Ode, nB * per), *de = s.in(eps, nB * k * p), *dA = s.in(A, nB * cube), *dL = s.in(L, nB * cube);
+    double *dT = s.tmp<double>(nB * per);
+    double *dor = step_major ? s.tmp<double>(nB * k * p) : nullptr;
+    double *dlm = step_major ? s.tmp<double>(nB) : nullptr, *dlo = step_major ? s.tmp<double>(nB) : nullptr;
+    if (!s.ok || !dO || !de || !dA || !dL) return fail("%s: bad arguments / staging failed", what);
+    if (p == 2)
+        k_transform_traj<2><<<nblk(B, 128), 128, 0, pb->stream>>>((int)k, B, dO, de, dA, dL, step_major, P.t_correct, dT,
+                                                                  dor, dlm, dlo);
+    else
+        k_transform_traj<3><<<nblk(B, 128), 128, 0, pb->stream>>>((int)k, B, dO, de, dA, dL, step_major, P.t_correct, dT,
+                                                                  dor, dlm, dlo);
+    if (launch_check(pb, what)) return -1;
+    s.back(traj, dT, nB * per);
+    s.back(origin, dor, nB * k * p);
+    s.back(lm, dlm, nB);
+    s.back(lo, dlo, nB);
+    return s.finish(what);
+}
+
+extern "C" int lna_transform_traj(lna_problem *pb, int64_t B, const double *Ode_coarse, const double *OriginLatent,
+                                  const double *Acube, const double *Lcube, double *LNA_traj) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    return transform_impl(pb, B, Ode_coarse, OriginLatent, Acube, Lcube, 0, LNA_traj, nullptr, nullptr, nullptr,
+                          "lna_transform_traj");
+}
+
+extern "C" int lna_traj_sim_noncentral(lna_problem *pb, int64_t B, const double *Ode_coarse, const double *Acube,
+                                       const double *Lcube, const double *normals, double *LNA_traj,
+                                       double *OriginLatent, double *logMultiNorm, double *logOrigin) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    return transform_impl(pb, B, Ode_coarse, normals, Acube, Lcube, 1, LNA_traj, OriginLatent, logMultiNorm, logOrigin,
+                          "lna_traj_sim_noncentral");
+}
+
+static int volz_events_dev(lna_problem *pb, int64_t B, const double *traj, const double *betaN, double *ll,
+                           int32_t *st) {
+    const DevProb &P = pb->dp;
+    const int warps = 4;
+    size_t sh = sizeof(double) * 2 * warps * (size_t)P.n0;
+    const size_t ev = (size_t)P.E * (2 * sizeof(double) + sizeof(int));
+    int stage = 0;
+    if (sh + ev <= 200 * 1024) {
+        stage = 1;
+        sh += ev;
+    }
+    if (sh > 48 * 1024)
+        cudaFuncSetAttribute(k_volz_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    k_volz_events<<<nblk(B, warps), warps * 32, sh, pb->stream>>>(P, B, traj, betaN, ll, st, stage);
+    return launch_check(pb, "k_volz_events");
+}
+
+extern "C" int lna_volz_loglik_nh2(lna_problem *pb, int64_t B, const double *traj, const double *betaN,
+                                   double *loglik, int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    if (!P.has_init) return fail("lna_volz_loglik_nh2: problem was created without a genealogy");
+    const size_t nB = (size_t)B, per = (size_t)P.nrow * (P.p + 1);
+    Stage s(pb);
+    const double *dT = s.in(traj, nB * per), *db = s.in(betaN, nB * P.nrow);
+    double *dll = s.tmp<double>(nB);
+    int32_t *dst = s.tmp<int32_t>(nB);
+    if (!s.ok || !dT || !db) return fail("lna_volz_loglik_nh2: bad arguments / staging failed");
+    if (volz_events_dev(pb, B, dT, db, dll, dst)) return -1;
+    s.back(loglik, dll, nB);
+    s.back(status, dst, nB);
+    return s.finish("lna_volz_loglik_nh2");
+}
+
+extern "C" int lna_coal_loglik(lna_problem *pb, int64_t B, const double *traj, const double *lambda, int col,
+                               int take_log, double *loglik) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    if (!P.has_init) return fail("lna_coal_loglik: problem was created without a genealogy");
+    if (col < 1 || col > P.p) return fail("lna_coal_loglik: col must be a state column 1..p");
+    const size_t nB = (size_t)B, per = (size_t)P.nrow * (P.p + 1);
+    Stage s(pb);
+    const double *dT = s.in(traj, nB * per), *dl = s.in(lambda, nB);
+    double *dll = s.tmp<double>(nB);
+    if (!s.ok || !dT || !dl) return fail("lna_coal_loglik: bad arguments / staging failed");
+    k_kingman<<<nblk(B, 4), 128, 0, pb->stream>>>(P, B, dT, dl, col, take_log, dll);
+    if (launch_check(pb, "k_kingman")) return -1;
+    s.back(loglik, dll, nB);
+    return s.finish("lna_coal_loglik");
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak microbenchmark
+// ------------------------------------------------------------------------------------------------
+extern "C" double lna_measure_fp64_peak(int device, int iters) {
+    if (lna_device_count() <= device || device < 0) {
+        fail("lna_measure_fp64_peak: no such device");
+        return -1.0;
+    }
+    cudaSetDevice(device);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    double *sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+    const int block = 256, grid = sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_fp64_peak<<<grid, block>>>(iters / 8 + 1, sink);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_fp64_peak<<<grid, block>>>(iters, sink);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * (double)block * (double)grid;
+        best = std::max(best, flops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
+#include "lna_capi_eslice.inl"

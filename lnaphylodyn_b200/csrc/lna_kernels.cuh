@@ -1,0 +1,451 @@
+// lna_kernels.cuh -- __global__ kernels of the LNA / coalescent path (sm_100a).  See lna_device.cuh.
+#pragma once
+#include "lna_device.cuh"
+
+namespace lna {
+
+// ================================================================================================
+// HOT KERNEL: one FULL evaluation per thread (New_Param_List -> TransformTraj -> volz_loglik_nh2,
+// reference LNA_functional.cpp:1217-1226), item-major inputs.
+// ================================================================================================
+template <int kModel, bool kStore>
+__global__ void __launch_bounds__(128)
+k_full_loglik(DevProb P, long long B, View param, View initial, View origin, FullOut out, double *coalLog,
+              int *status) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables T = stage_tables(P, smem);
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int st = 0;
+    double ll;
+    ChFromParam chs{param, b, P.nparam};
+    if (kModel == 0) {
+        const double R0 = param.at(b, P.iR0), gam = param.at(b, 1);
+        if (origin.ok()) {
+            EpsFromView eps{origin, b, P.k};
+            sir_full_eval<kStore>(P, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
+        } else {
+            EpsZero eps;
+            sir_full_eval<kStore>(P, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
+        }
+    } else {
+        const double R0 = param.at(b, P.iR0), mu = param.at(b, 1), gam = param.at(b, 2);
+        if (origin.ok()) {
+            EpsFromView eps{origin, b, P.k};
+            seir_full_eval<kStore>(P, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
+                                   initial.at(b, 2), out, b, ll, st);
+        } else {
+            EpsZero eps;
+            seir_full_eval<kStore>(P, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
+                                   initial.at(b, 2), out, b, ll, st);
+        }
+    }
+    if (coalLog) coalLog[b] = ll;
+    if (status) status[b] = st;
+}
+
+// MH decision of Update_Param (LNA_functional.cpp:1228-1241) on top of a finished FULL evaluation.
+__global__ void k_mh_accept(long long B, const double *coalLog_new, const double *coal_log, const double *offset,
+                            const double *unif, const int *status, int *accept) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double a = coalLog_new[b] - coal_log[b] + (offset ? offset[b] : 0.0);
+    // a Cholesky failure is an exception in the reference: the R wrapper's tryCatch keeps the old state
+    accept[b] = (!(status[b] & ST_CHOL_FAIL) && log(unif[b]) < a) ? 1 : 0;
+}
+
+// ================================================================================================
+// Per-genealogy precompute: segmented reduction of the sorted events into per-cell sums.
+// One warp per cell, lanes stride over the cell's events, shuffle-reduce.
+// ================================================================================================
+__global__ void k_cell_sums(int n0, const int *evStart, const double *C, const double *D, const double *y,
+                            double *cellCD, double *cellY) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n0) return;
+    double cd = 0.0, yy = 0.0;
+    for (int e = evStart[warp] + lane; e < evStart[warp + 1]; e += 32) {
+        cd = fma(C[e], D[e], cd);
+        yy += y[e];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cd += __shfl_xor_sync(0xffffffffu, cd, o);
+        yy += __shfl_xor_sync(0xffffffffu, yy, o);
+    }
+    if (lane == 0) {
+        cellCD[warp] = cd;
+        cellY[warp] = yy;
+    }
+}
+
+// ================================================================================================
+// Mirrors of the individual Rcpp exports (API completeness; not the fused hot path).
+// ================================================================================================
+
+// theta0(t) per param_transform (LNA_functional.cpp:63-86): cumulative product over cht_j <= t.
+__device__ inline double beta_at(const DevProb &P, const View &param, long long b, double t) {
+    double R0 = param.at(b, P.iR0);
+    for (int i = 0; i < P.nch; ++i) {
+        if (!(P.cht[i] <= t)) break;
+        R0 *= param.at(b, P.nparam + i);
+    }
+    return R0 * param.at(b, P.iGamma) / P.N;
+}
+
+__global__ void k_betaTs(DevProb P, long long B, View param, const double *times, int m, double *betas) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    // single sweep like betaTs (LNA_functional.cpp:31-58)
+    double R0 = param.at(b, P.iR0);
+    const double gam = param.at(b, P.iGamma);
+    int i = 0;
+    for (int j = 0; j < m; ++j) {
+        while (i < P.nch && P.cht[i] <= times[j]) R0 *= param.at(b, P.nparam + i++);
+        betas[b * m + j] = R0 * gam / P.N;
+    }
+}
+
+__global__ void k_param_transform(DevProb P, long long B, const double *t, View param, double *param2) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int j = 1; j < P.npt; ++j) param2[b * P.npt + j] = param.at(b, j);
+    param2[b * P.npt] = beta_at(P, param, b, t[b]);
+}
+
+// Generic small-matrix model pieces (used by the mirrors below; the hot path has fused versions).
+template <int kModel>
+struct Model;
+template <>
+struct Model<0> {  // SIR
+    static constexpr int P = 2;
+    __device__ static void rhs(const double *x, const double *th, double *d) {
+        const double a = th[0] * x[0] * x[1];
+        d[0] = -a;
+        d[1] = a - th[1] * x[1];
+    }
+    __device__ static void F(const double *x, const double *th, double *Fm) {  // row-major Fm[r*P+c]
+        Fm[0] = -th[0] * x[1]; Fm[1] = -th[0] * x[0];
+        Fm[2] = th[0] * x[1];  Fm[3] = th[0] * x[0] - th[1];
+    }
+    __device__ static void Q(const double *x, const double *th, double *Qm) {  // A' diag(h) A, row-major
+        const double h0 = th[0] * x[0] * x[1], h1 = th[1] * x[1];
+        Qm[0] = h0;  Qm[1] = -h0;
+        Qm[2] = -h0; Qm[3] = h0 + h1;
+    }
+};
+template <>
+struct Model<1> {  // SEIR
+    static constexpr int P = 3;
+    __device__ static void rhs(const double *x, const double *th, double *d) {
+        const double a = th[0] * x[0] * x[2];
+        d[0] = -a;
+        d[1] = a - th[1] * x[1];
+        d[2] = th[1] * x[1] - th[2] * x[2];
+    }
+    __device__ static void F(const double *x, const double *th, double *Fm) {
+        Fm[0] = -th[0] * x[2]; Fm[1] = 0.0;    Fm[2] = -th[0] * x[0];
+        Fm[3] = th[0] * x[2];  Fm[4] = -th[1]; Fm[5] = th[0] * x[0];
+        Fm[6] = 0.0;           Fm[7] = th[1];  Fm[8] = -th[2];
+    }
+    __device__ static void Q(const double *x, const double *th, double *Qm) {
+        const double h0 = th[0] * x[0] * x[2], h1 = th[1] * x[1], h2 = th[2] * x[2];
+        Qm[0] = h0;  Qm[1] = -h0;     Qm[2] = 0.0;
+        Qm[3] = -h0; Qm[4] = h0 + h1; Qm[5] = -h1;
+        Qm[6] = 0.0; Qm[7] = -h1;     Qm[8] = h1 + h2;
+    }
+};
+
+// ODE_rk45 (LNA_functional.cpp:455-491): full fine trajectory, one thread per item.
+template <int kModel>
+__global__ void k_ode_rk45(DevProb P, long long B, View initial, View param, double *OdeTraj) {
+    using M = Model<kModel>;
+    constexpr int p = M::P;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double *out = OdeTraj + b * (long long)P.nt * (p + 1);
+    double x[p], th[3] = {0.0, param.at(b, 1), P.npt > 2 ? param.at(b, 2) : 0.0};
+    const double gam = param.at(b, P.iGamma);
+    double R0 = param.at(b, P.iR0);
+    int nxt = 0;
+    const double dt = P.dt_ode;
+    for (int c = 0; c < p; ++c) {
+        x[c] = initial.at(b, c);
+        out[(long long)(c + 1) * P.nt] = x[c];
+    }
+    out[0] = P.times[0];
+    for (int i = 1; i < P.nt; ++i) {
+        while (nxt < P.nch && P.chidx[nxt] <= i - 1) R0 *= param.at(b, P.nparam + nxt++);
+        th[0] = R0 * gam / P.N;
+        double k1[p], k2[p], k3[p], k4[p], xs[p];
+        M::rhs(x, th, k1);
+        for (int c = 0; c < p; ++c) xs[c] = x[c] + k1[c] * dt / 2;
+        M::rhs(xs, th, k2);
+        for (int c = 0; c < p; ++c) xs[c] = x[c] + k2[c] * dt / 2;
+        M::rhs(xs, th, k3);
+        for (int c = 0; c < p; ++c) xs[c] = x[c] + k3[c] * dt / 2;
+        M::rhs(xs, th, k4);
+        out[i] = P.times[i];
+        for (int c = 0; c < p; ++c) {
+            x[c] = x[c] + (k1[c] / 6 + k2[c] / 3 + k3[c] / 3 + k4[c] / 6) * dt;
+            out[i + (long long)(c + 1) * P.nt] = x[c];
+        }
+    }
+}
+
+// KF_param / KF_param_chol (LNA_functional.cpp:603-670) from a GIVEN fine trajectory:
+// one thread per (item, segment) -- the k segments are independent.
+template <int kModel>
+__global__ void k_kf_param(DevProb P, long long B, const double *OdeTraj, View param, int chol, double *Acube,
+                           double *Scube, int *status) {
+    using M = Model<kModel>;
+    constexpr int p = M::P;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= B * P.k) return;
+    const long long b = tid / P.k;
+    const int seg = (int)(tid % P.k);
+    const double *tr = OdeTraj + b * (long long)P.nt * (p + 1);
+    double F0[p * p], Sg[p * p], Fm[p * p], Qm[p * p], T1[p * p];
+    for (int e = 0; e < p * p; ++e) F0[e] = 0.0, Sg[e] = 0.0;
+    for (int c = 0; c < p; ++c) F0[c * p + c] = 1.0;
+    double th[3] = {0.0, param.at(b, 1), P.npt > 2 ? param.at(b, 2) : 0.0};
+    const int r0 = seg * P.g;
+    const double dt = tr[r0 + 1] - tr[r0];
+    for (int i = 0; i < P.g; ++i) {
+        const int r = r0 + i;
+        th[0] = beta_at(P, param, b, tr[r]);
+        double x[p];
+        for (int c = 0; c < p; ++c) x[c] = tr[r + (long long)(c + 1) * P.nt];
+        M::F(x, th, Fm);
+        M::Q(x, th, Qm);
+        // F0 += (F*F0)*dt
+        for (int a = 0; a < p; ++a)
+            for (int c = 0; c < p; ++c) {
+                double s = 0.0;
+                for (int q = 0; q < p; ++q) s += Fm[a * p + q] * F0[q * p + c];
+                T1[a * p + c] = s;
+            }
+        for (int e = 0; e < p * p; ++e) F0[e] = F0[e] + T1[e] * dt;
+        // Sigma += (Sigma*F' + F*Sigma + Q)*dt
+        for (int a = 0; a < p; ++a)
+            for (int c = 0; c < p; ++c) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q < p; ++q) {
+                    s1 += Sg[a * p + q] * Fm[c * p + q];
+                    s2 += Fm[a * p + q] * Sg[q * p + c];
+                }
+                T1[a * p + c] = (s1 + s2) + Qm[a * p + c];
+            }
+        for (int e = 0; e < p * p; ++e) Sg[e] = Sg[e] + T1[e] * dt;
+    }
+    double *Ao = Acube + (b * P.k + seg) * (long long)(p * p);
+    double *So = Scube + (b * P.k + seg) * (long long)(p * p);
+    for (int a = 0; a < p; ++a)
+        for (int c = 0; c < p; ++c) Ao[a + c * p] = F0[a * p + c];
+    if (!chol) {
+        for (int a = 0; a < p; ++a)
+            for (int c = 0; c < p; ++c) So[a + c * p] = Sg[a * p + c];
+        return;
+    }
+    // upper Cholesky of Sigma + 1e-8 I on the upper triangle (dpotrf 'U'), store L = U'
+    double U[p * p];
+    bool fail = false;
+    for (int e = 0; e < p * p; ++e) U[e] = 0.0;
+    for (int j = 0; j < p; ++j) {
+        double ajj = Sg[j * p + j] + kJitter;
+        for (int q = 0; q < j; ++q) ajj -= U[q * p + j] * U[q * p + j];
+        if (!(ajj > 0.0)) fail = true;
+        ajj = sqrt(ajj);
+        U[j * p + j] = ajj;
+        for (int c = j + 1; c < p; ++c) {
+            double s = Sg[j * p + c];
+            for (int q = 0; q < j; ++q) s -= U[q * p + j] * U[q * p + c];
+            U[j * p + c] = s / ajj;
+        }
+    }
+    for (int a = 0; a < p; ++a)
+        for (int c = 0; c < p; ++c) So[a + c * p] = U[c * p + a];
+    if (fail && status) atomicOr(&status[b], ST_CHOL_FAIL);
+}
+
+// Ode_Coarse_Slicer (LNA_functional.cpp:1179-1188)
+__global__ void k_coarse_slicer(int nt, int ncol, int g, int nrow, long long B, const double *thin, double *coarse) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)nrow * ncol;
+    if (tid >= B * per) return;
+    const long long b = tid / per;
+    const int e = (int)(tid % per), c = e / nrow, r = e % nrow;
+    coarse[tid] = thin[b * (long long)nt * ncol + (long long)c * nt + (long long)r * g];
+}
+
+// TransformTraj (LNA_functional.cpp:877-900) and Traj_sim_general_noncentral (:824-872, eps supplied).
+// mode 0: OriginLatent is k x p column-major; mode 1: `normals` step-major + extra outputs.
+template <int p>
+__global__ void k_transform_traj(int k, long long B, const double *Ode, const double *eps_in, const double *Acube,
+                                 const double *Lcube, int step_major, double t_correct, double *traj,
+                                 double *OriginLatent, double *logMultiNorm, double *logOrigin) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nrow = k + 1;
+    const double *O = Ode + b * (long long)nrow * (p + 1);
+    double *T = traj + b * (long long)nrow * (p + 1);
+    const double *A = Acube + b * (long long)k * p * p, *L = Lcube + b * (long long)k * p * p;
+    const double *ep = eps_in + b * (long long)k * p;
+    double X[p], lm = 0.0, lo = 0.0;
+    for (int c = 0; c < p; ++c) X[c] = 0.0;
+    for (int c = 0; c <= p; ++c) T[(long long)c * nrow] = O[(long long)c * nrow];
+    for (int i = 0; i < k; ++i) {
+        double e[p], nX[p];
+        for (int c = 0; c < p; ++c) e[c] = step_major ? ep[i * p + c] : ep[i + c * k];
+        const double *Ai = A + i * p * p, *Li = L + i * p * p;
+        for (int r = 0; r < p; ++r) {
+            double ax = Ai[r] * X[0], le = Li[r] * e[0];
+            for (int q = 1; q < p; ++q) {
+                ax += Ai[r + q * p] * X[q];
+                le += Li[r + q * p] * e[q];
+            }
+            nX[r] = ax + le;
+        }
+        T[i + 1] = O[i + 1];
+        for (int r = 0; r < p; ++r) {
+            X[r] = nX[r];
+            T[(i + 1) + (long long)(r + 1) * nrow] = nX[r] + O[(i + 1) + (long long)(r + 1) * nrow];
+        }
+        if (step_major) {
+            for (int c = 0; c < p; ++c) OriginLatent[b * (long long)k * p + i + c * k] = e[c];
+            if (O[i + 1] <= t_correct) {
+                double ee = 0.0, det;
+                for (int c = 0; c < p; ++c) ee += e[c] * e[c];
+                if (p == 2) det = Li[0] * Li[3] - Li[2] * Li[1];
+                else
+                    det = Li[0] * (Li[4] * Li[8] - Li[7] * Li[5]) - Li[3] * (Li[1] * Li[8] - Li[7] * Li[2]) +
+                          Li[6] * (Li[1] * Li[5] - Li[4] * Li[2]);
+                lm += -log(det);
+                lo += -0.5 * ee;
+            }
+        }
+    }
+    if (step_major) {
+        logMultiNorm[b] = lm;
+        logOrigin[b] = lo;
+    }
+}
+
+// volz_loglik_nh2 (LNA_functional.cpp:1119-1176), literal PER-EVENT form: one warp per trajectory.
+// The block stages the genealogy's event arrays (C*D and y) in shared memory once; each warp first
+// derives the per-cell factors of its trajectory (lane = cell), then strides over the events and
+// reduces with warp shuffles.
+__global__ void k_volz_events(DevProb P, long long B, const double *traj, const double *betaN, double *loglik,
+                              int *status, int stage_events) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *cellq = reinterpret_cast<double *>(smem);      // [warps][n0] beta*exp(-f)*exp(s)
+    double *celll = cellq + (size_t)warps * P.n0;          // [warps][n0] log beta - f + s
+    double *evCD = celll + (size_t)warps * P.n0;           // [E] (optional)
+    double *evY = evCD + (stage_events ? P.E : 0);
+    int *evCell = reinterpret_cast<int *>(evY + (stage_events ? P.E : 0));  // [E] (optional)
+    if (stage_events) {
+        for (int e = threadIdx.x; e < P.E; e += blockDim.x) {
+            evCD[e] = P.evC[e] * P.evD[e];
+            evY[e] = P.evY[e];
+        }
+        for (int c = 0; c < P.n0; ++c)
+            for (int e = P.evStart[c] + threadIdx.x; e < P.evStart[c + 1]; e += blockDim.x) evCell[e] = c;
+    }
+    __syncthreads();
+    const long long b = (long long)blockIdx.x * warps + w;
+    if (b >= B) return;
+    const int nrow = P.nrow, p = P.p;
+    const double *f1 = traj + b * (long long)nrow * (p + 1);
+    const double *bN = betaN + b * (long long)nrow;
+    // negative-state check on rows 0..n0, all state columns
+    int neg = 0;
+    for (int e = lane; e < (P.n0 + 1) * p; e += 32) {
+        const int r = e % (P.n0 + 1), c = e / (P.n0 + 1);
+        if (f1[r + (long long)(c + 1) * nrow] < 0.0) neg = 1;
+    }
+    neg = __any_sync(0xffffffffu, neg);
+    double *cq = cellq + (size_t)w * P.n0, *cl = celll + (size_t)w * P.n0;
+    for (int i = lane; i < P.n0; i += 32) {
+        const int row = P.Lrow - i;
+        const double f = log(f1[row + (long long)(P.idxI + 1) * nrow]);
+        const double s = log(f1[row + (long long)(P.idxS + 1) * nrow]);
+        const double be = bN[row];
+        cq[i] = be * exp(-f) * exp(s);
+        cl[i] = log(be) - f + s;
+    }
+    __syncwarp();
+    double acc = 0.0;
+    int nan = 0;
+    if (stage_events) {
+        for (int e = lane; e < P.E; e += 32) {
+            const int c = evCell[e];
+            const double v = -2.0 * (evCD[e] * cq[c]) + evY[e] * cl[c];
+            nan |= (v != v);
+            acc += v;
+        }
+    } else {
+        for (int c = 0; c < P.n0; ++c)
+            for (int e = P.evStart[c] + lane; e < P.evStart[c + 1]; e += 32) {
+                const double v = -2.0 * (P.evC[e] * P.evD[e] * cq[c]) + P.evY[e] * cl[c];
+                nan |= (v != v);
+                acc += v;
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    nan = __any_sync(0xffffffffu, nan);
+    if (lane == 0) {
+        int st = 0;
+        double r = acc;
+        if (neg) {
+            r = kSentinel;
+            st = ST_NEG_STATE;
+        } else if (nan) {
+            r = kSentinel;
+            st = ST_NAN;
+        }
+        loglik[b] = r;
+        if (status) status[b] = st;
+    }
+}
+
+// coal_loglik3 (LNA_functional.cpp:1016-1054) / coal_loglik (SIR_phylodyn.cpp:436-468): Kingman-lambda.
+// One warp per trajectory; cell c uses row n0k - c where n0k = first row with time >= t_correct.
+__global__ void k_kingman(DevProb P, long long B, const double *traj, const double *lambda, int col, int take_log,
+                          double *loglik) {
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * warps + w;
+    if (b >= B) return;
+    const int nrow = P.nrow;
+    const double *f1 = traj + b * (long long)nrow * (P.p + 1);
+    int n0k = 0;
+    while (n0k < nrow - 1 && f1[n0k] < P.t_correct) n0k++;
+    const double lam = lambda[b], llam = log(lam);
+    double acc = 0.0;
+    const int ncell = n0k < P.n0 + 1 ? n0k : P.n0 + 1;
+    for (int c = 0; c < ncell && c < P.n0; ++c) {
+        double f = f1[(n0k - c) + (long long)col * nrow];
+        if (take_log) f = log(f);
+        const double ef = exp(-f), lf = llam - f;
+        for (int e = P.evStart[c] + lane; e < P.evStart[c + 1]; e += 32)
+            acc += -lam * (P.evC[e] * P.evD[e] * ef) + P.evY[e] * lf;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) loglik[b] = acc;
+}
+
+// Independent-DFMA microbenchmark for the FP64 roofline denominator: 8 independent chains/thread.
+__global__ void k_fp64_peak(int iters, double *sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) sink[0] = s;
+}
+
+}  // namespace lna

@@ -865,3 +865,26 @@ void orc_chols(const double *S, double *L) {
     L[2] = 0;
     L[3] = r11;
 }
+
+/* ---------------------------------------------------------------- batch driver (bench baseline) */
+
+/* B independent FULL evaluations, item-major inputs like the product's C ABI; one core.
+ * Used by bench.py (cpu_baseline / --impl reference) and by the parity tests. */
+int orc_full_loglik_batch(const orc_cfg *c, const orc_init *init, long B, const double *param,
+                          const double *initial, const double *t, int nt, int gridsize,
+                          const double *OriginTraj, double t_correct, double *coalLog, int *status) {
+    int p = c->p, nrow = nt / gridsize + 1, k = (nt - 1) / gridsize;
+    double *A = (double *)malloc(sizeof(double) * (size_t)(p * p * k) * 2);
+    double *ode = (double *)malloc(sizeof(double) * (size_t)nrow * (p + 1) * 2);
+    double *bn = (double *)malloc(sizeof(double) * (size_t)nrow);
+    for (long b = 0; b < B; b++) {
+        int st = orc_full_loglik(c, init, param + b * c->nparam_total, initial + b * p, t, nt, gridsize,
+                                 OriginTraj + b * (long)k * p, t_correct, A, A + p * p * k, ode, bn,
+                                 ode + (size_t)nrow * (p + 1), &coalLog[b]);
+        if (status) status[b] = st;
+    }
+    free(A);
+    free(ode);
+    free(bn);
+    return 0;
+}

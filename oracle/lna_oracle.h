@@ -137,6 +137,11 @@ int orc_eslice_change_points(const orc_cfg *c, const orc_init *init, const doubl
                              double *param_new, double *Acube, double *Lcube, double *Ode_coarse,
                              double *betaN, double *LatentTraj, double *CoalLog, double *LogChProb);
 
+/* B independent FULL evaluations on one core (item-major inputs like the product's C ABI). */
+int orc_full_loglik_batch(const orc_cfg *c, const orc_init *init, long B, const double *param,
+                          const double *initial, const double *t, int nt, int gridsize,
+                          const double *OriginTraj, double t_correct, double *coalLog, int *status);
+
 /* basic_util.cpp:23-41 */
 void orc_inv2(const double *a, double *res);
 void orc_chols(const double *S, double *L);

@@ -254,6 +254,18 @@ def full_loglik(cfg, ini, param, initial, t, gridsize, OriginTraj, t_correct):
             "coalLog": cl.value}
 
 
+def full_loglik_batch(cfg, ini, param, initial, t, gridsize, OriginTraj, t_correct):
+    """B FULL evaluations on ONE core; param (B,npt), initial (B,p), OriginTraj (B,k,p) natural indexing.
+    ctypes releases the GIL during the call, so several of these can run on separate threads."""
+    param, initial, t = _d(param), _d(initial), _d(t)
+    B = param.shape[0]
+    eps = np.ascontiguousarray(np.transpose(np.asarray(OriginTraj, dtype=np.float64), (0, 2, 1)))
+    cl, st = np.empty(B), np.zeros(B, dtype=np.int32)
+    lib().orc_full_loglik_batch(cfg.ref, ini.ref, C.c_long(B), _p(param), _p(initial), _p(t), len(t), int(gridsize),
+                                _p(eps), C.c_double(t_correct), _p(cl), st.ctypes.data_as(_ip))
+    return cl, st
+
+
 def Update_Param(param, initial, t, OriginTraj, x_r, x_i, init, gridsize, coal_log=0.0,
                  prior_proposal_offset=0.0, t_correct=0.0, transP="changepoint", model="SIR",
                  transX="standard", volz=True, *, unif):

@@ -1,0 +1,220 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance (BASELINE.json north_star): log-likelihoods and trajectories within 1e-10 relative, FP64.
+"""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def api():
+    import lnaphylodyn_b200 as m
+    from lnaphylodyn_b200 import _lib
+    assert _lib.lib().lna_device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return m.api
+
+
+def draw_inputs(g, B, seed, scale=0.05):
+    """Parameter draws around the cached final state + fresh N(0,1) latent increments."""
+    rng = np.random.default_rng(seed)
+    par = np.tile(g.final["par"].ravel(), (B, 1))
+    par[:, 2] *= np.exp(scale * rng.standard_normal(B))            # R0
+    par[:, 3] *= np.exp(scale * rng.standard_normal(B))            # gamma
+    par[:, 4:43] *= np.exp(0.5 * scale * rng.standard_normal((B, 39)))  # change ratios
+    eps = rng.standard_normal((B, 40, 2))
+    return par, eps
+
+
+@pytest.mark.parametrize("name", ["changepoint", "constant"])
+def test_full_loglik_final_state_vs_golden(api, name, request):
+    g = request.getfixturevalue(name)
+    par = g.final["par"].ravel()
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    res = pb.full_loglik(par[2:], par[:2], g.final["OriginTraj"], want=("coalLog", "FT", "Ode", "betaN", "LatentTraj"))
+    assert res["status"] == 0
+    assert relerr(res["Ode"], g.final["Ode_Traj_coarse"]) < TOL
+    assert relerr(res["FT"]["A"], g.final["FT.A"]) < TOL
+    assert np.max(np.abs(res["FT"]["Sigma"] - g.final["FT.Sigma"])) < 1e-9
+    assert relerr(res["betaN"], g.final["betaN"].ravel()) < TOL
+    assert relerr(res["LatentTraj"][:, 1:], g.final["LatentTraj"][:, 1:]) < TOL
+    assert abs(res["coalLog"] - float(g.final["coalLog"][0])) < TOL * abs(res["coalLog"])
+
+
+@pytest.mark.parametrize("name", ["changepoint", "constant"])
+def test_full_loglik_batch_vs_oracle(api, name, request):
+    g = request.getfixturevalue(name)
+    B = 96
+    par, eps = draw_inputs(g, B, seed=11)
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    res = pb.full_loglik(par[:, 2:], par[:, :2], eps, want=("coalLog", "FT", "Ode", "betaN", "LatentTraj"))
+    res_ll_only = pb.full_loglik(par[:, 2:], par[:, :2], eps)
+    cfg, ini = orc.Cfg(g.x_r, g.x_i, 42), orc.Init(g.init)
+    worst = 0.0
+    for b in range(B):
+        o = orc.full_loglik(cfg, ini, par[b, 2:], par[b, :2], g.times, g.gridsize, eps[b], g.t_correct)
+        assert o["status"] == res["status"][b]
+        if o["coalLog"] == orc.SENTINEL:
+            assert res["coalLog"][b] == orc.SENTINEL
+        else:
+            worst = max(worst, abs(res["coalLog"][b] - o["coalLog"]) / abs(o["coalLog"]))
+        assert res_ll_only["coalLog"][b] == res["coalLog"][b]
+        assert relerr(res["Ode"][b], o["Ode"]) < TOL
+        assert relerr(res["FT"]["A"][b], o["FT"]["A"]) < 1e-9
+        assert np.max(np.abs(res["FT"]["Sigma"][b] - o["FT"]["Sigma"])) < 1e-8
+        assert relerr(res["betaN"][b], o["betaN"]) < TOL
+        assert np.max(np.abs(res["LatentTraj"][b][:, 1:] - o["LatentTraj"][:, 1:]) /
+                      np.maximum(np.abs(o["LatentTraj"][:, 1:]), 1.0)) < TOL
+    assert worst < TOL, worst
+
+
+@pytest.mark.parametrize("name", ["changepoint", "constant"])
+def test_per_iteration_known_answers_event_kernel(api, name, request):
+    """(par_i, Trajectory_i) -> coalLog_i of the reference's own MCMC run, via the per-event kernel."""
+    g = request.getfixturevalue(name)
+    traj = g.iters["Trajectory"]
+    betaN = np.stack([orc.betaTs(par[2:], tr[:, 0], g.x_r, g.x_i) for par, tr in zip(g.iters["par"], traj)])
+    ll = api.volz_loglik_nh2(g.init, traj, betaN, g.t_correct, g.x_i[2:4])
+    assert np.max(np.abs(ll - g.iters["coalLog"]) / np.abs(g.iters["coalLog"])) < TOL
+    b1 = api.betaTs(g.iters["par"][5][2:], traj[5][:, 0], g.x_r, g.x_i)
+    assert relerr(b1, betaN[5]) < 1e-14
+
+
+def test_cell_sums_match_events(api, changepoint):
+    g = changepoint
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    cd, yy, cnt = pb.cell_sums()
+    start = np.concatenate([[0], np.cumsum(g.init["gridrep"][:-1])]).astype(int)
+    for i in range(len(cd)):
+        sl = slice(start[i], start[i + 1])
+        assert cnt[i] == g.init["gridrep"][i]
+        assert cd[i] == pytest.approx(np.sum(g.init["C"][sl] * g.init["D"][sl]), rel=1e-13, abs=1e-300)
+        assert yy[i] == np.sum(g.init["y"][sl])
+
+
+def test_negative_state_sentinel(api, changepoint):
+    """A huge negative latent increment drives I < 0 inside the checked rows -> -1e7 (A.9)."""
+    g = changepoint
+    par = g.final["par"].ravel()
+    eps = np.zeros((40, 2))
+    eps[3, 1] = -1e6
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    res = pb.full_loglik(par[2:], par[:2], eps)
+    cfg, ini = orc.Cfg(g.x_r, g.x_i, 42), orc.Init(g.init)
+    o = orc.full_loglik(cfg, ini, par[2:], par[:2], g.times, g.gridsize, eps, g.t_correct)
+    assert o["coalLog"] == orc.SENTINEL and res["coalLog"] == orc.SENTINEL
+    assert res["status"] & 2
+
+
+def test_cholesky_failure_flag(api, changepoint):
+    """NaN parameters make arma::chol throw in the reference; here: status bit + -1e7, and the
+    Rcpp-style wrapper raises like KF_param_chol (LNA_functional.cpp:660-664)."""
+    g = changepoint
+    par = g.final["par"].ravel().copy()
+    par[2] = np.nan
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    res = pb.full_loglik(par[2:], par[:2], g.final["OriginTraj"])
+    assert res["status"] & 1 and res["coalLog"] == orc.SENTINEL
+    with pytest.raises(ValueError):
+        api.New_Param_List(par[2:], par[:2], g.gridsize, g.times, g.x_r, g.x_i)
+    with pytest.raises(ValueError):
+        orc.New_Param_List(par[2:], par[:2], g.gridsize, g.times, g.x_r, g.x_i)
+
+
+def test_rcpp_mirrors_vs_oracle(api, changepoint):
+    g = changepoint
+    par = g.final["par"].ravel()
+    param, initial = par[2:], par[:2]
+    o_ode = orc.ODE_rk45(initial, g.times, param, g.x_r, g.x_i)
+    d_ode = api.ODE_rk45(initial, g.times, param, g.x_r, g.x_i)
+    assert relerr(d_ode, np.where(o_ode == 0, 0, o_ode)) < TOL or np.max(np.abs(d_ode - o_ode) / np.maximum(np.abs(o_ode), 1e-300)[...]) < TOL
+    for fn in ("KF_param", "KF_param_chol"):
+        o = getattr(orc, fn)(o_ode, param, g.gridsize, g.x_r, g.x_i)
+        d = getattr(api, fn)(o_ode, param, g.gridsize, g.x_r, g.x_i)
+        assert relerr(d["A"], o["A"]) < TOL
+        assert np.max(np.abs(d["Sigma"] - o["Sigma"])) < 1e-9 * max(1.0, np.max(np.abs(o["Sigma"])))
+    assert np.array_equal(api.Ode_Coarse_Slicer(o_ode, g.gridsize), orc.Ode_Coarse_Slicer(o_ode, g.gridsize))
+    npl_o = orc.New_Param_List(param, initial, g.gridsize, g.times, g.x_r, g.x_i)
+    npl_d = api.New_Param_List(param, initial, g.gridsize, g.times, g.x_r, g.x_i)
+    assert relerr(npl_d["Ode"], npl_o["Ode"]) < TOL and relerr(npl_d["betaN"], npl_o["betaN"]) < TOL
+    lat_o = orc.TransformTraj(npl_o["Ode"], g.final["OriginTraj"], npl_o["FT"])
+    lat_d = api.TransformTraj(npl_o["Ode"], g.final["OriginTraj"], npl_o["FT"])
+    assert relerr(lat_d[:, 1:], lat_o[:, 1:]) < TOL
+    sf_o = orc.SigmaF(o_ode[100:150], param, g.x_r, g.x_i)
+    sf_d = api.SigmaF(o_ode[100:150], param, g.x_r, g.x_i)
+    assert relerr(sf_d["expF"], sf_o["expF"]) < TOL and relerr(sf_d["Sigma"], sf_o["Sigma"]) < 1e-9
+    pt_o = orc.param_transform(33.3, param, g.x_r, g.x_i)
+    pt_d = api.param_transform(33.3, param, g.x_r, g.x_i)
+    assert relerr(pt_d, pt_o) < 1e-14
+    rng = np.random.default_rng(3)
+    nrm = rng.standard_normal(80)
+    s_o = orc.Traj_sim_general_noncentral(npl_o["Ode"], npl_o["FT"], g.t_correct, nrm)
+    s_d = api.Traj_sim_general_noncentral(npl_o["Ode"], npl_o["FT"], g.t_correct, normals=nrm)
+    assert relerr(s_d["SimuTraj"][:, 1:], s_o["SimuTraj"][:, 1:]) < TOL
+    assert np.array_equal(s_d["OriginTraj"], s_o["OriginTraj"])
+    assert s_d["logOrigin"] == pytest.approx(s_o["logOrigin"], rel=1e-13)
+    assert s_d["logMultiNorm"] == pytest.approx(s_o["logMultiNorm"], rel=1e-10)
+    k_o = orc.coal_loglik3(g.init, lat_o, g.t_correct, 3.0, 1)
+    k_d = api.coal_loglik3(g.init, lat_o, g.t_correct, 3.0, 1)
+    assert k_d == pytest.approx(k_o, rel=TOL)
+    logtraj = lat_o.copy()
+    logtraj[:, 1:] = np.log(lat_o[:, 1:])
+    assert api.coal_loglik(g.init, logtraj, g.t_correct, 3.0) == pytest.approx(orc.coal_loglik(g.init, logtraj, g.t_correct, 3.0), rel=TOL)
+
+
+def test_update_param_decisions(api, changepoint):
+    g = changepoint
+    B = 64
+    par, _ = draw_inputs(g, B, seed=5, scale=0.01)
+    eps = g.final["OriginTraj"]
+    rng = np.random.default_rng(9)
+    u = rng.uniform(size=B)
+    coal_log = float(g.final["coalLog"][0])
+    d = api.Update_Param(par[:, 2:], par[:, :2], g.times, eps, g.x_r, g.x_i, g.init, g.gridsize, coal_log, 0.1,
+                         g.t_correct, unif=u)
+    flips = 0
+    for b in range(B):
+        o = orc.Update_Param(par[b, 2:], par[b, :2], g.times, eps, g.x_r, g.x_i, g.init, g.gridsize, coal_log, 0.1,
+                             g.t_correct, unif=u[b])
+        flips += int(bool(o["accept"]) != bool(d["accept"][b]))
+        ref = o["coalLog"] if o["accept"] else o["coalLog_proposed"]
+        assert d["coalLog"][b] == pytest.approx(ref, rel=TOL)
+    assert flips == 0
+    assert 0 < d["accept"].sum() < B  # the test exercises both branches
+
+
+def test_seir_full_loglik_vs_oracle(api, changepoint):
+    """p = 3 model variant (model="SEIR": states S,E,I; params R0, mu, gamma; volz index (0,2))."""
+    g = changepoint
+    B = 48
+    rng = np.random.default_rng(21)
+    x_i = [39, 3, 0, 2]
+    param = np.empty((B, 43))
+    param[:, 0] = 2.2 * np.exp(0.05 * rng.standard_normal(B))
+    param[:, 1] = 0.5 * np.exp(0.05 * rng.standard_normal(B))
+    param[:, 2] = 0.2 * np.exp(0.05 * rng.standard_normal(B))
+    param[:, 3:42] = np.exp(0.02 * rng.standard_normal((B, 39)))
+    param[:, 42] = 20.0
+    initial = np.tile([1e6, 5.0, 5.0], (B, 1))
+    eps = 0.5 * rng.standard_normal((B, 40, 3))
+    pb = api.problem_for(g.times, g.x_r, x_i, g.gridsize, g.t_correct, g.init, model="SEIR")
+    res = pb.full_loglik(param, initial, eps, want=("coalLog", "FT", "Ode", "betaN", "LatentTraj"))
+    cfg, ini = orc.Cfg(g.x_r, x_i, 43, model="SEIR"), orc.Init(g.init)
+    n_ok = 0
+    for b in range(B):
+        o = orc.full_loglik(cfg, ini, param[b], initial[b], g.times, g.gridsize, eps[b], g.t_correct)
+        assert o["status"] == res["status"][b]
+        assert relerr(res["Ode"][b], o["Ode"]) < TOL
+        assert relerr(res["FT"]["A"][b], o["FT"]["A"]) < 1e-9
+        assert np.max(np.abs(res["FT"]["Sigma"][b] - o["FT"]["Sigma"])) < 1e-8 * max(1.0, np.max(np.abs(o["FT"]["Sigma"])))
+        if o["coalLog"] == orc.SENTINEL:
+            assert res["coalLog"][b] == orc.SENTINEL
+        else:
+            n_ok += 1
+            assert res["coalLog"][b] == pytest.approx(o["coalLog"], rel=TOL)
+    assert n_ok > B // 2
