@@ -406,3 +406,158 @@ def Update_Param(param, initial, t, OriginTraj, x_r, x_i, init, gridsize, coal_l
     return {"accept": acc.astype(bool), "status": st, "coalLog": cl,
             "FT": {"A": pb._unmats(A, (p, p, k), False), "Sigma": pb._unmats(Lc, (p, p, k), False)},
             "Ode": pb._unmats(ode, (nrow, p + 1), False), "betaN": bn, "LatentTraj": pb._unmats(lat, (nrow, p + 1), False)}
+
+
+# ------------------------------------------------------------------------------------------------
+# elliptical slice operators (pre-drawn streams; SURVEY Appendix C gives the consumption order)
+# ------------------------------------------------------------------------------------------------
+
+def _pr8(priorList):
+    return _d(np.concatenate([np.asarray(v, dtype=np.float64).ravel()[:2] for v in priorList]))
+
+
+def _i32(a, n):
+    v = np.ascontiguousarray(np.asarray(a, dtype=np.float64).round().astype(np.int32).ravel())
+    assert v.size == n, (v.size, n)
+    return v
+
+
+def _unif22(u, B):
+    """pad the per-call uniform stream to the fixed LNA_ESLICE_MAX_UNIF width"""
+    u = _d(u)
+    u = u.reshape(B, -1) if u.ndim > 1 or B == 1 else u.reshape(B, -1)
+    out = np.full((B, ESLICE_MAX_UNIF), 0.5)
+    n = min(u.shape[1], ESLICE_MAX_UNIF)
+    out[:, :n] = u[:, :n]
+    return out
+
+
+def Param_Slice_update(param, x_r, x_i, theta, newChs, rho=1):
+    """LNA_functional.cpp:1246-1253"""
+    xi = _xi(x_i)
+    pb = problem_for(np.array([0.0, 1.0]), x_r, xi, 1)
+    P, single = pb._batch(param, pb.npt)
+    B = P.shape[0]
+    th = np.ascontiguousarray(np.broadcast_to(_d(theta).ravel(), (B,)))
+    nc = _d(newChs).reshape(B, xi[0])
+    out = np.empty_like(P)
+    check(_lib.lib().lna_param_slice_update(pb.h, B, _ptr(P), _ptr(th), _ptr(nc), _ptr(out)), "lna_param_slice_update")
+    return out[0] if single else out
+
+
+def Param_Slice_update_all2(par_old, x_r, x_i, theta, newChs, ESS_vec, priorList):
+    """LNA_functional.cpp:1268-1314"""
+    xi = _xi(x_i)
+    pb = problem_for(np.array([0.0, 1.0]), x_r, xi, 1)
+    npar = 2 + pb.npt
+    P, single = pb._batch(par_old, npar)
+    B = P.shape[0]
+    th = np.ascontiguousarray(np.broadcast_to(_d(theta).ravel(), (B,)))
+    nc = _d(newChs).reshape(B, npar - 1)
+    ev, pr = _i32(ESS_vec, 7), _pr8(priorList)
+    out = np.empty_like(P)
+    check(_lib.lib().lna_param_slice_update_all2(pb.h, B, _ptr(P), _ptr(th), _ptr(nc), _ptr(ev), _ptr(pr), _ptr(out)),
+          "lna_param_slice_update_all2")
+    return out[0] if single else out
+
+
+def ESlice_par_General(par_old, t, OriginTraj, priorList, x_r, x_i, init, gridsize, ESS_vec, coal_log=0.0,
+                       t_correct=0.0, transP="changepoint", model="SIR", transX="standard", volz=True, *,
+                       normals, uniforms, spec_width=0):
+    """LNA_functional.cpp:1532-1688.  normals: npar-1 per chain; uniforms: u, theta draws (<= 21)."""
+    pb = problem_for(t, x_r, x_i, gridsize, t_correct, init, model, transX)
+    npar = 2 + pb.npt
+    P, single = pb._batch(par_old, npar)
+    B = P.shape[0]
+    E, _ = pb._mats(OriginTraj, (pb.k, pb.p))
+    if E.shape[0] == 1 and B > 1:
+        E = np.ascontiguousarray(np.broadcast_to(E, (B, E.shape[1])))
+    cl0 = np.ascontiguousarray(np.broadcast_to(_d(coal_log).ravel(), (B,)))
+    nrm = _d(normals).reshape(B, -1)[:, :npar - 1].copy()
+    unf = _unif22(uniforms, B)
+    ev, pr = _i32(ESS_vec, 7), _pr8(priorList)
+    p, k, nrow = pb.p, pb.k, pb.nrow
+    par_new = np.empty((B, npar))
+    A, Lc = np.empty((B, p * p * k)), np.empty((B, p * p * k))
+    ode, bn, lat = np.empty((B, nrow * (p + 1))), np.empty((B, nrow)), np.empty((B, nrow * (p + 1)))
+    cl, lo = np.empty(B), np.empty(B)
+    ne, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_eslice_par_general(pb.h, B, _ptr(P), _ptr(E), _ptr(pr), _ptr(ev), _ptr(cl0), _ptr(nrm),
+                                            _ptr(unf), int(spec_width), _ptr(par_new), _ptr(A), _ptr(Lc), _ptr(ode),
+                                            _ptr(bn), _ptr(lat), _ptr(cl), _ptr(lo), _ptr(ne), _ptr(st)),
+          "lna_eslice_par_general")
+    if single and (st[0] & ST_CHOL_FAIL):
+        raise ValueError(CHOL_MSG)
+    pick = (lambda a: a[0]) if single else (lambda a: a)
+    return {"betaN": pick(bn), "FT": {"A": pb._unmats(A, (p, p, k), single), "Sigma": pb._unmats(Lc, (p, p, k), single)},
+            "OdeTraj": pb._unmats(ode, (nrow, p + 1), single), "par": pick(par_new),
+            "LatentTraj": pb._unmats(lat, (nrow, p + 1), single), "CoalLog": pick(cl),
+            "OriginTraj": (E.reshape(B, p, k).transpose(0, 2, 1)[0] if single else E.reshape(B, p, k).transpose(0, 2, 1)),
+            "logOrigin": pick(lo), "n_evals": pick(ne), "status": pick(st)}
+
+
+def ESlice_general_NC(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, coal_log=-99999999.0,
+                      gridsize=100, volz=False, model="SIR", transX="standard", *, normals, uniforms):
+    """LNA_functional.cpp:1690-1778 (volz=True path).  normals: k*p per chain, column-major k x p."""
+    if not volz:
+        raise LnaError("ESlice_general_NC(volz=False) needs LogTraj(), which the reference never defines in C++")
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    times = O[:, 0] if single else O[0, :, 0]
+    p = O.shape[-1] - 1
+    xi = [0, 2, 0, 1]
+    pb = problem_for(times, [1.0], xi, 1, t_correct, init, model, transX)
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, p + 1))
+    B = Of.shape[0]
+    Ff, _ = pb._mats(f_cur, (k, p))
+    Af, _ = pb._mats(FTs["A"], (p, p, k))
+    Lf, _ = pb._mats(FTs["Sigma"], (p, p, k))
+    bn = _d(betaN).reshape(B, nrow)
+    cl0 = np.ascontiguousarray(np.broadcast_to(_d(coal_log).ravel(), (B,)))
+    nrm = _d(normals).reshape(B, k * p)
+    unf = _unif22(uniforms, B)
+    lat, org = np.empty((B, nrow * (p + 1))), np.empty((B, k * p))
+    lo, cl = np.empty(B), np.empty(B)
+    ne, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_eslice_general_nc(pb.h, B, _ptr(Ff), _ptr(Of), _ptr(Af), _ptr(Lf), _ptr(bn), _ptr(cl0),
+                                           _ptr(nrm), _ptr(unf), _ptr(lat), _ptr(org), _ptr(lo), _ptr(cl), _ptr(ne),
+                                           _ptr(st)), "lna_eslice_general_nc")
+    pick = (lambda a: a[0]) if single else (lambda a: a)
+    return {"LatentTraj": pb._unmats(lat, (nrow, p + 1), single), "OriginTraj": pb._unmats(org, (k, p), single),
+            "logOrigin": pick(lo), "CoalLog": pick(cl), "n_evals": pick(ne), "status": pick(st)}
+
+
+def ESlice_change_points(param, initial, t, OriginTraj, x_r, x_i, init, gridsize, coal_log=0.0, t_correct=0.0,
+                         transP="changepoint", model="SIR", transX="standard", volz=True, *, normals, uniforms,
+                         spec_width=0):
+    """LNA_functional.cpp:1317-1409.  uniforms: u, theta_1, shrinks; normals: nch per chain."""
+    pb = problem_for(t, x_r, x_i, gridsize, t_correct, init, model, transX)
+    P, single = pb._batch(param, pb.npt)
+    B = P.shape[0]
+    I, _ = pb._batch(initial, pb.p)
+    if I.shape[0] == 1 and B > 1:
+        I = np.ascontiguousarray(np.broadcast_to(I, (B, pb.p)))
+    E, _ = pb._mats(OriginTraj, (pb.k, pb.p))
+    if E.shape[0] == 1 and B > 1:
+        E = np.ascontiguousarray(np.broadcast_to(E, (B, E.shape[1])))
+    cl0 = np.ascontiguousarray(np.broadcast_to(_d(coal_log).ravel(), (B,)))
+    nrm = _d(normals).reshape(B, -1)[:, :pb.x_i[0]].copy()
+    unf = _unif22(uniforms, B)
+    p, k, nrow = pb.p, pb.k, pb.nrow
+    pn = np.empty((B, pb.npt))
+    A, Lc = np.empty((B, p * p * k)), np.empty((B, p * p * k))
+    ode, bn, lat = np.empty((B, nrow * (p + 1))), np.empty((B, nrow)), np.empty((B, nrow * (p + 1)))
+    cl, lcp = np.empty(B), np.empty(B)
+    ne, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_eslice_change_points(pb.h, B, _ptr(P), _ptr(I), _ptr(E), _ptr(cl0), _ptr(nrm), _ptr(unf),
+                                              int(spec_width), _ptr(pn), _ptr(A), _ptr(Lc), _ptr(ode), _ptr(bn),
+                                              _ptr(lat), _ptr(cl), _ptr(lcp), _ptr(ne), _ptr(st)),
+          "lna_eslice_change_points")
+    if single and (st[0] & ST_CHOL_FAIL):
+        raise ValueError(CHOL_MSG)
+    pick = (lambda a: a[0]) if single else (lambda a: a)
+    return {"betaN": pick(bn), "FT": {"A": pb._unmats(A, (p, p, k), single), "Sigma": pb._unmats(Lc, (p, p, k), single)},
+            "OdeTraj": pb._unmats(ode, (nrow, p + 1), single), "param": pick(pn),
+            "LatentTraj": pb._unmats(lat, (nrow, p + 1), single), "CoalLog": pick(cl), "LogChProb": pick(lcp),
+            "n_evals": pick(ne), "status": pick(st)}

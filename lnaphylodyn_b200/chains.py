@@ -1,0 +1,172 @@
+"""Resident chain batches: the batched equivalent of the reference's R-level MCMC loop
+General_MCMC_with_ESlice (R/LNA_chpt_slice.R:723-849) over B independent chains on one GPU, and
+the torch.distributed plumbing that shards chains across the GPUs of one box.
+
+State lives in HBM between iterations (the R list MCMC_obj, general_change_point.R:558-561);
+only per-chain summaries are all-gathered across ranks.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import LnaMcmcOpts, LnaError, check
+from .api import ESLICE_MAX_UNIF, _d, _ptr
+
+ITER_UNIF = 3 + 2 * ESLICE_MAX_UNIF
+
+
+def make_opts(prior, proposal, ESS_vec, update_traj=True, hyper_noop_mh=True, spec_width=0,
+              gamma_prior_id=3, hyper_prior_id=5):
+    """Translate the vignettes' `prior` / `proposal` lists (by POSITION, like the R code does:
+    prlist = list(prior[[1]][1:2], prior[[2]], prior[[3]], prior[[5]]), LNA_chpt_slice.R:743)."""
+    pr = [np.asarray(v, dtype=np.float64).ravel() for v in prior]
+    po = [np.asarray(v, dtype=np.float64).ravel() for v in proposal]
+    o = LnaMcmcOpts()
+    pr8 = np.concatenate([pr[0][:2], pr[1][:2], pr[2][:2], pr[hyper_prior_id - 1][:2]])
+    for i in range(8):
+        o.prior8[i] = float(pr8[i])
+    o.gamma_prior[0], o.gamma_prior[1] = float(pr[gamma_prior_id - 1][0]), float(pr[gamma_prior_id - 1][1])
+    # Update_Param_each_Norm is called with proposeIdlist = priorIdlist (LNA_chpt_slice.R:791-792)
+    o.gamma_prop = float(po[gamma_prior_id - 1][0])
+    for i in range(7):
+        o.ESS_vec[i] = int(ESS_vec[i])
+    o.update_traj, o.hyper_noop_mh, o.spec_width = int(update_traj), int(hyper_noop_mh), int(spec_width)
+    return o
+
+
+class Chains:
+    """B resident chains on one GPU (wraps lna_chains)."""
+
+    def __init__(self, problem, par, OriginTraj):
+        self.pb = problem
+        par = _d(par)
+        self.B = par.shape[0]
+        self.npar = 2 + problem.npt
+        self.n_norm = (self.npar - 1) + problem.k * problem.p
+        L = _lib.lib()
+        self.h = L.lna_chains_create(problem.h, self.B)
+        if not self.h:
+            raise LnaError("lna_chains_create: " + L.lna_last_error().decode())
+        self._fin = weakref.finalize(self, L.lna_chains_destroy, self.h)
+        E, _ = problem._mats(OriginTraj, (problem.k, problem.p))
+        if E.shape[0] == 1 and self.B > 1:
+            E = np.ascontiguousarray(np.broadcast_to(E, (self.B, E.shape[1])))
+        check(L.lna_chains_init(self.h, _ptr(par), _ptr(E)), "lna_chains_init")
+
+    def step(self, opts, normals, uniforms):
+        """One MCMC iteration. normals (B, npar-1 + k*p), uniforms (B, 47): host arrays."""
+        n, u = _d(normals), _d(uniforms)
+        assert n.shape == (self.B, self.n_norm) and u.shape == (self.B, ITER_UNIF), (n.shape, u.shape)
+        check(_lib.lib().lna_chains_step(self.h, C.byref(opts), _ptr(n), _ptr(u)), "lna_chains_step")
+
+    def step_dev(self, opts, normals_ptr, uniforms_ptr):
+        """Same with streams already in HBM (raw device pointers, e.g. torch.Tensor.data_ptr())."""
+        check(_lib.lib().lna_chains_step_dev(self.h, C.byref(opts), normals_ptr, uniforms_ptr), "lna_chains_step_dev")
+
+    def get(self):
+        pb, B = self.pb, self.B
+        par = np.empty((B, self.npar))
+        org = np.empty((B, pb.k * pb.p))
+        lat = np.empty((B, pb.nrow * (pb.p + 1)))
+        cl, lo = np.empty(B), np.empty(B)
+        cnt = np.zeros((B, 4), dtype=np.int32)
+        check(_lib.lib().lna_chains_get(self.h, _ptr(par), _ptr(org), _ptr(lat), _ptr(cl), _ptr(lo), _ptr(cnt)),
+              "lna_chains_get")
+        return {"par": par, "OriginTraj": pb._unmats(org, (pb.k, pb.p), False),
+                "LatentTraj": pb._unmats(lat, (pb.nrow, pb.p + 1), False), "coalLog": cl, "logOrigin": lo,
+                "n_full_evals": cnt[:, 0], "n_cheap_evals": cnt[:, 1], "n_mh_accept": cnt[:, 2], "status": cnt[:, 3]}
+
+    def summary_ptr(self):
+        return _lib.lib().lna_chains_summary_dev(self.h)
+
+
+def draw_streams(B, n_norm, seed, iteration, chain_offset=0):
+    """Replayable per-chain streams: chain c of a job draws from default_rng([seed, c, iteration])."""
+    nrm = np.empty((B, n_norm))
+    unf = np.empty((B, ITER_UNIF))
+    for c in range(B):
+        rng = np.random.default_rng([seed, chain_offset + c, iteration])
+        nrm[c] = rng.standard_normal(n_norm)
+        u = rng.random(ITER_UNIF)
+        unf[c] = np.where(u == 0.0, 0.5, u)  # open interval like unif_rand()
+    return nrm, unf
+
+
+def vignette_opts(g, update_traj=True, spec_width=0):
+    """Options of the Changpoint_sim vignette call (vignettes/Changpoint_sim.Rmd:89-98) from a golden cache."""
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    proposal = [g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+    ess = [0, 1, 0, 0, 1, 1, 0]
+    if not update_traj:
+        ess[4] = 0  # ESS_temp for i < burn1 (LNA_chpt_slice.R:773-774)
+    return make_opts(prior, proposal, ess, update_traj=update_traj, hyper_noop_mh=True, spec_width=spec_width)
+
+
+def bench_eslice(pb, g, B, iters, rank, world, dev):
+    """ESlice chain-iterations/s for bench.py: B chains per GPU from the vignette's initial state,
+    streams resident in HBM (device-timed) and through host buffers (e2e)."""
+    import time
+    import torch
+    import torch.distributed as dist
+
+    par0 = np.concatenate([[g.x_r[0], float(g.setting("control.alpha")[0]) * g.x_r[0]],
+                           g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"),
+                           g.setting("control.hyper")])
+    par = np.tile(par0, (B, 1))
+    eps0 = g.setting("control.traj")
+    ch = Chains(pb, par, eps0)
+    opts_burn = vignette_opts(g, update_traj=False)
+    opts = vignette_opts(g, update_traj=True)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    nsets = iters + 8
+    nrm = torch.randn((nsets, B, ch.n_norm), dtype=torch.float64, device=dev, generator=gen)
+    unf = torch.rand((nsets, B, ITER_UNIF), dtype=torch.float64, device=dev, generator=gen).clamp_(1e-300, 1 - 1e-16)
+    stream = torch.cuda.current_stream(dev)
+    # burn-in like the vignette's first stage, then warm-up of the full iteration
+    for i in range(4):
+        ch.step_dev(opts_burn, nrm[i].data_ptr(), unf[i].data_ptr())
+    for i in range(4, 8):
+        ch.step_dev(opts, nrm[i].data_ptr(), unf[i].data_ptr())
+    torch.cuda.synchronize(dev)
+    before = ch.get()
+    if world > 1:
+        dist.barrier()
+    l0 = pb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(iters):
+        ch.step_dev(opts, nrm[8 + i].data_ptr(), unf[8 + i].data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    launches = pb.launch_count() - l0
+    after = ch.get()
+    # e2e: host streams (pinned) -> H2D -> iteration -> D2H of the summary block
+    nrm_h = torch.randn((B, ch.n_norm), dtype=torch.float64).pin_memory()
+    unf_h = torch.rand((B, ITER_UNIF), dtype=torch.float64).clamp_(1e-300, 1 - 1e-16).pin_memory()
+    summ_h = torch.empty((B, 4), dtype=torch.float64).pin_memory()
+    L = _lib.lib()
+    cl_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    lo_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    t0 = time.perf_counter()
+    for i in range(iters):
+        check(L.lna_chains_step(ch.h, C.byref(opts), nrm_h.data_ptr(), unf_h.data_ptr()), "lna_chains_step")
+        check(L.lna_chains_get(ch.h, None, None, None, cl_h.data_ptr(), lo_h.data_ptr(), None), "lna_chains_get")
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float((after["n_full_evals"] - before["n_full_evals"]).sum()),
+                        float((after["n_cheap_evals"] - before["n_cheap_evals"]).sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    tot = world * B * iters
+    return {"value": tot / (ms * 1e-3), "unit": "chain-iterations/s", "chains_per_gpu": B, "iters": iters,
+            "ms_per_iter": ms / iters, "e2e_value": tot / (e2e_ms * 1e-3),
+            "h2d_bytes_per_iter": int(nrm_h.numel() * 8 + unf_h.numel() * 8), "d2h_bytes_per_iter": int(B * 16),
+            "mean_full_evals_per_iter": float(cnt[0]) / tot, "mean_cheap_evals_per_iter": float(cnt[1]) / tot,
+            "consumed_full_evals_per_s": float(cnt[0]) / (ms * 1e-3), "gpu_launches": int(launches),
+            "spec_width": "auto", "finite_coalLog": bool(np.all(np.isfinite(after["coalLog"])))}

@@ -1,22 +1,562 @@
-// ESlice / chains entry points (stubs until the kernels land)
-#define LNA_STUB(name, ...) extern "C" int name(__VA_ARGS__) { return fail(#name ": not implemented yet"); }
-LNA_STUB(lna_param_slice_update, lna_problem *, int64_t, const double *, const double *, const double *, double *)
-LNA_STUB(lna_param_slice_update_all2, lna_problem *, int64_t, const double *, const double *, const double *,
-         const int32_t *, const double *, double *)
-LNA_STUB(lna_eslice_par_general, lna_problem *, int64_t, const double *, const double *, const double *,
-         const int32_t *, const double *, const double *, const double *, int, double *, double *, double *, double *,
-         double *, double *, double *, double *, int32_t *, int32_t *)
-LNA_STUB(lna_eslice_general_nc, lna_problem *, int64_t, const double *, const double *, const double *, const double *,
-         const double *, const double *, const double *, const double *, double *, double *, double *, double *,
-         int32_t *, int32_t *)
-LNA_STUB(lna_eslice_change_points, lna_problem *, int64_t, const double *, const double *, const double *,
-         const double *, const double *, const double *, int, double *, double *, double *, double *, double *,
-         double *, double *, double *, int32_t *, int32_t *)
-struct lna_chains { lna_problem *pb; };
-extern "C" lna_chains *lna_chains_create(lna_problem *, int64_t) { fail("lna_chains_create: not implemented yet"); return nullptr; }
-extern "C" void lna_chains_destroy(lna_chains *) {}
-LNA_STUB(lna_chains_init, lna_chains *, const double *, const double *)
-LNA_STUB(lna_chains_step, lna_chains *, const lna_mcmc_opts *, const double *, const double *)
-LNA_STUB(lna_chains_step_dev, lna_chains *, const lna_mcmc_opts *, const double *, const double *)
-LNA_STUB(lna_chains_get, lna_chains *, double *, double *, double *, double *, double *, int32_t *)
-extern "C" const double *lna_chains_summary_dev(lna_chains *) { return nullptr; }
+// lna_capi_eslice.inl -- C-ABI entry points of the Metropolis / elliptical-slice operators and of the
+// resident chain batches (included at the end of lna_capi.cu).
+
+// ------------------------------------------------------------------------------------------------
+// candidate scratch (slot-major) + per-chain decision arrays
+// ------------------------------------------------------------------------------------------------
+struct CandBuf {
+    long long NC = 0, B = 0;
+    double *cA = nullptr, *cL = nullptr, *cOde = nullptr, *cBeta = nullptr, *cLat = nullptr;
+    int *win_slot = nullptr, *n_evals = nullptr, *status = nullptr, *accept = nullptr;
+    double *cand_ll = nullptr, *theta = nullptr;
+};
+
+// slots >= base are used so that callers can keep their own staging below `base`
+static bool cand_alloc(lna_problem *pb, Scratch &s, size_t base, long long B, long long NC, CandBuf &cb) {
+    const DevProb &P = pb->dp;
+    const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nB = (size_t)P.nrow;
+    cb.B = B;
+    cb.NC = NC;
+    cb.cA = (double *)s.get(base + 0, sizeof(double) * nA * NC);
+    cb.cL = (double *)s.get(base + 1, sizeof(double) * nA * NC);
+    cb.cOde = (double *)s.get(base + 2, sizeof(double) * nO * NC);
+    cb.cBeta = (double *)s.get(base + 3, sizeof(double) * nB * NC);
+    cb.cLat = (double *)s.get(base + 4, sizeof(double) * nO * NC);
+    cb.win_slot = (int *)s.get(base + 5, sizeof(int) * B);
+    cb.n_evals = (int *)s.get(base + 6, sizeof(int) * B);
+    cb.status = (int *)s.get(base + 7, sizeof(int) * B);
+    cb.accept = (int *)s.get(base + 8, sizeof(int) * B);
+    cb.cand_ll = (double *)s.get(base + 9, sizeof(double) * B);
+    cb.theta = (double *)s.get(base + 10, sizeof(double) * B);
+    return cb.cA && cb.cL && cb.cOde && cb.cBeta && cb.cLat && cb.win_slot && cb.n_evals && cb.status && cb.accept &&
+           cb.cand_ll && cb.theta;
+}
+static constexpr size_t kCandSlots = 11;
+
+static FullOut cand_out(const CandBuf &cb) {
+    return FullOut{OutView{cb.cA, 1, cb.NC}, OutView{cb.cL, 1, cb.NC}, OutView{cb.cOde, 1, cb.NC},
+                   OutView{cb.cBeta, 1, cb.NC}, OutView{cb.cLat, 1, cb.NC}};
+}
+
+static int auto_width(const lna_problem *pb, long long B) {
+    // fill the machine (~512 resident FP64 threads per SM saturate the DFMA pipe) but not beyond
+    const long long target = (long long)pb->sm_count * 512;
+    int w = 1;
+    while (w < 32 && (long long)B * (w * 2) <= target) w *= 2;
+    return w;
+}
+
+template <int kProp>
+static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a) {
+    const DevProb &P = pb->dp;
+    const long long nthreads = B * W;
+    const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, B);
+    const unsigned grid = nblk(nthreads, block);
+#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, pb->tab_bytes, pb->stream>>>(P, B, a)
+    switch (W) {
+        case 1: LC(1); break;
+        case 2: LC(2); break;
+        case 4: LC(4); break;
+        case 8: LC(8); break;
+        case 16: LC(16); break;
+        case 32: LC(32); break;
+        default: return fail("speculation width must be 1,2,4,8,16 or 32 (got %d)", W);
+    }
+#undef LC
+    return launch_check(pb, "k_cand_eval");
+}
+
+static int launch_commit_fields(lna_problem *pb, long long B, const CandBuf &cb, OutView A, OutView L, OutView ode,
+                                OutView betaN, OutView latent) {
+    const DevProb &P = pb->dp;
+    CommitArgs ca{cb.win_slot, cb.NC, cb.cA, cb.cL, cb.cOde, cb.cBeta, cb.cLat, A, L, ode, betaN, latent,
+                  P.p * P.p * P.k, P.nrow * (P.p + 1), P.nrow, 0};
+    const long long n = B * (2LL * ca.nA + 2LL * ca.nOde + ca.nBeta);
+    k_commit_fields<<<nblk(n, 256), 256, 0, pb->stream>>>(B, ca);
+    return launch_check(pb, "k_commit_fields");
+}
+
+static int check_sir_sampler(const lna_problem *pb, const char *what) {
+    if (pb->dp.model != LNA_MODEL_SIR || pb->dp.nparam != 2)
+        return fail("%s: the reference's samplers are hard-wired to SIR (p = 2, nparam = 2)", what);
+    if (!pb->dp.has_init) return fail("%s: problem was created without a genealogy", what);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int lna_param_slice_update(lna_problem *pb, int64_t B, const double *param, const double *theta,
+                                      const double *newChs, double *param_new) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B;
+    Stage s(pb);
+    const double *dp = s.in(param, nB * P.npt), *dt = s.in(theta, nB), *dn = s.in(newChs, nB * P.nch);
+    double *dout = s.out(param_new, nB * P.npt);
+    if (!s.ok || !dp || !dt || !dn || !dout) return fail("lna_param_slice_update: bad arguments / staging failed");
+    k_param_slice_update<<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, item_view(dp, P.npt), dt, item_view(dn, P.nch), dout);
+    if (launch_check(pb, "k_param_slice_update")) return -1;
+    s.back(param_new, dout, nB * P.npt);
+    return s.finish("lna_param_slice_update");
+}
+
+extern "C" int lna_param_slice_update_all2(lna_problem *pb, int64_t B, const double *par_old, const double *theta,
+                                           const double *newChs, const int32_t *ESS_vec7, const double *prior8,
+                                           double *par_new) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    if (P.model != LNA_MODEL_SIR) return fail("lna_param_slice_update_all2: SIR only (hard-wired in the reference)");
+    if (!ESS_vec7 || !prior8) return fail("lna_param_slice_update_all2: null ESS_vec / prior");
+    const size_t nB = (size_t)B, npar = 2 + P.npt;
+    Stage s(pb);
+    const double *dp = s.in(par_old, nB * npar), *dt = s.in(theta, nB), *dn = s.in(newChs, nB * (npar - 1));
+    double *dout = s.out(par_new, nB * npar);
+    if (!s.ok || !dp || !dt || !dn || !dout) return fail("lna_param_slice_update_all2: bad arguments / staging failed");
+    CandArgs a{};
+    a.par = item_view(dp, npar);
+    a.normals = item_view(dn, npar - 1);
+    for (int i = 0; i < 8; ++i) a.pr[i] = prior8[i];
+    for (int i = 0; i < 7; ++i) a.ess[i] = ESS_vec7[i];
+    k_param_slice_update_all2<<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, a, dt, dout);
+    if (launch_check(pb, "k_param_slice_update_all2")) return -1;
+    s.back(par_new, dout, nB * npar);
+    return s.finish("lna_param_slice_update_all2");
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *par_old, const double *OriginTraj,
+                                      const double *prior8, const int32_t *ESS_vec7, const double *coal_log,
+                                      const double *normals, const double *uniforms, int spec_width, double *par_new,
+                                      double *Acube, double *Lcube, double *Ode_coarse, double *betaN,
+                                      double *LatentTraj, double *CoalLog, double *logOrigin, int32_t *n_evals,
+                                      int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (check_sir_sampler(pb, "lna_eslice_par_general")) return -1;
+    if (!par_old || !OriginTraj || !prior8 || !ESS_vec7 || !coal_log || !normals || !uniforms)
+        return fail("lna_eslice_par_general: null input");
+    if (ESS_vec7[6] != 0)
+        return fail("lna_eslice_par_general: ESS_vec[7] = 1 (the reference's self-mixing OriginTraj branch, "
+                    "LNA_functional.cpp:1660-1662) is not supported");
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
+    const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
+    const int W = spec_width > 0 ? spec_width : auto_width(pb, B);
+    Stage s(pb);
+    CandArgs a{};
+    a.par = item_view(s.in(par_old, nB * npar), npar);
+    a.origin = item_view(s.in(OriginTraj, nB * kp), kp);
+    a.normals = item_view(s.in(normals, nB * (npar - 1)), npar - 1);
+    a.uniforms = item_view(s.in(uniforms, nB * kMaxUnif), kMaxUnif);
+    a.coal_log = s.in(coal_log, nB);
+    for (int i = 0; i < 8; ++i) a.pr[i] = prior8[i];
+    for (int i = 0; i < 7; ++i) a.ess[i] = ESS_vec7[i];
+    double *dpar = s.tmp<double>(nB * npar), *dA = s.tmp<double>(nB * nA), *dL = s.tmp<double>(nB * nA);
+    double *dO = s.tmp<double>(nB * nO), *dbn = s.tmp<double>(nB * nrow), *dlat = s.tmp<double>(nB * nO);
+    double *dlo = s.tmp<double>(nB), *dcl = s.tmp<double>(nB);
+    CandBuf cb;
+    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * W, cb)) return fail("lna_eslice_par_general: device staging failed");
+    a.cand = cand_out(cb);
+    a.win_slot = cb.win_slot;
+    a.cand_ll = cb.cand_ll;
+    a.theta = cb.theta;
+    a.n_evals = cb.n_evals;
+    a.status = cb.status;
+    a.accept = cb.accept;
+    if (launch_cand<PROP_ESS_PAR>(pb, B, W, a)) return -1;
+    if (launch_commit_fields(pb, B, cb, item_out(dA, nA), item_out(dL, nA), item_out(dO, nO), item_out(dbn, nrow),
+                             item_out(dlat, nO)))
+        return -1;
+    k_commit_par<PROP_ESS_PAR><<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, a, item_out(dpar, npar), dcl, dlo, 1);
+    if (launch_check(pb, "k_commit_par")) return -1;
+    s.back(par_new, dpar, nB * npar);
+    s.back(Acube, dA, nB * nA);
+    s.back(Lcube, dL, nB * nA);
+    s.back(Ode_coarse, dO, nB * nO);
+    s.back(betaN, dbn, nB * nrow);
+    s.back(LatentTraj, dlat, nB * nO);
+    s.back(CoalLog, cb.cand_ll, nB);
+    s.back(logOrigin, dlo, nB);
+    s.back(n_evals, cb.n_evals, nB);
+    s.back(status, cb.status, nB);
+    return s.finish("lna_eslice_par_general");
+}
+
+extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                                        const double *OriginTraj, const double *coal_log, const double *normals,
+                                        const double *uniforms, int spec_width, double *param_new, double *Acube,
+                                        double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj,
+                                        double *CoalLog, double *LogChProb, int32_t *n_evals, int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (check_sir_sampler(pb, "lna_eslice_change_points")) return -1;
+    if (!param || !initial || !OriginTraj || !coal_log || !normals || !uniforms)
+        return fail("lna_eslice_change_points: null input");
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
+    const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
+    const int W = spec_width > 0 ? spec_width : auto_width(pb, B);
+    // par = c(initial, param): assemble on the host (small)
+    std::vector<double> par(nB * npar);
+    for (size_t b = 0; b < nB; ++b) {
+        par[b * npar] = initial[b * 2];
+        par[b * npar + 1] = initial[b * 2 + 1];
+        std::memcpy(&par[b * npar + 2], param + b * P.npt, sizeof(double) * P.npt);
+    }
+    Stage s(pb);
+    CandArgs a{};
+    a.par = item_view(s.in(par.data(), nB * npar), npar);
+    a.origin = item_view(s.in(OriginTraj, nB * kp), kp);
+    a.normals = item_view(s.in(normals, nB * P.nch), P.nch);
+    a.uniforms = item_view(s.in(uniforms, nB * kMaxUnif), kMaxUnif);
+    a.coal_log = s.in(coal_log, nB);
+    double *dpar = s.tmp<double>(nB * npar), *dA = s.tmp<double>(nB * nA), *dL = s.tmp<double>(nB * nA);
+    double *dO = s.tmp<double>(nB * nO), *dbn = s.tmp<double>(nB * nrow), *dlat = s.tmp<double>(nB * nO);
+    double *dlcp = s.tmp<double>(nB), *dcl = s.tmp<double>(nB);
+    CandBuf cb;
+    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * W, cb))
+        return fail("lna_eslice_change_points: device staging failed");
+    // the host vector must outlive the async copy
+    if (cudaStreamSynchronize(pb->stream) != cudaSuccess) return fail("lna_eslice_change_points: sync failed");
+    a.cand = cand_out(cb);
+    a.win_slot = cb.win_slot;
+    a.cand_ll = cb.cand_ll;
+    a.theta = cb.theta;
+    a.n_evals = cb.n_evals;
+    a.status = cb.status;
+    a.accept = cb.accept;
+    if (launch_cand<PROP_ESS_CHPT>(pb, B, W, a)) return -1;
+    if (launch_commit_fields(pb, B, cb, item_out(dA, nA), item_out(dL, nA), item_out(dO, nO), item_out(dbn, nrow),
+                             item_out(dlat, nO)))
+        return -1;
+    k_commit_par<PROP_ESS_CHPT><<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, a, item_out(dpar, npar), dcl, dlcp, 1);
+    if (launch_check(pb, "k_commit_par")) return -1;
+    std::vector<double> par_out(param_new ? nB * npar : 0);
+    s.back(param_new ? par_out.data() : nullptr, dpar, nB * npar);
+    s.back(Acube, dA, nB * nA);
+    s.back(Lcube, dL, nB * nA);
+    s.back(Ode_coarse, dO, nB * nO);
+    s.back(betaN, dbn, nB * nrow);
+    s.back(LatentTraj, dlat, nB * nO);
+    s.back(CoalLog, cb.cand_ll, nB);
+    s.back(LogChProb, dlcp, nB);
+    s.back(n_evals, cb.n_evals, nB);
+    s.back(status, cb.status, nB);
+    if (s.finish("lna_eslice_change_points")) return -1;
+    if (param_new)
+        for (size_t b = 0; b < nB; ++b) std::memcpy(param_new + b * P.npt, &par_out[b * npar + 2], sizeof(double) * P.npt);
+    return 0;
+}
+
+extern "C" int lna_eslice_general_nc(lna_problem *pb, int64_t B, const double *f_cur, const double *Ode_coarse,
+                                     const double *Acube, const double *Lcube, const double *betaN,
+                                     const double *coal_log, const double *normals, const double *uniforms,
+                                     double *LatentTraj, double *OriginTraj_new, double *logOrigin, double *CoalLog,
+                                     int32_t *n_evals, int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (check_sir_sampler(pb, "lna_eslice_general_nc")) return -1;
+    if (!f_cur || !Ode_coarse || !Acube || !Lcube || !betaN || !coal_log || !normals || !uniforms)
+        return fail("lna_eslice_general_nc: null input");
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, kp = (size_t)P.k * P.p;
+    const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
+    Stage s(pb);
+    TrajArgs a{};
+    a.f_cur = item_view(s.in(f_cur, nB * kp), kp);
+    a.normals = item_view(s.in(normals, nB * kp), kp);
+    a.uniforms = item_view(s.in(uniforms, nB * kMaxUnif), kMaxUnif);
+    a.A = item_view(s.in(Acube, nB * nA), nA);
+    a.L = item_view(s.in(Lcube, nB * nA), nA);
+    a.ode = item_view(s.in(Ode_coarse, nB * nO), nO);
+    a.betaN = item_view(s.in(betaN, nB * nrow), nrow);
+    a.coal_log = s.in(coal_log, nB);
+    double *dlat = s.tmp<double>(nB * nO), *dor = s.tmp<double>(nB * kp), *dcl = s.tmp<double>(nB), *dlo = s.tmp<double>(nB);
+    int32_t *dne = s.tmp<int32_t>(nB), *dst = s.tmp<int32_t>(nB);
+    if (!s.ok) return fail("lna_eslice_general_nc: device staging failed");
+    a.latent = item_out(dlat, nO);
+    a.origin_new = item_out(dor, kp);
+    a.CoalLog = dcl;
+    a.logOrigin = dlo;
+    a.n_evals = dne;
+    a.status = dst;
+    const int block = pick_block(pb, B);
+    k_eslice_traj<<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, B, a);
+    if (launch_check(pb, "k_eslice_traj")) return -1;
+    s.back(LatentTraj, dlat, nB * nO);
+    s.back(OriginTraj_new, dor, nB * kp);
+    s.back(logOrigin, dlo, nB);
+    s.back(CoalLog, dcl, nB);
+    s.back(n_evals, dne, nB);
+    s.back(status, dst, nB);
+    return s.finish("lna_eslice_general_nc");
+}
+
+// ------------------------------------------------------------------------------------------------
+// resident chain batches
+// ------------------------------------------------------------------------------------------------
+struct lna_chains {
+    lna_problem *pb = nullptr;
+    long long B = 0;
+    int W = 1;
+    // slot-major state: field[j*B + c]
+    double *par = nullptr, *origin = nullptr, *A = nullptr, *L = nullptr, *ode = nullptr, *betaN = nullptr,
+           *latent = nullptr, *coalLog = nullptr, *logOrigin = nullptr, *summary = nullptr;
+    int *counters = nullptr;  // [4][B]: n_full, n_cheap, n_mh_accept, status
+    int *tmp_i = nullptr;     // [2][B]
+    double *tmp_d = nullptr;  // [B]
+    CandBuf cb;
+    Scratch cand_scratch;
+    std::vector<void *> owned;
+    double *stage_n = nullptr, *stage_u = nullptr;  // staging for host-pointer steps
+    size_t n_norm = 0, n_unif = 0;
+};
+
+__global__ void k_bump(long long B, const int *n_evals, const int *accept, const int *status, const int *win_slot,
+                       int *counters, int which_evals, int count_accept) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    counters[(long long)which_evals * B + c] += n_evals[c];
+    if (count_accept) counters[2 * B + c] += accept[c];
+    // NEG/NAN bits of a proposal that was not adopted say nothing about the chain's state
+    const int adopted = win_slot ? (win_slot[c] >= 0) : 1;
+    counters[3 * B + c] |= adopted ? status[c] : (status[c] & (ST_CHOL_FAIL | ST_CAP_HIT));
+}
+
+__global__ void k_summary(long long B, const double *coalLog, const double *logOrigin, const int *counters,
+                          double *summary) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    summary[c * 4 + 0] = coalLog[c];
+    summary[c * 4 + 1] = logOrigin[c];
+    summary[c * 4 + 2] = (double)counters[c];
+    summary[c * 4 + 3] = (double)counters[3 * B + c];
+}
+
+template <class T>
+static T *chains_alloc(lna_chains *ch, size_t n) {
+    T *d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    ch->owned.push_back(d);
+    return d;
+}
+
+extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
+    if (!pb || B <= 0) {
+        fail("lna_chains_create: bad arguments");
+        return nullptr;
+    }
+    if (check_sir_sampler(pb, "lna_chains_create")) return nullptr;
+    cudaSetDevice(pb->device);
+    const DevProb &P = pb->dp;
+    lna_chains *ch = new lna_chains();
+    ch->pb = pb;
+    ch->B = B;
+    const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
+    const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
+    ch->par = chains_alloc<double>(ch, nB * npar);
+    ch->origin = chains_alloc<double>(ch, nB * kp);
+    ch->A = chains_alloc<double>(ch, nB * nA);
+    ch->L = chains_alloc<double>(ch, nB * nA);
+    ch->ode = chains_alloc<double>(ch, nB * nO);
+    ch->betaN = chains_alloc<double>(ch, nB * nrow);
+    ch->latent = chains_alloc<double>(ch, nB * nO);
+    ch->coalLog = chains_alloc<double>(ch, nB);
+    ch->logOrigin = chains_alloc<double>(ch, nB);
+    ch->summary = chains_alloc<double>(ch, nB * 4);
+    ch->counters = chains_alloc<int>(ch, nB * 4);
+    ch->tmp_i = chains_alloc<int>(ch, nB * 2);
+    ch->tmp_d = chains_alloc<double>(ch, nB);
+    ch->n_norm = (npar - 1) + kp;
+    ch->n_unif = LNA_ITER_UNIF;
+    ch->stage_n = chains_alloc<double>(ch, nB * ch->n_norm);
+    ch->stage_u = chains_alloc<double>(ch, nB * ch->n_unif);
+    if (!ch->par || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
+        !ch->logOrigin || !ch->summary || !ch->counters || !ch->tmp_i || !ch->tmp_d || !ch->stage_n || !ch->stage_u) {
+        fail("lna_chains_create: device allocation failed");
+        lna_chains_destroy(ch);
+        return nullptr;
+    }
+    cudaMemsetAsync(ch->counters, 0, sizeof(int) * nB * 4, pb->stream);
+    return ch;
+}
+
+extern "C" void lna_chains_destroy(lna_chains *ch) {
+    if (!ch) return;
+    cudaSetDevice(ch->pb->device);
+    cudaStreamSynchronize(ch->pb->stream);
+    for (void *p : ch->owned) cudaFree(p);
+    ch->cand_scratch.release();
+    delete ch;
+}
+
+static View soa_view(const double *d, long long B) { return View{d, 1, B}; }
+static OutView soa_out(double *d, long long B) { return OutView{d, 1, B}; }
+
+extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *OriginTraj) {
+    if (!ch || !par || !OriginTraj) return fail("lna_chains_init: null argument");
+    lna_problem *pb = ch->pb;
+    const DevProb &P = pb->dp;
+    const long long B = ch->B;
+    const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
+    Stage s(pb);
+    const double *dpar = s.in(par, nB * npar), *dor = s.in(OriginTraj, nB * kp);
+    if (!s.ok) return fail("lna_chains_init: device staging failed");
+    k_to_soa<<<nblk((long long)(nB * npar), 256), 256, 0, pb->stream>>>(B, (int)npar, dpar, ch->par);
+    if (launch_check(pb, "k_to_soa")) return -1;
+    k_to_soa<<<nblk((long long)(nB * kp), 256), 256, 0, pb->stream>>>(B, (int)kp, dor, ch->origin);
+    if (launch_check(pb, "k_to_soa")) return -1;
+    // New_Param_List + TransformTraj + volz_loglik_nh2 straight into the state (general_change_point.R:507-536)
+    FullOut out{soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B), soa_out(ch->betaN, B), soa_out(ch->latent, B)};
+    const View vp{ch->par + 2 * B, 1, B}, vi{ch->par, 1, B}, vo{ch->origin, 1, B};
+    const int block = pick_block(pb, B);
+    k_full_loglik<0, true><<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, B, vp, vi, vo, out, ch->coalLog,
+                                                                                 ch->counters + 3 * B);
+    if (launch_check(pb, "k_full_loglik")) return -1;
+    CK(cudaMemsetAsync(ch->logOrigin, 0, sizeof(double) * nB, pb->stream));
+    CK(cudaMemsetAsync(ch->counters, 0, sizeof(int) * nB * 3, pb->stream));
+    return s.finish("lna_chains_init");
+}
+
+static int chains_cand_args(lna_chains *ch, const lna_mcmc_opts *o, const double *normals, const double *uniforms,
+                            int unif_off, int W, CandArgs &a) {
+    lna_problem *pb = ch->pb;
+    const long long B = ch->B;
+    if (ch->cb.NC < B * W || ch->cb.B != B) {
+        if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * W, ch->cb))
+            return fail("lna_chains_step: candidate scratch allocation failed");
+    }
+    a = CandArgs{};
+    a.par = soa_view(ch->par, B);
+    a.origin = soa_view(ch->origin, B);
+    a.normals = View{normals, (long long)ch->n_norm, 1};
+    a.uniforms = View{uniforms + unif_off, (long long)ch->n_unif, 1};
+    a.coal_log = ch->coalLog;
+    for (int i = 0; i < 8; ++i) a.pr[i] = o->prior8[i];
+    for (int i = 0; i < 7; ++i) a.ess[i] = o->ESS_vec[i];
+    a.gamma_prior[0] = o->gamma_prior[0];
+    a.gamma_prior[1] = o->gamma_prior[1];
+    a.gamma_prop = o->gamma_prop;
+    a.cand = cand_out(ch->cb);
+    a.win_slot = ch->cb.win_slot;
+    a.cand_ll = ch->cb.cand_ll;
+    a.theta = ch->cb.theta;
+    a.n_evals = ch->cb.n_evals;
+    a.status = ch->cb.status;
+    a.accept = ch->cb.accept;
+    return 0;
+}
+
+template <int kProp>
+static int chains_stage(lna_chains *ch, const lna_mcmc_opts *o, const double *normals, const double *uniforms,
+                        int unif_off, int W) {
+    lna_problem *pb = ch->pb;
+    const DevProb &P = pb->dp;
+    const long long B = ch->B;
+    CandArgs a;
+    if (chains_cand_args(ch, o, normals, uniforms, unif_off, W, a)) return -1;
+    if (launch_cand<kProp>(pb, B, W, a)) return -1;
+    if (launch_commit_fields(pb, B, ch->cb, soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B),
+                             soa_out(ch->betaN, B), soa_out(ch->latent, B)))
+        return -1;
+    k_commit_par<kProp><<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, a, soa_out(ch->par, B), ch->coalLog,
+                                                             kProp == PROP_ESS_PAR ? ch->logOrigin : nullptr, 0);
+    if (launch_check(pb, "k_commit_par")) return -1;
+    const bool mh = (kProp == PROP_GAMMA_RW || kProp == PROP_HYPER_NOOP);
+    k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->cb.n_evals, ch->cb.accept, ch->cb.status, ch->cb.win_slot,
+                                                 ch->counters, 0, mh ? 1 : 0);
+    return launch_check(pb, "k_bump");
+}
+
+extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,
+                                   const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
+    lna_problem *pb = ch->pb;
+    cudaSetDevice(pb->device);
+    const DevProb &P = pb->dp;
+    const long long B = ch->B;
+    if (o->ESS_vec[6] != 0) return fail("lna_chains_step: ESS_vec[7] = 1 is not supported");
+    const int W = o->spec_width > 0 ? o->spec_width : auto_width(pb, B);
+    if (ch->cb.NC < B * W || ch->cb.B != B) {  // size the candidate scratch once for the widest stage
+        if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * W, ch->cb))
+            return fail("lna_chains_step: candidate scratch allocation failed");
+    }
+    // 1. Update_Param_each_Norm: gamma random walk (entry c) and the no-op hyper entry (d)  [A.17]
+    if (chains_stage<PROP_GAMMA_RW>(ch, o, normals, uniforms, 0, 1)) return -1;
+    if (o->hyper_noop_mh && chains_stage<PROP_HYPER_NOOP>(ch, o, normals, uniforms, 2, 1)) return -1;
+    // 2. update_Par_ESlice_combine -> ESlice_par_General
+    if (chains_stage<PROP_ESS_PAR>(ch, o, normals, uniforms, 3, W)) return -1;
+    // 3. updateTraj_general_NC -> ESlice_general_NC (in place on the state)
+    if (o->update_traj) {
+        TrajArgs a{};
+        const int npar = 2 + P.npt;
+        a.f_cur = soa_view(ch->origin, B);
+        a.normals = View{normals + (npar - 1), (long long)ch->n_norm, 1};
+        a.uniforms = View{uniforms + 3 + LNA_ESLICE_MAX_UNIF, (long long)ch->n_unif, 1};
+        a.A = soa_view(ch->A, B);
+        a.L = soa_view(ch->L, B);
+        a.ode = soa_view(ch->ode, B);
+        a.betaN = soa_view(ch->betaN, B);
+        a.coal_log = ch->coalLog;
+        a.latent = soa_out(ch->latent, B);
+        a.origin_new = soa_out(ch->origin, B);
+        a.CoalLog = ch->tmp_d;
+        a.logOrigin = ch->logOrigin;
+        a.n_evals = ch->tmp_i;
+        a.status = ch->tmp_i + B;
+        const int block = pick_block(pb, B);
+        k_eslice_traj<<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, B, a);
+        if (launch_check(pb, "k_eslice_traj")) return -1;
+        CK(cudaMemcpyAsync(ch->coalLog, ch->tmp_d, sizeof(double) * (size_t)B, cudaMemcpyDeviceToDevice, pb->stream));
+        k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->tmp_i, ch->tmp_i, ch->tmp_i + B, nullptr, ch->counters, 1, 0);
+        if (launch_check(pb, "k_bump")) return -1;
+    }
+    k_summary<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->coalLog, ch->logOrigin, ch->counters, ch->summary);
+    return launch_check(pb, "k_summary");
+}
+
+extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,
+                               const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
+    lna_problem *pb = ch->pb;
+    cudaSetDevice(pb->device);
+    const size_t nB = (size_t)ch->B;
+    CK(cudaMemcpyAsync(ch->stage_n, normals, sizeof(double) * nB * ch->n_norm, cudaMemcpyHostToDevice, pb->stream));
+    CK(cudaMemcpyAsync(ch->stage_u, uniforms, sizeof(double) * nB * ch->n_unif, cudaMemcpyHostToDevice, pb->stream));
+    return lna_chains_step_dev(ch, o, ch->stage_n, ch->stage_u);
+}
+
+extern "C" int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
+                              double *logOrigin, int32_t *counters) {
+    if (!ch) return fail("lna_chains_get: null chains");
+    lna_problem *pb = ch->pb;
+    const DevProb &P = pb->dp;
+    const long long B = ch->B;
+    const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p, nO = (size_t)P.nrow * (P.p + 1);
+    Stage s(pb);
+    auto fetch = [&](double *h, const double *soa, size_t n) -> int {
+        if (!h) return 0;
+        double *d = s.tmp<double>(nB * n);
+        if (!d) return -1;
+        k_from_soa<<<nblk((long long)(nB * n), 256), 256, 0, pb->stream>>>(B, (int)n, soa, d);
+        if (launch_check(pb, "k_from_soa")) return -1;
+        s.back(h, d, nB * n);
+        return 0;
+    };
+    if (fetch(par, ch->par, npar) || fetch(OriginTraj, ch->origin, kp) || fetch(LatentTraj, ch->latent, nO)) return -1;
+    if (coalLog) s.back(coalLog, ch->coalLog, nB);
+    if (logOrigin) s.back(logOrigin, ch->logOrigin, nB);
+    if (counters) {
+        // [4][B] -> B x 4
+        std::vector<int> tmp(nB * 4);
+        if (cudaStreamSynchronize(pb->stream) != cudaSuccess ||
+            cudaMemcpy(tmp.data(), ch->counters, sizeof(int) * nB * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail("lna_chains_get: counter copy failed");
+        for (size_t c = 0; c < nB; ++c)
+            for (int j = 0; j < 4; ++j) counters[c * 4 + j] = tmp[(size_t)j * nB + c];
+    }
+    return s.finish("lna_chains_get");
+}
+
+extern "C" const double *lna_chains_summary_dev(lna_chains *ch) { return ch ? ch->summary : nullptr; }

@@ -1,3 +1,584 @@
-// lna_eslice.cuh -- elliptical-slice kernels (filled in below)
+// lna_eslice.cuh -- batched Metropolis / elliptical-slice state machines (sm_100a).
+//
+// Reference (file:line into MingweiWilliamTang/LNAphyloDyn):
+//   Update_Param                 src/LNA_functional.cpp:1212-1243
+//   Param_Slice_update(_all2)    src/LNA_functional.cpp:1246-1253, 1268-1314
+//   ESlice_change_points         src/LNA_functional.cpp:1317-1409
+//   ESlice_par_General           src/LNA_functional.cpp:1532-1688
+//   ESlice_general_NC            src/LNA_functional.cpp:1690-1778
+//   Update_Param_each_Norm       R/LNA_chpt_slice.R:169-265 (gamma random walk, no-op hyper entry)
+//
+// Key fact used here: the sequence of slice angles theta_1, theta_2, ... depends only on the
+// pre-drawn uniforms (the bracket shrinks towards 0 by the SIGN of theta), never on likelihood
+// values.  So W candidates of one chain are evaluated speculatively by W adjacent lanes and a
+// warp ballot picks the first one the sequential loop would have accepted -- exactly the same
+// result, at 1/W of the sequential latency.
 #pragma once
 #include "lna_kernels.cuh"
+
+namespace lna {
+
+enum : int { PROP_PLAIN = 0, PROP_GAMMA_RW = 1, PROP_HYPER_NOOP = 2, PROP_ESS_PAR = 3, PROP_ESS_CHPT = 4 };
+
+constexpr int kMaxUnif = 22;
+constexpr double kLnSqrt2Pi = 0.918938533204672741780329736406;  // R's M_LN_SQRT_2PI
+
+// R::dnorm(x, mu, sigma, log=TRUE)  (nmath/dnorm.c)
+__device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {
+    const double z = (x - mu) / sigma;
+    return -(kLnSqrt2Pi + 0.5 * z * z + log(sigma));
+}
+
+// Contraction-proof rotation a*cos + b*sin: evaluated identically wherever it is inlined, so the
+// parameters a candidate was evaluated at and the ones committed to the chain state are the same bits.
+__device__ __forceinline__ double rot(double a, double ct, double b, double sn) {
+    return __dadd_rn(__dmul_rn(a, ct), __dmul_rn(b, sn));
+}
+
+// Everything a proposal needs besides per-change-point data.
+struct PropScalars {
+    double S0, I0, R0, gam;       // evaluated values
+    double ct, sn;                // cos/sin(theta)
+    double hyper_old, hyper_new;  // change-ratio scale before / after
+    int rot_ch;                   // ESS_vec[5]
+};
+
+// par layout (SIR): [S0, I0, R0, gamma, ch_1..ch_nch, hyper]  
+template <int kProp>
+struct ChProp {
+    View par;
+    View nrm;
+    long long c;
+    int off;  // index of ch_1 inside par
+    PropScalars x;
+    __device__ __forceinline__ double ch(int j) const {
+        const double cj = par.at(c, off + j);
+        if (kProp == PROP_HYPER_NOOP) {
+            // exp(log(ch) * hyper / hyper), R/LNA_chpt_slice.R:238-241 (ulp-level perturbation, A.17)
+            return exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_old));
+        } else if (kProp == PROP_ESS_PAR) {
+            if (!x.rot_ch) return cj;
+            const double z = __dmul_rn(log(cj), x.hyper_old);        // :1296
+            const double zp = rot(z, x.ct, nrm.at(c, 3 + j), x.sn);  // :1299
+            return exp(__ddiv_rn(zp, x.hyper_new));                  // :1310
+        } else if (kProp == PROP_ESS_CHPT) {
+            const double nu = __ddiv_rn(nrm.at(c, j), x.hyper_old);  // :1344
+            return exp(rot(log(cj), x.ct, nu, x.sn));                // :1249-1251
+        } else {
+            return cj;
+        }
+    }
+};
+
+// Slice-angle generator: replays the reference's bracket logic from the uniforms.
+struct ThetaSeq {
+    double th, lo, hi;
+    int j;  // number of angles generated so far
+    __device__ __forceinline__ void init() {
+        th = kTwoPi;
+        lo = 0.0;
+        hi = kTwoPi;
+        j = 0;
+    }
+    // advance to angle number `i` (1-based); unif(q) = q-th uniform of the call (0 = u, 1 = theta_1 ...)
+    template <class U>
+    __device__ __forceinline__ void advance(int i, const U &unif) {
+        while (j < i) {
+            ++j;
+            if (j == 1) {
+                th = 0.0 + (kTwoPi - 0.0) * unif(1);  // R::runif(0, 2*pi)
+                lo = th - kTwoPi;
+                hi = th;
+            } else {
+                if (th < 0.0) lo = th;
+                else hi = th;
+                th = lo + (hi - lo) * unif(j);  // R::runif(theta_min, theta_max)
+            }
+        }
+    }
+};
+
+struct CandArgs {
+    View par;        // chain state, npar per chain
+    View origin;     // k*p per chain
+    View normals;    // per-call normals
+    View uniforms;   // per-call uniforms
+    const double *coal_log;  // [B]
+    double pr[8];    // priorList (4 x (mean, sd))
+    int ess[7];
+    double gamma_prior[2], gamma_prop;
+    FullOut cand;    // candidate scratch: slot-major (sb = 1, sj = NC)
+    int *win_slot;   // [B] winning scratch slot, -1 = keep current state
+    double *cand_ll; // [B] log-likelihood of the winner (or of the rejected MH proposal)
+    double *theta;   // [B] accepted angle (ESS) / proposed log-gamma (MH gamma)
+    int *n_evals;    // [B] evaluations the sequential reference loop would have made
+    int *status;     // [B]
+    int *accept;     // [B] MH accept flag (MH kinds)
+};
+
+// Whitened scalars of Param_Slice_update_all2 (:1287-1296) and their rotated images (:1299-1311).
+struct EssParPre {
+    double z0, z1, z2, zh;  // (log I0 - m)/s, (log R0 - m)/s, (log gamma - m)/s, (log hyper - m)/s
+};
+
+__device__ __forceinline__ void ess_par_scalars(const CandArgs &a, long long c, int npar, const EssParPre &z,
+                                                double theta, PropScalars &x) {
+    double sn, ct;
+    sincos(theta, &sn, &ct);
+    x.ct = ct;
+    x.sn = sn;
+    const double I0 = a.par.at(c, 1), R0 = a.par.at(c, 2), gam = a.par.at(c, 3), hy = a.par.at(c, npar - 1);
+    x.S0 = a.par.at(c, 0);
+    x.hyper_old = hy;
+    x.I0 = a.ess[0] ? exp(__dadd_rn(__dmul_rn(rot(z.z0, ct, a.normals.at(c, 0), sn), a.pr[1]), a.pr[0])) : I0;
+    x.R0 = a.ess[1] ? exp(__dadd_rn(__dmul_rn(rot(z.z1, ct, a.normals.at(c, 1), sn), a.pr[3]), a.pr[2])) : R0;
+    x.gam = a.ess[2] ? exp(__dadd_rn(__dmul_rn(rot(z.z2, ct, a.normals.at(c, 2), sn), a.pr[5]), a.pr[4])) : gam;
+    x.hyper_new =
+        a.ess[4] ? exp(__dadd_rn(__dmul_rn(rot(z.zh, ct, a.normals.at(c, npar - 2), sn), a.pr[7]), a.pr[6])) : hy;
+    x.rot_ch = a.ess[5];
+}
+
+__device__ __forceinline__ EssParPre ess_par_pre(const CandArgs &a, long long c, int npar) {
+    EssParPre z;
+    z.z0 = __ddiv_rn(__dsub_rn(log(a.par.at(c, 1)), a.pr[0]), a.pr[1]);
+    z.z1 = __ddiv_rn(__dsub_rn(log(a.par.at(c, 2)), a.pr[2]), a.pr[3]);
+    z.z2 = __ddiv_rn(__dsub_rn(log(a.par.at(c, 3)), a.pr[4]), a.pr[5]);
+    z.zh = __ddiv_rn(__dsub_rn(log(a.par.at(c, npar - 1)), a.pr[6]), a.pr[7]);
+    return z;
+}
+
+// ================================================================================================
+// Candidate evaluation kernel.  W lanes per chain (W = 1 for the MH kinds); slot = global thread id.
+//   PROP_GAMMA_RW / PROP_HYPER_NOOP : one FULL evaluation + MH test (Update_Param)
+//   PROP_ESS_PAR  : ESlice_par_General  (candidates 1..20, then revert)
+//   PROP_ESS_CHPT : ESlice_change_points (candidates 1..21, then revert; a Cholesky failure aborts)
+// SIR (p = 2) only, like the reference's samplers (hard-wired subvec(0,1) / subvec(2,..)).
+// ================================================================================================
+template <int kProp, int W>
+__global__ void __launch_bounds__(128)
+k_cand_eval(DevProb P, long long B, CandArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables T = stage_tables(P, smem);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c = t / W;
+    const int w = (int)(t % W);
+    const bool valid = c < B;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (W >= 32) ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(W - 1)));
+    const int npar = 2 + P.npt;
+    const long long cc = valid ? c : 0;  // keep loads in range for idle lanes
+    constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
+    constexpr int kMaxCand = (kProp == PROP_ESS_PAR) ? 20 : (kProp == PROP_ESS_CHPT ? 21 : 1);
+
+    auto unif = [&](int q) { return a.uniforms.at(cc, q); };
+    EpsFromView eps{a.origin, cc, P.k};
+
+    if (!kIsEss) {
+        // ---- Metropolis step: Update_Param_each_Norm entry + Update_Param ------------------------
+        if (!valid) return;
+        PropScalars x;
+        x.S0 = a.par.at(c, 0);
+        x.I0 = a.par.at(c, 1);
+        x.R0 = a.par.at(c, 2);
+        x.gam = a.par.at(c, 3);
+        x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
+        x.ct = 1.0;
+        x.sn = 0.0;
+        x.rot_ch = 0;
+        double offset = 0.0, prop = 0.0;
+        int iu = 0;
+        if (kProp == PROP_GAMMA_RW) {
+            // log gamma' = log gamma + runif(-po, po); offset = dnorm(new) - dnorm(old)  (:217-218)
+            const double raw = log(x.gam), po = a.gamma_prop;
+            const double rnew = raw + (-po + (po - (-po)) * unif(iu++));
+            offset = dnorm_log(rnew, a.gamma_prior[0], a.gamma_prior[1]) - dnorm_log(raw, a.gamma_prior[0], a.gamma_prior[1]);
+            x.gam = exp(rnew);
+            prop = rnew;
+        }
+        ChProp<kProp> chs{a.par, a.normals, c, 4, x};
+        double ll;
+        int st = 0;
+        sir_full_eval<true>(P, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+        const double u = unif(kProp == PROP_GAMMA_RW ? 1 : 0);
+        const double acc_a = ll - a.coal_log[c] + offset;
+        // a Cholesky failure is an exception in the reference: tryCatch keeps the old state
+        const bool acc = !(st & ST_CHOL_FAIL) && (log(u) < acc_a);
+        a.win_slot[c] = acc ? (int)t : -1;
+        a.cand_ll[c] = ll;
+        a.theta[c] = prop;
+        a.n_evals[c] = 1;
+        a.status[c] = st;
+        a.accept[c] = acc ? 1 : 0;
+        return;
+    } else {
+        // ---- elliptical slice: speculative waves of W candidates ---------------------------------
+        EssParPre zpre{};
+        double hyper_old = 0.0, logy = 0.0;
+        if (valid) {
+            if (kProp == PROP_ESS_PAR) zpre = ess_par_pre(a, c, npar);
+            hyper_old = a.par.at(c, npar - 1);
+            logy = a.coal_log[c] + log(unif(0));
+        }
+        ThetaSeq ts;
+        ts.init();
+        bool done = !valid;
+        for (int wave = 0;; ++wave) {
+            const int i = wave * W + w + 1;  // candidate number in the sequential loop
+            const bool active = !done && i <= kMaxCand;
+            double ll = kSentinel;
+            int st = 0;
+            if (active) {
+                ts.advance(i, unif);
+                PropScalars x;
+                if (kProp == PROP_ESS_PAR) {
+                    ess_par_scalars(a, c, npar, zpre, ts.th, x);
+                } else {
+                    double sn, ct;
+                    sincos(ts.th, &sn, &ct);
+                    x.ct = ct;
+                    x.sn = sn;
+                    x.S0 = a.par.at(c, 0);
+                    x.I0 = a.par.at(c, 1);
+                    x.R0 = a.par.at(c, 2);
+                    x.gam = a.par.at(c, 3);
+                    x.hyper_old = x.hyper_new = hyper_old;
+                    x.rot_ch = 1;
+                }
+                ChProp<kProp> chs{a.par, a.normals, c, 4, x};
+                sir_full_eval<true>(P, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+            }
+            const bool failed = active && (st & ST_CHOL_FAIL);
+            // ESlice_par_General catches the exception and shrinks on (:1641-1651); ESlice_change_points
+            // does not catch it, so the first failing candidate aborts the update.
+            const bool stop_here = active && ((ll > logy && !failed) || (kProp == PROP_ESS_CHPT && failed));
+            const unsigned m = __ballot_sync(0xffffffffu, stop_here) & gmask;
+            if (!done) {
+                if (m) {
+                    const int winner = __ffs(m) - 1;
+                    if (lane == winner) {
+                        a.win_slot[c] = failed ? -1 : (int)t;
+                        a.cand_ll[c] = ll;
+                        a.theta[c] = ts.th;
+                        a.n_evals[c] = i;
+                        a.status[c] = st;
+                    }
+                    done = true;
+                } else if ((wave + 1) * W >= kMaxCand) {
+                    // 20-shrink cap: revert to the current parameters and recompute (:1609-1622 / :1363-1374)
+                    if (w == 0) {
+                        PropScalars x;
+                        x.ct = 1.0;
+                        x.sn = 0.0;
+                        x.S0 = a.par.at(c, 0);
+                        x.I0 = a.par.at(c, 1);
+                        x.R0 = a.par.at(c, 2);
+                        x.gam = a.par.at(c, 3);
+                        x.hyper_old = x.hyper_new = hyper_old;
+                        x.rot_ch = 0;
+                        ChProp<PROP_PLAIN> chs{a.par, a.normals, c, 4, x};
+                        sir_full_eval<true>(P, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+                        a.win_slot[c] = (st & ST_CHOL_FAIL) ? -1 : (int)t;
+                        a.cand_ll[c] = ll;
+                        a.theta[c] = 0.0;
+                        a.n_evals[c] = kMaxCand + 1;
+                        a.status[c] = st | ST_CAP_HIT;
+                    }
+                    done = true;
+                }
+            }
+            if (!__any_sync(0xffffffffu, !done)) break;
+        }
+    }
+}
+
+// ================================================================================================
+// Commit: copy the winning candidate's FT / coarse ODE / betaN / LatentTraj from scratch into the
+// destination (chain state or the caller's output arrays) and materialise the new parameter vector.
+// One thread per (chain, element).
+// ================================================================================================
+struct CommitArgs {
+    const int *win_slot;
+    long long NC;                       // scratch slots
+    const double *cA, *cL, *cOde, *cBeta, *cLat;  // candidate scratch (slot-major)
+    OutView A, L, ode, betaN, latent;  // destinations
+    int nA, nOde, nBeta;               // elements per item: p*p*k, nrow*(p+1), nrow
+    int copy_when_rejected;            // standalone entry points also want the evaluated candidate back
+};
+
+__global__ void k_commit_fields(long long B, CommitArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = 2 * a.nA + 2 * a.nOde + a.nBeta;
+    if (idx >= B * per) return;
+    const long long c = idx % B;
+    int e = (int)(idx / B);
+    const int slot = a.win_slot[c];
+    if (slot < 0) return;
+    if (e < a.nA) {
+        if (a.A.ok()) a.A.put(c, e, a.cA[(long long)e * a.NC + slot]);
+        return;
+    }
+    e -= a.nA;
+    if (e < a.nA) {
+        if (a.L.ok()) a.L.put(c, e, a.cL[(long long)e * a.NC + slot]);
+        return;
+    }
+    e -= a.nA;
+    if (e < a.nOde) {
+        if (a.ode.ok()) a.ode.put(c, e, a.cOde[(long long)e * a.NC + slot]);
+        return;
+    }
+    e -= a.nOde;
+    if (e < a.nOde) {
+        if (a.latent.ok()) a.latent.put(c, e, a.cLat[(long long)e * a.NC + slot]);
+        return;
+    }
+    e -= a.nOde;
+    if (a.betaN.ok()) a.betaN.put(c, e, a.cBeta[(long long)e * a.NC + slot]);
+}
+
+// New parameter vector of the accepted proposal (one thread per chain).  par_out may alias the chain
+// state: every entry is read before it is written by the same thread.
+template <int kProp>
+__global__ void k_commit_par(DevProb P, long long B, CandArgs a, OutView par_out, double *coalLog, double *logOrigin,
+                             int write_unaccepted) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    const int npar = 2 + P.npt, nch = P.nch;
+    const bool win = a.win_slot[c] >= 0;
+    if (!win && !write_unaccepted) return;
+    if (!win) {  // keep the current parameters (standalone entry points return them)
+        for (int j = 0; j < npar; ++j) par_out.put(c, j, a.par.at(c, j));
+        return;
+    }
+    if (coalLog) coalLog[c] = a.cand_ll[c];
+    if (kProp == PROP_GAMMA_RW) {
+        const double g = exp(a.theta[c]);
+        for (int j = 0; j < npar; ++j) par_out.put(c, j, j == 3 ? g : a.par.at(c, j));
+    } else if (kProp == PROP_HYPER_NOOP) {
+        PropScalars x{};
+        x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
+        ChProp<PROP_HYPER_NOOP> chs{a.par, a.normals, c, 4, x};
+        for (int j = 0; j < 4; ++j) par_out.put(c, j, a.par.at(c, j));
+        const double hy = a.par.at(c, npar - 1);
+        for (int j = 0; j < nch; ++j) par_out.put(c, 4 + j, chs.ch(j));
+        par_out.put(c, npar - 1, hy);
+    } else if (kProp == PROP_ESS_PAR) {
+        const bool reverted = a.status[c] & ST_CAP_HIT;
+        if (reverted) {
+            for (int j = 0; j < npar; ++j) par_out.put(c, j, a.par.at(c, j));
+        } else {
+            const EssParPre z = ess_par_pre(a, c, npar);
+            PropScalars x;
+            ess_par_scalars(a, c, npar, z, a.theta[c], x);
+            ChProp<PROP_ESS_PAR> chs{a.par, a.normals, c, 4, x};
+            const double s0 = a.par.at(c, 0);
+            double chv;
+            par_out.put(c, 0, s0);
+            // ch first (they read the OLD hyper through x, and par entries 4.. are only read here)
+            for (int j = 0; j < nch; ++j) {
+                chv = chs.ch(j);
+                par_out.put(c, 4 + j, chv);
+            }
+            par_out.put(c, 1, x.I0);
+            par_out.put(c, 2, x.R0);
+            par_out.put(c, 3, x.gam);
+            par_out.put(c, npar - 1, x.hyper_new);
+        }
+        if (logOrigin) {  // -1/2 sum over ALL rows (:1673-1678); OriginTraj is unchanged (ESS_vec[6] = 0)
+            double lo = 0.0;
+            for (int j = 0; j < P.k; ++j)
+                for (int q = 0; q < P.p; ++q) {
+                    const double v = a.origin.at(c, q * P.k + j);
+                    lo -= 0.5 * v * v;
+                }
+            logOrigin[c] = lo;
+        }
+    } else if (kProp == PROP_ESS_CHPT) {
+        const bool reverted = a.status[c] & ST_CAP_HIT;
+        PropScalars x{};
+        double sn, ct;
+        sincos(a.theta[c], &sn, &ct);
+        x.ct = ct;
+        x.sn = sn;
+        x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
+        ChProp<PROP_ESS_CHPT> chs{a.par, a.normals, c, 4, x};
+        for (int j = 0; j < 4; ++j) par_out.put(c, j, a.par.at(c, j));
+        const double hy = a.par.at(c, npar - 1);
+        double lcp = 0.0;
+        for (int j = 0; j < nch; ++j) {
+            const double v = reverted ? a.par.at(c, 4 + j) : chs.ch(j);
+            par_out.put(c, 4 + j, v);
+            const double d = log(v) * hy;  // LogChProb (:1395-1399)
+            lcp += -0.5 * d * d;
+        }
+        par_out.put(c, npar - 1, hy);
+        if (logOrigin) logOrigin[c] = lcp;  // slot reused for LogChProb
+    }
+}
+
+// ================================================================================================
+// ESlice_general_NC (volz likelihood): CHEAP evaluations only -- rotation of the latent increments,
+// TransformTraj and the per-cell coalescent sum -- so each chain runs its own sequential loop.
+// ================================================================================================
+struct TrajArgs {
+    View f_cur, normals, uniforms;      // k*p, k*p (column-major k x p), 22
+    View A, L, ode, betaN;              // FT, coarse ODE, betaN of the current parameters
+    const double *coal_log;             // [B]
+    OutView latent, origin_new;         // outputs (may alias the chain state: per-thread read-before-write)
+    double *CoalLog, *logOrigin;
+    int *n_evals, *status;
+};
+
+template <int kStoreMode, class FSrc>
+__device__ __forceinline__ double cheap_eval_sir(const DevProb &P, const Tables &T, const TrajArgs &a, long long c,
+                                                 const FSrc &f, bool &any_neg_all, const OutView *lat,
+                                                 const OutView *org, int &status) {
+    const int k = P.k, nrow = P.nrow;
+    double X0 = 0.0, X1 = 0.0;
+    VolzAcc va;
+    double S = a.ode.at(c, nrow), I = a.ode.at(c, 2 * nrow);
+    bool negall = (S < 0.0) | (I < 0.0);
+    if (kStoreMode) {
+        lat->put(c, 0, a.ode.at(c, 0));
+        lat->put(c, nrow, S);
+        lat->put(c, 2 * nrow, I);
+    }
+    va.row(P, T, 0, S, I, a.betaN.at(c, 0), negall);
+    for (int i = 0; i < k; ++i) {
+        const double e0 = f(i, 0), e1 = f(i, 1);
+        const double a00 = a.A.at(c, 4 * i), a10 = a.A.at(c, 4 * i + 1), a01 = a.A.at(c, 4 * i + 2), a11 = a.A.at(c, 4 * i + 3);
+        const double l00 = a.L.at(c, 4 * i), l10 = a.L.at(c, 4 * i + 1), l11 = a.L.at(c, 4 * i + 3);
+        const double nX0 = fma(a00, X0, a01 * X1) + l00 * e0;
+        const double nX1 = fma(a10, X0, a11 * X1) + fma(l10, e0, l11 * e1);
+        X0 = nX0;
+        X1 = nX1;
+        S = a.ode.at(c, nrow + i + 1) + X0;
+        I = a.ode.at(c, 2 * nrow + i + 1) + X1;
+        const bool neg = (S < 0.0) | (I < 0.0);
+        negall |= neg;
+        if (kStoreMode) {
+            lat->put(c, i + 1, a.ode.at(c, i + 1));
+            lat->put(c, nrow + i + 1, S);
+            lat->put(c, 2 * nrow + i + 1, I);
+            org->put(c, i, e0);
+            org->put(c, k + i, e1);
+        }
+        va.row(P, T, i + 1, S, I, a.betaN.at(c, i + 1), neg);
+    }
+    any_neg_all = negall;
+    return va.result(status);
+}
+
+__global__ void __launch_bounds__(128) k_eslice_traj(DevProb P, long long B, TrajArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables T = stage_tables(P, smem);
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    const int k = P.k;
+    auto unif = [&](int q) { return a.uniforms.at(c, q); };
+    int evals = 0, st = 0, stf = 0;
+    bool negall;
+    auto fcur = [&](int i, int q) { return a.f_cur.at(c, q * k + i); };
+    double logy;
+    const double lu = log(unif(0));
+    if (a.coal_log[c] != -99999999.0) {
+        logy = a.coal_log[c] + lu;
+    } else {  // recompute the current likelihood like the reference (:1717-1719)
+        logy = cheap_eval_sir<0>(P, T, a, c, fcur, negall, nullptr, nullptr, st) + lu;
+        evals++;
+        st = 0;
+    }
+    ThetaSeq ts;
+    ts.init();
+    ts.advance(1, unif);
+    double sn, ct;
+    sincos(ts.th, &sn, &ct);
+    auto fprime = [&](int i, int q) { return rot(a.f_cur.at(c, q * k + i), ct, a.normals.at(c, q * k + i), sn); };
+    double ll = cheap_eval_sir<0>(P, T, a, c, fprime, negall, nullptr, nullptr, st);
+    evals++;
+    int i = 0;
+    bool reverted = false;
+    while (negall || ll <= logy) {
+        i += 1;
+        if (i > 20) {
+            reverted = true;
+            break;
+        }
+        ts.advance(i + 1, unif);
+        sincos(ts.th, &sn, &ct);
+        st = 0;
+        ll = cheap_eval_sir<0>(P, T, a, c, fprime, negall, nullptr, nullptr, st);
+        evals++;
+    }
+    // final pass with the accepted angle (or the current f when the cap hit), storing the outputs
+    double lo = 0.0;
+    if (reverted) {
+        ll = cheap_eval_sir<1>(P, T, a, c, fcur, negall, &a.latent, &a.origin_new, stf);
+        stf |= ST_CAP_HIT;
+        for (int j = 0; j < k - 1; ++j)
+            for (int q = 0; q < 2; ++q) {
+                const double v = a.origin_new.base[c * a.origin_new.sb + (long long)(q * k + j) * a.origin_new.sj];
+                lo -= 0.5 * v * v;
+            }
+        evals++;
+    } else {
+        // logOrigin omits the LAST row (:1768)
+        for (int j = 0; j < k - 1; ++j)
+            for (int q = 0; q < 2; ++q) {
+                const double v = fprime(j, q);
+                lo -= 0.5 * v * v;
+            }
+        ll = cheap_eval_sir<1>(P, T, a, c, fprime, negall, &a.latent, &a.origin_new, stf);
+    }
+    a.CoalLog[c] = ll;
+    a.logOrigin[c] = lo;
+    a.n_evals[c] = evals;
+    a.status[c] = stf;
+}
+
+// Param_Slice_update / Param_Slice_update_all2 as stand-alone operators (one thread per item).
+__global__ void k_param_slice_update(DevProb P, long long B, View param, const double *theta, View newChs,
+                                     double *param_new) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double sn, ct;
+    sincos(theta[b], &sn, &ct);
+    for (int j = 0; j < P.npt; ++j) param_new[b * P.npt + j] = param.at(b, j);
+    for (int j = 0; j < P.nch; ++j)
+        param_new[b * P.npt + P.nparam + j] = exp(rot(log(param.at(b, P.nparam + j)), ct, newChs.at(b, j), sn));
+}
+
+__global__ void k_param_slice_update_all2(DevProb P, long long B, CandArgs a, const double *theta, double *par_new) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    const int npar = 2 + P.npt;
+    const EssParPre z = ess_par_pre(a, c, npar);
+    PropScalars x;
+    ess_par_scalars(a, c, npar, z, theta[c], x);
+    ChProp<PROP_ESS_PAR> chs{a.par, a.normals, c, 4, x};
+    double *o = par_new + c * npar;
+    o[0] = x.S0;
+    o[1] = x.I0;
+    o[2] = x.R0;
+    o[3] = x.gam;
+    for (int j = 0; j < P.nch; ++j) o[4 + j] = chs.ch(j);
+    o[npar - 1] = x.hyper_new;
+}
+
+// item-major <-> slot-major transposes for the resident chain state
+__global__ void k_to_soa(long long B, int n, const double *src_item_major, double *dst_soa) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * n) return;
+    const long long c = idx % B;
+    const int j = (int)(idx / B);
+    dst_soa[idx] = src_item_major[c * n + j];
+}
+__global__ void k_from_soa(long long B, int n, const double *src_soa, double *dst_item_major) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * n) return;
+    const long long c = idx / n;
+    const int j = (int)(idx % n);
+    dst_item_major[idx] = src_soa[(long long)j * B + c];
+}
+
+}  // namespace lna

@@ -496,7 +496,7 @@ double orc_log_like_traj_general2(const double *SdeTraj, const double *OdeTraj, 
 /* ---------------------------------------------------------------- coalescent likelihoods */
 
 static double volz_core(const orc_init *init, const double *f1, int nrow, int p, const double *betaN,
-                        double t_correct, const int *index, int transX, int nan_guard) {
+                        double t_correct, const int *index, int transX, int nan_guard, int *st_out) {
     /* volz_loglik_nh2: LNA_functional.cpp:1119-1176 (nh3 :1058-1113 = same without the NaN guard) */
     int n2 = nrow, n0 = init->ng - 1, L = 0;
     while (f1[L] < t_correct) {
@@ -505,7 +505,10 @@ static double volz_core(const orc_init *init, const double *f1, int nrow, int p,
     }
     for (int j = 1; j <= p; j++)
         for (int r = 0; r <= n0; r++)
-            if (f1[r + (size_t)j * nrow] < 0) return ORC_SENTINEL;
+            if (f1[r + (size_t)j * nrow] < 0) {
+                if (st_out) *st_out |= ORC_NEG_STATE;
+                return ORC_SENTINEL;
+            }
     int E = init->E;
     double *ll = (double *)malloc(sizeof(double) * (size_t)(E > 0 ? E : 1));
     int start = 0, has_nan = 0;
@@ -528,19 +531,23 @@ static double volz_core(const orc_init *init, const double *f1, int nrow, int p,
         }
     }
     double res;
-    if (nan_guard && has_nan) res = ORC_SENTINEL;
-    else res = accu2(ll, start);
+    if (nan_guard && has_nan) {
+        res = ORC_SENTINEL;
+        if (st_out) *st_out |= ORC_NAN;
+    } else {
+        res = accu2(ll, start);
+    }
     free(ll);
     return res;
 }
 
 double orc_volz_loglik_nh2(const orc_init *init, const double *f1, int nrow, int p, const double *betaN,
                            double t_correct, const int *index, int transX) {
-    return volz_core(init, f1, nrow, p, betaN, t_correct, index, transX, 1);
+    return volz_core(init, f1, nrow, p, betaN, t_correct, index, transX, 1, 0);
 }
 double orc_volz_loglik_nh3(const orc_init *init, const double *f1, int nrow, int p, const double *betaN,
                            double t_correct, const int *index, int transX) {
-    return volz_core(init, f1, nrow, p, betaN, t_correct, index, transX, 0);
+    return volz_core(init, f1, nrow, p, betaN, t_correct, index, transX, 0, 0);
 }
 
 static double kingman_core(const orc_init *init, const double *f1, int nrow, int col, double t_correct,
@@ -592,8 +599,9 @@ int orc_full_loglik(const orc_cfg *c, const orc_init *init, const double *param,
         return st;
     }
     orc_transform_traj(Ode_coarse, nrow, p, OriginTraj, k, Acube, Lcube, LatentTraj);
-    *coalLog = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, &c->x_i[2], c->transX);
-    return ORC_OK;
+    int vst = 0;
+    *coalLog = volz_core(init, LatentTraj, nrow, p, betaN, t_correct, &c->x_i[2], c->transX, 1, &vst);
+    return vst; /* ORC_NEG_STATE / ORC_NAN are informational: the value is the in-band -1e7 */
 }
 
 /* Update_Param: LNA_functional.cpp:1212-1243.  One uniform; accept iff log(u) < a. */
@@ -604,13 +612,13 @@ int orc_update_param(const orc_cfg *c, const orc_init *init, const double *param
                      double *coalLog_new) {
     int st = orc_full_loglik(c, init, param, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
                              Ode_coarse, betaN, LatentTraj, coalLog_new);
-    if (st != ORC_OK) { /* the reference throws here (-> R tryCatch keeps the old state) */
+    if (st & ORC_CHOL_FAIL) { /* the reference throws here (-> R tryCatch keeps the old state) */
         *accept = 0;
         return st;
     }
     double a = *coalLog_new - coal_log + prior_proposal_offset;
     *accept = (log(unif) < a) ? 1 : 0;
-    return ORC_OK;
+    return st;
 }
 
 /* ---------------------------------------------------------------- ESS rotations */
@@ -807,9 +815,9 @@ int orc_eslice_change_points(const orc_cfg *c, const orc_init *init, const doubl
     int st = orc_full_loglik(c, init, param_new, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
                              Ode_coarse, betaN, LatentTraj, &loglike);
     evals++;
-    status |= st; /* uncaught exception in the reference */
     int i = 0;
-    while (st == ORC_OK && loglike <= logy) {
+    /* a Cholesky failure is an uncaught exception in the reference: the update aborts */
+    while (!(st & ORC_CHOL_FAIL) && loglike <= logy) {
         i += 1;
         if (i > 20) {
             theta = 0;
@@ -817,7 +825,7 @@ int orc_eslice_change_points(const orc_cfg *c, const orc_init *init, const doubl
             st = orc_full_loglik(c, init, param, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
                                  Ode_coarse, betaN, LatentTraj, &loglike);
             evals++;
-            status |= ORC_CAP_HIT | st;
+            status |= ORC_CAP_HIT;
             break;
         }
         if (theta < 0) theta_min = theta;
@@ -827,8 +835,8 @@ int orc_eslice_change_points(const orc_cfg *c, const orc_init *init, const doubl
         st = orc_full_loglik(c, init, param_new, initial, t, nt, gridsize, OriginTraj, t_correct, Acube, Lcube,
                              Ode_coarse, betaN, LatentTraj, &loglike);
         evals++;
-        status |= st;
     }
+    status |= st; /* status of the evaluation the call ended on */
     double lcp = 0.0;
     for (int j = 0; j < nch; j++) {
         double d = log(param_new[c->x_i[1] + j]) * param_new[c->x_i[0] + c->x_i[1]];

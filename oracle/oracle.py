@@ -281,7 +281,7 @@ def Update_Param(param, initial, t, OriginTraj, x_r, x_i, init, gridsize, coal_l
                                 C.c_double(coal_log), C.c_double(prior_proposal_offset), C.c_double(t_correct),
                                 C.c_double(unif), C.byref(acc), _p(A), _p(L), _p(ode), _p(betaN), _p(lat),
                                 C.byref(cl))
-    if st:
+    if st & 1:
         raise ValueError("Invalid input for cholesky decomposition., parametrization fails")
     if not acc.value:
         return {"accept": False, "coalLog_proposed": cl.value}

@@ -1,0 +1,151 @@
+"""GPU parity of the Metropolis / elliptical-slice operators and of the resident chain driver against
+the CPU oracle on identical pre-drawn normals / uniforms: same accept / shrink decision sequences,
+values within 1e-10 relative (BASELINE.json north_star: "ESlice chains step-for-step equal")."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import driver
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def api():
+    import lnaphylodyn_b200 as m
+    from lnaphylodyn_b200 import _lib
+    assert _lib.lib().lna_device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return m.api
+
+
+def state_of(g):
+    return driver.init_state(g, g.final["par"].ravel(), g.final["OriginTraj"])
+
+
+def test_param_slice_updates(api, changepoint):
+    g = changepoint
+    par = g.final["par"].ravel()
+    rng = np.random.default_rng(0)
+    opts = driver.opts_from_golden(g)
+    for th in (0.3, -1.7, 5.9):
+        nu = rng.standard_normal(43)
+        for ess in ([0, 1, 0, 0, 1, 1, 0], [1, 1, 1, 0, 1, 1, 0], [0, 1, 0, 0, 0, 1, 0], [0, 0, 0, 0, 1, 0, 0]):
+            o = orc.Param_Slice_update_all2(par, g.x_r, g.x_i, th, nu, ess, opts["priorList"])
+            d = api.Param_Slice_update_all2(par, g.x_r, g.x_i, th, nu, ess, opts["priorList"])
+            assert relerr(d, o) < 1e-13
+        nc = rng.standard_normal(39) / par[43]
+        assert relerr(api.Param_Slice_update(par[2:], g.x_r, g.x_i, th, nc), orc.Param_Slice_update(par[2:], g.x_r, g.x_i, th, nc)) < 1e-13
+
+
+@pytest.mark.parametrize("width", [0, 1, 4, 32])
+def test_eslice_par_general_step_for_step(api, changepoint, width):
+    g = changepoint
+    st = state_of(g)
+    opts = driver.opts_from_golden(g)
+    B = 48
+    rng = np.random.default_rng(100)
+    nrm, unf = rng.standard_normal((B, 43)), rng.random((B, 22))
+    unf[:6, 0] = 1.0 - 1e-9 * rng.random(6)      # log u ~ 0: forces long shrink sequences / the 20-cap
+    d = api.ESlice_par_General(np.tile(st["par"], (B, 1)), g.times, st["OriginTraj"], opts["priorList"], g.x_r, g.x_i,
+                               g.init, g.gridsize, opts["ESS_vec"], st["coalLog"], g.t_correct, normals=nrm,
+                               uniforms=unf, spec_width=width)
+    caps = 0
+    for b in range(B):
+        o = orc.ESlice_par_General(st["par"], g.times, st["OriginTraj"], opts["priorList"], g.x_r, g.x_i, g.init,
+                                   g.gridsize, opts["ESS_vec"], st["coalLog"], g.t_correct, normals=nrm[b],
+                                   uniforms=unf[b])
+        assert d["n_evals"][b] == o["n_evals"], (b, d["n_evals"][b], o["n_evals"])
+        assert (d["status"][b] & 8) == (o["status"] & 8)
+        caps += int(bool(o["status"] & 8))
+        assert relerr(d["par"][b], o["par"]) < TOL
+        assert d["CoalLog"][b] == pytest.approx(o["CoalLog"], rel=TOL)
+        assert d["logOrigin"][b] == pytest.approx(o["logOrigin"], rel=1e-13)
+        assert relerr(d["LatentTraj"][b][:, 1:], o["LatentTraj"][:, 1:]) < 1e-9
+        assert relerr(d["betaN"][b], o["betaN"]) < TOL
+        assert relerr(d["OdeTraj"][b], o["OdeTraj"]) < TOL
+        assert relerr(d["FT"]["A"][b], o["FT"]["A"]) < 1e-9
+    assert d["n_evals"].max() > 3  # the sample exercises real shrinking
+
+
+def test_eslice_general_nc_step_for_step(api, changepoint):
+    g = changepoint
+    st = state_of(g)
+    B = 64
+    rng = np.random.default_rng(200)
+    nrm, unf = rng.standard_normal((B, 80)), rng.random((B, 22))
+    unf[:4, 0] = 1.0 - 1e-12
+    rep = lambda a: np.tile(a, (B,) + (1,) * np.ndim(a))
+    d = api.ESlice_general_NC(rep(st["OriginTraj"]), rep(st["Ode"]), {"A": rep(st["FT"]["A"]), "Sigma": rep(st["FT"]["Sigma"])},
+                              st["par"][:2], g.init, rep(st["betaN"]), g.t_correct, 1.0, st["coalLog"], g.gridsize, True,
+                              "SIR", normals=nrm, uniforms=unf)
+    for b in range(B):
+        o = orc.ESlice_general_NC(st["OriginTraj"], st["Ode"], st["FT"], st["par"][:2], g.init, st["betaN"], g.t_correct,
+                                  1.0, st["coalLog"], g.gridsize, True, "SIR", normals=nrm[b], uniforms=unf[b])
+        assert d["n_evals"][b] == o["n_evals"], (b, d["n_evals"][b], o["n_evals"])
+        assert (d["status"][b] & 8) == (o["status"] & 8)
+        assert d["CoalLog"][b] == pytest.approx(o["CoalLog"], rel=TOL)
+        assert d["logOrigin"][b] == pytest.approx(o["logOrigin"], rel=1e-12)
+        assert np.max(np.abs(d["OriginTraj"][b] - o["OriginTraj"])) < 1e-12
+        assert relerr(d["LatentTraj"][b][:, 1:], o["LatentTraj"][:, 1:]) < 1e-9
+    assert d["n_evals"].max() > 2
+    # coal_log = -99999999 recomputes the current likelihood first
+    d2 = api.ESlice_general_NC(st["OriginTraj"], st["Ode"], st["FT"], st["par"][:2], g.init, st["betaN"], g.t_correct,
+                               1.0, -99999999.0, g.gridsize, True, "SIR", normals=nrm[9], uniforms=unf[9])
+    o2 = orc.ESlice_general_NC(st["OriginTraj"], st["Ode"], st["FT"], st["par"][:2], g.init, st["betaN"], g.t_correct,
+                               1.0, -99999999.0, g.gridsize, True, "SIR", normals=nrm[9], uniforms=unf[9])
+    assert d2["n_evals"] == o2["n_evals"] and d2["CoalLog"] == pytest.approx(o2["CoalLog"], rel=TOL)
+
+
+@pytest.mark.parametrize("width", [0, 8])
+def test_eslice_change_points_step_for_step(api, constant, width):
+    """General_MCMC2's change-point update (constant_sim vignette)."""
+    g = constant
+    st = driver.init_state(g, g.final["par"].ravel(), g.final["OriginTraj"])
+    B = 32
+    rng = np.random.default_rng(300)
+    nrm, unf = rng.standard_normal((B, 39)), rng.random((B, 22))
+    unf[:4, 0] = 1.0 - 1e-10
+    d = api.ESlice_change_points(np.tile(st["par"][2:], (B, 1)), st["par"][:2], g.times, st["OriginTraj"], g.x_r, g.x_i,
+                                 g.init, g.gridsize, st["coalLog"], g.t_correct, normals=nrm, uniforms=unf,
+                                 spec_width=width)
+    for b in range(B):
+        o = orc.ESlice_change_points(st["par"][2:], st["par"][:2], g.times, st["OriginTraj"], g.x_r, g.x_i, g.init,
+                                     g.gridsize, st["coalLog"], g.t_correct, normals=nrm[b], uniforms=unf[b])
+        assert d["n_evals"][b] == o["n_evals"], (b, d["n_evals"][b], o["n_evals"])
+        assert relerr(d["param"][b], o["param"]) < TOL
+        assert d["CoalLog"][b] == pytest.approx(o["CoalLog"], rel=TOL)
+        assert d["LogChProb"][b] == pytest.approx(o["LogChProb"], rel=1e-9, abs=1e-12)
+        assert relerr(d["LatentTraj"][b][:, 1:], o["LatentTraj"][:, 1:]) < 1e-9
+
+
+def test_chains_step_for_step(api, changepoint):
+    """B chains x 6 iterations of the General_MCMC_with_ESlice body (2 burn-in style + 4 full) from the
+    vignette's initial state: every chain must reproduce the oracle's chain step for step."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    B, iters, seed = 12, 6, 77
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    ref = [driver.init_state(g, par0, g.setting("control.traj")) for _ in range(B)]
+    s0 = ch.get()
+    assert s0["coalLog"][0] == pytest.approx(ref[0]["coalLog"], rel=TOL)
+    for it in range(iters):
+        traj = it >= 2
+        nrm, unf = chm.draw_streams(B, ch.n_norm, seed, it)
+        ch.step(chm.vignette_opts(g, update_traj=traj), nrm, unf)
+        s = ch.get()
+        for c in range(B):
+            ref[c] = driver.eslice_iteration(ref[c], g, driver.opts_from_golden(g, update_traj=traj), nrm[c], unf[c])
+            assert relerr(s["par"][c], ref[c]["par"]) < TOL, (it, c)
+            assert s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL), (it, c)
+            assert np.max(np.abs(s["OriginTraj"][c] - ref[c]["OriginTraj"])) < 1e-11
+            assert relerr(s["LatentTraj"][c][:, 1:], ref[c]["LatentTraj"][:, 1:]) < 1e-9
+            assert s["logOrigin"][c] == pytest.approx(ref[c]["logOrigin"], rel=1e-11, abs=1e-300)
+            assert s["n_full_evals"][c] == ref[c]["n_full"], (it, c)
+            assert s["n_cheap_evals"][c] == ref[c]["n_cheap"], (it, c)
+            assert s["n_mh_accept"][c] == ref[c]["n_mh_accept"], (it, c)
+    assert np.all(np.isfinite(s["coalLog"]))
