@@ -76,6 +76,17 @@ static int launch_commit_fields(lna_problem *pb, long long B, const CandBuf &cb,
     return launch_check(pb, "k_commit_fields");
 }
 
+static int launch_traj(lna_problem *pb, long long B, const TrajArgs &a) {
+    const DevProb &P = pb->dp;
+    const size_t sh = pb->tab_bytes + sizeof(double) * kTrajWarps * traj_warp_doubles(P.k, P.nrow);
+    if (sh > 48 * 1024) {
+        if (sh > 200 * 1024) return fail("k_eslice_traj: k = %d LNA intervals do not fit in shared memory", P.k);
+        cudaFuncSetAttribute(k_eslice_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    }
+    k_eslice_traj<<<nblk(B, kTrajWarps), kTrajWarps * 32, sh, pb->stream>>>(P, B, a);
+    return launch_check(pb, "k_eslice_traj");
+}
+
 static int check_sir_sampler(const lna_problem *pb, const char *what) {
     if (pb->dp.model != LNA_MODEL_SIR || pb->dp.nparam != 2)
         return fail("%s: the reference's samplers are hard-wired to SIR (p = 2, nparam = 2)", what);
@@ -168,8 +179,10 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
     if (launch_commit_fields(pb, B, cb, item_out(dA, nA), item_out(dL, nA), item_out(dO, nO), item_out(dbn, nrow),
                              item_out(dlat, nO)))
         return -1;
-    k_commit_par<PROP_ESS_PAR><<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, a, item_out(dpar, npar), dcl, dlo, 1);
-    if (launch_check(pb, "k_commit_par")) return -1;
+    k_commit_par_wide<PROP_ESS_PAR><<<nblk((long long)(nB * npar), 256), 256, 0, pb->stream>>>(P, B, a, item_out(dpar, npar), dcl);
+    if (launch_check(pb, "k_commit_par_wide")) return -1;
+    k_log_origin<<<nblk((long long)B * 32, 128), 128, 0, pb->stream>>>(B, (int)kp, a.origin, dlo);
+    if (launch_check(pb, "k_log_origin")) return -1;
     s.back(par_new, dpar, nB * npar);
     s.back(Acube, dA, nB * nA);
     s.back(Lcube, dL, nB * nA);
@@ -230,8 +243,10 @@ extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double
     if (launch_commit_fields(pb, B, cb, item_out(dA, nA), item_out(dL, nA), item_out(dO, nO), item_out(dbn, nrow),
                              item_out(dlat, nO)))
         return -1;
-    k_commit_par<PROP_ESS_CHPT><<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, a, item_out(dpar, npar), dcl, dlcp, 1);
-    if (launch_check(pb, "k_commit_par")) return -1;
+    k_commit_par_wide<PROP_ESS_CHPT><<<nblk((long long)(nB * npar), 256), 256, 0, pb->stream>>>(P, B, a, item_out(dpar, npar), dcl);
+    if (launch_check(pb, "k_commit_par_wide")) return -1;
+    k_log_chprob<<<nblk((long long)B * 32, 128), 128, 0, pb->stream>>>(B, P.nch, (int)npar, item_view(dpar, npar), dlcp);
+    if (launch_check(pb, "k_log_chprob")) return -1;
     std::vector<double> par_out(param_new ? nB * npar : 0);
     s.back(param_new ? par_out.data() : nullptr, dpar, nB * npar);
     s.back(Acube, dA, nB * nA);
@@ -281,9 +296,7 @@ extern "C" int lna_eslice_general_nc(lna_problem *pb, int64_t B, const double *f
     a.logOrigin = dlo;
     a.n_evals = dne;
     a.status = dst;
-    const int block = pick_block(pb, B);
-    k_eslice_traj<<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, B, a);
-    if (launch_check(pb, "k_eslice_traj")) return -1;
+    if (launch_traj(pb, B, a)) return -1;
     s.back(LatentTraj, dlat, nB * nO);
     s.back(OriginTraj_new, dor, nB * kp);
     s.back(logOrigin, dlo, nB);
@@ -301,7 +314,7 @@ struct lna_chains {
     long long B = 0;
     int W = 1;
     // slot-major state: field[j*B + c]
-    double *par = nullptr, *origin = nullptr, *A = nullptr, *L = nullptr, *ode = nullptr, *betaN = nullptr,
+    double *par = nullptr, *par_alt = nullptr, *origin = nullptr, *A = nullptr, *L = nullptr, *ode = nullptr, *betaN = nullptr,
            *latent = nullptr, *coalLog = nullptr, *logOrigin = nullptr, *summary = nullptr;
     int *counters = nullptr;  // [4][B]: n_full, n_cheap, n_mh_accept, status
     int *tmp_i = nullptr;     // [2][B]
@@ -356,6 +369,7 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
     const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
     ch->par = chains_alloc<double>(ch, nB * npar);
+    ch->par_alt = chains_alloc<double>(ch, nB * npar);
     ch->origin = chains_alloc<double>(ch, nB * kp);
     ch->A = chains_alloc<double>(ch, nB * nA);
     ch->L = chains_alloc<double>(ch, nB * nA);
@@ -372,7 +386,7 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     ch->n_unif = LNA_ITER_UNIF;
     ch->stage_n = chains_alloc<double>(ch, nB * ch->n_norm);
     ch->stage_u = chains_alloc<double>(ch, nB * ch->n_unif);
-    if (!ch->par || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
+    if (!ch->par || !ch->par_alt || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
         !ch->logOrigin || !ch->summary || !ch->counters || !ch->tmp_i || !ch->tmp_d || !ch->stage_n || !ch->stage_u) {
         fail("lna_chains_create: device allocation failed");
         lna_chains_destroy(ch);
@@ -460,9 +474,10 @@ static int chains_stage(lna_chains *ch, const lna_mcmc_opts *o, const double *no
     if (launch_commit_fields(pb, B, ch->cb, soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B),
                              soa_out(ch->betaN, B), soa_out(ch->latent, B)))
         return -1;
-    k_commit_par<kProp><<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, a, soa_out(ch->par, B), ch->coalLog,
-                                                             kProp == PROP_ESS_PAR ? ch->logOrigin : nullptr, 0);
-    if (launch_check(pb, "k_commit_par")) return -1;
+    const int npar = 2 + P.npt;
+    k_commit_par_wide<kProp><<<nblk(B * npar, 256), 256, 0, pb->stream>>>(P, B, a, soa_out(ch->par_alt, B), ch->coalLog);
+    if (launch_check(pb, "k_commit_par_wide")) return -1;
+    std::swap(ch->par, ch->par_alt);  // update_Par_ESlice_combine does not touch logOrigin (LNA_chpt_slice.R:456-472)
     const bool mh = (kProp == PROP_GAMMA_RW || kProp == PROP_HYPER_NOOP);
     k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->cb.n_evals, ch->cb.accept, ch->cb.status, ch->cb.win_slot,
                                                  ch->counters, 0, mh ? 1 : 0);
@@ -505,9 +520,7 @@ extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const
         a.logOrigin = ch->logOrigin;
         a.n_evals = ch->tmp_i;
         a.status = ch->tmp_i + B;
-        const int block = pick_block(pb, B);
-        k_eslice_traj<<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, B, a);
-        if (launch_check(pb, "k_eslice_traj")) return -1;
+        if (launch_traj(pb, B, a)) return -1;
         CK(cudaMemcpyAsync(ch->coalLog, ch->tmp_d, sizeof(double) * (size_t)B, cudaMemcpyDeviceToDevice, pb->stream));
         k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->tmp_i, ch->tmp_i, ch->tmp_i + B, nullptr, ch->counters, 1, 0);
         if (launch_check(pb, "k_bump")) return -1;

@@ -108,11 +108,43 @@ struct FullOut {
 // Change-ratio sources.  The FULL evaluation pulls ch_j when the time loop crosses change point j,
 // so a proposal never has to be materialised as a 40-odd element vector per thread.
 // ------------------------------------------------------------------------------------------------
+// A source exposes   Raw raw(j)   (the global loads, issued one change point ahead so their latency
+// hides behind the previous run of fine steps) and   double eval(Raw)   (the arithmetic).
 struct ChFromParam {  // ch_j = param[nparam + j]
     View param;
     long long b;
     int nparam;
-    __device__ __forceinline__ double ch(int j) const { return param.at(b, nparam + j); }
+    struct Raw {
+        double c;
+    };
+    __device__ __forceinline__ Raw raw(int j) const { return Raw{param.at(b, nparam + j)}; }
+    __device__ __forceinline__ double eval(const Raw &r) const { return r.c; }
+    __device__ __forceinline__ double ch(int j) const { return eval(raw(j)); }
+};
+
+// Cursor over the change points of one trajectory: `next_s` is the fine-step index at which the next
+// change ratio applies (INT_MAX when none is left), so the time loop only compares two registers.
+template <class ChSrc>
+struct ChCursor {
+    const ChSrc &src;
+    const int *chidx;
+    int nch, nxt, next_s;
+    typename ChSrc::Raw pre;
+    __device__ __forceinline__ ChCursor(const ChSrc &s, const int *ci, int n) : src(s), chidx(ci), nch(n), nxt(0) {
+        next_s = nch > 0 ? chidx[0] : 0x7fffffff;
+        pre = src.raw(0);  // nch == 0 reads the (in-range) slot after the model parameters; never used
+    }
+    // apply every change with index <= s to the running R0; returns true if anything changed
+    __device__ __forceinline__ bool advance(int s, double &R0cum) {
+        if (next_s > s) return false;
+        do {
+            R0cum *= src.eval(pre);
+            ++nxt;
+            next_s = nxt < nch ? chidx[nxt] : 0x7fffffff;
+            pre = src.raw(nxt < nch ? nxt : 0);
+        } while (next_s <= s);
+        return true;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -158,13 +190,14 @@ template <bool kStore, class ChSrc, class EpsSrc>
 __device__ __forceinline__ void sir_full_eval(const DevProb &P, const Tables &T, const ChSrc &chs, const EpsSrc &eps,
                                               double R0, double gam, double S, double I, const FullOut &out,
                                               long long b, double &loglik, int &status) {
-    const double dt = P.dt_ode, h2 = 0.5 * dt, dt6 = dt / 6.0;
-    const double g2 = 2.0 * gam;
-    const int g = P.g, k = P.k, nrow = P.nrow, nch = P.nch;
+    const double dt = P.dt_ode, h2 = 0.5 * dt, dt6 = dt / 6.0, dt3 = dt / 3.0;
+    const double g2 = 2.0 * gam, hg = h2 * gam, dg6 = dt6 * gam, dg3 = dt3 * gam;
+    const double invN = 1.0 / P.N;
+    const int g = P.g, k = P.k, nrow = P.nrow;
     double R0cum = R0;
-    int nxt = 0;
-    while (nxt < nch && T.chidx[nxt] <= 0) R0cum *= chs.ch(nxt++);
-    double beta = R0cum * gam / P.N;
+    ChCursor<ChSrc> cur(chs, T.chidx, P.nch);
+    cur.advance(0, R0cum);
+    double beta = (R0cum * gam) * invN, hb = h2 * beta;
     double X0 = 0.0, X1 = 0.0;
     VolzAcc va;
     int st = 0;
@@ -190,46 +223,59 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const Tables &T,
         double s00 = 0.0, s01 = 0.0, s11 = 0.0;              // Sigma (symmetric)
         const double dts = T.dt_seg[seg];
         const double e0 = eps.at(seg, 0), e1 = eps.at(seg, 1);  // issued early: latency hidden by the loop
-        const int sbase = seg * g;
-#pragma unroll 2
-        for (int j = 0; j < g; ++j) {
-            const int s = sbase + j;
-            if (nxt < nch && T.chidx[nxt] <= s) {
-                do R0cum *= chs.ch(nxt++);
-                while (nxt < nch && T.chidx[nxt] <= s);
-                beta = R0cum * gam / P.N;
+        int s = seg * g;
+        const int s_end = s + g;
+        while (s < s_end) {
+            // runs of fine steps between change points carry no per-step bookkeeping at all
+            if (cur.advance(s, R0cum)) {
+                beta = (R0cum * gam) * invN;
+                hb = h2 * beta;
             }
-            const double bI = beta * I, bS = beta * S;
-            const double a1 = bS * I;   // h0 = beta*S*I
-            const double gI = gam * I;  // h1
-            // F0 <- F0 + (F F0) dts,  F = [[-bI, -bS], [bI, bS-gam]]
-            const double u0 = fma(bI, p00, bS * p10);
-            const double u1 = fma(bI, p01, bS * p11);
-            const double v0 = fma(-gam, p10, u0);
-            const double v1 = fma(-gam, p11, u1);
-            p00 = fma(-dts, u0, p00);
-            p01 = fma(-dts, u1, p01);
-            p10 = fma(dts, v0, p10);
-            p11 = fma(dts, v1, p11);
-            // Sigma <- Sigma + (Sigma F' + F Sigma + A' diag(h) A) dts
-            const double w0 = fma(bI, s00, bS * s01);
-            const double w1 = fma(bI, s01, bS * s11);
-            const double d00 = fma(-2.0, w0, a1);
-            const double d01 = fma(-gam, s01, w0 - w1) - a1;
-            const double d11 = fma(-g2, s11, fma(2.0, w1, a1 + gI));
-            s00 = fma(dts, d00, s00);
-            s01 = fma(dts, d01, s01);
-            s11 = fma(dts, d11, s11);
-            // RK4 variant: all stages at t[s], k4 at X0 + k3*dt/2
-            const double k1I = a1 - gI;
-            const double S2 = fma(-h2, a1, S), I2 = fma(h2, k1I, I);
-            const double a2 = (beta * S2) * I2, k2I = fma(-gam, I2, a2);
-            const double S3 = fma(-h2, a2, S), I3 = fma(h2, k2I, I);
-            const double a3 = (beta * S3) * I3, k3I = fma(-gam, I3, a3);
-            const double S4 = fma(-h2, a3, S), I4 = fma(h2, k3I, I);
-            const double a4 = (beta * S4) * I4, k4I = fma(-gam, I4, a4);
-            S = fma(-dt6, fma(2.0, a2 + a3, a1 + a4), S);
-            I = fma(dt6, fma(2.0, k2I + k3I, k1I + k4I), I);
+            const int run_end = min(s_end, cur.next_s);
+#pragma unroll 2
+            for (; s < run_end; ++s) {
+                const double bI = beta * I, bS = beta * S;
+                const double a1 = bS * I;   // h0 = beta*S*I
+                const double gI = gam * I;  // h1
+                // F0 <- F0 + (F F0) dts,  F = [[-bI, -bS], [bI, bS-gam]]
+                const double u0 = fma(bI, p00, bS * p10);
+                const double u1 = fma(bI, p01, bS * p11);
+                const double v0 = fma(-gam, p10, u0);
+                const double v1 = fma(-gam, p11, u1);
+                p00 = fma(-dts, u0, p00);
+                p01 = fma(-dts, u1, p01);
+                p10 = fma(dts, v0, p10);
+                p11 = fma(dts, v1, p11);
+                // Sigma <- Sigma + (Sigma F' + F Sigma + A' diag(h) A) dts
+                const double w0 = fma(bI, s00, bS * s01);
+                const double w1 = fma(bI, s01, bS * s11);
+                const double d00 = fma(-2.0, w0, a1);
+                const double d01 = fma(-gam, s01, w0 - w1) - a1;
+                const double d11 = fma(-g2, s11, fma(2.0, w1, a1 + gI));
+                s00 = fma(dts, d00, s00);
+                s01 = fma(dts, d01, s01);
+                s11 = fma(dts, d11, s11);
+                // RK4 variant (all stages at t[s], k4 at X0 + k3*dt/2), arranged for a short dependent
+                // chain: stage j needs only a_{j-1} on its critical path,
+                //   beta*S_j = beta*S - (h2 beta) a_{j-1},   I_j = (I - h2 gam I_{j-1}) + h2 a_{j-1},
+                // and the state update is accumulated term by term as the stages complete:
+                //   S' = S - dt/6 (a1 + 2 a2 + 2 a3 + a4)
+                //   I' = I + dt/6 (a1 + 2 a2 + 2 a3 + a4) - gam dt/6 (I + 2 I2 + 2 I3 + I4)
+                const double I2 = fma(h2, a1, fma(-hg, I, I));
+                const double a2 = fma(-hb, a1, bS) * I2;
+                double aS = fma(-dt6, a1, S);
+                double aI = fma(dt6, a1, fma(-dg6, I, I));
+                const double I3 = fma(h2, a2, fma(-hg, I2, I));
+                const double a3 = fma(-hb, a2, bS) * I3;
+                aS = fma(-dt3, a2, aS);
+                aI = fma(dt3, a2, fma(-dg3, I2, aI));
+                const double I4 = fma(h2, a3, fma(-hg, I3, I));
+                const double a4 = fma(-hb, a3, bS) * I4;
+                aS = fma(-dt3, a3, aS);
+                aI = fma(dt3, a3, fma(-dg3, I3, aI));
+                S = fma(-dt6, a4, aS);
+                I = fma(dt6, a4, fma(-dg6, I4, aI));
+            }
         }
         // Cholesky of Sigma + 1e-8 I  (lower)
         const double c00 = s00 + kJitter;
@@ -245,13 +291,9 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const Tables &T,
         X1 = nX1;
         const int r = seg + 1;
         // beta at the coarse time (betaTs on coarse times)
-        {
-            const int s = r * g;
-            if (nxt < nch && T.chidx[nxt] <= s) {
-                do R0cum *= chs.ch(nxt++);
-                while (nxt < nch && T.chidx[nxt] <= s);
-                beta = R0cum * gam / P.N;
-            }
+        if (cur.advance(r * g, R0cum)) {
+            beta = (R0cum * gam) * invN;
+            hb = h2 * beta;
         }
         const double lS = S + X0, lI = I + X1;
         if (kStore) {
@@ -300,11 +342,12 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const Tables &T
                                                double Ex, double I, const FullOut &out, long long b,
                                                double &loglik, int &status) {
     const double dt = P.dt_ode, h2 = 0.5 * dt, dt6 = dt / 6.0;
-    const int g = P.g, k = P.k, nrow = P.nrow, nch = P.nch;
+    const int g = P.g, k = P.k, nrow = P.nrow;
+    const double invN = 1.0 / P.N;
     double R0cum = R0;
-    int nxt = 0;
-    while (nxt < nch && T.chidx[nxt] <= 0) R0cum *= chs.ch(nxt++);
-    double beta = R0cum * gam / P.N;
+    ChCursor<ChSrc> cur(chs, T.chidx, P.nch);
+    cur.advance(0, R0cum);
+    double beta = (R0cum * gam) * invN;
     double X[3] = {0.0, 0.0, 0.0};
     VolzAcc va;
     int st = 0;
@@ -331,14 +374,12 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const Tables &T
         double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
         const double dts = T.dt_seg[seg];
         const double e0 = eps.at(seg, 0), e1 = eps.at(seg, 1), e2 = eps.at(seg, 2);
-        const int sbase = seg * g;
-        for (int j = 0; j < g; ++j) {
-            const int s = sbase + j;
-            if (nxt < nch && T.chidx[nxt] <= s) {
-                do R0cum *= chs.ch(nxt++);
-                while (nxt < nch && T.chidx[nxt] <= s);
-                beta = R0cum * gam / P.N;
-            }
+        int s = seg * g;
+        const int s_end = s + g;
+        while (s < s_end) {
+          if (cur.advance(s, R0cum)) beta = (R0cum * gam) * invN;
+          const int run_end = min(s_end, cur.next_s);
+          for (; s < run_end; ++s) {
             const double bI = beta * I, bS = beta * S;
             const double h0 = bS * I, h1 = mu * Ex, hh2 = gam * I;
             // F F0: row0 = -(bI*F0[0] + bS*F0[2]); row1 = -row0 - mu*F0[1]; row2 = mu*F0[1] - gam*F0[2]
@@ -375,6 +416,7 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const Tables &T
             S = fma(-dt6, fma(2.0, a2 + a3, h0 + a4), S);
             Ex = fma(dt6, fma(2.0, k2E + k3E, k1E + k4E), Ex);
             I = fma(dt6, fma(2.0, k2I + k3I, k1I + k4I), I);
+          }
         }
         // 3x3 Cholesky of Sigma + 1e-8 I (upper U as dpotrf, L = U')
         const double c00 = s00 + kJitter;
@@ -391,14 +433,7 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const Tables &T
         const double nX2 = fma(f20, X[0], fma(f21, X[1], f22 * X[2])) + fma(u02, e0, fma(u12, e1, u22 * e2));
         X[0] = nX0; X[1] = nX1; X[2] = nX2;
         const int r = seg + 1;
-        {
-            const int s = r * g;
-            if (nxt < nch && T.chidx[nxt] <= s) {
-                do R0cum *= chs.ch(nxt++);
-                while (nxt < nch && T.chidx[nxt] <= s);
-                beta = R0cum * gam / P.N;
-            }
-        }
+        if (cur.advance(r * g, R0cum)) beta = (R0cum * gam) * invN;
         const double lS = S + X[0], lE = Ex + X[1], lI = I + X[2];
         if (kStore) {
             if (out.A.ok()) {

@@ -51,23 +51,35 @@ struct ChProp {
     long long c;
     int off;  // index of ch_1 inside par
     PropScalars x;
-    __device__ __forceinline__ double ch(int j) const {
-        const double cj = par.at(c, off + j);
+    struct Raw {
+        double c, nu;
+    };
+    __device__ __forceinline__ Raw raw(int j) const {
+        Raw r;
+        r.c = par.at(c, off + j);
+        r.nu = 0.0;
+        if (kProp == PROP_ESS_PAR) r.nu = nrm.at(c, 3 + j);
+        if (kProp == PROP_ESS_CHPT) r.nu = nrm.at(c, j);
+        return r;
+    }
+    __device__ __forceinline__ double eval(const Raw &r) const {
+        const double cj = r.c;
         if (kProp == PROP_HYPER_NOOP) {
             // exp(log(ch) * hyper / hyper), R/LNA_chpt_slice.R:238-241 (ulp-level perturbation, A.17)
             return exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_old));
         } else if (kProp == PROP_ESS_PAR) {
             if (!x.rot_ch) return cj;
-            const double z = __dmul_rn(log(cj), x.hyper_old);        // :1296
-            const double zp = rot(z, x.ct, nrm.at(c, 3 + j), x.sn);  // :1299
-            return exp(__ddiv_rn(zp, x.hyper_new));                  // :1310
+            const double z = __dmul_rn(log(cj), x.hyper_old);  // :1296
+            const double zp = rot(z, x.ct, r.nu, x.sn);        // :1299
+            return exp(__ddiv_rn(zp, x.hyper_new));            // :1310
         } else if (kProp == PROP_ESS_CHPT) {
-            const double nu = __ddiv_rn(nrm.at(c, j), x.hyper_old);  // :1344
-            return exp(rot(log(cj), x.ct, nu, x.sn));                // :1249-1251
+            const double nu = __ddiv_rn(r.nu, x.hyper_old);    // :1344
+            return exp(rot(log(cj), x.ct, nu, x.sn));          // :1249-1251
         } else {
             return cj;
         }
     }
+    __device__ __forceinline__ double ch(int j) const { return eval(raw(j)); }
 };
 
 // Slice-angle generator: replays the reference's bracket logic from the uniforms.
@@ -336,204 +348,252 @@ __global__ void k_commit_fields(long long B, CommitArgs a) {
     if (a.betaN.ok()) a.betaN.put(c, e, a.cBeta[(long long)e * a.NC + slot]);
 }
 
-// New parameter vector of the accepted proposal (one thread per chain).  par_out may alias the chain
-// state: every entry is read before it is written by the same thread.
-template <int kProp>
-__global__ void k_commit_par(DevProb P, long long B, CandArgs a, OutView par_out, double *coalLog, double *logOrigin,
-                             int write_unaccepted) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// logOrigin of ESlice_par_General: -1/2 sum over ALL rows of OriginTraj (:1673-1678); one warp per chain.
+__global__ void k_log_origin(long long B, int n, View origin, double *logOrigin) {
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= B) return;
-    const int npar = 2 + P.npt, nch = P.nch;
-    const bool win = a.win_slot[c] >= 0;
-    if (!win && !write_unaccepted) return;
-    if (!win) {  // keep the current parameters (standalone entry points return them)
-        for (int j = 0; j < npar; ++j) par_out.put(c, j, a.par.at(c, j));
-        return;
+    double lo = 0.0;
+    for (int e = lane; e < n; e += 32) {
+        const double v = origin.at(c, e);
+        lo -= 0.5 * v * v;
     }
-    if (coalLog) coalLog[c] = a.cand_ll[c];
-    if (kProp == PROP_GAMMA_RW) {
-        const double g = exp(a.theta[c]);
-        for (int j = 0; j < npar; ++j) par_out.put(c, j, j == 3 ? g : a.par.at(c, j));
-    } else if (kProp == PROP_HYPER_NOOP) {
-        PropScalars x{};
-        x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
-        ChProp<PROP_HYPER_NOOP> chs{a.par, a.normals, c, 4, x};
-        for (int j = 0; j < 4; ++j) par_out.put(c, j, a.par.at(c, j));
-        const double hy = a.par.at(c, npar - 1);
-        for (int j = 0; j < nch; ++j) par_out.put(c, 4 + j, chs.ch(j));
-        par_out.put(c, npar - 1, hy);
-    } else if (kProp == PROP_ESS_PAR) {
-        const bool reverted = a.status[c] & ST_CAP_HIT;
-        if (reverted) {
-            for (int j = 0; j < npar; ++j) par_out.put(c, j, a.par.at(c, j));
-        } else {
-            const EssParPre z = ess_par_pre(a, c, npar);
-            PropScalars x;
-            ess_par_scalars(a, c, npar, z, a.theta[c], x);
-            ChProp<PROP_ESS_PAR> chs{a.par, a.normals, c, 4, x};
-            const double s0 = a.par.at(c, 0);
-            double chv;
-            par_out.put(c, 0, s0);
-            // ch first (they read the OLD hyper through x, and par entries 4.. are only read here)
-            for (int j = 0; j < nch; ++j) {
-                chv = chs.ch(j);
-                par_out.put(c, 4 + j, chv);
-            }
-            par_out.put(c, 1, x.I0);
-            par_out.put(c, 2, x.R0);
-            par_out.put(c, 3, x.gam);
-            par_out.put(c, npar - 1, x.hyper_new);
-        }
-        if (logOrigin) {  // -1/2 sum over ALL rows (:1673-1678); OriginTraj is unchanged (ESS_vec[6] = 0)
-            double lo = 0.0;
-            for (int j = 0; j < P.k; ++j)
-                for (int q = 0; q < P.p; ++q) {
-                    const double v = a.origin.at(c, q * P.k + j);
-                    lo -= 0.5 * v * v;
-                }
-            logOrigin[c] = lo;
-        }
-    } else if (kProp == PROP_ESS_CHPT) {
-        const bool reverted = a.status[c] & ST_CAP_HIT;
-        PropScalars x{};
-        double sn, ct;
-        sincos(a.theta[c], &sn, &ct);
-        x.ct = ct;
-        x.sn = sn;
-        x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
-        ChProp<PROP_ESS_CHPT> chs{a.par, a.normals, c, 4, x};
-        for (int j = 0; j < 4; ++j) par_out.put(c, j, a.par.at(c, j));
-        const double hy = a.par.at(c, npar - 1);
-        double lcp = 0.0;
-        for (int j = 0; j < nch; ++j) {
-            const double v = reverted ? a.par.at(c, 4 + j) : chs.ch(j);
-            par_out.put(c, 4 + j, v);
-            const double d = log(v) * hy;  // LogChProb (:1395-1399)
-            lcp += -0.5 * d * d;
-        }
-        par_out.put(c, npar - 1, hy);
-        if (logOrigin) logOrigin[c] = lcp;  // slot reused for LogChProb
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(0xffffffffu, lo, o);
+    if (lane == 0) logOrigin[c] = lo;
+}
+
+// LogChProb of ESlice_change_points: -1/2 sum (log(ch) * hyper)^2 (:1395-1399); one warp per chain.
+__global__ void k_log_chprob(long long B, int nch, int npar, View par, double *out) {
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= B) return;
+    const double hy = par.at(c, npar - 1);
+    double acc = 0.0;
+    for (int j = lane; j < nch; j += 32) {
+        const double d = log(par.at(c, 4 + j)) * hy;
+        acc += -0.5 * d * d;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[c] = acc;
 }
 
 // ================================================================================================
-// ESlice_general_NC (volz likelihood): CHEAP evaluations only -- rotation of the latent increments,
-// TransformTraj and the per-cell coalescent sum -- so each chain runs its own sequential loop.
+// ESlice_general_NC (volz likelihood): CHEAP evaluations only (rotation of the latent increments,
+// TransformTraj, per-cell coalescent sum).  ONE WARP PER CHAIN.
+//
+// TransformTraj is linear in the increments: with f' = f cos(th) + v sin(th),
+//     X(th) = cos(th) * X_f + sin(th) * X_v,
+// where X_f / X_v are the latent deviations driven by f / v alone.  The warp computes the two
+// recurrences once (lanes 0 and 1), after which every slice candidate is a lane-parallel map over
+// the coarse rows plus a warp-shuffle reduction of the per-cell coalescent terms.
 // ================================================================================================
 struct TrajArgs {
     View f_cur, normals, uniforms;      // k*p, k*p (column-major k x p), 22
     View A, L, ode, betaN;              // FT, coarse ODE, betaN of the current parameters
     const double *coal_log;             // [B]
-    OutView latent, origin_new;         // outputs (may alias the chain state: per-thread read-before-write)
+    OutView latent, origin_new;         // outputs (may alias the chain state: per-lane read-before-write)
     double *CoalLog, *logOrigin;
     int *n_evals, *status;
 };
 
-template <int kStoreMode, class FSrc>
-__device__ __forceinline__ double cheap_eval_sir(const DevProb &P, const Tables &T, const TrajArgs &a, long long c,
-                                                 const FSrc &f, bool &any_neg_all, const OutView *lat,
-                                                 const OutView *org, int &status) {
-    const int k = P.k, nrow = P.nrow;
-    double X0 = 0.0, X1 = 0.0;
-    VolzAcc va;
-    double S = a.ode.at(c, nrow), I = a.ode.at(c, 2 * nrow);
-    bool negall = (S < 0.0) | (I < 0.0);
-    if (kStoreMode) {
-        lat->put(c, 0, a.ode.at(c, 0));
-        lat->put(c, nrow, S);
-        lat->put(c, 2 * nrow, I);
-    }
-    va.row(P, T, 0, S, I, a.betaN.at(c, 0), negall);
-    for (int i = 0; i < k; ++i) {
-        const double e0 = f(i, 0), e1 = f(i, 1);
-        const double a00 = a.A.at(c, 4 * i), a10 = a.A.at(c, 4 * i + 1), a01 = a.A.at(c, 4 * i + 2), a11 = a.A.at(c, 4 * i + 3);
-        const double l00 = a.L.at(c, 4 * i), l10 = a.L.at(c, 4 * i + 1), l11 = a.L.at(c, 4 * i + 3);
-        const double nX0 = fma(a00, X0, a01 * X1) + l00 * e0;
-        const double nX1 = fma(a10, X0, a11 * X1) + fma(l10, e0, l11 * e1);
-        X0 = nX0;
-        X1 = nX1;
-        S = a.ode.at(c, nrow + i + 1) + X0;
-        I = a.ode.at(c, 2 * nrow + i + 1) + X1;
-        const bool neg = (S < 0.0) | (I < 0.0);
-        negall |= neg;
-        if (kStoreMode) {
-            lat->put(c, i + 1, a.ode.at(c, i + 1));
-            lat->put(c, nrow + i + 1, S);
-            lat->put(c, 2 * nrow + i + 1, I);
-            org->put(c, i, e0);
-            org->put(c, k + i, e1);
-        }
-        va.row(P, T, i + 1, S, I, a.betaN.at(c, i + 1), neg);
-    }
-    any_neg_all = negall;
-    return va.result(status);
-}
+constexpr int kTrajWarps = 4;
+__host__ __device__ inline size_t traj_warp_doubles(int k, int nrow) { return (size_t)7 * nrow + (size_t)8 * k; }
 
-__global__ void __launch_bounds__(128) k_eslice_traj(DevProb P, long long B, TrajArgs a) {
+__global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long long B, TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(P, smem);
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= B) return;
-    const int k = P.k;
+    const int k = P.k, nrow = P.nrow;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long c = (long long)blockIdx.x * kTrajWarps + w;
+    if (c >= B) return;  // whole warps exit together
+    double *ws = reinterpret_cast<double *>(smem + tables_bytes(P.nch, P.k, P.n0)) + (size_t)w * traj_warp_doubles(k, nrow);
+    double *oS = ws, *oI = oS + nrow, *bet = oI + nrow, *XfS = bet + nrow, *XfI = XfS + nrow, *XvS = XfI + nrow,
+           *XvI = XvS + nrow;
+    double *Am = XvI + nrow, *cf = Am + 4 * k, *cv = cf + 2 * k;
+    const unsigned full = 0xffffffffu;
+
+    for (int r = lane; r < nrow; r += 32) {
+        oS[r] = a.ode.at(c, nrow + r);
+        oI[r] = a.ode.at(c, 2 * nrow + r);
+        bet[r] = a.betaN.at(c, r);
+    }
+    for (int i = lane; i < k; i += 32) {
+        const double l00 = a.L.at(c, 4 * i), l10 = a.L.at(c, 4 * i + 1), l11 = a.L.at(c, 4 * i + 3);
+        const double f0 = a.f_cur.at(c, i), f1 = a.f_cur.at(c, k + i);
+        const double v0 = a.normals.at(c, i), v1 = a.normals.at(c, k + i);
+        cf[2 * i] = l00 * f0;
+        cf[2 * i + 1] = fma(l10, f0, l11 * f1);
+        cv[2 * i] = l00 * v0;
+        cv[2 * i + 1] = fma(l10, v0, l11 * v1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Am[4 * i + e] = a.A.at(c, 4 * i + e);
+    }
+    __syncwarp();
+    if (lane < 2) {  // lane 0: recurrence driven by f, lane 1: by v
+        const double *cc = lane == 0 ? cf : cv;
+        double *XS = lane == 0 ? XfS : XvS, *XI = lane == 0 ? XfI : XvI;
+        double x0 = 0.0, x1 = 0.0;
+        XS[0] = 0.0;
+        XI[0] = 0.0;
+        for (int i = 0; i < k; ++i) {
+            const double n0 = fma(Am[4 * i], x0, Am[4 * i + 2] * x1) + cc[2 * i];
+            const double n1 = fma(Am[4 * i + 1], x0, Am[4 * i + 3] * x1) + cc[2 * i + 1];
+            x0 = n0;
+            x1 = n1;
+            XS[i + 1] = x0;
+            XI[i + 1] = x1;
+        }
+    }
+    __syncwarp();
+
     auto unif = [&](int q) { return a.uniforms.at(c, q); };
-    int evals = 0, st = 0, stf = 0;
+    // one CHEAP evaluation at angle (ct, sn): returns the reference's volz_loglik_nh2 value and whether
+    // ANY latent state (all rows, both columns) is negative (the extra loop condition, :1738)
+    auto cheap = [&](double ct, double sn, bool &negall, int &st) -> double {
+        double acc = 0.0;
+        int neg_any = 0, neg_chk = 0, nan = 0;
+        for (int r = lane; r < nrow; r += 32) {
+            const double S = oS[r] + fma(ct, XfS[r], sn * XvS[r]);
+            const double I = oI[r] + fma(ct, XfI[r], sn * XvI[r]);
+            const int neg = (S < 0.0) | (I < 0.0);
+            neg_any |= neg;
+            if (r <= P.n0) neg_chk |= neg;
+            const int i = P.Lrow - r;
+            if (i >= 0 && i < P.n0 && T.cellCnt[i] > 0) {
+                const double ratio = S / I;
+                const double term = fma(-2.0 * T.cellCD[i] * bet[r], ratio, T.cellY[i] * log(bet[r] * ratio));
+                if (!(S > 0.0) || !(I > 0.0) || term != term) nan = 1;
+                acc += term;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+        negall = __any_sync(full, neg_any);
+        st = 0;
+        if (__any_sync(full, neg_chk)) {
+            st = ST_NEG_STATE;
+            return kSentinel;
+        }
+        if (__any_sync(full, nan)) {
+            st = ST_NAN;
+            return kSentinel;
+        }
+        return acc;
+    };
+
+    int evals = 0, st = 0;
     bool negall;
-    auto fcur = [&](int i, int q) { return a.f_cur.at(c, q * k + i); };
     double logy;
     const double lu = log(unif(0));
     if (a.coal_log[c] != -99999999.0) {
         logy = a.coal_log[c] + lu;
     } else {  // recompute the current likelihood like the reference (:1717-1719)
-        logy = cheap_eval_sir<0>(P, T, a, c, fcur, negall, nullptr, nullptr, st) + lu;
+        logy = cheap(1.0, 0.0, negall, st) + lu;
         evals++;
-        st = 0;
     }
     ThetaSeq ts;
     ts.init();
     ts.advance(1, unif);
     double sn, ct;
     sincos(ts.th, &sn, &ct);
-    auto fprime = [&](int i, int q) { return rot(a.f_cur.at(c, q * k + i), ct, a.normals.at(c, q * k + i), sn); };
-    double ll = cheap_eval_sir<0>(P, T, a, c, fprime, negall, nullptr, nullptr, st);
+    double ll = cheap(ct, sn, negall, st);
     evals++;
     int i = 0;
     bool reverted = false;
     while (negall || ll <= logy) {
         i += 1;
-        if (i > 20) {
+        if (i > 20) {  // cap: back to the current increments, recompute (:1741-1747)
             reverted = true;
+            ct = 1.0;
+            sn = 0.0;
+            ll = cheap(ct, sn, negall, st);
+            st |= ST_CAP_HIT;
+            evals++;
             break;
         }
         ts.advance(i + 1, unif);
         sincos(ts.th, &sn, &ct);
-        st = 0;
-        ll = cheap_eval_sir<0>(P, T, a, c, fprime, negall, nullptr, nullptr, st);
+        ll = cheap(ct, sn, negall, st);
         evals++;
     }
-    // final pass with the accepted angle (or the current f when the cap hit), storing the outputs
+    // outputs: latent rows, rotated increments, logOrigin without the LAST row (:1768)
+    for (int r = lane; r < nrow; r += 32) {
+        a.latent.put(c, r, a.ode.at(c, r));
+        a.latent.put(c, nrow + r, oS[r] + fma(ct, XfS[r], sn * XvS[r]));
+        a.latent.put(c, 2 * nrow + r, oI[r] + fma(ct, XfI[r], sn * XvI[r]));
+    }
     double lo = 0.0;
-    if (reverted) {
-        ll = cheap_eval_sir<1>(P, T, a, c, fcur, negall, &a.latent, &a.origin_new, stf);
-        stf |= ST_CAP_HIT;
-        for (int j = 0; j < k - 1; ++j)
-            for (int q = 0; q < 2; ++q) {
-                const double v = a.origin_new.base[c * a.origin_new.sb + (long long)(q * k + j) * a.origin_new.sj];
-                lo -= 0.5 * v * v;
-            }
-        evals++;
-    } else {
-        // logOrigin omits the LAST row (:1768)
-        for (int j = 0; j < k - 1; ++j)
-            for (int q = 0; q < 2; ++q) {
-                const double v = fprime(j, q);
-                lo -= 0.5 * v * v;
-            }
-        ll = cheap_eval_sir<1>(P, T, a, c, fprime, negall, &a.latent, &a.origin_new, stf);
+    for (int e = lane; e < 2 * k; e += 32) {
+        const double f = a.f_cur.at(c, e);
+        const double v = reverted ? f : rot(f, ct, a.normals.at(c, e), sn);
+        a.origin_new.put(c, e, v);
+        if ((e % k) < k - 1) lo -= 0.5 * v * v;
     }
-    a.CoalLog[c] = ll;
-    a.logOrigin[c] = lo;
-    a.n_evals[c] = evals;
-    a.status[c] = stf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(full, lo, o);
+    if (lane == 0) {
+        a.CoalLog[c] = ll;
+        a.logOrigin[c] = lo;
+        a.n_evals[c] = evals;
+        a.status[c] = st;
+    }
+}
+
+// New parameter vector of the accepted proposal, one thread per (chain, entry).  par_out must NOT
+// alias the chain's current parameters (the resident chains double-buffer `par`).
+template <int kProp>
+__global__ void k_commit_par_wide(DevProb P, long long B, CandArgs a, OutView par_out, double *coalLog) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int npar = 2 + P.npt;
+    if (idx >= B * npar) return;
+    const long long c = idx % B;
+    const int j = (int)(idx / B);
+    const double old = a.par.at(c, j);
+    const bool win = a.win_slot[c] >= 0;
+    if (win && j == 0 && coalLog) coalLog[c] = a.cand_ll[c];
+    const bool reverted = a.status[c] & ST_CAP_HIT;
+    if (!win || reverted) {
+        par_out.put(c, j, old);
+        return;
+    }
+    const bool is_ch = j >= 4 && j < npar - 1;
+    double v = old;
+    if (kProp == PROP_GAMMA_RW) {
+        if (j == 3) v = exp(a.theta[c]);
+    } else if (kProp == PROP_HYPER_NOOP) {
+        if (is_ch) {
+            PropScalars x{};
+            x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
+            ChProp<PROP_HYPER_NOOP> chs{a.par, a.normals, c, 4, x};
+            v = chs.ch(j - 4);
+        }
+    } else if (kProp == PROP_ESS_PAR) {
+        if (j >= 1) {
+            const EssParPre z = ess_par_pre(a, c, npar);
+            PropScalars x;
+            ess_par_scalars(a, c, npar, z, a.theta[c], x);
+            if (is_ch) {
+                ChProp<PROP_ESS_PAR> chs{a.par, a.normals, c, 4, x};
+                v = chs.ch(j - 4);
+            } else {
+                v = j == 1 ? x.I0 : j == 2 ? x.R0 : j == 3 ? x.gam : x.hyper_new;
+            }
+        }
+    } else if (kProp == PROP_ESS_CHPT) {
+        if (is_ch) {
+            PropScalars x{};
+            double sn, ct;
+            sincos(a.theta[c], &sn, &ct);
+            x.ct = ct;
+            x.sn = sn;
+            x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
+            ChProp<PROP_ESS_CHPT> chs{a.par, a.normals, c, 4, x};
+            v = chs.ch(j - 4);
+        }
+    }
+    par_out.put(c, j, v);
 }
 
 // Param_Slice_update / Param_Slice_update_all2 as stand-alone operators (one thread per item).

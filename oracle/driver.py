@@ -72,7 +72,7 @@ def eslice_iteration(st, g, opts, normals, uniforms):
     st["n_full"] += r["n_evals"]
     if not (r["status"] & 1):
         st["par"], st["LatentTraj"], st["betaN"], st["FT"] = r["par"], r["LatentTraj"], r["betaN"], r["FT"]
-        st["coalLog"], st["Ode"], st["logOrigin"] = r["CoalLog"], r["OdeTraj"], r["logOrigin"]
+        st["coalLog"], st["Ode"] = r["CoalLog"], r["OdeTraj"]  # logOrigin is NOT refreshed here (:456-472)
     st["last_par_evals"] = r["n_evals"]
     # --- trajectory ESS
     if opts.get("update_traj", True):

@@ -28,6 +28,9 @@ def draw_inputs(g, B, seed, scale=0.05):
     par[:, 3] *= np.exp(scale * rng.standard_normal(B))            # gamma
     par[:, 4:43] *= np.exp(0.5 * scale * rng.standard_normal((B, 39)))  # change ratios
     eps = rng.standard_normal((B, 40, 2))
+    # half of the draws stay close to the cached latent path (valid trajectories), half are wild
+    th = rng.uniform(-0.3, 0.3, size=(B // 2, 1, 1))
+    eps[: B // 2] = g.final["OriginTraj"][None] * np.cos(th) + eps[: B // 2] * np.sin(th)
     return par, eps
 
 
@@ -71,6 +74,7 @@ def test_full_loglik_batch_vs_oracle(api, name, request):
         assert np.max(np.abs(res["LatentTraj"][b][:, 1:] - o["LatentTraj"][:, 1:]) /
                       np.maximum(np.abs(o["LatentTraj"][:, 1:]), 1.0)) < TOL
     assert worst < TOL, worst
+    assert np.sum(res["coalLog"] != orc.SENTINEL) >= B // 4 and np.sum(res["coalLog"] == orc.SENTINEL) >= 1
 
 
 @pytest.mark.parametrize("name", ["changepoint", "constant"])
