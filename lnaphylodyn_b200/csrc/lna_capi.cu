@@ -82,6 +82,7 @@ struct lna_problem {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     DevProb dp{};
+    SegDt seg{};
     int sm_count = 0;
     std::vector<double> times, x_r;
     std::vector<int> chidx;
@@ -182,6 +183,10 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     pb->times.assign(cfg->times, cfg->times + cfg->nt);
     pb->x_r.assign(cfg->x_r, cfg->x_r + cfg->nch + 1);
     P.dt_ode = pb->times[1] - pb->times[0];
+    P.h2 = 0.5 * P.dt_ode;
+    P.dt6 = P.dt_ode / 6.0;
+    P.dt3 = P.dt_ode / 3.0;
+    P.invN = 1.0 / P.N;
     if ((cfg->nt - 1) % cfg->gridsize != 0) {
         fail("lna_problem_create: (nt-1) must be a multiple of gridsize (nt=%d, gridsize=%d)", cfg->nt, cfg->gridsize);
         lna_problem_destroy(pb);
@@ -199,6 +204,7 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     }
     pb->dt_seg.resize(P.k);
     for (int i = 0; i < P.k; ++i) pb->dt_seg[i] = pb->times[(size_t)i * P.g + 1] - pb->times[(size_t)i * P.g];
+    for (int i = 0; i < P.k && i < kSegConst; ++i) pb->seg.v[i] = pb->dt_seg[i];
     // Lrow: first coarse row with time >= t_correct, capped (volz_loglik_nh2, LNA_functional.cpp:1125-1129)
     int L = 0;
     while (pb->times[(size_t)L * P.g] < P.t_correct) {
@@ -405,7 +411,7 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
     const unsigned grid = nblk(B, block);
     const View vp = item_view(param, P.npt), vi = item_view(initial, p), vo = item_view(origin, (long long)P.k * p);
 #define LAUNCH(MODEL, STORE)                                                                                     \
-    k_full_loglik<MODEL, STORE><<<grid, block, pb->tab_bytes, pb->stream>>>(P, B, vp, vi, vo, out, coalLog, status)
+    k_full_loglik<MODEL, STORE><<<grid, block, pb->tab_bytes, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status)
     if (P.model == LNA_MODEL_SIR) {
         if (store) LAUNCH(0, true);
         else LAUNCH(0, false);

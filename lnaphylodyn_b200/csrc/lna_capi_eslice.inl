@@ -52,7 +52,7 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a) {
     const long long nthreads = B * W;
     const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, B);
     const unsigned grid = nblk(nthreads, block);
-#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, pb->tab_bytes, pb->stream>>>(P, B, a)
+#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, pb->tab_bytes, pb->stream>>>(P, pb->seg, B, a)
     switch (W) {
         case 1: LC(1); break;
         case 2: LC(2); break;
@@ -425,8 +425,8 @@ extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *
     FullOut out{soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B), soa_out(ch->betaN, B), soa_out(ch->latent, B)};
     const View vp{ch->par + 2 * B, 1, B}, vi{ch->par, 1, B}, vo{ch->origin, 1, B};
     const int block = pick_block(pb, B);
-    k_full_loglik<0, true><<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, B, vp, vi, vo, out, ch->coalLog,
-                                                                                 ch->counters + 3 * B);
+    k_full_loglik<0, true><<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out,
+                                                                                 ch->coalLog, ch->counters + 3 * B);
     if (launch_check(pb, "k_full_loglik")) return -1;
     CK(cudaMemsetAsync(ch->logOrigin, 0, sizeof(double) * nB, pb->stream));
     CK(cudaMemsetAsync(ch->counters, 0, sizeof(int) * nB * 3, pb->stream));

@@ -35,6 +35,10 @@ struct DevProb {
     int idxS, idxI;// state columns used by the Volz likelihood (x_i[2], x_i[3])
     int has_init;
     double N, dt_ode, t_correct;
+    // dt-derived constants computed on the host: as kernel parameters they are constant-bank operands,
+    // which keeps the DFMAs that use them at full issue rate (a DFMA with three distinct REGISTER
+    // sources issues at 2/3 rate on B200: tools/fp64_microbench.cu)
+    double h2, dt6, dt3, invN;
     const int *chidx;      // [nch] first fine index s with times[s] >= cht_j (monotone)
     const double *dt_seg;  // [k]   times[i*g+1]-times[i*g]   (SigmaF's per-block dt, A.3)
     const double *times;   // [nt]
@@ -49,6 +53,11 @@ struct DevProb {
 };
 
 // Shared-memory copy of the small tables.
+constexpr int kSegConst = 64;  // per-segment dt lives in the parameter block up to this many LNA intervals
+struct SegDt {
+    double v[kSegConst];
+};
+
 struct Tables {
     const int *chidx;
     const double *dt_seg;
@@ -187,13 +196,14 @@ struct VolzAcc {
 // the hazards h = (beta S I, gamma I) are shared between the covariance step and RK stage 1.
 // ------------------------------------------------------------------------------------------------
 template <bool kStore, class ChSrc, class EpsSrc>
-__device__ __forceinline__ void sir_full_eval(const DevProb &P, const Tables &T, const ChSrc &chs, const EpsSrc &eps,
-                                              double R0, double gam, double S, double I, const FullOut &out,
-                                              long long b, double &loglik, int &status) {
-    const double dt = P.dt_ode, h2 = 0.5 * dt, dt6 = dt / 6.0, dt3 = dt / 3.0;
-    const double g2 = 2.0 * gam, hg = h2 * gam, dg6 = dt6 * gam, dg3 = dt3 * gam;
-    const double invN = 1.0 / P.N;
+__device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD, const Tables &T, const ChSrc &chs,
+                                              const EpsSrc &eps, double R0, double gam, double S, double I,
+                                              const FullOut &out, long long b, double &loglik, int &status) {
+    const double h2 = P.h2, dt6 = P.dt6;
+    const double hg = h2 * gam, dg6 = dt6 * gam;
+    const double invN = P.invN;
     const int g = P.g, k = P.k, nrow = P.nrow;
+    const bool seg_const = k <= kSegConst;
     double R0cum = R0;
     ChCursor<ChSrc> cur(chs, T.chidx, P.nch);
     cur.advance(0, R0cum);
@@ -221,10 +231,53 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const Tables &T,
     for (int seg = 0; seg < k; ++seg) {
         double p00 = 1.0, p01 = 0.0, p10 = 0.0, p11 = 1.0;  // F0
         double s00 = 0.0, s01 = 0.0, s11 = 0.0;              // Sigma (symmetric)
-        const double dts = T.dt_seg[seg];
         const double e0 = eps.at(seg, 0), e1 = eps.at(seg, 1);  // issued early: latency hidden by the loop
         int s = seg * g;
         const int s_end = s + g;
+        // The step body is a macro-like lambda over `dts`: with k <= kSegConst the per-segment dt is read
+        // from the parameter block with a warp-uniform index (uniform-register operand), otherwise from
+        // the shared-memory table (vector register).
+        auto run = [&](const double dts, const int run_end) {
+            const double c1 = fma(-dts, gam, 1.0);        // 1 - gam dts
+            const double c2 = fma(-2.0 * dts, gam, 1.0);  // 1 - 2 gam dts
+#pragma unroll 2
+            for (; s < run_end; ++s) {
+                const double bI = beta * I, bS = beta * S;
+                const double a1 = bS * I;   // h0 = beta*S*I
+                const double gI = gam * I;  // h1
+                // F0 <- F0 + (F F0) dts,  F = [[-bI, -bS], [bI, bS-gam]]:
+                //   row 0 -= dts u,  row 1 = (1 - gam dts) row 1 + dts u,   u_c = bI F0[0][c] + bS F0[1][c]
+                const double t0 = bS * p10, t1 = bS * p11;
+                const double u0 = fma(bI, p00, t0);
+                const double u1 = fma(bI, p01, t1);
+                p00 = fma(-dts, u0, p00);
+                p01 = fma(-dts, u1, p01);
+                p10 = fma(dts, u0, c1 * p10);
+                p11 = fma(dts, u1, c1 * p11);
+                // Sigma <- Sigma + (Sigma F' + F Sigma + A' diag(h) A) dts  with w_c = bI S[0][c] + bS S[1][c]:
+                //   s00 += dts (a1 - 2 w0);  s01 = (1 - gam dts) s01 + dts (w0 - w1 - a1)
+                //   s11 = (1 - 2 gam dts) s11 + dts (2 w1 + a1 + gI)
+                const double q0 = bS * s01, q1 = bS * s11;
+                const double w0 = fma(bI, s00, q0);
+                const double w1 = fma(bI, s01, q1);
+                s00 = fma(dts, fma(-2.0, w0, a1), s00);
+                s01 = fma(dts, (w0 - w1) - a1, c1 * s01);
+                s11 = fma(dts, fma(2.0, w1, a1 + gI), c2 * s11);
+                // RK4 variant (all stages at t[s], k4 at X0 + k3*dt/2).  Stage j needs only a_{j-1} on its
+                // critical path:  beta*S_j = beta*S - (h2 beta) a_{j-1},  I_j = (I - h2 gam I_{j-1}) + h2 a_{j-1};
+                //   S' = S - dt/6 QA,  I' = I + dt/6 QA - gam dt/6 (I + 2 I2 + 2 I3 + I4),  QA = a1 + 2 a2 + 2 a3 + a4
+                const double I2 = fma(h2, a1, fma(-hg, I, I));
+                const double a2 = fma(-hb, a1, bS) * I2;
+                const double I3 = fma(h2, a2, fma(-hg, I2, I));
+                const double a3 = fma(-hb, a2, bS) * I3;
+                const double I4 = fma(h2, a3, fma(-hg, I3, I));
+                const double a4 = fma(-hb, a3, bS) * I4;
+                const double QA = fma(2.0, a2 + a3, a1) + a4;
+                const double PI = fma(2.0, I2 + I3, I) + I4;
+                S = fma(-dt6, QA, S);
+                I = fma(-dg6, PI, fma(dt6, QA, I));
+            }
+        };
         while (s < s_end) {
             // runs of fine steps between change points carry no per-step bookkeeping at all
             if (cur.advance(s, R0cum)) {
@@ -232,50 +285,8 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const Tables &T,
                 hb = h2 * beta;
             }
             const int run_end = min(s_end, cur.next_s);
-#pragma unroll 2
-            for (; s < run_end; ++s) {
-                const double bI = beta * I, bS = beta * S;
-                const double a1 = bS * I;   // h0 = beta*S*I
-                const double gI = gam * I;  // h1
-                // F0 <- F0 + (F F0) dts,  F = [[-bI, -bS], [bI, bS-gam]]
-                const double u0 = fma(bI, p00, bS * p10);
-                const double u1 = fma(bI, p01, bS * p11);
-                const double v0 = fma(-gam, p10, u0);
-                const double v1 = fma(-gam, p11, u1);
-                p00 = fma(-dts, u0, p00);
-                p01 = fma(-dts, u1, p01);
-                p10 = fma(dts, v0, p10);
-                p11 = fma(dts, v1, p11);
-                // Sigma <- Sigma + (Sigma F' + F Sigma + A' diag(h) A) dts
-                const double w0 = fma(bI, s00, bS * s01);
-                const double w1 = fma(bI, s01, bS * s11);
-                const double d00 = fma(-2.0, w0, a1);
-                const double d01 = fma(-gam, s01, w0 - w1) - a1;
-                const double d11 = fma(-g2, s11, fma(2.0, w1, a1 + gI));
-                s00 = fma(dts, d00, s00);
-                s01 = fma(dts, d01, s01);
-                s11 = fma(dts, d11, s11);
-                // RK4 variant (all stages at t[s], k4 at X0 + k3*dt/2), arranged for a short dependent
-                // chain: stage j needs only a_{j-1} on its critical path,
-                //   beta*S_j = beta*S - (h2 beta) a_{j-1},   I_j = (I - h2 gam I_{j-1}) + h2 a_{j-1},
-                // and the state update is accumulated term by term as the stages complete:
-                //   S' = S - dt/6 (a1 + 2 a2 + 2 a3 + a4)
-                //   I' = I + dt/6 (a1 + 2 a2 + 2 a3 + a4) - gam dt/6 (I + 2 I2 + 2 I3 + I4)
-                const double I2 = fma(h2, a1, fma(-hg, I, I));
-                const double a2 = fma(-hb, a1, bS) * I2;
-                double aS = fma(-dt6, a1, S);
-                double aI = fma(dt6, a1, fma(-dg6, I, I));
-                const double I3 = fma(h2, a2, fma(-hg, I2, I));
-                const double a3 = fma(-hb, a2, bS) * I3;
-                aS = fma(-dt3, a2, aS);
-                aI = fma(dt3, a2, fma(-dg3, I2, aI));
-                const double I4 = fma(h2, a3, fma(-hg, I3, I));
-                const double a4 = fma(-hb, a3, bS) * I4;
-                aS = fma(-dt3, a3, aS);
-                aI = fma(dt3, a3, fma(-dg3, I3, aI));
-                S = fma(-dt6, a4, aS);
-                I = fma(dt6, a4, fma(-dg6, I4, aI));
-            }
+            if (seg_const) run(SD.v[seg], run_end);
+            else run(T.dt_seg[seg], run_end);
         }
         // Cholesky of Sigma + 1e-8 I  (lower)
         const double c00 = s00 + kJitter;
@@ -337,13 +348,14 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const Tables &T,
 // A' diag(h) A = [[h0,-h0,0],[-h0,h0+h1,-h1],[0,-h1,h1+h2]], h = (bSI, mu E, gam I).
 // ------------------------------------------------------------------------------------------------
 template <bool kStore, class ChSrc, class EpsSrc>
-__device__ __forceinline__ void seir_full_eval(const DevProb &P, const Tables &T, const ChSrc &chs,
+__device__ __forceinline__ void seir_full_eval(const DevProb &P, const SegDt &SD, const Tables &T, const ChSrc &chs,
                                                const EpsSrc &eps, double R0, double mu, double gam, double S,
                                                double Ex, double I, const FullOut &out, long long b,
                                                double &loglik, int &status) {
-    const double dt = P.dt_ode, h2 = 0.5 * dt, dt6 = dt / 6.0;
+    const double h2 = P.h2, dt6 = P.dt6;
     const int g = P.g, k = P.k, nrow = P.nrow;
-    const double invN = 1.0 / P.N;
+    const double invN = P.invN;
+    (void)SD;
     double R0cum = R0;
     ChCursor<ChSrc> cur(chs, T.chidx, P.nch);
     cur.advance(0, R0cum);

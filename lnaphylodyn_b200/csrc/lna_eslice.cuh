@@ -168,7 +168,7 @@ __device__ __forceinline__ EssParPre ess_par_pre(const CandArgs &a, long long c,
 // ================================================================================================
 template <int kProp, int W>
 __global__ void __launch_bounds__(128)
-k_cand_eval(DevProb P, long long B, CandArgs a) {
+k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, CandArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(P, smem);
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,7 +210,7 @@ k_cand_eval(DevProb P, long long B, CandArgs a) {
         ChProp<kProp> chs{a.par, a.normals, c, 4, x};
         double ll;
         int st = 0;
-        sir_full_eval<true>(P, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+        sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
         const double u = unif(kProp == PROP_GAMMA_RW ? 1 : 0);
         const double acc_a = ll - a.coal_log[c] + offset;
         // a Cholesky failure is an exception in the reference: tryCatch keeps the old state
@@ -257,7 +257,7 @@ k_cand_eval(DevProb P, long long B, CandArgs a) {
                     x.rot_ch = 1;
                 }
                 ChProp<kProp> chs{a.par, a.normals, c, 4, x};
-                sir_full_eval<true>(P, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+                sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
             }
             const bool failed = active && (st & ST_CHOL_FAIL);
             // ESlice_par_General catches the exception and shrinks on (:1641-1651); ESlice_change_points
@@ -288,7 +288,7 @@ k_cand_eval(DevProb P, long long B, CandArgs a) {
                         x.hyper_old = x.hyper_new = hyper_old;
                         x.rot_ch = 0;
                         ChProp<PROP_PLAIN> chs{a.par, a.normals, c, 4, x};
-                        sir_full_eval<true>(P, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+                        sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
                         a.win_slot[c] = (st & ST_CHOL_FAIL) ? -1 : (int)t;
                         a.cand_ll[c] = ll;
                         a.theta[c] = 0.0;

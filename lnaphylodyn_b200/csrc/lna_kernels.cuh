@@ -10,8 +10,8 @@ namespace lna {
 // ================================================================================================
 template <int kModel, bool kStore>
 __global__ void __launch_bounds__(128)
-k_full_loglik(DevProb P, long long B, View param, View initial, View origin, FullOut out, double *coalLog,
-              int *status) {
+k_full_loglik(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, View param,
+              View initial, View origin, FullOut out, double *coalLog, int *status) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(P, smem);
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -23,20 +23,20 @@ k_full_loglik(DevProb P, long long B, View param, View initial, View origin, Ful
         const double R0 = param.at(b, P.iR0), gam = param.at(b, 1);
         if (origin.ok()) {
             EpsFromView eps{origin, b, P.k};
-            sir_full_eval<kStore>(P, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
+            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
         } else {
             EpsZero eps;
-            sir_full_eval<kStore>(P, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
+            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
         }
     } else {
         const double R0 = param.at(b, P.iR0), mu = param.at(b, 1), gam = param.at(b, 2);
         if (origin.ok()) {
             EpsFromView eps{origin, b, P.k};
-            seir_full_eval<kStore>(P, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
+            seir_full_eval<kStore>(P, SD, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
                                    initial.at(b, 2), out, b, ll, st);
         } else {
             EpsZero eps;
-            seir_full_eval<kStore>(P, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
+            seir_full_eval<kStore>(P, SD, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
                                    initial.at(b, 2), out, b, ll, st);
         }
     }
