@@ -9,6 +9,7 @@ struct CandBuf {
     double *cA = nullptr, *cL = nullptr, *cOde = nullptr, *cBeta = nullptr, *cLat = nullptr;
     int *win_slot = nullptr, *n_evals = nullptr, *status = nullptr, *accept = nullptr;
     double *cand_ll = nullptr, *theta = nullptr;
+    int *list = nullptr, *count = nullptr;  // compaction list of the two-phase slice evaluation
 };
 
 // slots >= base are used so that callers can keep their own staging below `base`
@@ -28,10 +29,12 @@ static bool cand_alloc(lna_problem *pb, Scratch &s, size_t base, long long B, lo
     cb.accept = (int *)s.get(base + 8, sizeof(int) * B);
     cb.cand_ll = (double *)s.get(base + 9, sizeof(double) * B);
     cb.theta = (double *)s.get(base + 10, sizeof(double) * B);
-    return cb.cA && cb.cL && cb.cOde && cb.cBeta && cb.cLat && cb.win_slot && cb.n_evals && cb.status && cb.accept &&
+    cb.list = (int *)s.get(base + 11, sizeof(int) * B);
+    cb.count = (int *)s.get(base + 12, sizeof(int) * 4);
+    return cb.list && cb.count && cb.cA && cb.cL && cb.cOde && cb.cBeta && cb.cLat && cb.win_slot && cb.n_evals && cb.status && cb.accept &&
            cb.cand_ll && cb.theta;
 }
-static constexpr size_t kCandSlots = 11;
+static constexpr size_t kCandSlots = 13;
 
 static FullOut cand_out(const CandBuf &cb) {
     return FullOut{OutView{cb.cA, 1, cb.NC}, OutView{cb.cL, 1, cb.NC}, OutView{cb.cOde, 1, cb.NC},
@@ -47,12 +50,12 @@ static int auto_width(const lna_problem *pb, long long B) {
 }
 
 template <int kProp>
-static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a) {
+static int launch_cand_one(lna_problem *pb, long long nchains, int W, const CandArgs &a) {
     const DevProb &P = pb->dp;
-    const long long nthreads = B * W;
-    const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, B);
+    const long long nthreads = nchains * W;
+    const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, nthreads);
     const unsigned grid = nblk(nthreads, block);
-#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, pb->tab_bytes, pb->stream>>>(P, pb->seg, B, a)
+#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, pb->tab_bytes, pb->stream>>>(P, pb->seg, nchains, a)
     switch (W) {
         case 1: LC(1); break;
         case 2: LC(2); break;
@@ -64,6 +67,35 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a) {
     }
 #undef LC
     return launch_check(pb, "k_cand_eval");
+}
+
+// W > 0: one launch, in-kernel waves of W candidates.  W == 0 (auto): width chosen to fill the machine;
+// when that width is 16 the slice runs in two phases -- candidates 1..8 for every chain, then candidates
+// 9..21 (+ the revert candidate) 16-wide for the compacted list of chains still unresolved -- so that
+// no wave is dominated by idle speculative lanes.
+template <int kProp>
+static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, const CandBuf &cb) {
+    CandArgs a = a0;
+    a.first_cand = 0;
+    a.slot_base = 0;
+    a.max_waves = 0;
+    a.chain_list = nullptr;
+    a.n_list = nullptr;
+    a.next_list = cb.list;
+    a.next_count = cb.count;
+    constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
+    if (!kIsEss || W > 0) return launch_cand_one<kProp>(pb, B, W > 0 ? W : 1, a);
+    const int Wa = auto_width(pb, B);
+    if (Wa != 16) return launch_cand_one<kProp>(pb, B, Wa, a);
+    if (cudaMemsetAsync(cb.count, 0, sizeof(int) * 4, pb->stream) != cudaSuccess) return fail("memset failed");
+    a.max_waves = 1;
+    if (launch_cand_one<kProp>(pb, B, 8, a)) return -1;
+    a.first_cand = 8;
+    a.slot_base = B * 8;
+    a.max_waves = 0;
+    a.chain_list = cb.list;
+    a.n_list = cb.count;
+    return launch_cand_one<kProp>(pb, B, 16, a);
 }
 
 static int launch_commit_fields(lna_problem *pb, long long B, const CandBuf &cb, OutView A, OutView L, OutView ode,
@@ -153,7 +185,7 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
     const DevProb &P = pb->dp;
     const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
     const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
-    const int W = spec_width > 0 ? spec_width : auto_width(pb, B);
+    const int W = spec_width;
     Stage s(pb);
     CandArgs a{};
     a.par = item_view(s.in(par_old, nB * npar), npar);
@@ -167,7 +199,7 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
     double *dO = s.tmp<double>(nB * nO), *dbn = s.tmp<double>(nB * nrow), *dlat = s.tmp<double>(nB * nO);
     double *dlo = s.tmp<double>(nB), *dcl = s.tmp<double>(nB);
     CandBuf cb;
-    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * W, cb)) return fail("lna_eslice_par_general: device staging failed");
+    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * std::max(W > 0 ? W : auto_width(pb, B), 24), cb)) return fail("lna_eslice_par_general: device staging failed");
     a.cand = cand_out(cb);
     a.win_slot = cb.win_slot;
     a.cand_ll = cb.cand_ll;
@@ -175,7 +207,7 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
     a.n_evals = cb.n_evals;
     a.status = cb.status;
     a.accept = cb.accept;
-    if (launch_cand<PROP_ESS_PAR>(pb, B, W, a)) return -1;
+    if (launch_cand<PROP_ESS_PAR>(pb, B, W, a, cb)) return -1;
     if (launch_commit_fields(pb, B, cb, item_out(dA, nA), item_out(dL, nA), item_out(dO, nO), item_out(dbn, nrow),
                              item_out(dlat, nO)))
         return -1;
@@ -209,7 +241,7 @@ extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double
     const DevProb &P = pb->dp;
     const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
     const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
-    const int W = spec_width > 0 ? spec_width : auto_width(pb, B);
+    const int W = spec_width;
     // par = c(initial, param): assemble on the host (small)
     std::vector<double> par(nB * npar);
     for (size_t b = 0; b < nB; ++b) {
@@ -228,7 +260,7 @@ extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double
     double *dO = s.tmp<double>(nB * nO), *dbn = s.tmp<double>(nB * nrow), *dlat = s.tmp<double>(nB * nO);
     double *dlcp = s.tmp<double>(nB), *dcl = s.tmp<double>(nB);
     CandBuf cb;
-    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * W, cb))
+    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * std::max(W > 0 ? W : auto_width(pb, B), 24), cb))
         return fail("lna_eslice_change_points: device staging failed");
     // the host vector must outlive the async copy
     if (cudaStreamSynchronize(pb->stream) != cudaSuccess) return fail("lna_eslice_change_points: sync failed");
@@ -239,7 +271,7 @@ extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double
     a.n_evals = cb.n_evals;
     a.status = cb.status;
     a.accept = cb.accept;
-    if (launch_cand<PROP_ESS_CHPT>(pb, B, W, a)) return -1;
+    if (launch_cand<PROP_ESS_CHPT>(pb, B, W, a, cb)) return -1;
     if (launch_commit_fields(pb, B, cb, item_out(dA, nA), item_out(dL, nA), item_out(dO, nO), item_out(dbn, nrow),
                              item_out(dlat, nO)))
         return -1;
@@ -331,7 +363,7 @@ __global__ void k_bump(long long B, const int *n_evals, const int *accept, const
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= B) return;
     counters[(long long)which_evals * B + c] += n_evals[c];
-    if (count_accept) counters[2 * B + c] += accept[c];
+    if (count_accept) counters[2 * B + c] += (accept[c] & 1) + ((accept[c] >> 1) & 1);
     // NEG/NAN bits of a proposal that was not adopted say nothing about the chain's state
     const int adopted = win_slot ? (win_slot[c] >= 0) : 1;
     counters[3 * B + c] |= adopted ? status[c] : (status[c] & (ST_CHOL_FAIL | ST_CAP_HIT));
@@ -435,12 +467,8 @@ extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *
 
 static int chains_cand_args(lna_chains *ch, const lna_mcmc_opts *o, const double *normals, const double *uniforms,
                             int unif_off, int W, CandArgs &a) {
-    lna_problem *pb = ch->pb;
     const long long B = ch->B;
-    if (ch->cb.NC < B * W || ch->cb.B != B) {
-        if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * W, ch->cb))
-            return fail("lna_chains_step: candidate scratch allocation failed");
-    }
+    (void)W;  // the scratch was sized for the widest stage by lna_chains_step_dev
     a = CandArgs{};
     a.par = soa_view(ch->par, B);
     a.origin = soa_view(ch->origin, B);
@@ -470,7 +498,7 @@ static int chains_stage(lna_chains *ch, const lna_mcmc_opts *o, const double *no
     const long long B = ch->B;
     CandArgs a;
     if (chains_cand_args(ch, o, normals, uniforms, unif_off, W, a)) return -1;
-    if (launch_cand<kProp>(pb, B, W, a)) return -1;
+    if (launch_cand<kProp>(pb, B, W, a, ch->cb)) return -1;
     if (launch_commit_fields(pb, B, ch->cb, soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B),
                              soa_out(ch->betaN, B), soa_out(ch->latent, B)))
         return -1;
@@ -478,7 +506,7 @@ static int chains_stage(lna_chains *ch, const lna_mcmc_opts *o, const double *no
     k_commit_par_wide<kProp><<<nblk(B * npar, 256), 256, 0, pb->stream>>>(P, B, a, soa_out(ch->par_alt, B), ch->coalLog);
     if (launch_check(pb, "k_commit_par_wide")) return -1;
     std::swap(ch->par, ch->par_alt);  // update_Par_ESlice_combine does not touch logOrigin (LNA_chpt_slice.R:456-472)
-    const bool mh = (kProp == PROP_GAMMA_RW || kProp == PROP_HYPER_NOOP);
+    const bool mh = (kProp == PROP_GAMMA_RW || kProp == PROP_HYPER_NOOP || kProp == PROP_MH_PAIR);
     k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->cb.n_evals, ch->cb.accept, ch->cb.status, ch->cb.win_slot,
                                                  ch->counters, 0, mh ? 1 : 0);
     return launch_check(pb, "k_bump");
@@ -492,14 +520,18 @@ extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const
     const DevProb &P = pb->dp;
     const long long B = ch->B;
     if (o->ESS_vec[6] != 0) return fail("lna_chains_step: ESS_vec[7] = 1 is not supported");
-    const int W = o->spec_width > 0 ? o->spec_width : auto_width(pb, B);
-    if (ch->cb.NC < B * W || ch->cb.B != B) {  // size the candidate scratch once for the widest stage
-        if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * W, ch->cb))
+    const int W = o->spec_width;  // 0 = auto (two-phase when the machine-filling width is 16)
+    const int Wmax = std::max(W > 0 ? W : auto_width(pb, B), 24);  // two-phase: 8 + 16 slots per chain
+    if (ch->cb.NC < B * Wmax || ch->cb.B != B) {  // size the candidate scratch once for the widest stage
+        if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * Wmax, ch->cb))
             return fail("lna_chains_step: candidate scratch allocation failed");
     }
     // 1. Update_Param_each_Norm: gamma random walk (entry c) and the no-op hyper entry (d)  [A.17]
-    if (chains_stage<PROP_GAMMA_RW>(ch, o, normals, uniforms, 0, 1)) return -1;
-    if (o->hyper_noop_mh && chains_stage<PROP_HYPER_NOOP>(ch, o, normals, uniforms, 2, 1)) return -1;
+    if (o->hyper_noop_mh) {  // both MH entries speculatively in one latency period
+        if (chains_stage<PROP_MH_PAIR>(ch, o, normals, uniforms, 0, 4)) return -1;
+    } else if (chains_stage<PROP_GAMMA_RW>(ch, o, normals, uniforms, 0, 1)) {
+        return -1;
+    }
     // 2. update_Par_ESlice_combine -> ESlice_par_General
     if (chains_stage<PROP_ESS_PAR>(ch, o, normals, uniforms, 3, W)) return -1;
     // 3. updateTraj_general_NC -> ESlice_general_NC (in place on the state)

@@ -18,7 +18,7 @@
 
 namespace lna {
 
-enum : int { PROP_PLAIN = 0, PROP_GAMMA_RW = 1, PROP_HYPER_NOOP = 2, PROP_ESS_PAR = 3, PROP_ESS_CHPT = 4 };
+enum : int { PROP_PLAIN = 0, PROP_GAMMA_RW = 1, PROP_HYPER_NOOP = 2, PROP_ESS_PAR = 3, PROP_ESS_CHPT = 4, PROP_MH_PAIR = 5 };
 
 constexpr int kMaxUnif = 22;
 constexpr double kLnSqrt2Pi = 0.918938533204672741780329736406;  // R's M_LN_SQRT_2PI
@@ -40,7 +40,8 @@ struct PropScalars {
     double S0, I0, R0, gam;       // evaluated values
     double ct, sn;                // cos/sin(theta)
     double hyper_old, hyper_new;  // change-ratio scale before / after
-    int rot_ch;                   // ESS_vec[5]
+    int rot_ch;                   // ESS_vec[5]; 0 also marks the "revert to the current parameters" candidate
+    int noop;                     // MH pair: this lane applies ch <- exp(log(ch) * hyper / hyper)
 };
 
 // par layout (SIR): [S0, I0, R0, gamma, ch_1..ch_nch, hyper]  
@@ -67,6 +68,10 @@ struct ChProp {
         if (kProp == PROP_HYPER_NOOP) {
             // exp(log(ch) * hyper / hyper), R/LNA_chpt_slice.R:238-241 (ulp-level perturbation, A.17)
             return exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_old));
+        } else if (kProp == PROP_MH_PAIR) {
+            // same instruction stream for all lanes of the pair kernel; the flag selects per lane
+            const double pert = exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_old));
+            return x.noop ? pert : cj;
         } else if (kProp == PROP_ESS_PAR) {
             if (!x.rot_ch) return cj;
             const double z = __dmul_rn(log(cj), x.hyper_old);  // :1296
@@ -74,7 +79,8 @@ struct ChProp {
             return exp(__ddiv_rn(zp, x.hyper_new));            // :1310
         } else if (kProp == PROP_ESS_CHPT) {
             const double nu = __ddiv_rn(r.nu, x.hyper_old);    // :1344
-            return exp(rot(log(cj), x.ct, nu, x.sn));          // :1249-1251
+            const double v = exp(rot(log(cj), x.ct, nu, x.sn));  // :1249-1251
+            return x.rot_ch ? v : cj;
         } else {
             return cj;
         }
@@ -126,6 +132,14 @@ struct CandArgs {
     int *n_evals;    // [B] evaluations the sequential reference loop would have made
     int *status;     // [B]
     int *accept;     // [B] MH accept flag (MH kinds)
+    // two-phase slice evaluation: a launch covers candidates first_cand+1 .. ; after `max_waves` waves the
+    // still-unresolved chains are appended to next_list (compaction) for a wider follow-up launch
+    int first_cand;
+    long long slot_base;    // scratch slots of this launch start here (phase B must not overwrite phase-A winners)
+    int max_waves;          // 0 = until resolved
+    const int *chain_list;  // null = chains 0..B-1
+    const int *n_list;      // device count of chain_list entries
+    int *next_list, *next_count;
 };
 
 // Whitened scalars of Param_Slice_update_all2 (:1287-1296) and their rotated images (:1299-1311).
@@ -167,14 +181,20 @@ __device__ __forceinline__ EssParPre ess_par_pre(const CandArgs &a, long long c,
 // SIR (p = 2) only, like the reference's samplers (hard-wired subvec(0,1) / subvec(2,..)).
 // ================================================================================================
 template <int kProp, int W>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, CandArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(P, smem);
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c = t / W;
-    const int w = (int)(t % W);
-    const bool valid = c < B;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ci = t0 / W;  // index into the (optional) compacted chain list
+    const int w = (int)(t0 % W);
+    const long long t = a.slot_base + t0;  // scratch slot of this thread's candidate
+    bool valid = ci < B;
+    long long c = ci;
+    if (a.chain_list) {
+        valid = ci < (long long)__ldg(a.n_list);
+        c = valid ? (long long)__ldg(a.chain_list + ci) : 0;
+    }
     const int lane = threadIdx.x & 31;
     const unsigned gmask = (W >= 32) ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(W - 1)));
     const int npar = 2 + P.npt;
@@ -185,7 +205,55 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
     auto unif = [&](int q) { return a.uniforms.at(cc, q); };
     EpsFromView eps{a.origin, cc, P.k};
 
-    if (!kIsEss) {
+    if (kProp == PROP_MH_PAIR) {
+        // ---- both entries of Update_Param_each_Norm in ONE latency period (W = 4 lanes per chain) -----
+        //   lane 0: gamma' proposal, current ch            (entry c)
+        //   lane 1: gamma' accepted, ch <- exp(log ch*h/h) (entry d after an accepted c)
+        //   lane 2: gamma  kept,     ch <- exp(log ch*h/h) (entry d after a rejected c)
+        // The MH tests are then chained exactly as the sequential code would (uniforms 1 and 2).
+        PropScalars x;
+        x.S0 = a.par.at(cc, 0);
+        x.I0 = a.par.at(cc, 1);
+        x.R0 = a.par.at(cc, 2);
+        x.gam = a.par.at(cc, 3);
+        x.hyper_old = x.hyper_new = a.par.at(cc, npar - 1);
+        x.ct = 1.0;
+        x.sn = 0.0;
+        x.rot_ch = 0;
+        const double raw = log(x.gam), po = a.gamma_prop;
+        const double rnew = raw + (-po + (po - (-po)) * unif(0));
+        const double offset =
+            dnorm_log(rnew, a.gamma_prior[0], a.gamma_prior[1]) - dnorm_log(raw, a.gamma_prior[0], a.gamma_prior[1]);
+        if (w <= 1) x.gam = exp(rnew);
+        x.noop = (w >= 1);
+        double ll = kSentinel;
+        int st = 0;
+        if (valid && w <= 2) {  // one instruction stream for the three lanes (no divergence)
+            ChProp<PROP_MH_PAIR> chs{a.par, a.normals, c, 4, x};
+            sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+        }
+        const int base = lane & ~3;
+        const double ll0 = __shfl_sync(0xffffffffu, ll, base), ll1 = __shfl_sync(0xffffffffu, ll, base + 1),
+                     ll2 = __shfl_sync(0xffffffffu, ll, base + 2);
+        const int st0 = __shfl_sync(0xffffffffu, st, base), st1 = __shfl_sync(0xffffffffu, st, base + 1),
+                  st2 = __shfl_sync(0xffffffffu, st, base + 2);
+        if (valid && w == 0) {
+            const double cl = a.coal_log[c];
+            const bool acc1 = !(st0 & ST_CHOL_FAIL) && (log(unif(1)) < ll0 - cl + offset);
+            const double cur = acc1 ? ll0 : cl;
+            const double lln = acc1 ? ll1 : ll2;
+            const int stn = acc1 ? st1 : st2;
+            const bool acc2 = !(stn & ST_CHOL_FAIL) && (log(unif(2)) < lln - cur + 0.0);
+            const int slot = acc2 ? (int)t + (acc1 ? 1 : 2) : (acc1 ? (int)t : -1);
+            a.win_slot[c] = slot;
+            a.cand_ll[c] = acc2 ? lln : cur;
+            a.theta[c] = rnew;
+            a.n_evals[c] = 2;
+            a.status[c] = acc2 ? stn : (acc1 ? st0 : ((st0 | stn) & ST_CHOL_FAIL));
+            a.accept[c] = (acc1 ? 1 : 0) | (acc2 ? 2 : 0);
+        }
+        return;
+    } else if (!kIsEss) {
         // ---- Metropolis step: Update_Param_each_Norm entry + Update_Param ------------------------
         if (!valid) return;
         PropScalars x;
@@ -197,6 +265,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
         x.ct = 1.0;
         x.sn = 0.0;
         x.rot_ch = 0;
+        x.noop = 0;
         double offset = 0.0, prop = 0.0;
         int iu = 0;
         if (kProp == PROP_GAMMA_RW) {
@@ -235,68 +304,60 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
         ts.init();
         bool done = !valid;
         for (int wave = 0;; ++wave) {
-            const int i = wave * W + w + 1;  // candidate number in the sequential loop
-            const bool active = !done && i <= kMaxCand;
+            const int i = a.first_cand + wave * W + w + 1;  // candidate number in the sequential loop
+            // candidate kMaxCand+1 is the reference's cap: revert to the current parameters and recompute
+            // (:1609-1622 / :1363-1374).  It is evaluated speculatively in the same wave as the last shrinks.
+            const bool is_revert = (i == kMaxCand + 1);
+            const bool active = !done && i <= kMaxCand + 1;
             double ll = kSentinel;
             int st = 0;
             if (active) {
-                ts.advance(i, unif);
                 PropScalars x;
+                if (!is_revert) ts.advance(i, unif);
+                const double th = is_revert ? 0.0 : ts.th;
                 if (kProp == PROP_ESS_PAR) {
-                    ess_par_scalars(a, c, npar, zpre, ts.th, x);
+                    ess_par_scalars(a, c, npar, zpre, th, x);
                 } else {
                     double sn, ct;
-                    sincos(ts.th, &sn, &ct);
+                    sincos(th, &sn, &ct);
                     x.ct = ct;
                     x.sn = sn;
-                    x.S0 = a.par.at(c, 0);
-                    x.I0 = a.par.at(c, 1);
-                    x.R0 = a.par.at(c, 2);
-                    x.gam = a.par.at(c, 3);
                     x.hyper_old = x.hyper_new = hyper_old;
                     x.rot_ch = 1;
                 }
+                x.S0 = a.par.at(c, 0);
+                if (kProp != PROP_ESS_PAR || is_revert) {  // current parameters, bit for bit
+                    x.I0 = a.par.at(c, 1);
+                    x.R0 = a.par.at(c, 2);
+                    x.gam = a.par.at(c, 3);
+                }
+                if (is_revert) x.rot_ch = 0;
+                x.noop = 0;
+                // one instruction stream for shrink and revert candidates (no divergence inside the warp)
                 ChProp<kProp> chs{a.par, a.normals, c, 4, x};
                 sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
             }
             const bool failed = active && (st & ST_CHOL_FAIL);
             // ESlice_par_General catches the exception and shrinks on (:1641-1651); ESlice_change_points
-            // does not catch it, so the first failing candidate aborts the update.
-            const bool stop_here = active && ((ll > logy && !failed) || (kProp == PROP_ESS_CHPT && failed));
+            // does not catch it, so the first failing candidate aborts the update.  The revert candidate
+            // always ends the loop.
+            const bool stop_here =
+                active && (is_revert || (ll > logy && !failed) || (kProp == PROP_ESS_CHPT && failed));
             const unsigned m = __ballot_sync(0xffffffffu, stop_here) & gmask;
-            if (!done) {
-                if (m) {
-                    const int winner = __ffs(m) - 1;
-                    if (lane == winner) {
-                        a.win_slot[c] = failed ? -1 : (int)t;
-                        a.cand_ll[c] = ll;
-                        a.theta[c] = ts.th;
-                        a.n_evals[c] = i;
-                        a.status[c] = st;
-                    }
-                    done = true;
-                } else if ((wave + 1) * W >= kMaxCand) {
-                    // 20-shrink cap: revert to the current parameters and recompute (:1609-1622 / :1363-1374)
-                    if (w == 0) {
-                        PropScalars x;
-                        x.ct = 1.0;
-                        x.sn = 0.0;
-                        x.S0 = a.par.at(c, 0);
-                        x.I0 = a.par.at(c, 1);
-                        x.R0 = a.par.at(c, 2);
-                        x.gam = a.par.at(c, 3);
-                        x.hyper_old = x.hyper_new = hyper_old;
-                        x.rot_ch = 0;
-                        ChProp<PROP_PLAIN> chs{a.par, a.normals, c, 4, x};
-                        sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
-                        a.win_slot[c] = (st & ST_CHOL_FAIL) ? -1 : (int)t;
-                        a.cand_ll[c] = ll;
-                        a.theta[c] = 0.0;
-                        a.n_evals[c] = kMaxCand + 1;
-                        a.status[c] = st | ST_CAP_HIT;
-                    }
-                    done = true;
+            if (!done && m) {
+                const int winner = __ffs(m) - 1;
+                if (lane == winner) {
+                    a.win_slot[c] = failed ? -1 : (int)t;
+                    a.cand_ll[c] = ll;
+                    a.theta[c] = is_revert ? 0.0 : ts.th;
+                    a.n_evals[c] = i;
+                    a.status[c] = st | (is_revert ? ST_CAP_HIT : 0);
                 }
+                done = true;
+            }
+            if (!done && a.max_waves && wave + 1 == a.max_waves) {
+                if (w == 0) a.next_list[atomicAdd(a.next_count, 1)] = (int)c;  // hand over to the next phase
+                done = true;
             }
             if (!__any_sync(0xffffffffu, !done)) break;
         }
@@ -560,7 +621,16 @@ __global__ void k_commit_par_wide(DevProb P, long long B, CandArgs a, OutView pa
     }
     const bool is_ch = j >= 4 && j < npar - 1;
     double v = old;
-    if (kProp == PROP_GAMMA_RW) {
+    if (kProp == PROP_MH_PAIR) {
+        const int acc = a.accept[c];
+        if (j == 3 && (acc & 1)) v = exp(a.theta[c]);
+        if (is_ch && (acc & 2)) {
+            PropScalars x{};
+            x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
+            ChProp<PROP_HYPER_NOOP> chs{a.par, a.normals, c, 4, x};
+            v = chs.ch(j - 4);
+        }
+    } else if (kProp == PROP_GAMMA_RW) {
         if (j == 3) v = exp(a.theta[c]);
     } else if (kProp == PROP_HYPER_NOOP) {
         if (is_ch) {
@@ -589,6 +659,7 @@ __global__ void k_commit_par_wide(DevProb P, long long B, CandArgs a, OutView pa
             x.ct = ct;
             x.sn = sn;
             x.hyper_old = x.hyper_new = a.par.at(c, npar - 1);
+            x.rot_ch = 1;
             ChProp<PROP_ESS_CHPT> chs{a.par, a.normals, c, 4, x};
             v = chs.ch(j - 4);
         }

@@ -69,6 +69,33 @@ def test_eslice_par_general_step_for_step(api, changepoint, width):
     assert d["n_evals"].max() > 3  # the sample exercises real shrinking
 
 
+def test_eslice_par_general_two_phase_window(api, changepoint):
+    """B inside the window where the automatic policy runs two compacted phases (candidates 1..8 for
+    every chain, then 9..21 sixteen-wide for the unresolved ones): same chains as the sequential loop.
+    Spot-checked against the oracle, fully checked against the single-phase GPU path."""
+    g = changepoint
+    st = state_of(g)
+    opts = driver.opts_from_golden(g)
+    B = 3000
+    rng = np.random.default_rng(101)
+    nrm, unf = rng.standard_normal((B, 43)), rng.random((B, 22))
+    unf[:40, 0] = 1.0 - 1e-9 * rng.random(40)
+    call = lambda w: api.ESlice_par_General(np.tile(st["par"], (B, 1)), g.times, st["OriginTraj"], opts["priorList"],
+                                            g.x_r, g.x_i, g.init, g.gridsize, opts["ESS_vec"], st["coalLog"],
+                                            g.t_correct, normals=nrm, uniforms=unf, spec_width=w)
+    d2, d1 = call(0), call(4)
+    assert np.array_equal(d2["n_evals"], d1["n_evals"]) and np.array_equal(d2["status"], d1["status"])
+    assert np.array_equal(d2["par"], d1["par"]) and np.array_equal(d2["CoalLog"], d1["CoalLog"])
+    assert np.array_equal(d2["LatentTraj"], d1["LatentTraj"]) and np.array_equal(d2["FT"]["A"], d1["FT"]["A"])
+    assert (d2["n_evals"] > 8).sum() > 100 and (d2["status"] & 8).sum() >= 1
+    for b in list(range(0, 40, 4)) + list(range(40, B, 300)):
+        o = orc.ESlice_par_General(st["par"], g.times, st["OriginTraj"], opts["priorList"], g.x_r, g.x_i, g.init,
+                                   g.gridsize, opts["ESS_vec"], st["coalLog"], g.t_correct, normals=nrm[b],
+                                   uniforms=unf[b])
+        assert d2["n_evals"][b] == o["n_evals"] and relerr(d2["par"][b], o["par"]) < TOL
+        assert d2["CoalLog"][b] == pytest.approx(o["CoalLog"], rel=TOL)
+
+
 def test_eslice_general_nc_step_for_step(api, changepoint):
     g = changepoint
     st = state_of(g)
