@@ -170,3 +170,33 @@ def bench_eslice(pb, g, B, iters, rank, world, dev):
             "mean_full_evals_per_iter": float(cnt[0]) / tot, "mean_cheap_evals_per_iter": float(cnt[1]) / tot,
             "consumed_full_evals_per_s": float(cnt[0]) / (ms * 1e-3), "gpu_launches": int(launches),
             "spec_width": "auto", "finite_coalLog": bool(np.all(np.isfinite(after["coalLog"])))}
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU plumbing: contiguous chain shards, no data-path collective
+# ------------------------------------------------------------------------------------------------
+
+def shard_range(B, rank, world):
+    """Contiguous block [begin, end) of the B global chains owned by `rank` (lna_shard)."""
+    b, e = C.c_int64(), C.c_int64()
+    check(_lib.lib().lna_shard(int(B), int(rank), int(world), C.byref(b), C.byref(e)), "lna_shard")
+    return b.value, e.value
+
+
+def gather_summaries(local, group=None):
+    """All-gather the per-chain summary rows (coalLog, logOrigin, n_full_evals, status) of every rank,
+    in global chain order.  `local`: torch tensor (B_local, 4) on this rank's device (NCCL) or on the CPU
+    (gloo).  Shards may differ by one chain, so the gather is padded to the largest shard."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    pad = torch.zeros((mx, local.shape[1]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)

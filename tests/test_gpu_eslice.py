@@ -176,3 +176,33 @@ def test_chains_step_for_step(api, changepoint):
             assert s["n_cheap_evals"][c] == ref[c]["n_cheap"], (it, c)
             assert s["n_mh_accept"][c] == ref[c]["n_mh_accept"], (it, c)
     assert np.all(np.isfinite(s["coalLog"]))
+
+
+def test_sharded_chains_equal_single_device(api, changepoint):
+    """chains are independent, so a batch sharded over two GPUs must reproduce the
+    single-GPU batch per chain, bit for bit."""
+    from lnaphylodyn_b200 import _lib, chains as chm
+    if _lib.lib().lna_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = changepoint
+    B, iters, seed = 16, 3, 9
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    single = chm.Chains(api.Problem(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init, device=0),
+                        np.tile(par0, (B, 1)), g.setting("control.traj"))
+    shards = []
+    for r in range(2):
+        b, e = chm.shard_range(B, r, 2)
+        pb = api.Problem(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init, device=r)
+        shards.append((b, e, chm.Chains(pb, np.tile(par0, (e - b, 1)), g.setting("control.traj"))))
+    opts = chm.vignette_opts(g, update_traj=True)
+    for it in range(iters):
+        nrm, unf = chm.draw_streams(B, single.n_norm, seed, it)
+        single.step(opts, nrm, unf)
+        for b, e, ch in shards:
+            ch.step(opts, nrm[b:e], unf[b:e])
+    s = single.get()
+    for b, e, ch in shards:
+        t = ch.get()
+        for k in ("par", "OriginTraj", "LatentTraj", "coalLog", "logOrigin", "n_full_evals", "n_cheap_evals"):
+            assert np.array_equal(t[k], s[k][b:e]), k
