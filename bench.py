@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--chains", type=int, default=4096, help="concurrent chains per GPU")
     ap.add_argument("--proposals", type=int, default=16, help="slice proposals per chain in one likelihood batch")
     ap.add_argument("--ref-evals-per-core", type=int, default=1024)
-    ap.add_argument("--cpu-evals-per-core", type=int, default=2048)
+    ap.add_argument("--cpu-evals-per-core", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eslice", action="store_true")
     ap.add_argument("--eslice-iters", type=int, default=5)

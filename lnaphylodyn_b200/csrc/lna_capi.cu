@@ -92,6 +92,10 @@ struct lna_problem {
     Scratch scratch;
     int64_t launches = 0;
     size_t tab_bytes = 0;
+    // host-buffer pipeline: inputs of chunk i+1 are copied on `copy_stream` while chunk i computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[8] = {};
+    cudaEvent_t done_ev = nullptr;
 };
 
 template <class T>
@@ -164,6 +168,9 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
         return nullptr;
     }
     pb->own_stream = true;
+    cudaStreamCreateWithFlags(&pb->copy_stream, cudaStreamNonBlocking);
+    for (auto &e : pb->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pb->done_ev, cudaEventDisableTiming);
     DevProb &P = pb->dp;
     P.model = cfg->model;
     P.p = cfg->model == LNA_MODEL_SIR ? 2 : 3;
@@ -291,6 +298,10 @@ extern "C" void lna_problem_destroy(lna_problem *pb) {
     if (pb->stream) cudaStreamSynchronize(pb->stream);
     for (void *p : pb->owned) cudaFree(p);
     pb->scratch.release();
+    if (pb->copy_stream) cudaStreamDestroy(pb->copy_stream);
+    for (auto &e : pb->chunk_ev)
+        if (e) cudaEventDestroy(e);
+    if (pb->done_ev) cudaEventDestroy(pb->done_ev);
     if (pb->own_stream && pb->stream) cudaStreamDestroy(pb->stream);
     delete pb;
 }
@@ -439,6 +450,42 @@ extern "C" int lna_full_loglik(lna_problem *pb, int64_t B, const double *param, 
     if (B <= 0) return 0;
     const DevProb &P = pb->dp;
     const size_t p = P.p, k = P.k, nrow = P.nrow, nB = (size_t)B;
+    const bool ll_only = coalLog && !Acube && !Lcube && !Ode_coarse && !betaN && !LatentTraj;
+    if (ll_only && B >= 16384 && param && initial && OriginTraj && pb->copy_stream) {
+        // Large likelihood-only batches are PCIe-bound (992 B in per evaluation): split into chunks and
+        // overlap the H2D copy of chunk i+1 (copy stream) with the kernel of chunk i (compute stream).
+        cudaSetDevice(pb->device);
+        const int nchunk = 4;  // >= 16k evaluations per chunk keeps each kernel off the ~0.2 ms single-evaluation latency floor
+        double *dpar = (double *)pb->scratch.get(0, nB * P.npt * sizeof(double));
+        double *dini = (double *)pb->scratch.get(1, nB * p * sizeof(double));
+        double *dor = (double *)pb->scratch.get(2, nB * k * p * sizeof(double));
+        double *dcl = (double *)pb->scratch.get(3, nB * sizeof(double));
+        int32_t *dst = (int32_t *)pb->scratch.get(4, nB * sizeof(int32_t));
+        if (!dpar || !dini || !dor || !dcl || !dst) return fail("lna_full_loglik: device staging failed");
+        // the copy stream must not run ahead of earlier work that still reads the staging buffers
+        CK(cudaEventRecord(pb->done_ev, pb->stream));
+        CK(cudaStreamWaitEvent(pb->copy_stream, pb->done_ev, 0));
+        for (int c = 0; c < nchunk; ++c) {
+            const size_t b0 = nB * c / nchunk, b1 = nB * (c + 1) / nchunk, n = b1 - b0;
+            if (!n) continue;
+            CK(cudaMemcpyAsync(dpar + b0 * P.npt, param + b0 * P.npt, n * P.npt * sizeof(double),
+                               cudaMemcpyHostToDevice, pb->copy_stream));
+            CK(cudaMemcpyAsync(dini + b0 * p, initial + b0 * p, n * p * sizeof(double), cudaMemcpyHostToDevice,
+                               pb->copy_stream));
+            CK(cudaMemcpyAsync(dor + b0 * k * p, OriginTraj + b0 * k * p, n * k * p * sizeof(double),
+                               cudaMemcpyHostToDevice, pb->copy_stream));
+            CK(cudaEventRecord(pb->chunk_ev[c], pb->copy_stream));
+            CK(cudaStreamWaitEvent(pb->stream, pb->chunk_ev[c], 0));
+            if (full_loglik_dev_impl(pb, (int64_t)n, dpar + b0 * P.npt, dini + b0 * p, dor + b0 * k * p, dcl + b0,
+                                     dst + b0, nullptr, nullptr, nullptr, nullptr, nullptr))
+                return -1;
+            CK(cudaMemcpyAsync(coalLog + b0, dcl + b0, n * sizeof(double), cudaMemcpyDeviceToHost, pb->stream));
+            if (status)
+                CK(cudaMemcpyAsync(status + b0, dst + b0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, pb->stream));
+        }
+        CK(cudaStreamSynchronize(pb->stream));
+        return 0;
+    }
     Stage s(pb);
     const double *dpar = s.in(param, nB * P.npt), *dini = s.in(initial, nB * p), *dor = s.in(OriginTraj, nB * k * p);
     double *dcl = s.out(coalLog, nB);
