@@ -130,6 +130,9 @@ int lna_traj_sim_noncentral(lna_problem *pb, int64_t B, const double *Ode_coarse
 /* volz_loglik_nh2 (:1119-1176) on given trajectories (B x nrow x (p+1)) and betaN (B x nrow). */
 int lna_volz_loglik_nh2(lna_problem *pb, int64_t B, const double *traj, const double *betaN,
                         double *loglik, int32_t *status);
+/* volz_loglik_nh3 (:1058-1113): the same without the NaN guard (a NaN sum is returned as is). */
+int lna_volz_loglik_nh3(lna_problem *pb, int64_t B, const double *traj, const double *betaN,
+                        double *loglik, int32_t *status);
 /* coal_loglik3 (:1016-1054) / coal_loglik (SIR_phylodyn.cpp:436-468): Kingman with scale lambda[b].
  * take_log != 0: column `col` (1-based state column of traj) holds counts (coal_loglik3, transX
  * "standard"); take_log == 0: it already holds log-counts (coal_loglik uses col = 2). */

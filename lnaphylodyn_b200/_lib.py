@@ -54,6 +54,7 @@ _SIGS = {
     "lna_transform_traj": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp, _vp]),
     "lna_traj_sim_noncentral": (C.c_int, [_vp, _I64] + [_vp] * 8),
     "lna_volz_loglik_nh2": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp]),
+    "lna_volz_loglik_nh3": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp]),
     "lna_coal_loglik": (C.c_int, [_vp, _I64, _vp, _vp, C.c_int, C.c_int, _vp]),
     "lna_full_loglik": (C.c_int, [_vp, _I64] + [_vp] * 10),
     "lna_full_loglik_dev": (C.c_int, [_vp, _I64] + [_vp] * 10),

@@ -334,7 +334,7 @@ def Traj_sim_general_noncentral(OdeTraj, Filter_NC, t_correct, *, normals):
             "logMultiNorm": float(lm[0]), "logOrigin": float(lo[0])}
 
 
-def volz_loglik_nh2(init, f1, betaN, t_correct, index, transX="standard"):
+def volz_loglik_nh2(init, f1, betaN, t_correct, index, transX="standard", _fn="lna_volz_loglik_nh2"):
     """LNA_functional.cpp:1119-1176 (literal per-event kernel)."""
     F = np.asarray(f1, dtype=np.float64)
     single = F.ndim == 2
@@ -346,9 +346,35 @@ def volz_loglik_nh2(init, f1, betaN, t_correct, index, transX="standard"):
     Ff, _ = pb._mats(F, (nrow, p + 1))
     b = _d(betaN).reshape(Ff.shape[0], nrow)
     ll, st = np.empty(Ff.shape[0]), np.zeros(Ff.shape[0], dtype=np.int32)
-    check(_lib.lib().lna_volz_loglik_nh2(pb.h, Ff.shape[0], _ptr(Ff), _ptr(b), _ptr(ll), _ptr(st)),
-          "lna_volz_loglik_nh2")
+    check(getattr(_lib.lib(), _fn)(pb.h, Ff.shape[0], _ptr(Ff), _ptr(b), _ptr(ll), _ptr(st)), _fn)
     return float(ll[0]) if single else ll
+
+
+def volz_loglik_nh3(init, f1, betaN, t_correct, index, transX="standard"):
+    """LNA_functional.cpp:1058-1113: volz_loglik_nh2 without the NaN guard."""
+    return volz_loglik_nh2(init, f1, betaN, t_correct, index, transX, _fn="lna_volz_loglik_nh3")
+
+
+def log_like_traj_general_adjust(SdeTraj, OdeTraj, Filter_NC, gridsize, t_correct):
+    """LNA_functional.cpp:746-767: the body is commented out in the reference; it returns 0."""
+    return 0.0
+
+
+def Traj_sim_ezG_NC(initial, times, param, gridsize, x_r, x_i, t_correct, transP="changepoint", model="SIR",
+                    transX="standard", *, normals):
+    """LNA_functional.cpp:980-1004 = New_Param_List's ODE/FT + Traj_sim_general_noncentral (normals supplied)."""
+    npl = New_Param_List(param, initial, gridsize, times, x_r, x_i, transP, model, transX)
+    return Traj_sim_general_noncentral(npl["Ode"], npl["FT"], t_correct, normals=normals)
+
+
+def ODE_rk45_stop(initial, t, param, x_r, x_i, transP="changepoint", model="SIR", transX="standard", tol=5):
+    """LNA_functional.cpp:495-530: first grid time at which state x_i[4] drops below `tol`
+    (else t[n-1] + 0.1).  The trajectory comes from the device; the scan is on the host."""
+    traj = ODE_rk45(initial, t, param, x_r, x_i, transP, model, transX)
+    col = traj[1:, 1 + _xi(x_i)[3]]
+    hit = np.nonzero(col < tol)[0]
+    tt = np.asarray(t, dtype=np.float64)
+    return float(tt[1 + hit[0]]) if len(hit) else float(tt[-1] + 0.1)
 
 
 def _kingman(init, f1, t_correct, lam, col, take_log):

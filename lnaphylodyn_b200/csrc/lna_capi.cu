@@ -677,7 +677,7 @@ extern "C" int lna_traj_sim_noncentral(lna_problem *pb, int64_t B, const double 
 }
 
 static int volz_events_dev(lna_problem *pb, int64_t B, const double *traj, const double *betaN, double *ll,
-                           int32_t *st) {
+                           int32_t *st, int nan_guard) {
     const DevProb &P = pb->dp;
     const int warps = 4;
     size_t sh = sizeof(double) * 2 * warps * (size_t)P.n0;
@@ -689,26 +689,36 @@ static int volz_events_dev(lna_problem *pb, int64_t B, const double *traj, const
     }
     if (sh > 48 * 1024)
         cudaFuncSetAttribute(k_volz_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    k_volz_events<<<nblk(B, warps), warps * 32, sh, pb->stream>>>(P, B, traj, betaN, ll, st, stage);
+    k_volz_events<<<nblk(B, warps), warps * 32, sh, pb->stream>>>(P, B, traj, betaN, ll, st, stage, nan_guard);
     return launch_check(pb, "k_volz_events");
 }
 
-extern "C" int lna_volz_loglik_nh2(lna_problem *pb, int64_t B, const double *traj, const double *betaN,
-                                   double *loglik, int32_t *status) {
+static int volz_host(lna_problem *pb, int64_t B, const double *traj, const double *betaN, double *loglik,
+                     int32_t *status, int nan_guard, const char *what) {
     if (!pb) return fail("null problem");
     if (B <= 0) return 0;
     const DevProb &P = pb->dp;
-    if (!P.has_init) return fail("lna_volz_loglik_nh2: problem was created without a genealogy");
+    if (!P.has_init) return fail("%s: problem was created without a genealogy", what);
     const size_t nB = (size_t)B, per = (size_t)P.nrow * (P.p + 1);
     Stage s(pb);
     const double *dT = s.in(traj, nB * per), *db = s.in(betaN, nB * P.nrow);
     double *dll = s.tmp<double>(nB);
     int32_t *dst = s.tmp<int32_t>(nB);
-    if (!s.ok || !dT || !db) return fail("lna_volz_loglik_nh2: bad arguments / staging failed");
-    if (volz_events_dev(pb, B, dT, db, dll, dst)) return -1;
+    if (!s.ok || !dT || !db) return fail("%s: bad arguments / staging failed", what);
+    if (volz_events_dev(pb, B, dT, db, dll, dst, nan_guard)) return -1;
     s.back(loglik, dll, nB);
     s.back(status, dst, nB);
-    return s.finish("lna_volz_loglik_nh2");
+    return s.finish(what);
+}
+
+extern "C" int lna_volz_loglik_nh2(lna_problem *pb, int64_t B, const double *traj, const double *betaN,
+                                   double *loglik, int32_t *status) {
+    return volz_host(pb, B, traj, betaN, loglik, status, 1, "lna_volz_loglik_nh2");
+}
+
+extern "C" int lna_volz_loglik_nh3(lna_problem *pb, int64_t B, const double *traj, const double *betaN,
+                                   double *loglik, int32_t *status) {
+    return volz_host(pb, B, traj, betaN, loglik, status, 0, "lna_volz_loglik_nh3");
 }
 
 extern "C" int lna_coal_loglik(lna_problem *pb, int64_t B, const double *traj, const double *lambda, int col,

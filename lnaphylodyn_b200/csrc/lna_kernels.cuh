@@ -335,7 +335,7 @@ __global__ void k_transform_traj(int k, long long B, const double *Ode, const do
 // derives the per-cell factors of its trajectory (lane = cell), then strides over the events and
 // reduces with warp shuffles.
 __global__ void k_volz_events(DevProb P, long long B, const double *traj, const double *betaN, double *loglik,
-                              int *status, int stage_events) {
+                              int *status, int stage_events, int nan_guard) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *cellq = reinterpret_cast<double *>(smem);      // [warps][n0] beta*exp(-f)*exp(s)
@@ -401,8 +401,8 @@ __global__ void k_volz_events(DevProb P, long long B, const double *traj, const 
             r = kSentinel;
             st = ST_NEG_STATE;
         } else if (nan) {
-            r = kSentinel;
             st = ST_NAN;
+            if (nan_guard) r = kSentinel;  // volz_loglik_nh3 (:1058-1113) has no NaN guard: the sum is returned
         }
         loglik[b] = r;
         if (status) status[b] = st;

@@ -130,6 +130,12 @@ def ODE_rk45(initial, t, param, x_r, x_i, transP="changepoint", model="SIR", tra
     return out
 
 
+def ODE_rk45_stop(initial, t, param, x_r, x_i, transP="changepoint", model="SIR", transX="standard", tol=5):
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    initial, t, param = _d(initial), _d(t), _d(param)
+    return lib().orc_ode_rk45_stop(cfg.ref, _p(initial), _p(t), len(t), _p(param), C.c_double(tol))
+
+
 def SigmaF(Traj_par, param, x_r, x_i, transP="changepoint", model="SIR", transX="standard"):
     cfg = Cfg(x_r, x_i, len(param), model, transX)
     T, param = _f(Traj_par), _d(param)

@@ -171,6 +171,28 @@ def test_rcpp_mirrors_vs_oracle(api, changepoint):
     assert api.coal_loglik(g.init, logtraj, g.t_correct, 3.0) == pytest.approx(orc.coal_loglik(g.init, logtraj, g.t_correct, 3.0), rel=TOL)
 
 
+def test_minor_exports(api, changepoint):
+    g = changepoint
+    par = g.final["par"].ravel()
+    param, initial = par[2:], par[:2]
+    lat = g.final["LatentTraj"]
+    bn = g.final["betaN"].ravel()
+    assert api.volz_loglik_nh3(g.init, lat, bn, g.t_correct, [0, 1]) == pytest.approx(
+        orc.volz_loglik_nh3(g.init, lat, bn, g.t_correct, [0, 1]), rel=TOL)
+    bad = lat.copy()
+    bad[40, 2] = -1.0  # beyond the checked rows: log(negative) -> NaN; nh2 guards it, nh3 does not
+    assert api.volz_loglik_nh2(g.init, bad, bn, 100.0, [0, 1]) == orc.volz_loglik_nh2(g.init, bad, bn, 100.0, [0, 1]) == orc.SENTINEL
+    assert np.isnan(api.volz_loglik_nh3(g.init, bad, bn, 100.0, [0, 1])) and np.isnan(orc.volz_loglik_nh3(g.init, bad, bn, 100.0, [0, 1]))
+    assert api.log_like_traj_general_adjust(lat, lat, None, 50, 90) == 0.0
+    for tol in (5.0, 2000.0):
+        assert api.ODE_rk45_stop(initial, g.times, param, g.x_r, g.x_i, tol=tol) == orc.ODE_rk45_stop(initial, g.times, param, g.x_r, g.x_i, tol=tol)
+    nrm = np.random.default_rng(8).standard_normal(80)
+    s_d = api.Traj_sim_ezG_NC(initial, g.times, param, 50, g.x_r, g.x_i, g.t_correct, normals=nrm)
+    npl = orc.New_Param_List(param, initial, 50, g.times, g.x_r, g.x_i)
+    s_o = orc.Traj_sim_general_noncentral(npl["Ode"], npl["FT"], g.t_correct, nrm)
+    assert relerr(s_d["SimuTraj"][:, 1:], s_o["SimuTraj"][:, 1:]) < TOL
+
+
 def test_update_param_decisions(api, changepoint):
     g = changepoint
     B = 64
