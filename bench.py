@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--cpu-evals-per-core", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eslice", action="store_true")
+    ap.add_argument("--no-seir", action="store_true")
     ap.add_argument("--eslice-iters", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -306,6 +307,43 @@ def main():
         except Exception as e:  # noqa: BLE001
             eslice = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- configs[3]: SEIR (p = 3) parameter sweep, 16384 i.i.d. draws per sweep, FULL evaluations only ----
+    seir = None
+    if not args.no_seir:
+        try:
+            rng = np.random.default_rng(77 + rank)
+            Bs = 16384
+            prm = np.empty((Bs, 43))
+            prm[:, 0] = np.exp(0.8 + 0.15 * rng.standard_normal(Bs))
+            prm[:, 1] = np.exp(-0.7 + 0.1 * rng.standard_normal(Bs))
+            prm[:, 2] = np.exp(-1.6 + 0.1 * rng.standard_normal(Bs))
+            prm[:, 3:42] = np.exp(rng.standard_normal((Bs, 39)) / 30.0)
+            prm[:, 42] = np.exp(3 + 0.2 * rng.standard_normal(Bs))
+            pbs = api.Problem(g.times, g.x_r, [39, 3, 0, 2], g.gridsize, g.t_correct, g.init, model="SEIR", device=local_rank)
+            _lib.check(L.lna_problem_set_stream(pbs.h, C.c_void_p(stream.cuda_stream)), "set_stream")
+            d_prm = torch.from_numpy(prm).to(dev)
+            d_ini = torch.tensor([[1e6, 4.0, 4.0]], dtype=torch.float64, device=dev).repeat(Bs, 1).contiguous()
+            d_eps = (0.3 * torch.randn((Bs, 3 * 40), dtype=torch.float64, device=dev)).contiguous()
+            d_out = torch.empty(Bs, dtype=torch.float64, device=dev)
+            d_st = torch.empty(Bs, dtype=torch.int32, device=dev)
+            run = lambda: _lib.check(L.lna_full_loglik_dev(pbs.h, Bs, d_prm.data_ptr(), d_ini.data_ptr(), d_eps.data_ptr(),
+                                                           d_out.data_ptr(), d_st.data_ptr(), None, None, None, None, None), "seir")
+            for _ in range(3):
+                run()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(10):
+                run()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms_s = e0.elapsed_time(e1) / 10
+            Wseir = 277.0 * (len(g.times) - 1) + 45.0 * 40 + 10.0 * 36
+            seir = {"value": Bs / (ms_s * 1e-3), "unit": UNIT, "draws_per_sweep": Bs, "ms_per_sweep": ms_s,
+                    "flops_per_eval": Wseir, "achieved_tflops": Bs / (ms_s * 1e-3) * Wseir / 1e12,
+                    "sentinel_frac": float((d_out == -10000000.0).double().mean())}
+        except Exception as e:  # noqa: BLE001
+            seir = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     if rank == 0:
         W = algorithmic_flops(g)
         achieved = (value / world) * W / 1e12
@@ -330,6 +368,8 @@ def main():
         }
         if eslice is not None:
             line["eslice"] = eslice
+        if seir is not None:
+            line["seir_sweep"] = seir
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             rate1, dt1 = time_oracle(g, max(64, args.cpu_evals_per_core // 2), 1)

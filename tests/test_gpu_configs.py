@@ -69,10 +69,7 @@ def test_synthetic_5000_tips(api):
     """configs[4]: volz_thin_sir genealogy with 5000 tips on a deterministic SIR trajectory (N = 1e6,
     R0 = 2.2, gamma = 0.2, I0 = 1, [0,100]), 2000 fine steps, gridsize 50."""
     times = np.linspace(0, 100, 2001)
-    ode = orc.ODE_rk45([1e6, 1.0], times, [2.2, 0.2], [1e6], [0, 2, 0, 1])
-    betaN = orc.betaTs([2.2, 0.2], times, [1e6], [0, 2, 0, 1])
-    c = gen.volz_thin_sir(ode, 90.0, [0, 10, 20, 40, 80, 85], [1000, 1000, 1450, 1450, 90, 10], betaN,
-                          np.random.default_rng(20260))
+    c = np.load(os.path.join(GOLDEN, "synthetic_5000.npz"))  # tests/golden/make_synthetic.py (8 min of thinning)
     init = gen.coal_lik_init(c["samp_times"], c["n_sampled"], c["coal_times"], times[::50])
     assert len(c["coal_times"]) == 4999 and len(init["C"]) > 5000
     cht = times[::50][1:-1]
