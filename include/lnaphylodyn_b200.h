@@ -230,6 +230,33 @@ int lna_chains_init(lna_chains *ch, const double *par, const double *OriginTraj)
  * `_dev`: streams already in HBM.  Host variant copies them in first. */
 int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *opts, const double *normals, const double *uniforms);
 int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *opts, const double *normals, const double *uniforms);
+/* Settings of General_MCMC2's iteration body (R/LNA_chpt_slice.R:576-691; the constant_sim vignette):
+ * Update_Param_each entries (random walk on one parameter each, R/LNA_chpt_slice.R:266-365),
+ * update_hyper (R/general_change_point.R:281-313), ESlice_change_points, trajectory ESS. */
+typedef struct lna_mcmc2_opts {
+    int32_t n_mh;              /* number of Update_Param_each entries (<= 4)                        */
+    int32_t mh_index[4];       /* 0-based index into par: 1 = I0, 2 = R0, 3 = gamma                 */
+    int32_t mh_is_log[4];      /* isLoglist: the walk is on log(par)                                */
+    int32_t mh_prior_kind[4];  /* 0: dnorm(mean, sd) on the (log) value; 1: dunif(lo, hi)           */
+    double mh_prior[4][2];
+    double mh_prop[4];         /* half-width of the uniform random walk                             */
+    int32_t update_hyper;      /* updateVec[5] == 0.5 and i >= burn1                                */
+    double hyper_prop;         /* proposal$hyper_prop                                               */
+    double hyper_prior[2];     /* dgamma(shape, rate)                                               */
+    int32_t update_chpt;       /* updateVec[6]                                                      */
+    int32_t update_traj;       /* updateVec[7] and i >= burn1                                       */
+    int32_t spec_width;        /* 0 = auto                                                          */
+} lna_mcmc2_opts;
+
+/* uniforms per General_MCMC2 iteration: 4 MH slots x (walk, accept), hyper (walk, accept), 22 + 22 */
+#define LNA_ITER2_UNIF (2 * 4 + 2 + 2 * LNA_ESLICE_MAX_UNIF)
+
+/* One General_MCMC2 iteration.  normals: B x (nch + k*p); uniforms: B x LNA_ITER2_UNIF laid out as
+ * [2e, 2e+1] for MH entry e, [8, 9] hyper, [10..31] change-point ESS, [32..53] trajectory ESS. */
+int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *opts, const double *normals, const double *uniforms);
+int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *opts, const double *normals,
+                              const double *uniforms);
+
 /* Read the state back (any pointer may be NULL).  counters: B x 4 int32 = (n_full_evals,
  * n_cheap_evals, n_mh_accept, status OR). */
 int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,

@@ -29,6 +29,13 @@ class LnaMcmcOpts(C.Structure):
                 ("spec_width", C.c_int32)]
 
 
+class LnaMcmc2Opts(C.Structure):
+    _fields_ = [("n_mh", C.c_int32), ("mh_index", C.c_int32 * 4), ("mh_is_log", C.c_int32 * 4),
+                ("mh_prior_kind", C.c_int32 * 4), ("mh_prior", (C.c_double * 2) * 4), ("mh_prop", C.c_double * 4),
+                ("update_hyper", C.c_int32), ("hyper_prop", C.c_double), ("hyper_prior", C.c_double * 2),
+                ("update_chpt", C.c_int32), ("update_traj", C.c_int32), ("spec_width", C.c_int32)]
+
+
 # name -> (restype, argtypes); pointers are passed as void* so that host (numpy) and device (torch
 # data_ptr) addresses go through the same declarations.
 _I64 = C.c_int64
@@ -69,6 +76,8 @@ _SIGS = {
     "lna_chains_init": (C.c_int, [_vp, _vp, _vp]),
     "lna_chains_step": (C.c_int, [_vp, C.POINTER(LnaMcmcOpts), _vp, _vp]),
     "lna_chains_step_dev": (C.c_int, [_vp, C.POINTER(LnaMcmcOpts), _vp, _vp]),
+    "lna_chains_step_mcmc2": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), _vp, _vp]),
+    "lna_chains_step_mcmc2_dev": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), _vp, _vp]),
     "lna_chains_get": (C.c_int, [_vp] + [_vp] * 6),
     "lna_chains_summary_dev": (_vp, [_vp]),
     "lna_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),

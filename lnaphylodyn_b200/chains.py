@@ -200,3 +200,41 @@ def gather_summaries(local, group=None):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# General_MCMC2 (constant_sim vignette) on resident chains
+# ------------------------------------------------------------------------------------------------
+ITER2_UNIF = 2 * 4 + 2 + 2 * ESLICE_MAX_UNIF
+
+
+def make_mcmc2_opts(prior, proposal, entries=((1, 1, 1), (2, 0, 2), (3, 1, 3)), update_hyper=True, update_chpt=True,
+                    update_traj=True, spec_width=0):
+    """`entries`: (0-based par index, isLog, priorId) per Update_Param_each entry -- the vignette passes
+    parIdlist = (2, 3, 4), isLoglist = (1, 0, 1), priorIdlist = (1, 2, 3) (vignettes/constant_sim.Rmd:87-96),
+    and the proposal ids equal the prior ids (R/LNA_chpt_slice.R:611-612).  priorId 2 is dunif, the others dnorm
+    (R/LNA_chpt_slice.R:306-320); update_hyper uses dgamma(hyper_pr) and proposal$hyper_prop."""
+    from ._lib import LnaMcmc2Opts
+    pr = [np.asarray(v, dtype=np.float64).ravel() for v in prior]
+    po = [np.asarray(v, dtype=np.float64).ravel() for v in proposal]
+    o = LnaMcmc2Opts()
+    o.n_mh = len(entries)
+    for e, (idx, is_log, pid) in enumerate(entries):
+        o.mh_index[e], o.mh_is_log[e], o.mh_prior_kind[e] = int(idx), int(is_log), 1 if pid == 2 else 0
+        o.mh_prior[e][0], o.mh_prior[e][1] = float(pr[pid - 1][0]), float(pr[pid - 1][1])
+        o.mh_prop[e] = float(po[pid - 1][0])
+    o.update_hyper, o.update_chpt, o.update_traj = int(update_hyper), int(update_chpt), int(update_traj)
+    o.hyper_prop = float(po[4][0])
+    o.hyper_prior[0], o.hyper_prior[1] = float(pr[4][0]), float(pr[4][1])
+    o.spec_width = int(spec_width)
+    return o
+
+
+def _step_mcmc2(self, opts, normals, uniforms):
+    """One General_MCMC2 iteration. normals (B, nch + k*p), uniforms (B, 54): host arrays."""
+    n, u = _d(normals), _d(uniforms)
+    assert u.shape == (self.B, ITER2_UNIF) and n.shape[0] == self.B, (n.shape, u.shape)
+    check(_lib.lib().lna_chains_step_mcmc2(self.h, C.byref(opts), _ptr(n), _ptr(u)), "lna_chains_step_mcmc2")
+
+
+Chains.step_mcmc2 = _step_mcmc2

@@ -416,8 +416,9 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     ch->tmp_d = chains_alloc<double>(ch, nB);
     ch->n_norm = (npar - 1) + kp;
     ch->n_unif = LNA_ITER_UNIF;
+    const size_t stage_unif = std::max<size_t>(LNA_ITER_UNIF, LNA_ITER2_UNIF);
     ch->stage_n = chains_alloc<double>(ch, nB * ch->n_norm);
-    ch->stage_u = chains_alloc<double>(ch, nB * ch->n_unif);
+    ch->stage_u = chains_alloc<double>(ch, nB * stage_unif);
     if (!ch->par || !ch->par_alt || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
         !ch->logOrigin || !ch->summary || !ch->counters || !ch->tmp_i || !ch->tmp_d || !ch->stage_n || !ch->stage_u) {
         fail("lna_chains_create: device allocation failed");
@@ -465,21 +466,15 @@ extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *
     return s.finish("lna_chains_init");
 }
 
-static int chains_cand_args(lna_chains *ch, const lna_mcmc_opts *o, const double *normals, const double *uniforms,
-                            int unif_off, int W, CandArgs &a) {
+// candidate-evaluation arguments common to every stage of the resident chains
+static void chains_base_args(lna_chains *ch, View normals, View uniforms, CandArgs &a) {
     const long long B = ch->B;
-    (void)W;  // the scratch was sized for the widest stage by lna_chains_step_dev
     a = CandArgs{};
     a.par = soa_view(ch->par, B);
     a.origin = soa_view(ch->origin, B);
-    a.normals = View{normals, (long long)ch->n_norm, 1};
-    a.uniforms = View{uniforms + unif_off, (long long)ch->n_unif, 1};
+    a.normals = normals;
+    a.uniforms = uniforms;
     a.coal_log = ch->coalLog;
-    for (int i = 0; i < 8; ++i) a.pr[i] = o->prior8[i];
-    for (int i = 0; i < 7; ++i) a.ess[i] = o->ESS_vec[i];
-    a.gamma_prior[0] = o->gamma_prior[0];
-    a.gamma_prior[1] = o->gamma_prior[1];
-    a.gamma_prop = o->gamma_prop;
     a.cand = cand_out(ch->cb);
     a.win_slot = ch->cb.win_slot;
     a.cand_ll = ch->cb.cand_ll;
@@ -487,17 +482,25 @@ static int chains_cand_args(lna_chains *ch, const lna_mcmc_opts *o, const double
     a.n_evals = ch->cb.n_evals;
     a.status = ch->cb.status;
     a.accept = ch->cb.accept;
+}
+
+static int chains_ensure_scratch(lna_chains *ch, int W) {
+    lna_problem *pb = ch->pb;
+    const long long B = ch->B;
+    const int Wmax = std::max(W > 0 ? W : auto_width(pb, B), 24);  // two-phase: 8 + 16 slots per chain
+    if (ch->cb.NC < B * Wmax || ch->cb.B != B) {
+        if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * Wmax, ch->cb))
+            return fail("lna_chains_step: candidate scratch allocation failed");
+    }
     return 0;
 }
 
+// evaluate the proposals of one stage, copy the winners into the state, bump the counters
 template <int kProp>
-static int chains_stage(lna_chains *ch, const lna_mcmc_opts *o, const double *normals, const double *uniforms,
-                        int unif_off, int W) {
+static int chains_stage(lna_chains *ch, const CandArgs &a, int W) {
     lna_problem *pb = ch->pb;
     const DevProb &P = pb->dp;
     const long long B = ch->B;
-    CandArgs a;
-    if (chains_cand_args(ch, o, normals, uniforms, unif_off, W, a)) return -1;
     if (launch_cand<kProp>(pb, B, W, a, ch->cb)) return -1;
     if (launch_commit_fields(pb, B, ch->cb, soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B),
                              soa_out(ch->betaN, B), soa_out(ch->latent, B)))
@@ -506,59 +509,131 @@ static int chains_stage(lna_chains *ch, const lna_mcmc_opts *o, const double *no
     k_commit_par_wide<kProp><<<nblk(B * npar, 256), 256, 0, pb->stream>>>(P, B, a, soa_out(ch->par_alt, B), ch->coalLog);
     if (launch_check(pb, "k_commit_par_wide")) return -1;
     std::swap(ch->par, ch->par_alt);  // update_Par_ESlice_combine does not touch logOrigin (LNA_chpt_slice.R:456-472)
-    const bool mh = (kProp == PROP_GAMMA_RW || kProp == PROP_HYPER_NOOP || kProp == PROP_MH_PAIR);
+    const bool mh = !(kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
     k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->cb.n_evals, ch->cb.accept, ch->cb.status, ch->cb.win_slot,
                                                  ch->counters, 0, mh ? 1 : 0);
     return launch_check(pb, "k_bump");
 }
 
+// updateTraj_general_NC -> ESlice_general_NC, in place on the state
+static int chains_traj(lna_chains *ch, View normals, View uniforms) {
+    lna_problem *pb = ch->pb;
+    const long long B = ch->B;
+    TrajArgs a{};
+    a.f_cur = soa_view(ch->origin, B);
+    a.normals = normals;
+    a.uniforms = uniforms;
+    a.A = soa_view(ch->A, B);
+    a.L = soa_view(ch->L, B);
+    a.ode = soa_view(ch->ode, B);
+    a.betaN = soa_view(ch->betaN, B);
+    a.coal_log = ch->coalLog;
+    a.latent = soa_out(ch->latent, B);
+    a.origin_new = soa_out(ch->origin, B);
+    a.CoalLog = ch->tmp_d;
+    a.logOrigin = ch->logOrigin;
+    a.n_evals = ch->tmp_i;
+    a.status = ch->tmp_i + B;
+    if (launch_traj(pb, B, a)) return -1;
+    CK(cudaMemcpyAsync(ch->coalLog, ch->tmp_d, sizeof(double) * (size_t)B, cudaMemcpyDeviceToDevice, pb->stream));
+    k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->tmp_i, ch->tmp_i, ch->tmp_i + B, nullptr, ch->counters, 1, 0);
+    return launch_check(pb, "k_bump");
+}
+
+static int chains_finish(lna_chains *ch) {
+    lna_problem *pb = ch->pb;
+    k_summary<<<nblk(ch->B, 256), 256, 0, pb->stream>>>(ch->B, ch->coalLog, ch->logOrigin, ch->counters, ch->summary);
+    return launch_check(pb, "k_summary");
+}
+
+// General_MCMC_with_ESlice iteration body (R/LNA_chpt_slice.R:775-847)
 extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,
                                    const double *uniforms) {
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
     lna_problem *pb = ch->pb;
     cudaSetDevice(pb->device);
     const DevProb &P = pb->dp;
-    const long long B = ch->B;
     if (o->ESS_vec[6] != 0) return fail("lna_chains_step: ESS_vec[7] = 1 is not supported");
     const int W = o->spec_width;  // 0 = auto (two-phase when the machine-filling width is 16)
-    const int Wmax = std::max(W > 0 ? W : auto_width(pb, B), 24);  // two-phase: 8 + 16 slots per chain
-    if (ch->cb.NC < B * Wmax || ch->cb.B != B) {  // size the candidate scratch once for the widest stage
-        if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * Wmax, ch->cb))
-            return fail("lna_chains_step: candidate scratch allocation failed");
-    }
+    if (chains_ensure_scratch(ch, W)) return -1;
+    const long long sn = (long long)ch->n_norm, su = (long long)ch->n_unif;
+    const int npar = 2 + P.npt;
+    CandArgs a;
     // 1. Update_Param_each_Norm: gamma random walk (entry c) and the no-op hyper entry (d)  [A.17]
+    chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
+    a.gamma_prior[0] = o->gamma_prior[0];
+    a.gamma_prior[1] = o->gamma_prior[1];
+    a.gamma_prop = o->gamma_prop;
     if (o->hyper_noop_mh) {  // both MH entries speculatively in one latency period
-        if (chains_stage<PROP_MH_PAIR>(ch, o, normals, uniforms, 0, 4)) return -1;
-    } else if (chains_stage<PROP_GAMMA_RW>(ch, o, normals, uniforms, 0, 1)) {
+        if (chains_stage<PROP_MH_PAIR>(ch, a, 4)) return -1;
+    } else if (chains_stage<PROP_GAMMA_RW>(ch, a, 1)) {
         return -1;
     }
     // 2. update_Par_ESlice_combine -> ESlice_par_General
-    if (chains_stage<PROP_ESS_PAR>(ch, o, normals, uniforms, 3, W)) return -1;
-    // 3. updateTraj_general_NC -> ESlice_general_NC (in place on the state)
-    if (o->update_traj) {
-        TrajArgs a{};
-        const int npar = 2 + P.npt;
-        a.f_cur = soa_view(ch->origin, B);
-        a.normals = View{normals + (npar - 1), (long long)ch->n_norm, 1};
-        a.uniforms = View{uniforms + 3 + LNA_ESLICE_MAX_UNIF, (long long)ch->n_unif, 1};
-        a.A = soa_view(ch->A, B);
-        a.L = soa_view(ch->L, B);
-        a.ode = soa_view(ch->ode, B);
-        a.betaN = soa_view(ch->betaN, B);
-        a.coal_log = ch->coalLog;
-        a.latent = soa_out(ch->latent, B);
-        a.origin_new = soa_out(ch->origin, B);
-        a.CoalLog = ch->tmp_d;
-        a.logOrigin = ch->logOrigin;
-        a.n_evals = ch->tmp_i;
-        a.status = ch->tmp_i + B;
-        if (launch_traj(pb, B, a)) return -1;
-        CK(cudaMemcpyAsync(ch->coalLog, ch->tmp_d, sizeof(double) * (size_t)B, cudaMemcpyDeviceToDevice, pb->stream));
-        k_bump<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->tmp_i, ch->tmp_i, ch->tmp_i + B, nullptr, ch->counters, 1, 0);
-        if (launch_check(pb, "k_bump")) return -1;
+    chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 3, su, 1}, a);
+    for (int i = 0; i < 8; ++i) a.pr[i] = o->prior8[i];
+    for (int i = 0; i < 7; ++i) a.ess[i] = o->ESS_vec[i];
+    if (chains_stage<PROP_ESS_PAR>(ch, a, W)) return -1;
+    // 3. updateTraj_general_NC -> ESlice_general_NC
+    if (o->update_traj &&
+        chains_traj(ch, View{normals + (npar - 1), sn, 1}, View{uniforms + 3 + LNA_ESLICE_MAX_UNIF, su, 1}))
+        return -1;
+    return chains_finish(ch);
+}
+
+// General_MCMC2 iteration body (R/LNA_chpt_slice.R:576-691, stages i < burn1 and burn1 <= i < warmup2)
+extern "C" int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *o, const double *normals,
+                                         const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
+    lna_problem *pb = ch->pb;
+    cudaSetDevice(pb->device);
+    const DevProb &P = pb->dp;
+    if (o->n_mh < 0 || o->n_mh > 4) return fail("lna_chains_step_mcmc2: n_mh must be 0..4");
+    const int W = o->spec_width;
+    if (chains_ensure_scratch(ch, W)) return -1;
+    const long long sn = (long long)(P.nch + P.k * P.p), su = (long long)LNA_ITER2_UNIF;
+    CandArgs a;
+    // Update_Param_each: one Metropolis entry per listed parameter, sequentially
+    for (int e = 0; e < o->n_mh; ++e) {
+        if (o->mh_index[e] < 1 || o->mh_index[e] > 3)
+            return fail("lna_chains_step_mcmc2: mh_index must be 1 (I0), 2 (R0) or 3 (gamma)");
+        chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 2 * e, su, 1}, a);
+        a.mh_index = o->mh_index[e];
+        a.mh_is_log = o->mh_is_log[e];
+        a.mh_prior_kind = o->mh_prior_kind[e];
+        a.mh_pr[0] = o->mh_prior[e][0];
+        a.mh_pr[1] = o->mh_prior[e][1];
+        a.mh_prop = o->mh_prop[e];
+        if (chains_stage<PROP_MH_SCALAR>(ch, a, 1)) return -1;
     }
-    k_summary<<<nblk(B, 256), 256, 0, pb->stream>>>(B, ch->coalLog, ch->logOrigin, ch->counters, ch->summary);
-    return launch_check(pb, "k_summary");
+    if (o->update_hyper) {  // update_hyper (general_change_point.R:281-313)
+        chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 8, su, 1}, a);
+        a.mh_pr[0] = o->hyper_prior[0];
+        a.mh_pr[1] = o->hyper_prior[1];
+        a.mh_prop = o->hyper_prop;
+        if (chains_stage<PROP_MH_HYPER>(ch, a, 1)) return -1;
+    }
+    if (o->update_chpt) {  // update_ChangePoint_ESlice -> ESlice_change_points
+        chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 10, su, 1}, a);
+        if (chains_stage<PROP_ESS_CHPT>(ch, a, W)) return -1;
+    }
+    if (o->update_traj &&
+        chains_traj(ch, View{normals + P.nch, sn, 1}, View{uniforms + 10 + LNA_ESLICE_MAX_UNIF, su, 1}))
+        return -1;
+    return chains_finish(ch);
+}
+
+extern "C" int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *o, const double *normals,
+                                     const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
+    lna_problem *pb = ch->pb;
+    cudaSetDevice(pb->device);
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)ch->B, nn = (size_t)(P.nch + P.k * P.p);
+    if (nn > ch->n_norm || (size_t)LNA_ITER2_UNIF > ch->n_unif + 8) return fail("lna_chains_step_mcmc2: staging too small");
+    CK(cudaMemcpyAsync(ch->stage_n, normals, sizeof(double) * nB * nn, cudaMemcpyHostToDevice, pb->stream));
+    CK(cudaMemcpyAsync(ch->stage_u, uniforms, sizeof(double) * nB * LNA_ITER2_UNIF, cudaMemcpyHostToDevice, pb->stream));
+    return lna_chains_step_mcmc2_dev(ch, o, ch->stage_n, ch->stage_u);
 }
 
 extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,

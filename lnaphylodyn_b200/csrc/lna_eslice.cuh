@@ -18,7 +18,11 @@
 
 namespace lna {
 
-enum : int { PROP_PLAIN = 0, PROP_GAMMA_RW = 1, PROP_HYPER_NOOP = 2, PROP_ESS_PAR = 3, PROP_ESS_CHPT = 4, PROP_MH_PAIR = 5 };
+enum : int {
+    PROP_PLAIN = 0, PROP_GAMMA_RW = 1, PROP_HYPER_NOOP = 2, PROP_ESS_PAR = 3, PROP_ESS_CHPT = 4, PROP_MH_PAIR = 5,
+    PROP_MH_SCALAR = 6,  // one entry of Update_Param_each (R/LNA_chpt_slice.R:266-365)
+    PROP_MH_HYPER = 7    // update_hyper (R/general_change_point.R:281-313)
+};
 
 constexpr int kMaxUnif = 22;
 constexpr double kLnSqrt2Pi = 0.918938533204672741780329736406;  // R's M_LN_SQRT_2PI
@@ -27,6 +31,16 @@ constexpr double kLnSqrt2Pi = 0.918938533204672741780329736406;  // R's M_LN_SQR
 __device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {
     const double z = (x - mu) / sigma;
     return -(kLnSqrt2Pi + 0.5 * z * z + log(sigma));
+}
+
+// R::dunif(x, a, b, log=TRUE)  (nmath/dunif.c)
+__device__ __forceinline__ double dunif_log(double x, double a, double b) {
+    return (a <= x && x <= b) ? -log(b - a) : -INFINITY;
+}
+// dgamma(x, shape, rate, log=TRUE) in closed form (R evaluates it through dpois_raw; R is not available
+// here, so this path is pinned CPU-restatement <-> GPU only)
+__device__ __forceinline__ double dgamma_log(double x, double shape, double rate) {
+    return shape * log(rate) - lgamma(shape) + (shape - 1.0) * log(x) - rate * x;
 }
 
 // Contraction-proof rotation a*cos + b*sin: evaluated identically wherever it is inlined, so the
@@ -65,9 +79,10 @@ struct ChProp {
     }
     __device__ __forceinline__ double eval(const Raw &r) const {
         const double cj = r.c;
-        if (kProp == PROP_HYPER_NOOP) {
-            // exp(log(ch) * hyper / hyper), R/LNA_chpt_slice.R:238-241 (ulp-level perturbation, A.17)
-            return exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_old));
+        if (kProp == PROP_HYPER_NOOP || kProp == PROP_MH_HYPER) {
+            // exp(log(ch) * hyper / hyper'), R/LNA_chpt_slice.R:238-241 with hyper' = hyper (ulp-level
+            // perturbation, A.17) and update_hyper (general_change_point.R:292-293) with hyper' = hyper e^u
+            return exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_new));
         } else if (kProp == PROP_MH_PAIR) {
             // same instruction stream for all lanes of the pair kernel; the flag selects per lane
             const double pert = exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_old));
@@ -125,6 +140,10 @@ struct CandArgs {
     double pr[8];    // priorList (4 x (mean, sd))
     int ess[7];
     double gamma_prior[2], gamma_prop;
+    // PROP_MH_SCALAR: random walk on par[mh_index] (log scale if mh_is_log), prior dnorm (0) / dunif (1)
+    // PROP_MH_HYPER : hyper' = hyper * exp(u), prior dgamma(shape = mh_pr[0], rate = mh_pr[1])
+    int mh_index, mh_is_log, mh_prior_kind;
+    double mh_pr[2], mh_prop;
     FullOut cand;    // candidate scratch: slot-major (sb = 1, sj = NC)
     int *win_slot;   // [B] winning scratch slot, -1 = keep current state
     double *cand_ll; // [B] log-likelihood of the winner (or of the rejected MH proposal)
@@ -276,11 +295,31 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
             x.gam = exp(rnew);
             prop = rnew;
         }
+        if (kProp == PROP_MH_SCALAR) {
+            const int j = a.mh_index;
+            const double cur = a.par.at(c, j);
+            const double raw = a.mh_is_log ? log(cur) : cur, po = a.mh_prop;
+            const double rnew = raw + (-po + (po - (-po)) * unif(iu++));
+            offset = a.mh_prior_kind == 0
+                         ? dnorm_log(rnew, a.mh_pr[0], a.mh_pr[1]) - dnorm_log(raw, a.mh_pr[0], a.mh_pr[1])
+                         : dunif_log(rnew, a.mh_pr[0], a.mh_pr[1]) - dunif_log(raw, a.mh_pr[0], a.mh_pr[1]);
+            const double val = a.mh_is_log ? exp(rnew) : rnew;
+            if (j == 1) x.I0 = val;
+            if (j == 2) x.R0 = val;
+            if (j == 3) x.gam = val;
+            prop = rnew;
+        }
+        if (kProp == PROP_MH_HYPER) {
+            const double hp = a.mh_prop, uu = -hp + (hp - (-hp)) * unif(iu++);
+            x.hyper_new = x.hyper_old * exp(uu);
+            offset = dgamma_log(x.hyper_new, a.mh_pr[0], a.mh_pr[1]) - dgamma_log(x.hyper_old, a.mh_pr[0], a.mh_pr[1]) + uu;
+            prop = x.hyper_new;
+        }
         ChProp<kProp> chs{a.par, a.normals, c, 4, x};
         double ll;
         int st = 0;
         sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
-        const double u = unif(kProp == PROP_GAMMA_RW ? 1 : 0);
+        const double u = unif(iu);
         const double acc_a = ll - a.coal_log[c] + offset;
         // a Cholesky failure is an exception in the reference: tryCatch keeps the old state
         const bool acc = !(st & ST_CHOL_FAIL) && (log(u) < acc_a);
@@ -632,6 +671,17 @@ __global__ void k_commit_par_wide(DevProb P, long long B, CandArgs a, OutView pa
         }
     } else if (kProp == PROP_GAMMA_RW) {
         if (j == 3) v = exp(a.theta[c]);
+    } else if (kProp == PROP_MH_SCALAR) {
+        if (j == a.mh_index) v = a.mh_is_log ? exp(a.theta[c]) : a.theta[c];
+    } else if (kProp == PROP_MH_HYPER) {
+        if (j == npar - 1) v = a.theta[c];
+        if (is_ch) {
+            PropScalars x{};
+            x.hyper_old = a.par.at(c, npar - 1);
+            x.hyper_new = a.theta[c];
+            ChProp<PROP_MH_HYPER> chs{a.par, a.normals, c, 4, x};
+            v = chs.ch(j - 4);
+        }
     } else if (kProp == PROP_HYPER_NOOP) {
         if (is_ch) {
             PropScalars x{};

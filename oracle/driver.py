@@ -96,3 +96,78 @@ def opts_from_golden(g, update_traj=True):
         ess[4] = 0
     return {"priorList": [prior[0][:2], prior[1][:2], prior[2][:2], prior[4][:2]], "gamma_prior": tuple(prior[2][:2]),
             "gamma_prop": float(proposal[2][0]), "ESS_vec": ess, "update_traj": update_traj, "hyper_noop_mh": True}
+
+
+# ------------------------------------------------------------------------------------------------
+# General_MCMC2 iteration body (R/LNA_chpt_slice.R:576-691), stages i < burn1 and burn1 <= i < warmup2
+# ------------------------------------------------------------------------------------------------
+import math
+
+
+def dunif_log(x, a, b):
+    return -math.log(b - a) if a <= x <= b else -math.inf
+
+
+def dgamma_log(x, shape, rate):
+    """closed form of dgamma(x, shape, rate, log = TRUE) (R goes through dpois_raw; unpinned)"""
+    return shape * math.log(rate) - math.lgamma(shape) + (shape - 1.0) * math.log(x) - rate * x
+
+
+def mcmc2_iteration(st, g, opts, normals, uniforms):
+    """uniforms: [2e, 2e+1] MH entry e (walk, accept); [8, 9] hyper; [10:32] change-point ESS; [32:54]
+    trajectory ESS.  normals: [0:nch] change-point ESS, [nch:] trajectory ESS."""
+    npar = len(st["par"])
+    nch = npar - 5
+    # Update_Param_each (R/LNA_chpt_slice.R:266-365)
+    for e, (idx, is_log, kind, pr, po) in enumerate(opts["entries"]):
+        par_new = st["par"].copy()
+        raw = math.log(par_new[idx]) if is_log else par_new[idx]
+        raw_new = raw + (-po + (po - (-po)) * uniforms[2 * e])
+        if kind == 0:
+            newdiff = dnorm_log(raw_new, pr[0], pr[1]) - dnorm_log(raw, pr[0], pr[1])
+        else:
+            newdiff = dunif_log(raw_new, pr[0], pr[1]) - dunif_log(raw, pr[0], pr[1])
+        par_new[idx] = math.exp(raw_new) if is_log else raw_new
+        _mh(st, g, par_new, newdiff, uniforms[2 * e + 1])
+    # update_hyper (R/general_change_point.R:281-313)
+    if opts.get("update_hyper", True):
+        par_new = st["par"].copy()
+        hs = par_new[npar - 1]
+        hp = opts["hyper_prop"]
+        u = -hp + (hp - (-hp)) * uniforms[8]
+        hs_new = hs * math.exp(u)
+        par_new[npar - 1] = hs_new
+        par_new[4:4 + nch] = np.exp(np.log(par_new[4:4 + nch]) * hs / hs_new)
+        off = dgamma_log(hs_new, *opts["hyper_prior"]) - dgamma_log(hs, *opts["hyper_prior"]) + u
+        _mh(st, g, par_new, off, uniforms[9])
+    # update_ChangePoint_ESlice (R/LNA_chpt_slice.R:419-440)
+    if opts.get("update_chpt", True):
+        r = orc.ESlice_change_points(st["par"][2:], st["par"][:2], g.times, st["OriginTraj"], g.x_r, g.x_i, g.init,
+                                     g.gridsize, st["coalLog"], g.t_correct, normals=normals[:nch],
+                                     uniforms=uniforms[10:32])
+        st["n_full"] += r["n_evals"]
+        if not (r["status"] & 1):
+            st["par"] = np.concatenate([st["par"][:2], r["param"]])
+            st["LatentTraj"], st["betaN"], st["FT"] = r["LatentTraj"], r["betaN"], r["FT"]
+            st["coalLog"], st["Ode"], st["chprobs"] = r["CoalLog"], r["OdeTraj"], r["LogChProb"]
+    if opts.get("update_traj", True):
+        betaN = orc.betaTs(st["par"][2:npar - 1], st["LatentTraj"][:, 0], g.x_r, g.x_i)
+        t = orc.ESlice_general_NC(st["OriginTraj"], st["Ode"], st["FT"], st["par"][:2], g.init, betaN, g.t_correct,
+                                  1.0, st["coalLog"], g.gridsize, True, "SIR", normals=normals[nch:],
+                                  uniforms=uniforms[32:54])
+        new_cl = orc.volz_loglik_nh2(g.init, t["LatentTraj"], betaN, g.t_correct, g.x_i[2:4])
+        st["coalLog"], st["LatentTraj"], st["OriginTraj"], st["logOrigin"] = (new_cl, t["LatentTraj"], t["OriginTraj"],
+                                                                              t["logOrigin"])
+        st["n_cheap"] += t["n_evals"]
+    return st
+
+
+def mcmc2_opts_from_golden(g, burn=False):
+    """Options of the constant_sim vignette call (vignettes/constant_sim.Rmd:87-96)."""
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    proposal = [g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+    ent = []
+    for idx, is_log, pid in ((1, 1, 1), (2, 0, 2), (3, 1, 3)):
+        ent.append((idx, is_log, 1 if pid == 2 else 0, tuple(prior[pid - 1][:2]), float(proposal[pid - 1][0])))
+    return {"entries": ent, "update_hyper": not burn, "hyper_prop": float(proposal[4][0]),
+            "hyper_prior": tuple(prior[4][:2]), "update_chpt": True, "update_traj": not burn}

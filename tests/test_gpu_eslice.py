@@ -206,3 +206,35 @@ def test_sharded_chains_equal_single_device(api, changepoint):
         t = ch.get()
         for k in ("par", "OriginTraj", "LatentTraj", "coalLog", "logOrigin", "n_full_evals", "n_cheap_evals"):
             assert np.array_equal(t[k], s[k][b:e]), k
+
+
+def test_chains_mcmc2_step_for_step(api, constant):
+    """General_MCMC2 (constant_sim vignette): Update_Param_each x3, update_hyper, change-point ESS,
+    trajectory ESS -- B chains x 5 iterations from the vignette's initial state against the oracle."""
+    from lnaphylodyn_b200 import chains as chm
+    g = constant
+    B, iters, seed = 10, 5, 41
+    par0 = np.concatenate([[g.x_r[0], float(g.setting("control.alpha")[0]) * g.x_r[0]], g.setting("control.R0"),
+                           g.setting("control.gamma"), g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    ref = [driver.init_state(g, par0, g.setting("control.traj")) for _ in range(B)]
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    proposal = [g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+    accepted = 0
+    for it in range(iters):
+        burn = it < 1
+        rng = np.random.default_rng([seed, it])
+        nrm = rng.standard_normal((B, 39 + 80))
+        unf = rng.random((B, chm.ITER2_UNIF))
+        ch.step_mcmc2(chm.make_mcmc2_opts(prior, proposal, update_hyper=not burn, update_traj=not burn), nrm, unf)
+        s = ch.get()
+        for c in range(B):
+            ref[c] = driver.mcmc2_iteration(ref[c], g, driver.mcmc2_opts_from_golden(g, burn=burn), nrm[c], unf[c])
+            assert relerr(s["par"][c], ref[c]["par"]) < TOL, (it, c)
+            assert s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL), (it, c)
+            assert np.max(np.abs(s["OriginTraj"][c] - ref[c]["OriginTraj"])) < 1e-11
+            assert s["n_full_evals"][c] == ref[c]["n_full"] and s["n_cheap_evals"][c] == ref[c]["n_cheap"]
+            assert s["n_mh_accept"][c] == ref[c]["n_mh_accept"], (it, c)
+        accepted = int(s["n_mh_accept"].sum())
+    assert 0 < accepted < B * iters * 4
