@@ -199,6 +199,24 @@ int lna_eslice_change_points(lna_problem *pb, int64_t B, const double *param, co
                              double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj,
                              double *CoalLog, double *LogChProb, int32_t *n_evals, int32_t *status);
 
+/* ---- centred parametrisation (legacy entry points) ------------------------------ */
+/* log_like_traj_general2 (:675-722): Gaussian transition log-density of SdeTraj around OdeTraj given
+ * KF_param's (A, Sigma); rows with time <= t_correct. */
+int lna_log_like_traj_general2(lna_problem *pb, int64_t B, const double *SdeTraj, const double *OdeTraj,
+                               const double *Acube, const double *Scube, double *loglik);
+/* Traj_sim_general3 (:771-817): centred LNA simulation with supplied normals (B x k*p, step-major);
+ * noise = mvrnormArma(Sigma) (basic_util.cpp:44-58).  Traj_sim_ezG2 (:907-975) = lna_ode_rk45 +
+ * lna_kf_param(chol = 0) + lna_ode_coarse_slicer + this. */
+int lna_traj_sim_general3(lna_problem *pb, int64_t B, const double *OdeTraj, const double *Acube,
+                          const double *Scube, const double *normals, double *LNA_traj, double *loglike,
+                          int32_t *status);
+/* ESlice_general2 (:1783-1857), volz likelihood: centred elliptical slice on the trajectory itself.
+ * f_cur, newTraj: B x (nrow x (p+1)); normals: B x k*p (drawn by the inner Traj_sim_general3);
+ * uniforms: B x LNA_ESLICE_MAX_UNIF. */
+int lna_eslice_general2(lna_problem *pb, int64_t B, const double *f_cur, const double *OdeTraj,
+                        const double *Acube, const double *Scube, const double *betaN, const double *normals,
+                        const double *uniforms, double *newTraj, int32_t *n_evals, int32_t *status);
+
 /* ---- resident chain batches: the MCMC driver loop on the device -------------------------------- */
 /* State of B chains kept in HBM between iterations (par, OriginTraj, FT, coarse ODE, betaN,
  * LatentTraj, coalLog, logOrigin): the batched equivalent of the R list MCMC_obj

@@ -587,3 +587,79 @@ def ESlice_change_points(param, initial, t, OriginTraj, x_r, x_i, init, gridsize
             "OdeTraj": pb._unmats(ode, (nrow, p + 1), single), "param": pick(pn),
             "LatentTraj": pb._unmats(lat, (nrow, p + 1), single), "CoalLog": pick(cl), "LogChProb": pick(lcp),
             "n_evals": pick(ne), "status": pick(st)}
+
+
+# ------------------------------------------------------------------------------------------------
+# centred parametrisation (legacy entry points of the same engine)
+# ------------------------------------------------------------------------------------------------
+
+def _centred_problem(OdeTraj, t_correct, init=None, model=None):
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    times = O[:, 0] if single else O[0, :, 0]
+    p = O.shape[-1] - 1
+    model = model or ("SIR" if p == 2 else "SEIR")
+    pb = problem_for(times, [1.0], [0, 2 if p == 2 else 3, 0, 1 if p == 2 else 2], 1, t_correct, init, model)
+    return pb, O, single, p
+
+
+def log_like_traj_general2(SdeTraj, OdeTraj, Filter, gridsize, t_correct):
+    """LNA_functional.cpp:675-722"""
+    pb, O, single, p = _centred_problem(OdeTraj, t_correct)
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, p + 1))
+    Xf, _ = pb._mats(SdeTraj, (nrow, p + 1))
+    Af, _ = pb._mats(Filter["A"], (p, p, k))
+    Sf, _ = pb._mats(Filter["Sigma"], (p, p, k))
+    ll = np.empty(Of.shape[0])
+    check(_lib.lib().lna_log_like_traj_general2(pb.h, Of.shape[0], _ptr(Xf), _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(ll)),
+          "lna_log_like_traj_general2")
+    return float(ll[0]) if single else ll
+
+
+def Traj_sim_general3(OdeTraj, Filter, t_correct, *, normals):
+    """LNA_functional.cpp:771-817 with supplied normals (k*p, step-major)."""
+    pb, O, single, p = _centred_problem(OdeTraj, t_correct)
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, p + 1))
+    B = Of.shape[0]
+    Af, _ = pb._mats(Filter["A"], (p, p, k))
+    Sf, _ = pb._mats(Filter["Sigma"], (p, p, k))
+    z = _d(normals).reshape(B, k * p)
+    traj, ll, st = np.empty_like(Of), np.empty(B), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_traj_sim_general3(pb.h, B, _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(z), _ptr(traj), _ptr(ll),
+                                           _ptr(st)), "lna_traj_sim_general3")
+    if single and st[0] & ST_CHOL_FAIL:
+        raise ValueError("chol(): decomposition failed")
+    return {"SimuTraj": pb._unmats(traj, (nrow, p + 1), single), "loglike": float(ll[0]) if single else ll}
+
+
+def Traj_sim_ezG2(initial, times, param, gridsize, x_r, x_i, t_correct, transP="changepoint", model="SIR",
+                  transX="standard", *, normals):
+    """LNA_functional.cpp:907-975 = ODE_rk45 + KF_param + coarse rows + the loop of Traj_sim_general3."""
+    ode = ODE_rk45(initial, times, param, x_r, x_i, transP, model, transX)
+    kf = KF_param(ode, param, gridsize, x_r, x_i, transP, model, transX)
+    return Traj_sim_general3(Ode_Coarse_Slicer(ode, gridsize), kf, t_correct, normals=normals)
+
+
+def ESlice_general2(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, reps=1, gridsize=100, volz=False,
+                    model="SIR", transX="standard", *, normals, uniforms):
+    """LNA_functional.cpp:1783-1857 (volz=True): centred elliptical slice on the trajectory; returns newTraj."""
+    if not volz:
+        raise LnaError("ESlice_general2(volz=False) needs LogTraj(), which the reference never defines in C++")
+    pb, O, single, p = _centred_problem(OdeTraj, t_correct, init, model)
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, p + 1))
+    B = Of.shape[0]
+    Ff, _ = pb._mats(f_cur, (nrow, p + 1))
+    Af, _ = pb._mats(FTs["A"], (p, p, k))
+    Sf, _ = pb._mats(FTs["Sigma"], (p, p, k))
+    bn = _d(betaN).reshape(B, nrow)
+    z = _d(normals).reshape(B, k * p)
+    unf = _unif22(uniforms, B)
+    out = np.empty_like(Of)
+    ne, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_eslice_general2(pb.h, B, _ptr(Ff), _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(bn), _ptr(z), _ptr(unf),
+                                         _ptr(out), _ptr(ne), _ptr(st)), "lna_eslice_general2")
+    pick = (lambda a: a[0]) if single else (lambda a: a)
+    return {"newTraj": pb._unmats(out, (nrow, p + 1), single), "n_evals": pick(ne), "status": pick(st)}

@@ -339,6 +339,98 @@ extern "C" int lna_eslice_general_nc(lna_problem *pb, int64_t B, const double *f
 }
 
 // ------------------------------------------------------------------------------------------------
+// centred parametrisation
+// ------------------------------------------------------------------------------------------------
+static int centred_launch(lna_problem *pb, int64_t B, int mode, const double *x, const double *O, const double *A,
+                          const double *S, double *traj, double *ll, int32_t *st) {
+    const DevProb &P = pb->dp;
+    if (P.p == 2)
+        k_centred<2><<<nblk(B, 64), 64, 0, pb->stream>>>(P.k, B, mode, P.t_correct, x, O, A, S, traj, ll, st);
+    else
+        k_centred<3><<<nblk(B, 64), 64, 0, pb->stream>>>(P.k, B, mode, P.t_correct, x, O, A, S, traj, ll, st);
+    return launch_check(pb, "k_centred");
+}
+
+extern "C" int lna_log_like_traj_general2(lna_problem *pb, int64_t B, const double *SdeTraj, const double *OdeTraj,
+                                          const double *Acube, const double *Scube, double *loglik) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, per = (size_t)P.nrow * (P.p + 1), cube = (size_t)P.p * P.p * P.k;
+    Stage s(pb);
+    const double *dX = s.in(SdeTraj, nB * per), *dO = s.in(OdeTraj, nB * per), *dA = s.in(Acube, nB * cube),
+                 *dS = s.in(Scube, nB * cube);
+    double *dll = s.tmp<double>(nB);
+    if (!s.ok || !dX || !dO || !dA || !dS) return fail("lna_log_like_traj_general2: bad arguments / staging failed");
+    if (centred_launch(pb, B, 0, dX, dO, dA, dS, nullptr, dll, nullptr)) return -1;
+    s.back(loglik, dll, nB);
+    return s.finish("lna_log_like_traj_general2");
+}
+
+extern "C" int lna_traj_sim_general3(lna_problem *pb, int64_t B, const double *OdeTraj, const double *Acube,
+                                     const double *Scube, const double *normals, double *LNA_traj, double *loglike,
+                                     int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, per = (size_t)P.nrow * (P.p + 1), cube = (size_t)P.p * P.p * P.k;
+    Stage s(pb);
+    const double *dO = s.in(OdeTraj, nB * per), *dA = s.in(Acube, nB * cube), *dS = s.in(Scube, nB * cube),
+                 *dz = s.in(normals, nB * P.k * P.p);
+    double *dT = s.tmp<double>(nB * per), *dll = s.tmp<double>(nB);
+    int32_t *dst = s.tmp<int32_t>(nB);
+    if (!s.ok || !dO || !dA || !dS || !dz) return fail("lna_traj_sim_general3: bad arguments / staging failed");
+    if (centred_launch(pb, B, 1, dz, dO, dA, dS, dT, dll, dst)) return -1;
+    s.back(LNA_traj, dT, nB * per);
+    s.back(loglike, dll, nB);
+    s.back(status, dst, nB);
+    return s.finish("lna_traj_sim_general3");
+}
+
+extern "C" int lna_eslice_general2(lna_problem *pb, int64_t B, const double *f_cur, const double *OdeTraj,
+                                   const double *Acube, const double *Scube, const double *betaN,
+                                   const double *normals, const double *uniforms, double *newTraj, int32_t *n_evals,
+                                   int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (check_sir_sampler(pb, "lna_eslice_general2")) return -1;
+    if (!f_cur || !OdeTraj || !Acube || !Scube || !betaN || !normals || !uniforms)
+        return fail("lna_eslice_general2: null input");
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, per = (size_t)P.nrow * (P.p + 1), cube = (size_t)P.p * P.p * P.k, nrow = P.nrow;
+    Stage s(pb);
+    const double *dF = s.in(f_cur, nB * per), *dO = s.in(OdeTraj, nB * per), *dA = s.in(Acube, nB * cube),
+                 *dS = s.in(Scube, nB * cube), *db = s.in(betaN, nB * nrow), *dz = s.in(normals, nB * P.k * P.p),
+                 *du = s.in(uniforms, nB * kMaxUnif);
+    double *dV = s.tmp<double>(nB * per), *dN = s.tmp<double>(nB * per), *dll = s.tmp<double>(nB);
+    int32_t *dne = s.tmp<int32_t>(nB), *dst = s.tmp<int32_t>(nB), *dst2 = s.tmp<int32_t>(nB);
+    if (!s.ok) return fail("lna_eslice_general2: device staging failed");
+    // v = Traj_sim_general3(OdeTraj, FTs, t_correct) consumes the k*p normals first (:1801)
+    if (centred_launch(pb, B, 1, dz, dO, dA, dS, dV, dll, dst2)) return -1;
+    TrajArgs a{};
+    a.mode = 1;
+    a.f_cur = item_view(dF, per);
+    a.normals = item_view(dV, per);
+    a.uniforms = item_view(du, kMaxUnif);
+    a.ode = item_view(dO, per);
+    a.betaN = item_view(db, nrow);
+    a.A = item_view(dA, cube);
+    a.L = item_view(dS, cube);
+    a.coal_log = dll;  // unused in mode 1
+    a.latent = item_out(dN, per);
+    a.origin_new = OutView{nullptr, 0, 0};
+    a.CoalLog = nullptr;
+    a.logOrigin = nullptr;
+    a.n_evals = dne;
+    a.status = dst;
+    if (launch_traj(pb, B, a)) return -1;
+    s.back(newTraj, dN, nB * per);
+    s.back(n_evals, dne, nB);
+    s.back(status, dst, nB);
+    return s.finish("lna_eslice_general2");
+}
+
+// ------------------------------------------------------------------------------------------------
 // resident chain batches
 // ------------------------------------------------------------------------------------------------
 struct lna_chains {

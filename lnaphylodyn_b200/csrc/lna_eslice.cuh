@@ -496,6 +496,10 @@ struct TrajArgs {
     OutView latent, origin_new;         // outputs (may alias the chain state: per-lane read-before-write)
     double *CoalLog, *logOrigin;
     int *n_evals, *status;
+    // mode 0: ESlice_general_NC (non-centred increments f, v; recurrences through FT)
+    // mode 1: ESlice_general2 (:1783-1857): f_cur and `normals` are (k+1) x (p+1) TRAJECTORIES (current and the
+    //         centred proposal drawn by Traj_sim_general3); the deviations from the ODE are rotated directly
+    int mode;
 };
 
 constexpr int kTrajWarps = 4;
@@ -519,7 +523,15 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
         oI[r] = a.ode.at(c, 2 * nrow + r);
         bet[r] = a.betaN.at(c, r);
     }
-    for (int i = lane; i < k; i += 32) {
+    if (a.mode == 1) {
+        for (int r = lane; r < nrow; r += 32) {
+            XfS[r] = a.f_cur.at(c, nrow + r) - oS[r];
+            XfI[r] = a.f_cur.at(c, 2 * nrow + r) - oI[r];
+            XvS[r] = a.normals.at(c, nrow + r) - oS[r];
+            XvI[r] = a.normals.at(c, 2 * nrow + r) - oI[r];
+        }
+    }
+    for (int i = lane; i < k && a.mode == 0; i += 32) {
         const double l00 = a.L.at(c, 4 * i), l10 = a.L.at(c, 4 * i + 1), l11 = a.L.at(c, 4 * i + 3);
         const double f0 = a.f_cur.at(c, i), f1 = a.f_cur.at(c, k + i);
         const double v0 = a.normals.at(c, i), v1 = a.normals.at(c, k + i);
@@ -531,7 +543,7 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
         for (int e = 0; e < 4; ++e) Am[4 * i + e] = a.A.at(c, 4 * i + e);
     }
     __syncwarp();
-    if (lane < 2) {  // lane 0: recurrence driven by f, lane 1: by v
+    if (lane < 2 && a.mode == 0) {  // lane 0: recurrence driven by f, lane 1: by v
         const double *cc = lane == 0 ? cf : cv;
         double *XS = lane == 0 ? XfS : XvS, *XI = lane == 0 ? XfI : XvI;
         double x0 = 0.0, x1 = 0.0;
@@ -587,9 +599,9 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
     bool negall;
     double logy;
     const double lu = log(unif(0));
-    if (a.coal_log[c] != -99999999.0) {
+    if (a.mode == 0 && a.coal_log[c] != -99999999.0) {
         logy = a.coal_log[c] + lu;
-    } else {  // recompute the current likelihood like the reference (:1717-1719)
+    } else {  // recompute the current likelihood like the reference (:1717-1719; always in ESlice_general2)
         logy = cheap(1.0, 0.0, negall, st) + lu;
         evals++;
     }
@@ -608,9 +620,11 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
             reverted = true;
             ct = 1.0;
             sn = 0.0;
-            ll = cheap(ct, sn, negall, st);
+            if (a.mode == 0) {  // ESlice_general2 just returns f_cur, without another evaluation (:1835-1839)
+                ll = cheap(ct, sn, negall, st);
+                evals++;
+            }
             st |= ST_CAP_HIT;
-            evals++;
             break;
         }
         ts.advance(i + 1, unif);
@@ -620,12 +634,13 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
     }
     // outputs: latent rows, rotated increments, logOrigin without the LAST row (:1768)
     for (int r = lane; r < nrow; r += 32) {
-        a.latent.put(c, r, a.ode.at(c, r));
-        a.latent.put(c, nrow + r, oS[r] + fma(ct, XfS[r], sn * XvS[r]));
-        a.latent.put(c, 2 * nrow + r, oI[r] + fma(ct, XfI[r], sn * XvI[r]));
+        const bool keep = a.mode == 1 && reverted;  // newTraj = f_cur, bit for bit
+        a.latent.put(c, r, a.mode == 1 ? a.f_cur.at(c, r) : a.ode.at(c, r));
+        a.latent.put(c, nrow + r, keep ? a.f_cur.at(c, nrow + r) : oS[r] + fma(ct, XfS[r], sn * XvS[r]));
+        a.latent.put(c, 2 * nrow + r, keep ? a.f_cur.at(c, 2 * nrow + r) : oI[r] + fma(ct, XfI[r], sn * XvI[r]));
     }
     double lo = 0.0;
-    for (int e = lane; e < 2 * k; e += 32) {
+    for (int e = lane; e < 2 * k && a.mode == 0; e += 32) {
         const double f = a.f_cur.at(c, e);
         const double v = reverted ? f : rot(f, ct, a.normals.at(c, e), sn);
         a.origin_new.put(c, e, v);
@@ -634,8 +649,8 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(full, lo, o);
     if (lane == 0) {
-        a.CoalLog[c] = ll;
-        a.logOrigin[c] = lo;
+        if (a.CoalLog) a.CoalLog[c] = ll;
+        if (a.logOrigin) a.logOrigin[c] = lo;
         a.n_evals[c] = evals;
         a.status[c] = st;
     }

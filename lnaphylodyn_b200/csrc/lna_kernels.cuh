@@ -330,6 +330,125 @@ __global__ void k_transform_traj(int k, long long B, const double *Ode, const do
     }
 }
 
+// Centred parametrisation, one thread per item:
+//   mode 0: log_like_traj_general2 (LNA_functional.cpp:675-722): Gaussian transition density of a trajectory
+//   mode 1: Traj_sim_general3 (:771-817): X1 = A (X0 - eta0) + eta1 + mvrnormArma(Sigma) with supplied normals
+template <int p>
+__device__ inline double det_small(const double *M) {
+    if (p == 2) return M[0] * M[3] - M[2] * M[1];
+    return M[0] * (M[4] * M[8] - M[7] * M[5]) - M[3] * (M[1] * M[8] - M[7] * M[2]) + M[6] * (M[1] * M[5] - M[4] * M[2]);
+}
+template <int p>
+__device__ inline void solve_small(const double *S, const double *v, double *w) {
+    const double d = det_small<p>(S);
+    if (p == 2) {
+        w[0] = (S[3] * v[0] - S[2] * v[1]) / d;
+        w[1] = (-S[1] * v[0] + S[0] * v[1]) / d;
+    } else {
+        double C[9];
+        C[0] = S[4] * S[8] - S[7] * S[5]; C[3] = -(S[3] * S[8] - S[6] * S[5]); C[6] = S[3] * S[7] - S[6] * S[4];
+        C[1] = -(S[1] * S[8] - S[7] * S[2]); C[4] = S[0] * S[8] - S[6] * S[2]; C[7] = -(S[0] * S[7] - S[6] * S[1]);
+        C[2] = S[1] * S[5] - S[4] * S[2]; C[5] = -(S[0] * S[5] - S[3] * S[2]); C[8] = S[0] * S[4] - S[3] * S[1];
+        for (int r = 0; r < 3; ++r) w[r] = (C[r] * v[0] + C[r + 3] * v[1] + C[r + 6] * v[2]) / d;
+    }
+}
+
+template <int p>
+__global__ void k_centred(int k, long long B, int mode, double t_correct, const double *Sde_or_normals,
+                          const double *Ode, const double *Acube, const double *Scube, double *traj_out,
+                          double *loglik, int *status) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nrow = k + 1;
+    const double *O = Ode + b * (long long)nrow * (p + 1);
+    const double *A = Acube + b * (long long)k * p * p, *S = Scube + b * (long long)k * p * p;
+    double ll = 0.0;
+    int st = 0;
+    if (mode == 0) {
+        const double *X = Sde_or_normals + b * (long long)nrow * (p + 1);
+        double d0[p], d1[p], v[p], w[p];
+        for (int j = 0; j < p; ++j) d1[j] = X[(long long)(j + 1) * nrow] - O[(long long)(j + 1) * nrow];
+        for (int i = 0; i < k; ++i) {
+            const double *Ai = A + i * p * p, *Si = S + i * p * p;
+            for (int j = 0; j < p; ++j) {
+                d0[j] = d1[j];
+                d1[j] = X[(i + 1) + (long long)(j + 1) * nrow] - O[(i + 1) + (long long)(j + 1) * nrow];
+            }
+            if (X[i + 1] <= t_correct) {
+                for (int r = 0; r < p; ++r) {
+                    double ax = 0.0;
+                    for (int q = 0; q < p; ++q) ax += Ai[r + q * p] * d0[q];
+                    v[r] = d1[r] - ax;
+                }
+                solve_small<p>(Si, v, w);
+                double q = 0.0;
+                for (int r = 0; r < p; ++r) q += v[r] * w[r];
+                ll += -log(det_small<p>(Si)) / 2.0 - 0.5 * q;
+            }
+        }
+    } else {
+        const double *z = Sde_or_normals + b * (long long)k * p;
+        double *T = traj_out + b * (long long)nrow * (p + 1);
+        double X0[p], X1[p], e0[p], e1[p], noise[p], w[p];
+        for (int j = 0; j < p; ++j) {
+            X1[j] = O[(long long)(j + 1) * nrow];
+            e1[j] = X1[j];
+            T[(long long)(j + 1) * nrow] = X1[j];
+        }
+        T[0] = 0.0;  // quirk of the reference (:782)
+        for (int i = 0; i < k; ++i) {
+            const double *Ai = A + i * p * p, *Si = S + i * p * p;
+            for (int j = 0; j < p; ++j) {
+                X0[j] = X1[j];
+                e0[j] = e1[j];
+                e1[j] = O[(i + 1) + (long long)(j + 1) * nrow];
+            }
+            // mvrnormArma (basic_util.cpp:44-58): chols(Sigma) z for p = 2, chol(Sigma + 1e-13 I)^T z otherwise
+            double L[p * p];
+            if (p == 2) {
+                const double r00 = sqrt(Si[0]), r01 = Si[1] / r00;
+                L[0] = r00; L[1] = r01; L[2] = 0.0; L[3] = sqrt(Si[3] - r01 * r01);
+            } else {
+                double U[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int j = 0; j < 3; ++j) {
+                    double ajj = Si[j + j * 3] + 0.0000000000001;
+                    for (int q = 0; q < j; ++q) ajj -= U[q + j * 3] * U[q + j * 3];
+                    if (!(ajj > 0.0)) st |= ST_CHOL_FAIL;
+                    ajj = sqrt(ajj);
+                    U[j + j * 3] = ajj;
+                    for (int c = j + 1; c < 3; ++c) {
+                        double s2 = Si[j + c * 3];
+                        for (int q = 0; q < j; ++q) s2 -= U[q + j * 3] * U[q + c * 3];
+                        U[j + c * 3] = s2 / ajj;
+                    }
+                }
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) L[r + c * 3] = U[c + r * 3];
+            }
+            for (int r = 0; r < p; ++r) {
+                double s2 = 0.0;
+                for (int q = 0; q < p; ++q) s2 += L[r + q * p] * z[i * p + q];
+                noise[r] = s2;
+            }
+            for (int r = 0; r < p; ++r) {
+                double ax = 0.0;
+                for (int q = 0; q < p; ++q) ax += Ai[r + q * p] * (X0[q] - e0[q]);
+                X1[r] = ax + e1[r] + noise[r];
+            }
+            if (O[i + 1] <= t_correct) {
+                solve_small<p>(Si, noise, w);
+                double q = 0.0;
+                for (int r = 0; r < p; ++r) q += noise[r] * w[r];
+                ll += -log(det_small<p>(Si)) / 2.0 + (-0.5) * q;
+            }
+            T[i + 1] = O[i + 1];
+            for (int j = 0; j < p; ++j) T[(i + 1) + (long long)(j + 1) * nrow] = X1[j];
+        }
+    }
+    if (loglik) loglik[b] = ll;
+    if (status) status[b] = st;
+}
+
 // volz_loglik_nh2 (LNA_functional.cpp:1119-1176), literal PER-EVENT form: one warp per trajectory.
 // The block stages the genealogy's event arrays (C*D and y) in shared memory once; each warp first
 // derives the per-cell factors of its trajectory (lane = cell), then strides over the events and

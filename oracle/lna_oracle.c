@@ -874,6 +874,151 @@ void orc_chols(const double *S, double *L) {
     L[3] = r11;
 }
 
+/* ---------------------------------------------------------------- centred parametrisation */
+
+/* mvrnormArma: basic_util.cpp:44-58.  n == 2: chols(sigma) * z, else chol(sigma + 1e-13 I)^T * z. */
+static int mvrnorm_small(const double *Sig, int p, const double *z, double *out) {
+    double L[MAXP * MAXP];
+    if (p == 2) {
+        orc_chols(Sig, L);
+    } else if (orc_chol_lower(Sig, p, 0.0000000000001, L)) {
+        return 1;
+    }
+    for (int r = 0; r < p; r++) {
+        double s = 0.0;
+        for (int q = 0; q < p; q++) s += L[r + q * p] * z[q];
+        out[r] = s;
+    }
+    return 0;
+}
+
+static void solve_small(const double *S, int p, const double *v, double *w) {
+    double d = det_small(S, p);
+    if (p == 2) {
+        w[0] = (S[3] * v[0] - S[2] * v[1]) / d;
+        w[1] = (-S[1] * v[0] + S[0] * v[1]) / d;
+    } else {
+        double C[9];
+        C[0] = S[4] * S[8] - S[7] * S[5]; C[3] = -(S[3] * S[8] - S[6] * S[5]); C[6] = S[3] * S[7] - S[6] * S[4];
+        C[1] = -(S[1] * S[8] - S[7] * S[2]); C[4] = S[0] * S[8] - S[6] * S[2]; C[7] = -(S[0] * S[7] - S[6] * S[1]);
+        C[2] = S[1] * S[5] - S[4] * S[2]; C[5] = -(S[0] * S[5] - S[3] * S[2]); C[8] = S[0] * S[4] - S[3] * S[1];
+        for (int r = 0; r < 3; r++) w[r] = (C[r] * v[0] + C[r + 3] * v[1] + C[r + 6] * v[2]) / d;
+    }
+}
+
+/* Traj_sim_general3: LNA_functional.cpp:771-817 (centred LNA simulation; normals step-major k*p).
+ * Quirk kept: LNA_traj(0,0) = 0 whatever OdeTraj(0,0) is. */
+int orc_traj_sim_general3(const double *OdeTraj, int nrow, int p, const double *Acube, const double *Scube,
+                          double t_correct, const double *normals, double *LNA_traj, double *loglike_out) {
+    int k = nrow - 1;
+    double X0[MAXP], X1[MAXP], eta0[MAXP], eta1[MAXP], noise[MAXP], w[MAXP], loglike = 0.0;
+    for (int j = 0; j < p; j++) {
+        X1[j] = OdeTraj[(size_t)(j + 1) * nrow];
+        eta1[j] = X1[j];
+        LNA_traj[(size_t)(j + 1) * nrow] = X1[j];
+    }
+    LNA_traj[0] = 0;
+    for (int i = 0; i < k; i++) {
+        const double *A = Acube + (size_t)i * p * p, *Sig = Scube + (size_t)i * p * p;
+        for (int j = 0; j < p; j++) {
+            X0[j] = X1[j];
+            eta0[j] = eta1[j];
+            eta1[j] = OdeTraj[(i + 1) + (size_t)(j + 1) * nrow];
+        }
+        if (mvrnorm_small(Sig, p, normals + (size_t)i * p, noise)) return ORC_CHOL_FAIL;
+        for (int r = 0; r < p; r++) {
+            double ax = 0.0;
+            for (int q = 0; q < p; q++) ax += A[r + q * p] * (X0[q] - eta0[q]);
+            X1[r] = ax + eta1[r] + noise[r];
+        }
+        if (OdeTraj[i + 1] <= t_correct) {
+            solve_small(Sig, p, noise, w);
+            double q = 0.0;
+            for (int r = 0; r < p; r++) q += noise[r] * w[r];
+            loglike += -log(det_small(Sig, p)) / 2.0 + (-0.5) * q;
+        }
+        LNA_traj[i + 1] = OdeTraj[i + 1];
+        for (int j = 0; j < p; j++) LNA_traj[(i + 1) + (size_t)(j + 1) * nrow] = X1[j];
+    }
+    *loglike_out = loglike;
+    return ORC_OK;
+}
+
+/* Traj_sim_ezG2: LNA_functional.cpp:907-975 = ODE_rk45 + coarse rows + KF_param + the loop of Traj_sim_general3. */
+int orc_traj_sim_ezG2(const orc_cfg *c, const double *initial, const double *t, int nt, const double *param,
+                      int gridsize, double t_correct, const double *normals, double *LNA_traj, double *loglike) {
+    int p = c->p, k = nt / gridsize, nrow = k + 1;
+    double *thin = (double *)malloc(sizeof(double) * (size_t)nt * (p + 1));
+    double *coarse = (double *)malloc(sizeof(double) * (size_t)nrow * (p + 1));
+    double *A = (double *)malloc(sizeof(double) * (size_t)p * p * k * 2), *S = A + (size_t)p * p * k;
+    orc_ode_rk45(c, initial, t, nt, param, thin);
+    for (int i = 0; i < nrow; i++)
+        for (int j = 0; j <= p; j++) coarse[i + (size_t)j * nrow] = thin[(size_t)i * gridsize + (size_t)j * nt];
+    orc_kf_param(c, thin, nt, param, gridsize, A, S);
+    int st = orc_traj_sim_general3(coarse, nrow, p, A, S, t_correct, normals, LNA_traj, loglike);
+    free(thin);
+    free(coarse);
+    free(A);
+    return st;
+}
+
+/* ESlice_general2: LNA_functional.cpp:1783-1857 (centred elliptical slice, volz likelihood).
+ * normals: k*p (consumed by Traj_sim_general3); uniforms: u, theta_1, one per shrink. */
+int orc_eslice_general2(const orc_init *init, const double *f_cur, int nrow, int p, const double *OdeTraj,
+                        const double *Acube, const double *Scube, const double *betaN, double t_correct,
+                        const int *Index, int transX, const double *normals, const double *uniforms, int *n_unif,
+                        int *n_evals, double *newTraj) {
+    int iu = 0, evals = 0, n = nrow * p;
+    double *v = (double *)malloc(sizeof(double) * (size_t)nrow * (p + 1));
+    double ll_sim;
+    int st = orc_traj_sim_general3(OdeTraj, nrow, p, Acube, Scube, t_correct, normals, v, &ll_sim);
+    if (st) {
+        free(v);
+        return st;
+    }
+    double u = uniforms[iu++];
+    double logy = orc_volz_loglik_nh2(init, f_cur, nrow, p, betaN, t_correct, Index, transX) + log(u);
+    evals++;
+    double theta = runif_ab(0, 2 * ORC_PI, uniforms[iu++]);
+    double theta_min = theta - 2 * ORC_PI, theta_max = theta;
+    for (int r = 0; r < nrow; r++) newTraj[r] = f_cur[r];
+    double ct = cos(theta), sn = sin(theta);
+    for (int e = 0; e < n; e++) {
+        double fc = f_cur[nrow + e] - OdeTraj[nrow + e], vt = v[nrow + e] - OdeTraj[nrow + e];
+        newTraj[nrow + e] = (fc * ct + vt * sn) + OdeTraj[nrow + e];
+    }
+    double loglike = orc_volz_loglik_nh2(init, newTraj, nrow, p, betaN, t_correct, Index, transX);
+    evals++;
+    int i = 0, status = 0;
+    for (;;) {
+        double mn = newTraj[nrow];
+        for (int e = nrow; e < nrow * (p + 1); e++)
+            if (newTraj[e] < mn) mn = newTraj[e];
+        if (!(mn < 0 || loglike <= logy)) break;
+        i += 1;
+        if (i > 20) {
+            memcpy(newTraj, f_cur, sizeof(double) * (size_t)nrow * (p + 1));
+            status |= ORC_CAP_HIT;
+            break;
+        }
+        if (theta < 0) theta_min = theta;
+        else theta_max = theta;
+        theta = runif_ab(theta_min, theta_max, uniforms[iu++]);
+        ct = cos(theta);
+        sn = sin(theta);
+        for (int e = 0; e < n; e++) {
+            double fc = f_cur[nrow + e] - OdeTraj[nrow + e], vt = v[nrow + e] - OdeTraj[nrow + e];
+            newTraj[nrow + e] = (fc * ct + vt * sn) + OdeTraj[nrow + e];
+        }
+        loglike = orc_volz_loglik_nh2(init, newTraj, nrow, p, betaN, t_correct, Index, transX);
+        evals++;
+    }
+    *n_unif = iu;
+    *n_evals = evals;
+    free(v);
+    return status;
+}
+
 /* ---------------------------------------------------------------- batch driver (bench baseline) */
 
 /* B independent FULL evaluations, item-major inputs like the product's C ABI; one core.

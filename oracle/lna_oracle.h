@@ -137,6 +137,16 @@ int orc_eslice_change_points(const orc_cfg *c, const orc_init *init, const doubl
                              double *param_new, double *Acube, double *Lcube, double *Ode_coarse,
                              double *betaN, double *LatentTraj, double *CoalLog, double *LogChProb);
 
+/* centred parametrisation */
+int orc_traj_sim_general3(const double *OdeTraj, int nrow, int p, const double *Acube, const double *Scube,
+                          double t_correct, const double *normals, double *LNA_traj, double *loglike);
+int orc_traj_sim_ezG2(const orc_cfg *c, const double *initial, const double *t, int nt, const double *param,
+                      int gridsize, double t_correct, const double *normals, double *LNA_traj, double *loglike);
+int orc_eslice_general2(const orc_init *init, const double *f_cur, int nrow, int p, const double *OdeTraj,
+                        const double *Acube, const double *Scube, const double *betaN, double t_correct,
+                        const int *Index, int transX, const double *normals, const double *uniforms, int *n_unif,
+                        int *n_evals, double *newTraj);
+
 /* B independent FULL evaluations on one core (item-major inputs like the product's C ABI). */
 int orc_full_loglik_batch(const orc_cfg *c, const orc_init *init, long B, const double *param,
                           const double *initial, const double *t, int nt, int gridsize,

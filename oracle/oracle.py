@@ -398,3 +398,50 @@ def inv2(a):
     out = np.empty((2, 2), order="F")
     lib().orc_inv2(_p(a), _p(out))
     return out
+
+
+def Traj_sim_general3(OdeTraj, Filter, t_correct, *, normals):
+    """LNA_functional.cpp:771-817 with supplied normals (k*p, step-major)."""
+    O = _f(OdeTraj)
+    A, S = _f(Filter["A"]), _f(Filter["Sigma"])
+    nrm = _d(normals)
+    out = np.empty_like(O, order="F")
+    ll = C.c_double()
+    st = lib().orc_traj_sim_general3(_p(O), O.shape[0], O.shape[1] - 1, _p(A), _p(S), C.c_double(t_correct), _p(nrm),
+                                     _p(out), C.byref(ll))
+    if st:
+        raise ValueError("chol(): decomposition failed")
+    return {"SimuTraj": out, "loglike": ll.value}
+
+
+def Traj_sim_ezG2(initial, times, param, gridsize, x_r, x_i, t_correct, transP="changepoint", model="SIR",
+                  transX="standard", *, normals):
+    """LNA_functional.cpp:907-975"""
+    cfg = Cfg(x_r, x_i, len(param), model, transX)
+    initial, times, param, nrm = _d(initial), _d(times), _d(param), _d(normals)
+    nrow = len(times) // gridsize + 1
+    out = np.empty((nrow, cfg.p + 1), order="F")
+    ll = C.c_double()
+    st = lib().orc_traj_sim_ezG2(cfg.ref, _p(initial), _p(times), len(times), _p(param), int(gridsize),
+                                 C.c_double(t_correct), _p(nrm), _p(out), C.byref(ll))
+    if st:
+        raise ValueError("chol(): decomposition failed")
+    return {"SimuTraj": out, "loglike": ll.value}
+
+
+def ESlice_general2(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, reps=1, gridsize=100, volz=False,
+                    model="SIR", transX="standard", *, normals, uniforms):
+    """LNA_functional.cpp:1783-1857 (volz=True)"""
+    if not volz:
+        raise NotImplementedError("ESlice_general2(volz=False) needs LogTraj()")
+    F, O = _f(f_cur), _f(OdeTraj)
+    A, S = _f(FTs["A"]), _f(FTs["Sigma"])
+    ini = init if isinstance(init, Init) else Init(init)
+    b, nrm, unf = _d(betaN), _d(normals), _d(uniforms)
+    Index = (C.c_int * 2)(0, 1 if model == "SIR" else 2)
+    out = np.empty_like(F, order="F")
+    nu, ne = C.c_int(), C.c_int()
+    st = lib().orc_eslice_general2(ini.ref, _p(F), F.shape[0], F.shape[1] - 1, _p(O), _p(A), _p(S), _p(b),
+                                   C.c_double(t_correct), Index, TRANSX[transX], _p(nrm), _p(unf), C.byref(nu),
+                                   C.byref(ne), _p(out))
+    return {"newTraj": out, "status": st, "n_uniforms": nu.value, "n_evals": ne.value}

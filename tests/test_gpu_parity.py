@@ -244,3 +244,45 @@ def test_seir_full_loglik_vs_oracle(api, changepoint):
             n_ok += 1
             assert res["coalLog"][b] == pytest.approx(o["coalLog"], rel=TOL)
     assert n_ok > B // 2
+
+
+def test_centred_entry_points(api, changepoint):
+    """KF_param / log_like_traj_general2 / Traj_sim_general3 / Traj_sim_ezG2 / ESlice_general2 and the
+    reference's own 'Test SIR model' identity (testStructureCoal.R:41-51) through the GPU path."""
+    g = changepoint
+    par = g.final["par"].ravel()
+    param, initial = par[2:], par[:2]
+    ode = orc.ODE_rk45(initial, g.times, param, g.x_r, g.x_i)
+    kf = orc.KF_param(ode, param, 50, g.x_r, g.x_i)
+    kfc = orc.KF_param_chol(ode, param, 50, g.x_r, g.x_i)
+    co = orc.Ode_Coarse_Slicer(ode, 50)
+    rng = np.random.default_rng(12)
+    z = rng.standard_normal(80)
+    s_o = orc.Traj_sim_general3(co, kf, g.t_correct, normals=z)
+    s_d = api.Traj_sim_general3(co, kf, g.t_correct, normals=z)
+    assert relerr(s_d["SimuTraj"][:, 1:], s_o["SimuTraj"][:, 1:]) < TOL and s_d["SimuTraj"][0, 0] == 0.0
+    assert s_d["loglike"] == pytest.approx(s_o["loglike"], rel=1e-9)
+    e_d = api.Traj_sim_ezG2(initial, g.times, param, 50, g.x_r, g.x_i, g.t_correct, normals=z)
+    e_o = orc.Traj_sim_ezG2(initial, g.times, param, 50, g.x_r, g.x_i, g.t_correct, normals=z)
+    assert relerr(e_d["SimuTraj"][:, 1:], e_o["SimuTraj"][:, 1:]) < 1e-9 and e_d["loglike"] == pytest.approx(e_o["loglike"], rel=1e-8)
+    l_o = orc.log_like_traj_general2(s_o["SimuTraj"], co, kf, 50, g.t_correct)
+    l_d = api.log_like_traj_general2(s_o["SimuTraj"], co, kf, 50, g.t_correct)
+    assert l_d == pytest.approx(l_o, rel=1e-9)
+    # testthat identity (c): non-centred simulation density == centred density (up to the 1e-8 jitter)
+    nc = api.Traj_sim_general_noncentral(co, kfc, 150.0, normals=z)
+    assert nc["logMultiNorm"] + nc["logOrigin"] == pytest.approx(
+        api.log_like_traj_general2(nc["SimuTraj"], co, kf, 50, 150.0), rel=1.5e-8)
+    # centred elliptical slice, step for step
+    bn = orc.betaTs(param, co[:, 0], g.x_r, g.x_i)
+    B = 24
+    nrm, unf = rng.standard_normal((B, 80)), rng.random((B, 22))
+    unf[:3, 0] = 1.0 - 1e-12
+    rep = lambda a: np.tile(a, (B,) + (1,) * np.ndim(a))
+    d = api.ESlice_general2(rep(g.final["LatentTraj"]), rep(co), {"A": rep(kf["A"]), "Sigma": rep(kf["Sigma"])}, initial,
+                            g.init, rep(bn), g.t_correct, volz=True, normals=nrm, uniforms=unf)
+    for b in range(B):
+        o = orc.ESlice_general2(g.final["LatentTraj"], co, kf, initial, g.init, bn, g.t_correct, volz=True,
+                                normals=nrm[b], uniforms=unf[b])
+        assert d["n_evals"][b] == o["n_evals"] and (d["status"][b] & 8) == (o["status"] & 8), b
+        assert relerr(d["newTraj"][b][:, 1:], o["newTraj"][:, 1:]) < 1e-9
+    assert d["n_evals"].max() > 3
