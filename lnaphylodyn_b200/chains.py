@@ -104,74 +104,6 @@ def vignette_opts(g, update_traj=True, spec_width=0):
     return make_opts(prior, proposal, ess, update_traj=update_traj, hyper_noop_mh=True, spec_width=spec_width)
 
 
-def bench_eslice(pb, g, B, iters, rank, world, dev):
-    """ESlice chain-iterations/s for bench.py: B chains per GPU from the vignette's initial state,
-    streams resident in HBM (device-timed) and through host buffers (e2e)."""
-    import time
-    import torch
-    import torch.distributed as dist
-
-    par0 = np.concatenate([[g.x_r[0], float(g.setting("control.alpha")[0]) * g.x_r[0]],
-                           g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"),
-                           g.setting("control.hyper")])
-    par = np.tile(par0, (B, 1))
-    eps0 = g.setting("control.traj")
-    ch = Chains(pb, par, eps0)
-    opts_burn = vignette_opts(g, update_traj=False)
-    opts = vignette_opts(g, update_traj=True)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    nsets = iters + 8
-    nrm = torch.randn((nsets, B, ch.n_norm), dtype=torch.float64, device=dev, generator=gen)
-    unf = torch.rand((nsets, B, ITER_UNIF), dtype=torch.float64, device=dev, generator=gen).clamp_(1e-300, 1 - 1e-16)
-    stream = torch.cuda.current_stream(dev)
-    # burn-in like the vignette's first stage, then warm-up of the full iteration
-    for i in range(4):
-        ch.step_dev(opts_burn, nrm[i].data_ptr(), unf[i].data_ptr())
-    for i in range(4, 8):
-        ch.step_dev(opts, nrm[i].data_ptr(), unf[i].data_ptr())
-    torch.cuda.synchronize(dev)
-    before = ch.get()
-    if world > 1:
-        dist.barrier()
-    l0 = pb.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(iters):
-        ch.step_dev(opts, nrm[8 + i].data_ptr(), unf[8 + i].data_ptr())
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    launches = pb.launch_count() - l0
-    after = ch.get()
-    # e2e: host streams (pinned) -> H2D -> iteration -> D2H of the summary block
-    nrm_h = torch.randn((B, ch.n_norm), dtype=torch.float64).pin_memory()
-    unf_h = torch.rand((B, ITER_UNIF), dtype=torch.float64).clamp_(1e-300, 1 - 1e-16).pin_memory()
-    summ_h = torch.empty((B, 4), dtype=torch.float64).pin_memory()
-    L = _lib.lib()
-    cl_h = torch.empty(B, dtype=torch.float64).pin_memory()
-    lo_h = torch.empty(B, dtype=torch.float64).pin_memory()
-    t0 = time.perf_counter()
-    for i in range(iters):
-        check(L.lna_chains_step(ch.h, C.byref(opts), nrm_h.data_ptr(), unf_h.data_ptr()), "lna_chains_step")
-        check(L.lna_chains_get(ch.h, None, None, None, cl_h.data_ptr(), lo_h.data_ptr(), None), "lna_chains_get")
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float((after["n_full_evals"] - before["n_full_evals"]).sum()),
-                        float((after["n_cheap_evals"] - before["n_cheap_evals"]).sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, e2e_ms = float(t[0]), float(t[1])
-    tot = world * B * iters
-    return {"value": tot / (ms * 1e-3), "unit": "chain-iterations/s", "chains_per_gpu": B, "iters": iters,
-            "ms_per_iter": ms / iters, "e2e_value": tot / (e2e_ms * 1e-3),
-            "h2d_bytes_per_iter": int(nrm_h.numel() * 8 + unf_h.numel() * 8), "d2h_bytes_per_iter": int(B * 16),
-            "mean_full_evals_per_iter": float(cnt[0]) / tot, "mean_cheap_evals_per_iter": float(cnt[1]) / tot,
-            "consumed_full_evals_per_s": float(cnt[0]) / (ms * 1e-3), "gpu_launches": int(launches),
-            "spec_width": "auto", "finite_coalLog": bool(np.all(np.isfinite(after["coalLog"])))}
-
-
 # ------------------------------------------------------------------------------------------------
 # multi-GPU plumbing (SURVEY section 8e): contiguous chain shards, no data-path collective
 # ------------------------------------------------------------------------------------------------

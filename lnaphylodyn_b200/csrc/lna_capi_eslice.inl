@@ -86,7 +86,7 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, 
     constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
     if (!kIsEss || W > 0) return launch_cand_one<kProp>(pb, B, W > 0 ? W : 1, a);
     const int Wa = auto_width(pb, B);
-    if (Wa != 16) return launch_cand_one<kProp>(pb, B, Wa, a);
+    if (Wa != 16 && W != -2) return launch_cand_one<kProp>(pb, B, Wa, a);  // W == -2 forces the two-phase path
     if (cudaMemsetAsync(cb.count, 0, sizeof(int) * 4, pb->stream) != cudaSuccess) return fail("memset failed");
     a.max_waves = 1;
     if (launch_cand_one<kProp>(pb, B, 8, a)) return -1;
