@@ -32,6 +32,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "LNA+coalescent loglik evals/sec (FULL evaluations, batched chains)"
 UNIT = "evals/s"
+WORKLOAD = ("configs[1] Changpoint_sim vignette: SIR LNA N=1e6, 2000 fine steps, gridsize 50, 39 R0 change points, "
+            "cached 342-tip genealogy (E=376); FULL (param, initial, OriginTraj) -> coalLog evaluations")
+# DRAM bytes per launch of the hot kernel at the default batch (ncu --set full, profiles/r1_ncu_full_loglik_final.md)
+NCU_TRAFFIC_BYTES_65536 = 65057792 + 761856
 
 
 def load_workload():
@@ -106,8 +110,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Changpoint_sim vignette shape: SIR LNA N=1e6, 2000 fine steps, gridsize 50, "
-                               "39 change points, E=376 genealogy; FULL loglik evaluations"},
+        "config": {"workload": WORKLOAD, "sample_evals_per_step": per * cores},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,19 +197,26 @@ def bench_eslice(pb, g, B, iters, rank, world, dev):
         check(L.lna_chains_step(ch.h, C.byref(opts), nrm_h.data_ptr(), unf_h.data_ptr()), "lna_chains_step")
         check(L.lna_chains_get(ch.h, None, None, None, cl_h.data_ptr(), lo_h.data_ptr(), None), "lna_chains_get")
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # same end-to-end loop with the streams drawn on the device (Philox): only the summaries cross PCIe
+    t0 = time.perf_counter()
+    for i in range(iters):
+        check(L.lna_chains_step_rng(ch.h, C.byref(opts), 20261020, 1000 + i, rank * B), "lna_chains_step_rng")
+        check(L.lna_chains_get(ch.h, None, None, None, cl_h.data_ptr(), lo_h.data_ptr(), None), "lna_chains_get")
+    rng_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s * 1e3, rng_s * 1e3], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float((after["n_full_evals"] - before["n_full_evals"]).sum()),
                         float((after["n_cheap_evals"] - before["n_cheap_evals"]).sum())], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, rng_ms = float(t[0]), float(t[1]), float(t[2])
     tot = world * B * iters
     cpu = None
     if rank == 0:
         cpu = cpu_reference(g)
     return {"value": tot / (ms * 1e-3), "unit": "chain-iterations/s", "chains_per_gpu": B, "iters": iters,
             "ms_per_iter": ms / iters, "e2e_value": tot / (e2e_ms * 1e-3),
+            "e2e_device_rng_value": tot / (rng_ms * 1e-3),
             "h2d_bytes_per_iter": int(nrm_h.numel() * 8 + unf_h.numel() * 8), "d2h_bytes_per_iter": int(B * 16),
             "mean_full_evals_per_iter": float(cnt[0]) / tot, "mean_cheap_evals_per_iter": float(cnt[1]) / tot,
             "consumed_full_evals_per_s": float(cnt[0]) / (ms * 1e-3), "gpu_launches": int(launches),
@@ -451,15 +461,16 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1] Changpoint_sim vignette: SIR LNA N=1e6, 2000 fine steps, gridsize 50, "
-                                   "39 R0 change points, cached 342-tip genealogy (E=376)",
+            "config": {"workload": WORKLOAD,
                        "chains_per_gpu": args.chains, "proposals_per_chain": args.proposals, "evals_per_step_per_gpu": B,
                        "l2": "256 MB flush write between timed iterations", "sentinel_evals_in_batch": n_sentinel},
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                         "frac": achieved / peak if peak > 0 else None,
+                         "traffic": NCU_TRAFFIC_BYTES_65536 if B == 65536 else None,
+                         "traffic_unit": "bytes per launch (algorithmic: %d)" % ((h2d + d2h)),
                          "flops_per_eval": W,
                          "peak_source": "measured here: independent-DFMA microbenchmark (lna_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",

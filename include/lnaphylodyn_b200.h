@@ -248,6 +248,17 @@ int lna_chains_init(lna_chains *ch, const double *par, const double *OriginTraj)
  * `_dev`: streams already in HBM.  Host variant copies them in first. */
 int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *opts, const double *normals, const double *uniforms);
 int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *opts, const double *normals, const double *uniforms);
+/* Replayable on-device random streams (Philox4x32-10 keyed by seed and global chain id, counter =
+ * iteration and slot; normals by Box-Muller).  lna_chains_step_rng draws this iteration's streams in HBM
+ * and runs lna_chains_step_dev on them: nothing but the summaries ever crosses PCIe.
+ * lna_draw_streams returns the very same streams to the host (B x n_norm, B x n_unif) so that a chain can
+ * be replayed through any other implementation draw for draw.  chain_offset = first global chain id of
+ * this batch (lna_shard), which makes the streams independent of how chains are sharded over GPUs. */
+int lna_chains_step_rng(lna_chains *ch, const lna_mcmc_opts *opts, uint64_t seed, uint64_t iteration,
+                        int64_t chain_offset);
+int lna_draw_streams(lna_problem *pb, int64_t B, int64_t chain_offset, int n_norm, int n_unif, uint64_t seed,
+                     uint64_t iteration, double *normals, double *uniforms);
+
 /* Settings of General_MCMC2's iteration body (R/LNA_chpt_slice.R:576-691; the constant_sim vignette):
  * Update_Param_each entries (random walk on one parameter each, R/LNA_chpt_slice.R:266-365),
  * update_hyper (R/general_change_point.R:281-313), ESlice_change_points, trajectory ESS. */

@@ -65,6 +65,18 @@ class Chains:
         """Same with streams already in HBM (raw device pointers, e.g. torch.Tensor.data_ptr())."""
         check(_lib.lib().lna_chains_step_dev(self.h, C.byref(opts), normals_ptr, uniforms_ptr), "lna_chains_step_dev")
 
+    def step_rng(self, opts, seed, iteration, chain_offset=0):
+        """One iteration on streams drawn in HBM (Philox4x32-10; replayable with device_streams)."""
+        check(_lib.lib().lna_chains_step_rng(self.h, C.byref(opts), int(seed), int(iteration), int(chain_offset)),
+              "lna_chains_step_rng")
+
+    def device_streams(self, seed, iteration, chain_offset=0):
+        """The streams step_rng(seed, iteration, chain_offset) consumes, copied to the host."""
+        nrm, unf = np.empty((self.B, self.n_norm)), np.empty((self.B, ITER_UNIF))
+        check(_lib.lib().lna_draw_streams(self.pb.h, self.B, int(chain_offset), self.n_norm, ITER_UNIF, int(seed),
+                                          int(iteration), _ptr(nrm), _ptr(unf)), "lna_draw_streams")
+        return nrm, unf
+
     def get(self):
         pb, B = self.pb, self.B
         par = np.empty((B, self.npar))

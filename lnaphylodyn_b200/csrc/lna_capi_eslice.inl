@@ -739,6 +739,42 @@ extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const dou
     return lna_chains_step_dev(ch, o, ch->stage_n, ch->stage_u);
 }
 
+// ------------------------------------------------------------------------------------------------
+// on-device replayable streams
+// ------------------------------------------------------------------------------------------------
+static int draw_streams_dev(lna_problem *pb, long long B, long long chain_offset, int n_norm, int n_unif,
+                            uint64_t seed, uint64_t iteration, double *dn, double *du) {
+    const long long n = B * ((n_norm + 1) / 2 + (n_unif + 1) / 2);
+    k_draw_streams<<<nblk(n, 256), 256, 0, pb->stream>>>(B, chain_offset, n_norm, n_unif, seed, iteration, dn, du);
+    return launch_check(pb, "k_draw_streams");
+}
+
+extern "C" int lna_draw_streams(lna_problem *pb, int64_t B, int64_t chain_offset, int n_norm, int n_unif,
+                                uint64_t seed, uint64_t iteration, double *normals, double *uniforms) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (n_norm < 0 || n_unif < 0 || !normals || !uniforms) return fail("lna_draw_streams: bad arguments");
+    const size_t nB = (size_t)B;
+    Stage s(pb);
+    double *dn = s.tmp<double>(nB * n_norm), *du = s.tmp<double>(nB * n_unif);
+    if (!s.ok) return fail("lna_draw_streams: device staging failed");
+    if (draw_streams_dev(pb, B, chain_offset, n_norm, n_unif, seed, iteration, dn, du)) return -1;
+    s.back(normals, dn, nB * n_norm);
+    s.back(uniforms, du, nB * n_unif);
+    return s.finish("lna_draw_streams");
+}
+
+extern "C" int lna_chains_step_rng(lna_chains *ch, const lna_mcmc_opts *o, uint64_t seed, uint64_t iteration,
+                                   int64_t chain_offset) {
+    if (!ch || !o) return fail("lna_chains_step_rng: null argument");
+    lna_problem *pb = ch->pb;
+    cudaSetDevice(pb->device);
+    if (draw_streams_dev(pb, ch->B, chain_offset, (int)ch->n_norm, (int)ch->n_unif, seed, iteration, ch->stage_n,
+                         ch->stage_u))
+        return -1;
+    return lna_chains_step_dev(ch, o, ch->stage_n, ch->stage_u);
+}
+
 extern "C" int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
                               double *logOrigin, int32_t *counters) {
     if (!ch) return fail("lna_chains_get: null chains");

@@ -761,6 +761,56 @@ __global__ void k_param_slice_update_all2(DevProb P, long long B, CandArgs a, co
     o[npar - 1] = x.hyper_new;
 }
 
+// ================================================================================================
+// Counter-based random streams (Philox4x32-10): chain c, iteration it, slot q -> one 128-bit block.
+// Replaces the reference's calls into R's global RNG (arma::randn / R::runif, unpinned third-party) for
+// resident chains; the streams are replayable on the host (lna_draw_streams) so that every chain can be
+// re-run through the CPU restatement draw for draw.
+// ================================================================================================
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// 53-bit uniform in the open interval (0,1), like unif_rand()
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+    const unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 11;  // 53 bits
+    return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+}
+// one thread per (chain, pair of outputs): normals via Box-Muller, uniforms directly
+__global__ void k_draw_streams(long long B, long long chain_offset, int n_norm, int n_unif, unsigned long long seed,
+                               unsigned long long iteration, double *normals, double *uniforms) {
+    const int npair_n = (n_norm + 1) / 2, npair_u = (n_unif + 1) / 2, per = npair_n + npair_u;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * per) return;
+    const long long c = idx / per;
+    const int q = (int)(idx % per);
+    const unsigned long long chain = (unsigned long long)(chain_offset + c);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)iteration, (uint32_t)(iteration >> 32), (uint32_t)q, (uint32_t)(chain >> 32),
+                  (uint32_t)seed ^ (uint32_t)chain, (uint32_t)(seed >> 32), r);
+    const double a = u01(r[0], r[1]), b = u01(r[2], r[3]);
+    if (q < npair_n) {
+        const double rad = sqrt(-2.0 * log(a));
+        double sn, cs;
+        sincospi(2.0 * b, &sn, &cs);
+        normals[c * n_norm + 2 * q] = rad * cs;
+        if (2 * q + 1 < n_norm) normals[c * n_norm + 2 * q + 1] = rad * sn;
+    } else {
+        const int j = q - npair_n;
+        uniforms[c * n_unif + 2 * j] = a;
+        if (2 * j + 1 < n_unif) uniforms[c * n_unif + 2 * j + 1] = b;
+    }
+}
+
 // item-major <-> slot-major transposes for the resident chain state
 __global__ void k_to_soa(long long B, int n, const double *src_item_major, double *dst_soa) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

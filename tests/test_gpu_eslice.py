@@ -238,3 +238,32 @@ def test_chains_mcmc2_step_for_step(api, constant):
             assert s["n_mh_accept"][c] == ref[c]["n_mh_accept"], (it, c)
         accepted = int(s["n_mh_accept"].sum())
     assert 0 < accepted < B * iters * 4
+
+
+def test_device_rng_streams_and_replay(api, changepoint):
+    """On-device Philox streams: N(0,1)/U(0,1) moments, independence of the sharding (chain_offset), and a
+    chain advanced with step_rng replays exactly through the oracle on the streams read back to the host."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    B = 8
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    big = chm.Chains(pb, np.tile(par0, (2048, 1)), g.setting("control.traj"))
+    n, u = big.device_streams(seed=7, iteration=3)
+    assert abs(n.mean()) < 0.01 and abs(n.std() - 1) < 0.01 and abs(u.mean() - 0.5) < 0.005
+    assert 0 < u.min() and u.max() < 1 and abs(np.mean(n ** 4) - 3) < 0.1
+    assert abs(np.corrcoef(n[:, 0], n[:, 1])[0, 1]) < 0.08 and len(np.unique(u)) == u.size
+    n2, u2 = ch.device_streams(seed=7, iteration=3, chain_offset=1000)
+    assert np.array_equal(n2, n[1000:1008]) and np.array_equal(u2, u[1000:1008])   # sharding-independent
+    ref = [driver.init_state(g, par0, g.setting("control.traj")) for _ in range(B)]
+    for it in range(3):
+        opts = chm.vignette_opts(g, update_traj=it >= 1)
+        nrm, unf = ch.device_streams(seed=11, iteration=it, chain_offset=40)
+        ch.step_rng(opts, seed=11, iteration=it, chain_offset=40)
+        s = ch.get()
+        for c in range(B):
+            ref[c] = driver.eslice_iteration(ref[c], g, driver.opts_from_golden(g, update_traj=it >= 1), nrm[c], unf[c])
+            assert relerr(s["par"][c], ref[c]["par"]) < TOL and s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL)
+            assert s["n_full_evals"][c] == ref[c]["n_full"]
