@@ -32,7 +32,10 @@ extern "C" {
 #define LNA_ABI_VERSION 1
 
 /* model strings of the reference ("SIR","SEIR": LNA_functional.cpp:390-443) become enums */
-enum { LNA_MODEL_SIR = 0, LNA_MODEL_SEIR = 1 };
+/* LNA_MODEL_SIRS_PERIOD: the seasonal SIRS of src/SIRS_period.cpp (param = (beta, gamma, mu, alpha), nch = 0,
+ * nparam = 4, x_r[0] = period): ODE2, SIRS_KOM_Filter and log_like_trajSIRS only -- the reference has no
+ * non-centred / sampler path for it. */
+enum { LNA_MODEL_SIR = 0, LNA_MODEL_SEIR = 1, LNA_MODEL_SIRS_PERIOD = 2 };
 /* transX: only "standard" is on the GPU path ("log" is legacy) */
 enum { LNA_TRANSX_STANDARD = 0 };
 
@@ -204,6 +207,10 @@ int lna_eslice_change_points(lna_problem *pb, int64_t B, const double *param, co
  * KF_param's (A, Sigma); rows with time <= t_correct. */
 int lna_log_like_traj_general2(lna_problem *pb, int64_t B, const double *SdeTraj, const double *OdeTraj,
                                const double *Acube, const double *Scube, double *loglik);
+/* log_like_trajSIRS (SIRS_period.cpp:82-118): the same density for the rank-2 covariance of the seasonal SIRS
+ * (PseudoInverse :22-48, DegenerateDet3 :17-19). */
+int lna_log_like_traj_sirs(lna_problem *pb, int64_t B, const double *SdeTraj, const double *OdeTraj,
+                           const double *Acube, const double *Scube, double *loglik);
 /* Traj_sim_general3 (:771-817): centred LNA simulation with supplied normals (B x k*p, step-major);
  * noise = mvrnormArma(Sigma) (basic_util.cpp:44-58).  Traj_sim_ezG2 (:907-975) = lna_ode_rk45 +
  * lna_kf_param(chol = 0) + lna_ode_coarse_slicer + this. */

@@ -72,6 +72,7 @@ _SIGS = {
     "lna_eslice_general_nc": (C.c_int, [_vp, _I64] + [_vp] * 14),
     "lna_eslice_change_points": (C.c_int, [_vp, _I64] + [_vp] * 6 + [C.c_int] + [_vp] * 10),
     "lna_log_like_traj_general2": (C.c_int, [_vp, _I64] + [_vp] * 5),
+    "lna_log_like_traj_sirs": (C.c_int, [_vp, _I64] + [_vp] * 5),
     "lna_traj_sim_general3": (C.c_int, [_vp, _I64] + [_vp] * 7),
     "lna_eslice_general2": (C.c_int, [_vp, _I64] + [_vp] * 10),
     "lna_chains_create": (_vp, [_vp, _I64]),

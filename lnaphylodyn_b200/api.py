@@ -18,8 +18,8 @@ import numpy as np
 from . import _lib
 from ._lib import LnaCfg, LnaInit, LnaError, check
 
-MODELS = {"SIR": 0, "SEIR": 1}
-MODEL_P = {"SIR": 2, "SEIR": 3}
+MODELS = {"SIR": 0, "SEIR": 1, "SIRS_period": 2}
+MODEL_P = {"SIR": 2, "SEIR": 3, "SIRS_period": 3}
 SENTINEL = -10000000.0
 ST_CHOL_FAIL, ST_NEG_STATE, ST_NAN, ST_CAP_HIT = 1, 2, 4, 8
 ESLICE_MAX_UNIF = 22
@@ -663,3 +663,51 @@ def ESlice_general2(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0
                                          _ptr(out), _ptr(ne), _ptr(st)), "lna_eslice_general2")
     pick = (lambda a: a[0]) if single else (lambda a: a)
     return {"newTraj": pb._unmats(out, (nrow, p + 1), single), "n_evals": pick(ne), "status": pick(st)}
+
+
+# ------------------------------------------------------------------------------------------------
+# seasonal SIRS model variant (src/SIRS_period.cpp): ODE / LNA moments / trajectory density
+# ------------------------------------------------------------------------------------------------
+
+def _sirs_problem(times, period, gridsize=1):
+    return problem_for(times, [float(period)], [0, 4, 0, 1], gridsize, 0.0, None, "SIRS_period")
+
+
+def ODE2(initial, t, param, period):
+    """SIRS_period.cpp:174-193: seasonal SIRS mean trajectory, param = (beta, gamma, mu, alpha)."""
+    pb = _sirs_problem(t, period)
+    P = _d(param).reshape(-1, 4)
+    I = _d(initial).reshape(-1, 3)
+    out = np.empty((P.shape[0], len(pb.times) * 4))
+    check(_lib.lib().lna_ode_rk45(pb.h, P.shape[0], _ptr(I), _ptr(P), _ptr(out)), "lna_ode_rk45")
+    return pb._unmats(out, (len(pb.times), 4), np.asarray(param).ndim == 1)
+
+
+def SIRS_KOM_Filter(OdeTraj, param, gridsize, period):
+    """SIRS_period.cpp:147-168 (+ SIRS_IntSigma :50-79): {A, Sigma} per LNA interval."""
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    pb = _sirs_problem(O[:, 0] if single else O[0, :, 0], period, gridsize)
+    Of, _ = pb._mats(O, (len(pb.times), 4))
+    P = _d(param).reshape(-1, 4)
+    B = Of.shape[0]
+    A, S, st = np.empty((B, 9 * pb.k)), np.empty((B, 9 * pb.k)), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_kf_param(pb.h, B, _ptr(Of), _ptr(P), 0, _ptr(A), _ptr(S), _ptr(st)), "lna_kf_param")
+    return {"A": pb._unmats(A, (3, 3, pb.k), single), "Sigma": pb._unmats(S, (3, 3, pb.k), single)}
+
+
+def log_like_trajSIRS(SdeTraj, OdeTraj, Filter, gridsize, t_correct):
+    """SIRS_period.cpp:82-118"""
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    times = O[:, 0] if single else O[0, :, 0]
+    pb = problem_for(times, [1.0], [0, 3, 0, 2], 1, t_correct, None, "SEIR")  # any 3-compartment problem on this grid
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, 4))
+    Xf, _ = pb._mats(SdeTraj, (nrow, 4))
+    Af, _ = pb._mats(Filter["A"], (3, 3, k))
+    Sf, _ = pb._mats(Filter["Sigma"], (3, 3, k))
+    ll = np.empty(Of.shape[0])
+    check(_lib.lib().lna_log_like_traj_sirs(pb.h, Of.shape[0], _ptr(Xf), _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(ll)),
+          "lna_log_like_traj_sirs")
+    return float(ll[0]) if single else ll

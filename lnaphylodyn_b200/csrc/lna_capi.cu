@@ -136,8 +136,12 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
         fail("lna_problem_create: null cfg/times/x_r");
         return nullptr;
     }
-    if (cfg->model != LNA_MODEL_SIR && cfg->model != LNA_MODEL_SEIR) {
-        fail("lna_problem_create: unsupported model %d (SIR=0, SEIR=1)", cfg->model);
+    if (cfg->model != LNA_MODEL_SIR && cfg->model != LNA_MODEL_SEIR && cfg->model != LNA_MODEL_SIRS_PERIOD) {
+        fail("lna_problem_create: unsupported model %d (SIR=0, SEIR=1, SIRS_PERIOD=2)", cfg->model);
+        return nullptr;
+    }
+    if (cfg->model == LNA_MODEL_SIRS_PERIOD && (cfg->nch != 0 || cfg->nparam != 4 || init)) {
+        fail("lna_problem_create: SIRS_PERIOD takes param = (beta, gamma, mu, alpha), no change points, no genealogy");
         return nullptr;
     }
     if (cfg->transX != LNA_TRANSX_STANDARD) {
@@ -174,6 +178,7 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     DevProb &P = pb->dp;
     P.model = cfg->model;
     P.p = cfg->model == LNA_MODEL_SIR ? 2 : 3;
+    if (cfg->model == LNA_MODEL_SIRS_PERIOD) P.npt = 4;
     P.nch = cfg->nch;
     P.nparam = cfg->nparam;
     P.iR0 = cfg->iR0;
@@ -184,7 +189,7 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     P.nt = cfg->nt;
     P.k = (cfg->nt - 1) / cfg->gridsize;
     P.nrow = P.k + 1;  // = nt/gridsize + 1 (Ode_Coarse_Slicer, :1182) whenever gridsize > 1 divides nt-1
-    P.npt = cfg->nparam + cfg->nch + 1;
+    P.npt = cfg->model == LNA_MODEL_SIRS_PERIOD ? 4 : cfg->nparam + cfg->nch + 1;
     P.N = cfg->x_r[0];
     P.t_correct = cfg->t_correct;
     pb->times.assign(cfg->times, cfg->times + cfg->nt);
@@ -412,6 +417,9 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
     if (B <= 0) return 0;
     const DevProb &P = pb->dp;
     if (!param || !initial) return fail("lna_full_loglik: param/initial must not be null");
+    if (P.model == LNA_MODEL_SIRS_PERIOD)
+        return fail("lna_full_loglik: the seasonal SIRS variant has no non-centred path in the reference "
+                    "(use lna_ode_rk45 / lna_kf_param / lna_log_like_traj_sirs)");
     if (coalLog && !P.has_init) return fail("lna_full_loglik: problem was created without a genealogy");
     const int p = P.p;
     FullOut out{item_out(A, (long long)p * p * P.k), item_out(L, (long long)p * p * P.k),
@@ -587,8 +595,10 @@ extern "C" int lna_ode_rk45(lna_problem *pb, int64_t B, const double *initial, c
     if (!s.ok || !dini || !dpar || !dout) return fail("lna_ode_rk45: bad arguments / staging failed");
     if (P.model == LNA_MODEL_SIR)
         k_ode_rk45<0><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
-    else
+    else if (P.model == LNA_MODEL_SEIR)
         k_ode_rk45<1><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
+    else
+        k_ode_rk45<2><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
     if (launch_check(pb, "k_ode_rk45")) return -1;
     s.back(OdeTraj, dout, nB * per);
     return s.finish("lna_ode_rk45");
@@ -607,10 +617,14 @@ extern "C" int lna_kf_param(lna_problem *pb, int64_t B, const double *OdeTraj, c
     if (!s.ok || !dtr || !dpar) return fail("lna_kf_param: bad arguments / staging failed");
     CK(cudaMemsetAsync(dst, 0, nB * sizeof(int32_t), pb->stream));
     const long long n = (long long)B * P.k;
+    if (P.model == LNA_MODEL_SIRS_PERIOD && chol)
+        return fail("lna_kf_param: SIRS_PERIOD has a rank-deficient covariance; only chol = 0 (SIRS_KOM_Filter) is provided");
     if (P.model == LNA_MODEL_SIR)
         k_kf_param<0><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);
-    else
+    else if (P.model == LNA_MODEL_SEIR)
         k_kf_param<1><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);
+    else
+        k_kf_param<2><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);
     if (launch_check(pb, "k_kf_param")) return -1;
     s.back(Acube, dA, nB * cube);
     s.back(Scube, dS, nB * cube);

@@ -367,6 +367,24 @@ extern "C" int lna_log_like_traj_general2(lna_problem *pb, int64_t B, const doub
     return s.finish("lna_log_like_traj_general2");
 }
 
+/* log_like_trajSIRS (SIRS_period.cpp:82-118): pseudo-inverse density of the rank-2 seasonal SIRS covariance */
+extern "C" int lna_log_like_traj_sirs(lna_problem *pb, int64_t B, const double *SdeTraj, const double *OdeTraj,
+                                      const double *Acube, const double *Scube, double *loglik) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    if (P.p != 3) return fail("lna_log_like_traj_sirs: needs a 3-compartment problem");
+    const size_t nB = (size_t)B, per = (size_t)P.nrow * (P.p + 1), cube = (size_t)P.p * P.p * P.k;
+    Stage s(pb);
+    const double *dX = s.in(SdeTraj, nB * per), *dO = s.in(OdeTraj, nB * per), *dA = s.in(Acube, nB * cube),
+                 *dS = s.in(Scube, nB * cube);
+    double *dll = s.tmp<double>(nB);
+    if (!s.ok || !dX || !dO || !dA || !dS) return fail("lna_log_like_traj_sirs: bad arguments / staging failed");
+    if (centred_launch(pb, B, 2, dX, dO, dA, dS, nullptr, dll, nullptr)) return -1;
+    s.back(loglik, dll, nB);
+    return s.finish("lna_log_like_traj_sirs");
+}
+
 extern "C" int lna_traj_sim_general3(lna_problem *pb, int64_t B, const double *OdeTraj, const double *Acube,
                                      const double *Scube, const double *normals, double *LNA_traj, double *loglike,
                                      int32_t *status) {

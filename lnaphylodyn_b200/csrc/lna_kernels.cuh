@@ -155,6 +155,28 @@ struct Model<1> {  // SEIR
     }
 };
 
+template <>
+struct Model<2> {  // seasonal SIRS (src/SIRS_period.cpp): states (S, I, R), th = (beta(t), gamma, mu)
+    static constexpr int P = 3;
+    __device__ static void rhs(const double *x, const double *th, double *d) {  // SIRS_ODE :122-144
+        d[0] = -th[0] * x[0] * x[1] + th[2] * x[2];
+        d[1] = th[0] * x[0] * x[1] - th[1] * x[1];
+        d[2] = th[1] * x[1] - th[2] * x[2];
+    }
+    __device__ static void F(const double *x, const double *th, double *Fm) {  // SIRS_Fm_LNA_period :6-14
+        Fm[0] = -th[0] * x[1]; Fm[1] = -th[0] * x[0];        Fm[2] = th[2];
+        Fm[3] = th[0] * x[1];  Fm[4] = th[0] * x[0] - th[1]; Fm[5] = 0.0;
+        Fm[6] = 0.0;           Fm[7] = th[1];                Fm[8] = -th[2];
+    }
+    __device__ static void Q(const double *x, const double *th, double *Qm) {  // A' diag(h) A, A = [-1 1 0; 0 -1 1; 1 0 -1]
+        const double h0 = th[0] * x[0] * x[1], h1 = th[1] * x[1], h2 = th[2] * x[2];
+        Qm[0] = h0 + h2; Qm[1] = -h0;     Qm[2] = -h2;
+        Qm[3] = -h0;     Qm[4] = h0 + h1; Qm[5] = -h1;
+        Qm[6] = -h2;     Qm[7] = -h1;     Qm[8] = h1 + h2;
+    }
+};
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
 // ODE_rk45 (LNA_functional.cpp:455-491): full fine trajectory, one thread per item.
 template <int kModel>
 __global__ void k_ode_rk45(DevProb P, long long B, View initial, View param, double *OdeTraj) {
@@ -174,8 +196,12 @@ __global__ void k_ode_rk45(DevProb P, long long B, View initial, View param, dou
     }
     out[0] = P.times[0];
     for (int i = 1; i < P.nt; ++i) {
-        while (nxt < P.nch && P.chidx[nxt] <= i - 1) R0 *= param.at(b, P.nparam + nxt++);
-        th[0] = R0 * gam / P.N;
+        if (kModel == 2) {  // ODE2 (SIRS_period.cpp:174-193): beta(t) = beta (1 + alpha sin(2 pi t / period)), x_r[0] = period
+            th[0] = param.at(b, 0) * (1 + param.at(b, 3) * sin(2 * kPi * P.times[i - 1] / P.N));
+        } else {
+            while (nxt < P.nch && P.chidx[nxt] <= i - 1) R0 *= param.at(b, P.nparam + nxt++);
+            th[0] = R0 * gam / P.N;
+        }
         double k1[p], k2[p], k3[p], k4[p], xs[p];
         M::rhs(x, th, k1);
         for (int c = 0; c < p; ++c) xs[c] = x[c] + k1[c] * dt / 2;
@@ -209,10 +235,12 @@ __global__ void k_kf_param(DevProb P, long long B, const double *OdeTraj, View p
     for (int c = 0; c < p; ++c) F0[c * p + c] = 1.0;
     double th[3] = {0.0, param.at(b, 1), P.npt > 2 ? param.at(b, 2) : 0.0};
     const int r0 = seg * P.g;
-    const double dt = tr[r0 + 1] - tr[r0];
+    // SigmaF uses the block's own first interval (:568); SIRS_KOM_Filter the global one (SIRS_period.cpp:149)
+    const double dt = kModel == 2 ? tr[1] - tr[0] : tr[r0 + 1] - tr[r0];
     for (int i = 0; i < P.g; ++i) {
         const int r = r0 + i;
-        th[0] = beta_at(P, param, b, tr[r]);
+        th[0] = kModel == 2 ? param.at(b, 0) * (1 + param.at(b, 3) * sin(tr[r] / P.N * 2 * kPi))
+                            : beta_at(P, param, b, tr[r]);
         double x[p];
         for (int c = 0; c < p; ++c) x[c] = tr[r + (long long)(c + 1) * P.nt];
         M::F(x, th, Fm);
@@ -364,7 +392,8 @@ __global__ void k_centred(int k, long long B, int mode, double t_correct, const 
     const double *A = Acube + b * (long long)k * p * p, *S = Scube + b * (long long)k * p * p;
     double ll = 0.0;
     int st = 0;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
+        // mode 2 = log_like_trajSIRS (SIRS_period.cpp:82-118): rank-2 covariance, PseudoInverse / DegenerateDet3
         const double *X = Sde_or_normals + b * (long long)nrow * (p + 1);
         double d0[p], d1[p], v[p], w[p];
         for (int j = 0; j < p; ++j) d1[j] = X[(long long)(j + 1) * nrow] - O[(long long)(j + 1) * nrow];
@@ -380,10 +409,29 @@ __global__ void k_centred(int k, long long B, int mode, double t_correct, const 
                     for (int q = 0; q < p; ++q) ax += Ai[r + q * p] * d0[q];
                     v[r] = d1[r] - ax;
                 }
-                solve_small<p>(Si, v, w);
-                double q = 0.0;
-                for (int r = 0; r < p; ++r) q += v[r] * w[r];
-                ll += -log(det_small<p>(Si)) / 2.0 - 0.5 * q;
+                if (mode == 2 && p == 3) {
+                    const double m01 = Si[3], m02 = Si[6], m11 = Si[4], m12 = Si[7], m22 = Si[8];
+                    const double tr = m11 + m22 - m01 - m02;
+                    const double dd = (m11 - m01) * (m22 - m02) - (m12 - m01) * (m12 - m02);  // DegenerateDet3
+                    const double sq = sqrt(tr * tr - 4 * dd);
+                    const double l1 = (tr + sq) / 2, l2 = (tr - sq) / 2;
+                    double e1[3], e2[3];
+                    e1[1] = (m12 - m01) / (m11 - m01 - l1); e1[0] = 1 - e1[1]; e1[2] = -1;
+                    e2[1] = (m12 - m01) / (m11 - m01 - l2); e2[0] = 1 - e2[1]; e2[2] = -1;
+                    const double n1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+                    const double n2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+                    double p1 = 0.0, p2 = 0.0;  // projections on the two eigenvectors
+                    for (int r = 0; r < 3; ++r) {
+                        p1 += (e1[r] / n1) * v[r];
+                        p2 += (e2[r] / n2) * v[r];
+                    }
+                    ll += -log(dd) * 0.5 - 0.5 * (p1 * p1 / l1 + p2 * p2 / l2);
+                } else {
+                    solve_small<p>(Si, v, w);
+                    double q = 0.0;
+                    for (int r = 0; r < p; ++r) q += v[r] * w[r];
+                    ll += -log(det_small<p>(Si)) / 2.0 - 0.5 * q;
+                }
             }
         }
     } else {

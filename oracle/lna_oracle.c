@@ -1019,6 +1019,165 @@ int orc_eslice_general2(const orc_init *init, const double *f_cur, int nrow, int
     return status;
 }
 
+/* ---------------------------------------------------------------- seasonal SIRS (SIRS_period.cpp) */
+
+/* SIRS_ODE: SIRS_period.cpp:122-144.  param = (beta, gamma, mu, alpha); states (S, I, R). */
+static void sirs_rhs(const double *x, const double *param, double t, double period, double *res) {
+    double th1 = param[0] * (1 + param[3] * sin(2 * ORC_PI * t / period));
+    res[0] = -th1 * x[0] * x[1] + param[2] * x[2];
+    res[1] = th1 * x[0] * x[1] - param[1] * x[1];
+    res[2] = param[1] * x[1] - param[2] * x[2];
+}
+
+/* ODE2: SIRS_period.cpp:174-193 (same RK variant as ODE_rk45). */
+void orc_sirs_ode2(const double *initial, const double *t, int n, const double *param, double period,
+                   double *OdeTraj) {
+    const int p = 3;
+    double dt = t[1] - t[0], X0[3], X1[3], k1[3], k2[3], k3[3], k4[3], xs[3];
+    for (int i = 0; i < n; i++) OdeTraj[i] = t[i];
+    for (int j = 0; j < p; j++) {
+        OdeTraj[(size_t)(j + 1) * n] = initial[j];
+        X1[j] = initial[j];
+    }
+    for (int i = 1; i < n; i++) {
+        for (int j = 0; j < p; j++) X0[j] = X1[j];
+        sirs_rhs(X0, param, t[i - 1], period, k1);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k1[j] * dt / 2;
+        sirs_rhs(xs, param, t[i - 1], period, k2);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k2[j] * dt / 2;
+        sirs_rhs(xs, param, t[i - 1], period, k3);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k3[j] * dt / 2;
+        sirs_rhs(xs, param, t[i - 1], period, k4);
+        for (int j = 0; j < p; j++) {
+            X1[j] = X0[j] + (k1[j] / 6 + k2[j] / 3 + k3[j] / 3 + k4[j] / 6) * dt;
+            OdeTraj[i + (size_t)(j + 1) * n] = X1[j];
+        }
+    }
+}
+
+/* SIRS_IntSigma :50-79 + SIRS_KOM_Filter :147-168 (global dt; A = [-1 1 0; 0 -1 1; 1 0 -1]). */
+void orc_sirs_kom_filter(const double *OdeTraj, int nrow, const double *param, int gridsize, double period,
+                         double *Acube, double *Scube) {
+    const int p = 3;
+    int k = (nrow - 1) / gridsize;
+    double dt = OdeTraj[1] - OdeTraj[0];
+    double th[3] = {param[0], param[1], param[2]}, alpha = param[3];
+    for (int seg = 0; seg < k; seg++) {
+        double F0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Sg[9] = {0}, F[9], Q[9], T1[9], T2[9], FF0[9];
+        for (int i = 0; i < gridsize; i++) {
+            int r = seg * gridsize + i;
+            double t = OdeTraj[r], X = OdeTraj[r + (size_t)nrow], Y = OdeTraj[r + (size_t)2 * nrow],
+                   Z = OdeTraj[r + (size_t)3 * nrow];
+            double th1 = th[0] * (1 + alpha * sin(t / period * 2 * ORC_PI));
+            double h0 = th1 * X * Y, h1 = th[1] * Y, h2 = th[2] * Z;
+            /* F (col-major), SIRS_Fm_LNA_period :6-14 */
+            F[0] = -th1 * Y; F[3] = -th1 * X;        F[6] = th[2];
+            F[1] = th1 * Y;  F[4] = th1 * X - th[1]; F[7] = 0;
+            F[2] = 0;        F[5] = th[1];           F[8] = -th[2];
+            /* A' H A */
+            Q[0] = h0 + h2; Q[3] = -h0;     Q[6] = -h2;
+            Q[1] = -h0;     Q[4] = h0 + h1; Q[7] = -h1;
+            Q[2] = -h2;     Q[5] = -h1;     Q[8] = h1 + h2;
+            mat_mul(F, F0, p, FF0);
+            for (int e = 0; e < 9; e++) F0[e] = F0[e] + FF0[e] * dt;
+            mat_mul_bt(Sg, F, p, T1);
+            mat_mul(F, Sg, p, T2);
+            for (int e = 0; e < 9; e++) Sg[e] = Sg[e] + ((T1[e] + T2[e]) + Q[e]) * dt;
+        }
+        memcpy(Acube + (size_t)seg * 9, F0, sizeof F0);
+        memcpy(Scube + (size_t)seg * 9, Sg, sizeof Sg);
+    }
+}
+
+/* DegenerateDet3 :17-19 and PseudoInverse :22-48 of the rank-2 covariance. */
+static double degenerate_det3(const double *M) {
+    return (M[4] - M[3]) * (M[8] - M[6]) - (M[7] - M[3]) * (M[7] - M[6]);
+}
+static void pseudo_inverse3(const double *M, double *out) {
+    /* M(r,c) = M[r + 3c] */
+    double m01 = M[3], m02 = M[6], m11 = M[4], m12 = M[7], m22 = M[8];
+    double tr = m11 + m22 - m01 - m02;
+    double delta = tr * tr - 4 * ((m11 - m01) * (m22 - m02) - (m12 - m01) * (m12 - m02));
+    double l1 = (tr + sqrt(delta)) / 2, l2 = (tr - sqrt(delta)) / 2;
+    double e1[3], e2[3];
+    e1[1] = (m12 - m01) / (m11 - m01 - l1); e1[0] = 1 - e1[1]; e1[2] = -1;
+    e2[1] = (m12 - m01) / (m11 - m01 - l2); e2[0] = 1 - e2[1]; e2[2] = -1;
+    double n1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    double n2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+    for (int i = 0; i < 3; i++) {
+        e1[i] /= n1;
+        e2[i] /= n2;
+    }
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) out[r + 3 * c] = e1[r] * (1 / l1) * e1[c] + e2[r] * (1 / l2) * e2[c];
+}
+
+/* log_like_trajSIRS :82-118 (mode 0) and Traj_sim_SIRS :196-240 (mode 1, normals step-major 3 per step). */
+int orc_sirs_centred(int mode, const double *X_or_normals, const double *initial, const double *OdeTraj, int nrow,
+                     const double *Acube, const double *Scube, double t_correct, double *traj_out, double *loglik) {
+    const int p = 3;
+    int k = nrow - 1;
+    double ll = 0.0, PI3[9], v[3], w[3];
+    if (mode == 0) {
+        const double *X = X_or_normals;
+        double d0[3], d1[3];
+        for (int j = 0; j < p; j++) d1[j] = X[(size_t)(j + 1) * nrow] - OdeTraj[(size_t)(j + 1) * nrow];
+        for (int i = 0; i < k; i++) {
+            const double *A = Acube + (size_t)i * 9, *S = Scube + (size_t)i * 9;
+            for (int j = 0; j < p; j++) {
+                d0[j] = d1[j];
+                d1[j] = X[(i + 1) + (size_t)(j + 1) * nrow] - OdeTraj[(i + 1) + (size_t)(j + 1) * nrow];
+            }
+            if (X[i + 1] <= t_correct) {
+                pseudo_inverse3(S, PI3);
+                for (int r = 0; r < p; r++) {
+                    double ax = 0.0;
+                    for (int q = 0; q < p; q++) ax += A[r + q * p] * d0[q];
+                    v[r] = d1[r] - ax;
+                }
+                for (int r = 0; r < p; r++) w[r] = PI3[r] * v[0] + PI3[r + 3] * v[1] + PI3[r + 6] * v[2];
+                ll += -log(degenerate_det3(S)) * 0.5 - 0.5 * (v[0] * w[0] + v[1] * w[1] + v[2] * w[2]);
+            }
+        }
+    } else {
+        double X0[3], X1[3], e0[3], e1[3], noise[3], L[9];
+        for (int j = 0; j < p; j++) {
+            X1[j] = initial[j];
+            e1[j] = initial[j];
+            traj_out[(size_t)(j + 1) * nrow] = initial[j];
+        }
+        traj_out[0] = 0;
+        for (int i = 0; i < k; i++) {
+            const double *A = Acube + (size_t)i * 9, *S = Scube + (size_t)i * 9;
+            for (int j = 0; j < p; j++) {
+                X0[j] = X1[j];
+                e0[j] = e1[j];
+                e1[j] = OdeTraj[(i + 1) + (size_t)(j + 1) * nrow];
+            }
+            if (orc_chol_lower(S, 3, 0.0000000000001, L)) return ORC_CHOL_FAIL; /* mvrnormArma2 */
+            for (int r = 0; r < 3; r++) {
+                double s2 = 0.0;
+                for (int q = 0; q < 3; q++) s2 += L[r + q * 3] * X_or_normals[(size_t)i * 3 + q];
+                noise[r] = s2;
+            }
+            for (int r = 0; r < p; r++) {
+                double ax = 0.0;
+                for (int q = 0; q < p; q++) ax += A[r + q * p] * (X0[q] - e0[q]);
+                X1[r] = ax + e1[r] + noise[r];
+            }
+            if (OdeTraj[i + 1] <= t_correct) {
+                pseudo_inverse3(S, PI3);
+                for (int r = 0; r < p; r++) w[r] = PI3[r] * noise[0] + PI3[r + 3] * noise[1] + PI3[r + 6] * noise[2];
+                ll += -log(degenerate_det3(S)) * 0.5 + (-0.5) * (noise[0] * w[0] + noise[1] * w[1] + noise[2] * w[2]);
+            }
+            traj_out[i + 1] = OdeTraj[i + 1];
+            for (int j = 0; j < p; j++) traj_out[(i + 1) + (size_t)(j + 1) * nrow] = X1[j];
+        }
+    }
+    *loglik = ll;
+    return ORC_OK;
+}
+
 /* ---------------------------------------------------------------- batch driver (bench baseline) */
 
 /* B independent FULL evaluations, item-major inputs like the product's C ABI; one core.

@@ -147,6 +147,14 @@ int orc_eslice_general2(const orc_init *init, const double *f_cur, int nrow, int
                         const int *Index, int transX, const double *normals, const double *uniforms, int *n_unif,
                         int *n_evals, double *newTraj);
 
+/* seasonal SIRS model variant (src/SIRS_period.cpp): ODE2, SIRS_KOM_Filter, log_like_trajSIRS / Traj_sim_SIRS */
+void orc_sirs_ode2(const double *initial, const double *t, int n, const double *param, double period,
+                   double *OdeTraj);
+void orc_sirs_kom_filter(const double *OdeTraj, int nrow, const double *param, int gridsize, double period,
+                         double *Acube, double *Scube);
+int orc_sirs_centred(int mode, const double *X_or_normals, const double *initial, const double *OdeTraj, int nrow,
+                     const double *Acube, const double *Scube, double t_correct, double *traj_out, double *loglik);
+
 /* B independent FULL evaluations on one core (item-major inputs like the product's C ABI). */
 int orc_full_loglik_batch(const orc_cfg *c, const orc_init *init, long B, const double *param,
                           const double *initial, const double *t, int nt, int gridsize,

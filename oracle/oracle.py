@@ -445,3 +445,40 @@ def ESlice_general2(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0
                                    C.c_double(t_correct), Index, TRANSX[transX], _p(nrm), _p(unf), C.byref(nu),
                                    C.byref(ne), _p(out))
     return {"newTraj": out, "status": st, "n_uniforms": nu.value, "n_evals": ne.value}
+
+
+# ---- seasonal SIRS (src/SIRS_period.cpp) -------------------------------------------------------------
+
+def ODE2(initial, t, param, period):
+    initial, t, param = _d(initial), _d(t), _d(param)
+    out = np.empty((len(t), 4), order="F")
+    lib().orc_sirs_ode2(_p(initial), _p(t), len(t), _p(param), C.c_double(period), _p(out))
+    return out
+
+
+def SIRS_KOM_Filter(OdeTraj, param, gridsize, period):
+    O, param = _f(OdeTraj), _d(param)
+    k = (O.shape[0] - 1) // gridsize
+    A, S = _cubes(3, k)
+    lib().orc_sirs_kom_filter(_p(O), O.shape[0], _p(param), int(gridsize), C.c_double(period), _p(A), _p(S))
+    return {"A": A, "Sigma": S}
+
+
+def log_like_trajSIRS(SdeTraj, OdeTraj, Filter, gridsize, t_correct):
+    X, O = _f(SdeTraj), _f(OdeTraj)
+    A, S = _f(Filter["A"]), _f(Filter["Sigma"])
+    ll = C.c_double()
+    lib().orc_sirs_centred(0, _p(X), None, _p(O), O.shape[0], _p(A), _p(S), C.c_double(t_correct), None, C.byref(ll))
+    return ll.value
+
+
+def Traj_sim_SIRS(initial, OdeTraj, Filter, t_correct, *, normals):
+    O, initial, z = _f(OdeTraj), _d(initial), _d(normals)
+    A, S = _f(Filter["A"]), _f(Filter["Sigma"])
+    out = np.empty_like(O, order="F")
+    ll = C.c_double()
+    st = lib().orc_sirs_centred(1, _p(z), _p(initial), _p(O), O.shape[0], _p(A), _p(S), C.c_double(t_correct), _p(out),
+                                C.byref(ll))
+    if st:
+        raise ValueError("chol(): decomposition failed")
+    return {"SimuTraj": out, "loglike": ll.value}

@@ -286,3 +286,31 @@ def test_centred_entry_points(api, changepoint):
         assert d["n_evals"][b] == o["n_evals"] and (d["status"][b] & 8) == (o["status"] & 8), b
         assert relerr(d["newTraj"][b][:, 1:], o["newTraj"][:, 1:]) < 1e-9
     assert d["n_evals"].max() > 3
+
+
+def test_seasonal_sirs_model_variant(api):
+    """src/SIRS_period.cpp as a model variant of the ODE / LNA-moment kernels (configs[3]): ODE2,
+    SIRS_KOM_Filter and the pseudo-inverse trajectory density, 64 parameter draws."""
+    t = np.linspace(0, 100, 2001)
+    rng = np.random.default_rng(31)
+    B = 64
+    param = np.column_stack([3e-6 * np.exp(0.1 * rng.standard_normal(B)), 0.2 * np.exp(0.1 * rng.standard_normal(B)),
+                             0.02 * np.exp(0.1 * rng.standard_normal(B)), rng.uniform(0.1, 0.5, B)])
+    init = np.tile([9e4, 100.0, 9900.0], (B, 1))
+    d_ode = api.ODE2(init, t, param, 40.0)
+    for b in range(0, B, 8):
+        o_ode = orc.ODE2(init[b], t, param[b], 40.0)
+        assert np.max(np.abs(d_ode[b] - o_ode) / np.maximum(np.abs(o_ode), 1e-300)[...]) < TOL
+        kf_o = orc.SIRS_KOM_Filter(o_ode, param[b], 50, 40.0)
+        kf_d = api.SIRS_KOM_Filter(o_ode, param[b], 50, 40.0)
+        assert relerr(kf_d["A"], kf_o["A"]) < 1e-9
+        assert np.max(np.abs(kf_d["Sigma"] - kf_o["Sigma"])) < 1e-9 * np.max(np.abs(kf_o["Sigma"]))
+        co = orc.Ode_Coarse_Slicer(o_ode, 50)
+        dev = rng.standard_normal((41, 3)) * 30.0
+        dev[:, 2] = -dev[:, 0] - dev[:, 1]           # stay on the conserved-population plane
+        dev[0] = 0
+        sde = co.copy()
+        sde[:, 1:] += dev
+        l_o = orc.log_like_trajSIRS(sde, co, kf_o, 50, 90.0)
+        l_d = api.log_like_trajSIRS(sde, co, kf_o, 50, 90.0)
+        assert np.isfinite(l_o) and l_d == pytest.approx(l_o, rel=1e-7)
