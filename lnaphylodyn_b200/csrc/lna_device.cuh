@@ -18,6 +18,12 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef LNA_UNROLL
+#define LNA_UNROLL 2  // fine steps unrolled in the time loop
+#endif
+#define LNA_DO_PRAGMA_(x) _Pragma(#x)
+#define LNA_DO_PRAGMA(x) LNA_DO_PRAGMA_(x)
+
 namespace lna {
 
 constexpr double kSentinel = -10000000.0;
@@ -240,7 +246,7 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
         auto run = [&](const double dts, const int run_end) {
             const double c1 = fma(-dts, gam, 1.0);        // 1 - gam dts
             const double c2 = fma(-2.0 * dts, gam, 1.0);  // 1 - 2 gam dts
-#pragma unroll 2
+            LNA_DO_PRAGMA(unroll LNA_UNROLL)
             for (; s < run_end; ++s) {
                 const double bI = beta * I, bS = beta * S;
                 const double a1 = bS * I;   // h0 = beta*S*I
@@ -272,10 +278,20 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
                 const double a3 = fma(-hb, a2, bS) * I3;
                 const double I4 = fma(h2, a3, fma(-hg, I3, I));
                 const double a4 = fma(-hb, a3, bS) * I4;
+#ifdef LNA_SHORT_CHAIN
+                // latency variant: everything except the a4 terms is ready when a4 arrives
+                const double QA3 = fma(2.0, a2 + a3, a1);
+                const double PI = fma(2.0, I2 + I3, I) + I4;
+                const double Sp = fma(-dt6, QA3, S);
+                const double Ip = fma(-dg6, PI, fma(dt6, QA3, I));
+                S = fma(-dt6, a4, Sp);
+                I = fma(dt6, a4, Ip);
+#else
                 const double QA = fma(2.0, a2 + a3, a1) + a4;
                 const double PI = fma(2.0, I2 + I3, I) + I4;
                 S = fma(-dt6, QA, S);
                 I = fma(-dg6, PI, fma(dt6, QA, I));
+#endif
             }
         };
         while (s < s_end) {

@@ -418,11 +418,10 @@ struct CommitArgs {
 };
 
 __global__ void k_commit_fields(long long B, CommitArgs a) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int per = 2 * a.nA + 2 * a.nOde + a.nBeta;
-    if (idx >= B * per) return;
-    const long long c = idx % B;
-    int e = (int)(idx / B);
+    // grid.y = element, grid.x covers the chains: no 64-bit div/mod per thread
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    int e = blockIdx.y;
     const int slot = a.win_slot[c];
     if (slot < 0) return;
     if (e < a.nA) {

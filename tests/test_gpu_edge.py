@@ -1,0 +1,137 @@
+"""Edge cases of the GPU path against the oracle: no change points (constant R0), change points off the
+coarse grid, other grid sizes (k > 32 rows per warp pass, k > 64 = shared-memory dt table path),
+single-item and empty batches, non-uniform tail of the time grid."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from lnaphylodyn_b200 import genealogy as gen
+from oracle import driver
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def api():
+    import lnaphylodyn_b200 as m
+    from lnaphylodyn_b200 import _lib
+    assert _lib.lib().lna_device_count() > 0
+    return m.api
+
+
+def make_init(g, times, gridsize):
+    a = {k: g.setting("Init.args." + k) for k in ("samp_times", "n_sampled", "coal_times")}
+    return gen.coal_lik_init(a["samp_times"], a["n_sampled"], a["coal_times"], times[::gridsize])
+
+
+def compare(api, times, x_r, x_i, init, gridsize, t_correct, param, initial, eps):
+    pb = api.problem_for(times, x_r, x_i, gridsize, t_correct, init)
+    res = pb.full_loglik(param, initial, eps, want=("coalLog", "FT", "Ode", "betaN", "LatentTraj"))
+    cfg, ini = orc.Cfg(x_r, x_i, param.shape[1]), orc.Init(init)
+    nok = 0
+    for b in range(param.shape[0]):
+        o = orc.full_loglik(cfg, ini, param[b], initial[b], times, gridsize, eps[b], t_correct)
+        assert o["status"] == res["status"][b]
+        assert relerr(res["Ode"][b], o["Ode"]) < TOL and relerr(res["betaN"][b], o["betaN"]) < TOL
+        assert relerr(res["FT"]["A"][b], o["FT"]["A"]) < 1e-9
+        assert np.max(np.abs(res["LatentTraj"][b][:, 1:] - o["LatentTraj"][:, 1:]) /
+                      np.maximum(np.abs(o["LatentTraj"][:, 1:]), 1.0)) < TOL
+        if o["coalLog"] == orc.SENTINEL:
+            assert res["coalLog"][b] == orc.SENTINEL
+        else:
+            nok += 1
+            assert res["coalLog"][b] == pytest.approx(o["coalLog"], rel=TOL)
+    assert nok >= param.shape[0] // 4
+    return pb, res
+
+
+def draws(rng, B, nch, k, eps_scale=0.2):
+    param = np.empty((B, 2 + nch + 1))
+    param[:, 0] = 2.2 * np.exp(0.05 * rng.standard_normal(B))
+    param[:, 1] = 0.2 * np.exp(0.05 * rng.standard_normal(B))
+    param[:, 2:2 + nch] = np.exp(0.03 * rng.standard_normal((B, nch)))
+    param[:, -1] = 20.0
+    eps = eps_scale * rng.standard_normal((B, k, 2))
+    eps[:, : k // 3] = np.abs(eps[:, : k // 3])
+    return param, np.tile([1e6, 1.0], (B, 1)), eps
+
+
+def test_constant_R0_no_change_points(api, changepoint):
+    """BASELINE.json: 'the constant-R0 SIR problem' -- x_i = (0, 2, 0, 1), param = (R0, gamma, hyper)."""
+    g = changepoint
+    rng = np.random.default_rng(1)
+    param, initial, eps = draws(rng, 24, 0, 40)
+    x_r, x_i = [1e6], [0, 2, 0, 1]
+    compare(api, g.times, x_r, x_i, g.init, 50, g.t_correct, param, initial, eps)
+    # parameter ESS without change points (rotates R0 and hyper only)
+    par = np.concatenate([[1e6, 1.0], param[0]])
+    st = orc.full_loglik(orc.Cfg(x_r, x_i, 3), orc.Init(g.init), par[2:], par[:2], g.times, 50, eps[0], g.t_correct)
+    opts = driver.opts_from_golden(g)
+    B = 16
+    nrm, unf = rng.standard_normal((B, 4)), rng.random((B, 22))
+    d = api.ESlice_par_General(np.tile(par, (B, 1)), g.times, eps[0], opts["priorList"], x_r, x_i, g.init, 50,
+                               opts["ESS_vec"], st["coalLog"], g.t_correct, normals=nrm, uniforms=unf)
+    for b in range(B):
+        o = orc.ESlice_par_General(par, g.times, eps[0], opts["priorList"], x_r, x_i, g.init, 50, opts["ESS_vec"],
+                                   st["coalLog"], g.t_correct, normals=nrm[b], uniforms=unf[b])
+        assert d["n_evals"][b] == o["n_evals"] and relerr(d["par"][b], o["par"]) < TOL
+        assert d["CoalLog"][b] == pytest.approx(o["CoalLog"], rel=TOL)
+
+
+def test_change_points_off_the_coarse_grid(api, changepoint):
+    g = changepoint
+    rng = np.random.default_rng(2)
+    cht = np.array([0.0, 3.33, 13.37, 13.38, 55.5, 55.55, 77.025, 99.99, 100.0, 250.0])
+    param, initial, eps = draws(rng, 24, len(cht), 40)
+    param[:, 2:2 + len(cht)] = np.exp(0.3 * rng.standard_normal((24, len(cht))))
+    compare(api, g.times, np.concatenate([[1e6], cht]), [len(cht), 2, 0, 1], g.init, 50, g.t_correct, param, initial, eps)
+
+
+@pytest.mark.parametrize("gridsize", [40, 20, 100])
+def test_other_grid_sizes(api, changepoint, gridsize):
+    """k = 50 (two lane passes in the trajectory kernel), k = 100 (> 64: per-interval dt from shared memory),
+    k = 20."""
+    g = changepoint
+    rng = np.random.default_rng(3 + gridsize)
+    k = 2000 // gridsize
+    init = make_init(g, g.times, gridsize)
+    cht = g.times[::gridsize][1:-1][:: max(1, k // 10)]
+    param, initial, eps = draws(rng, 16, len(cht), k, eps_scale=0.2 * np.sqrt(gridsize / 50))
+    x_r, x_i = np.concatenate([[1e6], cht]), [len(cht), 2, 0, 1]
+    pb, res = compare(api, g.times, x_r, x_i, init, gridsize, g.t_correct, param, initial, eps)
+    # trajectory ESS on this grid
+    ok = np.nonzero(res["coalLog"] != orc.SENTINEL)[0][:6]
+    nrm, unf = rng.standard_normal((len(ok), k * 2)), rng.random((len(ok), 22))
+    d = api.ESlice_general_NC(eps[ok], res["Ode"][ok], {"A": res["FT"]["A"][ok], "Sigma": res["FT"]["Sigma"][ok]},
+                              initial[0], init, res["betaN"][ok], g.t_correct, 1.0, res["coalLog"][ok], gridsize, True,
+                              "SIR", normals=nrm, uniforms=unf)
+    for j, b in enumerate(ok):
+        o = orc.ESlice_general_NC(eps[b], res["Ode"][b], {"A": res["FT"]["A"][b], "Sigma": res["FT"]["Sigma"][b]},
+                                  initial[0], init, res["betaN"][b], g.t_correct, 1.0, res["coalLog"][b], gridsize, True,
+                                  "SIR", normals=nrm[j], uniforms=unf[j])
+        assert d["n_evals"][j] == o["n_evals"], (gridsize, j)
+        assert d["CoalLog"][j] == pytest.approx(o["CoalLog"], rel=1e-9)
+        assert np.max(np.abs(d["OriginTraj"][j] - o["OriginTraj"])) < 1e-11
+
+
+def test_single_item_and_empty_batch(api, changepoint):
+    import ctypes as C
+    from lnaphylodyn_b200 import _lib
+    g = changepoint
+    par = g.final["par"].ravel()
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    r1 = pb.full_loglik(par[2:], par[:2], g.final["OriginTraj"])
+    rB = pb.full_loglik(np.tile(par[2:], (3, 1)), np.tile(par[:2], (3, 1)), np.tile(g.final["OriginTraj"], (3, 1, 1)))
+    assert r1["coalLog"] == rB["coalLog"][0] == rB["coalLog"][2]
+    assert _lib.lib().lna_full_loglik(pb.h, 0, None, None, None, None, None, None, None, None, None, None) == 0
+    # errors are loud and descriptive
+    pb2 = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, None)
+    with pytest.raises(_lib.LnaError, match="without a genealogy"):
+        pb2.full_loglik(par[2:], par[:2], g.final["OriginTraj"])
+    with pytest.raises(_lib.LnaError, match="multiple of gridsize"):
+        api.Problem(g.times[:-1], g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    with pytest.raises(_lib.LnaError, match="ESS_vec"):
+        api.ESlice_par_General(par, g.times, g.final["OriginTraj"], [[1, 1]] * 4, g.x_r, g.x_i, g.init, 50,
+                               [0, 1, 0, 0, 1, 1, 1], 0.0, g.t_correct, normals=np.zeros(43), uniforms=np.full(22, 0.5))
