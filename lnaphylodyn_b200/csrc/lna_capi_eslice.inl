@@ -56,14 +56,25 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, nthreads);
     const unsigned grid = nblk(nthreads, block);
 #define LC(WW) k_cand_eval<kProp, WW><<<grid, block, pb->tab_bytes, pb->stream>>>(P, pb->seg, nchains, a)
-    switch (W) {
-        case 1: LC(1); break;
-        case 2: LC(2); break;
-        case 4: LC(4); break;
-        case 8: LC(8); break;
-        case 16: LC(16); break;
-        case 32: LC(32); break;
-        default: return fail("speculation width must be 1,2,4,8,16 or 32 (got %d)", W);
+    // only the (proposal, width) pairs that exist are instantiated: MH kinds are one lane per chain,
+    // the MH pair uses 4, the slice kinds any power of two
+    constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
+    if constexpr (kIsEss) {
+        switch (W) {
+            case 1: LC(1); break;
+            case 2: LC(2); break;
+            case 4: LC(4); break;
+            case 8: LC(8); break;
+            case 16: LC(16); break;
+            case 32: LC(32); break;
+            default: return fail("speculation width must be 1,2,4,8,16 or 32 (got %d)", W);
+        }
+    } else if constexpr (kProp == PROP_MH_PAIR) {
+        if (W != 4) return fail("the MH pair kernel uses 4 lanes per chain");
+        LC(4);
+    } else {
+        if (W != 1) return fail("Metropolis kernels use one lane per chain");
+        LC(1);
     }
 #undef LC
     return launch_check(pb, "k_cand_eval");
