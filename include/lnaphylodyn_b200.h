@@ -176,8 +176,10 @@ int lna_param_slice_update_all2(lna_problem *pb, int64_t B, const double *par_ol
  * (npar = 2 + npt); normals: B x (npar-1); uniforms: B x LNA_ESLICE_MAX_UNIF (u, theta draws).
  * prior8 = (priorList[[1]][1:2], ..., priorList[[4]][1:2]); ESS_vec7[6] must be 0.
  * The candidates theta_1..theta_20 depend only on the uniforms, so they are evaluated
- * speculatively, `spec_width` (1,2,4,8,16,32; 0 = auto) per wave, and the first one with
- * loglike > logy is taken: identical to the sequential loop.  n_evals[b] = evaluations the
+ * speculatively, `spec_width` (1,2,4,8,16,32) per in-kernel wave, and the first one with loglike > logy
+ * is taken: identical to the sequential loop.  spec_width = 0 picks a phase plan from the batch size
+ * (lanes per chain that fill the machine, with the still-unresolved chains compacted between phases);
+ * a negative value -w forces the plan the automatic policy uses when w lanes per chain fill the machine.  n_evals[b] = evaluations the
  * sequential loop would have made (1 + shrinks). */
 int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *par_old, const double *OriginTraj,
                            const double *prior8, const int32_t *ESS_vec7, const double *coal_log,

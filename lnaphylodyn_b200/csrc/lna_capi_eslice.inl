@@ -29,8 +29,8 @@ static bool cand_alloc(lna_problem *pb, Scratch &s, size_t base, long long B, lo
     cb.accept = (int *)s.get(base + 8, sizeof(int) * B);
     cb.cand_ll = (double *)s.get(base + 9, sizeof(double) * B);
     cb.theta = (double *)s.get(base + 10, sizeof(double) * B);
-    cb.list = (int *)s.get(base + 11, sizeof(int) * B);
-    cb.count = (int *)s.get(base + 12, sizeof(int) * 4);
+    cb.list = (int *)s.get(base + 11, sizeof(int) * B * 2);
+    cb.count = (int *)s.get(base + 12, sizeof(int) * 24);
     return cb.list && cb.count && cb.cA && cb.cL && cb.cOde && cb.cBeta && cb.cLat && cb.win_slot && cb.n_evals && cb.status && cb.accept &&
            cb.cand_ll && cb.theta;
 }
@@ -80,10 +80,50 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     return launch_check(pb, "k_cand_eval");
 }
 
-// W > 0: one launch, in-kernel waves of W candidates.  W == 0 (auto): width chosen to fill the machine;
-// when that width is 16 the slice runs in two phases -- candidates 1..8 for every chain, then candidates
-// 9..21 (+ the revert candidate) 16-wide for the compacted list of chains still unresolved -- so that
-// no wave is dominated by idle speculative lanes.
+// Phase plan of a slice update.  Candidates are evaluated speculatively W lanes per chain; after
+// `waves` in-kernel waves the chains that are still unresolved are compacted into a dense list for the
+// next phase, so no launch is dominated by idle lanes of chains that already finished.  (The number
+// of candidates a chain needs is bell-shaped around ~10 for the vignette problems: tools/eslice_hist.py.)
+struct SlicePhase {
+    int W, first, waves;  // lanes per chain, candidates already covered, in-kernel waves (0 = until resolved)
+};
+
+static int slice_plan(const lna_problem *pb, long long B, int W, SlicePhase *ph) {
+    if (W > 0) {  // explicit width: one launch, in-kernel waves
+        ph[0] = {W, 0, 0};
+        return 1;
+    }
+    const int Wa = W < 0 ? -W : auto_width(pb, B);  // W < 0 forces the plan of machine-filling width -W (tests)
+    switch (Wa) {
+        case 32: ph[0] = {32, 0, 0}; return 1;                      // all 21 candidates in one wave
+        case 16: ph[0] = {8, 0, 1}; ph[1] = {16, 8, 0}; return 2;   // 1-8, then 9-21 for the unresolved
+        case 8: ph[0] = {8, 0, 1}; ph[1] = {8, 8, 1}; ph[2] = {8, 16, 0}; return 3;
+        case 4: ph[0] = {4, 0, 2}; ph[1] = {4, 8, 2}; ph[2] = {4, 16, 0}; return 3;
+        // With the machine full at <= 2 lanes per chain the early phases are throughput-bound; once most
+        // chains are resolved the launches sit on the single-evaluation latency floor, so the tail widens.
+        case 2: ph[0] = {2, 0, 2}; ph[1] = {2, 4, 2}; ph[2] = {2, 8, 2}; ph[3] = {4, 12, 1}; ph[4] = {8, 16, 0}; return 5;
+        default: {
+            int n = 0;
+            for (int f = 0; f < 12; f += 2) ph[n++] = {1, f, 2};  // candidates 1..12, compaction every 2
+            ph[n++] = {2, 12, 1};
+            ph[n++] = {2, 14, 1};
+            ph[n++] = {4, 16, 1};
+            ph[n++] = {4, 20, 0};
+            return n;
+        }
+    }
+}
+
+// scratch slots per chain needed by the plan (every phase keeps its own slot range so that a later
+// phase never overwrites the winner of an earlier one)
+static int slice_plan_slots(const lna_problem *pb, long long B, int W) {
+    SlicePhase ph[24];
+    const int n = slice_plan(pb, B, W, ph);
+    int tot = 0;
+    for (int i = 0; i < n; ++i) tot += ph[i].W;
+    return std::max(tot, 4);
+}
+
 template <int kProp>
 static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, const CandBuf &cb) {
     CandArgs a = a0;
@@ -95,18 +135,24 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, 
     a.next_list = cb.list;
     a.next_count = cb.count;
     constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
-    if (!kIsEss || W > 0) return launch_cand_one<kProp>(pb, B, W > 0 ? W : 1, a);
-    const int Wa = auto_width(pb, B);
-    if (Wa != 16 && W != -2) return launch_cand_one<kProp>(pb, B, Wa, a);  // W == -2 forces the two-phase path
-    if (cudaMemsetAsync(cb.count, 0, sizeof(int) * 4, pb->stream) != cudaSuccess) return fail("memset failed");
-    a.max_waves = 1;
-    if (launch_cand_one<kProp>(pb, B, 8, a)) return -1;
-    a.first_cand = 8;
-    a.slot_base = B * 8;
-    a.max_waves = 0;
-    a.chain_list = cb.list;
-    a.n_list = cb.count;
-    return launch_cand_one<kProp>(pb, B, 16, a);
+    if (!kIsEss) return launch_cand_one<kProp>(pb, B, W > 0 ? W : 1, a);
+    SlicePhase ph[24];
+    const int nph = slice_plan(pb, B, W, ph);
+    if (nph > 1 && cudaMemsetAsync(cb.count, 0, sizeof(int) * 24, pb->stream) != cudaSuccess)
+        return fail("memset failed");
+    long long slot = 0;
+    for (int i = 0; i < nph; ++i) {
+        a.first_cand = ph[i].first;
+        a.max_waves = ph[i].waves;
+        a.slot_base = slot;
+        a.chain_list = i == 0 ? nullptr : cb.list + (size_t)((i - 1) & 1) * B;  // ping-pong compaction lists
+        a.n_list = i == 0 ? nullptr : cb.count + (i - 1);
+        a.next_list = cb.list + (size_t)(i & 1) * B;
+        a.next_count = cb.count + i;
+        if (launch_cand_one<kProp>(pb, B, ph[i].W, a)) return -1;
+        slot += B * ph[i].W;
+    }
+    return 0;
 }
 
 static int launch_commit_fields(lna_problem *pb, long long B, const CandBuf &cb, OutView A, OutView L, OutView ode,
@@ -211,7 +257,7 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
     double *dO = s.tmp<double>(nB * nO), *dbn = s.tmp<double>(nB * nrow), *dlat = s.tmp<double>(nB * nO);
     double *dlo = s.tmp<double>(nB), *dcl = s.tmp<double>(nB);
     CandBuf cb;
-    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * std::max(W > 0 ? W : auto_width(pb, B), 24), cb)) return fail("lna_eslice_par_general: device staging failed");
+    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * slice_plan_slots(pb, B, W), cb)) return fail("lna_eslice_par_general: device staging failed");
     a.cand = cand_out(cb);
     a.win_slot = cb.win_slot;
     a.cand_ll = cb.cand_ll;
@@ -272,7 +318,7 @@ extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double
     double *dO = s.tmp<double>(nB * nO), *dbn = s.tmp<double>(nB * nrow), *dlat = s.tmp<double>(nB * nO);
     double *dlcp = s.tmp<double>(nB), *dcl = s.tmp<double>(nB);
     CandBuf cb;
-    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * std::max(W > 0 ? W : auto_width(pb, B), 24), cb))
+    if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * slice_plan_slots(pb, B, W), cb))
         return fail("lna_eslice_change_points: device staging failed");
     // the host vector must outlive the async copy
     if (cudaStreamSynchronize(pb->stream) != cudaSuccess) return fail("lna_eslice_change_points: sync failed");
@@ -609,7 +655,7 @@ static void chains_base_args(lna_chains *ch, View normals, View uniforms, CandAr
 static int chains_ensure_scratch(lna_chains *ch, int W) {
     lna_problem *pb = ch->pb;
     const long long B = ch->B;
-    const int Wmax = std::max(W > 0 ? W : auto_width(pb, B), 24);  // two-phase: 8 + 16 slots per chain
+    const int Wmax = slice_plan_slots(pb, B, W);
     if (ch->cb.NC < B * Wmax || ch->cb.B != B) {
         if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * Wmax, ch->cb))
             return fail("lna_chains_step: candidate scratch allocation failed");
@@ -686,10 +732,16 @@ extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const
     a.gamma_prior[0] = o->gamma_prior[0];
     a.gamma_prior[1] = o->gamma_prior[1];
     a.gamma_prop = o->gamma_prop;
-    if (o->hyper_noop_mh) {  // both MH entries speculatively in one latency period
+    if (o->hyper_noop_mh && ch->B * 4 <= (long long)pb->sm_count * 512) {
+        // few chains: both MH entries speculatively in one latency period (3 evaluations per chain)
         if (chains_stage<PROP_MH_PAIR>(ch, a, 4)) return -1;
-    } else if (chains_stage<PROP_GAMMA_RW>(ch, a, 1)) {
-        return -1;
+    } else {
+        // many chains: the machine is full anyway, so evaluate only what is consumed (2 per chain)
+        if (chains_stage<PROP_GAMMA_RW>(ch, a, 1)) return -1;
+        if (o->hyper_noop_mh) {
+            chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 2, su, 1}, a);
+            if (chains_stage<PROP_HYPER_NOOP>(ch, a, 1)) return -1;
+        }
     }
     // 2. update_Par_ESlice_combine -> ESlice_par_General
     chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 3, su, 1}, a);

@@ -96,6 +96,26 @@ def test_eslice_par_general_two_phase_window(api, changepoint):
         assert d2["CoalLog"][b] == pytest.approx(o["CoalLog"], rel=TOL)
 
 
+@pytest.mark.parametrize("plan", [-8, -4, -2, -1])
+def test_eslice_phase_plans_equal_sequential(api, changepoint, plan):
+    """Every automatic phase plan (compaction between phases, several in-kernel waves per phase) must give the
+    chains of the plain one-candidate-at-a-time evaluation, bit for bit."""
+    g = changepoint
+    st = state_of(g)
+    opts = driver.opts_from_golden(g)
+    B = 700
+    rng = np.random.default_rng(303)
+    nrm, unf = rng.standard_normal((B, 43)), rng.random((B, 22))
+    unf[:20, 0] = 1.0 - 1e-9 * rng.random(20)
+    call = lambda w: api.ESlice_par_General(np.tile(st["par"], (B, 1)), g.times, st["OriginTraj"], opts["priorList"],
+                                            g.x_r, g.x_i, g.init, g.gridsize, opts["ESS_vec"], st["coalLog"],
+                                            g.t_correct, normals=nrm, uniforms=unf, spec_width=w)
+    d, ref = call(plan), call(1)
+    for k in ("n_evals", "status", "par", "CoalLog", "LatentTraj", "betaN"):
+        assert np.array_equal(d[k], ref[k]), k
+    assert np.array_equal(d["FT"]["A"], ref["FT"]["A"]) and (ref["status"] & 8).sum() >= 1
+
+
 def test_eslice_general_nc_step_for_step(api, changepoint):
     g = changepoint
     st = state_of(g)

@@ -11,7 +11,7 @@ iters = 10
 g = Golden("changepoint_sim")
 par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"), g.setting("control.hyper")])
 dev = torch.device("cuda", 0)
-for W in (0, -2):
+for W in (0, -16):
   for G in (1, 2, 4, 8):
     Bg = B // G
     pbs = [api.Problem(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init) for _ in range(G)]
