@@ -94,6 +94,11 @@ struct lna_problem {
     int64_t launches = 0;
     size_t tab_bytes = 0;
     // host-buffer pipeline: inputs of chunk i+1 are copied on `copy_stream` while chunk i computes
+    // what lna_problem_create was given (host copies), so that stream-group clones can be made
+    lna_problem *parent = nullptr;
+    lna_cfg cfg{};
+    std::vector<double> iC, iD, iy, igridrep;
+    int iE = 0, ing = 0, has_init = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[8] = {};
     cudaEvent_t done_ev = nullptr;
@@ -195,6 +200,16 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     P.t_correct = cfg->t_correct;
     pb->times.assign(cfg->times, cfg->times + cfg->nt);
     pb->x_r.assign(cfg->x_r, cfg->x_r + cfg->nch + 1);
+    pb->cfg = *cfg;
+    if (init && init->C && init->D && init->y && init->gridrep && init->E >= 0 && init->ng >= 1) {
+        pb->iC.assign(init->C, init->C + init->E);
+        pb->iD.assign(init->D, init->D + init->E);
+        pb->iy.assign(init->y, init->y + init->E);
+        pb->igridrep.assign(init->gridrep, init->gridrep + init->ng);
+        pb->iE = init->E;
+        pb->ing = init->ng;
+        pb->has_init = 1;
+    }
     P.dt_ode = pb->times[1] - pb->times[0];
     P.h2 = 0.5 * P.dt_ode;
     P.dt6 = P.dt_ode / 6.0;
@@ -298,6 +313,17 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     return pb;
 }
 
+// a second problem on the same device with the same settings and genealogy but its own stream and scratch
+static lna_problem *problem_clone(lna_problem *src) {
+    lna_cfg c = src->cfg;
+    c.times = src->times.data();
+    c.x_r = src->x_r.data();
+    lna_init ini{src->iE, src->ing, src->iC.data(), src->iD.data(), src->iy.data(), src->igridrep.data()};
+    lna_problem *pb = lna_problem_create(&c, src->has_init ? &ini : nullptr, src->device);
+    if (pb) pb->parent = src;
+    return pb;
+}
+
 extern "C" void lna_problem_destroy(lna_problem *pb) {
     if (!pb) return;
     cudaSetDevice(pb->device);
@@ -393,6 +419,7 @@ struct Stage {
 
 static int launch_check(lna_problem *pb, const char *what) {
     pb->launches++;
+    if (pb->parent) pb->parent->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
     return 0;

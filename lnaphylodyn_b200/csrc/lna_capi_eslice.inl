@@ -125,7 +125,9 @@ static int slice_plan_slots(const lna_problem *pb, long long B, int W) {
 }
 
 template <int kProp>
-static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, const CandBuf &cb) {
+static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, const CandBuf &cb,
+                       long long planB = 0) {
+    if (planB <= 0) planB = B;
     CandArgs a = a0;
     a.first_cand = 0;
     a.slot_base = 0;
@@ -137,7 +139,7 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, 
     constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
     if (!kIsEss) return launch_cand_one<kProp>(pb, B, W > 0 ? W : 1, a);
     SlicePhase ph[24];
-    const int nph = slice_plan(pb, B, W, ph);
+    const int nph = slice_plan(pb, planB, W, ph);
     if (nph > 1 && cudaMemsetAsync(cb.count, 0, sizeof(int) * 24, pb->stream) != cudaSuccess)
         return fail("memset failed");
     long long slot = 0;
@@ -509,9 +511,10 @@ extern "C" int lna_eslice_general2(lna_problem *pb, int64_t B, const double *f_c
 // ------------------------------------------------------------------------------------------------
 // resident chain batches
 // ------------------------------------------------------------------------------------------------
-struct lna_chains {
-    lna_problem *pb = nullptr;
+struct ChainPart {  // one stream-group of a resident chain batch
+    lna_problem *pb = nullptr;  // this group's problem (own stream + scratch); == the user's problem when G == 1
     long long B = 0;
+    long long planB = 0;  // chain count of the WHOLE batch: phase plans and policies are chosen for it
     int W = 1;
     // slot-major state: field[j*B + c]
     double *par = nullptr, *par_alt = nullptr, *origin = nullptr, *A = nullptr, *L = nullptr, *ode = nullptr, *betaN = nullptr,
@@ -547,15 +550,17 @@ __global__ void k_summary(long long B, const double *coalLog, const double *logO
     summary[c * 4 + 3] = (double)counters[3 * B + c];
 }
 
+static void part_destroy(ChainPart *ch);
+
 template <class T>
-static T *chains_alloc(lna_chains *ch, size_t n) {
+static T *chains_alloc(ChainPart *ch, size_t n) {
     T *d = nullptr;
     if (cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
     ch->owned.push_back(d);
     return d;
 }
 
-extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
+static ChainPart *part_create(lna_problem *pb, int64_t B, int64_t planB, double *summary) {
     if (!pb || B <= 0) {
         fail("lna_chains_create: bad arguments");
         return nullptr;
@@ -563,9 +568,10 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     if (check_sir_sampler(pb, "lna_chains_create")) return nullptr;
     cudaSetDevice(pb->device);
     const DevProb &P = pb->dp;
-    lna_chains *ch = new lna_chains();
+    ChainPart *ch = new ChainPart();
     ch->pb = pb;
     ch->B = B;
+    ch->planB = planB;
     const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
     const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
     ch->par = chains_alloc<double>(ch, nB * npar);
@@ -578,7 +584,7 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     ch->latent = chains_alloc<double>(ch, nB * nO);
     ch->coalLog = chains_alloc<double>(ch, nB);
     ch->logOrigin = chains_alloc<double>(ch, nB);
-    ch->summary = chains_alloc<double>(ch, nB * 4);
+    ch->summary = summary;  // slice of the batch's contiguous summary block (owned by lna_chains)
     ch->counters = chains_alloc<int>(ch, nB * 4);
     ch->tmp_i = chains_alloc<int>(ch, nB * 2);
     ch->tmp_d = chains_alloc<double>(ch, nB);
@@ -588,16 +594,16 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     ch->stage_n = chains_alloc<double>(ch, nB * ch->n_norm);
     ch->stage_u = chains_alloc<double>(ch, nB * stage_unif);
     if (!ch->par || !ch->par_alt || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
-        !ch->logOrigin || !ch->summary || !ch->counters || !ch->tmp_i || !ch->tmp_d || !ch->stage_n || !ch->stage_u) {
+        !ch->logOrigin || !ch->counters || !ch->tmp_i || !ch->tmp_d || !ch->stage_n || !ch->stage_u) {
         fail("lna_chains_create: device allocation failed");
-        lna_chains_destroy(ch);
+        part_destroy(ch);
         return nullptr;
     }
     cudaMemsetAsync(ch->counters, 0, sizeof(int) * nB * 4, pb->stream);
     return ch;
 }
 
-extern "C" void lna_chains_destroy(lna_chains *ch) {
+static void part_destroy(ChainPart *ch) {
     if (!ch) return;
     cudaSetDevice(ch->pb->device);
     cudaStreamSynchronize(ch->pb->stream);
@@ -609,7 +615,7 @@ extern "C" void lna_chains_destroy(lna_chains *ch) {
 static View soa_view(const double *d, long long B) { return View{d, 1, B}; }
 static OutView soa_out(double *d, long long B) { return OutView{d, 1, B}; }
 
-extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *OriginTraj) {
+static int part_init(ChainPart *ch, const double *par, const double *OriginTraj) {
     if (!ch || !par || !OriginTraj) return fail("lna_chains_init: null argument");
     lna_problem *pb = ch->pb;
     const DevProb &P = pb->dp;
@@ -635,7 +641,7 @@ extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *
 }
 
 // candidate-evaluation arguments common to every stage of the resident chains
-static void chains_base_args(lna_chains *ch, View normals, View uniforms, CandArgs &a) {
+static void chains_base_args(ChainPart *ch, View normals, View uniforms, CandArgs &a) {
     const long long B = ch->B;
     a = CandArgs{};
     a.par = soa_view(ch->par, B);
@@ -652,10 +658,10 @@ static void chains_base_args(lna_chains *ch, View normals, View uniforms, CandAr
     a.accept = ch->cb.accept;
 }
 
-static int chains_ensure_scratch(lna_chains *ch, int W) {
+static int chains_ensure_scratch(ChainPart *ch, int W) {
     lna_problem *pb = ch->pb;
     const long long B = ch->B;
-    const int Wmax = slice_plan_slots(pb, B, W);
+    const int Wmax = slice_plan_slots(pb, ch->planB, W);
     if (ch->cb.NC < B * Wmax || ch->cb.B != B) {
         if (!cand_alloc(pb, ch->cand_scratch, 0, B, B * Wmax, ch->cb))
             return fail("lna_chains_step: candidate scratch allocation failed");
@@ -665,11 +671,11 @@ static int chains_ensure_scratch(lna_chains *ch, int W) {
 
 // evaluate the proposals of one stage, copy the winners into the state, bump the counters
 template <int kProp>
-static int chains_stage(lna_chains *ch, const CandArgs &a, int W) {
+static int chains_stage(ChainPart *ch, const CandArgs &a, int W) {
     lna_problem *pb = ch->pb;
     const DevProb &P = pb->dp;
     const long long B = ch->B;
-    if (launch_cand<kProp>(pb, B, W, a, ch->cb)) return -1;
+    if (launch_cand<kProp>(pb, B, W, a, ch->cb, ch->planB)) return -1;
     if (launch_commit_fields(pb, B, ch->cb, soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B),
                              soa_out(ch->betaN, B), soa_out(ch->latent, B)))
         return -1;
@@ -684,7 +690,7 @@ static int chains_stage(lna_chains *ch, const CandArgs &a, int W) {
 }
 
 // updateTraj_general_NC -> ESlice_general_NC, in place on the state
-static int chains_traj(lna_chains *ch, View normals, View uniforms) {
+static int chains_traj(ChainPart *ch, View normals, View uniforms) {
     lna_problem *pb = ch->pb;
     const long long B = ch->B;
     TrajArgs a{};
@@ -708,14 +714,14 @@ static int chains_traj(lna_chains *ch, View normals, View uniforms) {
     return launch_check(pb, "k_bump");
 }
 
-static int chains_finish(lna_chains *ch) {
+static int chains_finish(ChainPart *ch) {
     lna_problem *pb = ch->pb;
     k_summary<<<nblk(ch->B, 256), 256, 0, pb->stream>>>(ch->B, ch->coalLog, ch->logOrigin, ch->counters, ch->summary);
     return launch_check(pb, "k_summary");
 }
 
 // General_MCMC_with_ESlice iteration body (R/LNA_chpt_slice.R:775-847)
-extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,
+static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *normals,
                                    const double *uniforms) {
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
     lna_problem *pb = ch->pb;
@@ -732,7 +738,7 @@ extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const
     a.gamma_prior[0] = o->gamma_prior[0];
     a.gamma_prior[1] = o->gamma_prior[1];
     a.gamma_prop = o->gamma_prop;
-    if (o->hyper_noop_mh && ch->B * 4 <= (long long)pb->sm_count * 512) {
+    if (o->hyper_noop_mh && ch->planB * 4 <= (long long)pb->sm_count * 512) {
         // few chains: both MH entries speculatively in one latency period (3 evaluations per chain)
         if (chains_stage<PROP_MH_PAIR>(ch, a, 4)) return -1;
     } else {
@@ -756,7 +762,7 @@ extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const
 }
 
 // General_MCMC2 iteration body (R/LNA_chpt_slice.R:576-691, stages i < burn1 and burn1 <= i < warmup2)
-extern "C" int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *o, const double *normals,
+static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const double *normals,
                                          const double *uniforms) {
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
     lna_problem *pb = ch->pb;
@@ -797,7 +803,7 @@ extern "C" int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *o
     return chains_finish(ch);
 }
 
-extern "C" int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *o, const double *normals,
+static int part_step_mcmc2(ChainPart *ch, const lna_mcmc2_opts *o, const double *normals,
                                      const double *uniforms) {
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
     lna_problem *pb = ch->pb;
@@ -807,10 +813,10 @@ extern "C" int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *o, co
     if (nn > ch->n_norm || (size_t)LNA_ITER2_UNIF > ch->n_unif + 8) return fail("lna_chains_step_mcmc2: staging too small");
     CK(cudaMemcpyAsync(ch->stage_n, normals, sizeof(double) * nB * nn, cudaMemcpyHostToDevice, pb->stream));
     CK(cudaMemcpyAsync(ch->stage_u, uniforms, sizeof(double) * nB * LNA_ITER2_UNIF, cudaMemcpyHostToDevice, pb->stream));
-    return lna_chains_step_mcmc2_dev(ch, o, ch->stage_n, ch->stage_u);
+    return part_step_mcmc2_dev(ch, o, ch->stage_n, ch->stage_u);
 }
 
-extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,
+static int part_step(ChainPart *ch, const lna_mcmc_opts *o, const double *normals,
                                const double *uniforms) {
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
     lna_problem *pb = ch->pb;
@@ -818,7 +824,7 @@ extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const dou
     const size_t nB = (size_t)ch->B;
     CK(cudaMemcpyAsync(ch->stage_n, normals, sizeof(double) * nB * ch->n_norm, cudaMemcpyHostToDevice, pb->stream));
     CK(cudaMemcpyAsync(ch->stage_u, uniforms, sizeof(double) * nB * ch->n_unif, cudaMemcpyHostToDevice, pb->stream));
-    return lna_chains_step_dev(ch, o, ch->stage_n, ch->stage_u);
+    return part_step_dev(ch, o, ch->stage_n, ch->stage_u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -846,7 +852,7 @@ extern "C" int lna_draw_streams(lna_problem *pb, int64_t B, int64_t chain_offset
     return s.finish("lna_draw_streams");
 }
 
-extern "C" int lna_chains_step_rng(lna_chains *ch, const lna_mcmc_opts *o, uint64_t seed, uint64_t iteration,
+static int part_step_rng(ChainPart *ch, const lna_mcmc_opts *o, uint64_t seed, uint64_t iteration,
                                    int64_t chain_offset) {
     if (!ch || !o) return fail("lna_chains_step_rng: null argument");
     lna_problem *pb = ch->pb;
@@ -854,10 +860,10 @@ extern "C" int lna_chains_step_rng(lna_chains *ch, const lna_mcmc_opts *o, uint6
     if (draw_streams_dev(pb, ch->B, chain_offset, (int)ch->n_norm, (int)ch->n_unif, seed, iteration, ch->stage_n,
                          ch->stage_u))
         return -1;
-    return lna_chains_step_dev(ch, o, ch->stage_n, ch->stage_u);
+    return part_step_dev(ch, o, ch->stage_n, ch->stage_u);
 }
 
-extern "C" int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
+static int part_get(ChainPart *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
                               double *logOrigin, int32_t *counters) {
     if (!ch) return fail("lna_chains_get: null chains");
     lna_problem *pb = ch->pb;
@@ -887,6 +893,174 @@ extern "C" int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, d
             for (int j = 0; j < 4; ++j) counters[c * 4 + j] = tmp[(size_t)j * nB + c];
     }
     return s.finish("lna_chains_get");
+}
+
+
+
+// ------------------------------------------------------------------------------------------------
+// public handle: a resident chain batch = G stream-groups of chains.  With many chains the late slice
+// phases and the Metropolis steps of one group sit on the single-evaluation latency floor; running two
+// groups on two streams lets one group's latency-bound launches overlap the other's throughput-bound ones
+// (measured +29 % at 65 536 chains, +35 % at 16 384, +5 % at 4096; tools/eslice_groups.py).
+// ------------------------------------------------------------------------------------------------
+struct lna_chains {
+    lna_problem *pb = nullptr;
+    long long B = 0;
+    int G = 1;
+    std::vector<lna_problem *> gpb;  // per-group problems (clones; gpb[0] == pb when G == 1)
+    std::vector<ChainPart *> part;
+    std::vector<long long> off;      // first chain of each group, off[G] = B
+    double *summary = nullptr;       // B x 4, contiguous over the groups
+    cudaEvent_t ev_in = nullptr;
+    std::vector<cudaEvent_t> ev_out;
+    size_t n_norm = 0, n_unif = 0, n_norm2 = 0;
+};
+
+// order the groups' streams after everything already enqueued on the user's stream ...
+static int chains_fork(lna_chains *ch) {
+    if (ch->G == 1) return 0;
+    CK(cudaEventRecord(ch->ev_in, ch->pb->stream));
+    for (int g = 0; g < ch->G; ++g) CK(cudaStreamWaitEvent(ch->gpb[g]->stream, ch->ev_in, 0));
+    return 0;
+}
+// ... and the user's stream after the groups
+static int chains_join(lna_chains *ch) {
+    if (ch->G == 1) return 0;
+    for (int g = 0; g < ch->G; ++g) {
+        CK(cudaEventRecord(ch->ev_out[g], ch->gpb[g]->stream));
+        CK(cudaStreamWaitEvent(ch->pb->stream, ch->ev_out[g], 0));
+    }
+    return 0;
+}
+
+extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
+    if (!pb || B <= 0) {
+        fail("lna_chains_create: bad arguments");
+        return nullptr;
+    }
+    if (check_sir_sampler(pb, "lna_chains_create")) return nullptr;
+    cudaSetDevice(pb->device);
+    lna_chains *ch = new lna_chains();
+    ch->pb = pb;
+    ch->B = B;
+    ch->G = B >= 2048 ? 2 : 1;
+    if (const char *e = getenv("LNA_CHAIN_GROUPS")) ch->G = std::max(1, std::min(8, atoi(e)));
+    if (ch->G > B) ch->G = 1;
+    const DevProb &P = pb->dp;
+    ch->n_norm = (size_t)(2 + P.npt - 1) + (size_t)P.k * P.p;
+    ch->n_unif = LNA_ITER_UNIF;
+    ch->n_norm2 = (size_t)P.nch + (size_t)P.k * P.p;
+    if (cudaMalloc(&ch->summary, sizeof(double) * 4 * (size_t)B) != cudaSuccess) {
+        fail("lna_chains_create: device allocation failed");
+        delete ch;
+        return nullptr;
+    }
+    cudaEventCreateWithFlags(&ch->ev_in, cudaEventDisableTiming);
+    ch->off.assign(ch->G + 1, 0);
+    for (int g = 0; g < ch->G; ++g) {
+        int64_t b0, b1;
+        lna_shard(B, g, ch->G, &b0, &b1);
+        ch->off[g] = b0;
+        ch->off[g + 1] = b1;
+        lna_problem *gp = ch->G == 1 ? pb : problem_clone(pb);
+        ChainPart *pt = gp ? part_create(gp, b1 - b0, B, ch->summary + 4 * b0) : nullptr;
+        if (!pt) {
+            if (gp && gp != pb) lna_problem_destroy(gp);
+            lna_chains_destroy(ch);
+            return nullptr;
+        }
+        ch->gpb.push_back(gp);
+        ch->part.push_back(pt);
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ch->ev_out.push_back(e);
+    }
+    return ch;
+}
+
+extern "C" void lna_chains_destroy(lna_chains *ch) {
+    if (!ch) return;
+    cudaSetDevice(ch->pb->device);
+    for (size_t g = 0; g < ch->part.size(); ++g) {
+        part_destroy(ch->part[g]);
+        if (ch->gpb[g] != ch->pb) lna_problem_destroy(ch->gpb[g]);
+    }
+    for (cudaEvent_t e : ch->ev_out) cudaEventDestroy(e);
+    if (ch->ev_in) cudaEventDestroy(ch->ev_in);
+    if (ch->summary) cudaFree(ch->summary);
+    delete ch;
+}
+
+extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *OriginTraj) {
+    if (!ch || !par || !OriginTraj) return fail("lna_chains_init: null argument");
+    const DevProb &P = ch->pb->dp;
+    const size_t npar = 2 + P.npt, kp = (size_t)P.k * P.p;
+    for (int g = 0; g < ch->G; ++g)
+        if (part_init(ch->part[g], par + ch->off[g] * npar, OriginTraj + ch->off[g] * kp)) return -1;
+    return 0;
+}
+
+extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,
+                                   const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
+    if (chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g)
+        if (part_step_dev(ch->part[g], o, normals + ch->off[g] * ch->n_norm, uniforms + ch->off[g] * ch->n_unif)) return -1;
+    return chains_join(ch);
+}
+
+extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const double *normals, const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
+    if (chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g)
+        if (part_step(ch->part[g], o, normals + ch->off[g] * ch->n_norm, uniforms + ch->off[g] * ch->n_unif)) return -1;
+    return chains_join(ch);
+}
+
+extern "C" int lna_chains_step_rng(lna_chains *ch, const lna_mcmc_opts *o, uint64_t seed, uint64_t iteration,
+                                   int64_t chain_offset) {
+    if (!ch || !o) return fail("lna_chains_step_rng: null argument");
+    if (chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g)
+        if (part_step_rng(ch->part[g], o, seed, iteration, chain_offset + ch->off[g])) return -1;
+    return chains_join(ch);
+}
+
+extern "C" int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *o, const double *normals,
+                                         const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
+    if (chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g)
+        if (part_step_mcmc2_dev(ch->part[g], o, normals + ch->off[g] * ch->n_norm2,
+                                uniforms + ch->off[g] * (size_t)LNA_ITER2_UNIF))
+            return -1;
+    return chains_join(ch);
+}
+
+extern "C" int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *o, const double *normals,
+                                     const double *uniforms) {
+    if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
+    if (chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g)
+        if (part_step_mcmc2(ch->part[g], o, normals + ch->off[g] * ch->n_norm2,
+                            uniforms + ch->off[g] * (size_t)LNA_ITER2_UNIF))
+            return -1;
+    return chains_join(ch);
+}
+
+extern "C" int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
+                              double *logOrigin, int32_t *counters) {
+    if (!ch) return fail("lna_chains_get: null chains");
+    const DevProb &P = ch->pb->dp;
+    const size_t npar = 2 + P.npt, kp = (size_t)P.k * P.p, nO = (size_t)P.nrow * (P.p + 1);
+    for (int g = 0; g < ch->G; ++g) {
+        const size_t o = (size_t)ch->off[g];
+        if (part_get(ch->part[g], par ? par + o * npar : nullptr, OriginTraj ? OriginTraj + o * kp : nullptr,
+                     LatentTraj ? LatentTraj + o * nO : nullptr, coalLog ? coalLog + o : nullptr,
+                     logOrigin ? logOrigin + o : nullptr, counters ? counters + o * 4 : nullptr))
+            return -1;
+    }
+    return 0;
 }
 
 extern "C" const double *lna_chains_summary_dev(lna_chains *ch) { return ch ? ch->summary : nullptr; }

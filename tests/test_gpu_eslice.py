@@ -287,3 +287,32 @@ def test_device_rng_streams_and_replay(api, changepoint):
             ref[c] = driver.eslice_iteration(ref[c], g, driver.opts_from_golden(g, update_traj=it >= 1), nrm[c], unf[c])
             assert relerr(s["par"][c], ref[c]["par"]) < TOL and s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL)
             assert s["n_full_evals"][c] == ref[c]["n_full"]
+
+
+def test_chain_stream_groups_equal_single_group(api, changepoint, monkeypatch):
+    """Batches of >= 2048 chains run as two stream groups (overlap of latency-bound and throughput-bound
+    launches): per chain the result must not depend on the grouping, and must match the oracle."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    B, iters = 2101, 3
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    grouped = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    monkeypatch.setenv("LNA_CHAIN_GROUPS", "1")
+    single = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    monkeypatch.delenv("LNA_CHAIN_GROUPS")
+    ref = {c: driver.init_state(g, par0, g.setting("control.traj")) for c in (0, 1049, 1050, 1051, 2100)}
+    for it in range(iters):
+        opts = chm.vignette_opts(g, update_traj=it >= 1)
+        nrm, unf = grouped.device_streams(seed=3, iteration=it)
+        grouped.step_rng(opts, seed=3, iteration=it)
+        single.step(opts, nrm, unf)
+        for c in ref:
+            ref[c] = driver.eslice_iteration(ref[c], g, driver.opts_from_golden(g, update_traj=it >= 1), nrm[c], unf[c])
+    a, b = grouped.get(), single.get()
+    for k in ("par", "OriginTraj", "LatentTraj", "coalLog", "logOrigin", "n_full_evals", "n_cheap_evals", "n_mh_accept"):
+        assert np.array_equal(a[k], b[k]), k
+    for c, r in ref.items():
+        assert relerr(a["par"][c], r["par"]) < TOL and a["coalLog"][c] == pytest.approx(r["coalLog"], rel=TOL)
+        assert a["n_full_evals"][c] == r["n_full"]
