@@ -12,9 +12,12 @@ line on rank 0.  Workload = BASELINE.json configs[1] (Changpoint_sim vignette: S
   eslice     : chain-iterations/s of the batched General_MCMC_with_ESlice iteration (when built)
   roofline   : algorithmic FP64 flops (113/fine step + 21/interval + 10/cell)
                over the measured independent-DFMA peak of this GPU
-  cpu_baseline: the CPU oracle (restated reference algorithm) on the host cores, bounded sample
+  cpu_baseline: the reference's CPU implementation on the host cores, bounded sample: the reference's own
+               sources compiled verbatim on stand-in Armadillo/Rcpp headers (oracle/_ref, kind "reference") when
+               that library is present, else the C restatement (kind "port")
 
-`--impl reference` times only the CPU oracle (the reference cannot be built here: no R/Rcpp/Armadillo).
+`--impl reference` times only that CPU arm (R/Rcpp/Armadillo are absent, so the reference's package build cannot
+run; its C++ sources compile as they are against oracle/shim/).
 """
 import argparse
 import json
@@ -67,8 +70,22 @@ def algorithmic_flops(g):
 # ------------------------------------------------------------------------------------------------
 # CPU oracle timing (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def time_oracle(g, n_per_thread, threads, seed=123):
+def cpu_impl():
+    """The CPU arm: the reference's own sources compiled verbatim (oracle/_ref/liblna_ref.so, kind "reference") when that
+    library is here, else the C restatement (kind "port").  Both live under oracle/ and are only ever timed/checked."""
+    from oracle import reference as ref
+    if ref.available():
+        return ref, "reference", ("reference code as written: /root/reference/src/LNA_functional.cpp (+ basic_util, SIR_LNA, "
+                                  "SIRS_period, SIR_phylodyn) compiled verbatim, g++ -O2, on the Armadillo/Rcpp stand-in "
+                                  "headers of oracle/shim/; each evaluation is one Update_Param call")
     from oracle import oracle as orc
+    return orc, "port", "CPU oracle = allocation-free C restatement of the reference algorithm, gcc -O2 -ffp-contract=off"
+
+
+def time_oracle(g, n_per_thread, threads, seed=123, impl=None):
+    if impl is None:
+        from oracle import oracle as impl
+    orc = impl
     cfg, ini = orc.Cfg(g.x_r, g.x_i, 42), orc.Init(g.init)
     par, eps = synth_inputs(g, n_per_thread * threads, seed)
     chunks = [(par[i * n_per_thread:(i + 1) * n_per_thread], eps[i * n_per_thread:(i + 1) * n_per_thread])
@@ -96,22 +113,24 @@ def run_reference(args):
         return
     g = load_workload()
     cores = os.cpu_count() or 1
-    per = max(16, int(args.ref_evals_per_core))
+    impl, kind, what = cpu_impl()
+    per = args.ref_evals_per_core if args.ref_evals_per_core > 0 else (96 if kind == "reference" else 1024)
+    per = max(16, int(per))
     for _ in range(args.warmup):
-        time_oracle(g, 16, cores)
+        time_oracle(g, 16, cores, impl=impl)
     tot_t, tot_n = 0.0, 0
     for s in range(args.steps):
-        rate, dt = time_oracle(g, per, cores, seed=1000 + s)
+        rate, dt = time_oracle(g, per, cores, seed=1000 + s, impl=impl)
         tot_t += dt
         tot_n += per * cores
     val = tot_n / tot_t
-    sample = f"{per} FULL evals per core per step x {cores} threads (Changpoint_sim shape), CPU oracle -O2 -ffp-contract=off"
+    sample = f"{per} FULL evals per core per step x {cores} threads (Changpoint_sim shape); {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_evals_per_step": per * cores},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -122,8 +141,12 @@ def cpu_reference(g, iters=12):
     """bench.py's CPU leg for the ESlice metric: the restated reference driver (test infrastructure under
     oracle/, timed only -- never on the product path) on ONE host core, a bounded sample of chain-iterations."""
     import time
-    from oracle import driver
     from lnaphylodyn_b200.chains import ITER_UNIF
+    impl, kind, what = cpu_impl()
+    if kind == "reference":
+        driver = impl.driver()
+    else:
+        from oracle import driver
     par0 = np.concatenate([[g.x_r[0], float(g.setting("control.alpha")[0]) * g.x_r[0]],
                            g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"),
                            g.setting("control.hyper")])
@@ -137,9 +160,8 @@ def cpu_reference(g, iters=12):
     for _ in range(iters):
         st = driver.eslice_iteration(st, g, opts, rng.standard_normal(123), rng.random(ITER_UNIF))
     dt = time.perf_counter() - t0
-    return {"value": iters / dt, "unit": "chain-iterations/s", "cores": 1, "kind": "port",
-            "sample": f"{iters} iterations of one chain ({(st['n_full'] - n0) / iters:.1f} FULL evals/iteration), "
-                      "oracle/driver.py over the C oracle"}
+    return {"value": iters / dt, "unit": "chain-iterations/s", "cores": 1, "kind": kind,
+            "sample": f"{iters} iterations of one chain, the R-level iteration body (oracle/driver.py) over: {what}"}
 
 
 def bench_eslice(pb, g, B, iters, rank, world, dev):
@@ -285,8 +307,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=4096, help="concurrent chains per GPU")
     ap.add_argument("--proposals", type=int, default=16, help="slice proposals per chain in one likelihood batch")
-    ap.add_argument("--ref-evals-per-core", type=int, default=1024)
-    ap.add_argument("--cpu-evals-per-core", type=int, default=4096)
+    ap.add_argument("--ref-evals-per-core", type=int, default=0, help="0 = 96 (reference as written) / 1024 (port)")
+    ap.add_argument("--cpu-evals-per-core", type=int, default=0, help="0 = 192 (reference as written) / 4096 (port)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eslice", action="store_true")
     ap.add_argument("--no-seir", action="store_true")
@@ -482,13 +504,20 @@ def main():
             line["seir_sweep"] = seir
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            rate1, dt1 = time_oracle(g, max(64, args.cpu_evals_per_core // 2), 1)
-            rateN, dtN = time_oracle(g, args.cpu_evals_per_core, cores)
-            line["cpu_baseline"] = {"value": rateN, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "value_1core": rate1,
-                                    "sample": f"{args.cpu_evals_per_core} FULL evals/core x {cores} threads "
-                                              f"({dtN:.1f}s) + {max(64, args.cpu_evals_per_core // 2)} on 1 core ({dt1:.1f}s); "
-                                              "CPU oracle = literal restatement of the reference algorithm"}
+            impl, kind, what = cpu_impl()
+            per = args.cpu_evals_per_core if args.cpu_evals_per_core > 0 else (192 if kind == "reference" else 4096)
+            time_oracle(g, 8, cores, impl=impl)
+            rate1, dt1 = time_oracle(g, max(64, per // 2), 1, impl=impl)
+            rateN, dtN = time_oracle(g, per, cores, impl=impl)
+            line["cpu_baseline"] = {"value": rateN, "unit": UNIT, "cores": cores, "kind": kind, "value_1core": rate1,
+                                    "sample": f"{per} FULL evals/core x {cores} threads ({dtN:.1f}s) + "
+                                              f"{max(64, per // 2)} on 1 core ({dt1:.1f}s); {what}"}
+            if kind == "reference":  # the allocation-free C restatement beside it, for scale
+                from oracle import oracle as orc
+                rp1, _ = time_oracle(g, 1024, 1, impl=orc)
+                rpN, _ = time_oracle(g, 2048, cores, impl=orc)
+                line["cpu_baseline"]["port_value"] = rpN
+                line["cpu_baseline"]["port_value_1core"] = rp1
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

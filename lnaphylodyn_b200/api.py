@@ -526,7 +526,7 @@ def ESlice_general_NC(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10
                       gridsize=100, volz=False, model="SIR", transX="standard", *, normals, uniforms):
     """LNA_functional.cpp:1690-1778 (volz=True path).  normals: k*p per chain, column-major k x p."""
     if not volz:
-        raise LnaError("ESlice_general_NC(volz=False) needs LogTraj(), which the reference never defines in C++")
+        raise LnaError("ESlice_general_NC(volz=False): the Kingman branch (LogTraj + coal_loglik3) is not built; reached only with likelihood != \"volz\", which no BASELINE config uses")
     O = np.asarray(OdeTraj, dtype=np.float64)
     single = O.ndim == 2
     times = O[:, 0] if single else O[0, :, 0]
@@ -646,7 +646,7 @@ def ESlice_general2(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0
                     model="SIR", transX="standard", *, normals, uniforms):
     """LNA_functional.cpp:1783-1857 (volz=True): centred elliptical slice on the trajectory; returns newTraj."""
     if not volz:
-        raise LnaError("ESlice_general2(volz=False) needs LogTraj(), which the reference never defines in C++")
+        raise LnaError("ESlice_general2(volz=False): the Kingman branch (LogTraj + coal_loglik3) is not built; reached only with likelihood != \"volz\", which no BASELINE config uses")
     pb, O, single, p = _centred_problem(OdeTraj, t_correct, init, model)
     nrow, k = pb.nrow, pb.k
     Of, _ = pb._mats(O, (nrow, p + 1))

@@ -739,7 +739,7 @@ int orc_eslice_general_nc(const orc_init *init, const double *f_cur, int k, int 
     double *tmp = (double *)malloc(sizeof(double) * (size_t)nrow * (p + 1));
     double u = uniforms[iu++], logy;
     (void)lambda;
-    if (!volz) { /* Kingman branch needs LogTraj(), which the reference never defines in C++ */
+    if (!volz) { /* Kingman branch (LogTraj of SIR_LNA.cpp:40, then coal_loglik3 logs again): not restated, reached only with likelihood != 'volz', which no BASELINE config uses */
         free(tmp);
         return -1;
     }

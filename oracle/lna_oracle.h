@@ -7,15 +7,24 @@
  * call it, and only as the checker / the timed CPU baseline -- never from the product path
  * (lnaphylodyn_b200/), which must fail loudly when its CUDA library is missing.
  *
- * Parity pinning: tests/test_oracle_golden.py checks this oracle against the golden vectors the
- * reference ships in its knitr caches (tests/golden/*.npz, made by tests/golden/make_golden.py):
- * ODE trajectory, FT$A, FT$Sigma(=L), LatentTraj, betaN, coalLog of the final chain state and
- * 2x104 per-iteration (par, Trajectory)->coalLog triplets.  Random streams (arma::randn, R::runif)
- * are third-party and unpinned: every sampler here takes PRE-DRAWN normals / uniforms and consumes
- * them in the reference's order.
+ * Parity pinning, two independent anchors:
+ *  (1) tests/test_oracle_golden.py checks this oracle against the golden vectors the reference ships in
+ *      its knitr caches (tests/golden/{changepoint_sim,constant_sim}.npz, made by tests/golden/make_golden.py):
+ *      ODE trajectory, FT$A, FT$Sigma(=L), LatentTraj, betaN, coalLog of the final chain state and
+ *      2x104 per-iteration (par, Trajectory)->coalLog triplets.
+ *  (2) tests/test_ref_vs_oracle.py checks it, function by function, against THE REFERENCE'S OWN SOURCES compiled
+ *      verbatim (oracle/_ref/liblna_ref.so = /root/reference/src/LNA_functional.cpp, basic_util.cpp, SIR_LNA.cpp,
+ *      SIR_log_LNA.cpp, SIRS_period.cpp, SIR_phylodyn.cpp against the stand-in Armadillo/Rcpp headers of
+ *      oracle/shim/; recipe `make -C oracle ref`; harness oracle/ref_harness.cpp).  That covers what no cache
+ *      covers: Update_Param decisions and the shrink sequences of ESlice_par_General / ESlice_general_NC /
+ *      ESlice_change_points and of whole driver iterations, on injected streams.  The same library produced
+ *      tests/golden/ref_as_written.npz, which the GPU tests use where /root/reference does not exist.
+ * The random GENERATORS themselves (arma::randn over R's RNG, R::runif) are third-party and unpinned: every
+ * sampler takes PRE-DRAWN normals / uniforms and consumes them in the reference's order (SURVEY.md Appendix C;
+ * the consumption order IS pinned by (2)).
  *
- * The real reference cannot be compiled here (needs R, Rcpp, RcppArmadillo, LAPACK: all absent),
- * so there is no oracle/_ref build.
+ * The reference's R package build (R CMD INSTALL: R + Rcpp + RcppArmadillo + LAPACK) cannot run here; only its
+ * C++ sources are compiled, as they are, on the stand-in headers.
  *
  * Conventions: all matrices are COLUMN-MAJOR doubles exactly as Armadillo lays them out;
  * trajectories are nrow x (p+1) with column 0 = time; cubes are p x p x k (slice-major).

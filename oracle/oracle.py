@@ -359,7 +359,7 @@ def ESlice_general_NC(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10
                                      TRANSX[transX], _p(nrm), _p(unf), C.byref(nn), C.byref(nu), C.byref(ne),
                                      _p(lat), _p(eps_new), C.byref(lo), C.byref(cl))
     if st < 0:
-        raise NotImplementedError("ESlice_general_NC(volz=False): LogTraj() is not defined in the reference's C++")
+        raise NotImplementedError("ESlice_general_NC(volz=False): Kingman branch (LogTraj, SIR_LNA.cpp:40, then coal_loglik3 takes the log again) is not restated; reached only with likelihood != 'volz', which no BASELINE config uses")
     return {"LatentTraj": lat, "OriginTraj": eps_new, "logOrigin": lo.value, "CoalLog": cl.value,
             "status": st, "n_normals": nn.value, "n_uniforms": nu.value, "n_evals": ne.value}
 
@@ -433,7 +433,7 @@ def ESlice_general2(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0
                     model="SIR", transX="standard", *, normals, uniforms):
     """LNA_functional.cpp:1783-1857 (volz=True)"""
     if not volz:
-        raise NotImplementedError("ESlice_general2(volz=False) needs LogTraj()")
+        raise NotImplementedError("ESlice_general2(volz=False): Kingman branch is not restated; reached only with likelihood != 'volz', which no BASELINE config uses")
     F, O = _f(f_cur), _f(OdeTraj)
     A, S = _f(FTs["A"]), _f(FTs["Sigma"])
     ini = init if isinstance(init, Init) else Init(init)

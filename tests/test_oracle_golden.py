@@ -70,3 +70,35 @@ def test_chprobs(changepoint):
     MCMC_initialize_general (general_change_point.R:552) at control$ch=0.975, hyper=20."""
     ch, hyper = changepoint.setting("control.ch"), float(changepoint.setting("control.hyper")[0])
     assert -0.5 * np.sum((np.log(ch) * hyper) ** 2) == pytest.approx(float(changepoint.final["chprobs"][0]), rel=1e-12)
+
+
+def test_oracle_matches_reference_as_written_vectors(changepoint, constant):
+    """tests/golden/ref_as_written.npz = outputs of the reference's own code (compiled verbatim on oracle/shim/,
+    tests/golden/make_ref_golden.py).  The oracle must reproduce them; runs without /root/reference."""
+    import os
+    from conftest import GOLDEN
+    from oracle import driver
+    R = np.load(os.path.join(GOLDEN, "ref_as_written.npz"))
+    for tag, g in (("full_cp", changepoint), ("full_co", constant)):
+        par, eps = R[tag + ".par"], R[tag + ".eps"]
+        cfg, ini = orc.Cfg(g.x_r, g.x_i, par.shape[1] - 2), orc.Init(g.init)
+        for b in range(0, par.shape[0], 3):
+            o = orc.full_loglik(cfg, ini, par[b, 2:], par[b, :2], g.times, g.gridsize, eps[b], g.t_correct)
+            assert o["coalLog"] == pytest.approx(R[tag + ".coalLog"][b], rel=1e-12)
+            assert relerr(o["LatentTraj"], R[tag + ".LatentTraj"][b]) < 1e-11
+    g = changepoint
+    par, eps = g.final["par"].ravel(), g.final["OriginTraj"]
+    pri, ess = [(1.0, 1.0), (0.7, 0.5), (-1.7, 0.1), (3.0, 0.2)], [0, 1, 0, 0, 1, 1, 0]
+    for b in range(R["esp.normals"].shape[0]):
+        o = orc.ESlice_par_General(par, g.times, eps, pri, g.x_r, g.x_i, g.init, g.gridsize, ess, float(g.final["coalLog"][0]),
+                                   g.t_correct, normals=R["esp.normals"][b], uniforms=R["esp.uniforms"][b])
+        assert o["n_uniforms"] == R["esp.n_uniforms"][b]
+        assert relerr(o["par"], R["esp.par"][b]) < 1e-12 and o["CoalLog"] == pytest.approx(R["esp.CoalLog"][b], rel=1e-12)
+    # the chain trace
+    nrm, unf = R["chain.normals"], R["chain.uniforms"]
+    st = [driver.init_state(g, R["chain.par0"], g.setting("control.traj")) for _ in range(nrm.shape[1])]
+    for it in range(nrm.shape[0]):
+        for c in range(nrm.shape[1]):
+            st[c] = driver.eslice_iteration(st[c], g, driver.opts_from_golden(g, update_traj=it >= 2), nrm[it, c], unf[it, c])
+            assert relerr(st[c]["par"], R["chain.par"][it, c]) < 1e-11
+            assert st[c]["coalLog"] == pytest.approx(R["chain.coalLog"][it, c], rel=1e-11)
