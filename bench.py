@@ -233,6 +233,29 @@ def bench_eslice(pb, g, B, iters, rank, world, dev):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms, e2e_ms, rng_ms = float(t[0]), float(t[1]), float(t[2])
     tot = world * B * iters
+    # the one exchange of the path: all-gather of the per-chain summary rows, NCCL over NVLink
+    gather_us, gathered_rows = None, None
+    if world > 1:
+        from lnaphylodyn_b200.chains import gather_summaries
+
+        class _Dev:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+        local = torch.as_tensor(_Dev(ch.summary_ptr(), (B, 4)), device=dev)
+        for _ in range(3):
+            allrows = gather_summaries(local)
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(10):
+            allrows = gather_summaries(local)
+        g1.record(stream)
+        torch.cuda.synchronize(dev)
+        tg = torch.tensor([g0.elapsed_time(g1) * 100.0], dtype=torch.float64, device=dev)  # us per gather
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather_us, gathered_rows = float(tg[0]), int(allrows.shape[0])
+        assert gathered_rows == world * B and bool(torch.isfinite(allrows[:, 0]).all())
     cpu = None
     if rank == 0:
         cpu = cpu_reference(g)
@@ -243,6 +266,7 @@ def bench_eslice(pb, g, B, iters, rank, world, dev):
             "mean_full_evals_per_iter": float(cnt[0]) / tot, "mean_cheap_evals_per_iter": float(cnt[1]) / tot,
             "consumed_full_evals_per_s": float(cnt[0]) / (ms * 1e-3), "gpu_launches": int(launches),
             "spec_width": "auto", "finite_coalLog": bool(np.all(np.isfinite(after["coalLog"]))),
+            "summary_allgather_us": gather_us, "summary_rows_gathered": gathered_rows,
             "cpu_baseline": cpu}
 
 
@@ -308,7 +332,7 @@ def main():
     ap.add_argument("--chains", type=int, default=4096, help="concurrent chains per GPU")
     ap.add_argument("--proposals", type=int, default=16, help="slice proposals per chain in one likelihood batch")
     ap.add_argument("--ref-evals-per-core", type=int, default=0, help="0 = 96 (reference as written) / 1024 (port)")
-    ap.add_argument("--cpu-evals-per-core", type=int, default=0, help="0 = 192 (reference as written) / 4096 (port)")
+    ap.add_argument("--cpu-evals-per-core", type=int, default=0, help="0 = 512 (reference as written) / 4096 (port)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eslice", action="store_true")
     ap.add_argument("--no-seir", action="store_true")
@@ -505,7 +529,7 @@ def main():
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             impl, kind, what = cpu_impl()
-            per = args.cpu_evals_per_core if args.cpu_evals_per_core > 0 else (192 if kind == "reference" else 4096)
+            per = args.cpu_evals_per_core if args.cpu_evals_per_core > 0 else (512 if kind == "reference" else 4096)
             time_oracle(g, 8, cores, impl=impl)
             rate1, dt1 = time_oracle(g, max(64, per // 2), 1, impl=impl)
             rateN, dtN = time_oracle(g, per, cores, impl=impl)
