@@ -458,7 +458,7 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
     const unsigned grid = nblk(B, block);
     const View vp = item_view(param, P.npt), vi = item_view(initial, p), vo = item_view(origin, (long long)P.k * p);
 #define LAUNCH(MODEL, STORE)                                                                                     \
-    k_full_loglik<MODEL, STORE><<<grid, block, pb->tab_bytes, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status)
+    k_full_loglik<MODEL, STORE><<<grid, block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status)
     if (P.model == LNA_MODEL_SIR) {
         if (store) LAUNCH(0, true);
         else LAUNCH(0, false);

@@ -55,7 +55,7 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     const long long nthreads = nchains * W;
     const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, nthreads);
     const unsigned grid = nblk(nthreads, block);
-#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, pb->tab_bytes, pb->stream>>>(P, pb->seg, nchains, a)
+#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, nchains, a)
     // only the (proposal, width) pairs that exist are instantiated: MH kinds are one lane per chain,
     // the MH pair uses 4, the slice kinds any power of two
     constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
@@ -632,7 +632,7 @@ static int part_init(ChainPart *ch, const double *par, const double *OriginTraj)
     FullOut out{soa_out(ch->A, B), soa_out(ch->L, B), soa_out(ch->ode, B), soa_out(ch->betaN, B), soa_out(ch->latent, B)};
     const View vp{ch->par + 2 * B, 1, B}, vi{ch->par, 1, B}, vo{ch->origin, 1, B};
     const int block = pick_block(pb, B);
-    k_full_loglik<0, true><<<nblk(B, block), block, pb->tab_bytes, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out,
+    k_full_loglik<0, true><<<nblk(B, block), block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, B, vp, vi, vo, out,
                                                                                  ch->coalLog, ch->counters + 3 * B);
     if (launch_check(pb, "k_full_loglik")) return -1;
     CK(cudaMemsetAsync(ch->logOrigin, 0, sizeof(double) * nB, pb->stream));

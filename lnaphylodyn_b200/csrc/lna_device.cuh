@@ -70,24 +70,36 @@ struct Tables {
     const double *cellCD;
     const double *cellY;
     const int *cellCnt;
+    const double *ctimes;  // [nrow] times[r*g]: column 0 of every coarse trajectory
+    double *eps_slot;      // this thread's staging slot for the latent increments of one interval (kEpsSlot doubles)
 };
+constexpr int kEpsSlot = 4;  // doubles per thread (p <= 3, padded)
 
 __host__ __device__ inline size_t tables_bytes(int nch, int k, int n0) {
     size_t b = 0;
     b += sizeof(double) * (size_t)k;
+    b += sizeof(double) * (size_t)(k + 2);  // coarse times (nrow <= k + 2)
     b += sizeof(double) * (size_t)n0 * 2;
     b += sizeof(int) * (size_t)nch;
     b += sizeof(int) * (size_t)n0;
     return (b + 15) & ~(size_t)15;
 }
+// dynamic shared memory of a kernel that runs FULL evaluations: the tables + one staging slot per thread
+__host__ __device__ inline size_t full_eval_smem_bytes(size_t tab_bytes, int block) {
+    return tab_bytes + sizeof(double) * (size_t)kEpsSlot * (size_t)block;
+}
 
-__device__ inline Tables stage_tables(const DevProb &P, unsigned char *smem) {
+// `with_eps_slots`: the kernel was launched with full_eval_smem_bytes() and wants per-thread staging slots
+__device__ inline Tables stage_tables(const DevProb &P, unsigned char *smem, bool with_eps_slots = false) {
     double *dts = reinterpret_cast<double *>(smem);
-    double *cd = dts + P.k;
+    double *ct = dts + P.k;
+    double *cd = ct + (P.k + 2);
     double *yy = cd + P.n0;
     int *ci = reinterpret_cast<int *>(yy + P.n0);
     int *cc = ci + P.nch;
+    double *slots = reinterpret_cast<double *>(smem + tables_bytes(P.nch, P.k, P.n0));
     for (int i = threadIdx.x; i < P.k; i += blockDim.x) dts[i] = P.dt_seg[i];
+    for (int i = threadIdx.x; i < P.nrow && i < P.k + 2; i += blockDim.x) ct[i] = i * P.g < P.nt ? P.times[i * P.g] : 0.0;
     for (int i = threadIdx.x; i < P.nch; i += blockDim.x) ci[i] = P.chidx[i];
     if (P.has_init)
         for (int i = threadIdx.x; i < P.n0; i += blockDim.x) {
@@ -96,8 +108,16 @@ __device__ inline Tables stage_tables(const DevProb &P, unsigned char *smem) {
             cc[i] = P.cellCnt[i];
         }
     __syncthreads();
-    return Tables{ci, dts, cd, yy, cc};
+    return Tables{ci, dts, cd, yy, cc, ct, with_eps_slots ? slots + (size_t)threadIdx.x * kEpsSlot : nullptr};
 }
+
+// 8-byte asynchronous global -> shared copy (LDGSTS): no destination register, so no scoreboard is held across the
+// time loop; completion is awaited where the value is consumed.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Strided views: element j of item b at base[b*sb + j*sj].  (sb = n, sj = 1) is the C-ABI's
 // item-major layout; (sb = 1, sj = B) is the coalesced struct-of-arrays layout of resident chains.
@@ -221,12 +241,12 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
     // coarse row 0 = initial state
     if (kStore) {
         if (out.ode.ok()) {
-            out.ode.put(b, 0, P.times[0]);
+            out.ode.put(b, 0, T.ctimes[0]);
             out.ode.put(b, nrow, S);
             out.ode.put(b, 2 * nrow, I);
         }
         if (out.latent.ok()) {
-            out.latent.put(b, 0, P.times[0]);
+            out.latent.put(b, 0, T.ctimes[0]);
             out.latent.put(b, nrow, S);
             out.latent.put(b, 2 * nrow, I);
         }
@@ -237,7 +257,15 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
     for (int seg = 0; seg < k; ++seg) {
         double p00 = 1.0, p01 = 0.0, p10 = 0.0, p11 = 1.0;  // F0
         double s00 = 0.0, s01 = 0.0, s11 = 0.0;              // Sigma (symmetric)
-        const double e0 = eps.at(seg, 0), e1 = eps.at(seg, 1);  // issued early: latency hidden by the loop
+        // latent increments of this interval: asynchronous copy into the thread's shared-memory slot now, read at
+        // the end of the interval (a register load would make ptxas wait for it BEFORE the time loop: measured
+        // ~1000 stalled cycles per interval, profiles/r1b_ncu_kernels.md)
+        const bool staged = T.eps_slot != nullptr && eps.stage(seg, 2, T.eps_slot);
+        double e0 = 0.0, e1 = 0.0;
+        if (!staged) {
+            e0 = eps.at(seg, 0);
+            e1 = eps.at(seg, 1);
+        }
         int s = seg * g;
         const int s_end = s + g;
         // The step body is a macro-like lambda over `dts`: with k <= kSegConst the per-segment dt is read
@@ -304,6 +332,11 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
             if (seg_const) run(SD.v[seg], run_end);
             else run(T.dt_seg[seg], run_end);
         }
+        if (staged) {
+            cp_async_wait_all();
+            e0 = T.eps_slot[0];
+            e1 = T.eps_slot[1];
+        }
         // Cholesky of Sigma + 1e-8 I  (lower)
         const double c00 = s00 + kJitter;
         double l00 = sqrt(c00);
@@ -337,12 +370,12 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
                 out.L.put(b, seg * 4 + 3, l11);
             }
             if (out.ode.ok()) {
-                out.ode.put(b, r, P.times[r * g]);
+                out.ode.put(b, r, T.ctimes[r]);
                 out.ode.put(b, nrow + r, S);
                 out.ode.put(b, 2 * nrow + r, I);
             }
             if (out.latent.ok()) {
-                out.latent.put(b, r, P.times[r * g]);
+                out.latent.put(b, r, T.ctimes[r]);
                 out.latent.put(b, nrow + r, lS);
                 out.latent.put(b, 2 * nrow + r, lI);
             }
@@ -380,7 +413,7 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const SegDt &SD
     VolzAcc va;
     int st = 0;
     auto put_row = [&](const OutView &o, int r, double a, double c, double d) {
-        o.put(b, r, P.times[r * g]);
+        o.put(b, r, T.ctimes[r]);
         o.put(b, nrow + r, a);
         o.put(b, 2 * nrow + r, c);
         o.put(b, 3 * nrow + r, d);
@@ -494,9 +527,15 @@ struct EpsFromView {
     long long b;
     int k;
     __device__ __forceinline__ double at(int seg, int c) const { return v.at(b, c * k + seg); }
+    // start the asynchronous copy of components 0..p-1 of interval `seg` into `slot`
+    __device__ __forceinline__ bool stage(int seg, int p, double *slot) const {
+        for (int c = 0; c < p; ++c) cp_async8(slot + c, v.base + b * v.sb + (long long)(c * k + seg) * v.sj);
+        return true;
+    }
 };
 struct EpsZero {
     __device__ __forceinline__ double at(int, int) const { return 0.0; }
+    __device__ __forceinline__ bool stage(int, int, double *) const { return false; }
 };
 
 }  // namespace lna

@@ -200,10 +200,10 @@ __device__ __forceinline__ EssParPre ess_par_pre(const CandArgs &a, long long c,
 // SIR (p = 2) only, like the reference's samplers (hard-wired subvec(0,1) / subvec(2,..)).
 // ================================================================================================
 template <int kProp, int W>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 3)
 k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, CandArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Tables T = stage_tables(P, smem);
+    const Tables T = stage_tables(P, smem, true);
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long ci = t0 / W;  // index into the (optional) compacted chain list
     const int w = (int)(t0 % W);

@@ -9,11 +9,11 @@ namespace lna {
 // reference LNA_functional.cpp:1217-1226), item-major inputs.
 // ================================================================================================
 template <int kModel, bool kStore>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_full_loglik(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, View param,
               View initial, View origin, FullOut out, double *coalLog, int *status) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Tables T = stage_tables(P, smem);
+    const Tables T = stage_tables(P, smem, true);
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int st = 0;
