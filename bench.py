@@ -37,8 +37,9 @@ METRIC = "LNA+coalescent loglik evals/sec (FULL evaluations, batched chains)"
 UNIT = "evals/s"
 WORKLOAD = ("configs[1] Changpoint_sim vignette: SIR LNA N=1e6, 2000 fine steps, gridsize 50, 39 R0 change points, "
             "cached 342-tip genealogy (E=376); FULL (param, initial, OriginTraj) -> coalLog evaluations")
-# DRAM bytes per launch of the hot kernel at the default batch (ncu --set full, profiles/r1_ncu_full_loglik_final.md)
-NCU_TRAFFIC_BYTES_65536 = 65057792 + 761856
+# DRAM bytes per launch of the hot kernel at the default batch (dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture, profiles/r1c_ncu_kernels.md)
+NCU_TRAFFIC_BYTES_65536 = 65071104 + 747776
 
 
 def load_workload():
