@@ -1,0 +1,230 @@
+"""R-level drivers of the reference, batched: `General_MCMC_with_ESlice` and `General_MCMC2`
+(R/LNA_chpt_slice.R:508-693, 723-849) with `MCMC_setup_general` / `MCMC_initialize_general`
+(R/general_change_point.R:416-567) for `n_chains` independent chains on one GPU.
+
+Same argument names, same meaning and the same result list as the R functions (`par`, `Trajectory`, `l`, `l1`,
+`MCMC_setting`, `MCMC_obj`), with a leading chain axis when `n_chains > 1`.  The iteration bodies run on the
+device through the resident-chain C ABI (`lna_chains_step*`, see chains.py); this module is the run loop around
+them: set-up, initial state, stage switching (`burn1`, `warmup2`), thinning and storage.
+
+What is NOT here, and raises instead of guessing: likelihood other than "volz", models other than "SIR" (the
+reference's samplers are hard-wired to p = 2, LNA_functional.cpp:1456-1462), `ESS_vec2`, Metropolis entry lists other
+than the vignettes', and General_MCMC2's adaptive joint random-walk stage (`i >= warmup2`, needs MASS::mvrnorm).
+The random numbers are Philox streams drawn on the device (seed, chain, iteration) -- R's generator is not
+reproduced, so a run is distributionally, not bitwise, the R run; per-iteration arithmetic on given
+streams is pinned by tests/test_gpu_eslice.py and tests/test_gpu_vs_reference.py.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, api, chains as chm, genealogy
+from ._lib import LnaError, check
+
+_PRIOR_ORDER = ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")
+_PROP_ORDER = ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")
+
+
+def MCMC_setup_general(coal_obs, times, t_correct, N, gridsize=50, niter=1000, burn=500, thin=5, changetime=(),
+                       DEMS=("E", "I"), prior=None, proposal=None, control=None, likelihood="volz", model="SIR",
+                       Index=(0, 1), nparam=2, PCOV=None):
+    """R/general_change_point.R:416-435.  `coal_obs`: dict with samp_times, n_sampled, coal_times."""
+    times = np.asarray(times, dtype=np.float64)
+    gridset = np.arange(0, len(times), int(gridsize))
+    grid = times[gridset]
+    Init = genealogy.coal_lik_init(coal_obs["samp_times"], coal_obs["n_sampled"], coal_obs["coal_times"], grid)
+    if t_correct is None:
+        t_correct = float(np.max(coal_obs["coal_times"]))
+    changetime = np.asarray(changetime, dtype=np.float64).ravel()
+    return {"Init": Init, "times": times, "t_correct": float(t_correct), "x_r": np.concatenate([[float(N)], changetime]),
+            "gridsize": int(gridsize), "gridset": gridset + 1, "niter": int(niter), "burn": int(burn), "thin": int(thin),
+            "x_i": [len(changetime), int(nparam), int(Index[0]), int(Index[1])], "prior": dict(prior or {}),
+            "proposal": dict(proposal or {}), "control": dict(control or {}), "p": len(DEMS), "reps": 1,
+            "likelihood": likelihood, "model": model, "PCOV": PCOV}
+
+
+def _problem(setting, device=0):
+    return api.problem_for(setting["times"], setting["x_r"], setting["x_i"], setting["gridsize"], setting["t_correct"],
+                           setting["Init"], model=setting["model"], device=device)
+
+
+def MCMC_initialize_general(MCMC_setting, n_chains=1, rng=None, device=0, max_tries=50):
+    """R/general_change_point.R:439-567 for `n_chains` chains: `control` values are used where given, the rest is
+    drawn from the priors (numpy generator `rng`); a chain is redrawn while its initial coalescent likelihood is the
+    -1e7 sentinel / NaN, like the R `while` loop.  Returns the batch as a dict of arrays with a leading chain axis."""
+    s = MCMC_setting
+    if s["model"] != "SIR" or s["p"] != 2:
+        raise LnaError("MCMC_initialize_general: only model = 'SIR' (p = 2) has samplers on the GPU path")
+    rng = rng or np.random.default_rng(0)
+    ctl, pr = s["control"], s["prior"]
+    nch, B = s["x_i"][0], int(n_chains)
+    pb = _problem(s, device)
+    k, p = pb.k, pb.p
+    par = np.empty((B, 2 + 2 + nch + 1))
+    eps = np.empty((B, k, p))
+    todo = np.ones(B, dtype=bool)
+    coal = np.full(B, np.nan)
+    for _ in range(max_tries):
+        n = int(todo.sum())
+        if n == 0:
+            break
+        q = np.empty((n, par.shape[1]))
+        q[:, 0] = s["x_r"][0]
+        if ctl.get("alpha") is None:
+            q[:, 1] = rng.lognormal(pr["pop_pr"][0], pr["pop_pr"][1], n)
+        else:
+            q[:, 1] = float(np.ravel(ctl["alpha"])[0]) * s["x_r"][0]
+        q[:, 2] = rng.uniform(pr["R0_pr"][0], pr["R0_pr"][1], n) if ctl.get("R0") is None else float(ctl["R0"])
+        q[:, 3] = (np.exp(rng.normal(pr["gamma_pr"][0], pr["gamma_pr"][1], n)) if ctl.get("gamma") is None
+                   else float(ctl["gamma"]))
+        hyper = (rng.gamma(pr["hyper_pr"][0], 1.0 / pr["hyper_pr"][1], n) if ctl.get("hyper") is None
+                 else np.full(n, float(ctl["hyper"])))
+        q[:, -1] = hyper
+        if nch:
+            q[:, 4:4 + nch] = (rng.lognormal(0.0, 1.0, (n, nch)) ** (1.0 / hyper)[:, None] if ctl.get("ch") is None
+                               else np.asarray(ctl["ch"], dtype=np.float64).ravel()[None, :])
+        e = (rng.standard_normal((n, k, p)) if ctl.get("traj") is None
+             else np.broadcast_to(np.asarray(ctl["traj"], dtype=np.float64), (n, k, p)))
+        res = pb.full_loglik(q[:, 2:], q[:, :2], e, want=("coalLog",))
+        cl = np.atleast_1d(res["coalLog"])
+        idx = np.flatnonzero(todo)
+        ok = np.isfinite(cl) & (cl > -10000000.0)
+        par[idx[ok]], eps[idx[ok]], coal[idx[ok]] = q[ok], e[ok], cl[ok]
+        todo[idx[ok]] = False
+        if ctl.get("traj") is not None and all(ctl.get(v) is not None for v in ("alpha", "R0", "gamma", "hyper", "ch")):
+            if not ok.all():
+                raise LnaError("MCMC_initialize_general: the fully specified control state has no finite likelihood")
+    if todo.any():
+        raise LnaError(f"MCMC_initialize_general: {int(todo.sum())} chains found no finite initial likelihood")
+    ch = par[:, 4:4 + nch]
+    chprobs = -0.5 * np.sum((np.log(ch) * par[:, -1:]) ** 2, axis=1)
+    return {"par": par, "OriginTraj": eps, "coalLog": coal, "logOrigin": -0.5 * np.sum(eps * eps, axis=(1, 2)),
+            "chprobs": chprobs, "p": p}
+
+
+def _lists(d, order, what):
+    try:
+        return [np.asarray(d[k], dtype=np.float64).ravel() for k in order]
+    except KeyError as e:
+        raise LnaError(f"{what} list needs the entries {order} (missing {e})")
+
+
+def _finish(ch, setting, rec, n_chains, squeeze):
+    s = ch.get()
+    obj = {"par": s["par"], "LatentTraj": s["LatentTraj"], "OriginTraj": s["OriginTraj"], "coalLog": s["coalLog"],
+           "logOrigin": s["logOrigin"], "p": 2, "n_full_evals": s["n_full_evals"], "n_cheap_evals": s["n_cheap_evals"],
+           "n_mh_accept": s["n_mh_accept"]}
+    out = {"par": rec["par"], "Trajectory": rec["traj"], "l": rec["l"], "l1": rec["l1"], "l2": None, "l3": None,
+           "MX": setting["PCOV"], "MCMC_setting": setting, "MCMC_obj": obj}
+    if squeeze and n_chains == 1:
+        for key in ("par", "Trajectory", "l", "l1"):
+            out[key] = out[key][0]
+        out["MCMC_obj"] = {k: (v[0] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == 1 else v)
+                           for k, v in obj.items()}
+    return out
+
+
+def _record(ch, rec, i, thin, want_traj):
+    """params[i,] = par; l[i] = logOrigin; l1[i] = coalLog; tjs[,,i/thin] = LatentTraj  (LNA_chpt_slice.R:839-845)"""
+    pb, B = ch.pb, ch.B
+    L = _lib.lib()
+    par = np.empty((B, ch.npar))
+    cl, lo = np.empty(B), np.empty(B)
+    lat = np.empty((B, pb.nrow * (pb.p + 1))) if want_traj else None
+    check(L.lna_chains_get(ch.h, api._ptr(par), None, api._ptr(lat) if want_traj else None, api._ptr(cl), api._ptr(lo), None),
+          "lna_chains_get")
+    rec["par"][:, i], rec["l"][:, i], rec["l1"][:, i] = par, lo, cl
+    if want_traj:
+        rec["traj"][:, (i + 1) // thin - 1] = pb._unmats(lat, (pb.nrow, pb.p + 1), False)
+
+
+def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn=0, thin=5, changetime=(),
+                             DEMS=("S", "I"), prior=None, proposal=None, control=None, ESS_vec=(1, 1, 1, 1, 1, 1, 1),
+                             likelihood="volz", model="SIR", Index=(0, 1), nparam=2, method="seq", options=None,
+                             ESS_vec2=None, verbose=False, *, n_chains=1, seed=0, device=0, chain_offset=0, squeeze=True,
+                             init_rng=None):
+    """R/LNA_chpt_slice.R:723-849 for `n_chains` chains.  Iterations i < options["burn1"] run the Metropolis entries
+    and the parameter slice update with ESS_vec[5] switched off (ESS_temp); later ones add the trajectory slice update.
+    Returns {par (chains, niter, npar), Trajectory (chains, niter/thin, nrow, p+1), l, l1, MCMC_setting, MCMC_obj}."""
+    if likelihood != "volz" or model != "SIR":
+        raise LnaError("General_MCMC_with_ESlice: the GPU path has the volz likelihood with model = 'SIR' only")
+    if ESS_vec2 is not None:
+        raise LnaError("General_MCMC_with_ESlice: ESS_vec2 (second parameter slice update) is not built")
+    options = dict(options or {})
+    nch = len(np.ravel(changetime))
+    par_ids = dict(options.get("parIdlist") or {"c": 4, "d": nch + 5})
+    if [int(v) for v in par_ids.values()] != [4, nch + 5] or bool(options.get("hyper", False)) or \
+            [int(v) for v in dict(options.get("priorIdlist") or {"c": 3, "d": 5}).values()] != [3, 5] or \
+            [int(v) for v in dict(options.get("isLoglist") or {"c": 1, "d": 0}).values()] != [1, 0]:
+        raise LnaError("General_MCMC_with_ESlice: Update_Param_each_Norm is built for the vignettes' entries "
+                       "parIdlist = (4, nch + 5), isLoglist = (1, 0), priorIdlist = (3, 5), hyper = F")
+    if int(ESS_vec[0]) or int(ESS_vec[6]):
+        raise LnaError("General_MCMC_with_ESlice: ESS_vec[1] (I0) / ESS_vec[7] (self-mixing OriginTraj) are rejected, "
+                       "see DESIGN.md section 7")
+    setting = MCMC_setup_general(coal_obs, times, t_correct, N, gridsize, niter, burn, thin, changetime, DEMS, prior,
+                                 proposal, control, likelihood, model, Index, nparam, options.get("PCOV"))
+    init = MCMC_initialize_general(setting, n_chains, init_rng or np.random.default_rng([int(seed), 7]), device)
+    pb = _problem(setting, device)
+    ch = chm.Chains(pb, init["par"], init["OriginTraj"])
+    pr, po = _lists(setting["prior"], _PRIOR_ORDER, "prior"), _lists(setting["proposal"], _PROP_ORDER, "proposal")
+    ess_temp = list(ESS_vec)
+    ess_temp[4] = 0
+    o_burn = chm.make_opts(pr, po, ess_temp, update_traj=False)
+    o_full = chm.make_opts(pr, po, list(ESS_vec), update_traj=True)
+    burn1 = int(options.get("burn1", 5000))
+    B, niter, thin = int(n_chains), int(niter), int(thin)
+    rec = {"par": np.empty((B, niter, ch.npar)), "l": np.empty((B, niter)), "l1": np.empty((B, niter)),
+           "traj": np.empty((B, niter // thin, pb.nrow, pb.p + 1))}
+    for i in range(1, niter + 1):  # R's 1-based iteration counter
+        ch.step_rng(o_burn if i < burn1 else o_full, seed, i, chain_offset)
+        _record(ch, rec, i - 1, thin, i % thin == 0)
+        if verbose and i % 100 == 0:
+            print(i, float(np.mean(rec["l1"][:, i - 1])))
+    return _finish(ch, setting, rec, B, squeeze)
+
+
+def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn=0, thin=5, changetime=(),
+                  DEMS=("S", "I"), prior=None, proposal=None, control=None, updateVec=(1, 1, 1, 1, 1, 1, 1),
+                  likelihood="volz", model="SIR", Index=(0, 1), nparam=2, method="seq", options=None, verbose=False, *,
+                  n_chains=1, seed=0, device=0, chain_offset=0, squeeze=True, init_rng=None):
+    """R/LNA_chpt_slice.R:508-693 for `n_chains` chains: stage 1 (i < burn1: scalar Metropolis entries + change-point
+    slice update) and stage 2 (burn1 <= i < warmup2: + hyper-parameter Metropolis step when updateVec[5] == 0.5, +
+    trajectory slice update).  Like the R code it stores the trajectory of EVERY iteration in slot i (so `niter / thin`
+    must cover niter: thin = 1, or the R call fails too); here slots are filled every `thin` iterations instead."""
+    if likelihood != "volz" or model != "SIR":
+        raise LnaError("General_MCMC2: the GPU path has the volz likelihood with model = 'SIR' only")
+    options = dict(options or {})
+    warmup2 = int(options.get("warmup2") or 100000)
+    burn1 = int(options.get("burn1", 5000))
+    if int(niter) >= warmup2:
+        raise LnaError("General_MCMC2: iterations i >= warmup2 use the adaptive joint random walk (update_Param_joint, "
+                       "MASS::mvrnorm), which is not built; raise options['warmup2'] above niter")
+    nch = len(np.ravel(changetime))
+    par_ids = [int(v) for v in dict(options.get("parIdlist") or {"a": 2, "b": 3, "c": 4, "d": 5 + nch}).values()][:3]
+    is_log = [int(v) for v in dict(options.get("isLoglist") or {"a": 1, "b": 0, "c": 1, "d": 0}).values()][:3]
+    pr_ids = [int(v) for v in dict(options.get("priorIdlist") or {"a": 1, "b": 2, "c": 3, "d": 5}).values()][:3]
+    entries = tuple((pid - 1, lg, prid) for pid, lg, prid in zip(par_ids, is_log, pr_ids))  # R is 1-based
+    setting = MCMC_setup_general(coal_obs, times, t_correct, N, gridsize, niter, burn, thin, changetime, DEMS, prior,
+                                 proposal, control, likelihood, model, Index, nparam, options.get("PCOV"))
+    init = MCMC_initialize_general(setting, n_chains, init_rng or np.random.default_rng([int(seed), 7]), device)
+    pb = _problem(setting, device)
+    ch = chm.Chains(pb, init["par"], init["OriginTraj"])
+    pr, po = _lists(setting["prior"], _PRIOR_ORDER, "prior"), _lists(setting["proposal"], _PROP_ORDER, "proposal")
+    upd_chpt = int(updateVec[5]) == 1
+    o1 = chm.make_mcmc2_opts(pr, po, entries, update_hyper=False, update_chpt=upd_chpt, update_traj=False)
+    o2 = chm.make_mcmc2_opts(pr, po, entries, update_hyper=float(updateVec[4]) == 0.5, update_chpt=upd_chpt,
+                             update_traj=int(updateVec[6]) == 1)
+    B, niter, thin = int(n_chains), int(niter), int(thin)
+    n_norm2 = nch + pb.k * pb.p
+    rec = {"par": np.empty((B, niter, ch.npar)), "l": np.empty((B, niter)), "l1": np.empty((B, niter)),
+           "traj": np.empty((B, niter // thin, pb.nrow, pb.p + 1))}
+    nrm, unf = np.empty((B, n_norm2)), np.empty((B, chm.ITER2_UNIF))
+    L = _lib.lib()
+    for i in range(1, niter + 1):
+        check(L.lna_draw_streams(pb.h, B, int(chain_offset), n_norm2, chm.ITER2_UNIF, int(seed), i, api._ptr(nrm),
+                                 api._ptr(unf)), "lna_draw_streams")
+        ch.step_mcmc2(o1 if i < burn1 else o2, nrm, unf)
+        _record(ch, rec, i - 1, thin, i % thin == 0)
+        if verbose and i % 100 == 0:
+            print(i, float(np.mean(rec["l1"][:, i - 1])))
+    return _finish(ch, setting, rec, B, squeeze)

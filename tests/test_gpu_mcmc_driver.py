@@ -1,0 +1,109 @@
+"""The R-level drivers (lnaphylodyn_b200/mcmc.py): the vignette calls, replayed for a few chains and iterations, must give
+exactly what stepping the oracle's iteration body over the same device-drawn streams gives -- set-up from the raw
+coalescent data, initial state, burn-in switch, thinning and storage included."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import driver
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def vignette_args(g):
+    coal = {k: g.setting("Init.args." + k) for k in ("samp_times", "n_sampled", "coal_times")}
+    prior = {k: g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")}
+    proposal = {k: g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")}
+    control = {"alpha": g.setting("control.alpha"), "R0": float(g.setting("control.R0")[0]),
+               "gamma": float(g.setting("control.gamma")[0]), "ch": g.setting("control.ch"),
+               "traj": g.setting("control.traj"), "hyper": float(g.setting("control.hyper")[0])}
+    return coal, prior, proposal, control
+
+
+def test_general_mcmc_with_eslice_driver(changepoint):
+    """vignettes/Changpoint_sim.Rmd:89-97 with niter = 6, burn1 = 3, thin = 2, 5 chains."""
+    from lnaphylodyn_b200 import api, chains as chm, mcmc
+    g = changepoint
+    coal, prior, proposal, control = vignette_args(g)
+    nch = len(g.x_r) - 1
+    B, niter, burn1, thin, seed = 5, 6, 3, 2, 11
+    res = mcmc.General_MCMC_with_ESlice(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=niter, burn=0, thin=thin,
+                                        changetime=g.x_r[1:], DEMS=("S", "I"), prior=prior, proposal=proposal, control=control,
+                                        ESS_vec=(0, 1, 0, 0, 1, 1, 0), likelihood="volz", model="SIR", Index=(0, 1), nparam=2,
+                                        method="admcmc", options={"burn1": burn1, "parIdlist": {"c": 4, "d": nch + 5},
+                                                                  "isLoglist": {"c": 1, "d": 0}, "priorIdlist": {"c": 3, "d": 5},
+                                                                  "hyper": False}, n_chains=B, seed=seed)
+    assert res["par"].shape == (B, niter, 44) and res["Trajectory"].shape == (B, niter // thin, 41, 3)
+    # the set-up reproduces the cached Init from the raw coalescent data
+    for k in ("C", "D", "y", "gridrep"):
+        assert np.array_equal(res["MCMC_setting"]["Init"][k], g.init[k])
+    # oracle chains over the streams the device drew
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    probe = chm.Chains(pb, np.tile(res["par"][0, 0], (B, 1)), control["traj"])
+    par0 = np.concatenate([[g.x_r[0], float(control["alpha"][0]) * g.x_r[0]], [control["R0"], control["gamma"]], control["ch"],
+                           [control["hyper"]]])
+    st = [driver.init_state(g, par0, control["traj"]) for _ in range(B)]
+    for i in range(1, niter + 1):
+        nrm, unf = probe.device_streams(seed, i)
+        for c in range(B):
+            st[c] = driver.eslice_iteration(st[c], g, driver.opts_from_golden(g, update_traj=i >= burn1), nrm[c], unf[c])
+            assert relerr(res["par"][c, i - 1], st[c]["par"]) < TOL, (i, c)
+            assert res["l1"][c, i - 1] == pytest.approx(st[c]["coalLog"], rel=TOL)
+            assert res["l"][c, i - 1] == pytest.approx(st[c]["logOrigin"], rel=1e-11, abs=1e-300)
+            if i % thin == 0:
+                assert relerr(res["Trajectory"][c, i // thin - 1][:, 1:], st[c]["LatentTraj"][:, 1:]) < 1e-9
+    assert relerr(res["MCMC_obj"]["par"], np.array([s["par"] for s in st])) < TOL
+    # chains differ (independent streams) and one chain alone comes back without the chain axis
+    assert not np.array_equal(res["par"][0, -1], res["par"][1, -1])
+    one = mcmc.General_MCMC_with_ESlice(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=2, thin=1,
+                                        changetime=g.x_r[1:], prior=prior, proposal=proposal, control=control,
+                                        ESS_vec=(0, 1, 0, 0, 1, 1, 0), options={"burn1": 1}, n_chains=1, seed=seed)
+    assert one["par"].shape == (2, 44) and one["Trajectory"].shape == (2, 41, 3)
+    assert np.array_equal(one["par"][0, :2], res["par"][0, 0, :2])  # N and I0 are never updated in this configuration
+
+
+def test_general_mcmc2_driver(constant):
+    """vignettes/constant_sim.Rmd:87-95 with niter = 5, burn1 = 3, 4 chains."""
+    from lnaphylodyn_b200 import api, mcmc, chains as chm, _lib
+    from lnaphylodyn_b200._lib import check
+    g = constant
+    coal, prior, proposal, control = vignette_args(g)
+    nch = len(g.x_r) - 1
+    B, niter, burn1, seed = 4, 5, 3, 5
+    res = mcmc.General_MCMC2(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=niter, burn=0, thin=1,
+                             changetime=g.x_r[1:], prior=prior, proposal=proposal, control=control,
+                             updateVec=(1, 1, 1, 0, 0.5, 1, 1), options={"burn1": burn1,
+                                                                        "parIdlist": {"a": 2, "b": 3, "c": 4, "d": 5 + nch},
+                                                                        "isLoglist": {"a": 1, "b": 0, "c": 1, "d": 0},
+                                                                        "priorIdlist": {"a": 1, "b": 2, "c": 3, "d": 5}},
+                             n_chains=B, seed=seed)
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    par0 = np.concatenate([[g.x_r[0], float(control["alpha"][0]) * g.x_r[0]], [control["R0"], control["gamma"]], control["ch"],
+                           [control["hyper"]]])
+    st = [driver.init_state(g, par0, control["traj"]) for _ in range(B)]
+    n2 = nch + 80
+    nrm, unf = np.empty((B, n2)), np.empty((B, chm.ITER2_UNIF))
+    for i in range(1, niter + 1):
+        check(_lib.lib().lna_draw_streams(pb.h, B, 0, n2, chm.ITER2_UNIF, seed, i, api._ptr(nrm), api._ptr(unf)))
+        for c in range(B):
+            st[c] = driver.mcmc2_iteration(st[c], g, driver.mcmc2_opts_from_golden(g, burn=i < burn1), nrm[c], unf[c])
+            assert relerr(res["par"][c, i - 1], st[c]["par"]) < TOL, (i, c)
+            assert res["l1"][c, i - 1] == pytest.approx(st[c]["coalLog"], rel=TOL)
+            assert relerr(res["Trajectory"][c, i - 1][:, 1:], st[c]["LatentTraj"][:, 1:]) < 1e-9
+    with pytest.raises(Exception):
+        mcmc.General_MCMC2(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=10, changetime=g.x_r[1:], prior=prior,
+                           proposal=proposal, control=control, options={"warmup2": 5})
+
+
+def test_initialisation_from_the_priors(changepoint):
+    """Without `control` the initial states are drawn from the priors and redrawn until the likelihood is finite."""
+    from lnaphylodyn_b200 import mcmc
+    g = changepoint
+    coal, prior, proposal, _ = vignette_args(g)
+    setting = mcmc.MCMC_setup_general(coal, g.times, g.t_correct, g.x_r[0], 50, 10, 0, 1, g.x_r[1:], ("S", "I"), prior, proposal,
+                                      {"alpha": [1e-6], "hyper": 20.0, "R0": 2.0}, "volz", "SIR", (0, 1), 2)
+    ini = mcmc.MCMC_initialize_general(setting, n_chains=64, rng=np.random.default_rng(3))
+    assert ini["par"].shape == (64, 44) and np.all(np.isfinite(ini["coalLog"])) and np.all(ini["coalLog"] > -1e7)
+    assert np.all(ini["par"][:, 2] == 2.0) and len(np.unique(ini["par"][:, 3])) == 64
+    assert np.all(ini["par"][:, 4:43] > 0) and np.allclose(ini["logOrigin"], -0.5 * np.sum(ini["OriginTraj"] ** 2, axis=(1, 2)))
