@@ -521,15 +521,20 @@ int ref_sirs_centred(int mode, const double *X_or_normals, const double *initial
     if (mode == 0) {
         *loglik = log_like_trajSIRS(M(X_or_normals, nrow, 4), M(OdeTraj, nrow, 4), ft, 1, t_correct);
     } else {
+#ifdef LNA_DROPIN  // the samplers of SIRS_period.cpp are outside the replaced path
+        return -1;
+#else
         streams(X_or_normals, (long)(nrow - 1) * 3, nullptr, 0);
         List r = Traj_sim_SIRS(V(initial, 3), M(OdeTraj, nrow, 4), ft, t_correct);
         put(as<arma::mat>(r[0]), traj_out);
         *loglik = as<double>(r[1]);
+#endif
     }
     return ORC_OK;
     REF_CATCH_STATUS
 }
 
+#ifndef LNA_DROPIN  // basic_util.cpp stays the reference's own file in a drop-in build
 // basic_util.cpp:5 / :16
 void ref_inv2(const double *a, double *res) {
     REF_TRY
@@ -541,5 +546,6 @@ void ref_chols(const double *S, double *L) {
     put(chols(M(S, 2, 2)), L);
     REF_CATCH_VOID
 }
+#endif
 
 }  // extern "C"

@@ -19,6 +19,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "liblna_ref.so")
+_SO_DROPIN = os.path.join(_HERE, "_ref", "liblna_dropin.so")
 REF_SRC = os.environ.get("LNA_REFERENCE_SRC", "/root/reference/src")
 
 
@@ -37,13 +38,30 @@ def available():
     return os.path.exists(_SO) or (os.path.isdir(REF_SRC) and build() is not None)
 
 
+def build_dropin(force=False):
+    """Compile oracle/_ref/liblna_dropin.so: the SAME harness (ref_harness.cpp) over integration/rcpp_shim.cpp -- the
+    reference-side binding that forwards every hot-path export to the C ABI -- instead of the reference's own bodies.
+    Needs the reference's header (LNA_functional.h) and the built CUDA library to link against."""
+    if not os.path.isdir(REF_SRC):
+        return _SO_DROPIN if os.path.exists(_SO_DROPIN) else None
+    cmd = ["make", "-C", _HERE, "-s", "dropin", f"REF_SRC={REF_SRC}"]
+    if force:
+        cmd.insert(1, "-B")
+    subprocess.check_call(cmd)
+    return _SO_DROPIN
+
+
+def dropin_available():
+    return os.path.exists(_SO_DROPIN) or (os.path.isdir(REF_SRC) and build_dropin() is not None)
+
+
 class _RefLib:
     """Maps orc_X -> ref_X of liblna_ref.so and raises on errors the reference would have thrown as R errors."""
 
-    def __init__(self):
-        if not os.path.exists(_SO) and build() is None:
-            raise RuntimeError("oracle/_ref/liblna_ref.so is missing and /root/reference is not here to build it")
-        self._dll = C.CDLL(_SO)
+    def __init__(self, so=_SO, builder=build):
+        if not os.path.exists(so) and builder() is None:
+            raise RuntimeError(f"{so} is missing and /root/reference is not here to build it")
+        self._dll = C.CDLL(so)
         self._dll.ref_last_error.restype = C.c_char_p
         for name in ("volz_loglik_nh2", "volz_loglik_nh3", "coal_loglik3", "coal_loglik", "log_like_traj_general2",
                      "ode_rk45_stop"):
@@ -79,13 +97,32 @@ def _get_lib():
     return _lib
 
 
-def _load_wrappers():
-    spec = importlib.util.spec_from_file_location("oracle._reference_wrappers", os.path.join(_HERE, "oracle.py"))
+def _load_wrappers(name="oracle._reference_wrappers", getter=None, builder=build):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(_HERE, "oracle.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    mod.lib = _get_lib
-    mod.build = build
+    mod.lib = getter or _get_lib
+    mod.build = builder
     return mod
+
+
+_dropin = None
+
+
+def dropin():
+    """The wrappers of oracle.py over liblna_dropin.so: `dropin().ESlice_par_General(...)` runs the reference-side
+    binding integration/rcpp_shim.cpp -> C ABI -> GPU, with the arguments of its reference and oracle twins."""
+    global _dropin
+    if _dropin is None:
+        holder = {}
+
+        def getter():
+            if "lib" not in holder:
+                holder["lib"] = _RefLib(_SO_DROPIN, build_dropin)
+            return holder["lib"]
+
+        _dropin = _load_wrappers("oracle._dropin_wrappers", getter, build_dropin)
+    return _dropin
 
 
 _w = _load_wrappers()

@@ -913,6 +913,12 @@ inline NullStream &shim_rcout() {
 }
 #define Rcout shim_rcout()
 
+// Rcpp::stop(msg) throws Rcpp::exception, which END_RCPP turns into an R error
+struct exception : std::runtime_error {
+    explicit exception(const std::string &m) : std::runtime_error(m) {}
+};
+[[noreturn]] inline void stop(const std::string &m) { throw exception(m); }
+
 }  // namespace Rcpp
 
 namespace R {

@@ -58,3 +58,33 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.lower() or f == "__init__.py" and False, f"{f} mentions the oracle"
+
+
+HOT_PATH_EXPORTS = """betaTs param_transform ODE_rk45 ODE_rk45_stop SigmaF KF_param KF_param_chol log_like_traj_general2
+log_like_traj_general_adjust Traj_sim_general3 Traj_sim_general_noncentral TransformTraj Traj_sim_ezG2 Traj_sim_ezG_NC
+coal_loglik3 coal_loglik volz_loglik_nh2 volz_loglik_nh3 Ode_Coarse_Slicer New_Param_List Update_Param Param_Slice_update
+Param_Slice_update_all2 ESlice_change_points ESlice_par_General ESlice_general_NC ESlice_general2""".split()
+
+
+def test_reference_side_binding_covers_the_export_list():
+    """integration/rcpp_shim.cpp defines every hot-path export of SURVEY.md section 8(b) (R/RcppExports.R names), and the
+    drop-in build of it (the reference's harness over the binding instead of the reference's bodies) links with no
+    unresolved symbol and exports the harness entry points the reference build exports."""
+    import ctypes as C
+    import subprocess
+    from oracle import reference as ref
+    src = open(os.path.join(ROOT, "integration", "rcpp_shim.cpp")).read()
+    for name in HOT_PATH_EXPORTS:
+        assert re.search(r"^[A-Za-z:<> ]+\b%s\(" % name, src, flags=re.M), f"{name} is not defined by the binding"
+    if not ref.dropin_available():
+        pytest.skip("oracle/_ref/liblna_dropin.so not built and /root/reference absent")
+    so = os.path.join(ROOT, "oracle", "_ref", "liblna_dropin.so")
+    C.CDLL(so)  # resolves liblnaphylodyn_b200.so through its rpath
+    def syms(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+        return {l.split()[-1] for l in out.splitlines() if " T ref_" in l}
+    mine = syms(so)
+    assert len(mine) >= 30
+    if ref.available():
+        theirs = syms(os.path.join(ROOT, "oracle", "_ref", "liblna_ref.so"))
+        assert theirs - mine <= {"ref_inv2", "ref_chols"}, theirs - mine  # basic_util.cpp stays the reference's own file
