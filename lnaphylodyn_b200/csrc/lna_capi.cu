@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "../../include/lnaphylodyn_b200.h"
@@ -427,6 +429,34 @@ static int launch_check(lna_problem *pb, const char *what) {
 
 static View item_view(const double *d, long long n) { return View{d, n, 1}; }
 static OutView item_out(double *d, long long n) { return OutView{d, n, 1}; }
+
+// Three-warp pipelined evaluation (lna_split.cuh): for launches that leave the machine mostly empty -- at most three
+// candidate warps per SM, so that the 3 x as many pipeline warps still find a sub-partition each -- and only when no second
+// stream group competes for the sub-partitions (chain batches of 2048 and more run as two groups, whose launches overlap:
+// measured, the pipeline then loses 5-12 %; below it wins 9-16 % per iteration, profiles/r1d_split_pipeline.md).
+// SIR only.  LNA_SPLIT=0 / 1 forces it off / on, LNA_SPLIT_MAX_WARPS overrides the threshold (experiments, tests).
+static bool use_split_eval(const lna_problem *pb, long long nthreads) {
+    if (pb->dp.model != LNA_MODEL_SIR || pb->dp.nch > lna::kSplitMaxCh) return false;
+    const char *e = getenv("LNA_SPLIT");
+    const int mode = e ? atoi(e) : -1;
+    if (mode == 0) return false;
+    if (mode == 1) return true;
+    if (pb->parent) return false;  // one of several concurrent stream groups
+    const char *w = getenv("LNA_SPLIT_MAX_WARPS");
+    const long long max_warps = w ? atoll(w) : (long long)pb->sm_count * 3;
+    return (nthreads + 31) / 32 <= max_warps;
+}
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory (once per kernel and device; all instantiations of a kernel
+// template share one function type, hence the address key).
+template <class K>
+static void big_smem_attr(K kern, int device) {
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done.insert({(const void *)kern, device}).second) return;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
 
 // Pick the block size so that small batches still spread over all SMs.
 static int pick_block(const lna_problem *pb, long long B) {

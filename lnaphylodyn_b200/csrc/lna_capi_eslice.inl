@@ -54,15 +54,34 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     const DevProb &P = pb->dp;
     const long long nthreads = nchains * W;
     const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, nthreads);
-    const unsigned grid = nblk(nthreads, block);
-#define LC(WW) k_cand_eval<kProp, WW><<<grid, block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, nchains, a)
+    // Launches that leave the SM sub-partitions at most about one warp each last as long as ONE evaluation takes ONE
+    // warp; there every candidate goes to a pipeline of three warps on three sub-partitions (lna_split.cuh).
+    const bool split = use_split_eval(pb, nthreads);
+#define LC2(WW, SPLIT)                                                                                              \
+    do {                                                                                                            \
+        if (SPLIT) {                                                                                                \
+            const int blk = 32 * kSplitWarps; /* one pipeline of three warps per block, ~53 KB of shared memory */   \
+            const size_t sm = full_eval_smem_bytes(pb->tab_bytes, blk) + split_group_bytes();                       \
+            auto kern = k_cand_eval<kProp, WW, SPLIT>;                                                              \
+            big_smem_attr(kern, pb->device);                                                                        \
+            kern<<<nblk(nthreads, 32), blk, sm, pb->stream>>>(P, pb->seg, nchains, a);                              \
+        } else {                                                                                                    \
+            k_cand_eval<kProp, WW, SPLIT><<<nblk(nthreads, block), block, full_eval_smem_bytes(pb->tab_bytes, block), \
+                                            pb->stream>>>(P, pb->seg, nchains, a);                                  \
+        }                                                                                                           \
+    } while (0)
+#define LC(WW)                      \
+    do {                            \
+        if (split) LC2(WW, true);   \
+        else LC2(WW, false);        \
+    } while (0)
     // only the (proposal, width) pairs that exist are instantiated: MH kinds are one lane per chain,
-    // the MH pair uses 4, the slice kinds any power of two
+    // the MH pair uses 4, the slice kinds any power of two (narrow slice launches are never latency-bound)
     constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
     if constexpr (kIsEss) {
         switch (W) {
-            case 1: LC(1); break;
-            case 2: LC(2); break;
+            case 1: LC2(1, false); break;
+            case 2: LC2(2, false); break;
             case 4: LC(4); break;
             case 8: LC(8); break;
             case 16: LC(16); break;
@@ -76,6 +95,7 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
         if (W != 1) return fail("Metropolis kernels use one lane per chain");
         LC(1);
     }
+#undef LC2
 #undef LC
     return launch_check(pb, "k_cand_eval");
 }

@@ -15,6 +15,7 @@
 // result, at 1/W of the sequential latency.
 #pragma once
 #include "lna_kernels.cuh"
+#include "lna_split.cuh"
 
 namespace lna {
 
@@ -199,12 +200,42 @@ __device__ __forceinline__ EssParPre ess_par_pre(const CandArgs &a, long long c,
 //   PROP_ESS_CHPT : ESlice_change_points (candidates 1..21, then revert; a Cholesky failure aborts)
 // SIR (p = 2) only, like the reference's samplers (hard-wired subvec(0,1) / subvec(2,..)).
 // ================================================================================================
-template <int kProp, int W>
+// kSplit: every candidate is evaluated by a pipeline of three warps (lna_split.cuh); the block then holds blockDim/96 groups,
+// warps 3j, 3j+1, 3j+2 = roles P, M, E of candidates [32 j, 32 j + 32).  The three warps run the same control flow below on
+// the same (handed-back) likelihoods; only E writes results.
+template <int kProp, int W, bool kSplit>
 __global__ void __launch_bounds__(128, 3)
 k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, CandArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Tables T = stage_tables(P, smem, true);
-    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int role = kSplit ? (warp_in_block % kSplitWarps) : 2;  // 0 = P (mean ODE), 1 = M (moments), 2 = E / the only warp
+    const int group = kSplit ? (warp_in_block / kSplitWarps) : 0;
+    const bool writer = role == 2;
+    SplitCtx sx{};
+    if (kSplit) {
+        unsigned char *group_smem = smem + full_eval_smem_bytes(tables_bytes(P.nch, P.k, P.n0), blockDim.x) +
+                                    (size_t)group * split_group_bytes();
+        sx = split_ctx(group_smem, threadIdx.x & 31);
+        if (role == 0 && (threadIdx.x & 31) == 0) split_reset(sx);
+    }
+    const Tables T = stage_tables(P, smem, true);  // (block-wide barrier inside: the counters above are visible after it)
+    const long long t0 = kSplit ? ((long long)blockIdx.x * (blockDim.x / (32 * kSplitWarps)) + group) * 32 + (threadIdx.x & 31)
+                                : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // one FULL evaluation of this lane's candidate; `on` = the lane really has one (the pipelined version runs all lanes,
+    // because its hand-over is warp-wide, and only suppresses the stores of the idle ones)
+    auto evaluate = [&](auto &chs, const EpsFromView &eps, const PropScalars &x, long long slot, bool on, double &ll, int &st) {
+        if (kSplit) {
+            if (role == 0) sir_split_P(sx, P, T, x.R0, x.gam, x.S0, x.I0, ll, st);
+            else if (role == 1) sir_split_M(sx, P, SD, T, x.R0, x.gam, ll, st);
+            else sir_split_E<true>(sx, P, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, slot, on, ll, st);
+            if (!on) {
+                ll = kSentinel;
+                st = 0;
+            }
+        } else if (on) {
+            sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, slot, ll, st);
+        }
+    };
     const long long ci = t0 / W;  // index into the (optional) compacted chain list
     const int w = (int)(t0 % W);
     const long long t = a.slot_base + t0;  // scratch slot of this thread's candidate
@@ -247,16 +278,16 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
         x.noop = (w >= 1);
         double ll = kSentinel;
         int st = 0;
-        if (valid && w <= 2) {  // one instruction stream for the three lanes (no divergence)
-            ChProp<PROP_MH_PAIR> chs{a.par, a.normals, c, 4, x};
-            sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+        {  // one instruction stream for the three lanes (no divergence)
+            ChProp<PROP_MH_PAIR> chs{a.par, a.normals, cc, 4, x};
+            evaluate(chs, eps, x, t, valid && w <= 2, ll, st);
         }
         const int base = lane & ~3;
         const double ll0 = __shfl_sync(0xffffffffu, ll, base), ll1 = __shfl_sync(0xffffffffu, ll, base + 1),
                      ll2 = __shfl_sync(0xffffffffu, ll, base + 2);
         const int st0 = __shfl_sync(0xffffffffu, st, base), st1 = __shfl_sync(0xffffffffu, st, base + 1),
                   st2 = __shfl_sync(0xffffffffu, st, base + 2);
-        if (valid && w == 0) {
+        if (valid && w == 0 && writer) {
             const double cl = a.coal_log[c];
             const bool acc1 = !(st0 & ST_CHOL_FAIL) && (log(unif(1)) < ll0 - cl + offset);
             const double cur = acc1 ? ll0 : cl;
@@ -274,7 +305,8 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
         return;
     } else if (!kIsEss) {
         // ---- Metropolis step: Update_Param_each_Norm entry + Update_Param ------------------------
-        if (!valid) return;
+        if (!valid && !kSplit) return;
+        c = cc;  // (idle lanes of a pair warp evaluate chain 0 and write nothing)
         PropScalars x;
         x.S0 = a.par.at(c, 0);
         x.I0 = a.par.at(c, 1);
@@ -316,9 +348,10 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
             prop = x.hyper_new;
         }
         ChProp<kProp> chs{a.par, a.normals, c, 4, x};
-        double ll;
+        double ll = kSentinel;
         int st = 0;
-        sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+        evaluate(chs, eps, x, t, valid, ll, st);
+        if (!valid || !writer) return;
         const double u = unif(iu);
         const double acc_a = ll - a.coal_log[c] + offset;
         // a Cholesky failure is an exception in the reference: tryCatch keeps the old state
@@ -350,12 +383,13 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
             const bool active = !done && i <= kMaxCand + 1;
             double ll = kSentinel;
             int st = 0;
-            if (active) {
+            const bool any_active = kSplit ? __any_sync(0xffffffffu, active) != 0 : false;  // (all lanes vote)
+            if (active || any_active) {
                 PropScalars x;
-                if (!is_revert) ts.advance(i, unif);
-                const double th = is_revert ? 0.0 : ts.th;
+                if (active && !is_revert) ts.advance(i, unif);
+                const double th = (is_revert || !active) ? 0.0 : ts.th;
                 if (kProp == PROP_ESS_PAR) {
-                    ess_par_scalars(a, c, npar, zpre, th, x);
+                    ess_par_scalars(a, cc, npar, zpre, th, x);
                 } else {
                     double sn, ct;
                     sincos(th, &sn, &ct);
@@ -364,17 +398,17 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
                     x.hyper_old = x.hyper_new = hyper_old;
                     x.rot_ch = 1;
                 }
-                x.S0 = a.par.at(c, 0);
-                if (kProp != PROP_ESS_PAR || is_revert) {  // current parameters, bit for bit
-                    x.I0 = a.par.at(c, 1);
-                    x.R0 = a.par.at(c, 2);
-                    x.gam = a.par.at(c, 3);
+                x.S0 = a.par.at(cc, 0);
+                if (kProp != PROP_ESS_PAR || is_revert || !active) {  // current parameters, bit for bit
+                    x.I0 = a.par.at(cc, 1);
+                    x.R0 = a.par.at(cc, 2);
+                    x.gam = a.par.at(cc, 3);
                 }
-                if (is_revert) x.rot_ch = 0;
+                if (is_revert || !active) x.rot_ch = 0;
                 x.noop = 0;
                 // one instruction stream for shrink and revert candidates (no divergence inside the warp)
-                ChProp<kProp> chs{a.par, a.normals, c, 4, x};
-                sir_full_eval<true>(P, SD, T, chs, eps, x.R0, x.gam, x.S0, x.I0, a.cand, t, ll, st);
+                ChProp<kProp> chs{a.par, a.normals, cc, 4, x};
+                evaluate(chs, eps, x, t, active, ll, st);
             }
             const bool failed = active && (st & ST_CHOL_FAIL);
             // ESlice_par_General catches the exception and shrinks on (:1641-1651); ESlice_change_points
@@ -385,7 +419,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
             const unsigned m = __ballot_sync(0xffffffffu, stop_here) & gmask;
             if (!done && m) {
                 const int winner = __ffs(m) - 1;
-                if (lane == winner) {
+                if (lane == winner && writer) {
                     a.win_slot[c] = failed ? -1 : (int)t;
                     a.cand_ll[c] = ll;
                     a.theta[c] = is_revert ? 0.0 : ts.th;
@@ -395,7 +429,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
                 done = true;
             }
             if (!done && a.max_waves && wave + 1 == a.max_waves) {
-                if (w == 0) a.next_list[atomicAdd(a.next_count, 1)] = (int)c;  // hand over to the next phase
+                if (w == 0 && writer) a.next_list[atomicAdd(a.next_count, 1)] = (int)c;  // hand over to the next phase
                 done = true;
             }
             if (!__any_sync(0xffffffffu, !done)) break;

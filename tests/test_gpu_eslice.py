@@ -316,3 +316,63 @@ def test_chain_stream_groups_equal_single_group(api, changepoint, monkeypatch):
     for c, r in ref.items():
         assert relerr(a["par"][c], r["par"]) < TOL and a["coalLog"][c] == pytest.approx(r["coalLog"], rel=TOL)
         assert a["n_full_evals"][c] == r["n_full"]
+
+
+@pytest.mark.parametrize("B", [5, 96, 700])
+def test_three_warp_pipeline_is_bit_identical(api, changepoint, monkeypatch, B):
+    """csrc/lna_split.cuh: the latency-bound launches evaluate every candidate with a pipeline of three warps (mean ODE ->
+    LNA moments -> interval epilogues) instead of one.  Same expressions in the same order, so the chains it produces must
+    equal the one-warp kernels' BIT FOR BIT -- parameters, latent trajectories, likelihoods and counters -- over several
+    iterations, for ragged batches (idle lanes), partially filled warps and multi-wave slice launches."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    iters, seed = 5, 123
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LNA_SPLIT", mode)
+        ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+        for it in range(iters):
+            ch.step_rng(chm.vignette_opts(g, update_traj=it >= 1), seed, it)
+        runs[mode] = ch.get()
+    a, b = runs["0"], runs["1"]
+    for key in ("par", "OriginTraj", "LatentTraj", "coalLog", "logOrigin", "n_full_evals", "n_cheap_evals", "n_mh_accept"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.all(np.isfinite(b["coalLog"])) and len(np.unique(b["coalLog"])) > B // 2
+
+
+def test_three_warp_pipeline_standalone_entry_points(api, changepoint, monkeypatch):
+    """The same through the standalone operators (ESlice_par_General with several in-kernel waves, ESlice_change_points,
+    Update_Param), including a proposal whose Cholesky fails and the 20-shrink cap."""
+    g = changepoint
+    par = g.final["par"].ravel().copy()
+    eps = g.final["OriginTraj"].copy()
+    rng = np.random.default_rng(5)
+    cl = float(g.final["coalLog"][0])
+    PRI = [(1.0, 1.0), (0.7, 0.5), (-1.7, 0.1), (3.0, 0.2)]
+    wild = [(1.0, 1.0), (0.7, 40.0), (-1.7, 0.1), (3.0, 0.2)]
+    cases = []
+    for s in range(6):
+        nrm, unf = rng.standard_normal(43), rng.uniform(size=22)
+        cases.append(("par", PRI, cl, nrm, unf))
+        cases.append(("par", wild, cl, 3.0 * nrm, unf))
+    cases.append(("par", PRI, 1e6, rng.standard_normal(43), rng.uniform(size=22)))  # cap
+    nrm_cp, unf_cp = rng.standard_normal(39), rng.uniform(size=22)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LNA_SPLIT", mode)
+        res = []
+        for kind, pri, c0, nrm, unf in cases:
+            for W in (0, 4):
+                r = api.ESlice_par_General(par, g.times, eps, pri, g.x_r, g.x_i, g.init, g.gridsize, [0, 1, 0, 0, 1, 1, 0], c0,
+                                           g.t_correct, normals=nrm, uniforms=unf, spec_width=W)
+                res.append((r["par"], r["LatentTraj"], r["CoalLog"], r["n_evals"], r["status"], r["FT"]["Sigma"]))
+        r = api.ESlice_change_points(par[2:], par[:2], g.times, eps, g.x_r, g.x_i, g.init, g.gridsize, cl, g.t_correct,
+                                     normals=nrm_cp, uniforms=unf_cp)
+        res.append((r["param"], r["LatentTraj"], r["CoalLog"], r["n_evals"], r["status"], r["FT"]["A"]))
+        out[mode] = res
+    for x, y in zip(out["0"], out["1"]):
+        for u, v in zip(x, y):
+            assert np.array_equal(np.asarray(u), np.asarray(v))
