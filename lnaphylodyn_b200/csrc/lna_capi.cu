@@ -20,6 +20,7 @@
 
 #include "../../include/lnaphylodyn_b200.h"
 #include "lna_kernels.cuh"
+#include "lna_split.cuh"
 #include "lna_eslice.cuh"
 
 using namespace lna;
@@ -435,7 +436,7 @@ static OutView item_out(double *d, long long n) { return OutView{d, n, 1}; }
 // stream group competes for the sub-partitions (chain batches of 2048 and more run as two groups, whose launches overlap:
 // measured, the pipeline then loses 5-12 %; below it wins 9-16 % per iteration, profiles/r1d_split_pipeline.md).
 // SIR only.  LNA_SPLIT=0 / 1 forces it off / on, LNA_SPLIT_MAX_WARPS overrides the threshold (experiments, tests).
-static bool use_split_eval(const lna_problem *pb, long long nthreads) {
+static bool use_split_eval(const lna_problem *pb, long long nthreads, int warps_per_sm = 3) {
     if (pb->dp.model != LNA_MODEL_SIR || pb->dp.nch > lna::kSplitMaxCh) return false;
     const char *e = getenv("LNA_SPLIT");
     const int mode = e ? atoi(e) : -1;
@@ -443,7 +444,7 @@ static bool use_split_eval(const lna_problem *pb, long long nthreads) {
     if (mode == 1) return true;
     if (pb->parent) return false;  // one of several concurrent stream groups
     const char *w = getenv("LNA_SPLIT_MAX_WARPS");
-    const long long max_warps = w ? atoll(w) : (long long)pb->sm_count * 3;
+    const long long max_warps = w ? atoll(w) : (long long)pb->sm_count * warps_per_sm;
     return (nthreads + 31) / 32 <= max_warps;
 }
 
@@ -489,7 +490,19 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
     const View vp = item_view(param, P.npt), vi = item_view(initial, p), vo = item_view(origin, (long long)P.k * p);
 #define LAUNCH(MODEL, STORE)                                                                                     \
     k_full_loglik<MODEL, STORE><<<grid, block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status)
-    if (P.model == LNA_MODEL_SIR) {
+    if (P.model == LNA_MODEL_SIR && use_split_eval(pb, B, 1)) {
+        // small batch (measured: up to ~one item warp per SM, 0.82 of the one-warp kernel's call latency at B = 1..32, break-even
+        // near 4096 items): the launch lasts as long as one evaluation takes one warp -> three-warp pipeline (lna_split.cuh)
+        const int blk = 32 * lna::kSplitWarps;
+        const size_t sm = full_eval_smem_bytes(pb->tab_bytes, blk) + lna::split_group_bytes();
+        if (store) {
+            big_smem_attr(k_full_loglik_split<true>, pb->device);
+            k_full_loglik_split<true><<<nblk(B, 32), blk, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status);
+        } else {
+            big_smem_attr(k_full_loglik_split<false>, pb->device);
+            k_full_loglik_split<false><<<nblk(B, 32), blk, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status);
+        }
+    } else if (P.model == LNA_MODEL_SIR) {
         if (store) LAUNCH(0, true);
         else LAUNCH(0, false);
     } else {

@@ -356,4 +356,44 @@ __device__ __forceinline__ void sir_split_E(SplitCtx &c, const DevProb &P, const
     c.evals += 1;
 }
 
+// ================================================================================================
+// FULL evaluations of a SMALL batch (one Update_Param / New_Param_List call of a single chain, a handful of proposals):
+// the same pipeline, one group of three warps per 32 items.  Item-major inputs like k_full_loglik.
+// ================================================================================================
+template <bool kStore>
+__global__ void __launch_bounds__(96, 4)
+k_full_loglik_split(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, View param, View initial,
+                    View origin, FullOut out, double *coalLog, int *status) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 0 = P, 1 = M, 2 = E
+    SplitCtx sx = split_ctx(smem + full_eval_smem_bytes(tables_bytes(P.nch, P.k, P.n0), blockDim.x), lane);
+    if (role == 0 && lane == 0) split_reset(sx);
+    const Tables T = stage_tables(P, smem, true);
+    const long long b0 = (long long)blockIdx.x * 32 + lane;
+    const bool on = b0 < B;
+    const long long b = on ? b0 : 0;  // idle lanes evaluate item 0 and write nothing (the hand-overs are warp-wide)
+    const double R0 = param.at(b, P.iR0), gam = param.at(b, 1);
+    const double S0 = initial.at(b, 0), I0 = initial.at(b, 1);
+    double ll = kSentinel;
+    int st = 0;
+    if (role == 0) {
+        sir_split_P(sx, P, T, R0, gam, S0, I0, ll, st);
+    } else if (role == 1) {
+        sir_split_M(sx, P, SD, T, R0, gam, ll, st);
+    } else {
+        ChFromParam chs{param, b, P.nparam};
+        if (origin.ok()) {
+            EpsFromView eps{origin, b, P.k};
+            sir_split_E<kStore>(sx, P, T, chs, eps, R0, gam, S0, I0, out, b, on, ll, st);
+        } else {
+            EpsZero eps;
+            sir_split_E<kStore>(sx, P, T, chs, eps, R0, gam, S0, I0, out, b, on, ll, st);
+        }
+        if (on) {
+            if (coalLog) coalLog[b] = ll;
+            if (status) status[b] = st;
+        }
+    }
+}
+
 }  // namespace lna
