@@ -36,8 +36,11 @@ extern "C" {
  * nparam = 4, x_r[0] = period): ODE2, SIRS_KOM_Filter and log_like_trajSIRS only -- the reference has no
  * non-centred / sampler path for it. */
 enum { LNA_MODEL_SIR = 0, LNA_MODEL_SEIR = 1, LNA_MODEL_SIRS_PERIOD = 2 };
-/* transX: only "standard" is on the GPU path ("log" is legacy) */
-enum { LNA_TRANSX_STANDARD = 0 };
+/* transX: "standard" everywhere; "log" (the reference's legacy log-scale LNA) for model SIR in the
+ * integrator / LNA-moment / likelihood entry points (lna_ode_rk45, lna_kf_param, lna_new_param_list, lna_full_loglik,
+ * lna_transform_traj, lna_volz_loglik_nh2/3, lna_coal_loglik); the Metropolis / slice operators are standard-scale only,
+ * like every driver of the reference that calls them. */
+enum { LNA_TRANSX_STANDARD = 0, LNA_TRANSX_LOG = 1 };
 
 /* per-item status bits (reference failure channels) */
 enum {
@@ -54,7 +57,7 @@ enum {
  * hot-path export repeats (e.g. New_Param_List, LNA_functional.cpp:1191-1193). */
 typedef struct lna_cfg {
     int model;          /* LNA_MODEL_*                                                        */
-    int transX;         /* LNA_TRANSX_STANDARD                                                */
+    int transX;         /* LNA_TRANSX_STANDARD | LNA_TRANSX_LOG                               */
     int nch;            /* x_i[0]: number of R0 change points                                 */
     int nparam;         /* x_i[1]: number of model parameters before the change ratios        */
     int iR0;            /* x_i[2]: index of R0 in `param`; also the S column for volz         */

@@ -86,7 +86,7 @@ struct InitView {  // the entries of coal_lik_init()'s list the likelihoods read
 };
 
 lna_problem *problem_for(const arma::vec &t, const arma::vec &x_r, const int (&xi)[4], int gridsize, double t_correct,
-                         const InitView &ini, int model) {
+                         const InitView &ini, int model, int transX = LNA_TRANSX_STANDARD) {
     static std::map<std::string, lna_problem *> cache;
     std::string key;
     key_add(key, t.memptr(), sizeof(double) * t.n_elem);
@@ -95,6 +95,7 @@ lna_problem *problem_for(const arma::vec &t, const arma::vec &x_r, const int (&x
     key_add(key, &gridsize, sizeof gridsize);
     key_add(key, &t_correct, sizeof t_correct);
     key_add(key, &model, sizeof model);
+    key_add(key, &transX, sizeof transX);
     if (ini.present) {
         key_add(key, ini.C.memptr(), sizeof(double) * ini.C.n_elem);
         key_add(key, ini.D.memptr(), sizeof(double) * ini.D.n_elem);
@@ -105,7 +106,7 @@ lna_problem *problem_for(const arma::vec &t, const arma::vec &x_r, const int (&x
     if (it != cache.end()) return it->second;
     lna_cfg cfg;
     cfg.model = model;
-    cfg.transX = LNA_TRANSX_STANDARD;
+    cfg.transX = transX;
     cfg.nch = xi[0];
     cfg.nparam = xi[1];
     cfg.iR0 = xi[2];
@@ -134,24 +135,29 @@ lna_problem *problem_for(const arma::vec &t, const arma::vec &x_r, const int (&x
     return pb;
 }
 
-int model_id(const std::string &model, const std::string &transX) {
-    if (transX != "standard") Rcpp::stop("GPU path: transX must be \"standard\"");
+int model_id(const std::string &model) {
     if (model == "SIR") return LNA_MODEL_SIR;
     if (model == "SEIR") return LNA_MODEL_SEIR;
     Rcpp::stop("GPU path: model must be \"SIR\" or \"SEIR\"");
 }
+int transx_id(const std::string &transX) {
+    if (transX == "standard") return LNA_TRANSX_STANDARD;
+    if (transX == "log") return LNA_TRANSX_LOG;  // (accepted for model SIR; the library says so otherwise)
+    Rcpp::stop("GPU path: transX must be \"standard\" or \"log\"");
+}
 lna_problem *problem_xi(const arma::vec &t, const arma::vec &x_r, const arma::ivec &x_i, int gridsize, double t_correct,
                         const InitView &ini, const std::string &model, const std::string &transX) {
     const int xi[4] = {(int)x_i[0], (int)x_i[1], (int)x_i[2], (int)x_i[3]};
-    return problem_for(t, x_r, xi, gridsize, t_correct, ini, model_id(model, transX));
+    return problem_for(t, x_r, xi, gridsize, t_correct, ini, model_id(model), transx_id(transX));
 }
 // problems for calls that carry only a coarse trajectory: its own time column is the grid, gridsize 1
-lna_problem *traj_problem(const arma::mat &traj, double t_correct, const InitView &ini, int iS, int iI) {
+lna_problem *traj_problem(const arma::mat &traj, double t_correct, const InitView &ini, int iS, int iI,
+                          int transX = LNA_TRANSX_STANDARD) {
     const int p = (int)traj.n_cols - 1;
     arma::vec times = traj.col(0), x_r(1);
     x_r[0] = 1.0;
     const int xi[4] = {0, p == 2 ? 2 : 3, iS, iI};
-    return problem_for(times, x_r, xi, 1, t_correct, ini, p == 2 ? LNA_MODEL_SIR : LNA_MODEL_SEIR);
+    return problem_for(times, x_r, xi, 1, t_correct, ini, p == 2 ? LNA_MODEL_SIR : LNA_MODEL_SEIR, transX);
 }
 struct Dims {
     int p, k, nrow, npt;
@@ -337,8 +343,7 @@ List Traj_sim_ezG_NC(arma::vec initial, arma::vec times, arma::vec param, int gr
 // ---- a9: volz_loglik_nh2 :1119-1176, volz_loglik_nh3 :1058-1113, coal_loglik3 :1016-1054, coal_loglik -----------------
 static double volz_impl(List init, const arma::mat &f1, const arma::vec &betaN, double t_correct, const arma::ivec &index,
                         const std::string &transX, bool nan_guard) {
-    if (transX != "standard") Rcpp::stop("GPU path: transX must be \"standard\"");
-    lna_problem *pb = traj_problem(f1, t_correct, InitView(init), (int)index[0], (int)index[1]);
+    lna_problem *pb = traj_problem(f1, t_correct, InitView(init), (int)index[0], (int)index[1], transx_id(transX));
     double ll = 0;
     int32_t st = 0;
     if (nan_guard) LNA_CALL(lna_volz_loglik_nh2(pb, 1, f1.memptr(), betaN.memptr(), &ll, &st), "lna_volz_loglik_nh2");

@@ -45,12 +45,12 @@ class Problem:
                  device=0):
         if model not in MODELS:
             raise LnaError(f"model {model!r} is not on the GPU path (SIR, SEIR)")
-        if transX != "standard":
-            raise LnaError('only transX="standard" is on the GPU path')
+        if transX not in ("standard", "log"):
+            raise LnaError(f"transX {transX!r}: must be \"standard\" or \"log\"")
         self.times, self.x_r = _d(times), _d(x_r)
         self.x_i = _xi(x_i)
         self.model, self.gridsize, self.t_correct, self.device = model, int(gridsize), float(t_correct), int(device)
-        cfg = LnaCfg(MODELS[model], 0, self.x_i[0], self.x_i[1], self.x_i[2], self.x_i[3], self.gridsize,
+        cfg = LnaCfg(MODELS[model], 1 if transX == "log" else 0, self.x_i[0], self.x_i[1], self.x_i[2], self.x_i[3], self.gridsize,
                      len(self.times), self.times.ctypes.data_as(_lib._dp), self.x_r.ctypes.data_as(_lib._dp),
                      self.t_correct)
         ini_ref = None

@@ -153,8 +153,9 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
         fail("lna_problem_create: SIRS_PERIOD takes param = (beta, gamma, mu, alpha), no change points, no genealogy");
         return nullptr;
     }
-    if (cfg->transX != LNA_TRANSX_STANDARD) {
-        fail("lna_problem_create: only transX=\"standard\" is implemented on the GPU path");
+    if (cfg->transX != LNA_TRANSX_STANDARD && !(cfg->transX == LNA_TRANSX_LOG && cfg->model == LNA_MODEL_SIR)) {
+        fail("lna_problem_create: transX must be \"standard\", or \"log\" with model SIR (the reference's SEIR log-scale "
+             "moments are never used by the package and not provided)");
         return nullptr;
     }
     if (cfg->nt < 2 || cfg->gridsize < 1 || cfg->nch < 0 || cfg->nparam < 2) {
@@ -201,6 +202,7 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     P.npt = cfg->model == LNA_MODEL_SIRS_PERIOD ? 4 : cfg->nparam + cfg->nch + 1;
     P.N = cfg->x_r[0];
     P.t_correct = cfg->t_correct;
+    P.transX = cfg->transX;
     pb->times.assign(cfg->times, cfg->times + cfg->nt);
     pb->x_r.assign(cfg->x_r, cfg->x_r + cfg->nch + 1);
     pb->cfg = *cfg;
@@ -470,6 +472,66 @@ static int pick_block(const lna_problem *pb, long long B) {
 // ------------------------------------------------------------------------------------------------
 // FULL evaluation
 // ------------------------------------------------------------------------------------------------
+// merge of the factorisation status into the likelihood of the composed (log-scale) FULL evaluation
+__global__ void k_merge_full_status(long long B, const int *st_chol, const int *st_volz, double *coalLog, int *status) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int st = st_chol[b] & lna::ST_CHOL_FAIL;
+    if (st) {
+        if (coalLog) coalLog[b] = lna::kSentinel;
+    } else if (st_volz) {
+        st |= st_volz[b];
+    }
+    if (status) status[b] = st;
+}
+
+static int volz_events_dev(lna_problem *pb, int64_t B, const double *traj, const double *betaN, double *ll, int32_t *st,
+                           int nan_guard);
+
+// FULL evaluation on the LOG scale (transX = "log", SIR): the reference's legacy variant, not a hot path -- composed from the
+// per-export kernels exactly as New_Param_List / TransformTraj / volz_loglik_nh2 compose them (:1191-1208, :1217-1226).
+static int full_loglik_log_dev(lna_problem *pb, int64_t B, const double *param, const double *initial, const double *origin,
+                               double *coalLog, int32_t *status, double *A, double *L, double *ode, double *betaN,
+                               double *latent) {
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, p = P.p, cube = p * p * P.k, nO = (size_t)P.nrow * (p + 1);
+    const size_t base = 48;  // scratch slots of this path (the host wrappers stage below 32)
+    double *fine = (double *)pb->scratch.get(base + 0, sizeof(double) * nB * P.nt * (p + 1));
+    double *dA = A ? A : (double *)pb->scratch.get(base + 1, sizeof(double) * nB * cube);
+    double *dL = L ? L : (double *)pb->scratch.get(base + 2, sizeof(double) * nB * cube);
+    double *dode = ode ? ode : (double *)pb->scratch.get(base + 3, sizeof(double) * nB * nO);
+    double *dbn = betaN ? betaN : (double *)pb->scratch.get(base + 4, sizeof(double) * nB * P.nrow);
+    double *dlat = latent ? latent : (double *)pb->scratch.get(base + 5, sizeof(double) * nB * nO);
+    double *ctimes = (double *)pb->scratch.get(base + 6, sizeof(double) * P.nrow);
+    int32_t *stc = (int32_t *)pb->scratch.get(base + 7, sizeof(int32_t) * nB);
+    int32_t *stv = (int32_t *)pb->scratch.get(base + 8, sizeof(int32_t) * nB);
+    double *zero = origin ? nullptr : (double *)pb->scratch.get(base + 9, sizeof(double) * nB * P.k * p);
+    if (!fine || !dA || !dL || !dode || !dbn || !dlat || !ctimes || !stc || !stv || (!origin && !zero))
+        return fail("lna_full_loglik (log scale): device scratch allocation failed");
+    const View vp = item_view(param, P.npt), vi = item_view(initial, p);
+    k_ode_rk45<3><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, vi, vp, fine);
+    if (launch_check(pb, "k_ode_rk45")) return -1;
+    CK(cudaMemsetAsync(stc, 0, nB * sizeof(int32_t), pb->stream));
+    k_kf_param<3><<<nblk((long long)B * P.k, 128), 128, 0, pb->stream>>>(P, B, fine, vp, 1, dA, dL, stc);
+    if (launch_check(pb, "k_kf_param")) return -1;
+    k_coarse_slicer<<<nblk((long long)(nB * nO), 256), 256, 0, pb->stream>>>(P.nt, (int)p + 1, P.g, P.nrow, B, fine, dode);
+    if (launch_check(pb, "k_coarse_slicer")) return -1;
+    std::vector<double> ct(P.nrow);
+    for (int r = 0; r < P.nrow; ++r) ct[r] = pb->times[(size_t)r * P.g];
+    CK(cudaMemcpyAsync(ctimes, ct.data(), sizeof(double) * P.nrow, cudaMemcpyHostToDevice, pb->stream));
+    CK(cudaStreamSynchronize(pb->stream));  // (ct is a host temporary)
+    k_betaTs<<<nblk(B, 128), 128, 0, pb->stream>>>(P, B, vp, ctimes, P.nrow, dbn);
+    if (launch_check(pb, "k_betaTs")) return -1;
+    if (!origin) CK(cudaMemsetAsync(zero, 0, sizeof(double) * nB * P.k * p, pb->stream));
+    k_transform_traj<2><<<nblk(B, 64), 64, 0, pb->stream>>>(P.k, B, dode, origin ? origin : zero, dA, dL, 0, P.t_correct, dlat,
+                                                            nullptr, nullptr, nullptr);
+    if (launch_check(pb, "k_transform_traj")) return -1;
+    const bool want_ll = coalLog != nullptr;
+    if (want_ll && volz_events_dev(pb, B, dlat, dbn, coalLog, stv, 1)) return -1;
+    k_merge_full_status<<<nblk(B, 128), 128, 0, pb->stream>>>(B, stc, want_ll ? stv : nullptr, coalLog, status);
+    return launch_check(pb, "k_merge_full_status");
+}
+
 static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param, const double *initial,
                                 const double *origin, double *coalLog, int32_t *status, double *A, double *L,
                                 double *ode, double *betaN, double *latent) {
@@ -480,6 +542,8 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
         return fail("lna_full_loglik: the seasonal SIRS variant has no non-centred path in the reference "
                     "(use lna_ode_rk45 / lna_kf_param / lna_log_like_traj_sirs)");
     if (coalLog && !P.has_init) return fail("lna_full_loglik: problem was created without a genealogy");
+    if (P.transX == LNA_TRANSX_LOG)
+        return full_loglik_log_dev(pb, B, param, initial, origin, coalLog, status, A, L, ode, betaN, latent);
     const int p = P.p;
     FullOut out{item_out(A, (long long)p * p * P.k), item_out(L, (long long)p * p * P.k),
                 item_out(ode, (long long)P.nrow * (p + 1)), item_out(betaN, P.nrow),
@@ -664,7 +728,9 @@ extern "C" int lna_ode_rk45(lna_problem *pb, int64_t B, const double *initial, c
     const double *dini = s.in(initial, nB * p), *dpar = s.in(param, nB * P.npt);
     double *dout = s.out(OdeTraj, nB * per);
     if (!s.ok || !dini || !dpar || !dout) return fail("lna_ode_rk45: bad arguments / staging failed");
-    if (P.model == LNA_MODEL_SIR)
+    if (P.model == LNA_MODEL_SIR && P.transX == LNA_TRANSX_LOG)
+        k_ode_rk45<3><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
+    else if (P.model == LNA_MODEL_SIR)
         k_ode_rk45<0><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
     else if (P.model == LNA_MODEL_SEIR)
         k_ode_rk45<1><<<nblk(B, 64), 64, 0, pb->stream>>>(P, B, item_view(dini, p), item_view(dpar, P.npt), dout);
@@ -690,7 +756,9 @@ extern "C" int lna_kf_param(lna_problem *pb, int64_t B, const double *OdeTraj, c
     const long long n = (long long)B * P.k;
     if (P.model == LNA_MODEL_SIRS_PERIOD && chol)
         return fail("lna_kf_param: SIRS_PERIOD has a rank-deficient covariance; only chol = 0 (SIRS_KOM_Filter) is provided");
-    if (P.model == LNA_MODEL_SIR)
+    if (P.model == LNA_MODEL_SIR && P.transX == LNA_TRANSX_LOG)
+        k_kf_param<3><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);
+    else if (P.model == LNA_MODEL_SIR)
         k_kf_param<0><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);
     else if (P.model == LNA_MODEL_SEIR)
         k_kf_param<1><<<nblk(n, 128), 128, 0, pb->stream>>>(P, B, dtr, item_view(dpar, P.npt), chol, dA, dS, dst);

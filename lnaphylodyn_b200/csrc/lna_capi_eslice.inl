@@ -203,6 +203,9 @@ static int check_sir_sampler(const lna_problem *pb, const char *what) {
     if (pb->dp.model != LNA_MODEL_SIR || pb->dp.nparam != 2)
         return fail("%s: the reference's samplers are hard-wired to SIR (p = 2, nparam = 2)", what);
     if (!pb->dp.has_init) return fail("%s: problem was created without a genealogy", what);
+    if (pb->dp.transX != LNA_TRANSX_STANDARD)
+        return fail("%s: the Metropolis / slice operators work on the standard scale (transX = \"standard\"), like every "
+                    "driver of the reference that calls them", what);
     return 0;
 }
 

@@ -40,6 +40,7 @@ struct DevProb {
     int Lrow;      // first coarse row with time >= t_correct (capped at nrow-1)
     int idxS, idxI;// state columns used by the Volz likelihood (x_i[2], x_i[3])
     int has_init;
+    int transX;    // 0 standard, 1 log (per-export kernels only; the fused evaluation is standard-scale)
     double N, dt_ode, t_correct;
     // dt-derived constants computed on the host: as kernel parameters they are constant-bank operands,
     // which keeps the DFMAs that use them at full issue rate (a DFMA with three distinct REGISTER

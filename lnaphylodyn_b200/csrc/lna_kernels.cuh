@@ -175,6 +175,26 @@ struct Model<2> {  // seasonal SIRS (src/SIRS_period.cpp): states (S, I, R), th 
         Qm[6] = -h2;     Qm[7] = -h1;     Qm[8] = h1 + h2;
     }
 };
+template <>
+struct Model<3> {  // SIR on the log scale (transX = "log"): states (log S, log I)
+    static constexpr int P = 2;
+    __device__ static void rhs(const double *x, const double *th, double *d) {  // ODE_SIR_one :117-119
+        d[0] = -th[0] * exp(x[1]) - th[0] * exp(x[1] - x[0]) / 2;
+        d[1] = th[0] * exp(x[0]) - th[1] - th[0] * exp(x[0] - x[1]) / 2 - th[1] * exp(-x[1]) / 2;
+    }
+    __device__ static void F(const double *x, const double *th, double *Fm) {  // SIR_F :256-258
+        Fm[0] = th[0] * exp(x[1] - x[0]) / 2;
+        Fm[1] = -th[0] * exp(x[1]) - th[0] / 2 * exp(x[1] - x[0]);
+        Fm[2] = th[0] * exp(x[0]) - th[0] * exp(x[0] - x[1]) / 2;
+        Fm[3] = th[0] * exp(x[0] - x[1]) / 2 + th[1] / 2 * exp(-x[1]);
+    }
+    __device__ static void Q(const double *x, const double *th, double *Qm) {  // Q A' diag(h) A Q, Q = diag(exp(-x)) :577-589
+        const double h0 = th[0] * exp(x[0]) * exp(x[1]), h1 = th[1] * exp(x[1]);  // SIR_h :310-311
+        const double q0 = exp(-x[0]), q1 = exp(-x[1]);
+        Qm[0] = q0 * h0 * q0;  Qm[1] = q0 * -h0 * q1;
+        Qm[2] = q1 * -h0 * q0; Qm[3] = q1 * (h0 + h1) * q1;
+    }
+};
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
 // ODE_rk45 (LNA_functional.cpp:455-491): full fine trajectory, one thread per item.
@@ -534,8 +554,10 @@ __global__ void k_volz_events(DevProb P, long long B, const double *traj, const 
     double *cq = cellq + (size_t)w * P.n0, *cl = celll + (size_t)w * P.n0;
     for (int i = lane; i < P.n0; i += 32) {
         const int row = P.Lrow - i;
-        const double f = log(f1[row + (long long)(P.idxI + 1) * nrow]);
-        const double s = log(f1[row + (long long)(P.idxS + 1) * nrow]);
+        // transX = "log": the trajectory already holds logs (:1160-1163)
+        const double vI = f1[row + (long long)(P.idxI + 1) * nrow], vS = f1[row + (long long)(P.idxS + 1) * nrow];
+        const double f = P.transX ? vI : log(vI);
+        const double s = P.transX ? vS : log(vS);
         const double be = bN[row];
         cq[i] = be * exp(-f) * exp(s);
         cl[i] = log(be) - f + s;

@@ -121,12 +121,30 @@ def test_cholesky_failure_is_the_reference_exception(dp, changepoint):
             m.New_Param_List(bad[2:], bad[:2], g.gridsize, g.times, g.x_r, g.x_i)
 
 
-def test_unbuilt_variants_fail_loudly(dp, changepoint):
-    """transX = "log" is refused with an R error (Rcpp::stop), never answered by a fallback."""
+def test_log_scale_through_the_binding(dp, changepoint):
+    """transX = "log" (SIR): integrator, LNA moments and likelihood through the binding against the reference's own code;
+    SEIR on the log scale -- never used by the package -- is refused with an R error (Rcpp::stop), not answered by a fallback."""
     g = changepoint
-    par, _ = state(g)
+    rng = np.random.default_rng(3)
+    x_i = [39, 2, 0, 1]
+    param = np.concatenate([[2.3, 0.21], np.exp(0.05 * rng.standard_normal(39)), [20.0]])
+    initial, t = np.log([1e6, 10.0]), g.times[:401]
+    kw = dict(model="SIR", transX="log")
+    ode_d, ode_r = dp.ODE_rk45(initial, t, param, g.x_r, x_i, **kw), ref.ODE_rk45(initial, t, param, g.x_r, x_i, **kw)
+    close(ode_d, ode_r)
+    a, b = dp.KF_param(ode_r, param, 50, g.x_r, x_i, **kw), ref.KF_param(ode_r, param, 50, g.x_r, x_i, **kw)
+    close(a["A"], b["A"])
+    close(a["Sigma"], b["Sigma"], 1e-9)
+    a, b = dp.SigmaF(ode_r[100:150], param, g.x_r, x_i, **kw), ref.SigmaF(ode_r[100:150], param, g.x_r, x_i, **kw)
+    close(a["expF"], b["expF"])
+    close(a["Sigma"], b["Sigma"], 1e-9)
+    lt = np.column_stack([g.final["LatentTraj"][:, 0], np.log(np.abs(g.final["LatentTraj"][:, 1:]) + 1.0)])
+    bn = g.final["betaN"].ravel()
+    assert dp.volz_loglik_nh2(g.init, lt, bn, g.t_correct, [0, 1], "log") == pytest.approx(
+        ref.volz_loglik_nh2(g.init, lt, bn, g.t_correct, [0, 1], "log"), rel=TOL)
     with pytest.raises(RuntimeError, match="transX"):
-        dp.ODE_rk45(np.log(par[:2] + 1), g.times, par[2:], g.x_r, g.x_i, transX="log")
+        dp.ODE_rk45(np.log([1e6, 20.0, 10.0]), t, np.concatenate([[2.3, 0.4, 0.21], param[2:]]), g.x_r, [39, 3, 0, 2],
+                    model="SEIR", transX="log")
 
 
 @pytest.mark.parametrize("name", ["changepoint_sim", "constant_sim"])
