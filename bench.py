@@ -441,6 +441,48 @@ def main():
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total * 1e-3)
 
+    # ---- supplemental: the same launches with TWO batches in flight (two problem handles, two streams) ----
+    # The headline batch is 2048 warp-loads on 592 SM sub-partitions (3.46 each): alone, a launch lasts as long as the
+    # sub-partitions that got 4.  With the next batch's launch overlapping the tail the quantisation loss disappears; the
+    # inputs rotate over NBUF = 4 distinct 65 MB batches (260 MB > L2), results go to two output buffers.
+    pipelined = None
+    try:
+        pb2 = api.Problem(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init, device=local_rank)
+        s2 = torch.cuda.Stream(dev)
+        _lib.check(L.lna_problem_set_stream(pb2.h, C.c_void_p(s2.cuda_stream)), "set_stream")
+        coal_d2 = torch.empty(B, dtype=torch.float64, device=dev)
+        st_d2 = torch.empty(B, dtype=torch.int32, device=dev)
+
+        def step_two(i):
+            p_, i_, e_ = bufs[i % NBUF]
+            h, cd, sd = (pb.h, coal_d, st_d) if i % 2 == 0 else (pb2.h, coal_d2, st_d2)
+            _lib.check(L.lna_full_loglik_dev(h, B, p_.data_ptr(), i_.data_ptr(), e_.data_ptr(), cd.data_ptr(), sd.data_ptr(),
+                                             None, None, None, None, None), "lna_full_loglik_dev")
+
+        nst = max(args.steps, 8) * 2
+        for i in range(4):
+            step_two(i)
+        barrier()
+        torch.cuda.synchronize(dev)
+        f0, f1, fj = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event())
+        f0.record(stream)
+        s2.wait_event(f0)
+        for i in range(nst):
+            step_two(i)
+        fj.record(s2)
+        stream.wait_event(fj)
+        f1.record(stream)
+        torch.cuda.synchronize(dev)
+        tp = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        pv = world * B * nst / (float(tp.item()) * 1e-3)
+        assert torch.equal(coal_d2.cpu(), coal_d2.cpu()) and bool(torch.isfinite(coal_d2).all())
+        pipelined = {"value": pv, "unit": UNIT, "launches": nst, "ms_per_launch": float(tp.item()) / nst,
+                     "how": "two problem handles on two streams, consecutive launches overlap; 4 rotating 65 MB input batches"}
+    except Exception as e:  # noqa: BLE001
+        pipelined = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- e2e: host buffers through the reference-facing C ABI call, copies inside the timed region ----
     barrier()
     t0 = time.perf_counter()
@@ -523,6 +565,10 @@ def main():
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "hbm_algorithmic_GBps": (value / world) * (h2d + d2h) / B / 1e9},
         }
+        if pipelined is not None:
+            if "value" in pipelined and peak > 0:
+                pipelined["frac"] = (pipelined["value"] / world) * W / 1e12 / peak
+            line["two_batches_in_flight"] = pipelined
         if eslice is not None:
             line["eslice"] = eslice
         if seir is not None:

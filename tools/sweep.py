@@ -26,7 +26,7 @@ opts_b = chm.vignette_opts(g, update_traj=False)
 print(f"genealogy: {len(c['coal_times']) + 1} tips, E = {len(init['C'])} events, ng = {init['ng']}")
 print("| chains | FULL evals/s (batch = chains) | us per batch | ESlice chain-iter/s | ms per iteration | FULL evals per iteration |")
 print("|---:|---:|---:|---:|---:|---:|")
-for B in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+for B in (1, 32, 256, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
     ch = chm.Chains(pb, np.tile(par0, (B, 1)), np.zeros((40, 2)))
     for it in range(6):
         ch.step_rng(opts_b if it < 3 else opts, 5, it)
