@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+_JSON_OUT = sys.stdout
 METRIC = "LNA+coalescent loglik evals/sec (FULL evaluations, batched chains)"
 UNIT = "evals/s"
 WORKLOAD = ("configs[1] Changpoint_sim vignette: SIR LNA N=1e6, 2000 fine steps, gridsize 50, 39 R0 change points, "
@@ -135,7 +136,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def cpu_reference(g, iters=12):
@@ -340,6 +341,12 @@ def main():
     ap.add_argument("--eslice-iters", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL prints its version banner
+    # there when NCCL_DEBUG is set on the box) are sent to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args)
@@ -589,7 +596,7 @@ def main():
                 rpN, _ = time_oracle(g, 2048, cores, impl=orc)
                 line["cpu_baseline"]["port_value"] = rpN
                 line["cpu_baseline"]["port_value_1core"] = rp1
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -135,3 +135,35 @@ def test_single_item_and_empty_batch(api, changepoint):
     with pytest.raises(_lib.LnaError, match="ESS_vec"):
         api.ESlice_par_General(par, g.times, g.final["OriginTraj"], [[1, 1]] * 4, g.x_r, g.x_i, g.init, 50,
                                [0, 1, 0, 0, 1, 1, 1], 0.0, g.t_correct, normals=np.zeros(43), uniforms=np.full(22, 0.5))
+
+
+@pytest.mark.parametrize("gridsize,nch", [(8, 39), (40, 0), (50, 3), (1, 2)])
+def test_pipelined_full_evaluation_odd_shapes(changepoint, monkeypatch, gridsize, nch):
+    """csrc/lna_split.cuh on shapes far from the vignette's: intervals shorter than a ring piece (g = 8, g = 1), more
+    intervals than the constant-bank table holds (k = 250 > 64, k = 500), no change points, change points inside a piece,
+    ragged batches.  The three-warp pipeline must return the one-warp kernel's bits for every output."""
+    from lnaphylodyn_b200 import api
+    g = changepoint
+    rng = np.random.default_rng(gridsize * 100 + nch)
+    nt = 2001 if gridsize > 1 else 501
+    times = g.times[:nt]
+    cht = np.sort(rng.uniform(times[0], times[-1], nch))
+    x_r, x_i = np.concatenate([[1e6], cht]), [nch, 2, 0, 1]
+    k = (nt - 1) // gridsize
+    pb = api.problem_for(times, x_r, x_i, gridsize, 0.0, None)
+    for B in (3, 70):
+        par = np.empty((B, 2 + nch + 1))
+        par[:, 0] = 2.2 * np.exp(0.1 * rng.standard_normal(B))
+        par[:, 1] = 0.2 * np.exp(0.1 * rng.standard_normal(B))
+        par[:, 2:2 + nch] = np.exp(0.05 * rng.standard_normal((B, nch)))
+        par[:, -1] = 20.0
+        ini = np.tile([1e6, 10.0], (B, 1))
+        eps = 0.5 * rng.standard_normal((B, k, 2))
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("LNA_SPLIT", mode)
+            out[mode] = pb.full_loglik(par, ini, eps, want=("FT", "Ode", "betaN", "LatentTraj"))
+        for key in ("Ode", "betaN", "LatentTraj", "status"):
+            assert np.array_equal(out["0"][key], out["1"][key]), key
+        assert np.array_equal(out["0"]["FT"]["A"], out["1"]["FT"]["A"]) and np.array_equal(out["0"]["FT"]["Sigma"], out["1"]["FT"]["Sigma"])
+        assert np.all(np.isfinite(out["1"]["Ode"]))
