@@ -39,8 +39,8 @@ UNIT = "evals/s"
 WORKLOAD = ("configs[1] Changpoint_sim vignette: SIR LNA N=1e6, 2000 fine steps, gridsize 50, 39 R0 change points, "
             "cached 342-tip genealogy (E=376); FULL (param, initial, OriginTraj) -> coalLog evaluations")
 # DRAM bytes per launch of the hot kernel at the default batch (dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture, profiles/r1c_ncu_kernels.md)
-NCU_TRAFFIC_BYTES_65536 = 65071104 + 747776
+# `ncu --set full` capture, profiles/r1d_ncu_full_loglik.md)
+NCU_TRAFFIC_BYTES_65536 = 65061120 + 1034752
 
 
 def load_workload():

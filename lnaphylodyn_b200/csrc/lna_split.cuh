@@ -8,7 +8,7 @@
 // seams into a pipeline of three warps that hold the same 32 trajectories (lane = trajectory):
 //
 //   P  ODE_rk45 (src/LNA_functional.cpp:455-491): the mean trajectory, 22 FP64 instructions per fine step on the 9-deep RK
-//      chain; writes (S, I) at every left endpoint into a shared-memory ring;
+//      chain; writes (S, I) at every left endpoint into a shared-memory ring, and the state at each coarse time into a second one;
 //   M  SigmaF / KF_param (:536-634): the Euler recurrences of F0 and Sigma along that trajectory (27 FP64 instructions per
 //      step, shallow chains); hands (F0, Sigma, S, I) of each finished LNA interval on through a second ring;
 //   E  first the change ratios of the proposal (param_transform's exp/div/log chains, :63-86, written to shared memory for
@@ -25,23 +25,25 @@ namespace lna {
 
 constexpr int kSplitPiece = 25;  // fine steps per piece of the P -> M ring
 constexpr int kSplitBufs = 3;    // pieces in the P -> M ring (slack for M's per-interval hand-over)
-constexpr int kSplitIvals = 4;   // intervals in the M -> E ring
+constexpr int kSplitIvals = 4;   // intervals in the M -> E ring and in the P -> M ring of coarse-time states
 constexpr int kSplitIvalVals = 9;  // F0 (4), Sigma (3), S, I at the coarse time
 constexpr int kSplitMaxCh = 48;  // change points held in shared memory (more: the host keeps the one-warp kernel)
 constexpr int kSplitWarps = 3;
 
 __host__ __device__ inline size_t split_group_bytes() {
-    return sizeof(double) * (size_t)(kSplitBufs * kSplitPiece * 64 + kSplitIvals * kSplitIvalVals * 32 + kSplitMaxCh * 32 + 32) +
+    return sizeof(double) * (size_t)(kSplitBufs * kSplitPiece * 64 + kSplitIvals * kSplitIvalVals * 32 + kSplitIvals * 64 +
+                                     kSplitMaxCh * 32 + 32) +
            sizeof(int) * (32 + 8);
 }
 
 struct SplitCtx {
     double *ring_pm;   // [kSplitBufs][kSplitPiece][2][32]
     double *ring_me;   // [kSplitIvals][kSplitIvalVals][32]
+    double *coarse;    // [kSplitIvals][2][32]  mean state at the end of each LNA interval (P -> M)
     double *ratios;    // [kSplitMaxCh][32]
     double *res_ll;    // [32]
     int *res_st;       // [32]
-    volatile int *pm_produced, *pm_consumed, *me_produced, *me_consumed, *ratios_ready, *res_seq;
+    volatile int *pm_produced, *pm_consumed, *me_produced, *me_consumed, *ratios_ready, *res_seq, *coarse_produced;
     int piece, ival, evals;  // this warp's running counts (the warps of a group count the same events)
     int lane;
 };
@@ -50,7 +52,8 @@ __device__ __forceinline__ SplitCtx split_ctx(unsigned char *group_smem, int lan
     SplitCtx c;
     c.ring_pm = reinterpret_cast<double *>(group_smem);
     c.ring_me = c.ring_pm + kSplitBufs * kSplitPiece * 64;
-    c.ratios = c.ring_me + kSplitIvals * kSplitIvalVals * 32;
+    c.coarse = c.ring_me + kSplitIvals * kSplitIvalVals * 32;
+    c.ratios = c.coarse + kSplitIvals * 64;
     c.res_ll = c.ratios + kSplitMaxCh * 32;
     c.res_st = reinterpret_cast<int *>(c.res_ll + 32);
     int *f = c.res_st + 32;
@@ -60,6 +63,7 @@ __device__ __forceinline__ SplitCtx split_ctx(unsigned char *group_smem, int lan
     c.me_consumed = f + 3;
     c.ratios_ready = f + 4;
     c.res_seq = f + 5;
+    c.coarse_produced = f + 6;
     c.piece = 0;
     c.ival = 0;
     c.evals = 0;
@@ -73,10 +77,16 @@ __device__ __forceinline__ void split_reset(const SplitCtx &c) {
     *c.me_consumed = 0;
     *c.ratios_ready = 0;
     *c.res_seq = 0;
+    *c.coarse_produced = 0;
 }
 
+#ifndef LNA_SPLIT_SLEEP_NS
+#define LNA_SPLIT_SLEEP_NS 0  // 0 = spin on the shared-memory word (one dependent LDS per ~30 cycles)
+#endif
 __device__ __forceinline__ void split_wait(volatile int *ctr, int need) {
-    while (*ctr < need) __nanosleep(20);
+    while (*ctr < need) {
+        if (LNA_SPLIT_SLEEP_NS > 0) __nanosleep(LNA_SPLIT_SLEEP_NS);
+    }
     __threadfence_block();
 }
 __device__ __forceinline__ void split_post(volatile int *ctr, int value, int lane) {
@@ -158,15 +168,17 @@ __device__ __forceinline__ void sir_split_P(SplitCtx &c, const DevProb &P, const
             split_post(c.pm_produced, n + 1, c.lane);
             c.piece = n + 1;
         }
-    }
-    {  // the state at the last coarse time: a one-entry piece
-        const int n = c.piece;
-        split_wait(c.pm_consumed, n - (kSplitBufs - 1));
-        double *buf = c.ring_pm + (n % kSplitBufs) * (kSplitPiece * 64) + c.lane;
-        buf[0] = S;
-        buf[32] = I;
-        split_post(c.pm_produced, n + 1, c.lane);
-        c.piece = n + 1;
+        // the mean state at the coarse time, posted at once (M closes the interval with it and must not wait for the
+        // next piece; measured: that wait made M the bottleneck of the pipeline)
+        {
+            const int m = c.ival;
+            split_wait(c.me_produced, m - (kSplitIvals - 1));  // M has long finished with the interval that used this slot
+            double *q = c.coarse + (m % kSplitIvals) * 64 + c.lane;
+            q[0] = S;
+            q[32] = I;
+            split_post(c.coarse_produced, m + 1, c.lane);
+            c.ival = m + 1;
+        }
     }
     split_take_result(c, loglik, status);
 }
@@ -219,19 +231,14 @@ __device__ __forceinline__ void sir_split_M(SplitCtx &c, const DevProb &P, const
             split_post(c.pm_consumed, n + 1, c.lane);
             c.piece = n + 1;
         }
-        // the mean state at the coarse time = first entry of the next piece (left endpoint of the next interval, or P's
-        // closing one-entry piece)
+        // the mean state at the coarse time (P posts it when it finishes the interval)
         double Sc, Ic;
         {
-            const int n = c.piece;
-            split_wait(c.pm_produced, n + 1);
-            const double *buf = c.ring_pm + (n % kSplitBufs) * (kSplitPiece * 64) + c.lane;
-            Sc = buf[0];
-            Ic = buf[32];
-            if (seg == k - 1) {
-                split_post(c.pm_consumed, n + 1, c.lane);
-                c.piece = n + 1;
-            }
+            const int m = c.ival;
+            split_wait(c.coarse_produced, m + 1);
+            const double *q = c.coarse + (m % kSplitIvals) * 64 + c.lane;
+            Sc = q[0];
+            Ic = q[32];
         }
         // hand the interval on to E
         {
@@ -262,10 +269,21 @@ __device__ __forceinline__ void sir_split_E(SplitCtx &c, const DevProb &P, const
     const double invN = P.invN;
     const int g = P.g, k = P.k, nrow = P.nrow, nch = P.nch;
     // the proposal's change ratios, for all three warps
+    // (their global loads run three ratios ahead: one exposed load latency per ratio made this phase 44 k cycles, long enough
+    // for the M -> E ring to fill and stall M and then P at the start of every evaluation)
     {
         const int base = c.evals * nch;
+        typedef typename ChSrc::Raw Raw;
+        Raw r0{}, r1{}, r2{};
+        if (nch > 0) r0 = chs.raw(0);
+        if (nch > 1) r1 = chs.raw(1);
+        if (nch > 2) r2 = chs.raw(2);
         for (int j = 0; j < nch; ++j) {
-            c.ratios[j * 32 + c.lane] = chs.eval(chs.raw(j));
+            const Raw cur_raw = r0;
+            r0 = r1;
+            r1 = r2;
+            if (j + 3 < nch) r2 = chs.raw(j + 3);
+            c.ratios[j * 32 + c.lane] = chs.eval(cur_raw);
             split_post(c.ratios_ready, base + j + 1, c.lane);
         }
     }
