@@ -287,7 +287,23 @@ typedef struct lna_mcmc2_opts {
     int32_t update_chpt;       /* updateVec[6]                                                      */
     int32_t update_traj;       /* updateVec[7] and i >= burn1                                       */
     int32_t spec_width;        /* 0 = auto                                                          */
+    /* stage i >= warmup2 (R/LNA_chpt_slice.R:655-663): the scalar entries and the hyper step are replaced by ONE joint
+     * random-walk Metropolis step, update_Param_joint(method = "admcmc") (:9-88), over the listed parameters;
+     * the proposal is raw' = raw + T z with the chain's transform set by lna_chains_set_joint_transform */
+    int32_t joint;             /* 1: joint step instead of mh_* / update_hyper                       */
+    int32_t joint_d;           /* number of jointly proposed parameters (1..4)                       */
+    int32_t joint_index[4];    /* 1 = I0, 2 = R0, 3 = gamma, 4 = hyper (last, if present)            */
+    int32_t joint_is_log[4];   /* the walk is on log(par)                                            */
+    int32_t joint_prior_kind[4]; /* 0 dnorm(mean, sd), 1 dunif(lo, hi), 2 dgamma(shape, rate) on the raw value */
+    double joint_prior[4][2];
 } lna_mcmc2_opts;
+
+/* Proposal transforms of the joint step: T is B x d x d row-major (host), raw' = raw + T z with z ~ N(0, I_d), i.e.
+ * T = V diag(sqrt(max(ev, 0))) of the chain's proposal covariance PCOV = V diag(ev) V' -- what MASS::mvrnorm(1, raw, PCOV)
+ * computes (R/LNA_chpt_slice.R:39).  The adaptation of PCOV from the chain's history (:608-630) is host logic
+ * (lnaphylodyn_b200/mcmc.py).  With `joint` set an iteration takes d more normals per chain, appended to the stream:
+ * normals are B x (nch + k*p + 4), the joint ones at column nch + k*p; its accept test uses uniform 1. */
+int lna_chains_set_joint_transform(lna_chains *ch, int d, const double *T);
 
 /* uniforms per General_MCMC2 iteration: 4 MH slots x (walk, accept), hyper (walk, accept), 22 + 22 */
 #define LNA_ITER2_UNIF (2 * 4 + 2 + 2 * LNA_ESLICE_MAX_UNIF)

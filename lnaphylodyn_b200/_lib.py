@@ -33,7 +33,9 @@ class LnaMcmc2Opts(C.Structure):
     _fields_ = [("n_mh", C.c_int32), ("mh_index", C.c_int32 * 4), ("mh_is_log", C.c_int32 * 4),
                 ("mh_prior_kind", C.c_int32 * 4), ("mh_prior", (C.c_double * 2) * 4), ("mh_prop", C.c_double * 4),
                 ("update_hyper", C.c_int32), ("hyper_prop", C.c_double), ("hyper_prior", C.c_double * 2),
-                ("update_chpt", C.c_int32), ("update_traj", C.c_int32), ("spec_width", C.c_int32)]
+                ("update_chpt", C.c_int32), ("update_traj", C.c_int32), ("spec_width", C.c_int32),
+                ("joint", C.c_int32), ("joint_d", C.c_int32), ("joint_index", C.c_int32 * 4),
+                ("joint_is_log", C.c_int32 * 4), ("joint_prior_kind", C.c_int32 * 4), ("joint_prior", (C.c_double * 2) * 4)]
 
 
 # name -> (restype, argtypes); pointers are passed as void* so that host (numpy) and device (torch
@@ -82,6 +84,7 @@ _SIGS = {
     "lna_chains_step_dev": (C.c_int, [_vp, C.POINTER(LnaMcmcOpts), _vp, _vp]),
     "lna_chains_step_mcmc2": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), _vp, _vp]),
     "lna_chains_step_mcmc2_dev": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), _vp, _vp]),
+    "lna_chains_set_joint_transform": (C.c_int, [_vp, C.c_int, _vp]),
     "lna_chains_step_rng": (C.c_int, [_vp, C.POINTER(LnaMcmcOpts), C.c_uint64, C.c_uint64, _I64]),
     "lna_draw_streams": (C.c_int, [_vp, _I64, _I64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp, _vp]),
     "lna_chains_get": (C.c_int, [_vp] + [_vp] * 6),

@@ -174,8 +174,40 @@ def make_mcmc2_opts(prior, proposal, entries=((1, 1, 1), (2, 0, 2), (3, 1, 3)), 
     return o
 
 
+def make_joint_opts(prior, entries, update_chpt=True, update_traj=True, spec_width=0):
+    """General_MCMC2's stage i >= warmup2: update_Param_joint(method = "admcmc") (R/LNA_chpt_slice.R:9-88) + change-point and
+    trajectory slice updates.  `entries`: (joint index, isLog, priorId) per jointly proposed parameter, joint index 1 = I0,
+    2 = R0, 3 = gamma, 4 = hyper (last); priorId 2 is dunif, 5 dgamma, the others dnorm (:44-58)."""
+    from ._lib import LnaMcmc2Opts
+    pr = [np.asarray(v, dtype=np.float64).ravel() for v in prior]
+    o = LnaMcmc2Opts()
+    o.joint, o.joint_d = 1, len(entries)
+    for e, (idx, is_log, pid) in enumerate(entries):
+        o.joint_index[e], o.joint_is_log[e] = int(idx), int(is_log)
+        o.joint_prior_kind[e] = 1 if pid == 2 else 2 if pid == 5 else 0
+        o.joint_prior[e][0], o.joint_prior[e][1] = float(pr[pid - 1][0]), float(pr[pid - 1][1])
+    o.update_chpt, o.update_traj, o.spec_width = int(update_chpt), int(update_traj), int(spec_width)
+    return o
+
+
+def mvrnorm_transform(pcov):
+    """T with raw' = raw + T z, z ~ N(0, I): MASS::mvrnorm's eS$vectors %*% diag(sqrt(pmax(ev, 0))) (R/LNA_chpt_slice.R:39).
+    pcov: (..., d, d).  (Eigenvector signs / order are LAPACK's: the proposal DISTRIBUTION is the reference's, its
+    realisation for given normals is not pinned -- MASS is a third-party package outside the reference tree.)"""
+    ev, vec = np.linalg.eigh(np.asarray(pcov, dtype=np.float64))
+    return vec * np.sqrt(np.maximum(ev, 0.0))[..., None, :]
+
+
+def _set_joint_transform(self, T):
+    T = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.float64), (self.B,) + np.shape(T)[-2:]))
+    check(_lib.lib().lna_chains_set_joint_transform(self.h, int(T.shape[-1]), _ptr(T)), "lna_chains_set_joint_transform")
+
+
+Chains.set_joint_transform = _set_joint_transform
+
+
 def _step_mcmc2(self, opts, normals, uniforms):
-    """One General_MCMC2 iteration. normals (B, nch + k*p), uniforms (B, 54): host arrays."""
+    """One General_MCMC2 iteration. normals (B, nch + k*p [+ 4 with opts.joint]), uniforms (B, 54): host arrays."""
     n, u = _d(normals), _d(uniforms)
     assert u.shape == (self.B, ITER2_UNIF) and n.shape[0] == self.B, (n.shape, u.shape)
     check(_lib.lib().lna_chains_step_mcmc2(self.h, C.byref(opts), _ptr(n), _ptr(u)), "lna_chains_step_mcmc2")

@@ -550,6 +550,8 @@ struct ChainPart {  // one stream-group of a resident chain batch
     std::vector<void *> owned;
     double *stage_n = nullptr, *stage_u = nullptr;  // staging for host-pointer steps
     size_t n_norm = 0, n_unif = 0;
+    double *jT = nullptr, *jnew = nullptr;  // joint Metropolis step: [B][16] transforms (padded 4 x 4), [B][4] proposed values
+    int jd = 0;
 };
 
 __global__ void k_bump(long long B, const int *n_evals, const int *accept, const int *status, const int *win_slot,
@@ -616,8 +618,10 @@ static ChainPart *part_create(lna_problem *pb, int64_t B, int64_t planB, double 
     const size_t stage_unif = std::max<size_t>(LNA_ITER_UNIF, LNA_ITER2_UNIF);
     ch->stage_n = chains_alloc<double>(ch, nB * ch->n_norm);
     ch->stage_u = chains_alloc<double>(ch, nB * stage_unif);
+    ch->jT = chains_alloc<double>(ch, nB * 16);
+    ch->jnew = chains_alloc<double>(ch, nB * 4);
     if (!ch->par || !ch->par_alt || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
-        !ch->logOrigin || !ch->counters || !ch->tmp_i || !ch->tmp_d || !ch->stage_n || !ch->stage_u) {
+        !ch->logOrigin || !ch->counters || !ch->tmp_i || !ch->tmp_d || !ch->stage_n || !ch->stage_u || !ch->jT || !ch->jnew) {
         fail("lna_chains_create: device allocation failed");
         part_destroy(ch);
         return nullptr;
@@ -794,10 +798,30 @@ static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const dou
     if (o->n_mh < 0 || o->n_mh > 4) return fail("lna_chains_step_mcmc2: n_mh must be 0..4");
     const int W = o->spec_width;
     if (chains_ensure_scratch(ch, W)) return -1;
-    const long long sn = (long long)(P.nch + P.k * P.p), su = (long long)LNA_ITER2_UNIF;
+    const long long sn = (long long)(P.nch + P.k * P.p) + (o->joint ? 4 : 0), su = (long long)LNA_ITER2_UNIF;
     CandArgs a;
+    if (o->joint) {  // i >= warmup2: update_Param_joint(method = "admcmc") replaces the scalar entries and the hyper step
+        if (o->joint_d < 1 || o->joint_d > 4) return fail("lna_chains_step_mcmc2: joint_d must be 1..4");
+        if (!ch->jT || ch->jd != o->joint_d)
+            return fail("lna_chains_step_mcmc2: joint step without a matching lna_chains_set_joint_transform (d = %d)", o->joint_d);
+        chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
+        a.jd = o->joint_d;
+        for (int i = 0; i < a.jd; ++i) {
+            if (o->joint_index[i] < 1 || o->joint_index[i] > 4 || (o->joint_index[i] == 4 && i != a.jd - 1))
+                return fail("lna_chains_step_mcmc2: joint_index must be 1 (I0), 2 (R0), 3 (gamma) or, last, 4 (hyper)");
+            a.jidx[i] = o->joint_index[i];
+            a.jlog[i] = o->joint_is_log[i];
+            a.jkind[i] = o->joint_prior_kind[i];
+            a.jpr[i][0] = o->joint_prior[i][0];
+            a.jpr[i][1] = o->joint_prior[i][1];
+        }
+        a.jnorm_off = P.nch + P.k * P.p;
+        a.jT = ch->jT;
+        a.jnew = ch->jnew;
+        if (chains_stage<PROP_MH_JOINT>(ch, a, 1)) return -1;
+    }
     // Update_Param_each: one Metropolis entry per listed parameter, sequentially
-    for (int e = 0; e < o->n_mh; ++e) {
+    for (int e = 0; !o->joint && e < o->n_mh; ++e) {
         if (o->mh_index[e] < 1 || o->mh_index[e] > 3)
             return fail("lna_chains_step_mcmc2: mh_index must be 1 (I0), 2 (R0) or 3 (gamma)");
         chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 2 * e, su, 1}, a);
@@ -809,7 +833,7 @@ static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const dou
         a.mh_prop = o->mh_prop[e];
         if (chains_stage<PROP_MH_SCALAR>(ch, a, 1)) return -1;
     }
-    if (o->update_hyper) {  // update_hyper (general_change_point.R:281-313)
+    if (o->update_hyper && !o->joint) {  // update_hyper (general_change_point.R:281-313)
         chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 8, su, 1}, a);
         a.mh_pr[0] = o->hyper_prior[0];
         a.mh_pr[1] = o->hyper_prior[1];
@@ -832,7 +856,7 @@ static int part_step_mcmc2(ChainPart *ch, const lna_mcmc2_opts *o, const double 
     lna_problem *pb = ch->pb;
     cudaSetDevice(pb->device);
     const DevProb &P = pb->dp;
-    const size_t nB = (size_t)ch->B, nn = (size_t)(P.nch + P.k * P.p);
+    const size_t nB = (size_t)ch->B, nn = (size_t)(P.nch + P.k * P.p) + (o->joint ? 4 : 0);
     if (nn > ch->n_norm || (size_t)LNA_ITER2_UNIF > ch->n_unif + 8) return fail("lna_chains_step_mcmc2: staging too small");
     CK(cudaMemcpyAsync(ch->stage_n, normals, sizeof(double) * nB * nn, cudaMemcpyHostToDevice, pb->stream));
     CK(cudaMemcpyAsync(ch->stage_u, uniforms, sizeof(double) * nB * LNA_ITER2_UNIF, cudaMemcpyHostToDevice, pb->stream));
@@ -1023,6 +1047,26 @@ extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *
     return 0;
 }
 
+extern "C" int lna_chains_set_joint_transform(lna_chains *ch, int d, const double *T) {
+    if (!ch || !T) return fail("lna_chains_set_joint_transform: null argument");
+    if (d < 1 || d > 4) return fail("lna_chains_set_joint_transform: d must be 1..4");
+    std::vector<double> pad;
+    for (int g = 0; g < ch->G; ++g) {
+        ChainPart *pt = ch->part[g];
+        cudaSetDevice(pt->pb->device);
+        const size_t nB = (size_t)pt->B;
+        pad.assign(nB * 16, 0.0);
+        const double *src = T + (size_t)ch->off[g] * d * d;
+        for (size_t c = 0; c < nB; ++c)
+            for (int i = 0; i < d; ++i)
+                for (int q = 0; q < d; ++q) pad[c * 16 + i * 4 + q] = src[c * d * d + i * d + q];
+        CK(cudaMemcpyAsync(pt->jT, pad.data(), sizeof(double) * nB * 16, cudaMemcpyHostToDevice, pt->pb->stream));
+        CK(cudaStreamSynchronize(pt->pb->stream));  // (pad is a host temporary)
+        pt->jd = d;
+    }
+    return 0;
+}
+
 extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const double *normals,
                                    const double *uniforms) {
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
@@ -1054,7 +1098,7 @@ extern "C" int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *o
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
     if (chains_fork(ch)) return -1;
     for (int g = 0; g < ch->G; ++g)
-        if (part_step_mcmc2_dev(ch->part[g], o, normals + ch->off[g] * ch->n_norm2,
+        if (part_step_mcmc2_dev(ch->part[g], o, normals + ch->off[g] * (ch->n_norm2 + (o->joint ? 4 : 0)),
                                 uniforms + ch->off[g] * (size_t)LNA_ITER2_UNIF))
             return -1;
     return chains_join(ch);
@@ -1065,7 +1109,7 @@ extern "C" int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *o, co
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step_mcmc2: null argument");
     if (chains_fork(ch)) return -1;
     for (int g = 0; g < ch->G; ++g)
-        if (part_step_mcmc2(ch->part[g], o, normals + ch->off[g] * ch->n_norm2,
+        if (part_step_mcmc2(ch->part[g], o, normals + ch->off[g] * (ch->n_norm2 + (o->joint ? 4 : 0)),
                             uniforms + ch->off[g] * (size_t)LNA_ITER2_UNIF))
             return -1;
     return chains_join(ch);

@@ -22,7 +22,8 @@ namespace lna {
 enum : int {
     PROP_PLAIN = 0, PROP_GAMMA_RW = 1, PROP_HYPER_NOOP = 2, PROP_ESS_PAR = 3, PROP_ESS_CHPT = 4, PROP_MH_PAIR = 5,
     PROP_MH_SCALAR = 6,  // one entry of Update_Param_each (R/LNA_chpt_slice.R:266-365)
-    PROP_MH_HYPER = 7    // update_hyper (R/general_change_point.R:281-313)
+    PROP_MH_HYPER = 7,   // update_hyper (R/general_change_point.R:281-313)
+    PROP_MH_JOINT = 8    // update_Param_joint, method "admcmc" (R/LNA_chpt_slice.R:9-88): General_MCMC2's stage i >= warmup2
 };
 
 constexpr int kMaxUnif = 22;
@@ -84,6 +85,10 @@ struct ChProp {
             // exp(log(ch) * hyper / hyper'), R/LNA_chpt_slice.R:238-241 with hyper' = hyper (ulp-level
             // perturbation, A.17) and update_hyper (general_change_point.R:292-293) with hyper' = hyper e^u
             return exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_new));
+        } else if (kProp == PROP_MH_JOINT) {
+            // only when the hyper-parameter is among the jointly proposed ones (:65-68): exp(log(ch) * hyper / hyper')
+            const double v = exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_new));
+            return x.rot_ch ? v : cj;
         } else if (kProp == PROP_MH_PAIR) {
             // same instruction stream for all lanes of the pair kernel; the flag selects per lane
             const double pert = exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_old));
@@ -145,6 +150,13 @@ struct CandArgs {
     // PROP_MH_HYPER : hyper' = hyper * exp(u), prior dgamma(shape = mh_pr[0], rate = mh_pr[1])
     int mh_index, mh_is_log, mh_prior_kind;
     double mh_pr[2], mh_prop;
+    // PROP_MH_JOINT: raw' = raw + T z over the jd listed parameters (1 = I0, 2 = R0, 3 = gamma, 4 = hyper, the last one if
+    // present), T = this chain's 4 x 4 row-major transform (eigenvectors * sqrt(eigenvalues) of its proposal covariance, as
+    // MASS::mvrnorm builds it), z = jd normals at column jnorm_off of the normals stream
+    int jd, jidx[4], jlog[4], jkind[4], jnorm_off;  // jkind: 0 dnorm, 1 dunif, 2 dgamma
+    double jpr[4][2];
+    const double *jT;  // [B][16]
+    double *jnew;      // [B][4] proposed values on the natural scale (read by the commit kernel)
     FullOut cand;    // candidate scratch: slot-major (sb = 1, sj = NC)
     int *win_slot;   // [B] winning scratch slot, -1 = keep current state
     double *cand_ll; // [B] log-likelihood of the winner (or of the rejected MH proposal)
@@ -340,6 +352,35 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
             if (j == 2) x.R0 = val;
             if (j == 3) x.gam = val;
             prop = rnew;
+        }
+        if (kProp == PROP_MH_JOINT) {
+            // RawTransParam_new = mvrnorm(1, RawTransParam, PCOV) (:37-39), the prior terms in list order (:41-61), the
+            // change ratios rescaled when the hyper-parameter moves (:65-68); one uniform: the accept test of Update_Param
+            double off = 0.0;
+            const double *Tm = a.jT + c * 16;
+            for (int i = 0; i < a.jd; ++i) {
+                const int j = a.jidx[i] == 4 ? npar - 1 : a.jidx[i];
+                const double cur = a.par.at(c, j);
+                const double raw = a.jlog[i] ? log(cur) : cur;
+                double rnew = raw;
+                for (int q = 0; q < a.jd; ++q) rnew = __dadd_rn(rnew, __dmul_rn(Tm[i * 4 + q], a.normals.at(c, a.jnorm_off + q)));
+                const double p0 = a.jpr[i][0], p1 = a.jpr[i][1];
+                off += a.jkind[i] == 0   ? dnorm_log(rnew, p0, p1) - dnorm_log(raw, p0, p1)
+                       : a.jkind[i] == 1 ? dunif_log(rnew, p0, p1) - dunif_log(raw, p0, p1)
+                                         : dgamma_log(rnew, p0, p1) - dgamma_log(raw, p0, p1);
+                const double val = a.jlog[i] ? exp(rnew) : rnew;
+                if (a.jidx[i] == 1) x.I0 = val;
+                if (a.jidx[i] == 2) x.R0 = val;
+                if (a.jidx[i] == 3) x.gam = val;
+                if (a.jidx[i] == 4) {
+                    x.hyper_new = val;
+                    x.rot_ch = 1;
+                }
+                if (valid && writer) a.jnew[c * 4 + i] = val;
+            }
+            offset = off;
+            iu = 1;  // uniform 0 of the slot is the (unused) walk draw of the scalar entries
+            prop = offset;
         }
         if (kProp == PROP_MH_HYPER) {
             const double hp = a.mh_prop, uu = -hp + (hp - (-hp)) * unif(iu++);
@@ -728,6 +769,25 @@ __global__ void k_commit_par_wide(DevProb P, long long B, CandArgs a, OutView pa
             x.hyper_old = a.par.at(c, npar - 1);
             x.hyper_new = a.theta[c];
             ChProp<PROP_MH_HYPER> chs{a.par, a.normals, c, 4, x};
+            v = chs.ch(j - 4);
+        }
+    } else if (kProp == PROP_MH_JOINT) {
+        bool has_hyper = false;
+        double hyper_new = a.par.at(c, npar - 1);
+        for (int i = 0; i < a.jd; ++i) {
+            const int jj = a.jidx[i] == 4 ? npar - 1 : a.jidx[i];
+            if (jj == j) v = a.jnew[c * 4 + i];
+            if (a.jidx[i] == 4) {
+                has_hyper = true;
+                hyper_new = a.jnew[c * 4 + i];
+            }
+        }
+        if (is_ch && has_hyper) {
+            PropScalars x{};
+            x.hyper_old = a.par.at(c, npar - 1);
+            x.hyper_new = hyper_new;
+            x.rot_ch = 1;
+            ChProp<PROP_MH_JOINT> chs{a.par, a.normals, c, 4, x};
             v = chs.ch(j - 4);
         }
     } else if (kProp == PROP_HYPER_NOOP) {

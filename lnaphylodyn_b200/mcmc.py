@@ -9,7 +9,9 @@ them: set-up, initial state, stage switching (`burn1`, `warmup2`), thinning and 
 
 What is NOT here, and raises instead of guessing: likelihood other than "volz", models other than "SIR" (the
 reference's samplers are hard-wired to p = 2, LNA_functional.cpp:1456-1462), `ESS_vec2`, Metropolis entry lists other
-than the vignettes', and General_MCMC2's adaptive joint random-walk stage (`i >= warmup2`, needs MASS::mvrnorm).
+than the vignettes'.  General_MCMC2's adaptive joint random-walk stage (`i >= warmup2`) draws its proposal as
+MASS::mvrnorm does (eigen-decomposition of the covariance), with LAPACK's eigenvector signs: same proposal distribution, the
+realisation for given normals is not pinned (MASS is outside the reference tree).
 The random numbers are Philox streams drawn on the device (seed, chain, iteration) -- R's generator is not
 reproduced, so a run is distributionally, not bitwise, the R run; per-iteration arithmetic on given
 streams is pinned by tests/test_gpu_eslice.py and tests/test_gpu_vs_reference.py.
@@ -196,9 +198,6 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
     options = dict(options or {})
     warmup2 = int(options.get("warmup2") or 100000)
     burn1 = int(options.get("burn1", 5000))
-    if int(niter) >= warmup2:
-        raise LnaError("General_MCMC2: iterations i >= warmup2 use the adaptive joint random walk (update_Param_joint, "
-                       "MASS::mvrnorm), which is not built; raise options['warmup2'] above niter")
     nch = len(np.ravel(changetime))
     par_ids = [int(v) for v in dict(options.get("parIdlist") or {"a": 2, "b": 3, "c": 4, "d": 5 + nch}).values()][:3]
     is_log = [int(v) for v in dict(options.get("isLoglist") or {"a": 1, "b": 0, "c": 1, "d": 0}).values()][:3]
@@ -218,12 +217,44 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
     n_norm2 = nch + pb.k * pb.p
     rec = {"par": np.empty((B, niter, ch.npar)), "l": np.empty((B, niter)), "l1": np.empty((B, niter)),
            "traj": np.empty((B, niter // thin, pb.nrow, pb.p + 1))}
-    nrm, unf = np.empty((B, n_norm2)), np.empty((B, chm.ITER2_UNIF))
+    # stage 3 (i >= warmup2, :655-663): joint adaptive random walk over parIndexALL[updateVec[c(1:3,5)] > 0] (:563-569)
+    uv = [float(v) for v in updateVec]
+    joint_entries = tuple((jidx, lg, prid) for jidx, lg, prid, on in
+                          zip((1, 2, 3, 4), (1, 0, 1, 0), (1, 2, 3, 5), (uv[0], uv[1], uv[2], uv[4])) if on > 0)
+    if uv[3] > 0:
+        raise LnaError("General_MCMC2: updateVec[4] (mu) has no parameter in the SIR model (the R code stops with "
+                       "'priors do not match')")
+    d = len(joint_entries)
+    par_cols = [ch.npar - 1 if j == 4 else j for j, _, _ in joint_entries]
+    o3 = chm.make_joint_opts(pr, joint_entries, update_chpt=upd_chpt, update_traj=int(updateVec[6]) == 1)
+    fix_pcov = setting.get("PCOV") is not None
+    tune, beta, up = float(options.get("tune") or 0.01), float(options.get("beta", 0.05)), int(options.get("up", 2000))
+    pcov = None
+    if fix_pcov:
+        pcov = np.broadcast_to(np.asarray(setting["PCOV"], dtype=np.float64) * tune, (B, d, d)).copy()
+        ch.set_joint_transform(chm.mvrnorm_transform(pcov))
+    nrm, nrm_j, unf = np.empty((B, n_norm2)), np.empty((B, n_norm2 + 4)), np.empty((B, chm.ITER2_UNIF))
     L = _lib.lib()
     for i in range(1, niter + 1):
-        check(L.lna_draw_streams(pb.h, B, int(chain_offset), n_norm2, chm.ITER2_UNIF, int(seed), i, api._ptr(nrm),
+        joint = i >= max(warmup2, burn1)
+        if not fix_pcov and (i == warmup2 or (i > warmup2 and i % up == 0)):
+            # proposal covariance from the chain's own history, rows floor(i/3) .. i-1 of `params` (:608-630)
+            lo = max(i // 3, 1)
+            if i - lo < 2:
+                raise LnaError("General_MCMC2: warmup2 is too small to estimate the proposal covariance (needs >= 2 rows)")
+            hist = rec["par"][:, lo - 1:i - 1, :][:, :, par_cols].copy()
+            for q, (_, lg, _) in enumerate(joint_entries):
+                if lg:
+                    hist[:, :, q] = np.log(hist[:, :, q])
+            dev = hist - hist.mean(axis=1, keepdims=True)
+            cov = np.einsum("bti,btj->bij", dev, dev) / (hist.shape[1] - 1)
+            sigma_n = (2.38 ** 2) * cov / d
+            pcov = (beta * sigma_n + (1 - beta) * np.eye(d) * 0.0001 / d) * tune
+            ch.set_joint_transform(chm.mvrnorm_transform(pcov))
+        buf = nrm_j if joint else nrm
+        check(L.lna_draw_streams(pb.h, B, int(chain_offset), buf.shape[1], chm.ITER2_UNIF, int(seed), i, api._ptr(buf),
                                  api._ptr(unf)), "lna_draw_streams")
-        ch.step_mcmc2(o1 if i < burn1 else o2, nrm, unf)
+        ch.step_mcmc2(o3 if joint else (o1 if i < burn1 else o2), buf, unf)
         _record(ch, rec, i - 1, thin, i % thin == 0)
         if verbose and i % 100 == 0:
             print(i, float(np.mean(rec["l1"][:, i - 1])))

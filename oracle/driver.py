@@ -162,6 +162,42 @@ def mcmc2_iteration(st, g, opts, normals, uniforms):
     return st
 
 
+def mcmc2_joint_iteration(st, g, opts, T, normals, uniforms):
+    """General_MCMC2's stage i >= warmup2 (R/LNA_chpt_slice.R:655-683): update_Param_joint(method = "admcmc") (:9-88), then
+    the change-point and trajectory slice updates.  `T` (d x d): RawTransParam_new = RawTransParam + T z, what
+    MASS::mvrnorm(1, RawTransParam, PCOV) computes with T = eS$vectors diag(sqrt(pmax(ev, 0))) (third-party: the
+    eigenvector signs are not pinned, so T is an input here).  normals: [0:nch] change-point ESS, [nch:nch+k*p] trajectory
+    ESS, [nch+k*p : +d] the joint proposal; uniforms: [1] accept of the joint step, [10:32], [32:54] as mcmc2_iteration."""
+    npar = len(st["par"])
+    nch = npar - 5
+    kp = len(normals) - nch - 4
+    z = normals[nch + kp:nch + kp + len(opts["joint"])]
+    par_new = st["par"].copy()
+    raw, raw_new, off = [], [], 0.0
+    for i, (idx, is_log, kind, pr) in enumerate(opts["joint"]):
+        j = npar - 1 if idx == 4 else idx
+        r = math.log(par_new[j]) if is_log else float(par_new[j])
+        rn = r
+        for q in range(len(opts["joint"])):
+            rn = rn + T[i][q] * z[q]
+        if kind == 0:
+            off += dnorm_log(rn, pr[0], pr[1]) - dnorm_log(r, pr[0], pr[1])
+        elif kind == 1:
+            off += dunif_log(rn, pr[0], pr[1]) - dunif_log(r, pr[0], pr[1])
+        else:
+            off += dgamma_log(rn, pr[0], pr[1]) - dgamma_log(r, pr[0], pr[1])
+        raw.append(r)
+        raw_new.append(rn)
+    for i, (idx, is_log, kind, pr) in enumerate(opts["joint"]):
+        j = npar - 1 if idx == 4 else idx
+        if idx == 4:  # :65-68, with the OLD and NEW hyper-parameter
+            par_new[4:4 + nch] = np.exp(np.log(par_new[4:4 + nch]) * raw[i] / raw_new[i])
+        par_new[j] = math.exp(raw_new[i]) if is_log else raw_new[i]
+    _mh(st, g, par_new, off, uniforms[1])
+    sub = dict(opts, entries=(), update_hyper=False)
+    return mcmc2_iteration(st, g, sub, normals[:nch + kp], uniforms)
+
+
 def mcmc2_opts_from_golden(g, burn=False):
     """Options of the constant_sim vignette call (vignettes/constant_sim.Rmd:87-96)."""
     prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]

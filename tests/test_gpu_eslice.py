@@ -376,3 +376,45 @@ def test_three_warp_pipeline_standalone_entry_points(api, changepoint, monkeypat
     for x, y in zip(out["0"], out["1"]):
         for u, v in zip(x, y):
             assert np.array_equal(np.asarray(u), np.asarray(v))
+
+
+def test_chains_mcmc2_joint_stage_step_for_step(api, constant):
+    """General_MCMC2's third stage (i >= warmup2): update_Param_joint(method = "admcmc") over (I0, R0, gamma, hyper) with
+    per-chain proposal transforms, then change-point and trajectory slice updates -- B chains x 5 iterations against the
+    restated R code (oracle/driver.py::mcmc2_joint_iteration) on the same streams and the same transforms."""
+    from lnaphylodyn_b200 import chains as chm
+    g = constant
+    B, iters, seed = 9, 5, 53
+    par0 = np.concatenate([[g.x_r[0], float(g.setting("control.alpha")[0]) * g.x_r[0]], g.setting("control.R0"),
+                           g.setting("control.gamma"), g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    ref = [driver.init_state(g, par0, g.setting("control.traj")) for _ in range(B)]
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    entries = ((1, 1, 1), (2, 0, 2), (3, 1, 3), (4, 0, 5))  # (joint index, isLog, priorId): I0, R0, gamma, hyper
+    rng = np.random.default_rng(seed)
+    # a different (correlated) proposal covariance per chain, small enough for a healthy acceptance rate
+    A = rng.standard_normal((B, 4, 4)) * np.array([0.02, 0.004, 0.01, 0.3])[None, :, None]
+    pcov = A @ np.transpose(A, (0, 2, 1))
+    T = chm.mvrnorm_transform(pcov)
+    assert np.allclose(T @ np.transpose(T, (0, 2, 1)), pcov, rtol=1e-9, atol=1e-18)
+    ch.set_joint_transform(T)
+    opts = chm.make_joint_opts(prior, entries)
+    oopts = dict(driver.mcmc2_opts_from_golden(g), joint=[(j, lg, 1 if pid == 2 else 2 if pid == 5 else 0, tuple(prior[pid - 1][:2]))
+                                                          for j, lg, pid in entries])
+    for it in range(iters):
+        nrm = rng.standard_normal((B, 39 + 80 + 4))
+        unf = rng.random((B, chm.ITER2_UNIF))
+        ch.step_mcmc2(opts, nrm, unf)
+        s = ch.get()
+        for c in range(B):
+            ref[c] = driver.mcmc2_joint_iteration(ref[c], g, oopts, T[c], nrm[c], unf[c])
+            assert relerr(s["par"][c], ref[c]["par"]) < TOL, (it, c)
+            assert s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL), (it, c)
+            assert np.max(np.abs(s["OriginTraj"][c] - ref[c]["OriginTraj"])) < 1e-11
+            assert s["n_full_evals"][c] == ref[c]["n_full"] and s["n_cheap_evals"][c] == ref[c]["n_cheap"]
+            assert s["n_mh_accept"][c] == ref[c]["n_mh_accept"], (it, c)
+    acc = int(s["n_mh_accept"].sum())
+    assert 0 < acc < B * iters
+    moved = np.abs(s["par"][:, [1, 2, 3, 43]] / par0[[1, 2, 3, 43]] - 1.0) > 0
+    assert moved.any(axis=0).all()  # every jointly proposed parameter moved in some chain

@@ -91,9 +91,57 @@ def test_general_mcmc2_driver(constant):
             assert relerr(res["par"][c, i - 1], st[c]["par"]) < TOL, (i, c)
             assert res["l1"][c, i - 1] == pytest.approx(st[c]["coalLog"], rel=TOL)
             assert relerr(res["Trajectory"][c, i - 1][:, 1:], st[c]["LatentTraj"][:, 1:]) < 1e-9
-    with pytest.raises(Exception):
-        mcmc.General_MCMC2(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=10, changetime=g.x_r[1:], prior=prior,
-                           proposal=proposal, control=control, options={"warmup2": 5})
+
+
+def test_general_mcmc2_third_stage(constant):
+    """options$warmup2 < niter: from iteration warmup2 on, General_MCMC2 proposes (I0, R0, gamma, hyper) jointly from a
+    covariance estimated from each chain's own history (R/LNA_chpt_slice.R:608-630, 655-663).  The driver's adaptation
+    (rows floor(i/3) .. i-1, 2.38^2 cov / d, beta-mixture with 1e-4 I / d, tune) and stage switch are replayed here with the
+    restated R iteration bodies on the device-drawn streams: the chains must agree."""
+    from lnaphylodyn_b200 import api, mcmc, chains as chm, _lib
+    from lnaphylodyn_b200._lib import check
+    g = constant
+    coal, prior, proposal, control = vignette_args(g)
+    nch = len(g.x_r) - 1
+    B, niter, burn1, warmup2, up, seed = 3, 12, 2, 8, 2, 11
+    opt = {"burn1": burn1, "warmup2": warmup2, "up": up, "beta": 0.9, "tune": 0.5,
+           "parIdlist": {"a": 2, "b": 3, "c": 4, "d": 5 + nch}, "isLoglist": {"a": 1, "b": 0, "c": 1, "d": 0},
+           "priorIdlist": {"a": 1, "b": 2, "c": 3, "d": 5}}
+    res = mcmc.General_MCMC2(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=niter, burn=0, thin=1,
+                             changetime=g.x_r[1:], prior=prior, proposal=proposal, control=control,
+                             updateVec=(1, 1, 1, 0, 0.5, 1, 1), options=opt, n_chains=B, seed=seed)
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    par0 = np.concatenate([[g.x_r[0], float(control["alpha"][0]) * g.x_r[0]], [control["R0"], control["gamma"]], control["ch"],
+                           [control["hyper"]]])
+    st = [driver.init_state(g, par0, control["traj"]) for _ in range(B)]
+    pl = [prior[k] for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    entries = ((1, 1, 1), (2, 0, 2), (3, 1, 3), (4, 0, 5))
+    jopts = dict(driver.mcmc2_opts_from_golden(g), joint=[(j, lg, 1 if pid == 2 else 2 if pid == 5 else 0, tuple(pl[pid - 1][:2]))
+                                                          for j, lg, pid in entries])
+    hist = np.empty((B, niter, 44))
+    T = None
+    n2 = nch + 80
+    for i in range(1, niter + 1):
+        joint = i >= warmup2
+        if i == warmup2 or (i > warmup2 and i % up == 0):
+            lo = max(i // 3, 1)
+            h = hist[:, lo - 1:i - 1][:, :, [1, 2, 3, 43]].copy()
+            h[:, :, 0], h[:, :, 2] = np.log(h[:, :, 0]), np.log(h[:, :, 2])
+            cov = np.stack([np.cov(h[c].T) for c in range(B)])
+            pcov = (0.9 * (2.38 ** 2) * cov / 4 + 0.1 * np.eye(4) * 0.0001 / 4) * 0.5
+            T = chm.mvrnorm_transform(pcov)
+        nn = n2 + (4 if joint else 0)
+        nrm, unf = np.empty((B, nn)), np.empty((B, chm.ITER2_UNIF))
+        check(_lib.lib().lna_draw_streams(pb.h, B, 0, nn, chm.ITER2_UNIF, seed, i, api._ptr(nrm), api._ptr(unf)))
+        for c in range(B):
+            if joint:
+                st[c] = driver.mcmc2_joint_iteration(st[c], g, jopts, T[c], nrm[c], unf[c])
+            else:
+                st[c] = driver.mcmc2_iteration(st[c], g, driver.mcmc2_opts_from_golden(g, burn=i < burn1), nrm[c], unf[c])
+            hist[c, i - 1] = st[c]["par"]
+            assert relerr(res["par"][c, i - 1], st[c]["par"]) < 1e-8, (i, c)
+            assert res["l1"][c, i - 1] == pytest.approx(st[c]["coalLog"], rel=1e-8)
+    assert np.any(res["par"][:, warmup2 - 1:, 1] != res["par"][:, warmup2 - 2, 1][:, None])  # I0 moves in the joint stage
 
 
 def test_initialisation_from_the_priors(changepoint):
