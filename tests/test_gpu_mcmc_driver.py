@@ -155,3 +155,42 @@ def test_initialisation_from_the_priors(changepoint):
     assert ini["par"].shape == (64, 44) and np.all(np.isfinite(ini["coalLog"])) and np.all(ini["coalLog"] > -1e7)
     assert np.all(ini["par"][:, 2] == 2.0) and len(np.unique(ini["par"][:, 3])) == 64
     assert np.all(ini["par"][:, 4:43] > 0) and np.allclose(ini["logOrigin"], -0.5 * np.sum(ini["OriginTraj"] ** 2, axis=(1, 2)))
+
+
+def test_reference_chain_is_typical_of_the_gpu_ensemble(changepoint):
+    """Distributional check against the reference's OWN MCMC run.  The Changpoint_sim vignette ships the chain R produced
+    (2000 iterations, burn1 = 1000, from a fixed initial state; 104 of them are in tests/golden/changepoint_sim.npz).  R's random
+    numbers cannot be reproduced here, but the law of the chain at iteration t can: 384 chains run by the same driver call from
+    the same initial state give an ensemble at every t, and the reference's value at t must look like one more draw from it.
+    For R0, gamma, the hyper-parameter, three change ratios and coalLog the reference's rank in the ensemble is computed at the
+    cached iterations: ranks must not pile up at the edges (a wrong prior scale, proposal width or acceptance rule moves them
+    there within a few hundred iterations)."""
+    from lnaphylodyn_b200 import mcmc
+    g = changepoint
+    coal, prior, proposal, control = vignette_args(g)
+    nch = len(g.x_r) - 1
+    B, niter = 384, 2000
+    res = mcmc.General_MCMC_with_ESlice(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=niter, burn=0, thin=50,
+                                        changetime=g.x_r[1:], DEMS=("S", "I"), prior=prior, proposal=proposal, control=control,
+                                        ESS_vec=(0, 1, 0, 0, 1, 1, 0), likelihood="volz", model="SIR", Index=(0, 1), nparam=2,
+                                        method="admcmc", options={"burn1": 1000, "parIdlist": {"c": 4, "d": nch + 5},
+                                                                  "isLoglist": {"c": 1, "d": 0}, "priorIdlist": {"c": 3, "d": 5},
+                                                                  "hyper": False}, n_chains=B, seed=20261020)
+    idx = g.iters["index"].astype(int)  # 0-based iteration of each cached row
+    keep = idx >= 200  # past the initial transient, where ensemble spread is still tiny and ranks are all-or-nothing
+    cols = {"R0": 2, "gamma": 3, "hyper": 43, "ch_3": 6, "ch_20": 23, "ch_36": 39}
+    ranks = {}
+    def midrank(ens, ref):  # ties (chains still at a frozen / initial value) count half
+        return (ens < ref).mean(axis=0) + 0.5 * (ens == ref).mean(axis=0)
+
+    for name, c in cols.items():
+        sel = keep & (idx >= 1000) if name == "hyper" else keep  # the hyper-parameter is frozen before burn1
+        ranks[name] = midrank(res["par"][:, idx[sel], c], g.iters["par"][sel, c][None, :])
+    ranks["coalLog"] = midrank(res["l1"][:, idx[keep]], g.iters["coalLog"][keep][None, :])
+    allr = np.concatenate(list(ranks.values()))
+    assert np.mean((allr < 0.002) | (allr > 0.998)) < 0.05, {k: (float(v.min()), float(v.max())) for k, v in ranks.items()}
+    for name, r in ranks.items():
+        assert 0.08 < float(np.mean(r)) < 0.92, (name, float(np.mean(r)))
+    # the stage switch is visible in both: the hyper-parameter is frozen before burn1 and moves after
+    assert np.all(res["par"][:, :999, 43] == control["hyper"]) and np.std(res["par"][:, -1, 43]) > 0
+    assert np.all(g.iters["par"][idx < 999, 43] == control["hyper"])
