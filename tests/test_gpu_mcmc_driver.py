@@ -194,3 +194,32 @@ def test_reference_chain_is_typical_of_the_gpu_ensemble(changepoint):
     # the stage switch is visible in both: the hyper-parameter is frozen before burn1 and moves after
     assert np.all(res["par"][:, :999, 43] == control["hyper"]) and np.std(res["par"][:, -1, 43]) > 0
     assert np.all(g.iters["par"][idx < 999, 43] == control["hyper"])
+
+
+def test_reference_mcmc2_chain_is_typical_of_the_gpu_ensemble(constant):
+    """The same distributional check for General_MCMC2 on the constant_sim vignette's cached chain (2000 iterations, burn1 = 10:
+    scalar Metropolis entries for I0, R0, gamma, the hyper-parameter step, change-point and trajectory slice updates)."""
+    from lnaphylodyn_b200 import mcmc
+    g = constant
+    coal, prior, proposal, control = vignette_args(g)
+    nch = len(g.x_r) - 1
+    B, niter = 256, 2000
+    res = mcmc.General_MCMC2(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=niter, burn=0, thin=100,
+                             changetime=g.x_r[1:], prior=prior, proposal=proposal, control=control,
+                             updateVec=(1, 1, 1, 0, 0.5, 1, 1),
+                             options={"burn1": 10, "parIdlist": {"a": 2, "b": 3, "c": 4, "d": 5 + nch},
+                                      "isLoglist": {"a": 1, "b": 0, "c": 1, "d": 0}, "priorIdlist": {"a": 1, "b": 2, "c": 3, "d": 5},
+                                      "up": 1000000}, n_chains=B, seed=20261021)
+    idx = g.iters["index"].astype(int)
+    keep = idx >= 200
+
+    def midrank(ens, ref):
+        return (ens < ref).mean(axis=0) + 0.5 * (ens == ref).mean(axis=0)
+
+    ranks = {name: midrank(res["par"][:, idx[keep], c], g.iters["par"][keep, c][None, :])
+             for name, c in {"I0": 1, "R0": 2, "gamma": 3, "hyper": 43, "ch_1": 4, "ch_2": 5}.items()}
+    ranks["coalLog"] = midrank(res["l1"][:, idx[keep]], g.iters["coalLog"][keep][None, :])
+    allr = np.concatenate(list(ranks.values()))
+    assert np.mean((allr < 0.002) | (allr > 0.998)) < 0.05, {k: (float(v.min()), float(v.max())) for k, v in ranks.items()}
+    for name, r in ranks.items():
+        assert 0.08 < float(np.mean(r)) < 0.92, (name, float(np.mean(r)))
