@@ -118,6 +118,13 @@ int lna_kf_param(lna_problem *pb, int64_t B, const double *OdeTraj, const double
                  double *Acube, double *Scube, int32_t *status);
 /* Ode_Coarse_Slicer (:1179-1188). Ode_coarse: B x (nrow x (p+1)). */
 int lna_ode_coarse_slicer(lna_problem *pb, int64_t B, const double *OdeTraj, double *Ode_coarse);
+/* lna_full_loglik (likelihood only) without the synchronisation at the end: the outputs are valid after lna_problem_sync(),
+ * and every host buffer passed in must stay alive and unmodified until then (pinned memory, or the copies serialise).
+ * Consecutive calls alternate between two device staging sets, so the host-to-device copies of call n+1 overlap the last
+ * kernel of call n -- what a caller streaming many batches through host memory wants.  No reference counterpart. */
+int lna_full_loglik_async(lna_problem *pb, int64_t B, const double *param, const double *initial, const double *OriginTraj,
+                          double *coalLog, int32_t *status);
+
 /* New_Param_List (:1191-1208): ODE -> FT (A, L) -> coarse ODE -> betaN, fused in one kernel. */
 int lna_new_param_list(lna_problem *pb, int64_t B, const double *param, const double *initial,
                        double *Acube, double *Lcube, double *Ode_coarse, double *betaN, int32_t *status);

@@ -67,6 +67,7 @@ _SIGS = {
     "lna_coal_loglik": (C.c_int, [_vp, _I64, _vp, _vp, C.c_int, C.c_int, _vp]),
     "lna_full_loglik": (C.c_int, [_vp, _I64] + [_vp] * 10),
     "lna_full_loglik_dev": (C.c_int, [_vp, _I64] + [_vp] * 10),
+    "lna_full_loglik_async": (C.c_int, [_vp, _I64] + [_vp] * 5),
     "lna_update_param": (C.c_int, [_vp, _I64] + [_vp] * 14),
     "lna_param_slice_update": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp]),
     "lna_param_slice_update_all2": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp, _vp, _vp]),

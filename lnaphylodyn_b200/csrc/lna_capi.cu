@@ -105,6 +105,8 @@ struct lna_problem {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[8] = {};
     cudaEvent_t done_ev = nullptr;
+    cudaEvent_t async_done[2] = {};  // lna_full_loglik_async: last use of staging set 0 / 1
+    int async_parity = 0;
 };
 
 template <class T>
@@ -185,6 +187,7 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     cudaStreamCreateWithFlags(&pb->copy_stream, cudaStreamNonBlocking);
     for (auto &e : pb->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pb->done_ev, cudaEventDisableTiming);
+    for (auto &e : pb->async_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     DevProb &P = pb->dp;
     P.model = cfg->model;
     P.p = cfg->model == LNA_MODEL_SIR ? 2 : 3;
@@ -339,6 +342,8 @@ extern "C" void lna_problem_destroy(lna_problem *pb) {
     for (auto &e : pb->chunk_ev)
         if (e) cudaEventDestroy(e);
     if (pb->done_ev) cudaEventDestroy(pb->done_ev);
+    for (auto &e : pb->async_done)
+        if (e) cudaEventDestroy(e);
     if (pb->own_stream && pb->stream) cudaStreamDestroy(pb->stream);
     delete pb;
 }
@@ -586,6 +591,57 @@ extern "C" int lna_full_loglik_dev(lna_problem *pb, int64_t B, const double *par
                                 LatentTraj);
 }
 
+// Large likelihood-only batches through host buffers are PCIe-bound (992 B in per evaluation): the batch is split into
+// chunks and the H2D copy of chunk i+1 (copy stream) overlaps the kernel of chunk i (compute stream).
+// async: no synchronisation at the end -- the caller reads the outputs after lna_problem_sync() and keeps all host buffers
+// alive until then; consecutive asynchronous calls alternate between two staging sets, so the copies of call n+1 overlap
+// the last kernel of call n (they wait only for call n-1, the previous user of their staging set).
+static int full_loglik_chunked(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                               const double *OriginTraj, double *coalLog, int32_t *status, bool async) {
+    const DevProb &P = pb->dp;
+    const size_t p = P.p, k = P.k, nB = (size_t)B;
+    cudaSetDevice(pb->device);
+    const int nchunk = 4;  // >= 16k evaluations per chunk keeps each kernel off the ~0.2 ms single-evaluation latency floor
+    const int q = async ? (pb->async_parity ^= 1) : 0;
+    const size_t base = async ? 32 + 5 * (size_t)q : 0;
+    double *dpar = (double *)pb->scratch.get(base + 0, nB * P.npt * sizeof(double));
+    double *dini = (double *)pb->scratch.get(base + 1, nB * p * sizeof(double));
+    double *dor = (double *)pb->scratch.get(base + 2, nB * k * p * sizeof(double));
+    double *dcl = (double *)pb->scratch.get(base + 3, nB * sizeof(double));
+    int32_t *dst = (int32_t *)pb->scratch.get(base + 4, nB * sizeof(int32_t));
+    if (!dpar || !dini || !dor || !dcl || !dst) return fail("lna_full_loglik: device staging failed");
+    // the copy stream must not run ahead of earlier work that still reads the staging buffers
+    if (async) {
+        CK(cudaStreamWaitEvent(pb->copy_stream, pb->async_done[q], 0));  // (a never-recorded event does not block)
+    } else {
+        CK(cudaEventRecord(pb->done_ev, pb->stream));
+        CK(cudaStreamWaitEvent(pb->copy_stream, pb->done_ev, 0));
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        const size_t b0 = nB * c / nchunk, b1 = nB * (c + 1) / nchunk, n = b1 - b0;
+        if (!n) continue;
+        CK(cudaMemcpyAsync(dpar + b0 * P.npt, param + b0 * P.npt, n * P.npt * sizeof(double), cudaMemcpyHostToDevice,
+                           pb->copy_stream));
+        CK(cudaMemcpyAsync(dini + b0 * p, initial + b0 * p, n * p * sizeof(double), cudaMemcpyHostToDevice, pb->copy_stream));
+        CK(cudaMemcpyAsync(dor + b0 * k * p, OriginTraj + b0 * k * p, n * k * p * sizeof(double), cudaMemcpyHostToDevice,
+                           pb->copy_stream));
+        cudaEvent_t ev = pb->chunk_ev[(async ? 4 * q : 0) + c];
+        CK(cudaEventRecord(ev, pb->copy_stream));
+        CK(cudaStreamWaitEvent(pb->stream, ev, 0));
+        if (full_loglik_dev_impl(pb, (int64_t)n, dpar + b0 * P.npt, dini + b0 * p, dor + b0 * k * p, dcl + b0, dst + b0,
+                                 nullptr, nullptr, nullptr, nullptr, nullptr))
+            return -1;
+        CK(cudaMemcpyAsync(coalLog + b0, dcl + b0, n * sizeof(double), cudaMemcpyDeviceToHost, pb->stream));
+        if (status) CK(cudaMemcpyAsync(status + b0, dst + b0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, pb->stream));
+    }
+    if (async) {
+        CK(cudaEventRecord(pb->async_done[q], pb->stream));
+        return 0;
+    }
+    CK(cudaStreamSynchronize(pb->stream));
+    return 0;
+}
+
 extern "C" int lna_full_loglik(lna_problem *pb, int64_t B, const double *param, const double *initial,
                                const double *OriginTraj, double *coalLog, int32_t *status, double *Acube,
                                double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj) {
@@ -594,41 +650,8 @@ extern "C" int lna_full_loglik(lna_problem *pb, int64_t B, const double *param, 
     const DevProb &P = pb->dp;
     const size_t p = P.p, k = P.k, nrow = P.nrow, nB = (size_t)B;
     const bool ll_only = coalLog && !Acube && !Lcube && !Ode_coarse && !betaN && !LatentTraj;
-    if (ll_only && B >= 16384 && param && initial && OriginTraj && pb->copy_stream) {
-        // Large likelihood-only batches are PCIe-bound (992 B in per evaluation): split into chunks and
-        // overlap the H2D copy of chunk i+1 (copy stream) with the kernel of chunk i (compute stream).
-        cudaSetDevice(pb->device);
-        const int nchunk = 4;  // >= 16k evaluations per chunk keeps each kernel off the ~0.2 ms single-evaluation latency floor
-        double *dpar = (double *)pb->scratch.get(0, nB * P.npt * sizeof(double));
-        double *dini = (double *)pb->scratch.get(1, nB * p * sizeof(double));
-        double *dor = (double *)pb->scratch.get(2, nB * k * p * sizeof(double));
-        double *dcl = (double *)pb->scratch.get(3, nB * sizeof(double));
-        int32_t *dst = (int32_t *)pb->scratch.get(4, nB * sizeof(int32_t));
-        if (!dpar || !dini || !dor || !dcl || !dst) return fail("lna_full_loglik: device staging failed");
-        // the copy stream must not run ahead of earlier work that still reads the staging buffers
-        CK(cudaEventRecord(pb->done_ev, pb->stream));
-        CK(cudaStreamWaitEvent(pb->copy_stream, pb->done_ev, 0));
-        for (int c = 0; c < nchunk; ++c) {
-            const size_t b0 = nB * c / nchunk, b1 = nB * (c + 1) / nchunk, n = b1 - b0;
-            if (!n) continue;
-            CK(cudaMemcpyAsync(dpar + b0 * P.npt, param + b0 * P.npt, n * P.npt * sizeof(double),
-                               cudaMemcpyHostToDevice, pb->copy_stream));
-            CK(cudaMemcpyAsync(dini + b0 * p, initial + b0 * p, n * p * sizeof(double), cudaMemcpyHostToDevice,
-                               pb->copy_stream));
-            CK(cudaMemcpyAsync(dor + b0 * k * p, OriginTraj + b0 * k * p, n * k * p * sizeof(double),
-                               cudaMemcpyHostToDevice, pb->copy_stream));
-            CK(cudaEventRecord(pb->chunk_ev[c], pb->copy_stream));
-            CK(cudaStreamWaitEvent(pb->stream, pb->chunk_ev[c], 0));
-            if (full_loglik_dev_impl(pb, (int64_t)n, dpar + b0 * P.npt, dini + b0 * p, dor + b0 * k * p, dcl + b0,
-                                     dst + b0, nullptr, nullptr, nullptr, nullptr, nullptr))
-                return -1;
-            CK(cudaMemcpyAsync(coalLog + b0, dcl + b0, n * sizeof(double), cudaMemcpyDeviceToHost, pb->stream));
-            if (status)
-                CK(cudaMemcpyAsync(status + b0, dst + b0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, pb->stream));
-        }
-        CK(cudaStreamSynchronize(pb->stream));
-        return 0;
-    }
+    if (ll_only && B >= 16384 && param && initial && OriginTraj && pb->copy_stream)
+        return full_loglik_chunked(pb, B, param, initial, OriginTraj, coalLog, status, /*async=*/false);
     Stage s(pb);
     const double *dpar = s.in(param, nB * P.npt), *dini = s.in(initial, nB * p), *dor = s.in(OriginTraj, nB * k * p);
     double *dcl = s.out(coalLog, nB);
@@ -646,6 +669,17 @@ extern "C" int lna_full_loglik(lna_problem *pb, int64_t B, const double *param, 
     s.back(betaN, dbn, nB * nrow);
     s.back(LatentTraj, dlat, nB * nrow * (p + 1));
     return s.finish("lna_full_loglik");
+}
+
+extern "C" int lna_full_loglik_async(lna_problem *pb, int64_t B, const double *param, const double *initial,
+                                     const double *OriginTraj, double *coalLog, int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (!param || !initial || !OriginTraj || !coalLog) return fail("lna_full_loglik_async: null argument");
+    if (!pb->dp.has_init) return fail("lna_full_loglik_async: problem was created without a genealogy");
+    if (B < 16384 || !pb->copy_stream)  // small batches: nothing to overlap, the synchronous call is the asynchronous one
+        return lna_full_loglik(pb, B, param, initial, OriginTraj, coalLog, status, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return full_loglik_chunked(pb, B, param, initial, OriginTraj, coalLog, status, /*async=*/true);
 }
 
 extern "C" int lna_new_param_list(lna_problem *pb, int64_t B, const double *param, const double *initial,

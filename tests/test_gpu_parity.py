@@ -314,3 +314,32 @@ def test_seasonal_sirs_model_variant(api):
         l_o = orc.log_like_trajSIRS(sde, co, kf_o, 50, 90.0)
         l_d = api.log_like_trajSIRS(sde, co, kf_o, 50, 90.0)
         assert np.isfinite(l_o) and l_d == pytest.approx(l_o, rel=1e-7)
+
+
+def test_async_host_buffer_evaluation(changepoint):
+    """lna_full_loglik_async: several calls in flight on alternating staging sets give, after lna_problem_sync, exactly what
+    the synchronous call gives -- including when the same staging set is reused (4 calls) and for a batch below the
+    chunking threshold (falls back to the synchronous path)."""
+    import ctypes as C
+    from lnaphylodyn_b200 import _lib, api
+    g = changepoint
+    L = _lib.lib()
+    pb = api.Problem(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    rng = np.random.default_rng(4)
+    for B in (20000, 300):
+        sets = []
+        for s in range(4):
+            par = np.tile(g.final["par"].ravel(), (B, 1))
+            par[:, 2] *= np.exp(0.05 * rng.standard_normal(B))
+            par[:, 3] *= np.exp(0.05 * rng.standard_normal(B))
+            eps = np.ascontiguousarray(np.transpose(0.5 * rng.standard_normal((B, 40, 2)), (0, 2, 1)))
+            sets.append((np.ascontiguousarray(par[:, 2:]), np.ascontiguousarray(par[:, :2]), eps, np.empty(B), np.empty(B, dtype=np.int32)))
+        for prm, ini, eps, cl, st in sets:
+            _lib.check(L.lna_full_loglik_async(pb.h, B, api._ptr(prm), api._ptr(ini), api._ptr(eps), api._ptr(cl), api._ptr(st)), "async")
+        _lib.check(L.lna_problem_sync(pb.h), "sync")
+        for prm, ini, eps, cl, st in sets:
+            cl2, st2 = np.empty(B), np.empty(B, dtype=np.int32)
+            _lib.check(L.lna_full_loglik(pb.h, B, api._ptr(prm), api._ptr(ini), api._ptr(eps), api._ptr(cl2), api._ptr(st2),
+                                         None, None, None, None, None), "sync call")
+            assert np.array_equal(cl, cl2) and np.array_equal(st, st2)
+        assert len(np.unique(np.stack([s[3] for s in sets]), axis=0)) == 4
