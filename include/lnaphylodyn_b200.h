@@ -253,10 +253,23 @@ typedef struct lna_mcmc_opts {
     int32_t update_traj;  /* 1: run updateTraj_general_NC (i >= burn1); 0: skip (i < burn1)          */
     int32_t hyper_noop_mh;/* 1: also run the no-op hyper MH entry (parIdlist d)         */
     int32_t spec_width;   /* speculative candidates per wave for the parameter ESS (0 = auto)        */
+    /* General entry list of Update_Param_each_Norm (R/LNA_chpt_slice.R:169-265), used instead of the two fields above when
+     * n_mh > 0 (e.g. the Ebola vignette's parIdlist = (1, 3, nch + 5)): entries run in order, one Update_Param each.
+     * mh_kind 0: uniform random walk of half-width mh_prop on par[mh_index] (0 = S0, 1 = I0, 2 = R0, 3 = gamma), on the log
+     *            scale if mh_is_log, prior term dnorm(raw; mh_prior) (:211-217);
+     *         1: the hyper entry with hyper = F: no proposal, ch <- exp(log(ch) * hyper / hyper), offset 0;
+     *         2: the hyper entry with hyper = T: hyper' = hyper * exp(u), u ~ U(-mh_prop, mh_prop), prior term
+     *            dlnorm(hyper'; mh_prior) - u - dlnorm(hyper; mh_prior), ch <- exp(log(ch) * hyper / hyper') (:219-241). */
+    int32_t n_mh;
+    int32_t mh_kind[4], mh_index[4], mh_is_log[4];
+    double mh_prior[4][2];
+    double mh_prop[4];
 } lna_mcmc_opts;
 
 /* uniforms per chain-iteration: gamma RW draw, MH accept, hyper MH accept, ESS-par (22), ESS-traj (22) */
 #define LNA_ITER_UNIF (3 + 2 * LNA_ESLICE_MAX_UNIF)
+/* with the general entry list (n_mh > 0): (walk, accept) per entry in slots [2e, 2e+1], ESS-par at 8, ESS-traj at 30 */
+#define LNA_ITER_UNIF_GENERAL (2 * 4 + 2 * LNA_ESLICE_MAX_UNIF)
 
 lna_chains *lna_chains_create(lna_problem *pb, int64_t B);
 void lna_chains_destroy(lna_chains *ch);

@@ -15,6 +15,7 @@ from ._lib import LnaMcmcOpts, LnaError, check
 from .api import ESLICE_MAX_UNIF, _d, _ptr
 
 ITER_UNIF = 3 + 2 * ESLICE_MAX_UNIF
+ITER_UNIF_GENERAL = 2 * 4 + 2 * ESLICE_MAX_UNIF  # with a general Update_Param_each_Norm entry list (opts.n_mh > 0)
 
 
 def make_opts(prior, proposal, ESS_vec, update_traj=True, hyper_noop_mh=True, spec_width=0,
@@ -33,6 +34,30 @@ def make_opts(prior, proposal, ESS_vec, update_traj=True, hyper_noop_mh=True, sp
     for i in range(7):
         o.ESS_vec[i] = int(ESS_vec[i])
     o.update_traj, o.hyper_noop_mh, o.spec_width = int(update_traj), int(hyper_noop_mh), int(spec_width)
+    return o
+
+
+def make_opts_general(prior, proposal, ESS_vec, entries, hyper=False, update_traj=True, spec_width=0, hyper_prior_id=5):
+    """Like make_opts for an arbitrary Update_Param_each_Norm entry list (R/LNA_chpt_slice.R:169-265).  `entries`:
+    (R's 1-based parId, isLog, priorId) per list entry, e.g. the Ebola vignette's ((1, 1, 1), (3, 1, 3), (nch + 5, 0, 5)).
+    parId 1..4 = S0, I0, R0, gamma; the last par (nch + 5) = the hyper-parameter, which is the no-op entry with hyper = F and
+    a log-normal random walk with hyper = T.  The proposal ids equal the prior ids (:791-792)."""
+    pr = [np.asarray(v, dtype=np.float64).ravel() for v in prior]
+    po = [np.asarray(v, dtype=np.float64).ravel() for v in proposal]
+    o = make_opts(prior, proposal, ESS_vec, update_traj=update_traj, hyper_noop_mh=False, spec_width=spec_width,
+                  hyper_prior_id=hyper_prior_id)
+    if not 1 <= len(entries) <= 4:
+        raise ValueError("1..4 Update_Param_each_Norm entries")
+    o.n_mh = len(entries)
+    for e, (par_id, is_log, pid) in enumerate(entries):
+        if pid == 5:
+            o.mh_kind[e], o.mh_index[e], o.mh_is_log[e] = (2 if hyper else 1), -1, 0
+        elif 1 <= par_id <= 4 and 1 <= pid <= 4:
+            o.mh_kind[e], o.mh_index[e], o.mh_is_log[e] = 0, int(par_id) - 1, int(is_log)
+        else:
+            raise ValueError(f"entry {(par_id, is_log, pid)}: parId must be 1..4 with priorId 1..4, or the hyper-parameter with priorId 5")
+        o.mh_prior[e][0], o.mh_prior[e][1] = float(pr[pid - 1][0]), float(pr[pid - 1][1])
+        o.mh_prop[e] = float(po[pid - 1][0])
     return o
 
 
@@ -58,7 +83,8 @@ class Chains:
     def step(self, opts, normals, uniforms):
         """One MCMC iteration. normals (B, npar-1 + k*p), uniforms (B, 47): host arrays."""
         n, u = _d(normals), _d(uniforms)
-        assert n.shape == (self.B, self.n_norm) and u.shape == (self.B, ITER_UNIF), (n.shape, u.shape)
+        nu = ITER_UNIF_GENERAL if opts.n_mh > 0 else ITER_UNIF
+        assert n.shape == (self.B, self.n_norm) and u.shape == (self.B, nu), (n.shape, u.shape)
         check(_lib.lib().lna_chains_step(self.h, C.byref(opts), _ptr(n), _ptr(u)), "lna_chains_step")
 
     def step_dev(self, opts, normals_ptr, uniforms_ptr):
@@ -70,10 +96,11 @@ class Chains:
         check(_lib.lib().lna_chains_step_rng(self.h, C.byref(opts), int(seed), int(iteration), int(chain_offset)),
               "lna_chains_step_rng")
 
-    def device_streams(self, seed, iteration, chain_offset=0):
-        """The streams step_rng(seed, iteration, chain_offset) consumes, copied to the host."""
-        nrm, unf = np.empty((self.B, self.n_norm)), np.empty((self.B, ITER_UNIF))
-        check(_lib.lib().lna_draw_streams(self.pb.h, self.B, int(chain_offset), self.n_norm, ITER_UNIF, int(seed),
+    def device_streams(self, seed, iteration, chain_offset=0, n_unif=ITER_UNIF):
+        """The streams step_rng(seed, iteration, chain_offset) consumes, copied to the host (n_unif = ITER_UNIF_GENERAL for
+        options with a general entry list)."""
+        nrm, unf = np.empty((self.B, self.n_norm)), np.empty((self.B, n_unif))
+        check(_lib.lib().lna_draw_streams(self.pb.h, self.B, int(chain_offset), self.n_norm, n_unif, int(seed),
                                           int(iteration), _ptr(nrm), _ptr(unf)), "lna_draw_streams")
         return nrm, unf
 

@@ -757,15 +757,45 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
     if (o->ESS_vec[6] != 0) return fail("lna_chains_step: ESS_vec[7] = 1 is not supported");
     const int W = o->spec_width;  // 0 = auto (two-phase when the machine-filling width is 16)
     if (chains_ensure_scratch(ch, W)) return -1;
-    const long long sn = (long long)ch->n_norm, su = (long long)ch->n_unif;
+    const bool general = o->n_mh > 0;
+    const long long sn = (long long)ch->n_norm, su = general ? (long long)LNA_ITER_UNIF_GENERAL : (long long)ch->n_unif;
+    const int ess_u = general ? 8 : 3;  // first uniform of the parameter slice update
     const int npar = 2 + P.npt;
     CandArgs a;
+    if (general) {
+        // Update_Param_each_Norm with an arbitrary entry list: one Update_Param per entry, in order
+        if (o->n_mh > 4) return fail("lna_chains_step: n_mh must be 0..4");
+        for (int e = 0; e < o->n_mh; ++e) {
+            chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 2 * e, su, 1}, a);
+            a.mh_pr[0] = o->mh_prior[e][0];
+            a.mh_pr[1] = o->mh_prior[e][1];
+            a.mh_prop = o->mh_prop[e];
+            if (o->mh_kind[e] == 0) {
+                if (o->mh_index[e] < 0 || o->mh_index[e] > 3)
+                    return fail("lna_chains_step: mh_index must be 0 (S0), 1 (I0), 2 (R0) or 3 (gamma)");
+                a.mh_index = o->mh_index[e];
+                a.mh_is_log = o->mh_is_log[e];
+                a.mh_prior_kind = 0;
+                if (chains_stage<PROP_MH_SCALAR>(ch, a, 1)) return -1;
+            } else if (o->mh_kind[e] == 1) {
+                chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 2 * e + 1, su, 1}, a);  // (accept draw only)
+                if (chains_stage<PROP_HYPER_NOOP>(ch, a, 1)) return -1;
+            } else if (o->mh_kind[e] == 2) {
+                a.mh_prior_kind = 2;
+                if (chains_stage<PROP_MH_HYPER>(ch, a, 1)) return -1;
+            } else {
+                return fail("lna_chains_step: mh_kind must be 0, 1 or 2");
+            }
+        }
+    }
     // 1. Update_Param_each_Norm: gamma random walk (entry c) and the no-op hyper entry (d)  [A.17]
     chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
     a.gamma_prior[0] = o->gamma_prior[0];
     a.gamma_prior[1] = o->gamma_prior[1];
     a.gamma_prop = o->gamma_prop;
-    if (o->hyper_noop_mh && ch->planB * 4 <= (long long)pb->sm_count * 512) {
+    if (general) {
+        // (done above)
+    } else if (o->hyper_noop_mh && ch->planB * 4 <= (long long)pb->sm_count * 512) {
         // few chains: both MH entries speculatively in one latency period (3 evaluations per chain)
         if (chains_stage<PROP_MH_PAIR>(ch, a, 4)) return -1;
     } else {
@@ -777,13 +807,13 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
         }
     }
     // 2. update_Par_ESlice_combine -> ESlice_par_General
-    chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 3, su, 1}, a);
+    chains_base_args(ch, View{normals, sn, 1}, View{uniforms + ess_u, su, 1}, a);
     for (int i = 0; i < 8; ++i) a.pr[i] = o->prior8[i];
     for (int i = 0; i < 7; ++i) a.ess[i] = o->ESS_vec[i];
     if (chains_stage<PROP_ESS_PAR>(ch, a, W)) return -1;
     // 3. updateTraj_general_NC -> ESlice_general_NC
     if (o->update_traj &&
-        chains_traj(ch, View{normals + (npar - 1), sn, 1}, View{uniforms + 3 + LNA_ESLICE_MAX_UNIF, su, 1}))
+        chains_traj(ch, View{normals + (npar - 1), sn, 1}, View{uniforms + ess_u + LNA_ESLICE_MAX_UNIF, su, 1}))
         return -1;
     return chains_finish(ch);
 }
@@ -870,7 +900,8 @@ static int part_step(ChainPart *ch, const lna_mcmc_opts *o, const double *normal
     cudaSetDevice(pb->device);
     const size_t nB = (size_t)ch->B;
     CK(cudaMemcpyAsync(ch->stage_n, normals, sizeof(double) * nB * ch->n_norm, cudaMemcpyHostToDevice, pb->stream));
-    CK(cudaMemcpyAsync(ch->stage_u, uniforms, sizeof(double) * nB * ch->n_unif, cudaMemcpyHostToDevice, pb->stream));
+    const size_t nu = o->n_mh > 0 ? (size_t)LNA_ITER_UNIF_GENERAL : ch->n_unif;
+    CK(cudaMemcpyAsync(ch->stage_u, uniforms, sizeof(double) * nB * nu, cudaMemcpyHostToDevice, pb->stream));
     return part_step_dev(ch, o, ch->stage_n, ch->stage_u);
 }
 
@@ -904,8 +935,8 @@ static int part_step_rng(ChainPart *ch, const lna_mcmc_opts *o, uint64_t seed, u
     if (!ch || !o) return fail("lna_chains_step_rng: null argument");
     lna_problem *pb = ch->pb;
     cudaSetDevice(pb->device);
-    if (draw_streams_dev(pb, ch->B, chain_offset, (int)ch->n_norm, (int)ch->n_unif, seed, iteration, ch->stage_n,
-                         ch->stage_u))
+    const int nu = o->n_mh > 0 ? (int)LNA_ITER_UNIF_GENERAL : (int)ch->n_unif;
+    if (draw_streams_dev(pb, ch->B, chain_offset, (int)ch->n_norm, nu, seed, iteration, ch->stage_n, ch->stage_u))
         return -1;
     return part_step_dev(ch, o, ch->stage_n, ch->stage_u);
 }
@@ -1072,7 +1103,9 @@ extern "C" int lna_chains_step_dev(lna_chains *ch, const lna_mcmc_opts *o, const
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
     if (chains_fork(ch)) return -1;
     for (int g = 0; g < ch->G; ++g)
-        if (part_step_dev(ch->part[g], o, normals + ch->off[g] * ch->n_norm, uniforms + ch->off[g] * ch->n_unif)) return -1;
+        if (part_step_dev(ch->part[g], o, normals + ch->off[g] * ch->n_norm,
+                          uniforms + ch->off[g] * (o->n_mh > 0 ? (size_t)LNA_ITER_UNIF_GENERAL : ch->n_unif)))
+            return -1;
     return chains_join(ch);
 }
 
@@ -1080,7 +1113,9 @@ extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const dou
     if (!ch || !o || !normals || !uniforms) return fail("lna_chains_step: null argument");
     if (chains_fork(ch)) return -1;
     for (int g = 0; g < ch->G; ++g)
-        if (part_step(ch->part[g], o, normals + ch->off[g] * ch->n_norm, uniforms + ch->off[g] * ch->n_unif)) return -1;
+        if (part_step(ch->part[g], o, normals + ch->off[g] * ch->n_norm,
+                      uniforms + ch->off[g] * (o->n_mh > 0 ? (size_t)LNA_ITER_UNIF_GENERAL : ch->n_unif)))
+            return -1;
     return chains_join(ch);
 }
 

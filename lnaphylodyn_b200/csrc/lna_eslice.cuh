@@ -348,6 +348,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
                          ? dnorm_log(rnew, a.mh_pr[0], a.mh_pr[1]) - dnorm_log(raw, a.mh_pr[0], a.mh_pr[1])
                          : dunif_log(rnew, a.mh_pr[0], a.mh_pr[1]) - dunif_log(raw, a.mh_pr[0], a.mh_pr[1]);
             const double val = a.mh_is_log ? exp(rnew) : rnew;
+            if (j == 0) x.S0 = val;
             if (j == 1) x.I0 = val;
             if (j == 2) x.R0 = val;
             if (j == 3) x.gam = val;
@@ -385,7 +386,13 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
         if (kProp == PROP_MH_HYPER) {
             const double hp = a.mh_prop, uu = -hp + (hp - (-hp)) * unif(iu++);
             x.hyper_new = x.hyper_old * exp(uu);
-            offset = dgamma_log(x.hyper_new, a.mh_pr[0], a.mh_pr[1]) - dgamma_log(x.hyper_old, a.mh_pr[0], a.mh_pr[1]) + uu;
+            if (a.mh_prior_kind == 2) {
+                // Update_Param_each_Norm with hyper = T (:219-227): dlnorm(new) - u - dlnorm(old)
+                const double ln = log(x.hyper_new), lo = log(x.hyper_old);
+                offset = (dnorm_log(ln, a.mh_pr[0], a.mh_pr[1]) - ln) - uu - (dnorm_log(lo, a.mh_pr[0], a.mh_pr[1]) - lo);
+            } else {  // update_hyper of General_MCMC2 (general_change_point.R:296-299)
+                offset = dgamma_log(x.hyper_new, a.mh_pr[0], a.mh_pr[1]) - dgamma_log(x.hyper_old, a.mh_pr[0], a.mh_pr[1]) + uu;
+            }
             prop = x.hyper_new;
         }
         ChProp<kProp> chs{a.par, a.normals, c, 4, x};

@@ -154,12 +154,18 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
         raise LnaError("General_MCMC_with_ESlice: ESS_vec2 (second parameter slice update) is not built")
     options = dict(options or {})
     nch = len(np.ravel(changetime))
-    par_ids = dict(options.get("parIdlist") or {"c": 4, "d": nch + 5})
-    if [int(v) for v in par_ids.values()] != [4, nch + 5] or bool(options.get("hyper", False)) or \
-            [int(v) for v in dict(options.get("priorIdlist") or {"c": 3, "d": 5}).values()] != [3, 5] or \
-            [int(v) for v in dict(options.get("isLoglist") or {"c": 1, "d": 0}).values()] != [1, 0]:
-        raise LnaError("General_MCMC_with_ESlice: Update_Param_each_Norm is built for the vignettes' entries "
-                       "parIdlist = (4, nch + 5), isLoglist = (1, 0), priorIdlist = (3, 5), hyper = F")
+    par_ids = [int(v) for v in dict(options.get("parIdlist") or {"c": 4, "d": nch + 5}).values()]
+    is_logs = [int(v) for v in dict(options.get("isLoglist") or {"c": 1, "d": 0}).values()]
+    pr_ids = [int(v) for v in dict(options.get("priorIdlist") or {"c": 3, "d": 5}).values()]
+    hyper_flag = bool(options.get("hyper", False))
+    if not (len(par_ids) == len(is_logs) == len(pr_ids)):
+        raise LnaError("General_MCMC_with_ESlice: parameters do not match")  # check_list_eq, R/LNA_chpt_slice.R:175-185
+    for pid_, prid_ in zip(par_ids, pr_ids):
+        if not ((1 <= pid_ <= 4 and 1 <= prid_ <= 4) or (pid_ == nch + 5 and prid_ == 5)):
+            raise LnaError("General_MCMC_with_ESlice: Update_Param_each_Norm entries are built for parId 1..4 (S0, I0, R0, gamma) "
+                           "with priorId 1..4 and for the hyper-parameter (parId nch + 5, priorId 5)")
+    # the vignettes' (gamma, no-op hyper) pair keeps its dedicated path: both entries in one latency period
+    standard_entries = par_ids == [4, nch + 5] and is_logs == [1, 0] and pr_ids == [3, 5] and not hyper_flag
     if int(ESS_vec[0]) or int(ESS_vec[6]):
         raise LnaError("General_MCMC_with_ESlice: ESS_vec[1] (I0) / ESS_vec[7] (self-mixing OriginTraj) are rejected, "
                        "see DESIGN.md section 7")
@@ -171,8 +177,14 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
     pr, po = _lists(setting["prior"], _PRIOR_ORDER, "prior"), _lists(setting["proposal"], _PROP_ORDER, "proposal")
     ess_temp = list(ESS_vec)
     ess_temp[4] = 0
-    o_burn = chm.make_opts(pr, po, ess_temp, update_traj=False)
-    o_full = chm.make_opts(pr, po, list(ESS_vec), update_traj=True)
+    if standard_entries:
+        o_burn = chm.make_opts(pr, po, ess_temp, update_traj=False)
+        o_full = chm.make_opts(pr, po, list(ESS_vec), update_traj=True)
+    else:
+        ent = tuple(zip(par_ids, is_logs, pr_ids))
+        # (i < burn1 runs the entries with hyper = F, i >= burn1 with options$hyper: R/LNA_chpt_slice.R:791-792, 809-810)
+        o_burn = chm.make_opts_general(pr, po, ess_temp, ent, hyper=False, update_traj=False)
+        o_full = chm.make_opts_general(pr, po, list(ESS_vec), ent, hyper=hyper_flag, update_traj=True)
     burn1 = int(options.get("burn1", 5000))
     B, niter, thin = int(n_chains), int(niter), int(thin)
     rec = {"par": np.empty((B, niter, ch.npar)), "l": np.empty((B, niter)), "l1": np.empty((B, niter)),

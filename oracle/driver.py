@@ -10,6 +10,8 @@ composed from the C oracle's functions, with pre-drawn streams laid out like the
 lna_chains_step: normals = [npar-1 for the parameter ESS | k*p for the trajectory ESS],
 uniforms = [gamma RW draw, gamma MH accept, hyper MH accept, 22 for the parameter ESS, 22 for the trajectory ESS].
 """
+import math
+
 import numpy as np
 
 from . import oracle as orc
@@ -85,6 +87,51 @@ def eslice_iteration(st, g, opts, normals, uniforms):
                                                                               t["logOrigin"])
         st["n_cheap"] += t["n_evals"]
         st["last_traj_evals"] = t["n_evals"]
+    return st
+
+
+def eslice_iteration_general(st, g, opts, normals, uniforms):
+    """General_MCMC_with_ESlice's loop body with an ARBITRARY Update_Param_each_Norm entry list (R/LNA_chpt_slice.R:169-265),
+    e.g. the Ebola vignette's parIdlist = (1, 3, nch + 5).  opts["entries"]: (0-based par index or -1 for the hyper entry,
+    isLog, (prior mean, sd), proposal half-width); opts["hyper"]: the R call's `hyper` flag.  Streams as the product's general
+    layout: uniforms [2e, 2e+1] = (walk, accept) of entry e, [8:30] parameter ESS, [30:52] trajectory ESS."""
+    npar = len(st["par"])
+    nch = npar - 5
+    for e, (idx, is_log, pr, po) in enumerate(opts["entries"]):
+        par_new = st["par"].copy()
+        if idx >= 0:  # priorId in 1:4 (:211-217)
+            raw = math.log(par_new[idx]) if is_log else float(par_new[idx])
+            raw_new = raw + (-po + (po - (-po)) * uniforms[2 * e])
+            off = dnorm_log(raw_new, pr[0], pr[1]) - dnorm_log(raw, pr[0], pr[1])
+            par_new[idx] = math.exp(raw_new) if is_log else raw_new
+        else:  # the hyper entry (priorId 5)
+            hy = float(par_new[npar - 1])
+            if opts.get("hyper", False):  # :219-227
+                u = -po + (po - (-po)) * uniforms[2 * e]
+                hy_new = hy * math.exp(u)
+                ln, lo = math.log(hy_new), math.log(hy)
+                off = (dnorm_log(ln, pr[0], pr[1]) - ln) - u - (dnorm_log(lo, pr[0], pr[1]) - lo)
+            else:
+                hy_new, off = hy, 0.0
+            par_new[4:4 + nch] = np.exp(np.log(par_new[4:4 + nch]) * hy / hy_new)  # :238-241
+            par_new[npar - 1] = hy_new
+        _mh(st, g, par_new, off, uniforms[2 * e + 1])
+    r = orc.ESlice_par_General(st["par"], g.times, st["OriginTraj"], opts["priorList"], g.x_r, g.x_i, g.init,
+                               g.gridsize, opts["ESS_vec"], st["coalLog"], g.t_correct,
+                               normals=normals[:npar - 1], uniforms=uniforms[8:30])
+    st["n_full"] += r["n_evals"]
+    if not (r["status"] & 1):
+        st["par"], st["LatentTraj"], st["betaN"], st["FT"] = r["par"], r["LatentTraj"], r["betaN"], r["FT"]
+        st["coalLog"], st["Ode"] = r["CoalLog"], r["OdeTraj"]
+    if opts.get("update_traj", True):
+        betaN = orc.betaTs(st["par"][2:npar - 1], st["LatentTraj"][:, 0], g.x_r, g.x_i)
+        t = orc.ESlice_general_NC(st["OriginTraj"], st["Ode"], st["FT"], st["par"][:2], g.init, betaN, g.t_correct,
+                                  1.0, st["coalLog"], g.gridsize, True, "SIR", normals=normals[npar - 1:],
+                                  uniforms=uniforms[30:52])
+        new_cl = orc.volz_loglik_nh2(g.init, t["LatentTraj"], betaN, g.t_correct, g.x_i[2:4])
+        st["coalLog"], st["LatentTraj"], st["OriginTraj"], st["logOrigin"] = (new_cl, t["LatentTraj"], t["OriginTraj"],
+                                                                              t["logOrigin"])
+        st["n_cheap"] += t["n_evals"]
     return st
 
 

@@ -136,3 +136,58 @@ def test_full_size_properties(api, changepoint):
     assert np.array_equal(st, r1["status"][pick])
     assert np.max(np.abs(ref - r1["coalLog"][pick]) / np.abs(ref)) < TOL
     assert 0 < np.mean(r1["coalLog"] == orc.SENTINEL) < 0.5
+
+
+class _EbolaSetting:
+    """The few attributes oracle/driver.py reads from a Golden, for the Ebola vignette's set-up."""
+
+    def __init__(self):
+        z = np.load(os.path.join(GOLDEN, "ebola_tree.npz"))
+        s = gen.summarize_phylo(z["edge"], z["edge_length"], int(z["ntip"]))
+        self.coal = {k: s[k] for k in ("samp_times", "n_sampled", "coal_times")}
+        self.times = np.linspace(0, 1.36, 2001)
+        self.gridsize, self.t_correct = 50, 1.36
+        self.init = gen.coal_lik_init(s["samp_times"], s["n_sampled"], s["coal_times"], self.times[::50])
+        self.cht = self.times[::50][1:-1]
+        self.x_r, self.x_i = np.concatenate([[7e6], self.cht]), [len(self.cht), 2, 0, 1]
+
+
+def test_ebola_vignette_iteration_as_written():
+    """vignettes/Ebola_sierra_leone2014.Rmd:76-88 AS WRITTEN: its Update_Param_each_Norm entry list is
+    parIdlist = (1, 3, nch + 5), isLoglist = (1, 1, 0), priorIdlist = (1, 3, 5) -- a log random walk on S0 under pop_pr, one on
+    R0 under gamma_pr, and the no-op hyper entry -- not the (gamma, hyper) pair of the other vignettes.  The driver runs it
+    through the general entry list; chains must follow the restated R iteration (oracle/driver.py::eslice_iteration_general)
+    step for step on the device-drawn streams, through both stages (burn1)."""
+    from lnaphylodyn_b200 import api, mcmc, chains as chm, _lib
+    from oracle import driver
+    g = _EbolaSetting()
+    nch = len(g.cht)
+    prior = {"pop_pr": [1, 0.5, 1, 1], "R0_pr": [0.7, 0.5], "gamma_pr": [3, 0.1], "mu_pr": [3, 0.15], "hyper_pr": [3, 0.2]}
+    proposal = {"pop_prop": 0.2, "R0_prop": 0.05, "gamma_prop": 0.09, "mu_prop": 0.1, "hyper_prop": 0.2}
+    control = {"alpha": [1 / 7e6], "R0": 2.0, "gamma": 30.0, "ch": np.full(nch, 0.975), "traj": np.zeros((40, 2)), "hyper": 20.0}
+    B, niter, burn1, seed = 4, 6, 3, 17
+    res = mcmc.General_MCMC_with_ESlice(g.coal, g.times, 1.36, 7e6, gridsize=50, niter=niter, burn=0, thin=1,
+                                        changetime=g.cht, DEMS=("S", "I"), prior=prior, proposal=proposal, control=control,
+                                        ESS_vec=(0, 1, 0, 0, 1, 1, 0), likelihood="volz", model="SIR", Index=(0, 1), nparam=2,
+                                        method="admcmc",
+                                        options={"joint": True, "PCOV": None, "beta": 0.95, "burn1": burn1,
+                                                 "parIdlist": {"a": 1, "c": 3, "d": nch + 5}, "isLoglist": {"a": 1, "c": 1, "d": 0},
+                                                 "priorIdlist": {"a": 1, "c": 3, "d": 5}, "up": 1000000, "tune": 0.01, "hyper": False},
+                                        n_chains=B, seed=seed)
+    par0 = np.concatenate([[7e6, 1.0, 2.0, 30.0], control["ch"], [20.0]])
+    st = [driver.init_state(g, par0, control["traj"]) for _ in range(B)]
+    pl = [np.asarray(prior[k], dtype=float) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    base = {"priorList": [pl[0][:2], pl[1][:2], pl[2][:2], pl[4][:2]], "hyper": False,
+            "entries": [(0, 1, (1.0, 0.5), 0.2), (2, 1, (3.0, 0.1), 0.09), (-1, 0, (3.0, 0.2), 0.2)]}
+    pb = api.problem_for(g.times, g.x_r, g.x_i, 50, 1.36, g.init)
+    n_norm = 43 + 80
+    nrm, unf = np.empty((B, n_norm)), np.empty((B, chm.ITER_UNIF_GENERAL))
+    for i in range(1, niter + 1):
+        _lib.check(_lib.lib().lna_draw_streams(pb.h, B, 0, n_norm, chm.ITER_UNIF_GENERAL, seed, i, api._ptr(nrm), api._ptr(unf)))
+        full = i >= burn1
+        opts = dict(base, ESS_vec=[0, 1, 0, 0, 1 if full else 0, 1, 0], update_traj=full)
+        for c in range(B):
+            st[c] = driver.eslice_iteration_general(st[c], g, opts, nrm[c], unf[c])
+            assert relerr(res["par"][c, i - 1], st[c]["par"]) < 1e-9, (i, c)
+            assert res["l1"][c, i - 1] == pytest.approx(st[c]["coalLog"], rel=1e-9), (i, c)
+    assert np.any(res["par"][:, -1, 0] != 7e6) and np.all(res["par"][:, :, 3] == 30.0)  # S0 walks, gamma is never updated

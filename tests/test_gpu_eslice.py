@@ -418,3 +418,38 @@ def test_chains_mcmc2_joint_stage_step_for_step(api, constant):
     assert 0 < acc < B * iters
     moved = np.abs(s["par"][:, [1, 2, 3, 43]] / par0[[1, 2, 3, 43]] - 1.0) > 0
     assert moved.any(axis=0).all()  # every jointly proposed parameter moved in some chain
+
+
+def test_chains_general_entry_list_with_hyper_proposal(api, changepoint):
+    """Update_Param_each_Norm with hyper = T (R/LNA_chpt_slice.R:219-241): the hyper entry proposes hyper' = hyper e^u under a
+    log-normal prior and rescales the change ratios; plus an I0 entry on the log scale and an R0 entry on the raw scale --
+    the general entry list against the restated R iteration, step for step."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    B, iters, seed = 7, 5, 91
+    nch = 39
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    ref = [driver.init_state(g, par0, g.setting("control.traj")) for _ in range(B)]
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    proposal = [g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+    entries = ((2, 1, 1), (3, 0, 2), (4, 1, 3), (nch + 5, 0, 5))  # I0 (log), R0 (raw), gamma (log), hyper
+    ess = [0, 1, 0, 0, 1, 1, 0]
+    opts = chm.make_opts_general(prior, proposal, ess, entries, hyper=True, update_traj=True)
+    oopts = {"priorList": [prior[0][:2], prior[1][:2], prior[2][:2], prior[4][:2]], "ESS_vec": ess, "update_traj": True,
+             "hyper": True,
+             "entries": [(1, 1, tuple(prior[0][:2]), float(proposal[0][0])), (2, 0, tuple(prior[1][:2]), float(proposal[1][0])),
+                         (3, 1, tuple(prior[2][:2]), float(proposal[2][0])), (-1, 0, tuple(prior[4][:2]), float(proposal[4][0]))]}
+    for it in range(iters):
+        rng = np.random.default_rng([seed, it])
+        nrm, unf = rng.standard_normal((B, ch.n_norm)), rng.random((B, chm.ITER_UNIF_GENERAL))
+        ch.step(opts, nrm, unf)
+        s = ch.get()
+        for c in range(B):
+            ref[c] = driver.eslice_iteration_general(ref[c], g, oopts, nrm[c], unf[c])
+            assert relerr(s["par"][c], ref[c]["par"]) < TOL, (it, c)
+            assert s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL), (it, c)
+            assert s["n_full_evals"][c] == ref[c]["n_full"] and s["n_mh_accept"][c] == ref[c]["n_mh_accept"], (it, c)
+    assert len(np.unique(s["par"][:, 43])) > 1 and len(np.unique(s["par"][:, 1])) > 1  # hyper and I0 moved
