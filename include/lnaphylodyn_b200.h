@@ -264,6 +264,11 @@ typedef struct lna_mcmc_opts {
     int32_t mh_kind[4], mh_index[4], mh_is_log[4];
     double mh_prior[4][2];
     double mh_prop[4];
+    /* ESS_vec2 of General_MCMC_with_ESlice (R/LNA_chpt_slice.R:826-833): when use_ess2 is set, iterations with update_traj run
+     * a SECOND update_Par_ESlice_combine with ESS_vec2 INSTEAD of the trajectory slice update; it consumes the first npar-1
+     * normals and the 22 uniforms of the trajectory update's slots. */
+    int32_t use_ess2;
+    int32_t ESS_vec2[7];
 } lna_mcmc_opts;
 
 /* uniforms per chain-iteration: gamma RW draw, MH accept, hyper MH accept, ESS-par (22), ESS-traj (22) */

@@ -27,7 +27,8 @@ class LnaMcmcOpts(C.Structure):
     _fields_ = [("prior8", C.c_double * 8), ("gamma_prior", C.c_double * 2), ("gamma_prop", C.c_double),
                 ("ESS_vec", C.c_int32 * 7), ("update_traj", C.c_int32), ("hyper_noop_mh", C.c_int32),
                 ("spec_width", C.c_int32), ("n_mh", C.c_int32), ("mh_kind", C.c_int32 * 4), ("mh_index", C.c_int32 * 4),
-                ("mh_is_log", C.c_int32 * 4), ("mh_prior", (C.c_double * 2) * 4), ("mh_prop", C.c_double * 4)]
+                ("mh_is_log", C.c_int32 * 4), ("mh_prior", (C.c_double * 2) * 4), ("mh_prop", C.c_double * 4),
+                ("use_ess2", C.c_int32), ("ESS_vec2", C.c_int32 * 7)]
 
 
 class LnaMcmc2Opts(C.Structure):

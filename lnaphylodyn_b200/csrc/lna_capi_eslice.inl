@@ -811,6 +811,15 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
     for (int i = 0; i < 8; ++i) a.pr[i] = o->prior8[i];
     for (int i = 0; i < 7; ++i) a.ess[i] = o->ESS_vec[i];
     if (chains_stage<PROP_ESS_PAR>(ch, a, W)) return -1;
+    if (o->update_traj && o->use_ess2) {
+        // 3'. ESS_vec2: a second parameter slice update instead of the trajectory update (:826-833)
+        if (o->ESS_vec2[6] != 0) return fail("lna_chains_step: ESS_vec2[7] = 1 is not supported");
+        chains_base_args(ch, View{normals + (npar - 1), sn, 1}, View{uniforms + ess_u + LNA_ESLICE_MAX_UNIF, su, 1}, a);
+        for (int i = 0; i < 8; ++i) a.pr[i] = o->prior8[i];
+        for (int i = 0; i < 7; ++i) a.ess[i] = o->ESS_vec2[i];
+        if (chains_stage<PROP_ESS_PAR>(ch, a, W)) return -1;
+        return chains_finish(ch);
+    }
     // 3. updateTraj_general_NC -> ESlice_general_NC
     if (o->update_traj &&
         chains_traj(ch, View{normals + (npar - 1), sn, 1}, View{uniforms + ess_u + LNA_ESLICE_MAX_UNIF, su, 1}))

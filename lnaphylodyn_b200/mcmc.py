@@ -8,8 +8,8 @@ device through the resident-chain C ABI (`lna_chains_step*`, see chains.py); thi
 them: set-up, initial state, stage switching (`burn1`, `warmup2`), thinning and storage.
 
 What is NOT here, and raises instead of guessing: likelihood other than "volz", models other than "SIR" (the
-reference's samplers are hard-wired to p = 2, LNA_functional.cpp:1456-1462), `ESS_vec2`, Metropolis entry lists other
-than the vignettes'.  General_MCMC2's adaptive joint random-walk stage (`i >= warmup2`) draws its proposal as
+reference's samplers are hard-wired to p = 2, LNA_functional.cpp:1456-1462), vector-valued Metropolis entries, the
+self-mixing `ESS_vec[7]` branch.  General_MCMC2's adaptive joint random-walk stage (`i >= warmup2`) draws its proposal as
 MASS::mvrnorm does (eigen-decomposition of the covariance), with LAPACK's eigenvector signs: same proposal distribution, the
 realisation for given normals is not pinned (MASS is outside the reference tree).
 The random numbers are Philox streams drawn on the device (seed, chain, iteration) -- R's generator is not
@@ -150,8 +150,8 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
     Returns {par (chains, niter, npar), Trajectory (chains, niter/thin, nrow, p+1), l, l1, MCMC_setting, MCMC_obj}."""
     if likelihood != "volz" or model != "SIR":
         raise LnaError("General_MCMC_with_ESlice: the GPU path has the volz likelihood with model = 'SIR' only")
-    if ESS_vec2 is not None:
-        raise LnaError("General_MCMC_with_ESlice: ESS_vec2 (second parameter slice update) is not built")
+    if ESS_vec2 is not None and int(ESS_vec2[6]):
+        raise LnaError("General_MCMC_with_ESlice: ESS_vec2[7] (self-mixing OriginTraj) is rejected, see DESIGN.md section 7")
     options = dict(options or {})
     nch = len(np.ravel(changetime))
     par_ids = [int(v) for v in dict(options.get("parIdlist") or {"c": 4, "d": nch + 5}).values()]
@@ -185,6 +185,10 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
         # (i < burn1 runs the entries with hyper = F, i >= burn1 with options$hyper: R/LNA_chpt_slice.R:791-792, 809-810)
         o_burn = chm.make_opts_general(pr, po, ess_temp, ent, hyper=False, update_traj=False)
         o_full = chm.make_opts_general(pr, po, list(ESS_vec), ent, hyper=hyper_flag, update_traj=True)
+    if ESS_vec2 is not None:  # a second parameter slice update replaces the trajectory update for i >= burn1 (:826-833)
+        o_full.use_ess2 = 1
+        for q in range(7):
+            o_full.ESS_vec2[q] = int(ESS_vec2[q])
     burn1 = int(options.get("burn1", 5000))
     B, niter, thin = int(n_chains), int(niter), int(thin)
     rec = {"par": np.empty((B, niter, ch.npar)), "l": np.empty((B, niter)), "l1": np.empty((B, niter)),

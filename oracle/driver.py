@@ -76,6 +76,17 @@ def eslice_iteration(st, g, opts, normals, uniforms):
         st["par"], st["LatentTraj"], st["betaN"], st["FT"] = r["par"], r["LatentTraj"], r["betaN"], r["FT"]
         st["coalLog"], st["Ode"] = r["CoalLog"], r["OdeTraj"]  # logOrigin is NOT refreshed here (:456-472)
     st["last_par_evals"] = r["n_evals"]
+    # --- ESS_vec2: a second parameter ESS INSTEAD of the trajectory ESS (R/LNA_chpt_slice.R:826-833); it takes the first
+    #     npar-1 normals and the 22 uniforms of the trajectory update's slots
+    if opts.get("update_traj", True) and opts.get("ESS_vec2") is not None:
+        r = orc.ESlice_par_General(st["par"], g.times, st["OriginTraj"], opts["priorList"], g.x_r, g.x_i, g.init,
+                                   g.gridsize, opts["ESS_vec2"], st["coalLog"], g.t_correct,
+                                   normals=normals[npar - 1:2 * (npar - 1)], uniforms=uniforms[25:47])
+        st["n_full"] += r["n_evals"]
+        if not (r["status"] & 1):
+            st["par"], st["LatentTraj"], st["betaN"], st["FT"] = r["par"], r["LatentTraj"], r["betaN"], r["FT"]
+            st["coalLog"], st["Ode"] = r["CoalLog"], r["OdeTraj"]
+        return st
     # --- trajectory ESS
     if opts.get("update_traj", True):
         betaN = orc.betaTs(st["par"][2:npar - 1], st["LatentTraj"][:, 0], g.x_r, g.x_i)

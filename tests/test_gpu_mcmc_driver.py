@@ -223,3 +223,33 @@ def test_reference_mcmc2_chain_is_typical_of_the_gpu_ensemble(constant):
     assert np.mean((allr < 0.002) | (allr > 0.998)) < 0.05, {k: (float(v.min()), float(v.max())) for k, v in ranks.items()}
     for name, r in ranks.items():
         assert 0.08 < float(np.mean(r)) < 0.92, (name, float(np.mean(r)))
+
+
+def test_general_mcmc_with_eslice_second_slice_update(changepoint):
+    """ESS_vec2: for i >= burn1 a second update_Par_ESlice_combine (here: R0 and the hyper-parameter only) replaces the
+    trajectory slice update (R/LNA_chpt_slice.R:826-833)."""
+    from lnaphylodyn_b200 import api, chains as chm, mcmc, _lib
+    g = changepoint
+    coal, prior, proposal, control = vignette_args(g)
+    nch = len(g.x_r) - 1
+    B, niter, burn1, seed = 4, 5, 2, 23
+    ess2 = (0, 1, 0, 0, 1, 0, 0)
+    res = mcmc.General_MCMC_with_ESlice(coal, g.times, g.t_correct, g.x_r[0], gridsize=50, niter=niter, burn=0, thin=1,
+                                        changetime=g.x_r[1:], prior=prior, proposal=proposal, control=control,
+                                        ESS_vec=(0, 1, 0, 0, 1, 1, 0), ESS_vec2=ess2,
+                                        options={"burn1": burn1, "parIdlist": {"c": 4, "d": nch + 5}, "isLoglist": {"c": 1, "d": 0},
+                                                 "priorIdlist": {"c": 3, "d": 5}, "hyper": False}, n_chains=B, seed=seed)
+    par0 = np.concatenate([[g.x_r[0], 1.0], [control["R0"], control["gamma"]], control["ch"], [control["hyper"]]])
+    st = [driver.init_state(g, par0, control["traj"]) for _ in range(B)]
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    nrm, unf = np.empty((B, 123)), np.empty((B, chm.ITER_UNIF))
+    for i in range(1, niter + 1):
+        _lib.check(_lib.lib().lna_draw_streams(pb.h, B, 0, 123, chm.ITER_UNIF, seed, i, api._ptr(nrm), api._ptr(unf)))
+        opts = driver.opts_from_golden(g, update_traj=i >= burn1)
+        if i >= burn1:
+            opts["ESS_vec2"] = list(ess2)
+        for c in range(B):
+            st[c] = driver.eslice_iteration(st[c], g, opts, nrm[c], unf[c])
+            assert relerr(res["par"][c, i - 1], st[c]["par"]) < TOL, (i, c)
+            assert res["l1"][c, i - 1] == pytest.approx(st[c]["coalLog"], rel=TOL)
+    assert np.all(res["l"] == 0.0)  # the latent increments are never updated in this configuration: logOrigin stays 0
