@@ -1,9 +1,11 @@
-"""Minimal reader for R's XDR serialization (version 2), enough for the knitr caches and the
-.RData file shipped with the reference.
+"""Reader for R's XDR serialization (version 2): `.RData` files (gzip, RDX2) and knitr lazy-load caches (`.rdb` / `.rdx`).
 
-Test infrastructure only: used by make_golden.py (run once, in the build container, where
-/root/reference is mounted) to turn the reference's cached MCMC outputs into .npz fixtures.
-Nothing in the product path imports this.
+The reference ships its genealogies as R objects (`data/Ebola_Sierra_Leone2014.RData`: a `phylo` tree) and its users keep
+theirs in `.RData` files; this module reads them without R, so that `read_phylo(path)` -> `genealogy.summarize_phylo` ->
+`mcmc.General_MCMC_with_ESlice` is the whole path from the reference's data file to chains on the GPU (SURVEY.md section 8(f.2),
+Appendix D).  Covers what those files contain: NULL, symbols, pairlists, character / logical / integer / real vectors,
+lists and their names / dim / class attributes; no closures, environments, ALTREP or bytecode.  Host-side NumPy only.
+tests/golden/make_golden.py uses the same reader to turn the reference's knitr caches into the .npz fixtures.
 """
 import gzip
 import struct
@@ -159,3 +161,19 @@ def read_rdata(path):
     r = _Reader(raw[5:])
     r.header()
     return {tag: simplify(val) for tag, val in r.item()}
+
+
+def read_phylo(path, name=None):
+    """The `phylo` tree stored in an .RData file as {edge (n x 2, 1-based), edge_length, Nnode, ntip}: the arguments of
+    genealogy.summarize_phylo.  `name`: the R variable (default: the only / first object of class "phylo")."""
+    objs = read_rdata(path)
+    keys = [name] if name else list(objs)
+    for k in keys:
+        t = objs[k]
+        if isinstance(t, dict) and "edge" in t and "edge.length" in t:
+            edge = np.asarray(t["edge"], dtype=np.int64)
+            nnode = int(np.ravel(t["Nnode"])[0])
+            return {"edge": edge, "edge_length": np.asarray(t["edge.length"], dtype=np.float64), "Nnode": nnode,
+                    "ntip": int(len(t["tip.label"])) if "tip.label" in t else int(edge.max()) - nnode}
+    raise ValueError(f"no phylo object in {path}")
+

@@ -22,8 +22,8 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
-import rxdr  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from lnaphylodyn_b200 import rdata as rxdr  # noqa: E402  (the package's XDR reader)
 
 REF = "/root/reference"
 
