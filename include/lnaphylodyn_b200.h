@@ -338,11 +338,22 @@ int lna_chains_set_joint_transform(lna_chains *ch, int d, const double *T);
 int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *opts, const double *normals, const double *uniforms);
 int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *opts, const double *normals,
                               const double *uniforms);
+/* The same on streams drawn on the device: exactly the numbers lna_draw_streams(pb, B, chain_offset, nch + k*p (+ 4 with
+ * opts->joint), LNA_ITER2_UNIF, seed, iteration, ...) hands to the host. */
+int lna_chains_step_mcmc2_rng(lna_chains *ch, const lna_mcmc2_opts *opts, uint64_t seed, uint64_t iteration,
+                              int64_t chain_offset);
 
 /* Read the state back (any pointer may be NULL).  counters: B x 4 int32 = (n_full_evals,
  * n_cheap_evals, n_mh_accept, status OR). */
 int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
                    double *logOrigin, int32_t *counters);
+/* The drivers' per-iteration records (params[i,] = par, l[i] = logOrigin, l1[i] = coalLog; R/LNA_chpt_slice.R:685-690, 842-845)
+ * kept on the device: begin(niter) allocates, record(i) stores the current state as iteration i (0-based; three
+ * device-to-device copies per stream group, no host round trip), get() returns par as B x niter x npar and l, l1 as B x niter
+ * (host buffers, any may be NULL).  2000 iterations of 4096 chains are 2.9 GB. */
+int lna_chains_history_begin(lna_chains *ch, int64_t niter);
+int lna_chains_history_record(lna_chains *ch, int64_t i);
+int lna_chains_history_get(lna_chains *ch, double *par, double *l, double *l1);
 /* Device pointer to the B x 4 summary block (coalLog, logOrigin, n_full_evals, status) that is
  * all-gathered across GPUs; valid until the next step. */
 const double *lna_chains_summary_dev(lna_chains *ch);

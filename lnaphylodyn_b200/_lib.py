@@ -88,10 +88,14 @@ _SIGS = {
     "lna_chains_step_mcmc2": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), _vp, _vp]),
     "lna_chains_step_mcmc2_dev": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), _vp, _vp]),
     "lna_chains_set_joint_transform": (C.c_int, [_vp, C.c_int, _vp]),
+    "lna_chains_step_mcmc2_rng": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), C.c_uint64, C.c_uint64, C.c_int64]),
     "lna_chains_step_rng": (C.c_int, [_vp, C.POINTER(LnaMcmcOpts), C.c_uint64, C.c_uint64, _I64]),
     "lna_draw_streams": (C.c_int, [_vp, _I64, _I64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp, _vp]),
     "lna_chains_get": (C.c_int, [_vp] + [_vp] * 6),
     "lna_chains_summary_dev": (_vp, [_vp]),
+    "lna_chains_history_begin": (C.c_int, [_vp, C.c_int64]),
+    "lna_chains_history_record": (C.c_int, [_vp, C.c_int64]),
+    "lna_chains_history_get": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lna_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
 }
 

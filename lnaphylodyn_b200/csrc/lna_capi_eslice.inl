@@ -950,6 +950,18 @@ static int part_step_rng(ChainPart *ch, const lna_mcmc_opts *o, uint64_t seed, u
     return part_step_dev(ch, o, ch->stage_n, ch->stage_u);
 }
 
+static int part_step_mcmc2_rng(ChainPart *ch, const lna_mcmc2_opts *o, uint64_t seed, uint64_t iteration,
+                               int64_t chain_offset) {
+    if (!ch || !o) return fail("lna_chains_step_mcmc2_rng: null argument");
+    lna_problem *pb = ch->pb;
+    cudaSetDevice(pb->device);
+    const DevProb &P = pb->dp;
+    const int nn = P.nch + P.k * P.p + (o->joint ? 4 : 0);
+    if ((size_t)nn > ch->n_norm) return fail("lna_chains_step_mcmc2_rng: staging too small");
+    if (draw_streams_dev(pb, ch->B, chain_offset, nn, (int)LNA_ITER2_UNIF, seed, iteration, ch->stage_n, ch->stage_u)) return -1;
+    return part_step_mcmc2_dev(ch, o, ch->stage_n, ch->stage_u);
+}
+
 static int part_get(ChainPart *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
                               double *logOrigin, int32_t *counters) {
     if (!ch) return fail("lna_chains_get: null chains");
@@ -1001,7 +1013,31 @@ struct lna_chains {
     cudaEvent_t ev_in = nullptr;
     std::vector<cudaEvent_t> ev_out;
     size_t n_norm = 0, n_unif = 0, n_norm2 = 0;
+    // per-iteration history kept on the device (params[i,], l[i], l1[i] of the R drivers): one buffer per group,
+    // [niter][npar + 2][Bg] in the groups' own slot-major layout, so recording is three device-to-device copies
+    std::vector<double *> hist;
+    long long hist_niter = 0;
 };
+
+// history slot of one iteration of one group: par (npar x Bg), then logOrigin (Bg), then coalLog (Bg)
+__global__ void k_hist_gather(long long Bg, int npar, long long niter, const double *hist, double *par_out, double *l_out,
+                              double *l1_out, long long Btot, long long c0) {
+    // one thread per (chain, iteration, entry): par_out is Btot x niter x npar (chain-major, like the R arrays per chain)
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_it = (long long)(npar + 2);
+    if (idx >= Bg * niter * per_it) return;
+    const int j = (int)(idx % per_it);
+    const long long i = (idx / per_it) % niter, c = idx / (per_it * niter);
+    const double v = hist[(i * per_it + j) * Bg + c];
+    if (j < npar) {
+        if (par_out) par_out[((c0 + c) * niter + i) * npar + j] = v;
+    } else if (j == npar) {
+        if (l_out) l_out[(c0 + c) * niter + i] = v;
+    } else {
+        if (l1_out) l1_out[(c0 + c) * niter + i] = v;
+    }
+    (void)Btot;
+}
 
 // order the groups' streams after everything already enqueued on the user's stream ...
 static int chains_fork(lna_chains *ch) {
@@ -1075,7 +1111,74 @@ extern "C" void lna_chains_destroy(lna_chains *ch) {
     for (cudaEvent_t e : ch->ev_out) cudaEventDestroy(e);
     if (ch->ev_in) cudaEventDestroy(ch->ev_in);
     if (ch->summary) cudaFree(ch->summary);
+    for (double *h : ch->hist)
+        if (h) cudaFree(h);
     delete ch;
+}
+
+// ---- on-device history of the drivers' per-iteration records -------------------------------------------------------------
+extern "C" int lna_chains_history_begin(lna_chains *ch, int64_t niter) {
+    if (!ch || niter <= 0) return fail("lna_chains_history_begin: bad arguments");
+    cudaSetDevice(ch->pb->device);
+    for (double *h : ch->hist)
+        if (h) cudaFree(h);
+    ch->hist.assign(ch->G, nullptr);
+    ch->hist_niter = 0;
+    const size_t per_it = (size_t)(2 + ch->pb->dp.npt) + 2;
+    for (int g = 0; g < ch->G; ++g)
+        if (cudaMalloc(&ch->hist[g], sizeof(double) * (size_t)niter * per_it * (size_t)ch->part[g]->B) != cudaSuccess) {
+            cudaGetLastError();
+            return fail("lna_chains_history_begin: device allocation failed (%lld iterations x %lld chains)", (long long)niter,
+                        ch->B);
+        }
+    ch->hist_niter = niter;
+    return 0;
+}
+
+extern "C" int lna_chains_history_record(lna_chains *ch, int64_t i) {
+    if (!ch || ch->hist_niter == 0) return fail("lna_chains_history_record: no history (lna_chains_history_begin)");
+    if (i < 0 || i >= ch->hist_niter) return fail("lna_chains_history_record: iteration %lld outside 0..%lld", (long long)i,
+                                                  ch->hist_niter - 1);
+    const size_t npar = (size_t)(2 + ch->pb->dp.npt), per_it = npar + 2;
+    if (chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g) {
+        ChainPart *pt = ch->part[g];
+        const size_t Bg = (size_t)pt->B;
+        double *dst = ch->hist[g] + (size_t)i * per_it * Bg;
+        cudaStream_t st = pt->pb->stream;
+        CK(cudaMemcpyAsync(dst, pt->par, sizeof(double) * npar * Bg, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dst + npar * Bg, pt->logOrigin, sizeof(double) * Bg, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dst + (npar + 1) * Bg, pt->coalLog, sizeof(double) * Bg, cudaMemcpyDeviceToDevice, st));
+    }
+    return chains_join(ch);
+}
+
+extern "C" int lna_chains_history_get(lna_chains *ch, double *par, double *l, double *l1) {
+    if (!ch || ch->hist_niter == 0) return fail("lna_chains_history_get: no history (lna_chains_history_begin)");
+    lna_problem *pb = ch->pb;
+    cudaSetDevice(pb->device);
+    const long long niter = ch->hist_niter;
+    const int npar = 2 + pb->dp.npt;
+    const size_t nB = (size_t)ch->B;
+    double *dpar = nullptr, *dl = nullptr, *dl1 = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (par) e = cudaMalloc(&dpar, sizeof(double) * nB * niter * npar);
+    if (e == cudaSuccess && l) e = cudaMalloc(&dl, sizeof(double) * nB * niter);
+    if (e == cudaSuccess && l1) e = cudaMalloc(&dl1, sizeof(double) * nB * niter);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    for (int g = 0; e == cudaSuccess && g < ch->G; ++g) {
+        const long long Bg = ch->part[g]->B, n = Bg * niter * (npar + 2);
+        k_hist_gather<<<nblk(n, 256), 256, 0, pb->stream>>>(Bg, npar, niter, ch->hist[g], dpar, dl, dl1, ch->B, ch->off[g]);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && par) e = cudaMemcpyAsync(par, dpar, sizeof(double) * nB * niter * npar, cudaMemcpyDeviceToHost, pb->stream);
+    if (e == cudaSuccess && l) e = cudaMemcpyAsync(l, dl, sizeof(double) * nB * niter, cudaMemcpyDeviceToHost, pb->stream);
+    if (e == cudaSuccess && l1) e = cudaMemcpyAsync(l1, dl1, sizeof(double) * nB * niter, cudaMemcpyDeviceToHost, pb->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(pb->stream);
+    if (dpar) cudaFree(dpar);
+    if (dl) cudaFree(dl);
+    if (dl1) cudaFree(dl1);
+    return e == cudaSuccess ? 0 : fail("lna_chains_history_get: %s", cudaGetErrorString(e));
 }
 
 extern "C" int lna_chains_init(lna_chains *ch, const double *par, const double *OriginTraj) {
@@ -1156,6 +1259,15 @@ extern "C" int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *o, co
         if (part_step_mcmc2(ch->part[g], o, normals + ch->off[g] * (ch->n_norm2 + (o->joint ? 4 : 0)),
                             uniforms + ch->off[g] * (size_t)LNA_ITER2_UNIF))
             return -1;
+    return chains_join(ch);
+}
+
+extern "C" int lna_chains_step_mcmc2_rng(lna_chains *ch, const lna_mcmc2_opts *o, uint64_t seed, uint64_t iteration,
+                                         int64_t chain_offset) {
+    if (!ch || !o) return fail("lna_chains_step_mcmc2_rng: null argument");
+    if (chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g)
+        if (part_step_mcmc2_rng(ch->part[g], o, seed, iteration, chain_offset + ch->off[g])) return -1;
     return chains_join(ch);
 }
 

@@ -127,17 +127,26 @@ def _finish(ch, setting, rec, n_chains, squeeze):
 
 
 def _record(ch, rec, i, thin, want_traj):
-    """params[i,] = par; l[i] = logOrigin; l1[i] = coalLog; tjs[,,i/thin] = LatentTraj  (LNA_chpt_slice.R:839-845)"""
+    """params[i,] = par; l[i] = logOrigin; l1[i] = coalLog; tjs[,,i/thin] = LatentTraj  (LNA_chpt_slice.R:839-845).
+    par, l, l1 are recorded ON THE DEVICE (lna_chains_history_record: device-to-device copies, no host round trip per
+    iteration) and fetched once by _fetch_history; only the thinned trajectories cross to the host as they are produced."""
     pb, B = ch.pb, ch.B
     L = _lib.lib()
-    par = np.empty((B, ch.npar))
-    cl, lo = np.empty(B), np.empty(B)
-    lat = np.empty((B, pb.nrow * (pb.p + 1))) if want_traj else None
-    check(L.lna_chains_get(ch.h, api._ptr(par), None, api._ptr(lat) if want_traj else None, api._ptr(cl), api._ptr(lo), None),
-          "lna_chains_get")
-    rec["par"][:, i], rec["l"][:, i], rec["l1"][:, i] = par, lo, cl
+    check(L.lna_chains_history_record(ch.h, int(i)), "lna_chains_history_record")
     if want_traj:
+        lat = np.empty((B, pb.nrow * (pb.p + 1)))
+        check(L.lna_chains_get(ch.h, None, None, api._ptr(lat), None, None, None), "lna_chains_get")
         rec["traj"][:, (i + 1) // thin - 1] = pb._unmats(lat, (pb.nrow, pb.p + 1), False)
+
+
+def _begin_history(ch, niter):
+    check(_lib.lib().lna_chains_history_begin(ch.h, int(niter)), "lna_chains_history_begin")
+
+
+def _fetch_history(ch, rec):
+    """The device-side records into rec["par"] (B, niter, npar), rec["l"], rec["l1"] (B, niter)."""
+    check(_lib.lib().lna_chains_history_get(ch.h, api._ptr(rec["par"]), api._ptr(rec["l"]), api._ptr(rec["l1"])),
+          "lna_chains_history_get")
 
 
 def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn=0, thin=5, changetime=(),
@@ -193,11 +202,13 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
     B, niter, thin = int(n_chains), int(niter), int(thin)
     rec = {"par": np.empty((B, niter, ch.npar)), "l": np.empty((B, niter)), "l1": np.empty((B, niter)),
            "traj": np.empty((B, niter // thin, pb.nrow, pb.p + 1))}
+    _begin_history(ch, niter)
     for i in range(1, niter + 1):  # R's 1-based iteration counter
         ch.step_rng(o_burn if i < burn1 else o_full, seed, i, chain_offset)
         _record(ch, rec, i - 1, thin, i % thin == 0)
         if verbose and i % 100 == 0:
-            print(i, float(np.mean(rec["l1"][:, i - 1])))
+            print(i, float(np.mean(ch.get()["coalLog"])))
+    _fetch_history(ch, rec)
     return _finish(ch, setting, rec, B, squeeze)
 
 
@@ -249,11 +260,12 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
     if fix_pcov:
         pcov = np.broadcast_to(np.asarray(setting["PCOV"], dtype=np.float64) * tune, (B, d, d)).copy()
         ch.set_joint_transform(chm.mvrnorm_transform(pcov))
-    nrm, nrm_j, unf = np.empty((B, n_norm2)), np.empty((B, n_norm2 + 4)), np.empty((B, chm.ITER2_UNIF))
     L = _lib.lib()
+    _begin_history(ch, niter)
     for i in range(1, niter + 1):
         joint = i >= max(warmup2, burn1)
         if not fix_pcov and (i == warmup2 or (i > warmup2 and i % up == 0)):
+            _fetch_history(ch, rec)  # (rows < i - 1 are recorded; the adaptation reads the chain's own past)
             # proposal covariance from the chain's own history, rows floor(i/3) .. i-1 of `params` (:608-630)
             lo = max(i // 3, 1)
             if i - lo < 2:
@@ -267,11 +279,10 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
             sigma_n = (2.38 ** 2) * cov / d
             pcov = (beta * sigma_n + (1 - beta) * np.eye(d) * 0.0001 / d) * tune
             ch.set_joint_transform(chm.mvrnorm_transform(pcov))
-        buf = nrm_j if joint else nrm
-        check(L.lna_draw_streams(pb.h, B, int(chain_offset), buf.shape[1], chm.ITER2_UNIF, int(seed), i, api._ptr(buf),
-                                 api._ptr(unf)), "lna_draw_streams")
-        ch.step_mcmc2(o3 if joint else (o1 if i < burn1 else o2), buf, unf)
+        opts_i = o3 if joint else (o1 if i < burn1 else o2)
+        check(L.lna_chains_step_mcmc2_rng(ch.h, C.byref(opts_i), int(seed), i, int(chain_offset)), "lna_chains_step_mcmc2_rng")
         _record(ch, rec, i - 1, thin, i % thin == 0)
         if verbose and i % 100 == 0:
-            print(i, float(np.mean(rec["l1"][:, i - 1])))
+            print(i, float(np.mean(ch.get()["coalLog"])))
+    _fetch_history(ch, rec)
     return _finish(ch, setting, rec, B, squeeze)

@@ -1,6 +1,8 @@
 """The R-level drivers (lnaphylodyn_b200/mcmc.py): the vignette calls, replayed for a few chains and iterations, must give
 exactly what stepping the oracle's iteration body over the same device-drawn streams gives -- set-up from the raw
 coalescent data, initial state, burn-in switch, thinning and storage included."""
+import os
+
 import numpy as np
 import pytest
 
@@ -253,3 +255,16 @@ def test_general_mcmc_with_eslice_second_slice_update(changepoint):
             assert relerr(res["par"][c, i - 1], st[c]["par"]) < TOL, (i, c)
             assert res["l1"][c, i - 1] == pytest.approx(st[c]["coalLog"], rel=TOL)
     assert np.all(res["l"] == 0.0)  # the latent increments are never updated in this configuration: logOrigin stays 0
+
+
+@pytest.mark.parametrize("which", ["changepoint", "constant", "ebola"])
+def test_vignette_examples_run(which):
+    """examples/vignettes.py: each vignette's driver call, many chains, a short run -- finite summaries."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vignettes_example", os.path.join(root, "examples", "vignettes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    o = mod.run(which, chains=48, niter=30, seed=3)
+    assert np.isfinite(o["coalLog_mean"]) and np.all(np.isfinite(o["R0_t_mean"])) and o["R0_t_mean"].shape == (39,)
+    assert o["gamma"][0] > 0 and o["chain_iterations_per_s"] > 0
