@@ -91,6 +91,9 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     } else if constexpr (kProp == PROP_MH_PAIR) {
         if (W != 4) return fail("the MH pair kernel uses 4 lanes per chain");
         LC(4);
+    } else if constexpr (kProp == PROP_MH_TREE) {
+        if (W != 16) return fail("the Metropolis tree kernel uses 16 lanes per chain");
+        LC(16);
     } else {
         if (W != 1) return fail("Metropolis kernels use one lane per chain");
         LC(1);
@@ -559,7 +562,7 @@ __global__ void k_bump(long long B, const int *n_evals, const int *accept, const
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= B) return;
     counters[(long long)which_evals * B + c] += n_evals[c];
-    if (count_accept) counters[2 * B + c] += (accept[c] & 1) + ((accept[c] >> 1) & 1);
+    if (count_accept) counters[2 * B + c] += __popc(accept[c] & 15);
     // NEG/NAN bits of a proposal that was not adopted say nothing about the chain's state
     const int adopted = win_slot ? (win_slot[c] >= 0) : 1;
     counters[3 * B + c] |= adopted ? status[c] : (status[c] & (ST_CHOL_FAIL | ST_CAP_HIT));
@@ -859,8 +862,45 @@ static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const dou
         a.jnew = ch->jnew;
         if (chains_stage<PROP_MH_JOINT>(ch, a, 1)) return -1;
     }
+    // few chains: all Metropolis entries (Update_Param_each + update_hyper) speculatively in ONE latency period
+    const int tm = o->joint ? 0 : o->n_mh + (o->update_hyper ? 1 : 0);
+    const char *tree_env = getenv("LNA_MH_TREE");  // 0 forces the sequential entries (tests, experiments)
+    const bool tree_off = tree_env && atoi(tree_env) == 0;
+    const bool tree = !tree_off && tm >= 2 && tm <= 4 && ch->planB * 16 <= (long long)pb->sm_count * 128;
+    if (tree) {
+        if (ch->cb.NC < ch->B * 16 &&
+            !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * 16, ch->cb))
+            return fail("lna_chains_step_mcmc2: candidate scratch allocation failed");
+        chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
+        a.tm = tm;
+        for (int e = 0; e < o->n_mh; ++e) {
+            if (o->mh_index[e] < 1 || o->mh_index[e] > 3)
+                return fail("lna_chains_step_mcmc2: mh_index must be 1 (I0), 2 (R0) or 3 (gamma)");
+            a.tkind[e] = 0;
+            a.tidx[e] = o->mh_index[e];
+            a.tlog[e] = o->mh_is_log[e];
+            a.tpk[e] = o->mh_prior_kind[e];
+            a.tpr[e][0] = o->mh_prior[e][0];
+            a.tpr[e][1] = o->mh_prior[e][1];
+            a.tprop[e] = o->mh_prop[e];
+            a.tu[e] = 2 * e;
+        }
+        if (o->update_hyper) {
+            const int e = o->n_mh;
+            a.tkind[e] = 1;
+            a.tidx[e] = -1;
+            a.tlog[e] = 0;
+            a.tpk[e] = 2;
+            a.tpr[e][0] = o->hyper_prior[0];
+            a.tpr[e][1] = o->hyper_prior[1];
+            a.tprop[e] = o->hyper_prop;
+            a.tu[e] = 8;
+        }
+        a.jnew = ch->jnew;
+        if (chains_stage<PROP_MH_TREE>(ch, a, 16)) return -1;
+    }
     // Update_Param_each: one Metropolis entry per listed parameter, sequentially
-    for (int e = 0; !o->joint && e < o->n_mh; ++e) {
+    for (int e = 0; !tree && !o->joint && e < o->n_mh; ++e) {
         if (o->mh_index[e] < 1 || o->mh_index[e] > 3)
             return fail("lna_chains_step_mcmc2: mh_index must be 1 (I0), 2 (R0) or 3 (gamma)");
         chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 2 * e, su, 1}, a);
@@ -872,7 +912,7 @@ static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const dou
         a.mh_prop = o->mh_prop[e];
         if (chains_stage<PROP_MH_SCALAR>(ch, a, 1)) return -1;
     }
-    if (o->update_hyper && !o->joint) {  // update_hyper (general_change_point.R:281-313)
+    if (o->update_hyper && !o->joint && !tree) {  // update_hyper (general_change_point.R:281-313)
         chains_base_args(ch, View{normals, sn, 1}, View{uniforms + 8, su, 1}, a);
         a.mh_pr[0] = o->hyper_prior[0];
         a.mh_pr[1] = o->hyper_prior[1];

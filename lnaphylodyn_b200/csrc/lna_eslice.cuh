@@ -23,7 +23,8 @@ enum : int {
     PROP_PLAIN = 0, PROP_GAMMA_RW = 1, PROP_HYPER_NOOP = 2, PROP_ESS_PAR = 3, PROP_ESS_CHPT = 4, PROP_MH_PAIR = 5,
     PROP_MH_SCALAR = 6,  // one entry of Update_Param_each (R/LNA_chpt_slice.R:266-365)
     PROP_MH_HYPER = 7,   // update_hyper (R/general_change_point.R:281-313)
-    PROP_MH_JOINT = 8    // update_Param_joint, method "admcmc" (R/LNA_chpt_slice.R:9-88): General_MCMC2's stage i >= warmup2
+    PROP_MH_JOINT = 8,   // update_Param_joint, method "admcmc" (R/LNA_chpt_slice.R:9-88): General_MCMC2's stage i >= warmup2
+    PROP_MH_TREE = 9     // up to 4 consecutive Metropolis entries (Update_Param_each + update_hyper) in ONE latency period
 };
 
 constexpr int kMaxUnif = 22;
@@ -85,6 +86,10 @@ struct ChProp {
             // exp(log(ch) * hyper / hyper'), R/LNA_chpt_slice.R:238-241 with hyper' = hyper (ulp-level
             // perturbation, A.17) and update_hyper (general_change_point.R:292-293) with hyper' = hyper e^u
             return exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_new));
+        } else if (kProp == PROP_MH_TREE) {
+            // (the hyper entry of the tree: exactly PROP_MH_HYPER's expression)
+            const double v = exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_new));
+            return x.rot_ch ? v : cj;
         } else if (kProp == PROP_MH_JOINT) {
             // only when the hyper-parameter is among the jointly proposed ones (:65-68): exp(log(ch) * hyper / hyper')
             const double v = exp(__ddiv_rn(__dmul_rn(log(cj), x.hyper_old), x.hyper_new));
@@ -157,6 +162,11 @@ struct CandArgs {
     double jpr[4][2];
     const double *jT;  // [B][16]
     double *jnew;      // [B][4] proposed values on the natural scale (read by the commit kernel)
+    // PROP_MH_TREE: tm consecutive Metropolis entries of General_MCMC2 (R/LNA_chpt_slice.R:266-365 + update_hyper). Entry e:
+    // tkind 0 = scalar random walk on par[tidx] (like PROP_MH_SCALAR), 1 = hyper step (like PROP_MH_HYPER, last entry);
+    // uniforms: walk at column tu[e], accept at tu[e] + 1 of the stream
+    int tm, tkind[4], tidx[4], tlog[4], tpk[4], tu[4];
+    double tpr[4][2], tprop[4];
     FullOut cand;    // candidate scratch: slot-major (sb = 1, sj = NC)
     int *win_slot;   // [B] winning scratch slot, -1 = keep current state
     double *cand_ll; // [B] log-likelihood of the winner (or of the rejected MH proposal)
@@ -267,7 +277,86 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
     auto unif = [&](int q) { return a.uniforms.at(cc, q); };
     EpsFromView eps{a.origin, cc, P.k};
 
-    if (kProp == PROP_MH_PAIR) {
+    if (kProp == PROP_MH_TREE) {
+        // ---- up to four consecutive Metropolis entries in ONE latency period (W = 16 lanes per chain) ----------------
+        // Entry e's proposal touches its own parameter only and is drawn from its own uniform, so what the sequential code
+        // evaluates at entry e is determined by WHICH earlier entries were accepted: lane l = 2^e - 1 + A evaluates entry e
+        // on top of the accepted subset A of entries 0..e-1 (1 + 2 + 4 + 8 = 15 candidates), and the accept tests are then
+        // chained exactly as the sequential code chains them.  Same evaluations, same decisions, 1/tm of the latency.
+        const int m = a.tm;
+        const int e_l = 31 - __clz(w + 1), A_l = (w + 1) - (1 << e_l);  // this lane's (entry, accepted subset)
+        const bool used = w < (1 << m) - 1;
+        PropScalars x;
+        x.S0 = a.par.at(cc, 0);
+        x.I0 = a.par.at(cc, 1);
+        x.R0 = a.par.at(cc, 2);
+        x.gam = a.par.at(cc, 3);
+        x.hyper_old = x.hyper_new = a.par.at(cc, npar - 1);
+        x.ct = 1.0;
+        x.sn = 0.0;
+        x.rot_ch = 0;
+        x.noop = 0;
+        double newv[4], off[4];
+        for (int e = 0; e < m; ++e) {  // every lane computes all proposals (a few scalar operations each)
+            if (a.tkind[e] == 0) {
+                const int j = a.tidx[e];
+                const double cur = a.par.at(cc, j);
+                const double raw = a.tlog[e] ? log(cur) : cur, po = a.tprop[e];
+                const double rnew = raw + (-po + (po - (-po)) * unif(a.tu[e]));
+                off[e] = a.tpk[e] == 0 ? dnorm_log(rnew, a.tpr[e][0], a.tpr[e][1]) - dnorm_log(raw, a.tpr[e][0], a.tpr[e][1])
+                                       : dunif_log(rnew, a.tpr[e][0], a.tpr[e][1]) - dunif_log(raw, a.tpr[e][0], a.tpr[e][1]);
+                newv[e] = a.tlog[e] ? exp(rnew) : rnew;
+            } else {
+                const double hp = a.tprop[e], uu = -hp + (hp - (-hp)) * unif(a.tu[e]);
+                newv[e] = x.hyper_old * exp(uu);
+                off[e] = dgamma_log(newv[e], a.tpr[e][0], a.tpr[e][1]) - dgamma_log(x.hyper_old, a.tpr[e][0], a.tpr[e][1]) + uu;
+            }
+        }
+        for (int e = 0; e < m; ++e) {
+            const bool on_e = used && (e == e_l || (e < e_l && ((A_l >> e) & 1)));
+            if (!on_e) continue;
+            if (a.tkind[e] == 0) {
+                if (a.tidx[e] == 1) x.I0 = newv[e];
+                if (a.tidx[e] == 2) x.R0 = newv[e];
+                if (a.tidx[e] == 3) x.gam = newv[e];
+            } else {
+                x.hyper_new = newv[e];
+                x.rot_ch = 1;
+            }
+        }
+        double ll = kSentinel;
+        int st = 0;
+        {
+            ChProp<PROP_MH_TREE> chs{a.par, a.normals, cc, 4, x};
+            evaluate(chs, eps, x, t, valid && used, ll, st);
+        }
+        // chained accept tests (every lane of the group computes them: the shuffles are warp-wide)
+        const int base = lane & ~15;
+        double cur = valid ? a.coal_log[cc] : 0.0;
+        int A = 0, last = -1, stc = 0;
+        for (int e = 0; e < m; ++e) {
+            const int src = base + (1 << e) - 1 + A;
+            const double ll_e = __shfl_sync(0xffffffffu, ll, src);
+            const int st_e = __shfl_sync(0xffffffffu, st, src);
+            const bool acc = !(st_e & ST_CHOL_FAIL) && (log(unif(a.tu[e] + 1)) < ll_e - cur + off[e]);
+            stc |= acc ? st_e : (st_e & (ST_CHOL_FAIL | ST_CAP_HIT));
+            if (acc) {
+                cur = ll_e;
+                last = (1 << e) - 1 + A;
+                A |= 1 << e;
+            }
+        }
+        if (valid && w == 0 && writer) {
+            a.win_slot[c] = last >= 0 ? (int)t + last : -1;
+            a.cand_ll[c] = cur;
+            a.theta[c] = 0.0;
+            a.n_evals[c] = m;
+            a.status[c] = stc;
+            a.accept[c] = A;
+            for (int e = 0; e < m; ++e) a.jnew[c * 4 + e] = newv[e];
+        }
+        return;
+    } else if (kProp == PROP_MH_PAIR) {
         // ---- both entries of Update_Param_each_Norm in ONE latency period (W = 4 lanes per chain) -----
         //   lane 0: gamma' proposal, current ch            (entry c)
         //   lane 1: gamma' accepted, ch <- exp(log ch*h/h) (entry d after an accepted c)
@@ -777,6 +866,24 @@ __global__ void k_commit_par_wide(DevProb P, long long B, CandArgs a, OutView pa
             x.hyper_new = a.theta[c];
             ChProp<PROP_MH_HYPER> chs{a.par, a.normals, c, 4, x};
             v = chs.ch(j - 4);
+        }
+    } else if (kProp == PROP_MH_TREE) {
+        const int acc = a.accept[c];
+        for (int e = 0; e < a.tm; ++e) {
+            if (!((acc >> e) & 1)) continue;
+            if (a.tkind[e] == 0) {
+                if (j == a.tidx[e]) v = a.jnew[c * 4 + e];
+            } else {
+                if (j == npar - 1) v = a.jnew[c * 4 + e];
+                if (is_ch) {
+                    PropScalars x{};
+                    x.hyper_old = a.par.at(c, npar - 1);
+                    x.hyper_new = a.jnew[c * 4 + e];
+                    x.rot_ch = 1;
+                    ChProp<PROP_MH_TREE> chs{a.par, a.normals, c, 4, x};
+                    v = chs.ch(j - 4);
+                }
+            }
         }
     } else if (kProp == PROP_MH_JOINT) {
         bool has_hyper = false;

@@ -453,3 +453,31 @@ def test_chains_general_entry_list_with_hyper_proposal(api, changepoint):
             assert s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL), (it, c)
             assert s["n_full_evals"][c] == ref[c]["n_full"] and s["n_mh_accept"][c] == ref[c]["n_mh_accept"], (it, c)
     assert len(np.unique(s["par"][:, 43])) > 1 and len(np.unique(s["par"][:, 1])) > 1  # hyper and I0 moved
+
+
+@pytest.mark.parametrize("B", [3, 40, 700])
+def test_metropolis_tree_is_bit_identical(api, constant, monkeypatch, B):
+    """General_MCMC2's four consecutive Metropolis entries (I0, R0, gamma, hyper) evaluated speculatively in one latency
+    period -- candidate (entry e, accepted subset A) on lane 2^e - 1 + A, accept tests chained afterwards -- must give the
+    chains the sequential entries give, bit for bit, counters included."""
+    from lnaphylodyn_b200 import chains as chm
+    g = constant
+    iters, seed = 6, 77
+    par0 = np.concatenate([[g.x_r[0], float(g.setting("control.alpha")[0]) * g.x_r[0]], g.setting("control.R0"),
+                           g.setting("control.gamma"), g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    proposal = [g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LNA_MH_TREE", mode)
+        ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+        for it in range(iters):
+            rng = np.random.default_rng([seed, it])
+            nrm, unf = rng.standard_normal((B, 39 + 80)), rng.random((B, chm.ITER2_UNIF))
+            ch.step_mcmc2(chm.make_mcmc2_opts(prior, proposal, update_hyper=it >= 1, update_traj=it >= 1), nrm, unf)
+        runs[mode] = ch.get()
+    for key in ("par", "OriginTraj", "LatentTraj", "coalLog", "logOrigin", "n_full_evals", "n_cheap_evals", "n_mh_accept"):
+        assert np.array_equal(runs["0"][key], runs["1"][key]), key
+    acc = runs["1"]["n_mh_accept"]
+    assert 0 < acc.sum() < B * iters * 4
