@@ -92,8 +92,12 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
         if (W != 4) return fail("the MH pair kernel uses 4 lanes per chain");
         LC(4);
     } else if constexpr (kProp == PROP_MH_TREE) {
-        if (W != 16) return fail("the Metropolis tree kernel uses 16 lanes per chain");
-        LC(16);
+        switch (W) {  // 2^tm lanes per chain
+            case 4: LC(4); break;
+            case 8: LC(8); break;
+            case 16: LC(16); break;
+            default: return fail("the Metropolis tree kernel uses 4, 8 or 16 lanes per chain");
+        }
     } else {
         if (W != 1) return fail("Metropolis kernels use one lane per chain");
         LC(1);
@@ -765,7 +769,32 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
     const int ess_u = general ? 8 : 3;  // first uniform of the parameter slice update
     const int npar = 2 + P.npt;
     CandArgs a;
-    if (general) {
+    const char *tree_env = getenv("LNA_MH_TREE");  // 0 forces the sequential entries (tests, experiments)
+    const int tW = 1 << std::max(o->n_mh, 2);
+    const bool tree = general && !(tree_env && atoi(tree_env) == 0) && o->n_mh >= 2 && o->n_mh <= 4 &&
+                      ch->planB * tW <= (long long)pb->sm_count * 128;
+    if (tree) {
+        // few chains: the whole entry list speculatively in ONE latency period (PROP_MH_TREE, lna_eslice.cuh)
+        if (ch->cb.NC < ch->B * tW && !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * tW, ch->cb))
+            return fail("lna_chains_step: candidate scratch allocation failed");
+        chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
+        a.tm = o->n_mh;
+        for (int e = 0; e < o->n_mh; ++e) {
+            if (o->mh_kind[e] == 0 && (o->mh_index[e] < 0 || o->mh_index[e] > 3))
+                return fail("lna_chains_step: mh_index must be 0 (S0), 1 (I0), 2 (R0) or 3 (gamma)");
+            if (o->mh_kind[e] < 0 || o->mh_kind[e] > 2) return fail("lna_chains_step: mh_kind must be 0, 1 or 2");
+            a.tkind[e] = o->mh_kind[e] == 0 ? 0 : (o->mh_kind[e] == 1 ? 2 : 3);
+            a.tidx[e] = o->mh_index[e];
+            a.tlog[e] = o->mh_is_log[e];
+            a.tpk[e] = 0;
+            a.tpr[e][0] = o->mh_prior[e][0];
+            a.tpr[e][1] = o->mh_prior[e][1];
+            a.tprop[e] = o->mh_prop[e];
+            a.tu[e] = 2 * e;
+        }
+        a.jnew = ch->jnew;
+        if (chains_stage<PROP_MH_TREE>(ch, a, tW)) return -1;
+    } else if (general) {
         // Update_Param_each_Norm with an arbitrary entry list: one Update_Param per entry, in order
         if (o->n_mh > 4) return fail("lna_chains_step: n_mh must be 0..4");
         for (int e = 0; e < o->n_mh; ++e) {
@@ -866,10 +895,11 @@ static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const dou
     const int tm = o->joint ? 0 : o->n_mh + (o->update_hyper ? 1 : 0);
     const char *tree_env = getenv("LNA_MH_TREE");  // 0 forces the sequential entries (tests, experiments)
     const bool tree_off = tree_env && atoi(tree_env) == 0;
-    const bool tree = !tree_off && tm >= 2 && tm <= 4 && ch->planB * 16 <= (long long)pb->sm_count * 128;
+    const int tW = 1 << std::max(tm, 2);
+    const bool tree = !tree_off && tm >= 2 && tm <= 4 && ch->planB * tW <= (long long)pb->sm_count * 128;
     if (tree) {
-        if (ch->cb.NC < ch->B * 16 &&
-            !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * 16, ch->cb))
+        if (ch->cb.NC < ch->B * tW &&
+            !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * tW, ch->cb))
             return fail("lna_chains_step_mcmc2: candidate scratch allocation failed");
         chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
         a.tm = tm;
@@ -897,7 +927,7 @@ static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const dou
             a.tu[e] = 8;
         }
         a.jnew = ch->jnew;
-        if (chains_stage<PROP_MH_TREE>(ch, a, 16)) return -1;
+        if (chains_stage<PROP_MH_TREE>(ch, a, tW)) return -1;
     }
     // Update_Param_each: one Metropolis entry per listed parameter, sequentially
     for (int e = 0; !tree && !o->joint && e < o->n_mh; ++e) {

@@ -163,7 +163,8 @@ struct CandArgs {
     const double *jT;  // [B][16]
     double *jnew;      // [B][4] proposed values on the natural scale (read by the commit kernel)
     // PROP_MH_TREE: tm consecutive Metropolis entries of General_MCMC2 (R/LNA_chpt_slice.R:266-365 + update_hyper). Entry e:
-    // tkind 0 = scalar random walk on par[tidx] (like PROP_MH_SCALAR), 1 = hyper step (like PROP_MH_HYPER, last entry);
+    // tkind 0 = scalar random walk on par[tidx] (like PROP_MH_SCALAR), 1 = hyper step (like PROP_MH_HYPER, last entry),
+    // 2 = the no-op hyper entry (like PROP_HYPER_NOOP), 3 = hyper log-normal walk (PROP_MH_HYPER with prior kind 2);
     // uniforms: walk at column tu[e], accept at tu[e] + 1 of the stream
     int tm, tkind[4], tidx[4], tlog[4], tpk[4], tu[4];
     double tpr[4][2], tprop[4];
@@ -278,7 +279,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
     EpsFromView eps{a.origin, cc, P.k};
 
     if (kProp == PROP_MH_TREE) {
-        // ---- up to four consecutive Metropolis entries in ONE latency period (W = 16 lanes per chain) ----------------
+        // ---- up to four consecutive Metropolis entries in ONE latency period (W = 2^tm lanes per chain) --------------
         // Entry e's proposal touches its own parameter only and is drawn from its own uniform, so what the sequential code
         // evaluates at entry e is determined by WHICH earlier entries were accepted: lane l = 2^e - 1 + A evaluates entry e
         // on top of the accepted subset A of entries 0..e-1 (1 + 2 + 4 + 8 = 15 candidates), and the accept tests are then
@@ -306,16 +307,25 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
                 off[e] = a.tpk[e] == 0 ? dnorm_log(rnew, a.tpr[e][0], a.tpr[e][1]) - dnorm_log(raw, a.tpr[e][0], a.tpr[e][1])
                                        : dunif_log(rnew, a.tpr[e][0], a.tpr[e][1]) - dunif_log(raw, a.tpr[e][0], a.tpr[e][1]);
                 newv[e] = a.tlog[e] ? exp(rnew) : rnew;
+            } else if (a.tkind[e] == 2) {
+                newv[e] = x.hyper_old;  // no proposal, offset 0: only ch <- exp(log(ch) * hyper / hyper)
+                off[e] = 0.0;
             } else {
                 const double hp = a.tprop[e], uu = -hp + (hp - (-hp)) * unif(a.tu[e]);
                 newv[e] = x.hyper_old * exp(uu);
-                off[e] = dgamma_log(newv[e], a.tpr[e][0], a.tpr[e][1]) - dgamma_log(x.hyper_old, a.tpr[e][0], a.tpr[e][1]) + uu;
+                if (a.tkind[e] == 3) {
+                    const double ln = log(newv[e]), lo = log(x.hyper_old);
+                    off[e] = (dnorm_log(ln, a.tpr[e][0], a.tpr[e][1]) - ln) - uu - (dnorm_log(lo, a.tpr[e][0], a.tpr[e][1]) - lo);
+                } else {
+                    off[e] = dgamma_log(newv[e], a.tpr[e][0], a.tpr[e][1]) - dgamma_log(x.hyper_old, a.tpr[e][0], a.tpr[e][1]) + uu;
+                }
             }
         }
         for (int e = 0; e < m; ++e) {
             const bool on_e = used && (e == e_l || (e < e_l && ((A_l >> e) & 1)));
             if (!on_e) continue;
             if (a.tkind[e] == 0) {
+                if (a.tidx[e] == 0) x.S0 = newv[e];
                 if (a.tidx[e] == 1) x.I0 = newv[e];
                 if (a.tidx[e] == 2) x.R0 = newv[e];
                 if (a.tidx[e] == 3) x.gam = newv[e];
@@ -331,7 +341,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
             evaluate(chs, eps, x, t, valid && used, ll, st);
         }
         // chained accept tests (every lane of the group computes them: the shuffles are warp-wide)
-        const int base = lane & ~15;
+        const int base = lane & ~(W - 1);
         double cur = valid ? a.coal_log[cc] : 0.0;
         int A = 0, last = -1, stc = 0;
         for (int e = 0; e < m; ++e) {

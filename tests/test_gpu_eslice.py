@@ -481,3 +481,31 @@ def test_metropolis_tree_is_bit_identical(api, constant, monkeypatch, B):
         assert np.array_equal(runs["0"][key], runs["1"][key]), key
     acc = runs["1"]["n_mh_accept"]
     assert 0 < acc.sum() < B * iters * 4
+
+
+@pytest.mark.parametrize("hyper", [False, True])
+def test_metropolis_tree_general_entries_bit_identical(api, changepoint, monkeypatch, hyper):
+    """The same for General_MCMC_with_ESlice's general Update_Param_each_Norm entry list (S0 and R0 walks + the hyper entry,
+    no-op or log-normal walk): tree of 7 candidates on 8 lanes against the sequential entries."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    B, iters, seed, nch = 37, 5, 5, 39
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    prior[0] = np.array([13.8, 0.5, 1.0, 1.0])  # a pop_pr under which a walk on log S0 is accepted now and then
+    proposal = [g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+    entries = ((1, 1, 1), (3, 1, 2), (nch + 5, 0, 5))
+    opts = chm.make_opts_general(prior, proposal, [0, 1, 0, 0, 1, 1, 0], entries, hyper=hyper, update_traj=True)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LNA_MH_TREE", mode)
+        ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+        for it in range(iters):
+            rng = np.random.default_rng([seed, it])
+            ch.step(opts, rng.standard_normal((B, ch.n_norm)), rng.random((B, chm.ITER_UNIF_GENERAL)))
+        runs[mode] = ch.get()
+    for key in ("par", "OriginTraj", "LatentTraj", "coalLog", "logOrigin", "n_full_evals", "n_cheap_evals", "n_mh_accept"):
+        assert np.array_equal(runs["0"][key], runs["1"][key]), key
+    assert len(np.unique(runs["1"]["par"][:, 0])) > 1  # S0 moved in some chains
