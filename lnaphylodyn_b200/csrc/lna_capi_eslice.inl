@@ -120,6 +120,15 @@ static int slice_plan(const lna_problem *pb, long long B, int W, SlicePhase *ph)
         ph[0] = {W, 0, 0};
         return 1;
     }
+    if (const char *e = getenv("LNA_SLICE_PLAN")) {  // experiments (tools/plan_sweep.py): "W:first:waves,W:first:waves,..."
+        int n = 0, w, f, v, used = 0;
+        while (n < 24 && sscanf(e, "%d:%d:%d%n", &w, &f, &v, &used) == 3) {
+            ph[n++] = {w, f, v};
+            e += used;
+            if (*e == ',') ++e;
+        }
+        if (n > 0) return n;
+    }
     const int Wa = W < 0 ? -W : auto_width(pb, B);  // W < 0 forces the plan of machine-filling width -W (tests)
     switch (Wa) {
         case 32: ph[0] = {32, 0, 0}; return 1;                      // all 21 candidates in one wave
