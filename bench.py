@@ -543,6 +543,35 @@ def main():
         except Exception as e:  # noqa: BLE001
             eslice = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- configs[0]: the constant_sim vignette's General_MCMC2 iteration body on resident chains (device-drawn streams) ----
+    mcmc2 = None
+    if not args.no_eslice:
+        try:
+            from conftest import Golden
+            from lnaphylodyn_b200.chains import Chains, make_mcmc2_opts
+            gc = Golden("constant_sim")
+            pbc = api.Problem(gc.times, gc.x_r, gc.x_i, gc.gridsize, gc.t_correct, gc.init, device=local_rank)
+            par0 = np.concatenate([[gc.x_r[0], float(gc.setting("control.alpha")[0]) * gc.x_r[0]], gc.setting("control.R0"),
+                                   gc.setting("control.gamma"), gc.setting("control.ch"), gc.setting("control.hyper")])
+            pr = [gc.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+            po = [gc.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+            o2 = make_mcmc2_opts(pr, po)
+            mcmc2 = {"unit": "chain-iterations/s", "workload": "constant_sim vignette (E = 1057), General_MCMC2 body: 3 Metropolis "
+                     "entries + hyper step + change-point slice update + trajectory slice update", "by_chains": {}}
+            for Bc in (1, 1024, 4096):
+                chc = Chains(pbc, np.tile(par0, (Bc, 1)), gc.setting("control.traj"))
+                for it in range(6):
+                    _lib.check(L.lna_chains_step_mcmc2_rng(chc.h, C.byref(o2), 7, it, rank * Bc), "mcmc2")
+                pbc.sync()
+                t0 = time.perf_counter()
+                for it in range(6, 6 + args.eslice_iters):
+                    _lib.check(L.lna_chains_step_mcmc2_rng(chc.h, C.byref(o2), 7, it, rank * Bc), "mcmc2")
+                pbc.sync()
+                dt = (time.perf_counter() - t0) / args.eslice_iters
+                mcmc2["by_chains"][str(Bc)] = {"ms_per_iter": 1e3 * dt, "value": world * Bc / dt}
+        except Exception as e:  # noqa: BLE001
+            mcmc2 = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- configs[3]: SEIR (p = 3) parameter sweep, 16384 i.i.d. draws per sweep, FULL evaluations only ----
     seir = None
     if not args.no_seir:
@@ -611,6 +640,8 @@ def main():
             line["two_batches_in_flight"] = pipelined
         if eslice is not None:
             line["eslice"] = eslice
+        if mcmc2 is not None:
+            line["mcmc2"] = mcmc2
         if seir is not None:
             line["seir_sweep"] = seir
         if not args.no_cpu_baseline:
