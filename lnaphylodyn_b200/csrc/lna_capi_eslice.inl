@@ -779,30 +779,36 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
     const int npar = 2 + P.npt;
     CandArgs a;
     const char *tree_env = getenv("LNA_MH_TREE");  // 0 forces the sequential entries (tests, experiments)
-    const int tW = 1 << std::max(o->n_mh, 2);
-    const bool tree = general && !(tree_env && atoi(tree_env) == 0) && o->n_mh >= 2 && o->n_mh <= 4 &&
-                      ch->planB * tW <= (long long)pb->sm_count * 128;
+    int m_max = 0;  // entries per speculative tree: 2^m lanes per chain must leave the launch latency-bound
+    while (m_max < 4 && ch->planB * (2LL << m_max) <= (long long)pb->sm_count * 128) ++m_max;
+    const bool tree = general && !(tree_env && atoi(tree_env) == 0) && o->n_mh >= 2 && o->n_mh <= 4 && m_max >= 2;
     if (tree) {
-        // few chains: the whole entry list speculatively in ONE latency period (PROP_MH_TREE, lna_eslice.cuh)
-        if (ch->cb.NC < ch->B * tW && !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * tW, ch->cb))
-            return fail("lna_chains_step: candidate scratch allocation failed");
-        chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
-        a.tm = o->n_mh;
+        // few chains: the entry list speculatively, m_max entries per latency period (PROP_MH_TREE, lna_eslice.cuh)
         for (int e = 0; e < o->n_mh; ++e) {
             if (o->mh_kind[e] == 0 && (o->mh_index[e] < 0 || o->mh_index[e] > 3))
                 return fail("lna_chains_step: mh_index must be 0 (S0), 1 (I0), 2 (R0) or 3 (gamma)");
             if (o->mh_kind[e] < 0 || o->mh_kind[e] > 2) return fail("lna_chains_step: mh_kind must be 0, 1 or 2");
-            a.tkind[e] = o->mh_kind[e] == 0 ? 0 : (o->mh_kind[e] == 1 ? 2 : 3);
-            a.tidx[e] = o->mh_index[e];
-            a.tlog[e] = o->mh_is_log[e];
-            a.tpk[e] = 0;
-            a.tpr[e][0] = o->mh_prior[e][0];
-            a.tpr[e][1] = o->mh_prior[e][1];
-            a.tprop[e] = o->mh_prop[e];
-            a.tu[e] = 2 * e;
         }
-        a.jnew = ch->jnew;
-        if (chains_stage<PROP_MH_TREE>(ch, a, tW)) return -1;
+        for (int e0 = 0; e0 < o->n_mh; e0 += m_max) {
+            const int m = std::min(m_max, o->n_mh - e0), tW = 1 << std::max(m, 2);
+            if (ch->cb.NC < ch->B * tW && !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * tW, ch->cb))
+                return fail("lna_chains_step: candidate scratch allocation failed");
+            chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
+            a.tm = m;
+            for (int e = 0; e < m; ++e) {
+                const int g = e0 + e;
+                a.tkind[e] = o->mh_kind[g] == 0 ? 0 : (o->mh_kind[g] == 1 ? 2 : 3);
+                a.tidx[e] = o->mh_index[g];
+                a.tlog[e] = o->mh_is_log[g];
+                a.tpk[e] = 0;
+                a.tpr[e][0] = o->mh_prior[g][0];
+                a.tpr[e][1] = o->mh_prior[g][1];
+                a.tprop[e] = o->mh_prop[g];
+                a.tu[e] = 2 * g;
+            }
+            a.jnew = ch->jnew;
+            if (chains_stage<PROP_MH_TREE>(ch, a, tW)) return -1;
+        }
     } else if (general) {
         // Update_Param_each_Norm with an arbitrary entry list: one Update_Param per entry, in order
         if (o->n_mh > 4) return fail("lna_chains_step: n_mh must be 0..4");
@@ -900,43 +906,47 @@ static int part_step_mcmc2_dev(ChainPart *ch, const lna_mcmc2_opts *o, const dou
         a.jnew = ch->jnew;
         if (chains_stage<PROP_MH_JOINT>(ch, a, 1)) return -1;
     }
-    // few chains: all Metropolis entries (Update_Param_each + update_hyper) speculatively in ONE latency period
+    // The Metropolis entries (Update_Param_each + update_hyper) speculatively, as trees of m entries per latency period:
+    // m = the largest tree whose 2^m lanes per chain still leave the launch latency-bound (4 up to 1184 chains, 3 up to
+    // 2368, 2 up to 4736); with more chains the machine is full and the entries run one by one.
     const int tm = o->joint ? 0 : o->n_mh + (o->update_hyper ? 1 : 0);
     const char *tree_env = getenv("LNA_MH_TREE");  // 0 forces the sequential entries (tests, experiments)
     const bool tree_off = tree_env && atoi(tree_env) == 0;
-    const int tW = 1 << std::max(tm, 2);
-    const bool tree = !tree_off && tm >= 2 && tm <= 4 && ch->planB * tW <= (long long)pb->sm_count * 128;
+    int m_max = 0;
+    while (m_max < 4 && ch->planB * (2LL << m_max) <= (long long)pb->sm_count * 128) ++m_max;
+    const bool tree = !tree_off && tm >= 2 && m_max >= 2;
     if (tree) {
-        if (ch->cb.NC < ch->B * tW &&
-            !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * tW, ch->cb))
-            return fail("lna_chains_step_mcmc2: candidate scratch allocation failed");
-        chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
-        a.tm = tm;
+        struct Ent {
+            int kind, idx, lg, pk, tu;
+            double pr0, pr1, prop;
+        } ent[4];
         for (int e = 0; e < o->n_mh; ++e) {
             if (o->mh_index[e] < 1 || o->mh_index[e] > 3)
                 return fail("lna_chains_step_mcmc2: mh_index must be 1 (I0), 2 (R0) or 3 (gamma)");
-            a.tkind[e] = 0;
-            a.tidx[e] = o->mh_index[e];
-            a.tlog[e] = o->mh_is_log[e];
-            a.tpk[e] = o->mh_prior_kind[e];
-            a.tpr[e][0] = o->mh_prior[e][0];
-            a.tpr[e][1] = o->mh_prior[e][1];
-            a.tprop[e] = o->mh_prop[e];
-            a.tu[e] = 2 * e;
+            ent[e] = {0, o->mh_index[e], o->mh_is_log[e], o->mh_prior_kind[e], 2 * e, o->mh_prior[e][0], o->mh_prior[e][1],
+                      o->mh_prop[e]};
         }
-        if (o->update_hyper) {
-            const int e = o->n_mh;
-            a.tkind[e] = 1;
-            a.tidx[e] = -1;
-            a.tlog[e] = 0;
-            a.tpk[e] = 2;
-            a.tpr[e][0] = o->hyper_prior[0];
-            a.tpr[e][1] = o->hyper_prior[1];
-            a.tprop[e] = o->hyper_prop;
-            a.tu[e] = 8;
+        if (o->update_hyper) ent[o->n_mh] = {1, -1, 0, 2, 8, o->hyper_prior[0], o->hyper_prior[1], o->hyper_prop};
+        for (int e0 = 0; e0 < tm; e0 += m_max) {
+            const int m = std::min(m_max, tm - e0), tW = 1 << std::max(m, 2);
+            if (ch->cb.NC < ch->B * tW && !cand_alloc(pb, ch->cand_scratch, 0, ch->B, ch->B * tW, ch->cb))
+                return fail("lna_chains_step_mcmc2: candidate scratch allocation failed");
+            chains_base_args(ch, View{normals, sn, 1}, View{uniforms, su, 1}, a);
+            a.tm = m;
+            for (int e = 0; e < m; ++e) {
+                const Ent &t = ent[e0 + e];
+                a.tkind[e] = t.kind;
+                a.tidx[e] = t.idx;
+                a.tlog[e] = t.lg;
+                a.tpk[e] = t.pk;
+                a.tpr[e][0] = t.pr0;
+                a.tpr[e][1] = t.pr1;
+                a.tprop[e] = t.prop;
+                a.tu[e] = t.tu;
+            }
+            a.jnew = ch->jnew;
+            if (chains_stage<PROP_MH_TREE>(ch, a, tW)) return -1;
         }
-        a.jnew = ch->jnew;
-        if (chains_stage<PROP_MH_TREE>(ch, a, tW)) return -1;
     }
     // Update_Param_each: one Metropolis entry per listed parameter, sequentially
     for (int e = 0; !tree && !o->joint && e < o->n_mh; ++e) {

@@ -455,14 +455,15 @@ def test_chains_general_entry_list_with_hyper_proposal(api, changepoint):
     assert len(np.unique(s["par"][:, 43])) > 1 and len(np.unique(s["par"][:, 1])) > 1  # hyper and I0 moved
 
 
-@pytest.mark.parametrize("B", [3, 40, 700])
+@pytest.mark.parametrize("B", [3, 40, 700, 1500, 3000])
 def test_metropolis_tree_is_bit_identical(api, constant, monkeypatch, B):
     """General_MCMC2's four consecutive Metropolis entries (I0, R0, gamma, hyper) evaluated speculatively in one latency
     period -- candidate (entry e, accepted subset A) on lane 2^e - 1 + A, accept tests chained afterwards -- must give the
-    chains the sequential entries give, bit for bit, counters included."""
+    chains the sequential entries give, bit for bit, counters included.  (Up to 1184 chains one tree of four entries; 1500
+    chains: trees of 3 + 1; 3000 chains, run as two stream groups: two trees of 2.)"""
     from lnaphylodyn_b200 import chains as chm
     g = constant
-    iters, seed = 6, 77
+    iters, seed = 6 if B < 1000 else 3, 77
     par0 = np.concatenate([[g.x_r[0], float(g.setting("control.alpha")[0]) * g.x_r[0]], g.setting("control.R0"),
                            g.setting("control.gamma"), g.setting("control.ch"), g.setting("control.hyper")])
     pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
