@@ -88,3 +88,27 @@ def test_reference_side_binding_covers_the_export_list():
     if ref.available():
         theirs = syms(os.path.join(ROOT, "oracle", "_ref", "liblna_ref.so"))
         assert theirs - mine <= {"ref_inv2", "ref_chols"}, theirs - mine  # basic_util.cpp stays the reference's own file
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/lnaphylodyn_b200.h must compile as C99 (no C++ in the signatures) and a
+    plain C program must link against the library and call into it."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "lnaphylodyn_b200.h"\n'
+                   "int main(void) { lna_cfg c; lna_mcmc_opts o; lna_mcmc2_opts o2; long long b, e;\n"
+                   "  (void)c; (void)o; (void)o2;\n"
+                   "  if (lna_shard(10, 1, 3, (int64_t *)&b, (int64_t *)&e)) return 2;\n"
+                   '  printf("%d %lld %lld\\n", lna_abi_version(), b, e); return 0; }\n')
+    libdir = os.path.join(ROOT, "lnaphylodyn_b200")
+    from lnaphylodyn_b200 import _lib
+    _lib.lib()  # built
+    exe = tmp_path / "t"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L", libdir, "-llnaphylodyn_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["1", "4", "7"], (out.stdout, out.stderr)
