@@ -398,3 +398,45 @@ def test_mcmc2_iterations_step_for_step(constant):
         assert sa["coalLog"] == pytest.approx(sb["coalLog"], rel=1e-11)
         close(sa["LatentTraj"], sb["LatentTraj"], 1e-10)
         assert sa["n_mh_accept"] == sb["n_mh_accept"]
+
+
+def test_general_entry_list_and_joint_stage_iterations(changepoint, constant):
+    """The restated R iteration bodies added for the Ebola vignette's entry list (Update_Param_each_Norm with arbitrary
+    entries, hyper = T) and for General_MCMC2's third stage (update_Param_joint, admcmc), composed from the reference's
+    functions and from the oracle's: the two chains stay together."""
+    rdriver = ref.driver()
+    # --- General_MCMC_with_ESlice with entries (S0 log walk, R0 log walk, hyper log-normal walk)
+    g = changepoint
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    sa, sb = rdriver.init_state(g, par0, g.setting("control.traj")), odriver.init_state(g, par0, g.setting("control.traj"))
+    opts = dict(odriver.opts_from_golden(g), hyper=True,
+                entries=[(0, 1, (13.8, 0.5), 0.2), (2, 1, (0.7, 0.5), 0.05), (-1, 0, (3.0, 0.2), 0.25)])
+    rng = np.random.default_rng(41)
+    for it in range(6):
+        nrm, unf = rng.standard_normal(43 + 80), rng.uniform(size=52)
+        sa = rdriver.eslice_iteration_general(sa, g, opts, nrm, unf)
+        sb = odriver.eslice_iteration_general(sb, g, opts, nrm, unf)
+        close(sa["par"], sb["par"], 1e-11)
+        assert sa["coalLog"] == pytest.approx(sb["coalLog"], rel=1e-11)
+        assert sa["n_mh_accept"] == sb["n_mh_accept"]
+    assert sb["par"][43] != par0[43] and sb["n_mh_accept"] > 0
+    # --- General_MCMC2, stage i >= warmup2
+    g = constant
+    par0, eps0 = state(g)
+    sa, sb = rdriver.init_state(g, par0, eps0), odriver.init_state(g, par0, eps0)
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    jopts = dict(odriver.mcmc2_opts_from_golden(g),
+                 joint=[(1, 1, 0, tuple(prior[0][:2])), (2, 0, 1, tuple(prior[1][:2])), (3, 1, 0, tuple(prior[2][:2])),
+                        (4, 0, 2, tuple(prior[4][:2]))])
+    A = rng.standard_normal((4, 4)) * np.array([0.02, 0.004, 0.01, 0.3])[:, None]
+    ev, vec = np.linalg.eigh(A @ A.T)
+    T = vec * np.sqrt(np.maximum(ev, 0.0))[None, :]
+    for it in range(6):
+        nrm, unf = rng.standard_normal(39 + 80 + 4), rng.uniform(size=54)
+        sa = rdriver.mcmc2_joint_iteration(sa, g, jopts, T, nrm, unf)
+        sb = odriver.mcmc2_joint_iteration(sb, g, jopts, T, nrm, unf)
+        close(sa["par"], sb["par"], 1e-11)
+        assert sa["coalLog"] == pytest.approx(sb["coalLog"], rel=1e-11)
+        assert sa["n_mh_accept"] == sb["n_mh_accept"]
+    assert sb["n_mh_accept"] > 0
