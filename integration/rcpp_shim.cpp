@@ -145,6 +145,10 @@ int transx_id(const std::string &transX) {
     if (transX == "log") return LNA_TRANSX_LOG;  // (accepted for model SIR; the library says so otherwise)
     Rcpp::stop("GPU path: transX must be \"standard\" or \"log\"");
 }
+// transformPtr (:96-102) knows "changepoint" only; anything else is a NULL external pointer, i.e. an R error at first use
+void check_transP(const std::string &transP) {
+    if (transP != "changepoint") Rcpp::stop("external pointer is not valid");
+}
 lna_problem *problem_xi(const arma::vec &t, const arma::vec &x_r, const arma::ivec &x_i, int gridsize, double t_correct,
                         const InitView &ini, const std::string &model, const std::string &transX) {
     const int xi[4] = {(int)x_i[0], (int)x_i[1], (int)x_i[2], (int)x_i[3]};
@@ -219,6 +223,7 @@ arma::vec param_transform(double t, arma::vec param, arma::vec x_r, arma::ivec x
 // ---- a3: ODE_rk45 :455-491, ODE_rk45_stop :495-530 ----------------------------------------------------------------------
 arma::mat ODE_rk45(arma::vec initial, arma::vec t, arma::vec param, arma::vec x_r, arma::ivec x_i, std::string transP,
                    std::string model, std::string transX) {
+    check_transP(transP);
     lna_problem *pb = problem_xi(t, x_r, x_i, 1, 0.0, InitView(), model, transX);
     Dims d(pb);
     arma::vec q = pad_param(param, d.npt);
@@ -251,14 +256,17 @@ static List kf_param_impl(const arma::mat &OdeTraj, const arma::vec &param, int 
 }
 List KF_param(arma::mat OdeTraj, arma::vec param, int gridsize, arma::vec x_r, arma::ivec x_i, std::string transP,
               std::string model, std::string transX) {
+    check_transP(transP);
     return kf_param_impl(OdeTraj, param, gridsize, x_r, x_i, model, transX, 0);
 }
 List KF_param_chol(arma::mat OdeTraj, arma::vec param, int gridsize, arma::vec x_r, arma::ivec x_i, std::string transP,
                    std::string model, std::string transX) {
+    check_transP(transP);
     return kf_param_impl(OdeTraj, param, gridsize, x_r, x_i, model, transX, 1);
 }
 List SigmaF(arma::mat Traj_par, arma::vec param, arma::vec x_r, arma::ivec x_i, std::string transP, std::string model,
             std::string transX) {
+    check_transP(transP);
     // one LNA interval = KF_param with gridsize = nrow(Traj_par); a closing row (never read) completes the grid
     const int g = (int)Traj_par.n_rows, nc = (int)Traj_par.n_cols;
     arma::mat T(g + 1, nc);
@@ -290,6 +298,7 @@ arma::mat Ode_Coarse_Slicer(arma::mat Ode_thin, int gridsize) {
 
 List New_Param_List(arma::vec param, arma::vec initial, int gridsize, arma::vec t, arma::vec x_r, arma::ivec x_i,
                     std::string transP, std::string model, std::string transX) {
+    check_transP(transP);
     lna_problem *pb = problem_xi(t, x_r, x_i, gridsize, 0.0, InitView(), model, transX);
     Dims d(pb);
     arma::vec q = pad_param(param, d.npt), betaN(d.nrow);
@@ -336,6 +345,7 @@ List Traj_sim_general_noncentral(arma::mat OdeTraj, List Filter_NC, double t_cor
 
 List Traj_sim_ezG_NC(arma::vec initial, arma::vec times, arma::vec param, int gridsize, arma::vec x_r, arma::ivec x_i,
                      double t_correct, std::string transP, std::string model, std::string transX) {
+    check_transP(transP);
     List npl = New_Param_List(param, initial, gridsize, times, x_r, x_i, transP, model, transX);
     return Traj_sim_general_noncentral(as<arma::mat>(npl[1]), as<List>(npl[0]), t_correct);
 }
@@ -373,6 +383,7 @@ double coal_loglik(List init, arma::mat f1, double t_correct, double lambda, int
 List Update_Param(arma::vec param, arma::vec initial, arma::vec t, arma::mat OriginTraj, arma::vec x_r, arma::ivec x_i,
                   List init, int gridsize, double coal_log, double prior_proposal_offset, double t_correct,
                   std::string transP, std::string model, std::string transX, bool volz) {
+    check_transP(transP);
     lna_problem *pb = problem_xi(t, x_r, x_i, gridsize, t_correct, InitView(init), model, transX);
     Dims d(pb);
     arma::vec q = pad_param(param, d.npt), betaN(d.nrow);
@@ -434,6 +445,7 @@ arma::vec Param_Slice_update_all2(arma::vec par_old, arma::vec x_r, arma::ivec x
 List ESlice_par_General(arma::vec par_old, arma::vec t, arma::mat OriginTraj, List priorList, arma::vec x_r, arma::ivec x_i,
                         List init, int gridsize, arma::ivec ESS_vec, double coal_log, double t_correct, std::string transP,
                         std::string model, std::string transX, bool volz) {
+    check_transP(transP);
     if (ESS_vec[6] != 0) Rcpp::stop("GPU path: ESS_vec[7] (the self-mixing OriginTraj branch, :1660-1662) is not built");
     lna_problem *pb = problem_xi(t, x_r, x_i, gridsize, t_correct, InitView(init), model, transX);
     Dims d(pb);
@@ -505,6 +517,7 @@ List ESlice_general_NC(arma::mat f_cur, arma::mat OdeTraj, List FTs, arma::vec s
 List ESlice_change_points(arma::vec param, arma::vec initial, arma::vec t, arma::mat OriginTraj, arma::vec x_r,
                           arma::ivec x_i, List init, int gridsize, double coal_log, double t_correct, std::string transP,
                           std::string model, std::string transX, bool volz) {
+    check_transP(transP);
     lna_problem *pb = problem_xi(t, x_r, x_i, gridsize, t_correct, InitView(init), model, transX);
     Dims d(pb);
     arma::vec un(LNA_ESLICE_MAX_UNIF);
@@ -567,6 +580,7 @@ List Traj_sim_general3(arma::mat OdeTraj, List Filter, double t_correct) {
 }
 List Traj_sim_ezG2(arma::vec initial, arma::vec times, arma::vec param, int gridsize, arma::vec x_r, arma::ivec x_i,
                    double t_correct, std::string transP, std::string model, std::string transX) {
+    check_transP(transP);
     arma::mat ode = ODE_rk45(initial, times, param, x_r, x_i, transP, model, transX);
     List kf = KF_param(ode, param, gridsize, x_r, x_i, transP, model, transX);
     return Traj_sim_general3(Ode_Coarse_Slicer(ode, gridsize), kf, t_correct);
