@@ -343,6 +343,19 @@ int lna_chains_step_mcmc2_dev(lna_chains *ch, const lna_mcmc2_opts *opts, const 
 int lna_chains_step_mcmc2_rng(lna_chains *ch, const lna_mcmc2_opts *opts, uint64_t seed, uint64_t iteration,
                               int64_t chain_offset);
 
+/* Stream groups.  A batch of >= 2048 chains runs as G groups on G streams (chains of different groups never interact).
+ * By default every step ends by ordering the problem's stream after all groups, so work the caller enqueues there
+ * afterwards sees the step's results.  With free-running groups (on = 1) that join is deferred: the groups run ahead of each
+ * other ACROSS iterations, so one group's latency-bound stages overlap another group's throughput-bound ones; results are
+ * the same bits.  The caller then observes the chains through lna_chains_get / lna_chains_history_get (which synchronise),
+ * or calls lna_chains_join (orders the problem's stream after everything enqueued so far: needed before reading
+ * lna_chains_summary_dev on that stream or recording a timing event there) / lna_chains_sync (host waits).  Buffers passed to
+ * the `_dev` step variants must stay valid until then.  No reference counterpart (the reference is single-threaded). */
+int lna_chains_set_free_running(lna_chains *ch, int on);
+int lna_chains_join(lna_chains *ch);
+int lna_chains_sync(lna_chains *ch);
+int lna_chains_groups(const lna_chains *ch);
+
 /* Read the state back (any pointer may be NULL).  counters: B x 4 int32 = (n_full_evals,
  * n_cheap_evals, n_mh_accept, status OR). */
 int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
@@ -358,7 +371,11 @@ int lna_chains_history_get(lna_chains *ch, double *par, double *l, double *l1);
  * all-gathered across GPUs; valid until the next step. */
 const double *lna_chains_summary_dev(lna_chains *ch);
 
-/* ---- measurement helper ---------------------------------------------------------------------- */
+/* ---- measurement helpers --------------------------------------------------------------------- */
+/* Debug timeline: with LNA_TIMELINE=1 in the environment every kernel launch is followed by a CUDA event on its stream;
+ * this writes "stream,kernel,t_end_us" rows (one GPU-global time axis) to `path` and clears the record.  Use with
+ * LNA_GRAPH=0 (launches replayed from a CUDA graph are not marked). */
+int lna_debug_timeline_dump(const char *path);
 /* Independent-DFMA microbenchmark: returns achieved FP64 FLOP/s of the device (2 flops per FMA),
  * used as the measured denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 entry). */
 double lna_measure_fp64_peak(int device, int iters);

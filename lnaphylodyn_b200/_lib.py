@@ -93,10 +93,15 @@ _SIGS = {
     "lna_draw_streams": (C.c_int, [_vp, _I64, _I64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp, _vp]),
     "lna_chains_get": (C.c_int, [_vp] + [_vp] * 6),
     "lna_chains_summary_dev": (_vp, [_vp]),
+    "lna_chains_set_free_running": (C.c_int, [_vp, C.c_int]),
+    "lna_chains_join": (C.c_int, [_vp]),
+    "lna_chains_sync": (C.c_int, [_vp]),
+    "lna_chains_groups": (C.c_int, [_vp]),
     "lna_chains_history_begin": (C.c_int, [_vp, C.c_int64]),
     "lna_chains_history_record": (C.c_int, [_vp, C.c_int64]),
     "lna_chains_history_get": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lna_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
+    "lna_debug_timeline_dump": (C.c_int, [C.c_char_p]),
 }
 
 _lib = None

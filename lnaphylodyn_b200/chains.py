@@ -64,7 +64,9 @@ def make_opts_general(prior, proposal, ESS_vec, entries, hyper=False, update_tra
 class Chains:
     """B resident chains on one GPU (wraps lna_chains)."""
 
-    def __init__(self, problem, par, OriginTraj):
+    def __init__(self, problem, par, OriginTraj, free_running=False):
+        """free_running: the stream groups of a large batch are not joined after every step (lna_chains_set_free_running);
+        get() / join() / sync() are the observation points."""
         self.pb = problem
         par = _d(par)
         self.B = par.shape[0]
@@ -79,6 +81,23 @@ class Chains:
         if E.shape[0] == 1 and self.B > 1:
             E = np.ascontiguousarray(np.broadcast_to(E, (self.B, E.shape[1])))
         check(L.lna_chains_init(self.h, _ptr(par), _ptr(E)), "lna_chains_init")
+        if free_running:
+            check(L.lna_chains_set_free_running(self.h, 1), "lna_chains_set_free_running")
+
+    def set_free_running(self, on=True):
+        check(_lib.lib().lna_chains_set_free_running(self.h, int(bool(on))), "lna_chains_set_free_running")
+
+    def join(self):
+        """Order the problem's stream after everything enqueued on the chains' stream groups so far."""
+        check(_lib.lib().lna_chains_join(self.h), "lna_chains_join")
+
+    def sync(self):
+        """Host waits for all stream groups."""
+        check(_lib.lib().lna_chains_sync(self.h), "lna_chains_sync")
+
+    @property
+    def groups(self):
+        return _lib.lib().lna_chains_groups(self.h)
 
     def step(self, opts, normals, uniforms):
         """One MCMC iteration. normals (B, npar-1 + k*p), uniforms (B, 47): host arrays."""
@@ -118,6 +137,7 @@ class Chains:
                 "n_full_evals": cnt[:, 0], "n_cheap_evals": cnt[:, 1], "n_mh_accept": cnt[:, 2], "status": cnt[:, 3]}
 
     def summary_ptr(self):
+        self.join()
         return _lib.lib().lna_chains_summary_dev(self.h)
 
 

@@ -102,8 +102,9 @@ struct lna_problem {
     lna_cfg cfg{};
     std::vector<double> iC, iD, iy, igridrep;
     int iE = 0, ing = 0, has_init = 0;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t chunk_ev[8] = {};
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t chunk_ev[8] = {}, kern_ev[8] = {}, d2h_ev[2] = {};
+    bool d2h_pending = false;  // asynchronous result copies in flight on d2h_stream (lna_problem_sync waits for them)
     cudaEvent_t done_ev = nullptr;
     cudaEvent_t async_done[2] = {};  // lna_full_loglik_async: last use of staging set 0 / 1
     int async_parity = 0;
@@ -165,6 +166,20 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
              cfg->nparam);
         return nullptr;
     }
+    if (cfg->model != LNA_MODEL_SIRS_PERIOD) {
+        // x_i[2], x_i[3] double as parameter indices (R0, gamma) and as the Volz likelihood's state columns (S, I)
+        const int p = cfg->model == LNA_MODEL_SIR ? 2 : 3;
+        if (cfg->iR0 < 0 || cfg->iR0 >= cfg->nparam || cfg->iGamma < 0 || cfg->iGamma >= cfg->nparam) {
+            fail("lna_problem_create: x_i[2] = %d / x_i[3] = %d must index the %d model parameters", cfg->iR0, cfg->iGamma,
+                 cfg->nparam);
+            return nullptr;
+        }
+        if (init && (cfg->iR0 >= p || cfg->iGamma >= p)) {
+            fail("lna_problem_create: x_i[2] = %d / x_i[3] = %d are also the S / I state columns of the coalescent likelihood "
+                 "and must be < p = %d", cfg->iR0, cfg->iGamma, p);
+            return nullptr;
+        }
+    }
     int ndev = lna_device_count();
     if (ndev <= 0) {
         fail("lna_problem_create: no CUDA device available (this library has no CPU fallback)");
@@ -185,7 +200,10 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
     }
     pb->own_stream = true;
     cudaStreamCreateWithFlags(&pb->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&pb->d2h_stream, cudaStreamNonBlocking);
     for (auto &e : pb->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : pb->kern_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : pb->d2h_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pb->done_ev, cudaEventDisableTiming);
     for (auto &e : pb->async_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     DevProb &P = pb->dp;
@@ -338,8 +356,14 @@ extern "C" void lna_problem_destroy(lna_problem *pb) {
     if (pb->stream) cudaStreamSynchronize(pb->stream);
     for (void *p : pb->owned) cudaFree(p);
     pb->scratch.release();
+    if (pb->d2h_stream) cudaStreamSynchronize(pb->d2h_stream);
     if (pb->copy_stream) cudaStreamDestroy(pb->copy_stream);
+    if (pb->d2h_stream) cudaStreamDestroy(pb->d2h_stream);
     for (auto &e : pb->chunk_ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : pb->kern_ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : pb->d2h_ev)
         if (e) cudaEventDestroy(e);
     if (pb->done_ev) cudaEventDestroy(pb->done_ev);
     for (auto &e : pb->async_done)
@@ -351,6 +375,10 @@ extern "C" void lna_problem_destroy(lna_problem *pb) {
 extern "C" int lna_problem_sync(lna_problem *pb) {
     if (!pb) return fail("null problem");
     CK(cudaStreamSynchronize(pb->stream));
+    if (pb->d2h_pending) {  // results of lna_full_loglik*_async calls return on their own stream
+        CK(cudaStreamSynchronize(pb->d2h_stream));
+        pb->d2h_pending = false;
+    }
     return 0;
 }
 extern "C" void *lna_problem_stream(lna_problem *pb) { return pb ? (void *)pb->stream : nullptr; }
@@ -427,9 +455,60 @@ struct Stage {
     }
 };
 
+// ---- debug timeline (LNA_TIMELINE=1): an event after every launch, dumped as CSV by lna_debug_timeline_dump ----------------
+// In-stream launches run back to back, so consecutive end-of-kernel timestamps of one stream give each kernel's span
+// (including any idle gap in front of it); timestamps are GPU-global, so the streams' rows interleave on one time axis.
+struct TimelineRow {
+    const char *what;
+    cudaStream_t stream;
+    cudaEvent_t ev;
+};
+static std::vector<TimelineRow> g_timeline;
+static std::mutex g_timeline_mu;
+static bool timeline_on() {
+    static const bool on = [] {
+        const char *e = getenv("LNA_TIMELINE");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+static void timeline_mark(cudaStream_t st, const char *what) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return;
+    }
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    std::lock_guard<std::mutex> lock(g_timeline_mu);
+    g_timeline.push_back({what, st, ev});
+}
+extern "C" int lna_debug_timeline_dump(const char *path) {
+    std::lock_guard<std::mutex> lock(g_timeline_mu);
+    if (g_timeline.empty()) return fail("lna_debug_timeline_dump: nothing recorded (set LNA_TIMELINE=1, LNA_GRAPH=0)");
+    FILE *f = fopen(path, "w");
+    if (!f) return fail("lna_debug_timeline_dump: cannot open %s", path);
+    cudaDeviceSynchronize();
+    fprintf(f, "stream,kernel,t_end_us\n");
+    std::vector<cudaStream_t> ids;
+    for (auto &r : g_timeline) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_timeline[0].ev, r.ev);
+        size_t id = std::find(ids.begin(), ids.end(), r.stream) - ids.begin();
+        if (id == ids.size()) ids.push_back(r.stream);
+        fprintf(f, "%zu,%s,%.3f\n", id, r.what, ms * 1e3);
+    }
+    fclose(f);
+    for (auto &r : g_timeline) cudaEventDestroy(r.ev);
+    g_timeline.clear();
+    return 0;
+}
+
 static int launch_check(lna_problem *pb, const char *what) {
     pb->launches++;
     if (pb->parent) pb->parent->launches++;
+    if (timeline_on()) timeline_mark(pb->stream, what);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
     return 0;
@@ -537,9 +616,10 @@ static int full_loglik_log_dev(lna_problem *pb, int64_t B, const double *param, 
     return launch_check(pb, "k_merge_full_status");
 }
 
+// `group` > 1: chain-shared inputs -- `initial` and `origin` hold one item per `group` consecutive evaluations
 static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param, const double *initial,
                                 const double *origin, double *coalLog, int32_t *status, double *A, double *L,
-                                double *ode, double *betaN, double *latent) {
+                                double *ode, double *betaN, double *latent, int group = 1) {
     if (B <= 0) return 0;
     const DevProb &P = pb->dp;
     if (!param || !initial) return fail("lna_full_loglik: param/initial must not be null");
@@ -547,8 +627,16 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
         return fail("lna_full_loglik: the seasonal SIRS variant has no non-centred path in the reference "
                     "(use lna_ode_rk45 / lna_kf_param / lna_log_like_traj_sirs)");
     if (coalLog && !P.has_init) return fail("lna_full_loglik: problem was created without a genealogy");
-    if (P.transX == LNA_TRANSX_LOG)
+    // The reference's rhs functions hard-wire R0 = param[0] and gamma = param[nparam-1] = thetas[p-1] (LNA_functional.cpp:
+    // 115-116, 170-176) while param_transform reads them at x_i[2], x_i[3]: any other layout makes the reference's own
+    // pieces disagree.  The fused evaluation takes the layouts the reference can run, (nch, 2, 0, 1) and (nch, 3, 0, 2).
+    if (P.nparam != P.p || P.iR0 != 0 || P.iGamma != P.p - 1)
+        return fail("lna_full_loglik: x_i = (nch, nparam, iR0, iGamma) must be (nch, %d, 0, %d) for this model (got nparam=%d "
+                    "iR0=%d iGamma=%d)", P.p, P.p - 1, P.nparam, P.iR0, P.iGamma);
+    if (P.transX == LNA_TRANSX_LOG) {
+        if (group > 1) return fail("lna_full_loglik_shared: standard scale only");
         return full_loglik_log_dev(pb, B, param, initial, origin, coalLog, status, A, L, ode, betaN, latent);
+    }
     const int p = P.p;
     FullOut out{item_out(A, (long long)p * p * P.k), item_out(L, (long long)p * p * P.k),
                 item_out(ode, (long long)P.nrow * (p + 1)), item_out(betaN, P.nrow),
@@ -558,7 +646,7 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
     const unsigned grid = nblk(B, block);
     const View vp = item_view(param, P.npt), vi = item_view(initial, p), vo = item_view(origin, (long long)P.k * p);
 #define LAUNCH(MODEL, STORE)                                                                                     \
-    k_full_loglik<MODEL, STORE><<<grid, block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status)
+    k_full_loglik<MODEL, STORE><<<grid, block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status, group)
     if (P.model == LNA_MODEL_SIR && use_split_eval(pb, B, 1)) {
         // small batch (measured: up to ~one item warp per SM, 0.82 of the one-warp kernel's call latency at B = 1..32, break-even
         // near 4096 items): the launch lasts as long as one evaluation takes one warp -> three-warp pipeline (lna_split.cuh)
@@ -566,10 +654,10 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
         const size_t sm = full_eval_smem_bytes(pb->tab_bytes, blk) + lna::split_group_bytes();
         if (store) {
             big_smem_attr(k_full_loglik_split<true>, pb->device);
-            k_full_loglik_split<true><<<nblk(B, 32), blk, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status);
+            k_full_loglik_split<true><<<nblk(B, 32), blk, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status, group);
         } else {
             big_smem_attr(k_full_loglik_split<false>, pb->device);
-            k_full_loglik_split<false><<<nblk(B, 32), blk, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status);
+            k_full_loglik_split<false><<<nblk(B, 32), blk, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status, group);
         }
     } else if (P.model == LNA_MODEL_SIR) {
         if (store) LAUNCH(0, true);
@@ -591,22 +679,28 @@ extern "C" int lna_full_loglik_dev(lna_problem *pb, int64_t B, const double *par
                                 LatentTraj);
 }
 
-// Large likelihood-only batches through host buffers are PCIe-bound (992 B in per evaluation): the batch is split into
-// chunks and the H2D copy of chunk i+1 (copy stream) overlaps the kernel of chunk i (compute stream).
+// Large likelihood-only batches through host buffers: the batch is split into chunks and the H2D copy of chunk i+1 (copy
+// stream) overlaps the kernel of chunk i (compute stream); results return on a third stream so that a D2H copy never sits
+// between two kernels.
 // async: no synchronisation at the end -- the caller reads the outputs after lna_problem_sync() and keeps all host buffers
 // alive until then; consecutive asynchronous calls alternate between two staging sets, so the copies of call n+1 overlap
-// the last kernel of call n (they wait only for call n-1, the previous user of their staging set).
+// the kernel of call n (they wait only for call n-1, the previous user of their staging set).
+// group > 1: chain-shared inputs (lna_full_loglik_shared): B = n_chains * group evaluations, `initial` / `OriginTraj` per
+// chain -- 336 + (16 + 640) / group bytes per evaluation instead of 992.
 static int full_loglik_chunked(lna_problem *pb, int64_t B, const double *param, const double *initial,
-                               const double *OriginTraj, double *coalLog, int32_t *status, bool async) {
+                               const double *OriginTraj, double *coalLog, int32_t *status, bool async, int group = 1) {
     const DevProb &P = pb->dp;
-    const size_t p = P.p, k = P.k, nB = (size_t)B;
+    const size_t p = P.p, k = P.k, nB = (size_t)B, nC = nB / (size_t)group;
     cudaSetDevice(pb->device);
-    const int nchunk = 4;  // >= 16k evaluations per chunk keeps each kernel off the ~0.2 ms single-evaluation latency floor
+    // chunk kernels of >= 32k evaluations stay off the ~0.2 ms single-evaluation latency floor; an asynchronous call
+    // pipelines against its neighbours, so it is not split at all unless it is very large
+    int nchunk = async ? (int)std::min<size_t>(4, std::max<size_t>(1, nB / 131072)) : (int)std::min<size_t>(4, std::max<size_t>(1, nB / 32768));
+    if (const char *e = getenv("LNA_H2D_CHUNKS")) nchunk = std::max(1, std::min(4, atoi(e)));
     const int q = async ? (pb->async_parity ^= 1) : 0;
     const size_t base = async ? 32 + 5 * (size_t)q : 0;
     double *dpar = (double *)pb->scratch.get(base + 0, nB * P.npt * sizeof(double));
-    double *dini = (double *)pb->scratch.get(base + 1, nB * p * sizeof(double));
-    double *dor = (double *)pb->scratch.get(base + 2, nB * k * p * sizeof(double));
+    double *dini = (double *)pb->scratch.get(base + 1, nC * p * sizeof(double));
+    double *dor = (double *)pb->scratch.get(base + 2, nC * k * p * sizeof(double));
     double *dcl = (double *)pb->scratch.get(base + 3, nB * sizeof(double));
     int32_t *dst = (int32_t *)pb->scratch.get(base + 4, nB * sizeof(int32_t));
     if (!dpar || !dini || !dor || !dcl || !dst) return fail("lna_full_loglik: device staging failed");
@@ -618,26 +712,35 @@ static int full_loglik_chunked(lna_problem *pb, int64_t B, const double *param, 
         CK(cudaStreamWaitEvent(pb->copy_stream, pb->done_ev, 0));
     }
     for (int c = 0; c < nchunk; ++c) {
-        const size_t b0 = nB * c / nchunk, b1 = nB * (c + 1) / nchunk, n = b1 - b0;
+        const size_t c0 = nC * c / nchunk, c1 = nC * (c + 1) / nchunk, nc = c1 - c0;  // chains (= items when group == 1)
+        const size_t b0 = c0 * group, n = nc * group;
         if (!n) continue;
         CK(cudaMemcpyAsync(dpar + b0 * P.npt, param + b0 * P.npt, n * P.npt * sizeof(double), cudaMemcpyHostToDevice,
                            pb->copy_stream));
-        CK(cudaMemcpyAsync(dini + b0 * p, initial + b0 * p, n * p * sizeof(double), cudaMemcpyHostToDevice, pb->copy_stream));
-        CK(cudaMemcpyAsync(dor + b0 * k * p, OriginTraj + b0 * k * p, n * k * p * sizeof(double), cudaMemcpyHostToDevice,
+        CK(cudaMemcpyAsync(dini + c0 * p, initial + c0 * p, nc * p * sizeof(double), cudaMemcpyHostToDevice, pb->copy_stream));
+        CK(cudaMemcpyAsync(dor + c0 * k * p, OriginTraj + c0 * k * p, nc * k * p * sizeof(double), cudaMemcpyHostToDevice,
                            pb->copy_stream));
         cudaEvent_t ev = pb->chunk_ev[(async ? 4 * q : 0) + c];
         CK(cudaEventRecord(ev, pb->copy_stream));
         CK(cudaStreamWaitEvent(pb->stream, ev, 0));
-        if (full_loglik_dev_impl(pb, (int64_t)n, dpar + b0 * P.npt, dini + b0 * p, dor + b0 * k * p, dcl + b0, dst + b0,
-                                 nullptr, nullptr, nullptr, nullptr, nullptr))
+        if (full_loglik_dev_impl(pb, (int64_t)n, dpar + b0 * P.npt, dini + c0 * p, dor + c0 * k * p, dcl + b0, dst + b0,
+                                 nullptr, nullptr, nullptr, nullptr, nullptr, group))
             return -1;
-        CK(cudaMemcpyAsync(coalLog + b0, dcl + b0, n * sizeof(double), cudaMemcpyDeviceToHost, pb->stream));
-        if (status) CK(cudaMemcpyAsync(status + b0, dst + b0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, pb->stream));
+        // results back on the D2H stream, behind this chunk's kernel
+        cudaEvent_t kev = pb->kern_ev[(async ? 4 * q : 0) + c];
+        CK(cudaEventRecord(kev, pb->stream));
+        CK(cudaStreamWaitEvent(pb->d2h_stream, kev, 0));
+        CK(cudaMemcpyAsync(coalLog + b0, dcl + b0, n * sizeof(double), cudaMemcpyDeviceToHost, pb->d2h_stream));
+        if (status) CK(cudaMemcpyAsync(status + b0, dst + b0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, pb->d2h_stream));
     }
+    // the compute stream is ordered after the result copies: lna_problem_sync() covers them, and so does the staging reuse
+    CK(cudaEventRecord(pb->d2h_ev[q], pb->d2h_stream));
     if (async) {
-        CK(cudaEventRecord(pb->async_done[q], pb->stream));
+        CK(cudaEventRecord(pb->async_done[q], pb->d2h_stream));
+        pb->d2h_pending = true;
         return 0;
     }
+    CK(cudaStreamSynchronize(pb->d2h_stream));
     CK(cudaStreamSynchronize(pb->stream));
     return 0;
 }
@@ -680,6 +783,41 @@ extern "C" int lna_full_loglik_async(lna_problem *pb, int64_t B, const double *p
     if (B < 16384 || !pb->copy_stream)  // small batches: nothing to overlap, the synchronous call is the asynchronous one
         return lna_full_loglik(pb, B, param, initial, OriginTraj, coalLog, status, nullptr, nullptr, nullptr, nullptr, nullptr);
     return full_loglik_chunked(pb, B, param, initial, OriginTraj, coalLog, status, /*async=*/true);
+}
+
+// ---- chain-shared form of the hot call -------------------------------------------------------------------------------------
+static int shared_args(lna_problem *pb, int64_t n_chains, int proposals, const void *param, const void *initial,
+                       const void *origin, const void *coalLog, const char *what) {
+    if (!pb) return fail("null problem");
+    if (n_chains < 0 || proposals < 1) return fail("%s: n_chains >= 0 and proposals >= 1 are required", what);
+    if (n_chains > 0 && (!param || !initial || !origin || !coalLog)) return fail("%s: null argument", what);
+    if (!pb->dp.has_init) return fail("%s: problem was created without a genealogy", what);
+    if (pb->dp.model == LNA_MODEL_SIRS_PERIOD || pb->dp.transX != LNA_TRANSX_STANDARD)
+        return fail("%s: SIR / SEIR on the standard scale only", what);
+    return 0;
+}
+
+extern "C" int lna_full_loglik_shared_dev(lna_problem *pb, int64_t n_chains, int proposals, const double *param,
+                                          const double *initial, const double *OriginTraj, double *coalLog, int32_t *status) {
+    if (shared_args(pb, n_chains, proposals, param, initial, OriginTraj, coalLog, "lna_full_loglik_shared_dev")) return -1;
+    cudaSetDevice(pb->device);
+    return full_loglik_dev_impl(pb, n_chains * proposals, param, initial, OriginTraj, coalLog, status, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, proposals);
+}
+
+extern "C" int lna_full_loglik_shared(lna_problem *pb, int64_t n_chains, int proposals, const double *param,
+                                      const double *initial, const double *OriginTraj, double *coalLog, int32_t *status) {
+    if (shared_args(pb, n_chains, proposals, param, initial, OriginTraj, coalLog, "lna_full_loglik_shared")) return -1;
+    if (n_chains == 0) return 0;
+    return full_loglik_chunked(pb, n_chains * proposals, param, initial, OriginTraj, coalLog, status, /*async=*/false, proposals);
+}
+
+extern "C" int lna_full_loglik_shared_async(lna_problem *pb, int64_t n_chains, int proposals, const double *param,
+                                            const double *initial, const double *OriginTraj, double *coalLog,
+                                            int32_t *status) {
+    if (shared_args(pb, n_chains, proposals, param, initial, OriginTraj, coalLog, "lna_full_loglik_shared_async")) return -1;
+    if (n_chains == 0) return 0;
+    return full_loglik_chunked(pb, n_chains * proposals, param, initial, OriginTraj, coalLog, status, /*async=*/true, proposals);
 }
 
 extern "C" int lna_new_param_list(lna_problem *pb, int64_t B, const double *param, const double *initial,
@@ -939,15 +1077,15 @@ extern "C" double lna_measure_fp64_peak(int device, int iters) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     double *sink = nullptr;
     if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
-    const int block = 256, grid = sms * 8;
+    const int block = 512, grid = sms * 4;  // 64 resident warps per SM = 16 per sub-partition
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    k_fp64_peak<<<grid, block>>>(iters / 8 + 1, sink);  // warm-up
+    k_fp64_peak<<<grid, block>>>(iters, 1.0000001, 1e-7, sink);  // warm-up (clocks ramp during it)
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0);
-        k_fp64_peak<<<grid, block>>>(iters, sink);
+        k_fp64_peak<<<grid, block>>>(iters, 1.0000001, 1e-7, sink);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) break;
         float ms = 0.f;

@@ -104,6 +104,14 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     }
 #undef LC2
 #undef LC
+    if (timeline_on()) {  // label with <proposal kind, lanes per chain, pipelined> and the first candidate of the phase
+        static std::mutex mu;
+        static std::set<std::string> names;
+        char buf[64];
+        snprintf(buf, sizeof buf, "k_cand_eval<%d;%d;%d>@%d", kProp, W, split ? 1 : 0, a.first_cand);
+        std::lock_guard<std::mutex> lock(mu);
+        return launch_check(pb, names.insert(buf).first->c_str());
+    }
     return launch_check(pb, "k_cand_eval");
 }
 
@@ -209,15 +217,15 @@ static int launch_traj(lna_problem *pb, long long B, const TrajArgs &a) {
     const size_t sh = pb->tab_bytes + sizeof(double) * kTrajWarps * traj_warp_doubles(P.k, P.nrow);
     if (sh > 48 * 1024) {
         if (sh > 200 * 1024) return fail("k_eslice_traj: k = %d LNA intervals do not fit in shared memory", P.k);
-        cudaFuncSetAttribute(k_eslice_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        big_smem_attr(k_eslice_traj, pb->device);  // (once per device: not repeated inside a stream capture)
     }
     k_eslice_traj<<<nblk(B, kTrajWarps), kTrajWarps * 32, sh, pb->stream>>>(P, B, a);
     return launch_check(pb, "k_eslice_traj");
 }
 
 static int check_sir_sampler(const lna_problem *pb, const char *what) {
-    if (pb->dp.model != LNA_MODEL_SIR || pb->dp.nparam != 2)
-        return fail("%s: the reference's samplers are hard-wired to SIR (p = 2, nparam = 2)", what);
+    if (pb->dp.model != LNA_MODEL_SIR || pb->dp.nparam != 2 || pb->dp.iR0 != 0 || pb->dp.iGamma != 1)
+        return fail("%s: the reference's samplers are hard-wired to SIR (p = 2, nparam = 2, x_i = (nch, 2, 0, 1))", what);
     if (!pb->dp.has_init) return fail("%s: problem was created without a genealogy", what);
     if (pb->dp.transX != LNA_TRANSX_STANDARD)
         return fail("%s: the Metropolis / slice operators work on the standard scale (transX = \"standard\"), like every "
@@ -556,6 +564,7 @@ struct ChainPart {  // one stream-group of a resident chain batch
     long long planB = 0;  // chain count of the WHOLE batch: phase plans and policies are chosen for it
     int W = 1;
     // slot-major state: field[j*B + c]
+    double *par_home = nullptr;  // the buffer `par` points to between iterations (see chains_finish)
     double *par = nullptr, *par_alt = nullptr, *origin = nullptr, *A = nullptr, *L = nullptr, *ode = nullptr, *betaN = nullptr,
            *latent = nullptr, *coalLog = nullptr, *logOrigin = nullptr, *summary = nullptr;
     int *counters = nullptr;  // [4][B]: n_full, n_cheap, n_mh_accept, status
@@ -568,6 +577,25 @@ struct ChainPart {  // one stream-group of a resident chain batch
     size_t n_norm = 0, n_unif = 0;
     double *jT = nullptr, *jnew = nullptr;  // joint Metropolis step: [B][16] transforms (padded 4 x 4), [B][4] proposed values
     int jd = 0;
+    // CUDA graphs of whole iterations on device-drawn streams (one per distinct option set): the ~14 launches of an
+    // iteration are replayed with one cudaGraphLaunch; only the Philox counter (iteration) changes between replays
+    struct StepGraph {
+        std::vector<unsigned char> key;
+        cudaGraph_t graph = nullptr;  // kept alive: draw_node is a handle into it
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t draw_node = nullptr;
+        cudaKernelNodeParams draw_params{};
+        int n_kernels = 0;
+        bool broken = false;
+        // argument block of the k_draw_streams node
+        long long aB = 0, aoff = 0;
+        int ann = 0, anu = 0;
+        unsigned long long aseed = 0, aiter = 0;
+        double *adn = nullptr, *adu = nullptr;
+        void *argv[8] = {};
+    };
+    std::vector<StepGraph *> graphs;
+    std::vector<unsigned char> last_key;
 };
 
 __global__ void k_bump(long long B, const int *n_evals, const int *accept, const int *status, const int *win_slot,
@@ -616,6 +644,7 @@ static ChainPart *part_create(lna_problem *pb, int64_t B, int64_t planB, double 
     const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
     const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
     ch->par = chains_alloc<double>(ch, nB * npar);
+    ch->par_home = ch->par;
     ch->par_alt = chains_alloc<double>(ch, nB * npar);
     ch->origin = chains_alloc<double>(ch, nB * kp);
     ch->A = chains_alloc<double>(ch, nB * nA);
@@ -652,6 +681,11 @@ static void part_destroy(ChainPart *ch) {
     cudaStreamSynchronize(ch->pb->stream);
     for (void *p : ch->owned) cudaFree(p);
     ch->cand_scratch.release();
+    for (auto *g : ch->graphs) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+        delete g;
+    }
     delete ch;
 }
 
@@ -676,9 +710,12 @@ static int part_init(ChainPart *ch, const double *par, const double *OriginTraj)
     const View vp{ch->par + 2 * B, 1, B}, vi{ch->par, 1, B}, vo{ch->origin, 1, B};
     const int block = pick_block(pb, B);
     k_full_loglik<0, true><<<nblk(B, block), block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, B, vp, vi, vo, out,
-                                                                                 ch->coalLog, ch->counters + 3 * B);
+                                                                                 ch->coalLog, ch->counters + 3 * B, 1);
     if (launch_check(pb, "k_full_loglik")) return -1;
-    CK(cudaMemsetAsync(ch->logOrigin, 0, sizeof(double) * nB, pb->stream));
+    // MCMC_obj$logOrigin = -sum(OriginTraj^2)/2 over all rows (general_change_point.R:530): what `l[i]` records until the
+    // first trajectory slice update replaces it
+    k_log_origin<<<nblk(B * 32, 128), 128, 0, pb->stream>>>(B, (int)kp, vo, ch->logOrigin);
+    if (launch_check(pb, "k_log_origin")) return -1;
     CK(cudaMemsetAsync(ch->counters, 0, sizeof(int) * nB * 3, pb->stream));
     return s.finish("lna_chains_init");
 }
@@ -759,8 +796,22 @@ static int chains_traj(ChainPart *ch, View normals, View uniforms) {
 
 static int chains_finish(ChainPart *ch) {
     lna_problem *pb = ch->pb;
+    // every stage flips the parameter double buffer; an iteration with an odd number of stages would leave the state in the
+    // other buffer, and a replayed CUDA graph of the iteration (captured pointers) would then read the wrong one
+    if (ch->par != ch->par_home) {
+        const size_t bytes = sizeof(double) * (size_t)ch->B * (size_t)(2 + pb->dp.npt);
+        CK(cudaMemcpyAsync(ch->par_home, ch->par, bytes, cudaMemcpyDeviceToDevice, pb->stream));
+        std::swap(ch->par, ch->par_alt);
+    }
     k_summary<<<nblk(ch->B, 256), 256, 0, pb->stream>>>(ch->B, ch->coalLog, ch->logOrigin, ch->counters, ch->summary);
     return launch_check(pb, "k_summary");
+}
+
+// Both Metropolis entries of the vignettes speculatively in one latency period (3 evaluations per chain) or one after the
+// other (2 evaluations, two latency periods): LNA_MH_PAIR=0/1 forces the choice (experiments).
+static bool mh_pair_policy(long long planB, int sm_count) {
+    if (const char *e = getenv("LNA_MH_PAIR")) return atoi(e) != 0;
+    return planB * 4 <= (long long)sm_count * 512;
 }
 
 // General_MCMC_with_ESlice iteration body (R/LNA_chpt_slice.R:775-847)
@@ -842,7 +893,7 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
     a.gamma_prop = o->gamma_prop;
     if (general) {
         // (done above)
-    } else if (o->hyper_noop_mh && ch->planB * 4 <= (long long)pb->sm_count * 512) {
+    } else if (o->hyper_noop_mh && mh_pair_policy(ch->planB, pb->sm_count)) {
         // few chains: both MH entries speculatively in one latency period (3 evaluations per chain)
         if (chains_stage<PROP_MH_PAIR>(ch, a, 4)) return -1;
     } else {
@@ -1008,7 +1059,9 @@ static int part_step(ChainPart *ch, const lna_mcmc_opts *o, const double *normal
 // ------------------------------------------------------------------------------------------------
 static int draw_streams_dev(lna_problem *pb, long long B, long long chain_offset, int n_norm, int n_unif,
                             uint64_t seed, uint64_t iteration, double *dn, double *du) {
-    const long long n = B * ((n_norm + 1) / 2 + (n_unif + 1) / 2);
+    const long long per = (n_norm + 1) / 2 + (n_unif + 1) / 2, n = B * per;
+    if (per >= 65536 || (iteration >> 48) != 0)
+        return fail("lna_draw_streams: the Philox counter holds 2^16 output pairs per chain-iteration and iterations < 2^48");
     k_draw_streams<<<nblk(n, 256), 256, 0, pb->stream>>>(B, chain_offset, n_norm, n_unif, seed, iteration, dn, du);
     return launch_check(pb, "k_draw_streams");
 }
@@ -1049,6 +1102,108 @@ static int part_step_mcmc2_rng(ChainPart *ch, const lna_mcmc2_opts *o, uint64_t 
     if ((size_t)nn > ch->n_norm) return fail("lna_chains_step_mcmc2_rng: staging too small");
     if (draw_streams_dev(pb, ch->B, chain_offset, nn, (int)LNA_ITER2_UNIF, seed, iteration, ch->stage_n, ch->stage_u)) return -1;
     return part_step_mcmc2_dev(ch, o, ch->stage_n, ch->stage_u);
+}
+
+// One iteration on device-drawn streams through a CUDA graph.  The first call with a given option set runs eagerly (it
+// sizes the scratch buffers and sets the kernels' shared-memory attributes), the second one is captured on the group's stream,
+// later ones replay the instantiated graph with the k_draw_streams node's `iteration` argument updated.  Same kernels, same
+// arguments, same order as the eager path: same bits.  LNA_GRAPH=0 keeps the eager launches.
+template <class Opts, class Eager>
+static int part_step_graph(ChainPart *ch, int kind, const Opts *o, uint64_t seed, uint64_t iteration, int64_t chain_offset,
+                           Eager eager) {
+    static const bool enabled = [] {
+        const char *e = getenv("LNA_GRAPH");
+        return !(e && atoi(e) == 0);
+    }();
+    if (!enabled) return eager();
+    lna_problem *pb = ch->pb;
+    std::vector<unsigned char> key(sizeof(int) + sizeof(Opts) + sizeof(uint64_t) + sizeof(int64_t));
+    std::memcpy(key.data(), &kind, sizeof(int));
+    std::memcpy(key.data() + sizeof(int), o, sizeof(Opts));
+    std::memcpy(key.data() + sizeof(int) + sizeof(Opts), &seed, sizeof(uint64_t));
+    std::memcpy(key.data() + sizeof(int) + sizeof(Opts) + sizeof(uint64_t), &chain_offset, sizeof(int64_t));
+    auto replay = [&](ChainPart::StepGraph *g) -> int {
+        if (g->broken) return eager();
+        g->aiter = iteration;
+        cudaError_t e = cudaGraphExecKernelNodeSetParams(g->exec, g->draw_node, &g->draw_params);
+        if (e == cudaSuccess) e = cudaGraphLaunch(g->exec, pb->stream);
+        if (e != cudaSuccess) {  // (never observed after the first successful replay; the eager path is always valid)
+            if (getenv("LNA_GRAPH_DEBUG")) fprintf(stderr, "lna: graph replay failed (%s), eager launches from here on\n", cudaGetErrorString(e));
+            cudaGetLastError();
+            g->broken = true;
+            return eager();
+        }
+        pb->launches += g->n_kernels;
+        if (pb->parent) pb->parent->launches += g->n_kernels;
+        return 0;
+    };
+    for (auto *g : ch->graphs)
+        if (g->key == key) return replay(g);
+    if (ch->last_key != key || ch->graphs.size() >= 8) {
+        ch->last_key = key;
+        return eager();
+    }
+    // second iteration with these options: capture
+    cudaSetDevice(pb->device);
+    const int64_t l0 = pb->launches, lp0 = pb->parent ? pb->parent->launches : 0;
+    if (cudaStreamBeginCapture(pb->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return eager();
+    }
+    const int rc = eager();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ec = cudaStreamEndCapture(pb->stream, &graph);
+    const int nk = (int)(pb->launches - l0);
+    pb->launches = l0;  // (nothing ran yet)
+    if (pb->parent) pb->parent->launches = lp0;
+    if (rc != 0 || ec != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != 0) return rc;
+        ch->last_key.clear();
+        return eager();
+    }
+    auto *g = new ChainPart::StepGraph();
+    g->key = key;
+    g->n_kernels = nk;
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes(nn);
+    cudaGraphGetNodes(graph, nodes.data(), &nn);
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+        if (kp.func == (void *)k_draw_streams) {
+            g->draw_node = nd;
+            g->draw_params = kp;
+            void **a = kp.kernelParams;
+            g->aB = *(long long *)a[0];
+            g->aoff = *(long long *)a[1];
+            g->ann = *(int *)a[2];
+            g->anu = *(int *)a[3];
+            g->aseed = *(unsigned long long *)a[4];
+            g->aiter = *(unsigned long long *)a[5];
+            g->adn = *(double **)a[6];
+            g->adu = *(double **)a[7];
+        }
+    }
+    void *argv[8] = {&g->aB, &g->aoff, &g->ann, &g->anu, &g->aseed, &g->aiter, &g->adn, &g->adu};
+    std::memcpy(g->argv, argv, sizeof argv);
+    g->draw_params.kernelParams = g->argv;
+    g->draw_params.extra = nullptr;
+    cudaError_t ei = g->draw_node ? cudaGraphInstantiate(&g->exec, graph, 0) : cudaErrorUnknown;
+    if (ei != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        cudaGetLastError();
+        delete g;
+        ch->last_key.clear();
+        return eager();
+    }
+    g->graph = graph;
+    ch->graphs.push_back(g);
+    return replay(g);
 }
 
 static int part_get(ChainPart *ch, double *par, double *OriginTraj, double *LatentTraj, double *coalLog,
@@ -1106,6 +1261,10 @@ struct lna_chains {
     // [niter][npar + 2][Bg] in the groups' own slot-major layout, so recording is three device-to-device copies
     std::vector<double *> hist;
     long long hist_niter = 0;
+    // free-running stream groups: the groups' streams are NOT joined after every step, so one group's latency-bound stages
+    // overlap another group's throughput-bound ones ACROSS iterations (chains of different groups never interact); the
+    // caller observes results through lna_chains_get / lna_chains_join
+    int free_running = 0;
 };
 
 // history slot of one iteration of one group: par (npar x Bg), then logOrigin (Bg), then coalLog (Bg)
@@ -1136,7 +1295,7 @@ static int chains_fork(lna_chains *ch) {
     return 0;
 }
 // ... and the user's stream after the groups
-static int chains_join(lna_chains *ch) {
+static int chains_join_now(lna_chains *ch) {
     if (ch->G == 1) return 0;
     for (int g = 0; g < ch->G; ++g) {
         CK(cudaEventRecord(ch->ev_out[g], ch->gpb[g]->stream));
@@ -1144,6 +1303,50 @@ static int chains_join(lna_chains *ch) {
     }
     return 0;
 }
+static int chains_join(lna_chains *ch) { return ch->free_running ? 0 : chains_join_now(ch); }
+
+// busy-wait of `ns` nanoseconds on one thread: offsets the stream groups against each other
+__global__ void k_delay(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+
+extern "C" int lna_chains_set_free_running(lna_chains *ch, int on) {
+    if (!ch) return fail("lna_chains_set_free_running: null chains");
+    cudaSetDevice(ch->pb->device);
+    if (ch->free_running && !on && chains_join_now(ch)) return -1;
+    if (on && !ch->free_running && ch->G > 1) {
+        // Identical groups started together stay in phase (all in their Metropolis stage, then all in the first slice phase,
+        // ...), which is the lock-step this mode is meant to break: group g starts g * stagger later, so that at any moment
+        // the groups are spread over the stages of an iteration.  LNA_STAGGER_US overrides the offset (0 = none).
+        double us = 700.0 / ch->G;
+        if (const char *e = getenv("LNA_STAGGER_US")) us = atof(e);
+        if (chains_fork(ch)) return -1;
+        for (int g = 1; g < ch->G && us > 0.0; ++g) {
+            k_delay<<<1, 1, 0, ch->gpb[g]->stream>>>((unsigned long long)(us * 1e3 * g));
+            if (launch_check(ch->gpb[g], "k_delay")) return -1;
+        }
+    }
+    ch->free_running = on ? 1 : 0;
+    return 0;
+}
+extern "C" int lna_chains_join(lna_chains *ch) {
+    if (!ch) return fail("lna_chains_join: null chains");
+    cudaSetDevice(ch->pb->device);
+    return chains_join_now(ch);
+}
+extern "C" int lna_chains_sync(lna_chains *ch) {
+    if (!ch) return fail("lna_chains_sync: null chains");
+    cudaSetDevice(ch->pb->device);
+    for (int g = 0; g < ch->G; ++g) CK(cudaStreamSynchronize(ch->gpb[g]->stream));
+    CK(cudaStreamSynchronize(ch->pb->stream));
+    return 0;
+}
+extern "C" int lna_chains_groups(const lna_chains *ch) { return ch ? ch->G : 0; }
 
 extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     if (!pb || B <= 0) {
@@ -1323,9 +1526,12 @@ extern "C" int lna_chains_step(lna_chains *ch, const lna_mcmc_opts *o, const dou
 extern "C" int lna_chains_step_rng(lna_chains *ch, const lna_mcmc_opts *o, uint64_t seed, uint64_t iteration,
                                    int64_t chain_offset) {
     if (!ch || !o) return fail("lna_chains_step_rng: null argument");
-    if (chains_fork(ch)) return -1;
-    for (int g = 0; g < ch->G; ++g)
-        if (part_step_rng(ch->part[g], o, seed, iteration, chain_offset + ch->off[g])) return -1;
+    if (!ch->free_running && chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g) {
+        ChainPart *pt = ch->part[g];
+        const int64_t off = chain_offset + ch->off[g];
+        if (part_step_graph(pt, 0, o, seed, iteration, off, [&] { return part_step_rng(pt, o, seed, iteration, off); })) return -1;
+    }
     return chains_join(ch);
 }
 
@@ -1354,9 +1560,13 @@ extern "C" int lna_chains_step_mcmc2(lna_chains *ch, const lna_mcmc2_opts *o, co
 extern "C" int lna_chains_step_mcmc2_rng(lna_chains *ch, const lna_mcmc2_opts *o, uint64_t seed, uint64_t iteration,
                                          int64_t chain_offset) {
     if (!ch || !o) return fail("lna_chains_step_mcmc2_rng: null argument");
-    if (chains_fork(ch)) return -1;
-    for (int g = 0; g < ch->G; ++g)
-        if (part_step_mcmc2_rng(ch->part[g], o, seed, iteration, chain_offset + ch->off[g])) return -1;
+    if (!ch->free_running && chains_fork(ch)) return -1;
+    for (int g = 0; g < ch->G; ++g) {
+        ChainPart *pt = ch->part[g];
+        const int64_t off = chain_offset + ch->off[g];
+        if (part_step_graph(pt, 1, o, seed, iteration, off, [&] { return part_step_mcmc2_rng(pt, o, seed, iteration, off); }))
+            return -1;
+    }
     return chains_join(ch);
 }
 

@@ -997,12 +997,16 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-// 53-bit uniform in the open interval (0,1), like unif_rand()
+// uniform in the OPEN interval (0,1), like unif_rand(): 52 random bits b -> (b + 1/2) 2^-52, every value exactly
+// representable (min 2^-53, max 1 - 2^-53)
 __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
-    const unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 11;  // 53 bits
-    return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+    const unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 12;  // 52 bits
+    return ((double)b + 0.5) * (1.0 / 4503599627370496.0);
 }
-// one thread per (chain, pair of outputs): normals via Box-Muller, uniforms directly
+// one thread per (chain, pair of outputs): normals via Box-Muller, uniforms directly.
+// Philox key = the 64-bit seed alone; counter = (iteration[31:0], iteration[47:32] << 16 | q, chain[31:0], chain[63:32]):
+// seed, chain, iteration and slot occupy disjoint bits, so no two (seed, chain, iteration, q) share a block
+// (the host checks q < 2^16 and iteration < 2^48).
 __global__ void k_draw_streams(long long B, long long chain_offset, int n_norm, int n_unif, unsigned long long seed,
                                unsigned long long iteration, double *normals, double *uniforms) {
     const int npair_n = (n_norm + 1) / 2, npair_u = (n_unif + 1) / 2, per = npair_n + npair_u;
@@ -1012,8 +1016,8 @@ __global__ void k_draw_streams(long long B, long long chain_offset, int n_norm, 
     const int q = (int)(idx % per);
     const unsigned long long chain = (unsigned long long)(chain_offset + c);
     uint32_t r[4];
-    philox4x32_10((uint32_t)iteration, (uint32_t)(iteration >> 32), (uint32_t)q, (uint32_t)(chain >> 32),
-                  (uint32_t)seed ^ (uint32_t)chain, (uint32_t)(seed >> 32), r);
+    philox4x32_10((uint32_t)iteration, ((uint32_t)(iteration >> 32) << 16) | (uint32_t)q, (uint32_t)chain,
+                  (uint32_t)(chain >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
     const double a = u01(r[0], r[1]), b = u01(r[2], r[3]);
     if (q < npair_n) {
         const double rad = sqrt(-2.0 * log(a));

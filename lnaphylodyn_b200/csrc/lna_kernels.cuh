@@ -11,33 +11,36 @@ namespace lna {
 template <int kModel, bool kStore>
 __global__ void __launch_bounds__(128, 4)
 k_full_loglik(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, View param,
-              View initial, View origin, FullOut out, double *coalLog, int *status) {
+              View initial, View origin, FullOut out, double *coalLog, int *status, int group) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(P, smem, true);
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    // chain-shared inputs: `group` consecutive items (the proposals of one chain) read the same initial state and the
+    // same latent increments (item bc of `initial` / `origin`); group = 1 is the per-item layout
+    const long long bc = group > 1 ? b / group : b;
     int st = 0;
     double ll;
     ChFromParam chs{param, b, P.nparam};
     if (kModel == 0) {
         const double R0 = param.at(b, P.iR0), gam = param.at(b, 1);
         if (origin.ok()) {
-            EpsFromView eps{origin, b, P.k};
-            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
+            EpsFromView eps{origin, bc, P.k};
+            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(bc, 0), initial.at(bc, 1), out, b, ll, st);
         } else {
             EpsZero eps;
-            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(b, 0), initial.at(b, 1), out, b, ll, st);
+            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(bc, 0), initial.at(bc, 1), out, b, ll, st);
         }
     } else {
         const double R0 = param.at(b, P.iR0), mu = param.at(b, 1), gam = param.at(b, 2);
         if (origin.ok()) {
-            EpsFromView eps{origin, b, P.k};
-            seir_full_eval<kStore>(P, SD, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
-                                   initial.at(b, 2), out, b, ll, st);
+            EpsFromView eps{origin, bc, P.k};
+            seir_full_eval<kStore>(P, SD, T, chs, eps, R0, mu, gam, initial.at(bc, 0), initial.at(bc, 1),
+                                   initial.at(bc, 2), out, b, ll, st);
         } else {
             EpsZero eps;
-            seir_full_eval<kStore>(P, SD, T, chs, eps, R0, mu, gam, initial.at(b, 0), initial.at(b, 1),
-                                   initial.at(b, 2), out, b, ll, st);
+            seir_full_eval<kStore>(P, SD, T, chs, eps, R0, mu, gam, initial.at(bc, 0), initial.at(bc, 1),
+                                   initial.at(bc, 2), out, b, ll, st);
         }
     }
     if (coalLog) coalLog[b] = ll;
@@ -624,16 +627,22 @@ __global__ void k_kingman(DevProb P, long long B, const double *traj, const doub
     if (lane == 0) loglik[b] = acc;
 }
 
-// Independent-DFMA microbenchmark for the FP64 roofline denominator: 8 independent chains/thread.
-__global__ void k_fp64_peak(int iters, double *sink) {
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
-           a7 = a0 + 7;
-    const double m = 1.0000001, c = 1e-7;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+// Independent-DFMA microbenchmark for the FP64 roofline denominator: 8 independent chains per thread, multiplier and
+// addend as kernel parameters (constant-bank operands: a DFMA with three distinct REGISTER sources issues at 2/3 rate,
+// tools/fp64_microbench.cu), time loop unrolled so that loop overhead does not compete for issue slots.  With 16 resident
+// warps per SM sub-partition this reads the pipe's rate: 64 lanes x 2 flop x SM clock per SM.
+__global__ void __launch_bounds__(512) k_fp64_peak(int iters, double m, double c, double *sink) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-9 + i;
+#pragma unroll 8
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
     }
-    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
     if (s == 12345.678) sink[0] = s;
 }
 

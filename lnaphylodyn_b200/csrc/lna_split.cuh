@@ -381,7 +381,7 @@ __device__ __forceinline__ void sir_split_E(SplitCtx &c, const DevProb &P, const
 template <bool kStore>
 __global__ void __launch_bounds__(96, 4)
 k_full_loglik_split(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, View param, View initial,
-                    View origin, FullOut out, double *coalLog, int *status) {
+                    View origin, FullOut out, double *coalLog, int *status, int group) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 0 = P, 1 = M, 2 = E
     SplitCtx sx = split_ctx(smem + full_eval_smem_bytes(tables_bytes(P.nch, P.k, P.n0), blockDim.x), lane);
@@ -390,8 +390,9 @@ k_full_loglik_split(const __grid_constant__ DevProb P, const __grid_constant__ S
     const long long b0 = (long long)blockIdx.x * 32 + lane;
     const bool on = b0 < B;
     const long long b = on ? b0 : 0;  // idle lanes evaluate item 0 and write nothing (the hand-overs are warp-wide)
+    const long long bc = group > 1 ? b / group : b;  // chain-shared initial state / latent increments (k_full_loglik)
     const double R0 = param.at(b, P.iR0), gam = param.at(b, 1);
-    const double S0 = initial.at(b, 0), I0 = initial.at(b, 1);
+    const double S0 = initial.at(bc, 0), I0 = initial.at(bc, 1);
     double ll = kSentinel;
     int st = 0;
     if (role == 0) {
@@ -401,7 +402,7 @@ k_full_loglik_split(const __grid_constant__ DevProb P, const __grid_constant__ S
     } else {
         ChFromParam chs{param, b, P.nparam};
         if (origin.ok()) {
-            EpsFromView eps{origin, b, P.k};
+            EpsFromView eps{origin, bc, P.k};
             sir_split_E<kStore>(sx, P, T, chs, eps, R0, gam, S0, I0, out, b, on, ll, st);
         } else {
             EpsZero eps;

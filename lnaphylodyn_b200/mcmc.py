@@ -226,9 +226,14 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
     warmup2 = int(options.get("warmup2") or 100000)
     burn1 = int(options.get("burn1", 5000))
     nch = len(np.ravel(changetime))
-    par_ids = [int(v) for v in dict(options.get("parIdlist") or {"a": 2, "b": 3, "c": 4, "d": 5 + nch}).values()][:3]
-    is_log = [int(v) for v in dict(options.get("isLoglist") or {"a": 1, "b": 0, "c": 1, "d": 0}).values()][:3]
-    pr_ids = [int(v) for v in dict(options.get("priorIdlist") or {"a": 1, "b": 2, "c": 3, "d": 5}).values()][:3]
+    # Update_Param_each is called with parIdlist[-4], isLoglist[-4], priorIdlist[-4] (R/LNA_chpt_slice.R:611-612): the
+    # FOURTH entry is dropped, whatever the length of the lists
+    drop4 = lambda seq: [v for q, v in enumerate(seq) if q != 3]
+    par_ids = drop4([int(v) for v in dict(options.get("parIdlist") or {"a": 2, "b": 3, "c": 4, "d": 5 + nch}).values()])
+    is_log = drop4([int(v) for v in dict(options.get("isLoglist") or {"a": 1, "b": 0, "c": 1, "d": 0}).values()])
+    pr_ids = drop4([int(v) for v in dict(options.get("priorIdlist") or {"a": 1, "b": 2, "c": 3, "d": 5}).values()])
+    if not (len(par_ids) == len(is_log) == len(pr_ids)) or len(par_ids) > 4:
+        raise LnaError("General_MCMC2: parameters do not match")
     entries = tuple((pid - 1, lg, prid) for pid, lg, prid in zip(par_ids, is_log, pr_ids))  # R is 1-based
     setting = MCMC_setup_general(coal_obs, times, t_correct, N, gridsize, niter, burn, thin, changetime, DEMS, prior,
                                  proposal, control, likelihood, model, Index, nparam, options.get("PCOV"))
@@ -248,9 +253,9 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
     uv = [float(v) for v in updateVec]
     joint_entries = tuple((jidx, lg, prid) for jidx, lg, prid, on in
                           zip((1, 2, 3, 4), (1, 0, 1, 0), (1, 2, 3, 5), (uv[0], uv[1], uv[2], uv[4])) if on > 0)
-    if uv[3] > 0:
-        raise LnaError("General_MCMC2: updateVec[4] (mu) has no parameter in the SIR model (the R code stops with "
-                       "'priors do not match')")
+    # updateVec[4] (mu) has no parameter in the SIR model: the R code stops with 'priors do not match' INSIDE
+    # update_Param_joint, i.e. only once an iteration reaches the joint stage (the default warmup2 = 100000 never does)
+    joint_invalid = uv[3] > 0
     d = len(joint_entries)
     par_cols = [ch.npar - 1 if j == 4 else j for j, _, _ in joint_entries]
     o3 = chm.make_joint_opts(pr, joint_entries, update_chpt=upd_chpt, update_traj=int(updateVec[6]) == 1)
@@ -264,6 +269,9 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
     _begin_history(ch, niter)
     for i in range(1, niter + 1):
         joint = i >= max(warmup2, burn1)
+        if joint and joint_invalid:
+            raise LnaError("General_MCMC2: priors do not match (updateVec[4] (mu) has no parameter in the SIR model; "
+                           f"reached at iteration {i} >= warmup2)")
         if not fix_pcov and (i == warmup2 or (i > warmup2 and i % up == 0)):
             _fetch_history(ch, rec)  # (rows < i - 1 are recorded; the adaptation reads the chain's own past)
             # proposal covariance from the chain's own history, rows floor(i/3) .. i-1 of `params` (:608-630)

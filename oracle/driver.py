@@ -31,7 +31,8 @@ def init_state(g, par, OriginTraj):
     lat = orc.TransformTraj(npl["Ode"], OriginTraj, npl["FT"])
     cl = orc.volz_loglik_nh2(g.init, lat, npl["betaN"], g.t_correct, g.x_i[2:4])
     return {"par": par, "OriginTraj": np.array(OriginTraj, dtype=np.float64), "FT": npl["FT"], "Ode": npl["Ode"],
-            "betaN": npl["betaN"], "LatentTraj": lat, "coalLog": cl, "logOrigin": 0.0,
+            "betaN": npl["betaN"], "LatentTraj": lat, "coalLog": cl,
+            "logOrigin": -float(np.sum(np.asarray(OriginTraj, dtype=np.float64) ** 2)) / 2,  # general_change_point.R:530
             "n_full": 0, "n_cheap": 0, "n_mh_accept": 0}
 
 

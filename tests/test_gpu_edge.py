@@ -167,3 +167,18 @@ def test_pipelined_full_evaluation_odd_shapes(changepoint, monkeypatch, gridsize
             assert np.array_equal(out["0"][key], out["1"][key]), key
         assert np.array_equal(out["0"]["FT"]["A"], out["1"]["FT"]["A"]) and np.array_equal(out["0"]["FT"]["Sigma"], out["1"]["FT"]["Sigma"])
         assert np.all(np.isfinite(out["1"]["Ode"]))
+
+
+def test_problem_create_rejects_layouts_the_reference_cannot_run(api, changepoint):
+    """x_i[2], x_i[3] are parameter indices AND the S / I columns of the coalescent likelihood: out-of-range values are
+    refused at create time, and the fused evaluation only takes the layouts whose rhs and param_transform agree in the
+    reference, (nch, 2, 0, 1) for SIR and (nch, 3, 0, 2) for SEIR."""
+    from lnaphylodyn_b200._lib import LnaError
+    g = changepoint
+    for bad in ([39, 2, 0, 2], [39, 2, -1, 1], [39, 2, 3, 1]):
+        with pytest.raises(LnaError):
+            api.Problem(g.times, g.x_r, bad, g.gridsize, g.t_correct, g.init)
+    pb = api.Problem(g.times, g.x_r, [39, 2, 1, 0], g.gridsize, g.t_correct, g.init)   # in range, but not the reference's layout
+    par = g.final["par"].ravel()
+    with pytest.raises(LnaError, match="must be"):
+        pb.full_loglik(par[2:], par[:2], g.final["OriginTraj"])

@@ -167,10 +167,13 @@ def test_eslice_change_points_step_for_step(api, constant, width):
         assert relerr(d["LatentTraj"][b][:, 1:], o["LatentTraj"][:, 1:]) < 1e-9
 
 
-def test_chains_step_for_step(api, changepoint):
+@pytest.mark.parametrize("mh_pair", ["1", "0"])
+def test_chains_step_for_step(api, changepoint, monkeypatch, mh_pair):
     """B chains x 6 iterations of the General_MCMC_with_ESlice body (2 burn-in style + 4 full) from the
-    vignette's initial state: every chain must reproduce the oracle's chain step for step."""
+    vignette's initial state: every chain must reproduce the oracle's chain step for step -- with the two Metropolis
+    entries evaluated speculatively in one launch (small batches) and one after the other (batches that fill the machine)."""
     from lnaphylodyn_b200 import chains as chm
+    monkeypatch.setenv("LNA_MH_PAIR", mh_pair)
     g = changepoint
     B, iters, seed = 12, 6, 77
     par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
@@ -287,6 +290,57 @@ def test_device_rng_streams_and_replay(api, changepoint):
             ref[c] = driver.eslice_iteration(ref[c], g, driver.opts_from_golden(g, update_traj=it >= 1), nrm[c], unf[c])
             assert relerr(s["par"][c], ref[c]["par"]) < TOL and s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL)
             assert s["n_full_evals"][c] == ref[c]["n_full"]
+
+
+def test_device_rng_streams_do_not_alias_across_seeds(api, changepoint):
+    """Seed and chain index occupy different Philox words: (seed 0, chain 1) and (seed 1, chain 0) -- and every other pair
+    with seed ^ chain equal -- draw different streams, so replicate runs with seeds 0, 1, 2, ... are independent."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (8, 1)), g.setting("control.traj"))
+    streams = {s: ch.device_streams(seed=s, iteration=5) for s in range(4)}
+    rows = {}
+    for s, (n, u) in streams.items():
+        for c in range(8):
+            rows[(s, c)] = np.concatenate([n[c], u[c]])
+    keys = list(rows)
+    for i, a in enumerate(keys):
+        for b in keys[i + 1:]:
+            assert not np.any(rows[a] == rows[b]), (a, b)   # no shared value at any position
+    # iteration is a separate word too
+    n5, _ = ch.device_streams(seed=0, iteration=5)
+    n6, _ = ch.device_streams(seed=0, iteration=6)
+    assert not np.any(n5 == n6)
+    u = np.concatenate([streams[s][1].ravel() for s in streams])
+    assert u.min() > 0.0 and u.max() < 1.0
+
+
+def test_initial_log_origin_is_recorded(api, changepoint):
+    """MCMC_obj$logOrigin starts at -sum(OriginTraj^2)/2 (R/general_change_point.R:530) and update_Par_ESlice_combine does
+    not touch it, so iterations before the first trajectory slice update record that value in `l`."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    B = 6
+    rng = np.random.default_rng(5)
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    eps = 0.3 * rng.standard_normal((B, 40, 2))
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), eps)
+    want = -0.5 * np.sum(eps ** 2, axis=(1, 2))
+    assert np.allclose(ch.get()["logOrigin"], want, rtol=1e-13, atol=0)
+    ref = [driver.init_state(g, par0, eps[c]) for c in range(B)]
+    for it in range(2):   # burn-in style iterations: no trajectory update
+        nrm, unf = chm.draw_streams(B, ch.n_norm, 3, it)
+        ch.step(chm.vignette_opts(g, update_traj=False), nrm, unf)
+        s = ch.get()
+        for c in range(B):
+            ref[c] = driver.eslice_iteration(ref[c], g, driver.opts_from_golden(g, update_traj=False), nrm[c], unf[c])
+            assert s["logOrigin"][c] == pytest.approx(ref[c]["logOrigin"], rel=1e-13) == pytest.approx(want[c], rel=1e-13)
+            assert relerr(s["par"][c], ref[c]["par"]) < TOL
 
 
 def test_chain_stream_groups_equal_single_group(api, changepoint, monkeypatch):
