@@ -163,6 +163,35 @@ int lna_full_loglik_dev(lna_problem *pb, int64_t B, const double *param, const d
                         const double *OriginTraj, double *coalLog, int32_t *status,
                         double *Acube, double *Lcube, double *Ode_coarse, double *betaN, double *LatentTraj);
 
+/* Chain-shared form of the hot call: the `proposals` consecutive evaluations of a chain -- the body of the slice loop,
+ * ESlice_par_General :1588-1640, where every candidate of a chain is evaluated on the chain's OriginTraj and, unless
+ * ESS_vec[1] is set, its initial state -- read ONE initial state and ONE OriginTraj per chain.  param: (n_chains *
+ * proposals) x npt; initial: n_chains x p; OriginTraj: n_chains x (k x p); coalLog / status: n_chains * proposals.
+ * Same kernel and same bits as lna_full_loglik on the expanded inputs; a step ships 336 + (16 + 640) / proposals bytes per
+ * evaluation instead of 992 (SIR, nch = 39).  `_dev`: device pointers, asynchronous on the problem's stream; `_async`: host
+ * pointers, results valid after lna_problem_sync() (copies of call n+1 overlap the kernel of call n). */
+int lna_full_loglik_shared(lna_problem *pb, int64_t n_chains, int proposals, const double *param, const double *initial,
+                           const double *OriginTraj, double *coalLog, int32_t *status);
+int lna_full_loglik_shared_dev(lna_problem *pb, int64_t n_chains, int proposals, const double *param, const double *initial,
+                               const double *OriginTraj, double *coalLog, int32_t *status);
+int lna_full_loglik_shared_async(lna_problem *pb, int64_t n_chains, int proposals, const double *param,
+                                 const double *initial, const double *OriginTraj, double *coalLog, int32_t *status);
+
+/* Seasonal SIRS (src/SIRS_period.cpp), fused: per draw
+ *     log_like_trajSIRS(SdeTraj, coarse rows of ODE2(initial, t, param, period), SIRS_KOM_Filter(ODE2(...), param, gridsize,
+ *                       period), gridsize, t_correct)                                   (:174-193, :147-168, :50-79, :82-118)
+ * in ONE pass per draw, registers only -- the likelihood sweep over parameter draws of BASELINE configs[3].  Problem created
+ * with LNA_MODEL_SIRS_PERIOD (x_r[0] = period).  param: B x 4 (beta, gamma, mu, alpha); initial: B x 3, or 1 x 3 with
+ * initial_shared; SdeTraj: nrow x 4 column-major per item -- one per draw (sde_group = 1), one per sde_group consecutive draws,
+ * or ONE for the whole sweep (sde_group = 0); NULL = no density (then loglik must be NULL).  Optional outputs: Acube, Scube
+ * (B x 3*3*k: SIRS_KOM_Filter's A and Sigma), Ode_coarse (B x nrow x 4).  status: LNA_ST_NAN where the density is NaN. */
+int lna_sirs_loglik(lna_problem *pb, int64_t B, const double *param, const double *initial, int initial_shared,
+                    const double *SdeTraj, int sde_group, double *loglik, int32_t *status, double *Acube, double *Scube,
+                    double *Ode_coarse);
+int lna_sirs_loglik_dev(lna_problem *pb, int64_t B, const double *param, const double *initial, int initial_shared,
+                        const double *SdeTraj, int sde_group, double *loglik, int32_t *status, double *Acube, double *Scube,
+                        double *Ode_coarse);
+
 /* Update_Param (:1212-1243): FULL evaluation + MH test  log(unif[b]) < coalLog_new - coal_log[b] +
  * prior_proposal_offset[b].  accept[b] in {0,1}; outputs are written for every item (the caller
  * keeps them only where accept[b] == 1, like the R wrapper LNA_chpt_slice.R:254-262). */
@@ -370,6 +399,59 @@ int lna_chains_history_get(lna_chains *ch, double *par, double *l, double *l1);
 /* Device pointer to the B x 4 summary block (coalLog, logOrigin, n_full_evals, status) that is
  * all-gathered across GPUs; valid until the next step. */
 const double *lna_chains_summary_dev(lna_chains *ch);
+
+/* ---- multi-GPU ---------------------------------------------------------------------------------------
+ * Chains shard contiguously over GPUs (lna_shard); nothing is exchanged inside an iteration.  The one exchange is an
+ * all-gather of the per-chain summary rows (coalLog, logOrigin, n_full_evals, status) over NCCL (NVLink 5 / NVSwitch):
+ * ONE ncclAllGather on preallocated buffers for equal shards, one grouped launch of broadcasts for ragged ones -- no size
+ * exchange, no host synchronisation.  NCCL is bound at run time (dlopen libnccl.so.2, LNA_NCCL_LIB overrides).
+ *
+ * One process per GPU (torchrun / MPI): rank 0 calls lna_comm_unique_id, the 128 bytes are distributed by the launcher's
+ * own means (torch.distributed broadcast, MPI_Bcast, a file), every rank calls lna_comm_create. */
+typedef struct lna_comm lna_comm;
+#define LNA_COMM_ID_BYTES 128
+int lna_comm_available(void);                 /* NCCL version code (> 0) if libnccl could be bound, else 0 (see lna_last_error) */
+int lna_comm_unique_id(void *id128);
+lna_comm *lna_comm_create(int nranks, int rank, const void *id128, int device);
+void lna_comm_destroy(lna_comm *c);
+int lna_comm_rank(const lna_comm *c);
+int lna_comm_size(const lna_comm *c);
+/* rank r owns counts[r] doubles at offset sum(counts[0..r-1]) of recv_dev; asynchronous on `stream` (cudaStream_t) */
+int lna_comm_allgather(lna_comm *c, const double *send_dev, double *recv_dev, const int64_t *counts, void *stream);
+/* the summary rows of all B_total chains of the job, in global chain order, into out_dev (B_total x 4, this rank's device);
+ * this rank's batch must be its lna_shard of B_total.  Asynchronous on the problem's stream. */
+int lna_chains_allgather_summaries(lna_chains *ch, lna_comm *c, int64_t B_total, double *out_dev);
+
+/* One process driving several GPUs (an R session behind the Rcpp layer): B_total chains sharded over `devices`, one problem
+ * and one resident batch per device.  Every step only enqueues work, so one host thread keeps all devices busy; the Philox
+ * streams are keyed by the global chain index, so results do not depend on the number of devices. */
+typedef struct lna_multi lna_multi;
+lna_multi *lna_multi_create(const lna_cfg *cfg, const lna_init *init, int ndev, const int *devices, int64_t B_total);
+void lna_multi_destroy(lna_multi *m);
+int lna_multi_devices(const lna_multi *m);
+lna_chains *lna_multi_chains(lna_multi *m, int i);    /* the resident batch / problem of device slot i (borrowed) */
+lna_problem *lna_multi_problem(lna_multi *m, int i);
+int lna_multi_init(lna_multi *m, const double *par, const double *OriginTraj);             /* B_total x npar, B_total x k*p */
+int lna_multi_set_free_running(lna_multi *m, int on);
+int lna_multi_step_rng(lna_multi *m, const lna_mcmc_opts *opts, uint64_t seed, uint64_t iteration, int64_t chain_offset);
+int lna_multi_step_mcmc2_rng(lna_multi *m, const lna_mcmc2_opts *opts, uint64_t seed, uint64_t iteration,
+                             int64_t chain_offset);
+int lna_multi_set_joint_transform(lna_multi *m, int d, const double *T);
+int lna_multi_sync(lna_multi *m);
+int lna_multi_get(lna_multi *m, double *par, double *OriginTraj, double *LatentTraj, double *coalLog, double *logOrigin,
+                  int32_t *counters);
+int lna_multi_history_begin(lna_multi *m, int64_t niter);
+int lna_multi_history_record(lna_multi *m, int64_t i);
+int lna_multi_history_get(lna_multi *m, int64_t niter, double *par, double *l, double *l1);
+/* every device ends up with the B_total x 4 summary rows of all chains (NCCL over NVLink when use_nccl != 0; device-to-host
+ * copies otherwise, e.g. with one device listed twice); out_host (may be NULL) receives a host copy */
+int lna_multi_gather_summaries(lna_multi *m, int use_nccl, double *out_host);
+const double *lna_multi_gathered_dev(lna_multi *m, int i);
+
+/* Measurement: FULL evaluations the chains' stage kernels have EXECUTED since creation, speculative ones included (compare
+ * with the consumed count, counters[0] of lna_chains_get), and the number of warp-evaluations they occupied (a warp costs the
+ * FP64 pipe the same whatever its lane mask).  Synchronises. */
+int lna_chains_exec_counts(lna_chains *ch, uint64_t *evals, uint64_t *warp_evals);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* Debug timeline: with LNA_TIMELINE=1 in the environment every kernel launch is followed by a CUDA event on its stream;

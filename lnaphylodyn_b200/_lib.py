@@ -70,6 +70,11 @@ _SIGS = {
     "lna_full_loglik": (C.c_int, [_vp, _I64] + [_vp] * 10),
     "lna_full_loglik_dev": (C.c_int, [_vp, _I64] + [_vp] * 10),
     "lna_full_loglik_async": (C.c_int, [_vp, _I64] + [_vp] * 5),
+    "lna_full_loglik_shared": (C.c_int, [_vp, _I64, C.c_int] + [_vp] * 5),
+    "lna_full_loglik_shared_dev": (C.c_int, [_vp, _I64, C.c_int] + [_vp] * 5),
+    "lna_full_loglik_shared_async": (C.c_int, [_vp, _I64, C.c_int] + [_vp] * 5),
+    "lna_sirs_loglik": (C.c_int, [_vp, _I64, _vp, _vp, C.c_int, _vp, C.c_int] + [_vp] * 5),
+    "lna_sirs_loglik_dev": (C.c_int, [_vp, _I64, _vp, _vp, C.c_int, _vp, C.c_int] + [_vp] * 5),
     "lna_update_param": (C.c_int, [_vp, _I64] + [_vp] * 14),
     "lna_param_slice_update": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp]),
     "lna_param_slice_update_all2": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -97,9 +102,35 @@ _SIGS = {
     "lna_chains_join": (C.c_int, [_vp]),
     "lna_chains_sync": (C.c_int, [_vp]),
     "lna_chains_groups": (C.c_int, [_vp]),
+    "lna_chains_exec_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "lna_chains_history_begin": (C.c_int, [_vp, C.c_int64]),
     "lna_chains_history_record": (C.c_int, [_vp, C.c_int64]),
     "lna_chains_history_get": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "lna_comm_available": (C.c_int, []),
+    "lna_comm_unique_id": (C.c_int, [_vp]),
+    "lna_comm_create": (_vp, [C.c_int, C.c_int, _vp, C.c_int]),
+    "lna_comm_destroy": (None, [_vp]),
+    "lna_comm_rank": (C.c_int, [_vp]),
+    "lna_comm_size": (C.c_int, [_vp]),
+    "lna_comm_allgather": (C.c_int, [_vp, _vp, _vp, C.POINTER(_I64), _vp]),
+    "lna_chains_allgather_summaries": (C.c_int, [_vp, _vp, _I64, _vp]),
+    "lna_multi_create": (_vp, [C.POINTER(LnaCfg), C.POINTER(LnaInit), C.c_int, C.POINTER(C.c_int), _I64]),
+    "lna_multi_destroy": (None, [_vp]),
+    "lna_multi_devices": (C.c_int, [_vp]),
+    "lna_multi_chains": (_vp, [_vp, C.c_int]),
+    "lna_multi_problem": (_vp, [_vp, C.c_int]),
+    "lna_multi_init": (C.c_int, [_vp, _vp, _vp]),
+    "lna_multi_set_free_running": (C.c_int, [_vp, C.c_int]),
+    "lna_multi_step_rng": (C.c_int, [_vp, C.POINTER(LnaMcmcOpts), C.c_uint64, C.c_uint64, _I64]),
+    "lna_multi_step_mcmc2_rng": (C.c_int, [_vp, C.POINTER(LnaMcmc2Opts), C.c_uint64, C.c_uint64, _I64]),
+    "lna_multi_set_joint_transform": (C.c_int, [_vp, C.c_int, _vp]),
+    "lna_multi_sync": (C.c_int, [_vp]),
+    "lna_multi_get": (C.c_int, [_vp] + [_vp] * 6),
+    "lna_multi_history_begin": (C.c_int, [_vp, _I64]),
+    "lna_multi_history_record": (C.c_int, [_vp, _I64]),
+    "lna_multi_history_get": (C.c_int, [_vp, _I64, _vp, _vp, _vp]),
+    "lna_multi_gather_summaries": (C.c_int, [_vp, C.c_int, _vp]),
+    "lna_multi_gathered_dev": (_vp, [_vp, C.c_int]),
     "lna_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
     "lna_debug_timeline_dump": (C.c_int, [C.c_char_p]),
 }

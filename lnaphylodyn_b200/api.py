@@ -148,6 +148,25 @@ class Problem:
         return out
 
 
+    def full_loglik_shared(self, param, initial, OriginTraj, asynchronous=False):
+        """Chain-shared FULL evaluations (lna_full_loglik_shared): param (n_chains, proposals, npt), initial (n_chains, p),
+        OriginTraj (n_chains, k, p) -> coalLog, status of shape (n_chains, proposals).  Every proposal of a chain is
+        evaluated on the chain's initial state and latent increments -- the slice loop's body, ESlice_par_General :1588-1640."""
+        P = _d(param)
+        if P.ndim != 3 or P.shape[2] != self.npt:
+            raise LnaError(f"full_loglik_shared: param must be (n_chains, proposals, {self.npt})")
+        nc, m = P.shape[0], P.shape[1]
+        I = _d(initial).reshape(nc, self.p)
+        E, _ = self._mats(np.asarray(OriginTraj, dtype=np.float64).reshape(nc, self.k, self.p), (self.k, self.p))
+        cl, st = np.empty((nc, m)), np.zeros((nc, m), dtype=np.int32)
+        L = _lib.lib()
+        fn = L.lna_full_loglik_shared_async if asynchronous else L.lna_full_loglik_shared
+        check(fn(self.h, nc, m, _ptr(P), _ptr(I), _ptr(E), _ptr(cl), _ptr(st)), "lna_full_loglik_shared")
+        if asynchronous:
+            self.sync()
+        return {"coalLog": cl, "status": st}
+
+
 _cache = {}
 
 
@@ -694,6 +713,50 @@ def SIRS_KOM_Filter(OdeTraj, param, gridsize, period):
     A, S, st = np.empty((B, 9 * pb.k)), np.empty((B, 9 * pb.k)), np.zeros(B, dtype=np.int32)
     check(_lib.lib().lna_kf_param(pb.h, B, _ptr(Of), _ptr(P), 0, _ptr(A), _ptr(S), _ptr(st)), "lna_kf_param")
     return {"A": pb._unmats(A, (3, 3, pb.k), single), "Sigma": pb._unmats(S, (3, 3, pb.k), single)}
+
+
+def SIRS_loglik_sweep(param, initial, times, SdeTraj, gridsize, t_correct, period, want=("loglik",), device=0):
+    """The seasonal-SIRS likelihood sweep over parameter draws (BASELINE configs[3]), fused: per draw
+        log_like_trajSIRS(SdeTraj, Ode_Coarse_Slicer(ODE2(initial, times, param, period), gridsize),
+                          SIRS_KOM_Filter(ODE2(...), param, gridsize, period), gridsize, t_correct)
+    (SIRS_period.cpp:174-193, :147-168, :82-118) in one kernel launch, one thread per draw.  param (B, 4); initial (3,) shared
+    or (B, 3); SdeTraj (nrow, 4) shared by the sweep, (B, nrow, 4) per draw, or (B / m, nrow, 4) per m consecutive draws; None
+    with want = ("A", "Sigma", "Ode") for the moments only."""
+    pb = problem_for(times, [float(period)], [0, 4, 0, 1], gridsize, t_correct, None, "SIRS_period", device=device)
+    P = _d(param).reshape(-1, 4)
+    B = P.shape[0]
+    I = _d(initial)
+    shared_init = I.ndim == 1 or I.shape[0] == 1
+    I = I.reshape(-1, 3)
+    nrow, k = pb.nrow, pb.k
+    X, group = None, 1
+    if SdeTraj is not None:
+        X, one = pb._mats(SdeTraj, (nrow, 4))
+        if one or X.shape[0] == 1:
+            group = 0
+        elif X.shape[0] != B:
+            if B % X.shape[0]:
+                raise LnaError("SIRS_loglik_sweep: the number of draws must be a multiple of the number of trajectories")
+            group = B // X.shape[0]
+    ll = np.empty(B) if "loglik" in want else None
+    if ll is not None and X is None:
+        raise LnaError("SIRS_loglik_sweep: a log-likelihood needs SdeTraj")
+    st = np.zeros(B, dtype=np.int32)
+    A = np.empty((B, 9 * k)) if "A" in want else None
+    S = np.empty((B, 9 * k)) if "Sigma" in want else None
+    O = np.empty((B, nrow * 4)) if "Ode" in want else None
+    check(_lib.lib().lna_sirs_loglik(pb.h, B, _ptr(P), _ptr(I), int(shared_init), _ptr(X), int(group), _ptr(ll), _ptr(st),
+                                     _ptr(A), _ptr(S), _ptr(O)), "lna_sirs_loglik")
+    out = {"status": st}
+    if ll is not None:
+        out["loglik"] = ll
+    if A is not None:
+        out["A"] = pb._unmats(A, (3, 3, k), False)
+    if S is not None:
+        out["Sigma"] = pb._unmats(S, (3, 3, k), False)
+    if O is not None:
+        out["Ode"] = pb._unmats(O, (nrow, 4), False)
+    return out
 
 
 def log_like_trajSIRS(SdeTraj, OdeTraj, Filter, gridsize, t_correct):

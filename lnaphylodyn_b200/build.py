@@ -12,13 +12,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblnaphylodyn_b200.so")
 SOURCES = ["lna_capi.cu"]
-DEPS = ["lna_capi.cu", "lna_capi_eslice.inl", "lna_device.cuh", "lna_kernels.cuh", "lna_eslice.cuh", "lna_split.cuh",
+DEPS = ["lna_capi.cu", "lna_capi_eslice.inl", "lna_comm.inl", "lna_device.cuh", "lna_kernels.cuh", "lna_eslice.cuh", "lna_split.cuh",
+        "lna_sirs.cuh",
         os.path.join("..", "..", "include", "lnaphylodyn_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
+    "--shared", "-Xcompiler", "-fPIC", "-ldl",
     "-Xptxas", "-v",
 ]
 

@@ -136,6 +136,32 @@ class Chains:
                 "LatentTraj": pb._unmats(lat, (pb.nrow, pb.p + 1), False), "coalLog": cl, "logOrigin": lo,
                 "n_full_evals": cnt[:, 0], "n_cheap_evals": cnt[:, 1], "n_mh_accept": cnt[:, 2], "status": cnt[:, 3]}
 
+    def step_mcmc2_rng(self, opts, seed, iteration, chain_offset=0):
+        """One General_MCMC2 iteration on device-drawn streams."""
+        check(_lib.lib().lna_chains_step_mcmc2_rng(self.h, C.byref(opts), int(seed), int(iteration), int(chain_offset)),
+              "lna_chains_step_mcmc2_rng")
+
+    def latent(self):
+        pb, B = self.pb, self.B
+        lat = np.empty((B, pb.nrow * (pb.p + 1)))
+        check(_lib.lib().lna_chains_get(self.h, None, None, _ptr(lat), None, None, None), "lna_chains_get")
+        return pb._unmats(lat, (pb.nrow, pb.p + 1), False)
+
+    def history_begin(self, niter):
+        check(_lib.lib().lna_chains_history_begin(self.h, int(niter)), "lna_chains_history_begin")
+
+    def history_record(self, i):
+        check(_lib.lib().lna_chains_history_record(self.h, int(i)), "lna_chains_history_record")
+
+    def history_get(self, par, l, l1):
+        check(_lib.lib().lna_chains_history_get(self.h, _ptr(par), _ptr(l), _ptr(l1)), "lna_chains_history_get")
+
+    def exec_counts(self):
+        """(FULL evaluations executed incl. speculative ones, warp-evaluations executed) since creation."""
+        e, w = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().lna_chains_exec_counts(self.h, C.byref(e), C.byref(w)), "lna_chains_exec_counts")
+        return int(e.value), int(w.value)
+
     def summary_ptr(self):
         self.join()
         return _lib.lib().lna_chains_summary_dev(self.h)
@@ -174,23 +200,32 @@ def shard_range(B, rank, world):
     return b.value, e.value
 
 
-def gather_summaries(local, group=None):
-    """All-gather the per-chain summary rows (coalLog, logOrigin, n_full_evals, status) of every rank,
-    in global chain order.  `local`: torch tensor (B_local, 4) on this rank's device (NCCL) or on the CPU
-    (gloo).  Shards may differ by one chain, so the gather is padded to the largest shard."""
+def gather_summaries(local, B_total=None, group=None):
+    """All-gather the per-chain summary rows (coalLog, logOrigin, n_full_evals, status) of every rank, in global chain
+    order, through torch.distributed (NCCL on device tensors, gloo on CPU tensors: the host-logic tests).  ONE
+    all_gather_into_tensor on a buffer padded to the largest shard; the shard sizes come from lna_shard(B_total), not from
+    an exchange.  B_total defaults to equal shards.  (Inside the library the same exchange is lna_chains_allgather_summaries
+    over ncclAllGather: comm.py.)"""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    n, cols = local.shape
+    if B_total is None:
+        B_total = n * world
+    sizes = [shard_range(B_total, r, world) for r in range(world)]
+    sizes = [e - b for b, e in sizes]
+    if sizes[dist.get_rank(group)] != n:
+        raise LnaError(f"gather_summaries: this rank holds {n} rows, its shard of {B_total} is {sizes[dist.get_rank(group)]}")
     mx = max(sizes)
-    pad = torch.zeros((mx, local.shape[1]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
-    return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
+    if mx == n and min(sizes) == mx:
+        out = torch.empty((world * n, cols), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = torch.zeros((mx, cols), dtype=local.dtype, device=local.device)
+    pad[:n] = local
+    out = torch.empty((world * mx, cols), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * mx:r * mx + s] for r, s in enumerate(sizes)], dim=0)
 
 
 # ------------------------------------------------------------------------------------------------

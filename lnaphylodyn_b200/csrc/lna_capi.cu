@@ -22,6 +22,7 @@
 #include "lna_kernels.cuh"
 #include "lna_split.cuh"
 #include "lna_eslice.cuh"
+#include "lna_sirs.cuh"
 
 using namespace lna;
 
@@ -94,6 +95,7 @@ struct lna_problem {
     std::vector<int> cellCnt, evStart;
     std::vector<void *> owned;
     Scratch scratch;
+    double *sinO = nullptr, *sinF = nullptr;  // seasonal SIRS: sin(2 pi t / period), sin(t / period * 2 pi) on the fine grid
     int64_t launches = 0;
     size_t tab_bytes = 0;
     // host-buffer pipeline: inputs of chunk i+1 are copied on `copy_stream` while chunk i computes
@@ -336,6 +338,23 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
         P.cellY = yy;
     }
     pb->tab_bytes = tables_bytes(P.nch, P.k, P.n0);
+    if (cfg->model == LNA_MODEL_SIRS_PERIOD) {
+        // beta(t)'s seasonal factor on the shared time grid, with the reference's two argument forms and its value of pi
+        // (SIRS_period.cpp:4, :8, :62, :133)
+        const double pi = 3.14159265358979323846264338327950288, period = P.N;
+        std::vector<double> so(P.nt), sf(P.nt);
+        for (int i = 0; i < P.nt; ++i) {
+            so[i] = std::sin(2 * pi * pb->times[i] / period);
+            sf[i] = std::sin(pb->times[i] / period * 2 * pi);
+        }
+        pb->sinO = dev_upload(pb, so.data(), so.size());
+        pb->sinF = dev_upload(pb, sf.data(), sf.size());
+        if (!pb->sinO || !pb->sinF) {
+            fail("lna_problem_create: device allocation failed");
+            lna_problem_destroy(pb);
+            return nullptr;
+        }
+    }
     return pb;
 }
 
@@ -785,6 +804,68 @@ extern "C" int lna_full_loglik_async(lna_problem *pb, int64_t B, const double *p
     return full_loglik_chunked(pb, B, param, initial, OriginTraj, coalLog, status, /*async=*/true);
 }
 
+// ---- fused seasonal-SIRS evaluation (configs[3]) ----------------------------------------------------------------------------
+static int sirs_dev_impl(lna_problem *pb, int64_t B, const double *param, const double *initial, int initial_shared,
+                         const double *sde, int sde_group, double *loglik, int32_t *status, double *A, double *S, double *ode) {
+    const DevProb &P = pb->dp;
+    if (B <= 0) return 0;
+    const long long nO = (long long)P.nrow * 4, cube = 9LL * P.k;
+    const View vp = item_view(param, 4), vi{initial, initial_shared ? 0 : 3, 1};
+    const View vs{sde, sde_group == 0 ? 0 : nO, 1};
+    SirsOut out{item_out(A, cube), item_out(S, cube), item_out(ode, nO)};
+    const bool store = A || S || ode;
+    const int block = pick_block(pb, B);
+    const unsigned grid = nblk(B, block);
+    const size_t sm = pb->tab_bytes;
+    if (store)
+        k_sirs_full<true><<<grid, block, sm, pb->stream>>>(P, pb->sinO, pb->sinF, B, vp, vi, vs, sde_group, out, loglik, status);
+    else
+        k_sirs_full<false><<<grid, block, sm, pb->stream>>>(P, pb->sinO, pb->sinF, B, vp, vi, vs, sde_group, out, loglik, status);
+    return launch_check(pb, "k_sirs_full");
+}
+
+static int sirs_args(lna_problem *pb, int64_t B, const void *param, const void *initial, const void *sde, int sde_group,
+                     const void *loglik, const char *what) {
+    if (!pb) return fail("null problem");
+    if (pb->dp.model != LNA_MODEL_SIRS_PERIOD) return fail("%s: needs a problem created with LNA_MODEL_SIRS_PERIOD", what);
+    if (B > 0 && (!param || !initial)) return fail("%s: param/initial must not be null", what);
+    if (sde_group < 0) return fail("%s: sde_group must be >= 0", what);
+    if (loglik && !sde) return fail("%s: a log-likelihood needs the trajectory SdeTraj", what);
+    if (sde_group > 1 && B % sde_group != 0) return fail("%s: B must be a multiple of sde_group", what);
+    return 0;
+}
+
+extern "C" int lna_sirs_loglik_dev(lna_problem *pb, int64_t B, const double *param, const double *initial, int initial_shared,
+                                   const double *SdeTraj, int sde_group, double *loglik, int32_t *status, double *Acube,
+                                   double *Scube, double *Ode_coarse) {
+    if (sirs_args(pb, B, param, initial, SdeTraj, sde_group, loglik, "lna_sirs_loglik_dev")) return -1;
+    cudaSetDevice(pb->device);
+    return sirs_dev_impl(pb, B, param, initial, initial_shared, SdeTraj, sde_group, loglik, status, Acube, Scube, Ode_coarse);
+}
+
+extern "C" int lna_sirs_loglik(lna_problem *pb, int64_t B, const double *param, const double *initial, int initial_shared,
+                               const double *SdeTraj, int sde_group, double *loglik, int32_t *status, double *Acube,
+                               double *Scube, double *Ode_coarse) {
+    if (sirs_args(pb, B, param, initial, SdeTraj, sde_group, loglik, "lna_sirs_loglik")) return -1;
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    const size_t nB = (size_t)B, nO = (size_t)P.nrow * 4, cube = 9 * (size_t)P.k;
+    const size_t n_sde = sde_group == 0 ? 1 : (sde_group == 1 ? nB : nB / (size_t)sde_group);
+    Stage s(pb);
+    const double *dpar = s.in(param, nB * 4), *dini = s.in(initial, initial_shared ? 3 : nB * 3), *dsde = s.in(SdeTraj, n_sde * nO);
+    double *dll = s.out(loglik, nB);
+    int32_t *dst = s.out(status, nB);
+    double *dA = s.out(Acube, nB * cube), *dS = s.out(Scube, nB * cube), *dode = s.out(Ode_coarse, nB * nO);
+    if (!s.ok) return fail("lna_sirs_loglik: device staging failed");
+    if (sirs_dev_impl(pb, B, dpar, dini, initial_shared, dsde, sde_group, dll, dst, dA, dS, dode)) return -1;
+    s.back(loglik, dll, nB);
+    s.back(status, dst, nB);
+    s.back(Acube, dA, nB * cube);
+    s.back(Scube, dS, nB * cube);
+    s.back(Ode_coarse, dode, nB * nO);
+    return s.finish("lna_sirs_loglik");
+}
+
 // ---- chain-shared form of the hot call -------------------------------------------------------------------------------------
 static int shared_args(lna_problem *pb, int64_t n_chains, int proposals, const void *param, const void *initial,
                        const void *origin, const void *coalLog, const char *what) {
@@ -1100,3 +1181,4 @@ extern "C" double lna_measure_fp64_peak(int device, int iters) {
 }
 
 #include "lna_capi_eslice.inl"
+#include "lna_comm.inl"

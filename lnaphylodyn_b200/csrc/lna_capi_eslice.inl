@@ -575,6 +575,7 @@ struct ChainPart {  // one stream-group of a resident chain batch
     std::vector<void *> owned;
     double *stage_n = nullptr, *stage_u = nullptr;  // staging for host-pointer steps
     size_t n_norm = 0, n_unif = 0;
+    unsigned long long *exec = nullptr;      // [2] executed evaluations / warp-evaluations (CandArgs::exec_count)
     double *jT = nullptr, *jnew = nullptr;  // joint Metropolis step: [B][16] transforms (padded 4 x 4), [B][4] proposed values
     int jd = 0;
     // CUDA graphs of whole iterations on device-drawn streams (one per distinct option set): the ~14 launches of an
@@ -663,6 +664,8 @@ static ChainPart *part_create(lna_problem *pb, int64_t B, int64_t planB, double 
     const size_t stage_unif = std::max<size_t>(LNA_ITER_UNIF, LNA_ITER2_UNIF);
     ch->stage_n = chains_alloc<double>(ch, nB * ch->n_norm);
     ch->stage_u = chains_alloc<double>(ch, nB * stage_unif);
+    ch->exec = chains_alloc<unsigned long long>(ch, 2);
+    if (ch->exec) cudaMemsetAsync(ch->exec, 0, 2 * sizeof(unsigned long long), pb->stream);
     ch->jT = chains_alloc<double>(ch, nB * 16);
     ch->jnew = chains_alloc<double>(ch, nB * 4);
     if (!ch->par || !ch->par_alt || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
@@ -736,6 +739,7 @@ static void chains_base_args(ChainPart *ch, View normals, View uniforms, CandArg
     a.n_evals = ch->cb.n_evals;
     a.status = ch->cb.status;
     a.accept = ch->cb.accept;
+    a.exec_count = ch->exec;
 }
 
 static int chains_ensure_scratch(ChainPart *ch, int W) {
@@ -1358,7 +1362,9 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     lna_chains *ch = new lna_chains();
     ch->pb = pb;
     ch->B = B;
-    ch->G = B >= 2048 ? 2 : 1;
+    // two stream groups from 8192 chains on (measured with the iterations replayed from CUDA graphs: one group is faster up
+    // to 4096 chains, 1.08 vs 1.16 ms per iteration there; two win from 8192, profiles/r2_eslice_timeline.md)
+    ch->G = B >= 8192 ? 2 : 1;
     if (const char *e = getenv("LNA_CHAIN_GROUPS")) ch->G = std::max(1, std::min(8, atoi(e)));
     if (ch->G > B) ch->G = 1;
     const DevProb &P = pb->dp;
@@ -1586,3 +1592,20 @@ extern "C" int lna_chains_get(lna_chains *ch, double *par, double *OriginTraj, d
 }
 
 extern "C" const double *lna_chains_summary_dev(lna_chains *ch) { return ch ? ch->summary : nullptr; }
+
+extern "C" int lna_chains_exec_counts(lna_chains *ch, uint64_t *evals, uint64_t *warp_evals) {
+    if (!ch) return fail("lna_chains_exec_counts: null chains");
+    uint64_t tot[2] = {0, 0};
+    for (int g = 0; g < ch->G; ++g) {
+        ChainPart *pt = ch->part[g];
+        cudaSetDevice(pt->pb->device);
+        unsigned long long h[2] = {0, 0};
+        CK(cudaStreamSynchronize(pt->pb->stream));
+        CK(cudaMemcpy(h, pt->exec, sizeof h, cudaMemcpyDeviceToHost));
+        tot[0] += h[0];
+        tot[1] += h[1];
+    }
+    if (evals) *evals = tot[0];
+    if (warp_evals) *warp_evals = tot[1];
+    return 0;
+}

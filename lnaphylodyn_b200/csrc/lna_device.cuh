@@ -405,7 +405,7 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const SegDt &SD
     const double h2 = P.h2, dt6 = P.dt6;
     const int g = P.g, k = P.k, nrow = P.nrow;
     const double invN = P.invN;
-    (void)SD;
+    const bool seg_const = k <= kSegConst;
     double R0cum = R0;
     ChCursor<ChSrc> cur(chs, T.chidx, P.nch);
     cur.advance(0, R0cum);
@@ -420,8 +420,9 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const SegDt &SD
         o.put(b, 3 * nrow + r, d);
     };
     auto volz_row = [&](int r, double a, double c, double d) {
-        const double st3[3] = {a, c, d};
-        va.row(P, T, r, st3[P.idxS], st3[P.idxI], beta, (a < 0.0) | (c < 0.0) | (d < 0.0));
+        // (selects, not an indexed local array: no stack frame)
+        const double vS = P.idxS == 0 ? a : (P.idxS == 1 ? c : d), vI = P.idxI == 0 ? a : (P.idxI == 1 ? c : d);
+        va.row(P, T, r, vS, vI, beta, (a < 0.0) | (c < 0.0) | (d < 0.0));
     };
     if (kStore) {
         if (out.ode.ok()) put_row(out.ode, 0, S, Ex, I);
@@ -434,13 +435,20 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const SegDt &SD
         // F0 row-major f[r][c]; Sigma symmetric: s00 s01 s02 s11 s12 s22
         double f00 = 1, f01 = 0, f02 = 0, f10 = 0, f11 = 1, f12 = 0, f20 = 0, f21 = 0, f22 = 1;
         double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
-        const double dts = T.dt_seg[seg];
-        const double e0 = eps.at(seg, 0), e1 = eps.at(seg, 1), e2 = eps.at(seg, 2);
+        // latent increments of this interval: asynchronous copy into the thread's shared-memory slot now, read at the end
+        // of the interval (like sir_full_eval: a register load would be waited for BEFORE the time loop)
+        const bool staged = T.eps_slot != nullptr && eps.stage(seg, 3, T.eps_slot);
+        double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+        if (!staged) {
+            e0 = eps.at(seg, 0);
+            e1 = eps.at(seg, 1);
+            e2 = eps.at(seg, 2);
+        }
         int s = seg * g;
         const int s_end = s + g;
-        while (s < s_end) {
-          if (cur.advance(s, R0cum)) beta = (R0cum * gam) * invN;
-          const int run_end = min(s_end, cur.next_s);
+        // per-segment dt from the parameter block (uniform-register operand) when k <= kSegConst, else shared memory
+        auto run = [&](const double dts, const int run_end) {
+          LNA_DO_PRAGMA(unroll LNA_UNROLL)
           for (; s < run_end; ++s) {
             const double bI = beta * I, bS = beta * S;
             const double h0 = bS * I, h1 = mu * Ex, hh2 = gam * I;
@@ -479,6 +487,18 @@ __device__ __forceinline__ void seir_full_eval(const DevProb &P, const SegDt &SD
             Ex = fma(dt6, fma(2.0, k2E + k3E, k1E + k4E), Ex);
             I = fma(dt6, fma(2.0, k2I + k3I, k1I + k4I), I);
           }
+        };
+        while (s < s_end) {
+            if (cur.advance(s, R0cum)) beta = (R0cum * gam) * invN;
+            const int run_end = min(s_end, cur.next_s);
+            if (seg_const) run(SD.v[seg], run_end);
+            else run(T.dt_seg[seg], run_end);
+        }
+        if (staged) {
+            cp_async_wait_all();
+            e0 = T.eps_slot[0];
+            e1 = T.eps_slot[1];
+            e2 = T.eps_slot[2];
         }
         // 3x3 Cholesky of Sigma + 1e-8 I (upper U as dpotrf, L = U')
         const double c00 = s00 + kJitter;

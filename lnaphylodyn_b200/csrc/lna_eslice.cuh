@@ -183,6 +183,9 @@ struct CandArgs {
     const int *chain_list;  // null = chains 0..B-1
     const int *n_list;      // device count of chain_list entries
     int *next_list, *next_count;
+    // measurement: [0] += evaluations executed (lanes that ran a FULL evaluation, speculative ones included),
+    // [1] += warp-evaluations executed (what the FP64 pipe is charged: a warp costs the same whatever its lane mask)
+    unsigned long long *exec_count;
 };
 
 // Whitened scalars of Param_Slice_update_all2 (:1287-1296) and their rotated images (:1299-1311).
@@ -247,6 +250,13 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
     // one FULL evaluation of this lane's candidate; `on` = the lane really has one (the pipelined version runs all lanes,
     // because its hand-over is warp-wide, and only suppresses the stores of the idle ones)
     auto evaluate = [&](auto &chs, const EpsFromView &eps, const PropScalars &x, long long slot, bool on, double &ll, int &st) {
+        if (a.exec_count && writer) {
+            const unsigned am = __activemask(), m = __ballot_sync(am, on);
+            if (m && (threadIdx.x & 31) == __ffs(am) - 1) {
+                atomicAdd(a.exec_count, (unsigned long long)__popc(m));
+                atomicAdd(a.exec_count + 1, 1ull);
+            }
+        }
         if (kSplit) {
             if (role == 0) sir_split_P(sx, P, T, x.R0, x.gam, x.S0, x.I0, ll, st);
             else if (role == 1) sir_split_M(sx, P, SD, T, x.R0, x.gam, ll, st);

@@ -130,30 +130,39 @@ def _record(ch, rec, i, thin, want_traj):
     """params[i,] = par; l[i] = logOrigin; l1[i] = coalLog; tjs[,,i/thin] = LatentTraj  (LNA_chpt_slice.R:839-845).
     par, l, l1 are recorded ON THE DEVICE (lna_chains_history_record: device-to-device copies, no host round trip per
     iteration) and fetched once by _fetch_history; only the thinned trajectories cross to the host as they are produced."""
-    pb, B = ch.pb, ch.B
-    L = _lib.lib()
-    check(L.lna_chains_history_record(ch.h, int(i)), "lna_chains_history_record")
+    ch.history_record(i)
     if want_traj:
-        lat = np.empty((B, pb.nrow * (pb.p + 1)))
-        check(L.lna_chains_get(ch.h, None, None, api._ptr(lat), None, None, None), "lna_chains_get")
-        rec["traj"][:, (i + 1) // thin - 1] = pb._unmats(lat, (pb.nrow, pb.p + 1), False)
+        rec["traj"][:, (i + 1) // thin - 1] = ch.latent()
 
 
 def _begin_history(ch, niter):
-    check(_lib.lib().lna_chains_history_begin(ch.h, int(niter)), "lna_chains_history_begin")
+    ch.history_begin(niter)
 
 
 def _fetch_history(ch, rec):
     """The device-side records into rec["par"] (B, niter, npar), rec["l"], rec["l1"] (B, niter)."""
-    check(_lib.lib().lna_chains_history_get(ch.h, api._ptr(rec["par"]), api._ptr(rec["l"]), api._ptr(rec["l1"])),
-          "lna_chains_history_get")
+    ch.history_get(rec["par"], rec["l"], rec["l1"])
+
+
+def _make_chains(setting, init, device, devices):
+    """The resident batch: one GPU (`device`), or sharded over `devices` (an int = that many GPUs from 0, or a list) and
+    driven by this process through lna_multi."""
+    if devices is None:
+        pb = _problem(setting, device)
+        return pb, chm.Chains(pb, init["par"], init["OriginTraj"], free_running=True)
+    from . import comm
+    devs = list(range(int(devices))) if isinstance(devices, (int, np.integer)) else [int(d) for d in devices]
+    mc = comm.MultiChains({"times": setting["times"], "x_r": setting["x_r"], "x_i": setting["x_i"],
+                           "gridsize": setting["gridsize"], "t_correct": setting["t_correct"], "init": setting["Init"]},
+                          init["par"], init["OriginTraj"], devs)
+    return mc.pb, mc
 
 
 def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn=0, thin=5, changetime=(),
                              DEMS=("S", "I"), prior=None, proposal=None, control=None, ESS_vec=(1, 1, 1, 1, 1, 1, 1),
                              likelihood="volz", model="SIR", Index=(0, 1), nparam=2, method="seq", options=None,
-                             ESS_vec2=None, verbose=False, *, n_chains=1, seed=0, device=0, chain_offset=0, squeeze=True,
-                             init_rng=None):
+                             ESS_vec2=None, verbose=False, *, n_chains=1, seed=0, device=0, devices=None, chain_offset=0,
+                             squeeze=True, init_rng=None):
     """R/LNA_chpt_slice.R:723-849 for `n_chains` chains.  Iterations i < options["burn1"] run the Metropolis entries
     and the parameter slice update with ESS_vec[5] switched off (ESS_temp); later ones add the trajectory slice update.
     Returns {par (chains, niter, npar), Trajectory (chains, niter/thin, nrow, p+1), l, l1, MCMC_setting, MCMC_obj}."""
@@ -181,8 +190,7 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
     setting = MCMC_setup_general(coal_obs, times, t_correct, N, gridsize, niter, burn, thin, changetime, DEMS, prior,
                                  proposal, control, likelihood, model, Index, nparam, options.get("PCOV"))
     init = MCMC_initialize_general(setting, n_chains, init_rng or np.random.default_rng([int(seed), 7]), device)
-    pb = _problem(setting, device)
-    ch = chm.Chains(pb, init["par"], init["OriginTraj"])
+    pb, ch = _make_chains(setting, init, device, devices)
     pr, po = _lists(setting["prior"], _PRIOR_ORDER, "prior"), _lists(setting["proposal"], _PROP_ORDER, "proposal")
     ess_temp = list(ESS_vec)
     ess_temp[4] = 0
@@ -215,7 +223,7 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
 def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn=0, thin=5, changetime=(),
                   DEMS=("S", "I"), prior=None, proposal=None, control=None, updateVec=(1, 1, 1, 1, 1, 1, 1),
                   likelihood="volz", model="SIR", Index=(0, 1), nparam=2, method="seq", options=None, verbose=False, *,
-                  n_chains=1, seed=0, device=0, chain_offset=0, squeeze=True, init_rng=None):
+                  n_chains=1, seed=0, device=0, devices=None, chain_offset=0, squeeze=True, init_rng=None):
     """R/LNA_chpt_slice.R:508-693 for `n_chains` chains: stage 1 (i < burn1: scalar Metropolis entries + change-point
     slice update) and stage 2 (burn1 <= i < warmup2: + hyper-parameter Metropolis step when updateVec[5] == 0.5, +
     trajectory slice update).  Like the R code it stores the trajectory of EVERY iteration in slot i (so `niter / thin`
@@ -238,8 +246,7 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
     setting = MCMC_setup_general(coal_obs, times, t_correct, N, gridsize, niter, burn, thin, changetime, DEMS, prior,
                                  proposal, control, likelihood, model, Index, nparam, options.get("PCOV"))
     init = MCMC_initialize_general(setting, n_chains, init_rng or np.random.default_rng([int(seed), 7]), device)
-    pb = _problem(setting, device)
-    ch = chm.Chains(pb, init["par"], init["OriginTraj"])
+    pb, ch = _make_chains(setting, init, device, devices)
     pr, po = _lists(setting["prior"], _PRIOR_ORDER, "prior"), _lists(setting["proposal"], _PROP_ORDER, "proposal")
     upd_chpt = int(updateVec[5]) == 1
     o1 = chm.make_mcmc2_opts(pr, po, entries, update_hyper=False, update_chpt=upd_chpt, update_traj=False)
@@ -288,7 +295,7 @@ def General_MCMC2(coal_obs, times, t_correct, N, gridsize=1000, niter=1000, burn
             pcov = (beta * sigma_n + (1 - beta) * np.eye(d) * 0.0001 / d) * tune
             ch.set_joint_transform(chm.mvrnorm_transform(pcov))
         opts_i = o3 if joint else (o1 if i < burn1 else o2)
-        check(L.lna_chains_step_mcmc2_rng(ch.h, C.byref(opts_i), int(seed), i, int(chain_offset)), "lna_chains_step_mcmc2_rng")
+        ch.step_mcmc2_rng(opts_i, seed, i, chain_offset)
         _record(ch, rec, i - 1, thin, i % thin == 0)
         if verbose and i % 100 == 0:
             print(i, float(np.mean(ch.get()["coalLog"])))

@@ -344,19 +344,22 @@ def test_initial_log_origin_is_recorded(api, changepoint):
 
 
 def test_chain_stream_groups_equal_single_group(api, changepoint, monkeypatch):
-    """Batches of >= 2048 chains run as two stream groups (overlap of latency-bound and throughput-bound
-    launches): per chain the result must not depend on the grouping, and must match the oracle."""
+    """Large batches run as several stream groups (overlap of latency-bound and throughput-bound launches), optionally
+    free-running (not joined after every step) and with the iterations replayed from CUDA graphs: per chain the result must
+    not depend on the grouping, the joining or the replay, and must match the oracle."""
     from lnaphylodyn_b200 import chains as chm
     g = changepoint
-    B, iters = 2101, 3
+    B, iters = 2101, 5
     par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
                            g.setting("control.ch"), g.setting("control.hyper")])
     pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
-    grouped = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    monkeypatch.setenv("LNA_CHAIN_GROUPS", "3")
+    grouped = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"), free_running=True)
+    assert grouped.groups == 3
     monkeypatch.setenv("LNA_CHAIN_GROUPS", "1")
     single = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
     monkeypatch.delenv("LNA_CHAIN_GROUPS")
-    ref = {c: driver.init_state(g, par0, g.setting("control.traj")) for c in (0, 1049, 1050, 1051, 2100)}
+    ref = {c: driver.init_state(g, par0, g.setting("control.traj")) for c in (0, 699, 700, 701, 1400, 2100)}
     for it in range(iters):
         opts = chm.vignette_opts(g, update_traj=it >= 1)
         nrm, unf = grouped.device_streams(seed=3, iteration=it)

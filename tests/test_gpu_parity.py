@@ -316,6 +316,118 @@ def test_seasonal_sirs_model_variant(api):
         assert np.isfinite(l_o) and l_d == pytest.approx(l_o, rel=1e-7)
 
 
+@pytest.mark.parametrize("n_chains,proposals", [(1, 1), (3, 16), (700, 7), (4096, 16)])
+def test_chain_shared_full_loglik_equals_per_item(api, changepoint, n_chains, proposals):
+    """lna_full_loglik_shared (one initial state and one OriginTraj per chain, `proposals` parameter vectors each) is the
+    per-item call on the expanded inputs, bit for bit -- synchronous (chunked above 32k evaluations), asynchronous, and for
+    odd shapes; spot-checked against the oracle."""
+    g = changepoint
+    rng = np.random.default_rng(n_chains)
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    par0 = g.final["par"].ravel()
+    param = np.tile(par0[2:], (n_chains, proposals, 1))
+    param[:, :, 0] *= np.exp(0.05 * rng.standard_normal((n_chains, proposals)))
+    param[:, :, 1] *= np.exp(0.05 * rng.standard_normal((n_chains, proposals)))
+    param[:, :, 2:41] *= np.exp(0.02 * rng.standard_normal((n_chains, proposals, 39)))
+    initial = np.tile(par0[:2], (n_chains, 1)) * np.exp(0.01 * rng.standard_normal((n_chains, 2)))
+    eps = g.final["OriginTraj"][None] + 0.1 * rng.standard_normal((n_chains, 40, 2))
+    sh = pb.full_loglik_shared(param, initial, eps)
+    flat = pb.full_loglik(param.reshape(-1, 42), np.repeat(initial, proposals, axis=0), np.repeat(eps, proposals, axis=0))
+    assert np.array_equal(sh["coalLog"].ravel(), np.atleast_1d(flat["coalLog"]))
+    assert np.array_equal(sh["status"].ravel(), np.atleast_1d(flat["status"]))
+    sh2 = pb.full_loglik_shared(param, initial, eps, asynchronous=True)
+    assert np.array_equal(sh2["coalLog"], sh["coalLog"]) and np.array_equal(sh2["status"], sh["status"])
+    cfg, ini = orc.Cfg(g.x_r, g.x_i, 42), orc.Init(g.init)
+    for c in sorted({0, n_chains // 2, n_chains - 1}):
+        ref, _ = orc.full_loglik_batch(cfg, ini, param[c], np.tile(initial[c], (proposals, 1)), g.times, g.gridsize,
+                                       np.tile(eps[c], (proposals, 1, 1)), g.t_correct)
+        assert relerr(sh["coalLog"][c], ref) < TOL
+
+
+def _sirs_draws(rng, B):
+    return np.column_stack([3e-6 * np.exp(0.1 * rng.standard_normal(B)), 0.2 * np.exp(0.1 * rng.standard_normal(B)),
+                            0.02 * np.exp(0.1 * rng.standard_normal(B)), rng.uniform(0.1, 0.5, B)])
+
+
+def _sirs_data(t, rng, truth=(3e-6, 0.2, 0.02, 0.3), init=(9e4, 100.0, 9900.0), scale=30.0):
+    """A 'data' trajectory for the sweep: the ODE at the true parameters plus a perturbation on the conserved-population plane."""
+    co = orc.Ode_Coarse_Slicer(orc.ODE2(np.array(init), t, np.array(truth), 40.0), 50)
+    dev = rng.standard_normal((41, 3)) * scale
+    dev[:, 2] = -dev[:, 0] - dev[:, 1]
+    dev[0] = 0
+    sde = co.copy()
+    sde[:, 1:] += dev
+    return sde
+
+
+def _sirs_oracle(init, t, param, sde, t_correct=90.0):
+    ode = orc.ODE2(np.asarray(init, dtype=float), t, param, 40.0)
+    kf = orc.SIRS_KOM_Filter(ode, param, 50, 40.0)
+    co = orc.Ode_Coarse_Slicer(ode, 50)
+    return orc.log_like_trajSIRS(sde, co, kf, 50, t_correct), kf, co
+
+
+def test_seasonal_sirs_fused_sweep_vs_oracle(api):
+    """The fused seasonal-SIRS evaluation (one thread per draw: ODE2 -> SIRS_KOM_Filter -> log_like_trajSIRS in registers)
+    against the oracle's composition of the three exports, draw by draw: moments at 1e-10 relative to the largest entry of
+    each interval's matrix, coarse ODE at 1e-10.  The density goes through the closed-form pseudo-inverse of a covariance
+    whose entries cancel to its rank-2 part (m11 - m01 - lambda in the eigenvectors): the reference's own formula turns a
+    1e-14 relative change of Sigma into up to ~1e-9 of the log-density on these draws, so the log-density is held to 1e-8
+    relative here and to 1e-12 when BOTH sides are given the same moments (test_seasonal_sirs_model_variant)."""
+    t = np.linspace(0, 100, 2001)
+    rng = np.random.default_rng(32)
+    B = 48
+    param = _sirs_draws(rng, B)
+    init = np.array([9e4, 100.0, 9900.0])
+    sde = _sirs_data(t, rng)
+    d = api.SIRS_loglik_sweep(param, init, t, sde, 50, 90.0, 40.0, want=("loglik", "A", "Sigma", "Ode"))
+    assert not d["status"].any()
+    worst = 0.0
+    for b in range(B):
+        l_o, kf, co = _sirs_oracle(init, t, param[b], sde)
+        assert relerr(d["Ode"][b][:, 1:], co[:, 1:]) < TOL and np.array_equal(d["Ode"][b][:, 0], co[:, 0])
+        for i in range(40):
+            assert np.max(np.abs(d["A"][b][:, :, i] - kf["A"][:, :, i])) < TOL * np.max(np.abs(kf["A"][:, :, i]))
+            assert np.max(np.abs(d["Sigma"][b][:, :, i] - kf["Sigma"][:, :, i])) < TOL * np.max(np.abs(kf["Sigma"][:, :, i]))
+        assert np.isfinite(l_o)
+        worst = max(worst, abs(d["loglik"][b] - l_o) / abs(l_o))
+    assert worst < 1e-8, worst
+    # per-draw initial states and per-draw / per-group trajectories are the same evaluation
+    d2 = api.SIRS_loglik_sweep(param, np.tile(init, (B, 1)), t, np.tile(sde, (B, 1, 1)), 50, 90.0, 40.0)
+    d3 = api.SIRS_loglik_sweep(param, init, t, np.tile(sde, (B // 8, 1, 1)), 50, 90.0, 40.0)
+    assert np.array_equal(d2["loglik"], d["loglik"]) and np.array_equal(d3["loglik"], d["loglik"])
+    # rows later than t_correct do not count (:104)
+    early = api.SIRS_loglik_sweep(param, init, t, sde, 50, 50.0, 40.0)["loglik"]
+    l_e, _, _ = _sirs_oracle(init, t, param[0], sde, 50.0)
+    assert early[0] == pytest.approx(l_e, rel=1e-8) and not np.allclose(early, d["loglik"])
+
+
+def test_seasonal_sirs_fused_sweep_full_size(api):
+    """BASELINE configs[3]: 16 384 draws per sweep in ONE launch.  Size-independent properties: the sweep equals the same
+    draws evaluated in small batches (bit for bit: a draw's result does not depend on its neighbours or its position),
+    permuting the draws permutes the results, duplicated draws give duplicated results; spot-checked against the oracle."""
+    t = np.linspace(0, 100, 2001)
+    rng = np.random.default_rng(33)
+    B = 16384
+    param = _sirs_draws(rng, B)
+    param[1000] = param[7]
+    init = np.array([9e4, 100.0, 9900.0])
+    sde = _sirs_data(t, rng)
+    full = api.SIRS_loglik_sweep(param, init, t, sde, 50, 90.0, 40.0)["loglik"]
+    assert np.all(np.isfinite(full)) and full[1000] == full[7]
+    perm = rng.permutation(B)
+    assert np.array_equal(api.SIRS_loglik_sweep(param[perm], init, t, sde, 50, 90.0, 40.0)["loglik"], full[perm])
+    for lo in (0, 4096 - 13, 16384 - 100):
+        part = api.SIRS_loglik_sweep(param[lo:lo + 100], init, t, sde, 50, 90.0, 40.0)["loglik"]
+        assert np.array_equal(part, full[lo:lo + 100])
+    for b in (0, 1, 5000, 12345, 16383):
+        l_o, _, _ = _sirs_oracle(init, t, param[b], sde)
+        assert full[b] == pytest.approx(l_o, rel=1e-8)
+    # the likelihood surface is informative: the sweep ranks draws near the truth above draws far from it
+    near = np.argsort(np.abs(np.log(param[:, 0] / 3e-6)) + np.abs(np.log(param[:, 1] / 0.2)))
+    assert full[near[:200]].mean() > full[near[-200:]].mean()
+
+
 def test_async_host_buffer_evaluation(changepoint):
     """lna_full_loglik_async: several calls in flight on alternating staging sets give, after lna_problem_sync, exactly what
     the synchronous call gives -- including when the same staging set is reused (4 calls) and for a batch below the

@@ -27,7 +27,7 @@ def _worker(rank, world, port, B, out_dir):
     nrm, unf = chm.draw_streams(e - b, 7, seed=5, iteration=3, chain_offset=b)
     # a fake per-chain summary that encodes the global chain id
     local = torch.tensor(np.stack([np.arange(b, e), nrm[:, 0], unf[:, 0], np.full(e - b, rank)], axis=1))
-    allsum = chm.gather_summaries(local)
+    allsum = chm.gather_summaries(local, B_total=B)
     np.save(os.path.join(out_dir, f"r{rank}.npy"), allsum.numpy())
     np.save(os.path.join(out_dir, f"n{rank}.npy"), nrm)
     dist.destroy_process_group()
