@@ -213,7 +213,7 @@ int lna_param_slice_update_all2(lna_problem *pb, int64_t B, const double *par_ol
 
 /* ESlice_par_General (:1532-1688), SIR (p = 2) only like the reference.  par_old: B x npar
  * (npar = 2 + npt); normals: B x (npar-1); uniforms: B x LNA_ESLICE_MAX_UNIF (u, theta draws).
- * prior8 = (priorList[[1]][1:2], ..., priorList[[4]][1:2]); ESS_vec7[6] must be 0.
+ * prior8 = (priorList[[1]][1:2], ..., priorList[[4]][1:2]); ESS_vec7[6] = 1: see lna_eslice_par_general_ex.
  * The candidates theta_1..theta_20 depend only on the uniforms, so they are evaluated
  * speculatively, `spec_width` (1,2,4,8,16,32) per in-kernel wave, and the first one with loglike > logy
  * is taken: identical to the sequential loop.  spec_width = 0 picks a phase plan from the batch size
@@ -227,6 +227,20 @@ int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *par_old, co
                            double *betaN, double *LatentTraj, double *CoalLog, double *logOrigin,
                            int32_t *n_evals, int32_t *status);
 
+/* The same with the slot of the reference's result list the call above leaves out: OriginTraj_new (B x k*p; may be NULL).
+ * It equals OriginTraj unless ESS_vec7[6] = 1, the self-mixing branch (:1576-1578, 1660-1662): there every candidate whose
+ * New_Param_List succeeds replaces OriginTraj_new by OriginTraj cos(theta) + OriginTraj_new sin(theta), a running scalar
+ * multiple of OriginTraj; the candidates of a chain are then evaluated one per wave in order (the multiple depends on which
+ * earlier candidates failed their factorisation), and the k*p extra normals the reference draws and discards are simply
+ * not taken.  The R caller (update_Par_ESlice_combine, R/LNA_chpt_slice.R:456-472) never stores OriginTraj_new, and
+ * neither do the resident chains. */
+int lna_eslice_par_general_ex(lna_problem *pb, int64_t B, const double *par_old, const double *OriginTraj,
+                              const double *prior8, const int32_t *ESS_vec7, const double *coal_log,
+                              const double *normals, const double *uniforms, int spec_width,
+                              double *par_new, double *Acube, double *Lcube, double *Ode_coarse,
+                              double *betaN, double *LatentTraj, double *CoalLog, double *logOrigin,
+                              int32_t *n_evals, int32_t *status, double *OriginTraj_new);
+
 /* ESlice_general_NC (:1690-1778), volz likelihood.  f_cur: B x (k x p); normals: B x (k*p)
  * (column-major k x p like arma::randn(k,p)); uniforms: B x LNA_ESLICE_MAX_UNIF.
  * coal_log[b] == -99999999 recomputes the current likelihood like the reference. */
@@ -235,6 +249,17 @@ int lna_eslice_general_nc(lna_problem *pb, int64_t B, const double *f_cur, const
                           const double *coal_log, const double *normals, const double *uniforms,
                           double *LatentTraj, double *OriginTraj_new, double *logOrigin, double *CoalLog,
                           int32_t *n_evals, int32_t *status);
+
+/* ESlice_general_NC with volz = FALSE (:1717-1721, 1733-1760): the slice loop on the Kingman likelihood
+ * coal_loglik3(init, LogTraj(newTraj), t_correct, lambda, Index(1)) -- LogTraj (SIR_LNA.cpp:40-46) logs the trajectory and
+ * coal_loglik3 logs it again, so the value is NaN as soon as I < 1, and a NaN ENDS the loop and is returned (status gets
+ * LNA_ST_NAN); the 20-shrink cap recomputes with volz_loglik_nh2 like the reference.  lambda: B.  coal_log must be the
+ * caller's current likelihood (-99999999 makes the reference treat the increment matrix as a trajectory: refused). */
+int lna_eslice_general_nc_kingman(lna_problem *pb, int64_t B, const double *f_cur, const double *Ode_coarse,
+                                  const double *Acube, const double *Lcube, const double *betaN,
+                                  const double *coal_log, const double *lambda, const double *normals,
+                                  const double *uniforms, double *LatentTraj, double *OriginTraj_new, double *logOrigin,
+                                  double *CoalLog, int32_t *n_evals, int32_t *status);
 
 /* ESlice_change_points (:1317-1409).  param: B x npt; normals: B x nch; uniforms: B x 22. */
 int lna_eslice_change_points(lna_problem *pb, int64_t B, const double *param, const double *initial,

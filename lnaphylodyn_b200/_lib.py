@@ -79,7 +79,9 @@ _SIGS = {
     "lna_param_slice_update": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp]),
     "lna_param_slice_update_all2": (C.c_int, [_vp, _I64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lna_eslice_par_general": (C.c_int, [_vp, _I64] + [_vp] * 7 + [C.c_int] + [_vp] * 10),
+    "lna_eslice_par_general_ex": (C.c_int, [_vp, _I64] + [_vp] * 7 + [C.c_int] + [_vp] * 11),
     "lna_eslice_general_nc": (C.c_int, [_vp, _I64] + [_vp] * 14),
+    "lna_eslice_general_nc_kingman": (C.c_int, [_vp, _I64] + [_vp] * 15),
     "lna_eslice_change_points": (C.c_int, [_vp, _I64] + [_vp] * 6 + [C.c_int] + [_vp] * 10),
     "lna_log_like_traj_general2": (C.c_int, [_vp, _I64] + [_vp] * 5),
     "lna_log_like_traj_sirs": (C.c_int, [_vp, _I64] + [_vp] * 5),

@@ -527,25 +527,26 @@ def ESlice_par_General(par_old, t, OriginTraj, priorList, x_r, x_i, init, gridsi
     ode, bn, lat = np.empty((B, nrow * (p + 1))), np.empty((B, nrow)), np.empty((B, nrow * (p + 1)))
     cl, lo = np.empty(B), np.empty(B)
     ne, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
-    check(_lib.lib().lna_eslice_par_general(pb.h, B, _ptr(P), _ptr(E), _ptr(pr), _ptr(ev), _ptr(cl0), _ptr(nrm),
-                                            _ptr(unf), int(spec_width), _ptr(par_new), _ptr(A), _ptr(Lc), _ptr(ode),
-                                            _ptr(bn), _ptr(lat), _ptr(cl), _ptr(lo), _ptr(ne), _ptr(st)),
+    org = np.empty((B, k * p))
+    check(_lib.lib().lna_eslice_par_general_ex(pb.h, B, _ptr(P), _ptr(E), _ptr(pr), _ptr(ev), _ptr(cl0), _ptr(nrm),
+                                               _ptr(unf), int(spec_width), _ptr(par_new), _ptr(A), _ptr(Lc), _ptr(ode),
+                                               _ptr(bn), _ptr(lat), _ptr(cl), _ptr(lo), _ptr(ne), _ptr(st), _ptr(org)),
           "lna_eslice_par_general")
     if single and (st[0] & ST_CHOL_FAIL):
         raise ValueError(CHOL_MSG)
     pick = (lambda a: a[0]) if single else (lambda a: a)
+    # OriginTraj = OriginTraj_new of the result list: the input, or its running self-mixture with ESS_vec[7] = 1 (:1660-1662)
     return {"betaN": pick(bn), "FT": {"A": pb._unmats(A, (p, p, k), single), "Sigma": pb._unmats(Lc, (p, p, k), single)},
             "OdeTraj": pb._unmats(ode, (nrow, p + 1), single), "par": pick(par_new),
             "LatentTraj": pb._unmats(lat, (nrow, p + 1), single), "CoalLog": pick(cl),
-            "OriginTraj": (E.reshape(B, p, k).transpose(0, 2, 1)[0] if single else E.reshape(B, p, k).transpose(0, 2, 1)),
+            "OriginTraj": pb._unmats(org, (k, p), single),
             "logOrigin": pick(lo), "n_evals": pick(ne), "status": pick(st)}
 
 
 def ESlice_general_NC(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, coal_log=-99999999.0,
                       gridsize=100, volz=False, model="SIR", transX="standard", *, normals, uniforms):
-    """LNA_functional.cpp:1690-1778 (volz=True path).  normals: k*p per chain, column-major k x p."""
-    if not volz:
-        raise LnaError("ESlice_general_NC(volz=False): the Kingman branch (LogTraj + coal_loglik3) is not built; reached only with likelihood != \"volz\", which no BASELINE config uses")
+    """LNA_functional.cpp:1690-1778.  normals: k*p per chain, column-major k x p.  volz=False: the Kingman branch
+    (coal_loglik3 of LogTraj(newTraj) with scale `lam`, :1733-1760; NaN as soon as I < 1, which ends the loop)."""
     O = np.asarray(OdeTraj, dtype=np.float64)
     single = O.ndim == 2
     times = O[:, 0] if single else O[0, :, 0]
@@ -565,9 +566,15 @@ def ESlice_general_NC(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10
     lat, org = np.empty((B, nrow * (p + 1))), np.empty((B, k * p))
     lo, cl = np.empty(B), np.empty(B)
     ne, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
-    check(_lib.lib().lna_eslice_general_nc(pb.h, B, _ptr(Ff), _ptr(Of), _ptr(Af), _ptr(Lf), _ptr(bn), _ptr(cl0),
-                                           _ptr(nrm), _ptr(unf), _ptr(lat), _ptr(org), _ptr(lo), _ptr(cl), _ptr(ne),
-                                           _ptr(st)), "lna_eslice_general_nc")
+    if volz:
+        check(_lib.lib().lna_eslice_general_nc(pb.h, B, _ptr(Ff), _ptr(Of), _ptr(Af), _ptr(Lf), _ptr(bn), _ptr(cl0),
+                                               _ptr(nrm), _ptr(unf), _ptr(lat), _ptr(org), _ptr(lo), _ptr(cl), _ptr(ne),
+                                               _ptr(st)), "lna_eslice_general_nc")
+    else:
+        lamv = np.ascontiguousarray(np.broadcast_to(_d(lam).ravel(), (B,)))
+        check(_lib.lib().lna_eslice_general_nc_kingman(pb.h, B, _ptr(Ff), _ptr(Of), _ptr(Af), _ptr(Lf), _ptr(bn), _ptr(cl0),
+                                                       _ptr(lamv), _ptr(nrm), _ptr(unf), _ptr(lat), _ptr(org), _ptr(lo),
+                                                       _ptr(cl), _ptr(ne), _ptr(st)), "lna_eslice_general_nc_kingman")
     pick = (lambda a: a[0]) if single else (lambda a: a)
     return {"LatentTraj": pb._unmats(lat, (nrow, p + 1), single), "OriginTraj": pb._unmats(org, (k, p), single),
             "logOrigin": pick(lo), "CoalLog": pick(cl), "n_evals": pick(ne), "status": pick(st)}

@@ -183,7 +183,13 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, 
     constexpr bool kIsEss = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT);
     if (!kIsEss) return launch_cand_one<kProp>(pb, B, W > 0 ? W : 1, a);
     SlicePhase ph[24];
-    const int nph = slice_plan(pb, planB, W, ph);
+    int nph = slice_plan(pb, planB, W, ph);
+    if (kProp == PROP_ESS_PAR && a0.ess[6]) {
+        // self-mixing OriginTraj (ESS_vec[6] = 1): candidate i's increments depend on which earlier candidates failed their
+        // factorisation, so the candidates of a chain are evaluated one per wave, in order, in ONE launch
+        ph[0] = {1, 0, 0};
+        nph = 1;
+    }
     if (nph > 1 && cudaMemsetAsync(cb.count, 0, sizeof(int) * 24, pb->stream) != cudaSuccess)
         return fail("memset failed");
     long long slot = 0;
@@ -275,20 +281,35 @@ extern "C" int lna_param_slice_update_all2(lna_problem *pb, int64_t B, const dou
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *par_old, const double *OriginTraj,
-                                      const double *prior8, const int32_t *ESS_vec7, const double *coal_log,
-                                      const double *normals, const double *uniforms, int spec_width, double *par_new,
-                                      double *Acube, double *Lcube, double *Ode_coarse, double *betaN,
-                                      double *LatentTraj, double *CoalLog, double *logOrigin, int32_t *n_evals,
-                                      int32_t *status) {
+// logOrigin and OriginTraj_new of the self-mixing branch: OriginTraj_new = scale * OriginTraj (:1660-1662, 1673-1678)
+__global__ void k_scale_origin(long long B, int n, const double *origin, const double *scale, double *origin_new, double *logOrigin) {
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= B) return;
+    const double sc = scale[c];
+    double lo = 0.0;
+    for (int e = lane; e < n; e += 32) {
+        const double v = origin[c * n + e] * sc;
+        if (origin_new) origin_new[c * n + e] = v;
+        lo -= 0.5 * v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(0xffffffffu, lo, o);
+    if (lane == 0 && logOrigin) logOrigin[c] = lo;
+}
+
+extern "C" int lna_eslice_par_general_ex(lna_problem *pb, int64_t B, const double *par_old, const double *OriginTraj,
+                                         const double *prior8, const int32_t *ESS_vec7, const double *coal_log,
+                                         const double *normals, const double *uniforms, int spec_width, double *par_new,
+                                         double *Acube, double *Lcube, double *Ode_coarse, double *betaN,
+                                         double *LatentTraj, double *CoalLog, double *logOrigin, int32_t *n_evals,
+                                         int32_t *status, double *OriginTraj_new) {
     if (!pb) return fail("null problem");
     if (B <= 0) return 0;
     if (check_sir_sampler(pb, "lna_eslice_par_general")) return -1;
     if (!par_old || !OriginTraj || !prior8 || !ESS_vec7 || !coal_log || !normals || !uniforms)
         return fail("lna_eslice_par_general: null input");
-    if (ESS_vec7[6] != 0)
-        return fail("lna_eslice_par_general: ESS_vec[7] = 1 (the reference's self-mixing OriginTraj branch, "
-                    "LNA_functional.cpp:1660-1662) is not supported");
+    const bool selfmix = ESS_vec7[6] != 0;
     const DevProb &P = pb->dp;
     const size_t nB = (size_t)B, npar = 2 + P.npt, kp = (size_t)P.k * P.p;
     const size_t nA = (size_t)P.p * P.p * P.k, nO = (size_t)P.nrow * (P.p + 1), nrow = P.nrow;
@@ -305,8 +326,10 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
     double *dpar = s.tmp<double>(nB * npar), *dA = s.tmp<double>(nB * nA), *dL = s.tmp<double>(nB * nA);
     double *dO = s.tmp<double>(nB * nO), *dbn = s.tmp<double>(nB * nrow), *dlat = s.tmp<double>(nB * nO);
     double *dlo = s.tmp<double>(nB), *dcl = s.tmp<double>(nB);
+    double *dsc = selfmix ? s.tmp<double>(nB) : nullptr, *don = (selfmix && OriginTraj_new) ? s.tmp<double>(nB * kp) : nullptr;
     CandBuf cb;
     if (!s.ok || !cand_alloc(pb, pb->scratch, s.slot, B, (long long)B * slice_plan_slots(pb, B, W), cb)) return fail("lna_eslice_par_general: device staging failed");
+    a.eps_scale = dsc;
     a.cand = cand_out(cb);
     a.win_slot = cb.win_slot;
     a.cand_ll = cb.cand_ll;
@@ -320,8 +343,13 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
         return -1;
     k_commit_par_wide<PROP_ESS_PAR><<<nblk((long long)(nB * npar), 256), 256, 0, pb->stream>>>(P, B, a, item_out(dpar, npar), dcl);
     if (launch_check(pb, "k_commit_par_wide")) return -1;
-    k_log_origin<<<nblk((long long)B * 32, 128), 128, 0, pb->stream>>>(B, (int)kp, a.origin, dlo);
-    if (launch_check(pb, "k_log_origin")) return -1;
+    if (selfmix) {
+        k_scale_origin<<<nblk((long long)B * 32, 128), 128, 0, pb->stream>>>(B, (int)kp, a.origin.base, dsc, don, dlo);
+        if (launch_check(pb, "k_scale_origin")) return -1;
+    } else {
+        k_log_origin<<<nblk((long long)B * 32, 128), 128, 0, pb->stream>>>(B, (int)kp, a.origin, dlo);
+        if (launch_check(pb, "k_log_origin")) return -1;
+    }
     s.back(par_new, dpar, nB * npar);
     s.back(Acube, dA, nB * nA);
     s.back(Lcube, dL, nB * nA);
@@ -332,7 +360,22 @@ extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *
     s.back(logOrigin, dlo, nB);
     s.back(n_evals, cb.n_evals, nB);
     s.back(status, cb.status, nB);
+    if (OriginTraj_new) {
+        if (selfmix) s.back(OriginTraj_new, don, nB * kp);
+        else s.back(OriginTraj_new, a.origin.base, nB * kp);  // OriginTraj_new = OriginTraj (:1580)
+    }
     return s.finish("lna_eslice_par_general");
+}
+
+extern "C" int lna_eslice_par_general(lna_problem *pb, int64_t B, const double *par_old, const double *OriginTraj,
+                                      const double *prior8, const int32_t *ESS_vec7, const double *coal_log,
+                                      const double *normals, const double *uniforms, int spec_width, double *par_new,
+                                      double *Acube, double *Lcube, double *Ode_coarse, double *betaN,
+                                      double *LatentTraj, double *CoalLog, double *logOrigin, int32_t *n_evals,
+                                      int32_t *status) {
+    return lna_eslice_par_general_ex(pb, B, par_old, OriginTraj, prior8, ESS_vec7, coal_log, normals, uniforms, spec_width,
+                                     par_new, Acube, Lcube, Ode_coarse, betaN, LatentTraj, CoalLog, logOrigin, n_evals, status,
+                                     nullptr);
 }
 
 extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double *param, const double *initial,
@@ -403,11 +446,40 @@ extern "C" int lna_eslice_change_points(lna_problem *pb, int64_t B, const double
     return 0;
 }
 
+static int eslice_general_nc_impl(lna_problem *pb, int64_t B, const double *f_cur, const double *Ode_coarse,
+                                  const double *Acube, const double *Lcube, const double *betaN,
+                                  const double *coal_log, const double *normals, const double *uniforms,
+                                  double *LatentTraj, double *OriginTraj_new, double *logOrigin, double *CoalLog,
+                                  int32_t *n_evals, int32_t *status, const double *lambda);
+
 extern "C" int lna_eslice_general_nc(lna_problem *pb, int64_t B, const double *f_cur, const double *Ode_coarse,
                                      const double *Acube, const double *Lcube, const double *betaN,
                                      const double *coal_log, const double *normals, const double *uniforms,
                                      double *LatentTraj, double *OriginTraj_new, double *logOrigin, double *CoalLog,
                                      int32_t *n_evals, int32_t *status) {
+    return eslice_general_nc_impl(pb, B, f_cur, Ode_coarse, Acube, Lcube, betaN, coal_log, normals, uniforms, LatentTraj,
+                                  OriginTraj_new, logOrigin, CoalLog, n_evals, status, nullptr);
+}
+
+extern "C" int lna_eslice_general_nc_kingman(lna_problem *pb, int64_t B, const double *f_cur, const double *Ode_coarse,
+                                             const double *Acube, const double *Lcube, const double *betaN,
+                                             const double *coal_log, const double *lambda, const double *normals,
+                                             const double *uniforms, double *LatentTraj, double *OriginTraj_new,
+                                             double *logOrigin, double *CoalLog, int32_t *n_evals, int32_t *status) {
+    if (!lambda || !coal_log) return fail("lna_eslice_general_nc_kingman: null lambda / coal_log");
+    for (int64_t b = 0; b < B; ++b)
+        if (coal_log[b] == -99999999.0)
+            return fail("lna_eslice_general_nc_kingman: coal_log = -99999999 makes the reference hand the increment matrix to "
+                        "coal_loglik3 as a trajectory (LNA_functional.cpp:1720); pass the current likelihood");
+    return eslice_general_nc_impl(pb, B, f_cur, Ode_coarse, Acube, Lcube, betaN, coal_log, normals, uniforms, LatentTraj,
+                                  OriginTraj_new, logOrigin, CoalLog, n_evals, status, lambda);
+}
+
+static int eslice_general_nc_impl(lna_problem *pb, int64_t B, const double *f_cur, const double *Ode_coarse,
+                                  const double *Acube, const double *Lcube, const double *betaN,
+                                  const double *coal_log, const double *normals, const double *uniforms,
+                                  double *LatentTraj, double *OriginTraj_new, double *logOrigin, double *CoalLog,
+                                  int32_t *n_evals, int32_t *status, const double *lambda) {
     if (!pb) return fail("null problem");
     if (B <= 0) return 0;
     if (check_sir_sampler(pb, "lna_eslice_general_nc")) return -1;
@@ -426,6 +498,8 @@ extern "C" int lna_eslice_general_nc(lna_problem *pb, int64_t B, const double *f
     a.ode = item_view(s.in(Ode_coarse, nB * nO), nO);
     a.betaN = item_view(s.in(betaN, nB * nrow), nrow);
     a.coal_log = s.in(coal_log, nB);
+    a.kingman = lambda != nullptr;
+    a.lambda = s.in(lambda, nB);
     double *dlat = s.tmp<double>(nB * nO), *dor = s.tmp<double>(nB * kp), *dcl = s.tmp<double>(nB), *dlo = s.tmp<double>(nB);
     int32_t *dne = s.tmp<int32_t>(nB), *dst = s.tmp<int32_t>(nB);
     if (!s.ok) return fail("lna_eslice_general_nc: device staging failed");
@@ -825,7 +899,6 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
     lna_problem *pb = ch->pb;
     cudaSetDevice(pb->device);
     const DevProb &P = pb->dp;
-    if (o->ESS_vec[6] != 0) return fail("lna_chains_step: ESS_vec[7] = 1 is not supported");
     const int W = o->spec_width;  // 0 = auto (two-phase when the machine-filling width is 16)
     if (chains_ensure_scratch(ch, W)) return -1;
     const bool general = o->n_mh > 0;
@@ -915,7 +988,6 @@ static int part_step_dev(ChainPart *ch, const lna_mcmc_opts *o, const double *no
     if (chains_stage<PROP_ESS_PAR>(ch, a, W)) return -1;
     if (o->update_traj && o->use_ess2) {
         // 3'. ESS_vec2: a second parameter slice update instead of the trajectory update (:826-833)
-        if (o->ESS_vec2[6] != 0) return fail("lna_chains_step: ESS_vec2[7] = 1 is not supported");
         chains_base_args(ch, View{normals + (npar - 1), sn, 1}, View{uniforms + ess_u + LNA_ESLICE_MAX_UNIF, su, 1}, a);
         for (int i = 0; i < 8; ++i) a.pr[i] = o->prior8[i];
         for (int i = 0; i < 7; ++i) a.ess[i] = o->ESS_vec2[i];

@@ -554,6 +554,14 @@ struct EpsFromView {
         return true;
     }
 };
+// OriginTraj scaled by one factor: the self-mixing branch of ESlice_par_General (ESS_vec[6] = 1, LNA_functional.cpp:1660-1662),
+// where the candidate's increments are OriginTraj * cos(theta) + (running OriginTraj_new) * sin(theta) = c * OriginTraj
+struct EpsScaled {
+    EpsFromView e;
+    double c;
+    __device__ __forceinline__ double at(int seg, int comp) const { return e.at(seg, comp) * c; }
+    __device__ __forceinline__ bool stage(int, int, double *) const { return false; }
+};
 struct EpsZero {
     __device__ __forceinline__ double at(int, int) const { return 0.0; }
     __device__ __forceinline__ bool stage(int, int, double *) const { return false; }

@@ -186,6 +186,10 @@ struct CandArgs {
     // measurement: [0] += evaluations executed (lanes that ran a FULL evaluation, speculative ones included),
     // [1] += warp-evaluations executed (what the FP64 pipe is charged: a warp costs the same whatever its lane mask)
     unsigned long long *exec_count;
+    // ESS_vec[6] = 1 (self-mixing OriginTraj, :1576-1578, 1660-1662): the accepted candidate's scale of OriginTraj per chain
+    // (output, may be null); such calls run one candidate per chain and wave (the scale depends on which earlier
+    // candidates failed their Cholesky factorisation)
+    double *eps_scale;
 };
 
 // Whitened scalars of Param_Slice_update_all2 (:1287-1296) and their rotated images (:1299-1311).
@@ -249,7 +253,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
                                 : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // one FULL evaluation of this lane's candidate; `on` = the lane really has one (the pipelined version runs all lanes,
     // because its hand-over is warp-wide, and only suppresses the stores of the idle ones)
-    auto evaluate = [&](auto &chs, const EpsFromView &eps, const PropScalars &x, long long slot, bool on, double &ll, int &st) {
+    auto evaluate = [&](auto &chs, const auto &eps, const PropScalars &x, long long slot, bool on, double &ll, int &st) {
         if (a.exec_count && writer) {
             const unsigned am = __activemask(), m = __ballot_sync(am, on);
             if (m && (threadIdx.x & 31) == __ffs(am) - 1) {
@@ -532,6 +536,10 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
         ThetaSeq ts;
         ts.init();
         bool done = !valid;
+        // ESS_vec[6] = 1: OriginTraj_new = OriginTraj cos(theta) + OriginTraj_new sin(theta) accumulates over the candidates
+        // whose New_Param_List succeeded, i.e. candidate i is evaluated on c_i OriginTraj, c_i = cos(theta_i) + c_{i-1} sin(theta_i)
+        constexpr bool kSelfMix = (kProp == PROP_ESS_PAR && W == 1 && !kSplit);
+        double eps_c = 1.0;
         for (int wave = 0;; ++wave) {
             const int i = a.first_cand + wave * W + w + 1;  // candidate number in the sequential loop
             // candidate kMaxCand+1 is the reference's cap: revert to the current parameters and recompute
@@ -565,7 +573,18 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
                 x.noop = 0;
                 // one instruction stream for shrink and revert candidates (no divergence inside the warp)
                 ChProp<kProp> chs{a.par, a.normals, cc, 4, x};
-                evaluate(chs, eps, x, t, active, ll, st);
+                bool mixed = false;
+                if constexpr (kSelfMix) {
+                    if (a.ess[6]) {
+                        const double c_try = (active && !is_revert) ? fma(eps_c, x.sn, x.ct) : 1.0;
+                        EpsScaled epsS{eps, c_try};
+                        evaluate(chs, epsS, x, t, active, ll, st);
+                        if (active && !is_revert && !(st & ST_CHOL_FAIL)) eps_c = c_try;  // (a failed candidate leaves it, :1641-1651)
+                        if (is_revert) eps_c = 1.0;
+                        mixed = true;
+                    }
+                }
+                if (!mixed) evaluate(chs, eps, x, t, active, ll, st);
             }
             const bool failed = active && (st & ST_CHOL_FAIL);
             // ESlice_par_General catches the exception and shrinks on (:1641-1651); ESlice_change_points
@@ -582,6 +601,7 @@ k_cand_eval(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD,
                     a.theta[c] = is_revert ? 0.0 : ts.th;
                     a.n_evals[c] = i;
                     a.status[c] = st | (is_revert ? ST_CAP_HIT : 0);
+                    if (kSelfMix && a.eps_scale) a.eps_scale[c] = eps_c;
                 }
                 done = true;
             }
@@ -690,6 +710,10 @@ struct TrajArgs {
     // mode 1: ESlice_general2 (:1783-1857): f_cur and `normals` are (k+1) x (p+1) TRAJECTORIES (current and the
     //         centred proposal drawn by Traj_sim_general3); the deviations from the ODE are rotated directly
     int mode;
+    // volz = FALSE (:1717-1721, 1733-1760): the Kingman likelihood coal_loglik3(LogTraj(newTraj), lambda) -- log(log I), NaN
+    // as soon as I < 1, and a NaN ends the loop -- with scale lambda[c]; the 20-cap still recomputes with volz_loglik_nh2
+    int kingman;
+    const double *lambda;
 };
 
 constexpr int kTrajWarps = 4;
@@ -785,6 +809,26 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
         return acc;
     };
 
+    // coal_loglik3 (:1016-1054) on LogTraj(newTraj) (SIR_LNA.cpp:40-46): cell c uses row n0k - c, f = log(log I)
+    const double lam = a.kingman ? a.lambda[c] : 1.0, llam = log(lam);
+    auto kingman = [&](double ct, double sn, bool &negall) -> double {
+        double acc = 0.0;
+        int neg_any = 0;
+        for (int r = lane; r < nrow; r += 32) {
+            const double S = oS[r] + fma(ct, XfS[r], sn * XvS[r]);
+            const double I = oI[r] + fma(ct, XfI[r], sn * XvI[r]);
+            neg_any |= (S < 0.0) | (I < 0.0);
+            const int i = P.Lrow - r;
+            if (i >= 0 && i < P.n0 && r >= 1 && T.cellCnt[i] > 0) {
+                const double f = log(log(I));
+                acc += fma(-lam * T.cellCD[i], exp(-f), T.cellY[i] * (llam - f));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+        negall = __any_sync(full, neg_any);
+        return acc;
+    };
     int evals = 0, st = 0;
     bool negall;
     double logy;
@@ -800,11 +844,11 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
     ts.advance(1, unif);
     double sn, ct;
     sincos(ts.th, &sn, &ct);
-    double ll = cheap(ct, sn, negall, st);
+    double ll = a.kingman ? kingman(ct, sn, negall) : cheap(ct, sn, negall, st);
     evals++;
     int i = 0;
     bool reverted = false;
-    while (negall || ll <= logy) {
+    while (negall || ll <= logy) {  // (a NaN Kingman value compares false and ends the loop, like the reference)
         i += 1;
         if (i > 20) {  // cap: back to the current increments, recompute (:1741-1747)
             reverted = true;
@@ -819,9 +863,10 @@ __global__ void __launch_bounds__(kTrajWarps * 32) k_eslice_traj(DevProb P, long
         }
         ts.advance(i + 1, unif);
         sincos(ts.th, &sn, &ct);
-        ll = cheap(ct, sn, negall, st);
+        ll = a.kingman ? kingman(ct, sn, negall) : cheap(ct, sn, negall, st);
         evals++;
     }
+    if (a.kingman && ll != ll) st |= ST_NAN;
     // outputs: latent rows, rotated increments, logOrigin without the LAST row (:1768)
     for (int r = lane; r < nrow; r += 32) {
         const bool keep = a.mode == 1 && reverted;  // newTraj = f_cur, bit for bit

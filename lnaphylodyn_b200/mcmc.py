@@ -8,8 +8,8 @@ device through the resident-chain C ABI (`lna_chains_step*`, see chains.py); thi
 them: set-up, initial state, stage switching (`burn1`, `warmup2`), thinning and storage.
 
 What is NOT here, and raises instead of guessing: likelihood other than "volz", models other than "SIR" (the
-reference's samplers are hard-wired to p = 2, LNA_functional.cpp:1456-1462), vector-valued Metropolis entries, the
-self-mixing `ESS_vec[7]` branch.  General_MCMC2's adaptive joint random-walk stage (`i >= warmup2`) draws its proposal as
+reference's samplers are hard-wired to p = 2, LNA_functional.cpp:1456-1462), vector-valued Metropolis entries.
+General_MCMC2's adaptive joint random-walk stage (`i >= warmup2`) draws its proposal as
 MASS::mvrnorm does (eigen-decomposition of the covariance), with LAPACK's eigenvector signs: same proposal distribution, the
 realisation for given normals is not pinned (MASS is outside the reference tree).
 The random numbers are Philox streams drawn on the device (seed, chain, iteration) -- R's generator is not
@@ -168,8 +168,6 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
     Returns {par (chains, niter, npar), Trajectory (chains, niter/thin, nrow, p+1), l, l1, MCMC_setting, MCMC_obj}."""
     if likelihood != "volz" or model != "SIR":
         raise LnaError("General_MCMC_with_ESlice: the GPU path has the volz likelihood with model = 'SIR' only")
-    if ESS_vec2 is not None and int(ESS_vec2[6]):
-        raise LnaError("General_MCMC_with_ESlice: ESS_vec2[7] (self-mixing OriginTraj) is rejected, see DESIGN.md section 7")
     options = dict(options or {})
     nch = len(np.ravel(changetime))
     par_ids = [int(v) for v in dict(options.get("parIdlist") or {"c": 4, "d": nch + 5}).values()]
@@ -184,9 +182,6 @@ def General_MCMC_with_ESlice(coal_obs, times, t_correct, N, gridsize=1000, niter
                            "with priorId 1..4 and for the hyper-parameter (parId nch + 5, priorId 5)")
     # the vignettes' (gamma, no-op hyper) pair keeps its dedicated path: both entries in one latency period
     standard_entries = par_ids == [4, nch + 5] and is_logs == [1, 0] and pr_ids == [3, 5] and not hyper_flag
-    if int(ESS_vec[0]) or int(ESS_vec[6]):
-        raise LnaError("General_MCMC_with_ESlice: ESS_vec[1] (I0) / ESS_vec[7] (self-mixing OriginTraj) are rejected, "
-                       "see DESIGN.md section 7")
     setting = MCMC_setup_general(coal_obs, times, t_correct, N, gridsize, niter, burn, thin, changetime, DEMS, prior,
                                  proposal, control, likelihood, model, Index, nparam, options.get("PCOV"))
     init = MCMC_initialize_general(setting, n_chains, init_rng or np.random.default_rng([int(seed), 7]), device)

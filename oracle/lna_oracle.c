@@ -726,6 +726,12 @@ int orc_eslice_par_general(const orc_cfg *c, const orc_init *init, const double 
     return status;
 }
 
+/* LogTraj: SIR_LNA.cpp:40-46 (time column copied, log of every state column). */
+static void log_traj(const double *traj, int nrow, int p, double *out) {
+    for (int r = 0; r < nrow; r++) out[r] = traj[r];
+    for (int e = nrow; e < nrow * (p + 1); e++) out[e] = log(traj[e]);
+}
+
 /* ESlice_general_NC: LNA_functional.cpp:1690-1778.
  * normals: k*p (column-major k x p); uniforms: u, theta_1, one per shrink (<= 20). */
 int orc_eslice_general_nc(const orc_init *init, const double *f_cur, int k, int p, const double *OdeTraj,
@@ -738,14 +744,21 @@ int orc_eslice_general_nc(const orc_init *init, const double *f_cur, int k, int 
     const double *v_traj = normals;
     double *tmp = (double *)malloc(sizeof(double) * (size_t)nrow * (p + 1));
     double u = uniforms[iu++], logy;
-    (void)lambda;
-    if (!volz) { /* Kingman branch (LogTraj of SIR_LNA.cpp:40, then coal_loglik3 logs again): not restated, reached only with likelihood != 'volz', which no BASELINE config uses */
-        free(tmp);
-        return -1;
-    }
+    /* volz = FALSE (:1717-1721, 1733-1760): the Kingman likelihood of LogTraj(newTraj) (SIR_LNA.cpp:40-46: log of every state
+     * column) through coal_loglik3, which with transX = "standard" takes the log AGAIN -- log(log I), NaN as soon as I < 1.
+     * A NaN compares false in `loglike <= logy`, so it ENDS the loop and is returned.  The 20-shrink cap still recomputes with
+     * volz_loglik_nh2 (:1743).  With coal_log == -99999999 the reference hands the k x p increment matrix f_cur to
+     * coal_loglik3 as if it were a trajectory (:1720): not restated (rejected), no driver reaches it. */
+#define NC_LOGLIKE(traj)                                                                              \
+    (volz ? orc_volz_loglik_nh2(init, traj, nrow, p, betaN, t_correct, Index, transX)                  \
+          : (log_traj(traj, nrow, p, tmp), orc_coal_loglik3(init, tmp, nrow, p, t_correct, lambda, Index[1], transX)))
     if (coal_log != -99999999) {
         logy = coal_log + log(u);
     } else {
+        if (!volz) {
+            free(tmp);
+            return -1;
+        }
         orc_transform_traj(OdeTraj, nrow, p, f_cur, k, Acube, Lcube, tmp);
         logy = orc_volz_loglik_nh2(init, tmp, nrow, p, betaN, t_correct, Index, transX) + log(u);
         evals++;
@@ -756,7 +769,7 @@ int orc_eslice_general_nc(const orc_init *init, const double *f_cur, int k, int 
     double ct = cos(theta), sn = sin(theta);
     for (int e = 0; e < k * p; e++) f_prime[e] = f_cur[e] * ct + v_traj[e] * sn;
     orc_transform_traj(OdeTraj, nrow, p, f_prime, k, Acube, Lcube, LatentTraj);
-    double loglike = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, Index, transX);
+    double loglike = NC_LOGLIKE(LatentTraj);
     evals++;
     int i = 0;
     for (;;) {
@@ -780,9 +793,10 @@ int orc_eslice_general_nc(const orc_init *init, const double *f_cur, int k, int 
         sn = sin(theta);
         for (int e = 0; e < k * p; e++) f_prime[e] = f_cur[e] * ct + v_traj[e] * sn;
         orc_transform_traj(OdeTraj, nrow, p, f_prime, k, Acube, Lcube, LatentTraj);
-        loglike = orc_volz_loglik_nh2(init, LatentTraj, nrow, p, betaN, t_correct, Index, transX);
+        loglike = NC_LOGLIKE(LatentTraj);
         evals++;
     }
+#undef NC_LOGLIKE
     double lo = 0.0;
     for (int j = 0; j < k - 1; j++) /* omits the LAST row (:1768) */
         for (int q = 0; q < p; q++) lo -= 0.5 * f_prime[j + (size_t)q * k] * f_prime[j + (size_t)q * k];

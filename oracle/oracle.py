@@ -359,7 +359,8 @@ def ESlice_general_NC(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10
                                      TRANSX[transX], _p(nrm), _p(unf), C.byref(nn), C.byref(nu), C.byref(ne),
                                      _p(lat), _p(eps_new), C.byref(lo), C.byref(cl))
     if st < 0:
-        raise NotImplementedError("ESlice_general_NC(volz=False): Kingman branch (LogTraj, SIR_LNA.cpp:40, then coal_loglik3 takes the log again) is not restated; reached only with likelihood != 'volz', which no BASELINE config uses")
+        raise NotImplementedError("ESlice_general_NC(volz=False, coal_log=-99999999): the reference hands the increment "
+                                  "matrix to coal_loglik3 as a trajectory (:1720); not restated")
     return {"LatentTraj": lat, "OriginTraj": eps_new, "logOrigin": lo.value, "CoalLog": cl.value,
             "status": st, "n_normals": nn.value, "n_uniforms": nu.value, "n_evals": ne.value}
 

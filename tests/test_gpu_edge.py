@@ -132,9 +132,9 @@ def test_single_item_and_empty_batch(api, changepoint):
         pb2.full_loglik(par[2:], par[:2], g.final["OriginTraj"])
     with pytest.raises(_lib.LnaError, match="multiple of gridsize"):
         api.Problem(g.times[:-1], g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
-    with pytest.raises(_lib.LnaError, match="ESS_vec"):
-        api.ESlice_par_General(par, g.times, g.final["OriginTraj"], [[1, 1]] * 4, g.x_r, g.x_i, g.init, 50,
-                               [0, 1, 0, 0, 1, 1, 1], 0.0, g.t_correct, normals=np.zeros(43), uniforms=np.full(22, 0.5))
+    with pytest.raises(_lib.LnaError, match="hard-wired to SIR"):   # the samplers are p = 2 only, like the reference's
+        pbs = api.problem_for(g.times, g.x_r, [39, 3, 0, 2], g.gridsize, g.t_correct, g.init, "SEIR")
+        _lib.check(_lib.lib().lna_chains_create(pbs.h, 4) and 0 or -1, "lna_chains_create")
 
 
 @pytest.mark.parametrize("gridsize,nch", [(8, 39), (40, 0), (50, 3), (1, 2)])

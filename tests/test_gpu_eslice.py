@@ -69,6 +69,108 @@ def test_eslice_par_general_step_for_step(api, changepoint, width):
     assert d["n_evals"].max() > 3  # the sample exercises real shrinking
 
 
+@pytest.mark.parametrize("ess", [[0, 1, 0, 0, 1, 1, 1], [1, 1, 1, 0, 1, 1, 1]])
+def test_eslice_par_general_self_mixing_branch(api, changepoint, ess):
+    """ESS_vec[7] = 1 (the default ESS_vec of the R drivers): k*p extra normals are drawn and discarded and every candidate
+    whose New_Param_List succeeds replaces OriginTraj_new by OriginTraj cos(theta) + OriginTraj_new sin(theta)
+    (LNA_functional.cpp:1576-1578, 1660-1662) -- a running multiple of OriginTraj.  Step for step against the oracle (which
+    follows the reference code as written here: tests/test_ref_vs_oracle.py), including the returned OriginTraj / logOrigin."""
+    g = changepoint
+    st = state_of(g)
+    opts = driver.opts_from_golden(g)
+    B = 24
+    rng = np.random.default_rng(111)
+    nrm, unf = rng.standard_normal((B, 43)), rng.random((B, 22))
+    unf[:3, 0] = 1.0 - 1e-9 * rng.random(3)   # long shrink sequences
+    d = api.ESlice_par_General(np.tile(st["par"], (B, 1)), g.times, st["OriginTraj"], opts["priorList"], g.x_r, g.x_i,
+                               g.init, g.gridsize, ess, st["coalLog"], g.t_correct, normals=nrm, uniforms=unf)
+    mixed = 0
+    for b in range(B):
+        o = orc.ESlice_par_General(st["par"], g.times, st["OriginTraj"], opts["priorList"], g.x_r, g.x_i, g.init,
+                                   g.gridsize, ess, st["coalLog"], g.t_correct, normals=nrm[b], uniforms=unf[b])
+        assert d["n_evals"][b] == o["n_evals"] and (d["status"][b] & 8) == (o["status"] & 8), b
+        assert relerr(d["par"][b], o["par"]) < TOL and d["CoalLog"][b] == pytest.approx(o["CoalLog"], rel=TOL)
+        assert np.max(np.abs(d["OriginTraj"][b] - o["OriginTraj"])) < 1e-13 * np.max(np.abs(o["OriginTraj"]))
+        assert d["logOrigin"][b] == pytest.approx(o["logOrigin"], rel=1e-12)
+        assert relerr(d["LatentTraj"][b][:, 1:], o["LatentTraj"][:, 1:]) < 1e-9
+        mixed += not np.array_equal(o["OriginTraj"], st["OriginTraj"])
+    assert mixed >= B - 4 and d["n_evals"].max() > 3   # (with the increments rescaled even log u ~ 0 is beaten before the cap)
+
+
+def test_chains_with_default_ess_vec_self_mixing(api, changepoint):
+    """The R drivers' DEFAULT ESS_vec = (1,1,1,1,1,1,1): I0, R0, gamma, hyper and the change ratios rotate, and the
+    self-mixing branch evaluates the candidates on a multiple of OriginTraj -- which update_Par_ESlice_combine then does
+    NOT store (R/LNA_chpt_slice.R:456-472), so the chain keeps its OriginTraj.  Chains against the restated iteration."""
+    from lnaphylodyn_b200 import chains as chm
+    g = changepoint
+    B, iters, seed = 8, 4, 5
+    ess = [1, 1, 1, 1, 1, 1, 1]
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"),
+                           g.setting("control.ch"), g.setting("control.hyper")])
+    eps0 = 0.2 * np.random.default_rng(2).standard_normal((40, 2))
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), eps0)
+    ref = [driver.init_state(g, par0, eps0) for _ in range(B)]
+    prior = [g.setting("prior." + k) for k in ("pop_pr", "R0_pr", "gamma_pr", "mu_pr", "hyper_pr")]
+    proposal = [g.setting("proposal." + k) for k in ("pop_prop", "R0_prop", "gamma_prop", "mu_prop", "hyper_prop")]
+    for it in range(iters):
+        traj = it >= 2
+        e = list(ess)
+        if not traj:
+            e[4] = 0
+        nrm, unf = chm.draw_streams(B, ch.n_norm, seed, it)
+        ch.step(chm.make_opts(prior, proposal, e, update_traj=traj), nrm, unf)
+        s = ch.get()
+        o = dict(driver.opts_from_golden(g, update_traj=traj), ESS_vec=e)
+        for c in range(B):
+            ref[c] = driver.eslice_iteration(ref[c], g, o, nrm[c], unf[c])
+            assert relerr(s["par"][c], ref[c]["par"]) < TOL, (it, c)
+            assert s["coalLog"][c] == pytest.approx(ref[c]["coalLog"], rel=TOL), (it, c)
+            assert np.max(np.abs(s["OriginTraj"][c] - ref[c]["OriginTraj"])) < 1e-11
+            assert s["n_full_evals"][c] == ref[c]["n_full"], (it, c)
+    assert not np.array_equal(s["par"][:, 1], np.full(B, 1.0))   # I0 moves under ESS_vec[1]
+
+
+def test_eslice_general_nc_kingman_branch(api, changepoint):
+    """ESlice_general_NC(volz = FALSE): coal_loglik3 of LogTraj(newTraj) -- log(log I), NaN as soon as I < 1, and a NaN ends
+    the loop and is returned; the 20-cap recomputes with volz_loglik_nh2 (:1717-1760).  Step for step against the oracle,
+    which follows the reference code as written on the same cases (tests/test_ref_vs_oracle.py)."""
+    g = changepoint
+    rng0 = np.random.default_rng(9)
+    seen_nan = seen_cap = seen_shrink = 0
+    for s in range(14):
+        par = g.final["par"].ravel().copy()
+        par[2] *= np.exp(0.02 * (s % 3))
+        par[1] = 0.5 if s >= 10 else 80.0
+        eps = g.final["OriginTraj"] + 0.05 * rng0.standard_normal((40, 2))
+        st = driver.init_state(g, par, eps)
+        rng = np.random.default_rng([23, s])
+        kw = dict(normals=rng.standard_normal(80), uniforms=rng.uniform(size=22))
+        lam = (1.0, 300.0)[s % 2]
+        lat0 = np.array(st["LatentTraj"], order="F")
+        with np.errstate(invalid="ignore", divide="ignore"):
+            base = orc.coal_loglik3(g.init, np.column_stack([lat0[:, 0], np.log(lat0[:, 1:])]), g.t_correct, lam, 1)
+        cl = (base - 3.0, base + 0.5, 1e9, base)[s % 4] if np.isfinite(base) else -2000.0
+        args = (eps, st["Ode"], st["FT"], par[:2], g.init, st["betaN"], g.t_correct, lam, cl, g.gridsize, False, "SIR")
+        a, b = orc.ESlice_general_NC(*args, **kw), api.ESlice_general_NC(*args, **kw)
+        assert a["n_evals"] == b["n_evals"], s
+        assert np.allclose(a["OriginTraj"], b["OriginTraj"], rtol=1e-12, atol=1e-300)
+        assert relerr(b["LatentTraj"][:, 1:], a["LatentTraj"][:, 1:]) < 1e-9
+        if np.isnan(a["CoalLog"]):
+            assert np.isnan(b["CoalLog"]) and (b["status"] & 4)
+            seen_nan += 1
+        else:
+            assert b["CoalLog"] == pytest.approx(a["CoalLog"], rel=TOL)
+        assert b["logOrigin"] == pytest.approx(a["logOrigin"], rel=1e-12)
+        seen_cap += bool(a["status"] & 8)
+        seen_shrink += a["n_evals"] > 2
+    assert seen_nan >= 1 and seen_cap >= 1 and seen_shrink >= 2
+    from lnaphylodyn_b200._lib import LnaError
+    with pytest.raises(LnaError, match="99999999"):
+        api.ESlice_general_NC(eps, st["Ode"], st["FT"], par[:2], g.init, st["betaN"], g.t_correct, 1.0, -99999999.0,
+                              g.gridsize, False, "SIR", **kw)
+
+
 def test_eslice_par_general_two_phase_window(api, changepoint):
     """B inside the window where the automatic policy runs two compacted phases (candidates 1..8 for
     every chain, then 9..21 sixteen-wide for the unresolved ones): same chains as the sequential loop.

@@ -284,18 +284,40 @@ def test_eslice_general_nc_step_for_step(name):
 
 
 def test_eslice_general_nc_kingman_branch(changepoint):
-    """volz = FALSE goes through LogTraj (SIR_LNA.cpp:40) and coal_loglik3, which logs the trajectory a second time
-    (NaN whenever I < e).  Reached only with likelihood != "volz" (no BASELINE config); the reference code runs, the oracle and the product decline."""
+    """volz = FALSE goes through LogTraj (SIR_LNA.cpp:40) and coal_loglik3, which logs the trajectory a second time:
+    log(log I), NaN as soon as I < 1 -- and a NaN ends the loop (`NaN <= logy` is false) and is returned.  Reached only with
+    likelihood != "volz" (no BASELINE config); oracle vs the reference code as written, step for step, over given
+    coal_log values that end at once, shrink several times, hit the 20-cap (which recomputes with volz_loglik_nh2), and a
+    trajectory pushed below one infective (NaN)."""
     g = changepoint
-    par, eps = state(g)
-    st = odriver.init_state(g, par, eps)
-    rng = np.random.default_rng(4)
-    r = ref.ESlice_general_NC(eps, st["Ode"], st["FT"], par[:2], g.init, st["betaN"], g.t_correct, 300.0, -2000.0, g.gridsize,
-                              False, "SIR", normals=rng.standard_normal(80), uniforms=rng.uniform(size=22))
-    assert r["n_normals"] == 80 and r["n_uniforms"] >= 2
-    with pytest.raises(NotImplementedError):
-        orc.ESlice_general_NC(eps, st["Ode"], st["FT"], par[:2], g.init, st["betaN"], g.t_correct, 300.0, -2000.0, g.gridsize,
-                              False, "SIR", normals=rng.standard_normal(80), uniforms=rng.uniform(size=22))
+    seen_nan = seen_shrink = seen_cap = 0
+    for s in range(14):
+        par, eps = state(g, 0.02 * (s % 3), seed=160 + s)
+        par = par.copy()
+        par[1] = 0.5 if s >= 10 else 80.0   # < 1 infective at the start: log(log I) is NaN there; 80: finite everywhere
+        st = odriver.init_state(g, par, eps)
+        rng = np.random.default_rng([23, s])
+        kw = dict(normals=rng.standard_normal(80), uniforms=rng.uniform(size=22))
+        lam = (1.0, 300.0)[s % 2]
+        lat0 = np.array(st["LatentTraj"], order="F")
+        base = orc.coal_loglik3(g.init, np.column_stack([lat0[:, 0], np.log(lat0[:, 1:])]), g.t_correct, lam, 1)
+        cl = (base - 3.0, base + 0.5, 1e9, base)[s % 4] if np.isfinite(base) else -2000.0
+        args = (eps, st["Ode"], st["FT"], par[:2], g.init, st["betaN"], g.t_correct, lam, cl, g.gridsize, False, "SIR")
+        a, b = ref.ESlice_general_NC(*args, **kw), orc.ESlice_general_NC(*args, **kw)
+        assert a["n_uniforms"] == b["n_uniforms"] and a["n_normals"] == b["n_normals"] == 80, s
+        assert np.allclose(a["OriginTraj"], b["OriginTraj"], rtol=1e-13, atol=0) and np.allclose(a["LatentTraj"], b["LatentTraj"], rtol=1e-12)
+        if np.isnan(a["CoalLog"]):
+            assert np.isnan(b["CoalLog"])
+            seen_nan += 1
+        else:
+            assert a["CoalLog"] == pytest.approx(b["CoalLog"], rel=1e-12)
+        assert a["logOrigin"] == pytest.approx(b["logOrigin"], rel=1e-13)
+        seen_shrink += a["n_uniforms"] > 3
+        seen_cap += a["n_uniforms"] == 22
+    assert seen_nan >= 1 and seen_shrink >= 2 and seen_cap >= 1, (seen_nan, seen_shrink, seen_cap)
+    with pytest.raises(NotImplementedError):   # the -99999999 default in this branch treats the increments as a trajectory
+        orc.ESlice_general_NC(eps, st["Ode"], st["FT"], par[:2], g.init, st["betaN"], g.t_correct, 300.0, -99999999.0,
+                              g.gridsize, False, "SIR", normals=rng.standard_normal(80), uniforms=rng.uniform(size=22))
 
 
 def test_eslice_change_points_step_for_step(constant):
