@@ -277,6 +277,13 @@ int lna_log_like_traj_general2(lna_problem *pb, int64_t B, const double *SdeTraj
  * (PseudoInverse :22-48, DegenerateDet3 :17-19). */
 int lna_log_like_traj_sirs(lna_problem *pb, int64_t B, const double *SdeTraj, const double *OdeTraj,
                            const double *Acube, const double *Scube, double *loglik);
+/* Traj_sim_SIRS (SIRS_period.cpp:197-240): centred simulation of the seasonal SIRS from `initial` (B x 3) with supplied
+ * normals (B x k*3, step-major); noise = mvrnormArma2(Sigma) = chol(Sigma + 1e-13 I_3)' z (basic_util.cpp:72-81), density via
+ * PseudoInverse / DegenerateDet3.  Sigma has rank 2, so whether its jittered factorisation exists hangs on the last rounding:
+ * the outcome is reported per item (status LNA_ST_CHOL_FAIL = the reference's chol() exception; that item's outputs after
+ * the failing interval are meaningless). */
+int lna_traj_sim_sirs(lna_problem *pb, int64_t B, const double *initial, const double *OdeTraj, const double *Acube,
+                      const double *Scube, const double *normals, double *LNA_traj, double *loglike, int32_t *status);
 /* Traj_sim_general3 (:771-817): centred LNA simulation with supplied normals (B x k*p, step-major);
  * noise = mvrnormArma(Sigma) (basic_util.cpp:44-58).  Traj_sim_ezG2 (:907-975) = lna_ode_rk45 +
  * lna_kf_param(chol = 0) + lna_ode_coarse_slicer + this. */

@@ -86,6 +86,7 @@ _SIGS = {
     "lna_log_like_traj_general2": (C.c_int, [_vp, _I64] + [_vp] * 5),
     "lna_log_like_traj_sirs": (C.c_int, [_vp, _I64] + [_vp] * 5),
     "lna_traj_sim_general3": (C.c_int, [_vp, _I64] + [_vp] * 7),
+    "lna_traj_sim_sirs": (C.c_int, [_vp, _I64] + [_vp] * 8),
     "lna_eslice_general2": (C.c_int, [_vp, _I64] + [_vp] * 10),
     "lna_chains_create": (_vp, [_vp, _I64]),
     "lna_chains_destroy": (None, [_vp]),

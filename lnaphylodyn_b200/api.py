@@ -766,6 +766,30 @@ def SIRS_loglik_sweep(param, initial, times, SdeTraj, gridsize, t_correct, perio
     return out
 
 
+def Traj_sim_SIRS(initial, OdeTraj, Filter, t_correct, *, normals):
+    """SIRS_period.cpp:197-240 with supplied normals (k*3, step-major).  A failed chol(Sigma + 1e-13 I) -- the covariance has
+    rank 2, the outcome hangs on its last rounding -- raises like the reference for a single call and is reported in
+    `status` (ST_CHOL_FAIL) per item for a batch."""
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    times = O[:, 0] if single else O[0, :, 0]
+    pb = problem_for(times, [1.0], [0, 3, 0, 2], 1, t_correct, None, "SEIR")  # any 3-compartment problem on this grid
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, 4))
+    B = Of.shape[0]
+    Af, _ = pb._mats(Filter["A"], (3, 3, k))
+    Sf, _ = pb._mats(Filter["Sigma"], (3, 3, k))
+    I = np.ascontiguousarray(np.broadcast_to(_d(initial).reshape(-1, 3), (B, 3)))
+    z = _d(normals).reshape(B, k * 3)
+    T, ll, st = np.empty((B, nrow * 4)), np.empty(B), np.zeros(B, dtype=np.int32)
+    check(_lib.lib().lna_traj_sim_sirs(pb.h, B, _ptr(I), _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(z), _ptr(T), _ptr(ll), _ptr(st)),
+          "lna_traj_sim_sirs")
+    if single and (st[0] & ST_CHOL_FAIL):
+        raise ValueError("chol(): decomposition failed")
+    return {"SimuTraj": pb._unmats(T, (nrow, 4), single), "loglike": float(ll[0]) if single else ll,
+            "status": st[0] if single else st}
+
+
 def log_like_trajSIRS(SdeTraj, OdeTraj, Filter, gridsize, t_correct):
     """SIRS_period.cpp:82-118"""
     O = np.asarray(OdeTraj, dtype=np.float64)

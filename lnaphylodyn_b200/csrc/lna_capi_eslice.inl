@@ -523,12 +523,12 @@ static int eslice_general_nc_impl(lna_problem *pb, int64_t B, const double *f_cu
 // centred parametrisation
 // ------------------------------------------------------------------------------------------------
 static int centred_launch(lna_problem *pb, int64_t B, int mode, const double *x, const double *O, const double *A,
-                          const double *S, double *traj, double *ll, int32_t *st) {
+                          const double *S, double *traj, double *ll, int32_t *st, const double *initial = nullptr) {
     const DevProb &P = pb->dp;
     if (P.p == 2)
-        k_centred<2><<<nblk(B, 64), 64, 0, pb->stream>>>(P.k, B, mode, P.t_correct, x, O, A, S, traj, ll, st);
+        k_centred<2><<<nblk(B, 64), 64, 0, pb->stream>>>(P.k, B, mode, P.t_correct, x, O, A, S, traj, ll, st, initial);
     else
-        k_centred<3><<<nblk(B, 64), 64, 0, pb->stream>>>(P.k, B, mode, P.t_correct, x, O, A, S, traj, ll, st);
+        k_centred<3><<<nblk(B, 64), 64, 0, pb->stream>>>(P.k, B, mode, P.t_correct, x, O, A, S, traj, ll, st, initial);
     return launch_check(pb, "k_centred");
 }
 
@@ -584,6 +584,28 @@ extern "C" int lna_traj_sim_general3(lna_problem *pb, int64_t B, const double *O
     s.back(loglike, dll, nB);
     s.back(status, dst, nB);
     return s.finish("lna_traj_sim_general3");
+}
+
+/* Traj_sim_SIRS (SIRS_period.cpp:197-240) */
+extern "C" int lna_traj_sim_sirs(lna_problem *pb, int64_t B, const double *initial, const double *OdeTraj, const double *Acube,
+                                 const double *Scube, const double *normals, double *LNA_traj, double *loglike,
+                                 int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    const DevProb &P = pb->dp;
+    if (P.p != 3) return fail("lna_traj_sim_sirs: needs a 3-compartment problem");
+    const size_t nB = (size_t)B, per = (size_t)P.nrow * 4, cube = 9 * (size_t)P.k;
+    Stage s(pb);
+    const double *dI = s.in(initial, nB * 3), *dO = s.in(OdeTraj, nB * per), *dA = s.in(Acube, nB * cube),
+                 *dS = s.in(Scube, nB * cube), *dz = s.in(normals, nB * P.k * 3);
+    double *dT = s.tmp<double>(nB * per), *dll = s.tmp<double>(nB);
+    int32_t *dst = s.tmp<int32_t>(nB);
+    if (!s.ok || !dI || !dO || !dA || !dS || !dz) return fail("lna_traj_sim_sirs: bad arguments / staging failed");
+    if (centred_launch(pb, B, 3, dz, dO, dA, dS, dT, dll, dst, dI)) return -1;
+    s.back(LNA_traj, dT, nB * per);
+    s.back(loglike, dll, nB);
+    s.back(status, dst, nB);
+    return s.finish("lna_traj_sim_sirs");
 }
 
 extern "C" int lna_eslice_general2(lna_problem *pb, int64_t B, const double *f_cur, const double *OdeTraj,

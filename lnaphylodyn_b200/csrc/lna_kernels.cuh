@@ -404,10 +404,14 @@ __device__ inline void solve_small(const double *S, const double *v, double *w) 
     }
 }
 
+//   mode 3: Traj_sim_SIRS (SIRS_period.cpp:197-240): like mode 1 from a given initial state, noise = mvrnormArma2(Sigma) =
+//           chol(Sigma + 1e-13 I_3)' z (basic_util.cpp:72-81) of the RANK-2 seasonal-SIRS covariance -- whether that
+//           factorisation exists is decided by the last rounding of Sigma, so the outcome is reported per item (ST_CHOL_FAIL =
+//           the reference's chol() exception) -- and the density through PseudoInverse / DegenerateDet3
 template <int p>
 __global__ void k_centred(int k, long long B, int mode, double t_correct, const double *Sde_or_normals,
                           const double *Ode, const double *Acube, const double *Scube, double *traj_out,
-                          double *loglik, int *status) {
+                          double *loglik, int *status, const double *initial) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int nrow = k + 1;
@@ -462,11 +466,11 @@ __global__ void k_centred(int k, long long B, int mode, double t_correct, const 
         double *T = traj_out + b * (long long)nrow * (p + 1);
         double X0[p], X1[p], e0[p], e1[p], noise[p], w[p];
         for (int j = 0; j < p; ++j) {
-            X1[j] = O[(long long)(j + 1) * nrow];
+            X1[j] = (mode == 3 && initial) ? initial[b * p + j] : O[(long long)(j + 1) * nrow];
             e1[j] = X1[j];
             T[(long long)(j + 1) * nrow] = X1[j];
         }
-        T[0] = 0.0;  // quirk of the reference (:782)
+        T[0] = 0.0;  // quirk of the reference (:782, SIRS_period.cpp:205)
         for (int i = 0; i < k; ++i) {
             const double *Ai = A + i * p * p, *Si = S + i * p * p;
             for (int j = 0; j < p; ++j) {
@@ -479,6 +483,8 @@ __global__ void k_centred(int k, long long B, int mode, double t_correct, const 
             if (p == 2) {
                 const double r00 = sqrt(Si[0]), r01 = Si[1] / r00;
                 L[0] = r00; L[1] = r01; L[2] = 0.0; L[3] = sqrt(Si[3] - r01 * r01);
+            } else if (st & ST_CHOL_FAIL) {
+                for (int e = 0; e < p * p; ++e) L[e] = 0.0;  // (the reference threw at the first failure: nothing after it counts)
             } else {
                 double U[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                 for (int j = 0; j < 3; ++j) {
@@ -507,10 +513,30 @@ __global__ void k_centred(int k, long long B, int mode, double t_correct, const 
                 X1[r] = ax + e1[r] + noise[r];
             }
             if (O[i + 1] <= t_correct) {
-                solve_small<p>(Si, noise, w);
-                double q = 0.0;
-                for (int r = 0; r < p; ++r) q += noise[r] * w[r];
-                ll += -log(det_small<p>(Si)) / 2.0 + (-0.5) * q;
+                if (mode == 3 && p == 3) {
+                    // -log(DegenerateDet3(Sig)) / 2 - noise' PseudoInverse(Sig) noise / 2 (:226-231), same closed form as mode 2
+                    const double m01 = Si[3], m02 = Si[6], m11 = Si[4], m12 = Si[7], m22 = Si[8];
+                    const double tr = m11 + m22 - m01 - m02;
+                    const double dd = (m11 - m01) * (m22 - m02) - (m12 - m01) * (m12 - m02);
+                    const double sq = sqrt(tr * tr - 4 * dd);
+                    const double l1 = (tr + sq) / 2, l2 = (tr - sq) / 2;
+                    double g1[3], g2[3];
+                    g1[1] = (m12 - m01) / (m11 - m01 - l1); g1[0] = 1 - g1[1]; g1[2] = -1;
+                    g2[1] = (m12 - m01) / (m11 - m01 - l2); g2[0] = 1 - g2[1]; g2[2] = -1;
+                    const double n1 = sqrt(g1[0] * g1[0] + g1[1] * g1[1] + g1[2] * g1[2]);
+                    const double n2 = sqrt(g2[0] * g2[0] + g2[1] * g2[1] + g2[2] * g2[2]);
+                    double p1 = 0.0, p2 = 0.0;
+                    for (int r = 0; r < 3; ++r) {
+                        p1 += (g1[r] / n1) * noise[r];
+                        p2 += (g2[r] / n2) * noise[r];
+                    }
+                    ll += -log(dd) * 0.5 + (-0.5) * (p1 * p1 / l1 + p2 * p2 / l2);
+                } else {
+                    solve_small<p>(Si, noise, w);
+                    double q = 0.0;
+                    for (int r = 0; r < p; ++r) q += noise[r] * w[r];
+                    ll += -log(det_small<p>(Si)) / 2.0 + (-0.5) * q;
+                }
             }
             T[i + 1] = O[i + 1];
             for (int j = 0; j < p; ++j) T[(i + 1) + (long long)(j + 1) * nrow] = X1[j];

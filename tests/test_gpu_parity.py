@@ -428,6 +428,51 @@ def test_seasonal_sirs_fused_sweep_full_size(api):
     assert full[near[:200]].mean() > full[near[-200:]].mean()
 
 
+def test_traj_sim_sirs_reports_cholesky_outcome_per_item(api):
+    """Traj_sim_SIRS (SIRS_period.cpp:197-240): noise = chol(Sigma + 1e-13 I)' z of a RANK-2 covariance -- whether the
+    factorisation exists hangs on the last rounding of Sigma, so the outcome is reported per item and compared with the
+    oracle (which raises where the reference's arma::chol throws): same verdict on the same (A, Sigma), same trajectory and
+    density where it succeeds; a covariance lifted off the singular plane always factorises."""
+    t = np.linspace(0, 100, 2001)
+    rng = np.random.default_rng(41)
+    B = 40
+    param = _sirs_draws(rng, B)
+    init = np.array([9e4, 100.0, 9900.0])
+    ok_o = ok_d = both = 0
+    for b in range(B):
+        ode = orc.ODE2(init, t, param[b], 40.0)
+        kf = orc.SIRS_KOM_Filter(ode, param[b], 50, 40.0)
+        co = orc.Ode_Coarse_Slicer(ode, 50)
+        z = rng.standard_normal(120)
+        try:
+            o = orc.Traj_sim_SIRS(init, co, kf, 90.0, normals=z)
+        except ValueError:
+            o = None
+        try:
+            d = api.Traj_sim_SIRS(init, co, kf, 90.0, normals=z)
+        except ValueError:
+            d = None
+        ok_o += o is not None
+        ok_d += d is not None
+        assert (o is None) == (d is None), b   # same arithmetic on the same Sigma: same verdict
+        if o is not None and d is not None:
+            both += 1
+            assert relerr(d["SimuTraj"][:, 1:], o["SimuTraj"][:, 1:]) < 1e-9
+            assert d["loglike"] == pytest.approx(o["loglike"], rel=1e-7)
+        # well-conditioned variant: Sigma + 1e-3 I always factorises, on both sides
+        kf2 = {"A": kf["A"], "Sigma": kf["Sigma"] + 1e-3 * np.eye(3)[:, :, None]}
+        o2, d2 = orc.Traj_sim_SIRS(init, co, kf2, 90.0, normals=z), api.Traj_sim_SIRS(init, co, kf2, 90.0, normals=z)
+        assert relerr(d2["SimuTraj"][:, 1:], o2["SimuTraj"][:, 1:]) < TOL
+    # batch form: the per-item status says which draws the reference would have thrown on
+    ode = orc.ODE2(init, t, param[0], 40.0)
+    kf, co = orc.SIRS_KOM_Filter(ode, param[0], 50, 40.0), orc.Ode_Coarse_Slicer(ode, 50)
+    zs = rng.standard_normal((6, 120))
+    r = api.Traj_sim_SIRS(init, np.tile(co, (6, 1, 1)), {"A": np.tile(kf["A"], (6, 1, 1, 1)), "Sigma": np.tile(kf["Sigma"], (6, 1, 1, 1))},
+                          90.0, normals=zs)
+    assert r["status"].shape == (6,) and len(set(r["status"].tolist())) == 1   # Sigma decides, not the normals
+    print(f"Traj_sim_SIRS: chol(Sigma + 1e-13 I) exists for {ok_o}/{B} draws (oracle), {ok_d}/{B} (device), compared {both}")
+
+
 def test_async_host_buffer_evaluation(changepoint):
     """lna_full_loglik_async: several calls in flight on alternating staging sets give, after lna_problem_sync, exactly what
     the synchronous call gives -- including when the same staging set is reused (4 calls) and for a batch below the
