@@ -30,9 +30,12 @@ class Golden:
         self.init = {k: s("Init." + k) for k in ("C", "D", "y", "gridrep", "ng", "t", "l")}
         self.final = {k[len("final."):]: self.z[k] for k in self.z.files if k.startswith("final.")}
         self.iters = {k[len("iter."):]: self.z[k] for k in self.z.files if k.startswith("iter.")}
+        # read eagerly: NpzFile decompresses on every access and is not thread-safe (the long-horizon tests replay the
+        # oracle chains from a thread pool)
+        self._settings = {k[len("setting."):]: self.z[k] for k in self.z.files if k.startswith("setting.")}
 
     def setting(self, key):
-        return self.z["setting." + key]
+        return self._settings[key]
 
 
 @pytest.fixture(scope="session")
