@@ -284,6 +284,45 @@ int lna_log_like_traj_sirs(lna_problem *pb, int64_t B, const double *SdeTraj, co
  * the failing interval are meaningless). */
 int lna_traj_sim_sirs(lna_problem *pb, int64_t B, const double *initial, const double *OdeTraj, const double *Acube,
                       const double *Scube, const double *normals, double *LNA_traj, double *loglike, int32_t *status);
+/* ---- legacy copies of the pipeline: src/LNA_NS_general.cpp, class Foo of src/generalLNA.cpp, ESlice_SIRS ----
+ * The integrator / moment functions of LNA_NS_general.cpp are arithmetic twins of the current ones on the SIR model
+ * (betafs :25-47 = lna_betaTs; General_ODE_rk45 :76-98 = lna_ode_rk45; General_IntSigmaF :103-135 / General_KOM_Filter
+ * :139-159 = lna_kf_param(chol = 0)) and are served by those entry points with x_i = (nch, nparam, 0, 1); the functions
+ * below are the ones whose arithmetic differs. */
+/* log_like_traj_general (LNA_NS_general.cpp:164-200) = Foo::LNA_log_like_traj (generalLNA.cpp:178-214): the Gaussian
+ * transition density of a centred trajectory through inv2(Sigma) (basic_util.cpp:5-14); p = 2. */
+int lna_log_like_traj_general(lna_problem *pb, int64_t B, const double *SdeTraj, const double *OdeTraj, const double *Acube,
+                              const double *Scube, double *loglik);
+/* Traj_sim_general (LNA_NS_general.cpp:205-250) = Foo::LNA_Traj_sim (generalLNA.cpp:217-262): centred simulation with
+ * supplied normals (B x k*2, step-major), noise = chols(Sigma) z, density through inv2.  Traj_sim_ezG (:257-314) =
+ * lna_ode_rk45 + lna_kf_param(chol = 0) + lna_ode_coarse_slicer + this. */
+int lna_traj_sim_general(lna_problem *pb, int64_t B, const double *OdeTraj, const double *Acube, const double *Scube,
+                         const double *normals, double *LNA_traj, double *loglike);
+/* volz_loglik_nh (SIR_phylodyn.cpp:517-560): f1_log = B x nrow x 3 LOG trajectories (LogTraj, SIR_LNA.cpp:40-46). */
+int lna_volz_loglik_nh(lna_problem *pb, int64_t B, const double *f1_log, const double *betaN, double *loglik);
+/* The centred trajectory slice update of the legacy drivers, `reps` repetitions per call:
+ *   kind 0 ESlice_general (LNA_NS_general.cpp:320-394), kind 2 Foo::LNA_ESlice (generalLNA.cpp:296-372; same text): p = 2,
+ *          proposal Traj_sim_general, betaN_or_params4 = betaN (B x nrow), at the 20-shrink cap newTraj = f_cur;
+ *   kind 1 ESlice_SIRS (SIRS_period.cpp:313-402): p = 3, proposal Traj_sim_SIRS(state, .), betaN_or_params4 = params4
+ *          (B x 4: beta, A, period, N; betat = betaDyn(.) * N), at the cap the LAST candidate stays (:377-380); a failed
+ *          chol(Sigma + 1e-13 I) of a proposal = the reference's exception: status LNA_ST_CHOL_FAIL, outputs meaningless.
+ * volz != 0: volz_loglik_nh(LogTraj(.), betaN); volz == 0: coal_loglik(LogTraj(.), lambda[b]) (SIR_phylodyn.cpp:436-468).
+ * normals: reps x B x k*p (repetition-major, each item step-major); uniforms: B x reps*22, consumed contiguously
+ * (u, theta_1, one per shrink; per repetition); n_unif returns how many were consumed. */
+int lna_eslice_legacy(lna_problem *pb, int64_t B, int kind, int reps, int volz, const double *f_cur, const double *OdeTraj,
+                      const double *Acube, const double *Scube, const double *state, const double *betaN_or_params4,
+                      const double *lambda, const double *normals, const double *uniforms, double *newTraj,
+                      int32_t *n_evals, int32_t *n_unif, int32_t *status);
+/* class Foo (generalLNA.cpp:9-372): reaction network with the hard-wired hazards h = (param0 param1 / N S I, param1 I,
+ * param2 N) and effect matrix A_post - A_pre (B x 6: 3 reactions x 2 species, column-major).  mode 0 rate_h :76-83 (out B x
+ * 3), 1 dh :84-90 (B x 6), 2 ODE_ones :96-98 (B x 2), 3 the product A' dh that F_vec :92-94 forms (B x 4), 4 ODE_rk45
+ * :100-122 (B x n*3 column-major trajectories; t = the n grid times, states_or_initial = the initial states); modes 5 / 6 =
+ * 2 / 3 with the infection rate given directly in param[0]: ODE_general_one / general_F (LNA_NS_general.cpp:52-72) on the SIR
+ * effect matrix with param[0] = betaf(t) (lna_betaTs).
+ * (Foo::IntSigmaF / KOM_Filter_MX / LNA_Traj_sim_ez cannot run as written -- F_vec returns a 2 x 2 product through an
+ * arma::vec and IntSigmaF multiplies by an empty local `A` (:130, 146) -- and have no entry point.) */
+int lna_foo(lna_problem *pb, int64_t B, int mode, int n, const double *A_pre, const double *A_post, const double *param,
+            const double *N, const double *states_or_initial, const double *t, double *out);
 /* Traj_sim_general3 (:771-817): centred LNA simulation with supplied normals (B x k*p, step-major);
  * noise = mvrnormArma(Sigma) (basic_util.cpp:44-58).  Traj_sim_ezG2 (:907-975) = lna_ode_rk45 +
  * lna_kf_param(chol = 0) + lna_ode_coarse_slicer + this. */

@@ -88,6 +88,11 @@ _SIGS = {
     "lna_traj_sim_general3": (C.c_int, [_vp, _I64] + [_vp] * 7),
     "lna_traj_sim_sirs": (C.c_int, [_vp, _I64] + [_vp] * 8),
     "lna_eslice_general2": (C.c_int, [_vp, _I64] + [_vp] * 10),
+    "lna_log_like_traj_general": (C.c_int, [_vp, _I64] + [_vp] * 5),
+    "lna_traj_sim_general": (C.c_int, [_vp, _I64] + [_vp] * 6),
+    "lna_volz_loglik_nh": (C.c_int, [_vp, _I64] + [_vp] * 3),
+    "lna_eslice_legacy": (C.c_int, [_vp, _I64, C.c_int, C.c_int, C.c_int] + [_vp] * 13),
+    "lna_foo": (C.c_int, [_vp, _I64, C.c_int, C.c_int] + [_vp] * 7),
     "lna_chains_create": (_vp, [_vp, _I64]),
     "lna_chains_destroy": (None, [_vp]),
     "lna_chains_init": (C.c_int, [_vp, _vp, _vp]),

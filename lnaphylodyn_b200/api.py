@@ -805,3 +805,268 @@ def log_like_trajSIRS(SdeTraj, OdeTraj, Filter, gridsize, t_correct):
     check(_lib.lib().lna_log_like_traj_sirs(pb.h, Of.shape[0], _ptr(Xf), _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(ll)),
           "lna_log_like_traj_sirs")
     return float(ll[0]) if single else ll
+
+
+# ------------------------------------------------------------------------------------------------
+# legacy copies of the pipeline: src/LNA_NS_general.cpp, class Foo of src/generalLNA.cpp, ESlice_SIRS.
+# x_i has two entries there, (nch, nparam); param = (R0, gamma, .., ch_1 ..).  The integrator / moment functions are
+# arithmetic twins of the current ones on the SIR model and run on the same kernels.
+# ------------------------------------------------------------------------------------------------
+
+def _legacy_xi(x_i):
+    xi = [int(round(float(v))) for v in np.asarray(x_i).ravel()[:2]]
+    return [xi[0], xi[1], 0, 1]
+
+
+def _legacy_param(param, x_i):
+    """(R0, gamma, .., ch_1..ch_nch) -> the current layout's param with a trailing (unused) hyper-parameter"""
+    xi = _legacy_xi(x_i)
+    param = _d(param)
+    return np.append(param[:xi[0] + xi[1]], 1.0)
+
+
+def betafs(ts, param, x_r, x_i):
+    """LNA_NS_general.cpp:25-47"""
+    return betaTs(_legacy_param(param, x_i), ts, x_r, _legacy_xi(x_i))
+
+
+def betaf(t, param, x_r, x_i):
+    """LNA_NS_general.cpp:6-21"""
+    return float(betafs([t], param, x_r, x_i)[0])
+
+
+_SIR_PRE = np.array([1.0, 0.0, 0.0, 1.0, 1.0, 0.0])    # 3 x 2 column-major: S + I -> 2 I, I -> 0, (no third reaction)
+_SIR_POST = np.array([0.0, 0.0, 0.0, 2.0, 0.0, 0.0])
+
+
+def _foo_call(mode, A_pre, A_post, param3, N, states, t=None):
+    pb = problem_for(np.array([0.0, 1.0]), [1.0], [0, 2, 0, 1], 1)
+
+    def colmajor(A):  # 3 x 2 matrix (or its 6 column-major entries)
+        A = np.asarray(A, dtype=np.float64)
+        return np.ascontiguousarray(A.reshape(-1, order="F") if A.ndim == 2 else A)
+
+    ap, aq = colmajor(A_pre), colmajor(A_post)
+    par, Nv, x = _d(param3).reshape(1, 3), np.array([float(N)]), _d(states).reshape(1, 2)
+    n = 0 if t is None else len(t)
+    per = {0: 3, 1: 6, 2: 2, 3: 4, 4: n * 3, 5: 2, 6: 4}[mode]
+    out = np.empty((1, per))
+    tt = None if t is None else _d(t)
+    check(_lib.lib().lna_foo(pb.h, 1, mode, n, _ptr(ap), _ptr(aq), _ptr(par), _ptr(Nv), _ptr(x),
+                             None if tt is None else _ptr(tt), _ptr(out)), "lna_foo")
+    return out[0]
+
+
+def ODE_general_one(states, param, t, x_r, x_i):
+    """LNA_NS_general.cpp:52-62"""
+    th1 = betaf(t, param, x_r, x_i)
+    return _foo_call(5, _SIR_PRE, _SIR_POST, [th1, _d(param)[1], 0.0], 1.0, states)
+
+
+def general_F(states, param, t, x_r, x_i):
+    """LNA_NS_general.cpp:66-72"""
+    th1 = betaf(t, param, x_r, x_i)
+    return _foo_call(6, _SIR_PRE, _SIR_POST, [th1, _d(param)[1], 0.0], 1.0, states).reshape(2, 2, order="F")
+
+
+def General_ODE_rk45(initial, t, param, x_r, x_i):
+    """LNA_NS_general.cpp:76-98"""
+    return ODE_rk45(initial, t, _legacy_param(param, x_i), x_r, _legacy_xi(x_i))
+
+
+def General_IntSigmaF(Traj_par, param, x_r, x_i):
+    """LNA_NS_general.cpp:103-135 (the reference spells the second entry "Simga")"""
+    r = SigmaF(Traj_par, _legacy_param(param, x_i), x_r, _legacy_xi(x_i))
+    return {"expF": r["expF"], "Simga": r["Sigma"]}
+
+
+def General_KOM_Filter(OdeTraj, param, gridsize, x_r, x_i):
+    """LNA_NS_general.cpp:139-159"""
+    return KF_param(OdeTraj, _legacy_param(param, x_i), gridsize, x_r, _legacy_xi(x_i))
+
+
+def log_like_traj_general(SdeTraj, OdeTraj, Filter, gridsize, t_correct):
+    """LNA_NS_general.cpp:164-200 (density through inv2)"""
+    pb, O, single, p = _centred_problem(OdeTraj, t_correct)
+    if p != 2:
+        raise LnaError("log_like_traj_general: the legacy copies are SIR-only (p = 2)")
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, 3))
+    Xf, _ = pb._mats(SdeTraj, (nrow, 3))
+    Af, _ = pb._mats(Filter["A"], (2, 2, k))
+    Sf, _ = pb._mats(Filter["Sigma"], (2, 2, k))
+    ll = np.empty(Of.shape[0])
+    check(_lib.lib().lna_log_like_traj_general(pb.h, Of.shape[0], _ptr(Xf), _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(ll)),
+          "lna_log_like_traj_general")
+    return float(ll[0]) if single else ll
+
+
+def Traj_sim_general(OdeTraj, Filter, t_correct, *, normals):
+    """LNA_NS_general.cpp:205-250 with supplied normals (k*2, step-major)"""
+    pb, O, single, p = _centred_problem(OdeTraj, t_correct)
+    if p != 2:
+        raise LnaError("Traj_sim_general: the legacy copies are SIR-only (p = 2)")
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, 3))
+    B = Of.shape[0]
+    Af, _ = pb._mats(Filter["A"], (2, 2, k))
+    Sf, _ = pb._mats(Filter["Sigma"], (2, 2, k))
+    z = _d(normals).reshape(B, k * 2)
+    traj, ll = np.empty_like(Of), np.empty(B)
+    check(_lib.lib().lna_traj_sim_general(pb.h, B, _ptr(Of), _ptr(Af), _ptr(Sf), _ptr(z), _ptr(traj), _ptr(ll)),
+          "lna_traj_sim_general")
+    return {"SimuTraj": pb._unmats(traj, (nrow, 3), single), "loglike": float(ll[0]) if single else ll}
+
+
+def Traj_sim_ezG(initial, times, param, gridsize, x_r, x_i, t_correct, *, normals):
+    """LNA_NS_general.cpp:257-314 = General_ODE_rk45 + General_KOM_Filter + coarse rows + the loop of Traj_sim_general"""
+    ode = General_ODE_rk45(initial, times, param, x_r, x_i)
+    kf = General_KOM_Filter(ode, param, gridsize, x_r, x_i)
+    return Traj_sim_general(Ode_Coarse_Slicer(ode, gridsize), kf, t_correct, normals=normals)
+
+
+def volz_loglik_nh(init, f1, betaN, t_correct, gridsize=1):
+    """SIR_phylodyn.cpp:517-560 (f1 = a LOG trajectory, nrow x 3)"""
+    F = np.asarray(f1, dtype=np.float64)
+    single = F.ndim == 2
+    times = F[:, 0] if single else F[0, :, 0]
+    pb = problem_for(times, [1.0], [0, 2, 0, 1], 1, t_correct, init, "SIR")
+    Ff, _ = pb._mats(F, (pb.nrow, 3))
+    B = Ff.shape[0]
+    bn = _d(betaN).reshape(B, pb.nrow)
+    ll = np.empty(B)
+    check(_lib.lib().lna_volz_loglik_nh(pb.h, B, _ptr(Ff), _ptr(bn), _ptr(ll)), "lna_volz_loglik_nh")
+    return float(ll[0]) if single else ll
+
+
+def _eslice_legacy(kind, f_cur, OdeTraj, FTs, state, init, betaN_or_params4, t_correct, lam, reps, volz, normals, uniforms):
+    O = np.asarray(OdeTraj, dtype=np.float64)
+    single = O.ndim == 2
+    times = O[:, 0] if single else O[0, :, 0]
+    p = 3 if kind == 1 else 2
+    if O.shape[-1] != p + 1:
+        raise LnaError(f"trajectory has {O.shape[-1] - 1} compartments, this sampler works on {p}")
+    pb = problem_for(times, [1.0], [0, 3, 0, 2] if p == 3 else [0, 2, 0, 1], 1, t_correct, init, "SEIR" if p == 3 else "SIR")
+    nrow, k = pb.nrow, pb.k
+    Of, _ = pb._mats(O, (nrow, p + 1))
+    B = Of.shape[0]
+    Ff, _ = pb._mats(f_cur, (nrow, p + 1))
+    Af, _ = pb._mats(FTs["A"], (p, p, k))
+    Sf, _ = pb._mats(FTs["Sigma"], (p, p, k))
+    q = _d(betaN_or_params4).reshape(B, 4 if kind == 1 else nrow)
+    st0 = None if kind != 1 else np.ascontiguousarray(np.broadcast_to(_d(state).reshape(-1, 3), (B, 3)))
+    lamv = np.ascontiguousarray(np.broadcast_to(_d(lam).reshape(-1), (B,)))
+    # normals arrive per item as reps x k*p (the order the reference consumes them in); the C ABI wants repetition-major
+    z = np.ascontiguousarray(_d(normals).reshape(B, reps, k * p).transpose(1, 0, 2))
+    unf = np.zeros((B, reps * 22))
+    u = _d(uniforms).reshape(B, -1)
+    unf[:, :min(u.shape[1], reps * 22)] = u[:, :reps * 22]
+    out = np.empty_like(Of)
+    ne, nu, st = (np.zeros(B, dtype=np.int32) for _ in range(3))
+    check(_lib.lib().lna_eslice_legacy(pb.h, B, kind, int(reps), int(bool(volz)), _ptr(Ff), _ptr(Of), _ptr(Af), _ptr(Sf),
+                                       None if st0 is None else _ptr(st0), _ptr(q), _ptr(lamv), _ptr(z), _ptr(unf), _ptr(out),
+                                       _ptr(ne), _ptr(nu), _ptr(st)), "lna_eslice_legacy")
+    if single and st[0] & ST_CHOL_FAIL:
+        raise ValueError("chol(): decomposition failed")
+    pick = (lambda a: a[0]) if single else (lambda a: a)
+    return {"newTraj": pb._unmats(out, (nrow, p + 1), single), "n_evals": pick(ne), "n_uniforms": pick(nu), "status": pick(st)}
+
+
+def ESlice_general(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, reps=1, gridsize=100, volz=False, *,
+                   normals, uniforms):
+    """LNA_NS_general.cpp:320-394; normals reps x k*2 per item, uniforms consumed contiguously over the repetitions"""
+    return _eslice_legacy(0, f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam, reps, volz, normals, uniforms)
+
+
+def ESlice_SIRS(f_cur, OdeTraj, FTs, state, init, params4, t_correct, lam=10.0, reps=1, gridsize=100, volz=True, *,
+                normals, uniforms):
+    """SIRS_period.cpp:313-402; params4 = (beta, A, period, N)"""
+    return _eslice_legacy(1, f_cur, OdeTraj, FTs, state, init, params4, t_correct, lam, reps, volz, normals, uniforms)
+
+
+class Foo:
+    """class Foo of src/generalLNA.cpp:9-372 (exposed to R through RCPP_MODULE(mod_Foo)): a reaction network with m = 3
+    reactions on p = 2 species, hazards hard-wired to (param0 param1 / N S I, param1 I, param2 N)."""
+
+    def __init__(self, A_pre, A_post, param, x_i, x_r):
+        self.A_pre, self.A_post = np.asarray(A_pre, dtype=np.float64), np.asarray(A_post, dtype=np.float64)
+        if self.A_pre.shape != (3, 2) or self.A_post.shape != (3, 2):
+            raise LnaError("Foo: rate_h / dh are written for 3 reactions on 2 species (generalLNA.cpp:76-90)")
+        self.param, self.x_i, self.x_r = _d(param), np.asarray(x_i), _d(x_r)
+        self.m, self.p, self.N = 3, 2, float(self.x_r[0])
+
+    # get / set functions (:38-47)
+    def get_A_pre(self):
+        return self.A_pre
+
+    def get_A_post(self):
+        return self.A_post
+
+    def get_A(self):
+        return self.A_post - self.A_pre
+
+    def get_param(self):
+        return self.param
+
+    def set_param(self, new_param):
+        self.param = _d(new_param)
+
+    def set_x_i(self, new_x_i):
+        self.x_i = np.asarray(new_x_i)
+
+    def set_x_r(self, new_x_r):
+        self.x_r = _d(new_x_r)   # (N is NOT refreshed: the reference copies it in the constructor only, :35)
+
+    def transform_param(self, t=0.0):
+        """:50-55"""
+        h = self.rate_h([1.0, 1.0], t)  # param_new(0) = h(0) at S = I = 1
+        res = self.param.copy()
+        res[0] = h[0]
+        return res
+
+    def _call(self, mode, states, t=None):
+        return _foo_call(mode, self.A_pre, self.A_post, self.param[:3], self.N, states, t)
+
+    def rate_h(self, states, t=0.0):
+        return self._call(0, states)
+
+    def dh(self, states, t=0.0):
+        return self._call(1, states).reshape(3, 2, order="F")
+
+    def ODE_ones(self, states, t=0.0):
+        return self._call(2, states)
+
+    def F_matrix(self, states, t=0.0):
+        """A' dh (2 x 2): the product F_vec (:92-94) forms"""
+        return self._call(3, states).reshape(2, 2, order="F")
+
+    def F_vec(self, states, t=0.0):
+        raise LnaError("Foo::F_vec (generalLNA.cpp:92-94) returns the 2 x 2 product A' dh through an arma::vec: the reference "
+                       "throws here; F_matrix() returns the product")
+
+    def ODE_rk45(self, initial, t):
+        t = _d(t)
+        return self._call(4, initial, t).reshape(len(t), 3, order="F")
+
+    def IntSigmaF(self, Traj_par):
+        raise LnaError("Foo::IntSigmaF (generalLNA.cpp:124-156) cannot run as written: it calls F_vec and multiplies by an "
+                       "empty local `A` (:130, 146); use General_IntSigmaF")
+
+    def KOM_Filter_MX(self, OdeTraj, gridsize):
+        return self.IntSigmaF(None)
+
+    def LNA_Traj_sim_ez(self, initial, times, gridsize, t_correct):
+        return self.IntSigmaF(None)
+
+    def LNA_log_like_traj(self, SdeTraj, OdeTraj, Filter, gridsize, t_correct):
+        """:178-214"""
+        return log_like_traj_general(SdeTraj, OdeTraj, Filter, gridsize, t_correct)
+
+    def LNA_Traj_sim(self, OdeTraj, Filter, t_correct, *, normals):
+        """:217-262"""
+        return Traj_sim_general(OdeTraj, Filter, t_correct, normals=normals)
+
+    def LNA_ESlice(self, f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, reps=1, gridsize=100, volz=False, *,
+                   normals, uniforms):
+        """:296-372"""
+        return _eslice_legacy(2, f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam, reps, volz, normals, uniforms)

@@ -23,6 +23,7 @@
 #include "lna_split.cuh"
 #include "lna_eslice.cuh"
 #include "lna_sirs.cuh"
+#include "lna_legacy.cuh"
 
 using namespace lna;
 
@@ -1181,4 +1182,5 @@ extern "C" double lna_measure_fp64_peak(int device, int iters) {
 }
 
 #include "lna_capi_eslice.inl"
+#include "lna_capi_legacy.inl"
 #include "lna_comm.inl"

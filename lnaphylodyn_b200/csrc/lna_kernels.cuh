@@ -408,12 +408,22 @@ __device__ inline void solve_small(const double *S, const double *v, double *w) 
 //           chol(Sigma + 1e-13 I_3)' z (basic_util.cpp:72-81) of the RANK-2 seasonal-SIRS covariance -- whether that
 //           factorisation exists is decided by the last rounding of Sigma, so the outcome is reported per item (ST_CHOL_FAIL =
 //           the reference's chol() exception) -- and the density through PseudoInverse / DegenerateDet3
+//   mode | 8 (p = 2): the legacy copies' density, through inv2(Sigma) (basic_util.cpp:5-14) instead of solve():
+//           log_like_traj_general / Traj_sim_general (LNA_NS_general.cpp:164-250), Foo::LNA_log_like_traj / LNA_Traj_sim
+__device__ inline double quad_inv2(const double *S, const double *v) {  // (v' inv2(S)) v
+    const double r00 = S[3], r11 = S[0], r10 = -S[1], r01 = -S[2];
+    const double iD = 1 / (r00 * r11 - r10 * r01);
+    const double w0 = v[0] * (r00 * iD) + v[1] * (r10 * iD), w1 = v[0] * (r01 * iD) + v[1] * (r11 * iD);
+    return w0 * v[0] + w1 * v[1];
+}
 template <int p>
-__global__ void k_centred(int k, long long B, int mode, double t_correct, const double *Sde_or_normals,
+__global__ void k_centred(int k, long long B, int mode_flags, double t_correct, const double *Sde_or_normals,
                           const double *Ode, const double *Acube, const double *Scube, double *traj_out,
                           double *loglik, int *status, const double *initial) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const int mode = mode_flags & 7;
+    const bool inv2_density = (mode_flags & 8) && p == 2;
     const int nrow = k + 1;
     const double *O = Ode + b * (long long)nrow * (p + 1);
     const double *A = Acube + b * (long long)k * p * p, *S = Scube + b * (long long)k * p * p;
@@ -453,6 +463,8 @@ __global__ void k_centred(int k, long long B, int mode, double t_correct, const 
                         p2 += (e2[r] / n2) * v[r];
                     }
                     ll += -log(dd) * 0.5 - 0.5 * (p1 * p1 / l1 + p2 * p2 / l2);
+                } else if (inv2_density) {
+                    ll += -log(det_small<p>(Si)) / 2.0 - 0.5 * quad_inv2(Si, v);
                 } else {
                     solve_small<p>(Si, v, w);
                     double q = 0.0;
@@ -531,6 +543,8 @@ __global__ void k_centred(int k, long long B, int mode, double t_correct, const 
                         p2 += (g2[r] / n2) * noise[r];
                     }
                     ll += -log(dd) * 0.5 + (-0.5) * (p1 * p1 / l1 + p2 * p2 / l2);
+                } else if (inv2_density) {
+                    ll += -log(det_small<p>(Si)) / 2 + (-0.5) * quad_inv2(Si, noise);
                 } else {
                     solve_small<p>(Si, noise, w);
                     double q = 0.0;

@@ -1192,6 +1192,298 @@ int orc_sirs_centred(int mode, const double *X_or_normals, const double *initial
     return ORC_OK;
 }
 
+/* ---------------------------------------------------------------- legacy copies of the pipeline
+ * src/LNA_NS_general.cpp (the SIR-only predecessor of LNA_functional.cpp), class Foo of src/generalLNA.cpp and
+ * ESlice_SIRS of src/SIRS_period.cpp.  x_i has two entries here: (nch, nparam); param = (R0, gamma, .., ch_1..). */
+
+static orc_cfg legacy_cfg(const double *x_r, const int *x_i2, int nparam_total) {
+    orc_cfg c;
+    c.model = ORC_SIR;
+    c.transX = ORC_STANDARD;
+    c.p = 2;
+    c.nparam_total = nparam_total;
+    c.x_r = x_r;
+    c.x_i[0] = x_i2[0];
+    c.x_i[1] = x_i2[1];
+    c.x_i[2] = 0;
+    c.x_i[3] = 1;
+    return c;
+}
+
+/* betafs: LNA_NS_general.cpp:25-47 (betaf :6-21 is its single-time form) = betaTs with R0 = param[0], gamma = param[1] */
+void orc_general_betafs(const double *ts, int m, const double *param, const double *x_r, const int *x_i2, double *betas) {
+    int x_i[4] = {x_i2[0], x_i2[1], 0, 1};
+    orc_betaTs(param, ts, m, x_r, x_i, betas);
+}
+/* ODE_general_one :52-62 (mode 0: 2 values) and general_F :66-72 (mode 1: 2 x 2 column-major) */
+void orc_general_point(int mode, const double *states, const double *param, int nparam_total, double t, const double *x_r,
+                       const int *x_i2, double *out) {
+    orc_cfg c = legacy_cfg(x_r, x_i2, nparam_total);
+    double th[3];
+    thetas3(&c, t, param, th);
+    if (mode == 0) {
+        out[0] = -th[0] * states[0] * states[1];
+        out[1] = th[0] * states[0] * states[1] - param[1] * states[1];
+    } else {
+        out[0] = -th[0] * states[1];
+        out[1] = th[0] * states[1];
+        out[2] = -th[0] * states[0];
+        out[3] = th[0] * states[0] - param[1];
+    }
+}
+/* General_ODE_rk45 :76-98: the same stages as ODE_rk45 (all at t[i-1], k4 at dt/2) */
+void orc_general_ode_rk45(const double *initial, const double *t, int n, const double *param, int nparam_total,
+                          const double *x_r, const int *x_i2, double *OdeTraj) {
+    orc_cfg c = legacy_cfg(x_r, x_i2, nparam_total);
+    orc_ode_rk45(&c, initial, t, n, param, OdeTraj);
+}
+/* General_IntSigmaF :103-135 (SigmaF without the Q factors, which are the identity on the standard scale) */
+void orc_general_intsigmaf(const double *Traj_par, int nrow, const double *param, int nparam_total, const double *x_r,
+                           const int *x_i2, double *expF, double *Sigma) {
+    orc_cfg c = legacy_cfg(x_r, x_i2, nparam_total);
+    orc_sigmaF(&c, Traj_par, nrow, nrow, param, expF, Sigma);
+}
+/* General_KOM_Filter :139-159 */
+void orc_general_kom_filter(const double *OdeTraj, int nrow, const double *param, int nparam_total, int gridsize,
+                            const double *x_r, const int *x_i2, double *Acube, double *Scube) {
+    orc_cfg c = legacy_cfg(x_r, x_i2, nparam_total);
+    orc_kf_param(&c, OdeTraj, nrow, param, gridsize, Acube, Scube);
+}
+
+/* log_like_traj_general :164-200 (mode 0) and Traj_sim_general :205-250 (mode 1; normals step-major, 2 per step):
+ * p = 2, the density through inv2(Sigma) (basic_util.cpp:5-14), noise = mvrnormArma(2, Sigma) = chols(Sigma) z.
+ * Foo::LNA_log_like_traj / Foo::LNA_Traj_sim (generalLNA.cpp:178-214, 217-262) are the same text. */
+int orc_legacy_centred(int mode, const double *X_or_normals, const double *OdeTraj, int nrow, const double *Acube,
+                       const double *Scube, double t_correct, double *traj_out, double *loglik) {
+    const int p = 2;
+    int k = nrow - 1;
+    double ll = 0.0, SI[4];
+    if (mode == 0) {
+        const double *X = X_or_normals;
+        double d0[2], d1[2], v[2];
+        for (int j = 0; j < p; j++) d1[j] = X[(size_t)(j + 1) * nrow] - OdeTraj[(size_t)(j + 1) * nrow];
+        for (int i = 0; i < k; i++) {
+            const double *A = Acube + (size_t)i * 4, *S = Scube + (size_t)i * 4;
+            orc_inv2(S, SI);
+            for (int j = 0; j < p; j++) {
+                d0[j] = d1[j];
+                d1[j] = X[(i + 1) + (size_t)(j + 1) * nrow] - OdeTraj[(i + 1) + (size_t)(j + 1) * nrow];
+            }
+            if (X[i + 1] <= t_correct) {
+                for (int r = 0; r < p; r++) v[r] = d1[r] - (A[r] * d0[0] + A[r + 2] * d0[1]);
+                /* (v' SigInv) v */
+                double w0 = v[0] * SI[0] + v[1] * SI[1], w1 = v[0] * SI[2] + v[1] * SI[3];
+                ll += -log(S[0] * S[3] - S[2] * S[1]) / 2.0 - 0.5 * (w0 * v[0] + w1 * v[1]);
+            }
+        }
+    } else {
+        double X0[2], X1[2], e0[2], e1[2], noise[2], L[4];
+        for (int j = 0; j < p; j++) {
+            X1[j] = OdeTraj[(size_t)(j + 1) * nrow];
+            e1[j] = X1[j];
+            traj_out[(size_t)(j + 1) * nrow] = X1[j];
+        }
+        traj_out[0] = 0;
+        for (int i = 0; i < k; i++) {
+            const double *A = Acube + (size_t)i * 4, *S = Scube + (size_t)i * 4;
+            for (int j = 0; j < p; j++) {
+                X0[j] = X1[j];
+                e0[j] = e1[j];
+                e1[j] = OdeTraj[(i + 1) + (size_t)(j + 1) * nrow];
+            }
+            orc_chols(S, L);
+            for (int r = 0; r < p; r++) noise[r] = L[r] * X_or_normals[(size_t)i * 2] + L[r + 2] * X_or_normals[(size_t)i * 2 + 1];
+            for (int r = 0; r < p; r++) X1[r] = (A[r] * (X0[0] - e0[0]) + A[r + 2] * (X0[1] - e0[1])) + e1[r] + noise[r];
+            if (OdeTraj[i + 1] <= t_correct) {
+                orc_inv2(S, SI);
+                /* ((-0.5) noise') inv2(Sig) noise */
+                double a0 = (-0.5) * noise[0], a1 = (-0.5) * noise[1];
+                double w0 = a0 * SI[0] + a1 * SI[1], w1 = a0 * SI[2] + a1 * SI[3];
+                ll += -log(S[0] * S[3] - S[2] * S[1]) / 2 + (w0 * noise[0] + w1 * noise[1]);
+            }
+            traj_out[i + 1] = OdeTraj[i + 1];
+            for (int j = 0; j < p; j++) traj_out[(i + 1) + (size_t)(j + 1) * nrow] = X1[j];
+        }
+    }
+    *loglik = ll;
+    return ORC_OK;
+}
+
+/* Traj_sim_ezG :257-314 = General_ODE_rk45 + coarse rows + General_KOM_Filter + the loop of Traj_sim_general started from
+ * `initial` (k = length(times) / gridsize). */
+int orc_traj_sim_ezG(const double *initial, const double *t, int nt, const double *param, int nparam_total, int gridsize,
+                     const double *x_r, const int *x_i2, double t_correct, const double *normals, double *LNA_traj,
+                     double *loglike) {
+    const int p = 2;
+    int k = nt / gridsize, nrow = k + 1;
+    double *thin = (double *)malloc(sizeof(double) * (size_t)nt * (p + 1));
+    double *coarse = (double *)malloc(sizeof(double) * (size_t)nrow * (p + 1));
+    double *A = (double *)malloc(sizeof(double) * (size_t)p * p * k * 2), *S = A + (size_t)p * p * k;
+    orc_general_ode_rk45(initial, t, nt, param, nparam_total, x_r, x_i2, thin);
+    for (int i = 0; i < nrow; i++)
+        for (int j = 0; j <= p; j++) coarse[i + (size_t)j * nrow] = thin[(size_t)i * gridsize + (size_t)j * nt];
+    orc_general_kom_filter(thin, nt, param, nparam_total, gridsize, x_r, x_i2, A, S);
+    /* (row 0 of the coarse ODE is `initial`, so the loop is Traj_sim_general's) */
+    int st = orc_legacy_centred(1, normals, coarse, nrow, A, S, t_correct, LNA_traj, loglike);
+    free(thin);
+    free(coarse);
+    free(A);
+    return st;
+}
+
+/* volz_loglik_nh: SIR_phylodyn.cpp:517-560.  f1 is a LOG trajectory (LogTraj): columns 1, 2 = log S, log I; cell i of the
+ * genealogy uses row L - i, L = first row with time >= t_correct; -1e7 when a LOG state of rows 0..n0 is negative. */
+double orc_volz_loglik_nh(const orc_init *init, const double *f1, int nrow, const double *betaN, double t_correct) {
+    int n0 = init->ng - 1, L = 0;
+    while (f1[L] < t_correct) L++;
+    for (int j = 1; j <= 2; j++)
+        for (int r = 0; r <= n0; r++)
+            if (f1[r + (size_t)j * nrow] < 0) return ORC_SENTINEL;
+    int E = init->E, start = 0;
+    double *ll = (double *)malloc(sizeof(double) * (size_t)(E > 0 ? E : 1));
+    for (int i = 0; i < n0; i++) {
+        int row = L - i, reps = (int)init->gridrep[i];
+        double f = f1[row + (size_t)2 * nrow], s = f1[row + (size_t)nrow], b = betaN[row];
+        for (int j = 0; j < reps; j++) {
+            ll[start] = -2 * (init->C[start] * init->D[start] * b * exp(-f) * exp(s)) + init->y[start] * (log(b) - f + s);
+            start++;
+        }
+    }
+    double res = accu2(ll, start);
+    free(ll);
+    return res;
+}
+
+/* ESlice_general (LNA_NS_general.cpp:320-394; kind 0), Foo::LNA_ESlice (generalLNA.cpp:296-372, the same text; kind 2) and
+ * ESlice_SIRS (SIRS_period.cpp:313-402; kind 1): the trajectory slice update in the CENTRED parametrisation, `reps` times.
+ *   proposal v: Traj_sim_general(OdeTraj, FTs) [kinds 0, 2; p = 2]  /  Traj_sim_SIRS(state, OdeTraj, FTs) [kind 1; p = 3]
+ *   likelihood: volz_loglik_nh(LogTraj(.), betaN) or coal_loglik(LogTraj(.), lambda)
+ *   kind 1 computes betaN = betaDyn(params4[0], params4[1], times, params4[2]) * params4[3] (SIR_phylodyn.cpp:40-46)
+ *   20-shrink cap: kinds 0, 2 return to f_cur; kind 1 just leaves the loop, the LAST candidate stays (:377-380)
+ * normals: reps x k*p (step-major), uniforms: consumed contiguously (u, theta_1, one per shrink; per repetition). */
+int orc_eslice_legacy(const orc_init *init, int kind, const double *f_cur0, int nrow, int p, const double *OdeTraj,
+                      const double *Acube, const double *Scube, const double *state, const double *betaN_or_params4,
+                      double t_correct, double lambda, int reps, int volz, const double *normals, const double *uniforms,
+                      int *n_unif, int *n_evals, double *newTraj) {
+    int iu = 0, evals = 0, n = nrow * p, k = nrow - 1, status = 0;
+    size_t sz = (size_t)nrow * (p + 1);
+    double *v = (double *)malloc(sizeof(double) * sz * 4), *f_cur = v + sz, *lg = f_cur + sz, *bet = lg + sz;
+    memcpy(f_cur, f_cur0, sizeof(double) * sz);
+    if (kind == 1) {
+        const double *q = betaN_or_params4;
+        for (int r = 0; r < nrow; r++) bet[r] = q[0] * (1 + q[1] * sin(2 * ORC_PI * f_cur[r] / q[2])) * q[3];
+    } else {
+        memcpy(bet, betaN_or_params4, sizeof(double) * (size_t)nrow);
+    }
+#define LEGACY_LL(T) (log_traj((T), nrow, p, lg), volz ? orc_volz_loglik_nh(init, lg, nrow, bet, t_correct) \
+                                                       : orc_coal_loglik(init, lg, nrow, p, t_correct, lambda))
+    for (int count = 0; count < reps; count++) {
+        double ll_sim;
+        int st = kind == 1 ? orc_sirs_centred(1, normals + (size_t)count * k * 3, state, OdeTraj, nrow, Acube, Scube, t_correct, v, &ll_sim)
+                           : orc_legacy_centred(1, normals + (size_t)count * k * 2, OdeTraj, nrow, Acube, Scube, t_correct, v, &ll_sim);
+        if (st) {
+            free(v);
+            return st;
+        }
+        double u = uniforms[iu++];
+        double logy = LEGACY_LL(f_cur) + log(u);
+        evals++;
+        double theta = runif_ab(0, 2 * ORC_PI, uniforms[iu++]);
+        double theta_min = theta - 2 * ORC_PI, theta_max = theta;
+        for (int r = 0; r < nrow; r++) newTraj[r] = f_cur[r];
+        double ct = cos(theta), sn = sin(theta);
+        for (int e = 0; e < n; e++) {
+            double fc = f_cur[nrow + e] - OdeTraj[nrow + e], vt = v[nrow + e] - OdeTraj[nrow + e];
+            newTraj[nrow + e] = (fc * ct + vt * sn) + OdeTraj[nrow + e];
+        }
+        double loglike = LEGACY_LL(newTraj);
+        evals++;
+        int i = 0;
+        for (;;) {
+            double mn = newTraj[nrow];
+            for (int e = nrow; e < nrow * (p + 1); e++)
+                if (newTraj[e] < mn) mn = newTraj[e];
+            if (!(mn < 0 || loglike <= logy)) break;
+            i += 1;
+            if (i > 20) {
+                if (kind != 1) memcpy(newTraj, f_cur, sizeof(double) * sz);
+                status |= ORC_CAP_HIT;
+                break;
+            }
+            if (theta < 0) theta_min = theta;
+            else theta_max = theta;
+            theta = runif_ab(theta_min, theta_max, uniforms[iu++]);
+            ct = cos(theta);
+            sn = sin(theta);
+            for (int e = 0; e < n; e++) {
+                double fc = f_cur[nrow + e] - OdeTraj[nrow + e], vt = v[nrow + e] - OdeTraj[nrow + e];
+                newTraj[nrow + e] = (fc * ct + vt * sn) + OdeTraj[nrow + e];
+            }
+            loglike = LEGACY_LL(newTraj);
+            evals++;
+        }
+        memcpy(f_cur, newTraj, sizeof(double) * sz);
+    }
+#undef LEGACY_LL
+    *n_unif = iu;
+    *n_evals = evals;
+    free(v);
+    return status;
+}
+
+/* class Foo (generalLNA.cpp:9-372): a reaction network with hard-wired SIR-with-immigration hazards
+ *   h = (param0 * param1 / N * S * I, param1 * I, param2 * N)  (rate_h :76-83, transform_param :50-55)
+ * and effect matrix A = A_post - A_pre (m = 3 reactions x p = 2 species, column-major).
+ *   mode 0: rate_h (3), 1: dh (3 x 2, :84-90), 2: ODE_ones = A' h (2, :96-98), 3: A' dh (2 x 2: what F_vec :92-94 computes
+ *   before its arma::vec return type rejects it) */
+void orc_foo_point(int mode, const double *A_pre, const double *A_post, const double *param, double N, const double *states,
+                   double *out) {
+    double pn0 = param[0] * param[1] / N, h[3], dh[6], A[6];
+    for (int e = 0; e < 6; e++) A[e] = A_post[e] - A_pre[e];
+    h[0] = pn0 * states[0] * states[1];
+    h[1] = param[1] * states[1];
+    h[2] = param[2] * N;
+    dh[0] = pn0 * states[1]; dh[3] = pn0 * states[0];
+    dh[1] = 0;               dh[4] = param[1];
+    dh[2] = 0.0;             dh[5] = 0.0;
+    if (mode == 0) {
+        memcpy(out, h, sizeof h);
+    } else if (mode == 1) {
+        memcpy(out, dh, sizeof dh);
+    } else if (mode == 2) {
+        for (int j = 0; j < 2; j++) out[j] = A[3 * j] * h[0] + A[3 * j + 1] * h[1] + A[3 * j + 2] * h[2];
+    } else {
+        for (int c = 0; c < 2; c++)
+            for (int j = 0; j < 2; j++) out[j + 2 * c] = A[3 * j] * dh[3 * c] + A[3 * j + 1] * dh[3 * c + 1] + A[3 * j + 2] * dh[3 * c + 2];
+    }
+}
+/* Foo::ODE_rk45 :100-122 */
+void orc_foo_ode_rk45(const double *A_pre, const double *A_post, const double *param, double N, const double *initial,
+                      const double *t, int n, double *OdeTraj) {
+    const int p = 2;
+    double dt = t[1] - t[0];
+    double X0[2], X1[2], k1[2], k2[2], k3[2], k4[2], xs[2];
+    for (int i = 0; i < n; i++) OdeTraj[i] = t[i];
+    for (int j = 0; j < p; j++) {
+        OdeTraj[(size_t)(j + 1) * n] = initial[j];
+        X1[j] = initial[j];
+    }
+    for (int i = 1; i < n; i++) {
+        for (int j = 0; j < p; j++) X0[j] = X1[j];
+        orc_foo_point(2, A_pre, A_post, param, N, X0, k1);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k1[j] * dt / 2;
+        orc_foo_point(2, A_pre, A_post, param, N, xs, k2);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k2[j] * dt / 2;
+        orc_foo_point(2, A_pre, A_post, param, N, xs, k3);
+        for (int j = 0; j < p; j++) xs[j] = X0[j] + k3[j] * dt / 2;
+        orc_foo_point(2, A_pre, A_post, param, N, xs, k4);
+        for (int j = 0; j < p; j++) {
+            X1[j] = X0[j] + (k1[j] / 6 + k2[j] / 3 + k3[j] / 3 + k4[j] / 6) * dt;
+            OdeTraj[i + (size_t)(j + 1) * n] = X1[j];
+        }
+    }
+}
+
 /* ---------------------------------------------------------------- batch driver (bench baseline) */
 
 /* B independent FULL evaluations, item-major inputs like the product's C ABI; one core.

@@ -164,6 +164,31 @@ void orc_sirs_kom_filter(const double *OdeTraj, int nrow, const double *param, i
 int orc_sirs_centred(int mode, const double *X_or_normals, const double *initial, const double *OdeTraj, int nrow,
                      const double *Acube, const double *Scube, double t_correct, double *traj_out, double *loglik);
 
+/* legacy copies: src/LNA_NS_general.cpp, class Foo of src/generalLNA.cpp, ESlice_SIRS; x_i2 = (nch, nparam) */
+void orc_general_betafs(const double *ts, int m, const double *param, const double *x_r, const int *x_i2, double *betas);
+void orc_general_point(int mode, const double *states, const double *param, int nparam_total, double t, const double *x_r,
+                       const int *x_i2, double *out);
+void orc_general_ode_rk45(const double *initial, const double *t, int n, const double *param, int nparam_total,
+                          const double *x_r, const int *x_i2, double *OdeTraj);
+void orc_general_intsigmaf(const double *Traj_par, int nrow, const double *param, int nparam_total, const double *x_r,
+                           const int *x_i2, double *expF, double *Sigma);
+void orc_general_kom_filter(const double *OdeTraj, int nrow, const double *param, int nparam_total, int gridsize,
+                            const double *x_r, const int *x_i2, double *Acube, double *Scube);
+int orc_legacy_centred(int mode, const double *X_or_normals, const double *OdeTraj, int nrow, const double *Acube,
+                       const double *Scube, double t_correct, double *traj_out, double *loglik);
+int orc_traj_sim_ezG(const double *initial, const double *t, int nt, const double *param, int nparam_total, int gridsize,
+                     const double *x_r, const int *x_i2, double t_correct, const double *normals, double *LNA_traj,
+                     double *loglike);
+double orc_volz_loglik_nh(const orc_init *init, const double *f1, int nrow, const double *betaN, double t_correct);
+int orc_eslice_legacy(const orc_init *init, int kind, const double *f_cur, int nrow, int p, const double *OdeTraj,
+                      const double *Acube, const double *Scube, const double *state, const double *betaN_or_params4,
+                      double t_correct, double lambda, int reps, int volz, const double *normals, const double *uniforms,
+                      int *n_unif, int *n_evals, double *newTraj);
+void orc_foo_point(int mode, const double *A_pre, const double *A_post, const double *param, double N, const double *states,
+                   double *out);
+void orc_foo_ode_rk45(const double *A_pre, const double *A_post, const double *param, double N, const double *initial,
+                      const double *t, int n, double *OdeTraj);
+
 /* B independent FULL evaluations on one core (item-major inputs like the product's C ABI). */
 int orc_full_loglik_batch(const orc_cfg *c, const orc_init *init, long B, const double *param,
                           const double *initial, const double *t, int nt, int gridsize,

@@ -48,7 +48,7 @@ def lib():
             build()
         _lib = C.CDLL(_SO)
         for name in ("orc_volz_loglik_nh2", "orc_volz_loglik_nh3", "orc_coal_loglik3", "orc_coal_loglik",
-                     "orc_log_like_traj_general2", "orc_ode_rk45_stop"):
+                     "orc_log_like_traj_general2", "orc_ode_rk45_stop", "orc_volz_loglik_nh"):
             getattr(_lib, name).restype = C.c_double
     return _lib
 
@@ -483,3 +483,193 @@ def Traj_sim_SIRS(initial, OdeTraj, Filter, t_correct, *, normals):
     if st:
         raise ValueError("chol(): decomposition failed")
     return {"SimuTraj": out, "loglike": ll.value}
+
+
+# ---- legacy copies of the pipeline: src/LNA_NS_general.cpp, class Foo of src/generalLNA.cpp, ESlice_SIRS ----
+# x_i has two entries there: (nch, nparam); param = (R0, gamma, ..., ch_1, ..).
+
+def _xi2(x_i):
+    arr = np.ascontiguousarray(np.asarray(x_i, dtype=np.float64).round().astype(np.int32)[:2])
+    return arr, arr.ctypes.data_as(_ip)
+
+
+def betafs(ts, param, x_r, x_i):
+    """LNA_NS_general.cpp:25-47"""
+    ts, param, x_r = _d(ts), _d(param), _d(x_r)
+    xi, xip = _xi2(x_i)
+    out = np.empty(len(ts))
+    lib().orc_general_betafs(_p(ts), len(ts), _p(param), _p(x_r), xip, _p(out))
+    return out
+
+
+def betaf(t, param, x_r, x_i):
+    """LNA_NS_general.cpp:6-21"""
+    return float(betafs([t], param, x_r, x_i)[0])
+
+
+def _general_point(mode, states, param, t, x_r, x_i):
+    states, param, x_r = _d(states), _d(param), _d(x_r)
+    xi, xip = _xi2(x_i)
+    out = np.empty((2, 2), order="F") if mode else np.empty(2)
+    lib().orc_general_point(mode, _p(states), _p(param), len(param), C.c_double(t), _p(x_r), xip, _p(out))
+    return out
+
+
+def ODE_general_one(states, param, t, x_r, x_i):
+    """LNA_NS_general.cpp:52-62"""
+    return _general_point(0, states, param, t, x_r, x_i)
+
+
+def general_F(states, param, t, x_r, x_i):
+    """LNA_NS_general.cpp:66-72"""
+    return _general_point(1, states, param, t, x_r, x_i)
+
+
+def General_ODE_rk45(initial, t, param, x_r, x_i):
+    """LNA_NS_general.cpp:76-98"""
+    initial, t, param, x_r = _d(initial), _d(t), _d(param), _d(x_r)
+    xi, xip = _xi2(x_i)
+    out = np.empty((len(t), 3), order="F")
+    lib().orc_general_ode_rk45(_p(initial), _p(t), len(t), _p(param), len(param), _p(x_r), xip, _p(out))
+    return out
+
+
+def General_IntSigmaF(Traj_par, param, x_r, x_i):
+    """LNA_NS_general.cpp:103-135 (the reference names the second entry "Simga")"""
+    T, param, x_r = _f(Traj_par), _d(param), _d(x_r)
+    xi, xip = _xi2(x_i)
+    F, S = np.empty((2, 2), order="F"), np.empty((2, 2), order="F")
+    lib().orc_general_intsigmaf(_p(T), T.shape[0], _p(param), len(param), _p(x_r), xip, _p(F), _p(S))
+    return {"expF": F, "Simga": S}
+
+
+def General_KOM_Filter(OdeTraj, param, gridsize, x_r, x_i):
+    """LNA_NS_general.cpp:139-159"""
+    O, param, x_r = _f(OdeTraj), _d(param), _d(x_r)
+    xi, xip = _xi2(x_i)
+    k = (O.shape[0] - 1) // gridsize
+    A, S = _cubes(2, k)
+    lib().orc_general_kom_filter(_p(O), O.shape[0], _p(param), len(param), int(gridsize), _p(x_r), xip, _p(A), _p(S))
+    return {"A": A, "Sigma": S}
+
+
+def _legacy_centred(mode, X, OdeTraj, Filter, t_correct):
+    O = _f(OdeTraj)
+    A, S = _f(Filter["A"]), _f(Filter["Sigma"])
+    X = _f(X) if mode in (0, 2) else _d(X)
+    out = np.empty_like(O, order="F")
+    ll = C.c_double()
+    st = lib().orc_legacy_centred(mode, _p(X), _p(O), O.shape[0], _p(A), _p(S), C.c_double(t_correct), _p(out), C.byref(ll))
+    if st:
+        raise ValueError("legacy centred call failed")
+    return out, ll.value
+
+
+def log_like_traj_general(SdeTraj, OdeTraj, Filter, gridsize, t_correct, _mode=0):
+    """LNA_NS_general.cpp:164-200 (density through inv2)"""
+    return _legacy_centred(_mode, SdeTraj, OdeTraj, Filter, t_correct)[1]
+
+
+def Traj_sim_general(OdeTraj, Filter, t_correct, *, normals, _mode=1):
+    """LNA_NS_general.cpp:205-250 with supplied normals (k*2, step-major)"""
+    out, ll = _legacy_centred(_mode, normals, OdeTraj, Filter, t_correct)
+    return {"SimuTraj": out, "loglike": ll}
+
+
+def Traj_sim_ezG(initial, times, param, gridsize, x_r, x_i, t_correct, *, normals):
+    """LNA_NS_general.cpp:257-314"""
+    initial, times, param, x_r, nrm = _d(initial), _d(times), _d(param), _d(x_r), _d(normals)
+    xi, xip = _xi2(x_i)
+    nrow = len(times) // gridsize + 1
+    out = np.empty((nrow, 3), order="F")
+    ll = C.c_double()
+    st = lib().orc_traj_sim_ezG(_p(initial), _p(times), len(times), _p(param), len(param), int(gridsize), _p(x_r), xip,
+                                C.c_double(t_correct), _p(nrm), _p(out), C.byref(ll))
+    if st:
+        raise ValueError("Traj_sim_ezG failed")
+    return {"SimuTraj": out, "loglike": ll.value}
+
+
+def volz_loglik_nh(init, f1, betaN, t_correct, gridsize=1):
+    """SIR_phylodyn.cpp:517-560 (f1 = a LOG trajectory)"""
+    ini = init if isinstance(init, Init) else Init(init)
+    f1, b = _f(f1), _d(betaN)
+    return float(lib().orc_volz_loglik_nh(ini.ref, _p(f1), f1.shape[0], _p(b), C.c_double(t_correct)))
+
+
+def _eslice_legacy(kind, f_cur, OdeTraj, FTs, state, init, betaN_or_params4, t_correct, lam, reps, volz, normals, uniforms):
+    F, O = _f(f_cur), _f(OdeTraj)
+    A, S = _f(FTs["A"]), _f(FTs["Sigma"])
+    ini = init if isinstance(init, Init) else Init(init)
+    b, nrm, unf, state = _d(betaN_or_params4), _d(normals), _d(uniforms), _d(state)
+    out = np.empty_like(F, order="F")
+    nu, ne = C.c_int(), C.c_int()
+    st = lib().orc_eslice_legacy(ini.ref, kind, _p(F), F.shape[0], F.shape[1] - 1, _p(O), _p(A), _p(S), _p(state), _p(b),
+                                 C.c_double(t_correct), C.c_double(lam), int(reps), int(bool(volz)), _p(nrm), _p(unf),
+                                 C.byref(nu), C.byref(ne), _p(out))
+    if st == 1:
+        raise ValueError("chol(): decomposition failed")
+    return {"newTraj": out, "status": st, "n_uniforms": nu.value, "n_evals": ne.value}
+
+
+def ESlice_general(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, reps=1, gridsize=100, volz=False, *,
+                   normals, uniforms, _kind=0):
+    """LNA_NS_general.cpp:320-394; normals reps x k*2, uniforms consumed contiguously over the repetitions"""
+    return _eslice_legacy(_kind, f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam, reps, volz, normals, uniforms)
+
+
+def ESlice_SIRS(f_cur, OdeTraj, FTs, state, init, params4, t_correct, lam=10.0, reps=1, gridsize=100, volz=True, *,
+                normals, uniforms):
+    """SIRS_period.cpp:313-402; params4 = (beta, A, period, N)"""
+    return _eslice_legacy(1, f_cur, OdeTraj, FTs, state, init, params4, t_correct, lam, reps, volz, normals, uniforms)
+
+
+class Foo:
+    """class Foo of src/generalLNA.cpp:9-372 (m = 3 reactions, p = 2 species)"""
+
+    def __init__(self, A_pre, A_post, param, x_i, x_r):
+        self.A_pre, self.A_post = _f(A_pre), _f(A_post)
+        self.param, self.x_i, self.x_r = _d(param), np.asarray(x_i), _d(x_r)
+        self.m, self.p, self.N = self.A_pre.shape[0], self.A_pre.shape[1], float(self.x_r[0])
+
+    def _point(self, mode, states, shape):
+        out = np.empty(shape, order="F")
+        lib().orc_foo_point(mode, _p(self.A_pre), _p(self.A_post), _p(self.param), C.c_double(self.N), _p(_d(states)), _p(out))
+        return out
+
+    def rate_h(self, states, t=0.0):
+        return self._point(0, states, 3)
+
+    def dh(self, states, t=0.0):
+        return self._point(1, states, (3, 2))
+
+    def ODE_ones(self, states, t=0.0):
+        return self._point(2, states, 2)
+
+    def F_matrix(self, states, t=0.0):
+        """A' dh: what F_vec (:92-94) computes before its arma::vec return type rejects it"""
+        return self._point(3, states, (2, 2))
+
+    def ODE_rk45(self, initial, t):
+        initial, t = _d(initial), _d(t)
+        out = np.empty((len(t), 3), order="F")
+        lib().orc_foo_ode_rk45(_p(self.A_pre), _p(self.A_post), _p(self.param), C.c_double(self.N), _p(initial), _p(t),
+                               len(t), _p(out))
+        return out
+
+    def LNA_log_like_traj(self, SdeTraj, OdeTraj, Filter, gridsize, t_correct):
+        return log_like_traj_general(SdeTraj, OdeTraj, Filter, gridsize, t_correct, _mode=2 if _is_ref() else 0)
+
+    def LNA_Traj_sim(self, OdeTraj, Filter, t_correct, *, normals):
+        return Traj_sim_general(OdeTraj, Filter, t_correct, normals=normals, _mode=3 if _is_ref() else 1)
+
+    def LNA_ESlice(self, f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam=10.0, reps=1, gridsize=100, volz=False, *,
+                   normals, uniforms):
+        return ESlice_general(f_cur, OdeTraj, FTs, state, init, betaN, t_correct, lam, reps, gridsize, volz, normals=normals,
+                              uniforms=uniforms, _kind=2 if _is_ref() else 0)
+
+
+def _is_ref():
+    """True when these wrappers run over the reference's code (oracle/reference.py swaps `lib`): there the Foo methods are
+    reached through the class (modes 2, 3 / kind 2 of the harness); the C oracle has one body for both spellings."""
+    return getattr(lib, "__module__", __name__) != __name__

@@ -64,7 +64,7 @@ class _RefLib:
         self._dll = C.CDLL(so)
         self._dll.ref_last_error.restype = C.c_char_p
         for name in ("volz_loglik_nh2", "volz_loglik_nh3", "coal_loglik3", "coal_loglik", "log_like_traj_general2",
-                     "ode_rk45_stop"):
+                     "ode_rk45_stop", "volz_loglik_nh"):
             getattr(self._dll, "ref_" + name).restype = C.c_double
         self._cache = {}
 

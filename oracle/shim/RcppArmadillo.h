@@ -919,6 +919,17 @@ struct exception : std::runtime_error {
 };
 [[noreturn]] inline void stop(const std::string &m) { throw exception(m); }
 
+// Rcpp modules (RCPP_MODULE body of src/generalLNA.cpp): registration is a no-op here, the class is used directly
+template <class T>
+struct class_ {
+    explicit class_(const char *) {}
+    template <class... A> class_ &constructor() { return *this; }
+    template <class M> class_ &field(const char *, M) { return *this; }
+    template <class G> class_ &property(const char *, G) { return *this; }
+    template <class G, class S> class_ &property(const char *, G, S) { return *this; }
+    template <class M> class_ &method(const char *, M) { return *this; }
+};
+
 }  // namespace Rcpp
 
 namespace R {
