@@ -425,14 +425,10 @@ int ref_sirs_centred(int mode, const double *X_or_normals, const double *initial
     if (mode == 0) {
         *loglik = log_like_trajSIRS(M(X_or_normals, nrow, 4), M(OdeTraj, nrow, 4), ft, 1, t_correct);
     } else {
-#ifdef LNA_DROPIN  // the samplers of SIRS_period.cpp are outside the replaced path
-        return -1;
-#else
         streams(X_or_normals, (long)(nrow - 1) * 3, nullptr, 0);
         List r = Traj_sim_SIRS(V(initial, 3), M(OdeTraj, nrow, 4), ft, t_correct);
         put(as<arma::mat>(r[0]), traj_out);
         *loglik = as<double>(r[1]);
-#endif
     }
     return ORC_OK;
     REF_CATCH_STATUS
