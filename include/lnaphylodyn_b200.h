@@ -323,6 +323,19 @@ int lna_eslice_legacy(lna_problem *pb, int64_t B, int kind, int reps, int volz, 
  * arma::vec and IntSigmaF multiplies by an empty local `A` (:130, 146) -- and have no entry point.) */
 int lna_foo(lna_problem *pb, int64_t B, int mode, int n, const double *A_pre, const double *A_post, const double *param,
             const double *N, const double *states_or_initial, const double *t, double *out);
+/* ---- data simulator ----
+ * volz_thin_sir (R/coal_simulation.R:11-70): B genealogies' coalescent times by thinning against the Volz rate on SIR
+ * trajectories given on a fine grid of n points (t, S, I, betaN: item b at + b * traj_stride; traj_stride 0 = one
+ * trajectory for all items), sampling design (samp_times, n_sampled)[ns] shared by all items.  One warp per genealogy, 32
+ * consecutive proposals per round; R's rexp / runif are a counter-based stream (Philox4x32-10, keyed by seed, indexed by
+ * (item_offset + b, proposal number)), replayable with lna_thin_draws, and the result is bit-identical to the sequential
+ * loop consuming that stream.  Outputs per item: coal_times / lineages (B x max_coal, zero-padded), n_coal, n_draws
+ * (proposals consumed), status (1 = max_draws [0 = default cap] or max_coal was hit). */
+int lna_volz_thin_sir(lna_problem *pb, int64_t B, int n, int64_t traj_stride, const double *t, const double *S, const double *I,
+                      const double *betaN, int ns, const double *samp_times, const int32_t *n_sampled, double t_correct,
+                      double lower, uint64_t seed, int64_t item_offset, uint64_t max_draws, int max_coal, double *coal_times,
+                      int32_t *lineages, int32_t *n_coal, uint64_t *n_draws, int32_t *status);
+int lna_thin_draws(lna_problem *pb, uint64_t seed, uint64_t item, uint64_t first, int64_t count, double *ua, double *ub);
 /* Traj_sim_general3 (:771-817): centred LNA simulation with supplied normals (B x k*p, step-major);
  * noise = mvrnormArma(Sigma) (basic_util.cpp:44-58).  Traj_sim_ezG2 (:907-975) = lna_ode_rk45 +
  * lna_kf_param(chol = 0) + lna_ode_coarse_slicer + this. */

@@ -93,6 +93,9 @@ _SIGS = {
     "lna_volz_loglik_nh": (C.c_int, [_vp, _I64] + [_vp] * 3),
     "lna_eslice_legacy": (C.c_int, [_vp, _I64, C.c_int, C.c_int, C.c_int] + [_vp] * 13),
     "lna_foo": (C.c_int, [_vp, _I64, C.c_int, C.c_int] + [_vp] * 7),
+    "lna_volz_thin_sir": (C.c_int, [_vp, _I64, C.c_int, _I64] + [_vp] * 4 + [C.c_int, _vp, _vp, C.c_double, C.c_double,
+                                    C.c_uint64, _I64, C.c_uint64, C.c_int] + [_vp] * 5),
+    "lna_thin_draws": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _I64, _vp, _vp]),
     "lna_chains_create": (_vp, [_vp, _I64]),
     "lna_chains_destroy": (None, [_vp]),
     "lna_chains_init": (C.c_int, [_vp, _vp, _vp]),

@@ -24,6 +24,7 @@
 #include "lna_eslice.cuh"
 #include "lna_sirs.cuh"
 #include "lna_legacy.cuh"
+#include "lna_thin.cuh"
 
 using namespace lna;
 

@@ -137,3 +137,73 @@ extern "C" int lna_foo(lna_problem *pb, int64_t B, int mode, int n, const double
     s.back(out, dout, nB * per);
     return s.finish("lna_foo");
 }
+
+// ------------------------------------------------------------------------------------------------
+// data simulator: volz_thin_sir on the device (lna_thin.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lna_volz_thin_sir(lna_problem *pb, int64_t B, int n, int64_t traj_stride, const double *t, const double *S,
+                                 const double *I, const double *betaN, int ns, const double *samp_times,
+                                 const int32_t *n_sampled, double t_correct, double lower, uint64_t seed, int64_t item_offset,
+                                 uint64_t max_draws, int max_coal, double *coal_times, int32_t *lineages, int32_t *n_coal,
+                                 uint64_t *n_draws, int32_t *status) {
+    if (!pb) return fail("null problem");
+    if (B <= 0) return 0;
+    if (!t || !S || !I || !betaN || !samp_times || !n_sampled || !coal_times || !lineages || !n_coal)
+        return fail("lna_volz_thin_sir: null argument");
+    if (n < 2 || ns < 1 || max_coal < 1 || !(lower > 0.0) || (traj_stride != 0 && traj_stride < n))
+        return fail("lna_volz_thin_sir: bad sizes (n >= 2, ns >= 1, max_coal >= 1, lower > 0, stride 0 or >= n)");
+    for (int s = 0; s < ns; ++s)
+        if (n_sampled[s] < 1) return fail("lna_volz_thin_sir: n_sampled must be positive");
+    for (int64_t b = 0; b < (traj_stride ? B : 1); ++b)  // R: `which.min(ts >= 0) - 1` is 0 otherwise and ts[0] stops the loop
+        if (!(t[b * traj_stride + n - 1] > t_correct)) return fail("lna_volz_thin_sir: the time grid must extend beyond t_correct");
+    const size_t nB = (size_t)B, len = traj_stride ? (size_t)traj_stride * nB : (size_t)n;
+    Stage s(pb);
+    ThinArgs a{};
+    a.t = s.in(t, len);
+    a.S = s.in(S, len);
+    a.I = s.in(I, len);
+    a.betaN = s.in(betaN, len);
+    a.stride = traj_stride;
+    a.n = n;
+    a.samp_times = s.in(samp_times, (size_t)ns);
+    a.n_sampled = s.in(n_sampled, (size_t)ns);
+    a.ns = ns;
+    a.t_correct = t_correct;
+    a.lower = lower;
+    a.seed = seed;
+    a.item_offset = item_offset;
+    a.coal_times = s.tmp<double>(nB * max_coal);
+    a.lineages = s.tmp<int32_t>(nB * max_coal);
+    a.max_coal = max_coal;
+    a.n_coal = s.tmp<int32_t>(nB);
+    a.status = s.tmp<int32_t>(nB);
+    a.n_draws = (unsigned long long *)s.tmp<uint64_t>(nB);
+    a.max_draws = max_draws ? max_draws : 40000000000ull;  // (~ a minute of one warp: a hung launch would cost the GPU box)
+    if (!s.ok) return fail("lna_volz_thin_sir: device staging failed");
+    if (cudaMemsetAsync(a.coal_times, 0, sizeof(double) * nB * max_coal, pb->stream) != cudaSuccess ||
+        cudaMemsetAsync(a.lineages, 0, sizeof(int32_t) * nB * max_coal, pb->stream) != cudaSuccess)
+        return fail("lna_volz_thin_sir: memset failed");
+    k_volz_thin_sir<<<nblk(B, kThinWarps), kThinWarps * 32, 0, pb->stream>>>(B, a);
+    if (launch_check(pb, "k_volz_thin_sir")) return -1;
+    s.back(coal_times, a.coal_times, nB * max_coal);
+    s.back(lineages, a.lineages, nB * max_coal);
+    s.back(n_coal, a.n_coal, nB);
+    s.back(status, a.status, nB);
+    s.back(n_draws, (uint64_t *)a.n_draws, nB);
+    return s.finish("lna_volz_thin_sir");
+}
+
+/* proposals first .. first + count - 1 of genealogy `item`'s stream (test replay: the CPU restatement consumes them) */
+extern "C" int lna_thin_draws(lna_problem *pb, uint64_t seed, uint64_t item, uint64_t first, int64_t count, double *ua,
+                              double *ub) {
+    if (!pb) return fail("null problem");
+    if (count <= 0) return 0;
+    Stage s(pb);
+    double *da = s.tmp<double>((size_t)count), *db = s.tmp<double>((size_t)count);
+    if (!s.ok) return fail("lna_thin_draws: device staging failed");
+    k_thin_draws<<<nblk(count, 256), 256, 0, pb->stream>>>(seed, item, first, count, da, db);
+    if (launch_check(pb, "k_thin_draws")) return -1;
+    s.back(ua, da, (size_t)count);
+    s.back(ub, db, (size_t)count);
+    return s.finish("lna_thin_draws");
+}

@@ -3,9 +3,9 @@ likelihood (SURVEY.md section 8f.2 -- the "input format" row next to the hot pat
 
   coal_lik_init        R/coal_simulation.R:204-277   -> the `Init` sufficient statistics
   summarize_phylo      phylodyn (external, not in the reference tree): sampling / coalescent times of a tree
-  volz_thin_sir        R/coal_simulation.R:11-70     -> synthetic genealogies by thinning (seeded NumPy RNG)
+  volz_thin_sir        R/coal_simulation.R:11-70     -> synthetic genealogies by thinning, ON THE DEVICE (csrc/lna_thin.cuh)
 
-These run once per data set on the host (NumPy); the per-cell reduction of C*D and y happens on the
+coal_lik_init / summarize_phylo run once per data set on the host (NumPy); the per-cell reduction of C*D and y happens on the
 device when the problem is created (csrc/lna_kernels.cuh: k_cell_sums).
 """
 import numpy as np
@@ -83,43 +83,48 @@ def summarize_phylo(edge, edge_length, ntip):
     return {"samp_times": samp_times, "n_sampled": n_sampled.astype(np.float64), "coal_times": np.sort(internal)}
 
 
-def volz_thin_sir(eff_pop, t_correct, samp_times, n_sampled, betaN, rng, lower=1.0):
-    """R/coal_simulation.R:11-70: simulate coalescent times by thinning against the Volz rate on an SIR
-    trajectory `eff_pop` (columns: time, S, I).  `rng` is a numpy Generator (replaces R's rexp/runif)."""
-    eff_pop = np.asarray(eff_pop, dtype=np.float64)
-    samp_times = np.asarray(samp_times, dtype=np.float64)
-    n_sampled = np.asarray(n_sampled, dtype=np.int64)
-    coal_times, lineages = [], []
-    curr = 0
-    active = int(n_sampled[curr])
-    time = float(samp_times[curr])
-    traj = 1.0 / (betaN * eff_pop[:, 1] / (eff_pop[:, 2] / 2.0))
-    ts = t_correct - eff_pop[:, 0]
-    i = int(np.argmin(ts >= 0)) - 1                # which.min(ts >= 0) - 1, then 0-based = that - 1 + ... see below
-    # R: i = which.min(ts>=0) - 1 is a 1-based index of the last grid time <= t_correct; 0-based: subtract 1
-    i = max(i, 0)
-    max_samp = samp_times.max()
-    while time <= max_samp or active > 1:
-        if active == 1:
-            curr += 1
-            active += int(n_sampled[curr])
-            time = float(samp_times[curr])
-        time = time + rng.exponential(1.0 / (0.5 * active * (active - 1) / lower))
-        while time > ts[i]:
-            i -= 1
-            if i < 0:
-                i = 0
-                break
-        thed = traj[i]
-        if curr < len(samp_times) - 1 and time >= samp_times[curr + 1]:
-            curr += 1
-            active += int(n_sampled[curr])
-            time = float(samp_times[curr])
-        elif rng.random() <= lower / thed:
-            time = min(time, t_correct)
-            coal_times.append(time)
-            lineages.append(active)
-            active -= 1
-    coal_times = np.array(coal_times)
-    return {"coal_times": coal_times, "lineages": np.array(lineages), "samp_times": samp_times,
-            "n_sampled": n_sampled.astype(np.float64)}
+def volz_thin_sir(eff_pop, t_correct, samp_times, n_sampled, betaN, seed=0, lower=1.0, n_genealogies=None, item_offset=0,
+                  max_draws=0, device=0):
+    """R/coal_simulation.R:11-70 on the device (csrc/lna_thin.cuh: one warp per genealogy, 32 thinning proposals per round):
+    coalescent times simulated by thinning against the Volz rate on SIR trajectories `eff_pop` (columns time, S, I; one
+    n x 3 trajectory, or B x n x 3 for B genealogies on their own trajectories) with `betaN` on the same grid.  R's rexp /
+    runif are a counter-based stream keyed by `seed` and indexed by (item_offset + genealogy, proposal number).
+    `n_genealogies = B` with a single trajectory draws B independent genealogies on it; the result is then a list."""
+    from . import _lib, api
+    E = np.asarray(eff_pop, dtype=np.float64)
+    single_traj = E.ndim == 2
+    B = int(n_genealogies) if n_genealogies is not None else (1 if single_traj else E.shape[0])
+    if not single_traj and E.shape[0] != B:
+        raise ValueError("n_genealogies must match the number of trajectories")
+    n = E.shape[-2]
+    if not np.all(E[..., -1, 0] > t_correct):
+        # R: i = which.min(ts >= 0) - 1 is 0 when no grid time lies beyond t_correct, and `ts[0]` then stops the loop with an error
+        raise ValueError("volz_thin_sir: the time grid must extend beyond t_correct")
+    cols = [np.ascontiguousarray(E[..., j]).reshape(-1) for j in range(3)]
+    bn = np.ascontiguousarray(np.broadcast_to(np.asarray(betaN, dtype=np.float64), E.shape[:-1])).reshape(-1)
+    st = np.ascontiguousarray(np.asarray(samp_times, dtype=np.float64))
+    ns = np.ascontiguousarray(np.asarray(n_sampled, dtype=np.float64).round().astype(np.int32))
+    max_coal = int(ns.sum()) - 1
+    pb = api.problem_for(np.array([0.0, 1.0]), [1.0], [0, 2, 0, 1], 1, device=device)
+    ct, lin = np.empty((B, max_coal)), np.empty((B, max_coal), dtype=np.int32)
+    nc, stt, nd = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.uint64)
+    _lib.check(_lib.lib().lna_volz_thin_sir(pb.h, B, n, 0 if single_traj else n, api._ptr(cols[0]), api._ptr(cols[1]),
+                                            api._ptr(cols[2]), api._ptr(bn), len(st), api._ptr(st), api._ptr(ns),
+                                            float(t_correct), float(lower), int(seed), int(item_offset), int(max_draws),
+                                            max_coal, api._ptr(ct), api._ptr(lin), api._ptr(nc), api._ptr(nd), api._ptr(stt)),
+               "lna_volz_thin_sir")
+    out = [{"coal_times": ct[b, :nc[b]].copy(), "lineages": lin[b, :nc[b]].copy(), "samp_times": st,
+            "n_sampled": ns.astype(np.float64), "n_draws": int(nd[b]), "status": int(stt[b])} for b in range(B)]
+    for o in out:
+        o["intercoal_times"] = np.diff(o["coal_times"], prepend=0.0)
+    return out[0] if (n_genealogies is None and single_traj) else out
+
+
+def thin_draws(seed, item, first, count, device=0):
+    """proposals first .. first + count - 1 of genealogy `item`'s stream: (waiting-time uniforms, thinning marks)"""
+    from . import _lib, api
+    pb = api.problem_for(np.array([0.0, 1.0]), [1.0], [0, 2, 0, 1], 1, device=device)
+    ua, ub = np.empty(count), np.empty(count)
+    _lib.check(_lib.lib().lna_thin_draws(pb.h, int(seed), int(item), int(first), int(count), api._ptr(ua), api._ptr(ub)),
+               "lna_thin_draws")
+    return ua, ub

@@ -1484,6 +1484,71 @@ void orc_foo_ode_rk45(const double *A_pre, const double *A_post, const double *p
     }
 }
 
+/* ---------------------------------------------------------------- data simulators */
+
+/* volz_thin_sir: R/coal_simulation.R:11-70.  Coalescent times by thinning against the Volz rate on an SIR trajectory
+ * (t, S, I on a fine grid, betaN on the same grid).  R's rexp / runif are replaced by a pre-drawn stream indexed by
+ * PROPOSAL number: proposal j waits -log(ua[j]) / rate and, if it is not overtaken by the next sampling time, is accepted
+ * when ub[j] <= lower / thed (ub[j] is skipped otherwise, like the short-circuited runif(1) of the reference).
+ * Returns 0, or 1 when the stream (n_avail proposals) or the output (max_coal) ran out. */
+int orc_volz_thin_sir(const double *t, const double *S, const double *I, const double *betaN, int n, double t_correct,
+                      const double *samp_times, const int *n_sampled, int ns, double lower, const double *ua,
+                      const double *ub, long n_avail, double *coal_times, int *lineages, int max_coal, int *n_coal,
+                      long *n_draws) {
+    int first_false = n;
+    for (int r = 0; r < n; r++)
+        if (!(t_correct - t[r] >= 0)) {
+            first_false = r;
+            break;
+        }
+    int i = first_false >= n ? 0 : (first_false - 1 > 0 ? first_false - 1 : 0);
+    double max_samp = samp_times[0];
+    for (int s = 1; s < ns; s++)
+        if (samp_times[s] > max_samp) max_samp = samp_times[s];
+    int curr = 0, active = n_sampled[0], ncoal = 0, status = 0;
+    double time = samp_times[0];
+    long draw = 0;
+    while (time <= max_samp || active > 1) {
+        if (active == 1) {
+            if (curr + 1 >= ns) {
+                status = 1;
+                break;
+            }
+            curr = curr + 1;
+            active = active + n_sampled[curr];
+            time = samp_times[curr];
+        }
+        if (draw >= n_avail || ncoal >= max_coal) {
+            status = 1;
+            break;
+        }
+        time = time + (-log(ua[draw])) / (0.5 * active * (active - 1) / lower);
+        while (time > t_correct - t[i]) {
+            i = i - 1;
+            if (i < 0) {
+                i = 0;
+                break;
+            }
+        }
+        double thed = 1.0 / (betaN[i] * S[i] / (I[i] / 2.0));
+        if (curr < ns - 1 && time >= samp_times[curr + 1]) {
+            curr = curr + 1;
+            active = active + n_sampled[curr];
+            time = samp_times[curr];
+        } else if (ub[draw] <= lower / thed) {
+            time = time < t_correct ? time : t_correct;
+            coal_times[ncoal] = time;
+            lineages[ncoal] = active;
+            ncoal++;
+            active = active - 1;
+        }
+        draw++;
+    }
+    *n_coal = ncoal;
+    *n_draws = draw;
+    return status;
+}
+
 /* ---------------------------------------------------------------- batch driver (bench baseline) */
 
 /* B independent FULL evaluations, item-major inputs like the product's C ABI; one core.

@@ -189,6 +189,12 @@ void orc_foo_point(int mode, const double *A_pre, const double *A_post, const do
 void orc_foo_ode_rk45(const double *A_pre, const double *A_post, const double *param, double N, const double *initial,
                       const double *t, int n, double *OdeTraj);
 
+/* data simulator: volz_thin_sir, R/coal_simulation.R:11-70, on a pre-drawn stream indexed by proposal number */
+int orc_volz_thin_sir(const double *t, const double *S, const double *I, const double *betaN, int n, double t_correct,
+                      const double *samp_times, const int *n_sampled, int ns, double lower, const double *ua,
+                      const double *ub, long n_avail, double *coal_times, int *lineages, int max_coal, int *n_coal,
+                      long *n_draws);
+
 /* B independent FULL evaluations on one core (item-major inputs like the product's C ABI). */
 int orc_full_loglik_batch(const orc_cfg *c, const orc_init *init, long B, const double *param,
                           const double *initial, const double *t, int nt, int gridsize,

@@ -673,3 +673,21 @@ def _is_ref():
     """True when these wrappers run over the reference's code (oracle/reference.py swaps `lib`): there the Foo methods are
     reached through the class (modes 2, 3 / kind 2 of the harness); the C oracle has one body for both spellings."""
     return getattr(lib, "__module__", __name__) != __name__
+
+
+# ---- data simulator (SURVEY 8f.4) -------------------------------------------------------------------------------------
+
+def volz_thin_sir(eff_pop, t_correct, samp_times, n_sampled, betaN, lower=1.0, *, ua, ub):
+    """R/coal_simulation.R:11-70 on a pre-drawn stream indexed by proposal number (ua -> waiting times, ub -> thinning marks)"""
+    E = np.asarray(eff_pop, dtype=np.float64)
+    t, S, I, b = _d(E[:, 0]), _d(E[:, 1]), _d(E[:, 2]), _d(betaN)
+    st, ua, ub = _d(samp_times), _d(ua), _d(ub)
+    ns_arr = np.ascontiguousarray(np.asarray(n_sampled, dtype=np.float64).round().astype(np.int32))
+    max_coal = int(ns_arr.sum())
+    ct, lin = np.empty(max_coal), np.empty(max_coal, dtype=np.int32)
+    nc, nd = C.c_int(), C.c_long()
+    rc = lib().orc_volz_thin_sir(_p(t), _p(S), _p(I), _p(b), len(t), C.c_double(t_correct), _p(st), ns_arr.ctypes.data_as(_ip),
+                                 len(st), C.c_double(lower), _p(ua), _p(ub), C.c_long(len(ua)), _p(ct),
+                                 lin.ctypes.data_as(_ip), max_coal, C.byref(nc), C.byref(nd))
+    return {"coal_times": ct[:nc.value].copy(), "lineages": lin[:nc.value].copy(), "samp_times": st,
+            "n_sampled": ns_arr.astype(np.float64), "n_draws": nd.value, "status": rc}

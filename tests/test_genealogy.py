@@ -44,8 +44,9 @@ def test_volz_thin_sir_synthetic_genealogy():
     times = np.linspace(0, 100, 2001)
     ode = orc.ODE_rk45([1e6, 1.0], times, [2.2, 0.2], [1e6], [0, 2, 0, 1])
     betaN = orc.betaTs([2.2, 0.2], times, [1e6], [0, 2, 0, 1])
+    from oracle import sampler
     rng = np.random.default_rng(20260)
-    c = gen.volz_thin_sir(ode, 90.0, [0, 10, 20, 40, 80, 85], [100, 100, 145, 145, 9, 1], betaN, rng)
+    c = sampler.volz_thin_sir(ode, 90.0, [0, 10, 20, 40, 80, 85], [100, 100, 145, 145, 9, 1], betaN, rng)
     assert len(c["coal_times"]) == 499
     assert np.all(np.diff(c["coal_times"]) >= 0) and c["coal_times"].max() <= 90.0
     ini = gen.coal_lik_init(c["samp_times"], c["n_sampled"], c["coal_times"], times[::50])
