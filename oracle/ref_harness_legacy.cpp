@@ -20,6 +20,11 @@
 
 #include "ref_harness_util.h"
 
+#ifdef LNA_DROPIN
+List General_MCMC_with_ESlice_chains(List MCMC_setting, arma::mat par, arma::cube OriginTraj, arma::ivec ESS_vec, int niter,
+                                     int burn1, int thin, double seed, arma::ivec devices);
+#endif
+
 // exported by src/LNA_NS_general.cpp and src/SIRS_period.cpp, declared in no header of theirs
 arma::vec betafs(arma::vec ts, arma::vec param, arma::vec x_r, arma::ivec x_i);
 double betaf(double t, arma::vec param, arma::vec x_r, arma::ivec x_i);
@@ -186,5 +191,42 @@ int ref_foo_intsigmaf_runs(const double *A_pre, const double *A_post, const doub
     return 0;
     REF_CATCH_STATUS
 }
+
+#ifdef LNA_DROPIN
+// General_MCMC_with_ESlice_chains (integration/rcpp_chains.cpp): the batched entry of the binding; no reference counterpart
+// (the reference runs one chain per call), so this entry point exists in the drop-in build only
+int ref_chains_run(const orc_cfg *c, const orc_init *init, const double *times, int nt, int gridsize, double t_correct,
+                   const double *prior10, const double *proposal5, const int *ess7, long B, const double *par,
+                   const double *eps, int eps_shared, int niter, int burn1, int thin, double seed, const int *devices, int ndev,
+                   double *par_hist, double *l, double *l1, double *par_final, double *latent, double *coalLog) {
+    REF_TRY
+    const int nch = c->x_i[0], npar = 2 + c->nparam_total, k = (nt - 1) / gridsize, p = c->p;
+    List setting, prior(5), proposal(5);
+    for (int i = 0; i < 5; ++i) {
+        prior[i] = V(prior10 + 2 * i, 2);
+        proposal[i] = V(proposal5 + i, 1);
+    }
+    arma::vec xi(4);
+    for (int i = 0; i < 4; ++i) xi[i] = c->x_i[i];
+    setting["times"] = V(times, nt);
+    setting["x_r"] = V(c->x_r, nch + 1);
+    setting["x_i"] = xi;
+    setting["t_correct"] = t_correct;
+    setting["gridsize"] = gridsize;
+    setting["prior"] = prior;
+    setting["proposal"] = proposal;
+    setting["Init"] = make_init(init);
+    List r = General_MCMC_with_ESlice_chains(setting, M(par, npar, B), CU(eps, k, p, eps_shared ? 1 : B), IV(ess7, 7), niter, burn1,
+                                             thin, seed, IV(devices, ndev));
+    put(as<arma::cube>(r["par"]), par_hist);
+    put(as<arma::mat>(r["l"]), l);
+    put(as<arma::mat>(r["l1"]), l1);
+    put(as<arma::mat>(r["par_final"]), par_final);
+    put(as<arma::cube>(r["LatentTraj"]), latent);
+    put(as<arma::mat>(r["coalLog"]), coalLog);
+    return ORC_OK;
+    REF_CATCH_STATUS
+}
+#endif
 
 }  // extern "C"

@@ -58,7 +58,7 @@ def test_full_loglik_batch_vs_oracle(api, name, request):
     res = pb.full_loglik(par[:, 2:], par[:, :2], eps, want=("coalLog", "FT", "Ode", "betaN", "LatentTraj"))
     res_ll_only = pb.full_loglik(par[:, 2:], par[:, :2], eps)
     cfg, ini = orc.Cfg(g.x_r, g.x_i, 42), orc.Init(g.init)
-    worst = 0.0
+    worst, worst_ft = 0.0, {"A": 0.0, "Sigma": 0.0, "LatentTraj": 0.0}
     for b in range(B):
         o = orc.full_loglik(cfg, ini, par[b, 2:], par[b, :2], g.times, g.gridsize, eps[b], g.t_correct)
         assert o["status"] == res["status"][b]
@@ -68,11 +68,19 @@ def test_full_loglik_batch_vs_oracle(api, name, request):
             worst = max(worst, abs(res["coalLog"][b] - o["coalLog"]) / abs(o["coalLog"]))
         assert res_ll_only["coalLog"][b] == res["coalLog"][b]
         assert relerr(res["Ode"][b], o["Ode"]) < TOL
-        assert relerr(res["FT"]["A"][b], o["FT"]["A"]) < 1e-9
-        assert np.max(np.abs(res["FT"]["Sigma"][b] - o["FT"]["Sigma"])) < 1e-8
         assert relerr(res["betaN"][b], o["betaN"]) < TOL
-        assert np.max(np.abs(res["LatentTraj"][b][:, 1:] - o["LatentTraj"][:, 1:]) /
-                      np.maximum(np.abs(o["LatentTraj"][:, 1:]), 1.0)) < TOL
+        # FT$A, FT$Sigma (= L) and the latent states: 1e-10 relative to the size of the object each entry belongs to --
+        # the 2 x 2 matrix of its LNA interval, the trajectory column.  Entry-wise relative error is not a meaningful bar
+        # for the entries that are differences of O(1) quantities (A's off-diagonals of 1e-6 next to diagonals of 1, the
+        # Cholesky factor's l11 = sqrt(s11 - l10^2), a latent I of a few individuals next to S of 1e6).
+        for key in ("A", "Sigma"):
+            d, ref = res["FT"][key][b], o["FT"][key]
+            scale = np.max(np.abs(ref), axis=(0, 1), keepdims=True)
+            worst_ft[key] = max(worst_ft[key], float(np.max(np.abs(d - ref) / scale)))
+        lat, lref = res["LatentTraj"][b][:, 1:], o["LatentTraj"][:, 1:]
+        worst_ft["LatentTraj"] = max(worst_ft["LatentTraj"], float(np.max(np.abs(lat - lref) / np.max(np.abs(lref), axis=0))))
+    print("worst scaled errors:", worst_ft, "coalLog", worst)
+    assert all(v < TOL for v in worst_ft.values()), worst_ft
     assert worst < TOL, worst
     assert np.sum(res["coalLog"] != orc.SENTINEL) >= B // 4 and np.sum(res["coalLog"] == orc.SENTINEL) >= 1
 
