@@ -22,6 +22,7 @@
 #include "lna_kernels.cuh"
 #include "lna_split.cuh"
 #include "lna_eslice.cuh"
+#include "lna_async.cuh"
 #include "lna_sirs.cuh"
 #include "lna_legacy.cuh"
 #include "lna_thin.cuh"
@@ -338,6 +339,26 @@ extern "C" lna_problem *lna_problem_create(const lna_cfg *cfg, const lna_init *i
         }
         P.cellCD = cd;
         P.cellY = yy;
+        // upper bounds of the not-yet-visited coalescent terms (lna_async.cuh): cell i sits at row Lrow - i
+        std::vector<double> ub((size_t)P.nrow, 0.0);
+        for (int r = P.nrow - 1; r >= 0; --r) {
+            double u = r + 1 < P.nrow ? ub[(size_t)r + 1] : 0.0;
+            const int i = P.Lrow - (r + 1);  // the cell whose row is r + 1
+            if (r + 1 < P.nrow && i >= 0 && i < P.n0 && pb->cellCnt[i] > 0) {
+                const double a_ = pb->cellCD[i], y_ = pb->cellY[i];
+                if (y_ > 0.0) u += a_ > 0.0 ? y_ * (std::log(y_ / (2.0 * a_)) - 1.0) : INFINITY;
+            }
+            ub[(size_t)r] = u;
+        }
+        P.rowUB = dev_upload(pb, ub.data(), ub.size());
+        if (!P.rowUB) {
+            fail("lna_problem_create: device allocation failed");
+            lna_problem_destroy(pb);
+            return nullptr;
+        }
+        bool ok = true;  // change points on interval boundaries (or beyond the grid: never applied)
+        for (int j = 0; j < P.nch && ok; ++j) ok = pb->chidx[j] % P.g == 0 || pb->chidx[j] > P.k * P.g;
+        P.async_ok = ok ? 1 : 0;
     }
     pb->tab_bytes = tables_bytes(P.nch, P.k, P.n0);
     if (cfg->model == LNA_MODEL_SIRS_PERIOD) {

@@ -30,7 +30,7 @@ static bool cand_alloc(lna_problem *pb, Scratch &s, size_t base, long long B, lo
     cb.cand_ll = (double *)s.get(base + 9, sizeof(double) * B);
     cb.theta = (double *)s.get(base + 10, sizeof(double) * B);
     cb.list = (int *)s.get(base + 11, sizeof(int) * B * 2);
-    cb.count = (int *)s.get(base + 12, sizeof(int) * 24);
+    cb.count = (int *)s.get(base + 12, sizeof(int) * 32);  // [0, 24): compaction counts, [31]: k_ess_par_async's work counter
     return cb.list && cb.count && cb.cA && cb.cL && cb.cOde && cb.cBeta && cb.cLat && cb.win_slot && cb.n_evals && cb.status && cb.accept &&
            cb.cand_ll && cb.theta;
 }
@@ -168,10 +168,64 @@ static int slice_plan_slots(const lna_problem *pb, long long B, int W) {
     return std::max(tot, 4);
 }
 
+// ESlice_par_General of resident chains without wave barriers and with provable early rejection (lna_async.cuh):
+// W lanes per chain, lane w walks candidates w+1, w+1+W, ..  LNA_ESS_ASYNC=0 keeps the wave kernels, LNA_ESS_ASYNC_W forces W.
+static int ess_async_width(const lna_problem *pb, long long planB, const CandArgs &a0, int W_req, const CandBuf &cb, long long B) {
+    const DevProb &P = pb->dp;
+    if (!P.async_ok || !P.has_init || a0.ess[6] || W_req != 0) return 0;  // (an explicit speculation width asks for the wave kernel)
+    if (const char *e = getenv("LNA_ESS_ASYNC"))
+        if (atoi(e) == 0) return 0;
+    int w = 8;
+    if (const char *e = getenv("LNA_ESS_ASYNC_W")) {
+        w = atoi(e);
+    } else {
+        // measured (tools/async_sweep.sh, profiles/r2_async_slice.md): 8 lanes per chain win where they make 1-2 warps per SM
+        // sub-partition (4096 chains: 1.08 -> 0.99 ms per iteration); smaller batches are faster with all candidates of a
+        // chain in flight at once (wave kernels), larger ones are throughput-bound either way
+        const long long warps = planB * 8 / 32, subp = (long long)pb->sm_count * 4;
+        if (warps < subp * 5 / 4 || warps > subp * 5 / 2) return 0;
+    }
+    if (w != 1 && w != 2 && w != 4 && w != 8 && w != 16 && w != 32) return 0;
+    if (cb.NC < B * w) return 0;
+    return w;
+}
+
 template <int kProp>
 static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, const CandBuf &cb,
                        long long planB = 0) {
     if (planB <= 0) planB = B;
+    if constexpr (kProp == PROP_ESS_PAR) {
+        const int wa = ess_async_width(pb, planB, a0, W, cb, B);
+        if (wa) {
+            // persistent: at most `wps` warps per SM sub-partition (LNA_ESS_ASYNC_WPS, default 2), groups of wa lanes pull chains
+            int wps = 2;
+            if (const char *e = getenv("LNA_ESS_ASYNC_WPS")) wps = std::max(1, atoi(e));
+            const long long warps_needed = (B * wa + 31) / 32, warps_cap = (long long)pb->sm_count * 4 * wps;
+            const long long warps = std::min(warps_needed, warps_cap);
+            const unsigned grid = (unsigned)((warps + 3) / 4);
+            // tables + per-thread eps slots + per-group staging of the chain's scalars, uniforms and change ratios
+            const size_t sm = full_eval_smem_bytes(pb->tab_bytes, 128) +
+                              sizeof(double) * (size_t)(128 / wa) * (size_t)(kMaxUnif + 9 + 2 * pb->dp.nch);
+            if (sm > 48 * 1024) {
+                if (sm > 200 * 1024) return fail("k_ess_par_async: %d change points do not fit in shared memory", pb->dp.nch);
+                big_smem_attr(k_ess_par_async<1>, pb->device);
+                big_smem_attr(k_ess_par_async<2>, pb->device);
+                big_smem_attr(k_ess_par_async<4>, pb->device);
+            }
+            CandArgs aa = a0;
+            aa.work_counter = cb.count + 31;
+            if (cudaMemsetAsync(aa.work_counter, 0, sizeof(int), pb->stream) != cudaSuccess) return fail("memset failed");
+            switch (wa) {
+                case 1: k_ess_par_async<1><<<grid, 128, sm, pb->stream>>>(pb->dp, pb->seg, B, aa); break;
+                case 2: k_ess_par_async<2><<<grid, 128, sm, pb->stream>>>(pb->dp, pb->seg, B, aa); break;
+                case 4: k_ess_par_async<4><<<grid, 128, sm, pb->stream>>>(pb->dp, pb->seg, B, aa); break;
+                case 8: k_ess_par_async<8><<<grid, 128, sm, pb->stream>>>(pb->dp, pb->seg, B, aa); break;
+                case 16: k_ess_par_async<16><<<grid, 128, sm, pb->stream>>>(pb->dp, pb->seg, B, aa); break;
+                default: k_ess_par_async<32><<<grid, 128, sm, pb->stream>>>(pb->dp, pb->seg, B, aa); break;
+            }
+            return launch_check(pb, "k_ess_par_async");
+        }
+    }
     CandArgs a = a0;
     a.first_cand = 0;
     a.slot_base = 0;

@@ -53,6 +53,10 @@ struct DevProb {
     const double *cellCD;  // [n0]  sum_{e in cell} C_e*D_e
     const double *cellY;   // [n0]  sum_{e in cell} y_e
     const int *cellCnt;    // [n0]  gridrep
+    // rowUB[r] = upper bound of the coalescent terms of all trajectory rows > r, whatever the trajectory: cell i contributes
+    // at most y_i (log(y_i / (2 a_i)) - 1) (the maximum of -2 a lambda + y log lambda over lambda > 0); lna_async.cuh
+    const double *rowUB;   // [nrow]
+    int async_ok;          // change points on LNA-interval boundaries (what k_ess_par_async needs)
     // raw events (for the per-event mirror of volz_loglik_nh2 / coal_loglik)
     int E;
     const double *evC, *evD, *evY;

@@ -190,6 +190,8 @@ struct CandArgs {
     // (output, may be null); such calls run one candidate per chain and wave (the scale depends on which earlier
     // candidates failed their Cholesky factorisation)
     double *eps_scale;
+    // k_ess_par_async (lna_async.cuh): next chain of the batch to hand to a group of lanes (zeroed before the launch)
+    int *work_counter;
 };
 
 // Whitened scalars of Param_Slice_update_all2 (:1287-1296) and their rotated images (:1299-1311).
