@@ -273,29 +273,27 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
             const int r = seg + 1;
             apply_changes(r * g);  // beta at the coarse time (betaTs on coarse times) = beta of the next interval
             const double lS = S + X0, lI = I + X1;
-            if (a.cand.A.ok()) {
-                a.cand.A.put(slot, seg * 4 + 0, p00);
-                a.cand.A.put(slot, seg * 4 + 1, p10);
-                a.cand.A.put(slot, seg * 4 + 2, p01);
-                a.cand.A.put(slot, seg * 4 + 3, p11);
+            {   // candidate outputs, slot-major scratch (element j of slot s at base[s + j NC]): one 64-bit offset per array
+                const long long NC = a.cand.A.sj, oA = slot + (long long)seg * 4 * NC, oR = slot + (long long)r * NC;
+                const long long oS = oR + (long long)nrow * NC, oI = oS + (long long)nrow * NC;
+                double *pA = a.cand.A.base + oA, *pL = a.cand.L.base + oA;
+                pA[0] = p00;
+                pA[NC] = p10;
+                pA[2 * NC] = p01;
+                pA[3 * NC] = p11;
+                pL[0] = l00;
+                pL[NC] = l10;
+                pL[2 * NC] = 0.0;
+                pL[3 * NC] = l11;
+                const double tr = T.ctimes[r];
+                a.cand.ode.base[oR] = tr;
+                a.cand.ode.base[oS] = S;
+                a.cand.ode.base[oI] = I;
+                a.cand.latent.base[oR] = tr;
+                a.cand.latent.base[oS] = lS;
+                a.cand.latent.base[oI] = lI;
+                a.cand.betaN.base[oR] = beta;
             }
-            if (a.cand.L.ok()) {
-                a.cand.L.put(slot, seg * 4 + 0, l00);
-                a.cand.L.put(slot, seg * 4 + 1, l10);
-                a.cand.L.put(slot, seg * 4 + 2, 0.0);
-                a.cand.L.put(slot, seg * 4 + 3, l11);
-            }
-            if (a.cand.ode.ok()) {
-                a.cand.ode.put(slot, r, T.ctimes[r]);
-                a.cand.ode.put(slot, nrow + r, S);
-                a.cand.ode.put(slot, 2 * nrow + r, I);
-            }
-            if (a.cand.latent.ok()) {
-                a.cand.latent.put(slot, r, T.ctimes[r]);
-                a.cand.latent.put(slot, nrow + r, lS);
-                a.cand.latent.put(slot, 2 * nrow + r, lI);
-            }
-            if (a.cand.betaN.ok()) a.cand.betaN.put(slot, r, beta);
             volz_row(r, lS, lI);
             seg += 1;
             if (seg == k) {

@@ -179,11 +179,12 @@ static int ess_async_width(const lna_problem *pb, long long planB, const CandArg
     if (const char *e = getenv("LNA_ESS_ASYNC_W")) {
         w = atoi(e);
     } else {
-        // measured (tools/async_sweep.sh, profiles/r2_async_slice.md): 8 lanes per chain win where they make 1-2 warps per SM
-        // sub-partition (4096 chains: 1.08 -> 0.99 ms per iteration); smaller batches are faster with all candidates of a
-        // chain in flight at once (wave kernels), larger ones are throughput-bound either way
+        // measured (tools/async_sweep.sh, profiles/r2_async_slice.md): 8 lanes per chain win where they make 1.5-2.2 warps per
+        // SM sub-partition (4096 chains: 1.08 -> 0.98 ms per iteration; 3072: 0.915 wave / 0.939; 6144: 1.426 / 1.430);
+        // smaller batches are faster with all candidates of a chain in flight at once (wave kernels), larger ones are
+        // throughput-bound either way
         const long long warps = planB * 8 / 32, subp = (long long)pb->sm_count * 4;
-        if (warps < subp * 5 / 4 || warps > subp * 5 / 2) return 0;
+        if (warps * 10 < subp * 15 || warps * 10 > subp * 22) return 0;
     }
     if (w != 1 && w != 2 && w != 4 && w != 8 && w != 16 && w != 32) return 0;
     if (cb.NC < B * w) return 0;

@@ -7,5 +7,5 @@ for B in ${@:-4096}; do
       LNA_ESS_ASYNC_W=$W LNA_ESS_ASYNC_WPS=$WPS python tools/plan_sweep.py child $B 2>&1 | tail -1 | sed "s/^/B=$B async W=$W wps=$WPS       /"
     done
   done
-  python tools/plan_sweep.py child $B 2>&1 | tail -1 | sed "s/^/B=$B async auto            /"
+  python tools/plan_sweep.py child $B 2>&1 | tail -1 | sed "s/^/B=$B default               /"
 done
