@@ -215,6 +215,7 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, 
             }
             CandArgs aa = a0;
             aa.work_counter = cb.count + 31;
+            aa.max_waves = getenv("LNA_ASYNC_COUNT_LANES") ? 1 : 0;  // (experiments: exec_count[1] accumulates lane-evaluations)
             if (cudaMemsetAsync(aa.work_counter, 0, sizeof(int), pb->stream) != cudaSuccess) return fail("memset failed");
             switch (wa) {
                 case 1: k_ess_par_async<1><<<grid, 128, sm, pb->stream>>>(pb->dp, pb->seg, B, aa); break;
