@@ -56,8 +56,9 @@ WORKLOADS = {
 }
 # DRAM bytes per launch of the hot kernel at the default batch: dram__bytes_read.sum + dram__bytes_write.sum of ONE
 # `ncu --set full` capture (a constant from that capture, not measured by this run)
-NCU_TRAFFIC = {"bytes": 65061120 + 1034752, "source": "constant from the ncu --set full capture profiles/r1d_ncu_full_loglik.md "
-               "(k_full_loglik<0,0>, B = 65536; unchanged kernel)"}
+NCU_TRAFFIC = {"bytes": 65065472 + 565760, "source": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture "
+               "profiles/r2_ncu_kernels.md (k_full_loglik<0,0>, B = 65536, 1024 x 64 threads; tools/headline_kernel.py): ncu cannot "
+               "run inside the timed bench, so the figure is the capture's, not this run's"}
 SMSP = 4  # FP64 pipes (SM sub-partitions) per SM
 P3_NOTE = ("`achieved` uses SURVEY.md 8d's dense small-matrix ESTIMATE for p = 3 (~277 flops per fine step); the evidence is "
            "`achieved_executed` (flops of the instructions the kernel executes, counted in the SASS) and `pipe_util`")
