@@ -56,7 +56,8 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, nthreads);
     // Launches that leave the SM sub-partitions at most about one warp each last as long as ONE evaluation takes ONE
     // warp; there every candidate goes to a pipeline of three warps on three sub-partitions (lna_split.cuh).
-    const bool split = use_split_eval(pb, nthreads);
+    // (the Metropolis pair of a 4096-chain batch is 512 candidate warps: 4 pipelines of 53 KB fit an SM)
+    const bool split = use_split_eval(pb, nthreads, (kProp == PROP_MH_PAIR && getenv("LNA_SPLIT_PAIR4")) ? 4 : 3);
 #define LC2(WW, SPLIT)                                                                                              \
     do {                                                                                                            \
         if (SPLIT) {                                                                                                \
