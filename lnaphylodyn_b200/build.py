@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblnaphylodyn_b200.so")
 SOURCES = ["lna_capi.cu"]
 DEPS = ["lna_capi.cu", "lna_capi_eslice.inl", "lna_comm.inl", "lna_device.cuh", "lna_kernels.cuh", "lna_eslice.cuh", "lna_split.cuh",
-        "lna_sirs.cuh", "lna_legacy.cuh", "lna_thin.cuh", "lna_async.cuh", "lna_capi_legacy.inl",
+        "lna_sirs.cuh", "lna_legacy.cuh", "lna_thin.cuh", "lna_async.cuh", "lna_seg.cuh", "lna_capi_legacy.inl",
         os.path.join("..", "..", "include", "lnaphylodyn_b200.h")]
 
 NVCC_FLAGS = [

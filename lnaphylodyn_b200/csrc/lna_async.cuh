@@ -213,7 +213,10 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
         if (!__any_sync(full, run)) {
             // nobody in the warp is evaluating: the batch is exhausted.  What the FP64 pipe was charged: one
             // warp-interval per tick whatever the lane mask, i.e. (ticks - 1) / k warp-evaluations
-            if (a.exec_count && lane == 0) atomicAdd(a.exec_count + 1, (unsigned long long)((ticks - (a.max_waves ? 0 : 1) + k / 2) / k));
+            if (a.exec_count && lane == 0) {
+                if (a.max_waves) atomicAdd(a.exec_count + 1, (unsigned long long)((ticks + k / 2) / k));
+                else atomicAdd(a.exec_count + 2, (unsigned long long)(ticks - 1));  // warp-ticks
+            }
             break;
         }
         // ---- 2. one LNA interval: g fine steps (sir_full_eval's step, same expressions) ----------------------------

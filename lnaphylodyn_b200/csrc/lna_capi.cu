@@ -23,6 +23,7 @@
 #include "lna_split.cuh"
 #include "lna_eslice.cuh"
 #include "lna_async.cuh"
+#include "lna_seg.cuh"
 #include "lna_sirs.cuh"
 #include "lna_legacy.cuh"
 #include "lna_thin.cuh"

@@ -10,6 +10,8 @@ struct CandBuf {
     int *win_slot = nullptr, *n_evals = nullptr, *status = nullptr, *accept = nullptr;
     double *cand_ll = nullptr, *theta = nullptr;
     int *list = nullptr, *count = nullptr;  // compaction list of the two-phase slice evaluation
+    double *seg_d = nullptr;                // k_ess_par_seg: parked per-chain state (lna_seg.cuh)
+    int *seg_i = nullptr;
 };
 
 // slots >= base are used so that callers can keep their own staging below `base`
@@ -30,11 +32,13 @@ static bool cand_alloc(lna_problem *pb, Scratch &s, size_t base, long long B, lo
     cb.cand_ll = (double *)s.get(base + 9, sizeof(double) * B);
     cb.theta = (double *)s.get(base + 10, sizeof(double) * B);
     cb.list = (int *)s.get(base + 11, sizeof(int) * B * 2);
-    cb.count = (int *)s.get(base + 12, sizeof(int) * 32);  // [0, 24): compaction counts, [31]: k_ess_par_async's work counter
+    cb.count = (int *)s.get(base + 12, sizeof(int) * 256);  // [0, 24): compaction counts, [31]: k_ess_par_async's work counter, [32, 256): k_ess_par_seg's list counts
+    cb.seg_d = (double *)s.get(base + 13, sizeof(double) * kSegD * B);
+    cb.seg_i = (int *)s.get(base + 14, sizeof(int) * kSegI * B);
     return cb.list && cb.count && cb.cA && cb.cL && cb.cOde && cb.cBeta && cb.cLat && cb.win_slot && cb.n_evals && cb.status && cb.accept &&
-           cb.cand_ll && cb.theta;
+           cb.cand_ll && cb.theta && cb.seg_d && cb.seg_i;
 }
-static constexpr size_t kCandSlots = 13;
+static constexpr size_t kCandSlots = 15;
 
 static FullOut cand_out(const CandBuf &cb) {
     return FullOut{OutView{cb.cA, 1, cb.NC}, OutView{cb.cL, 1, cb.NC}, OutView{cb.cOde, 1, cb.NC},
@@ -56,8 +60,7 @@ static int launch_cand_one(lna_problem *pb, long long nchains, int W, const Cand
     const int block = (kProp == PROP_ESS_PAR || kProp == PROP_ESS_CHPT) ? 128 : pick_block(pb, nthreads);
     // Launches that leave the SM sub-partitions at most about one warp each last as long as ONE evaluation takes ONE
     // warp; there every candidate goes to a pipeline of three warps on three sub-partitions (lna_split.cuh).
-    // (the Metropolis pair of a 4096-chain batch is 512 candidate warps: 4 pipelines of 53 KB fit an SM)
-    const bool split = use_split_eval(pb, nthreads, (kProp == PROP_MH_PAIR && getenv("LNA_SPLIT_PAIR4")) ? 4 : 3);
+    const bool split = use_split_eval(pb, nthreads);
 #define LC2(WW, SPLIT)                                                                                              \
     do {                                                                                                            \
         if (SPLIT) {                                                                                                \
@@ -169,6 +172,20 @@ static int slice_plan_slots(const lna_problem *pb, long long B, int W) {
     return std::max(tot, 4);
 }
 
+// ESlice_par_General with sequential candidates, early rejection, resumable evaluation and compaction between launches
+// (lna_seg.cuh).  Measured SLOWER than the wave kernels at every batch size (65 536 chains: 10.1 vs 8.06 ms per iteration although
+// it executes half the FP64 work: lanes of a warp sit in different intervals of different candidates, so candidate starts, the
+// change-ratio loads and the 13 per-interval stores are uncoalesced and serialised -- a tick costs 2.6 x the wave kernel's interval,
+// profiles/r2_async_slice.md), so it is OFF unless LNA_ESS_SEG=1 asks for it; kept because it is the sequential reference schedule
+// on the device and is held to the same step-for-step tests.
+static bool ess_seg_on(const lna_problem *pb, long long planB, const CandArgs &a0, int W_req) {
+    const DevProb &P = pb->dp;
+    if (!P.async_ok || !P.has_init || a0.ess[6] || W_req != 0) return false;
+    (void)planB;
+    const char *e = getenv("LNA_ESS_SEG");
+    return e && atoi(e) != 0;
+}
+
 // ESlice_par_General of resident chains without wave barriers and with provable early rejection (lna_async.cuh):
 // W lanes per chain, lane w walks candidates w+1, w+1+W, ..  LNA_ESS_ASYNC=0 keeps the wave kernels, LNA_ESS_ASYNC_W forces W.
 static int ess_async_width(const lna_problem *pb, long long planB, const CandArgs &a0, int W_req, const CandBuf &cb, long long B) {
@@ -197,6 +214,24 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, 
                        long long planB = 0) {
     if (planB <= 0) planB = B;
     if constexpr (kProp == PROP_ESS_PAR) {
+        if (ess_seg_on(pb, planB, a0, W)) {
+            // large batches: one candidate of a chain at a time, early rejection, T ticks per launch, compaction (lna_seg.cuh)
+            int T = 16;
+            if (const char *e = getenv("LNA_ESS_SEG_T")) T = std::max(1, atoi(e));
+            const int nl = std::min(220, ((20 + 1) * pb->dp.k + T - 1) / T + 1);
+            const size_t sm = full_eval_smem_bytes(pb->tab_bytes, 128) + sizeof(double) * 128 * (size_t)(kMaxUnif + 9);
+            if (cudaMemsetAsync(cb.seg_i, 0, sizeof(int) * kSegI * (size_t)B, pb->stream) != cudaSuccess ||
+                cudaMemsetAsync(cb.count + 32, 0, sizeof(int) * 224, pb->stream) != cudaSuccess)
+                return fail("memset failed");
+            const SegState ss{cb.seg_d, cb.seg_i};
+            for (int l = 0; l < nl; ++l) {
+                const int *lin = l == 0 ? nullptr : cb.list + (size_t)((l - 1) & 1) * B, *cin = l == 0 ? nullptr : cb.count + 32 + (l - 1);
+                k_ess_par_seg<<<nblk(B, 128), 128, sm, pb->stream>>>(pb->dp, pb->seg, B, a0, ss, lin, cin, cb.list + (size_t)(l & 1) * B,
+                                                                     cb.count + 32 + l, T);
+                if (launch_check(pb, "k_ess_par_seg")) return -1;
+            }
+            return 0;
+        }
         const int wa = ess_async_width(pb, planB, a0, W, cb, B);
         if (wa) {
             // persistent: at most `wps` warps per SM sub-partition (LNA_ESS_ASYNC_WPS, default 2), groups of wa lanes pull chains
@@ -817,8 +852,8 @@ static ChainPart *part_create(lna_problem *pb, int64_t B, int64_t planB, double 
     const size_t stage_unif = std::max<size_t>(LNA_ITER_UNIF, LNA_ITER2_UNIF);
     ch->stage_n = chains_alloc<double>(ch, nB * ch->n_norm);
     ch->stage_u = chains_alloc<double>(ch, nB * stage_unif);
-    ch->exec = chains_alloc<unsigned long long>(ch, 2);
-    if (ch->exec) cudaMemsetAsync(ch->exec, 0, 2 * sizeof(unsigned long long), pb->stream);
+    ch->exec = chains_alloc<unsigned long long>(ch, 4);  // evaluations, warp-evaluations, warp-ticks (intervals), spare
+    if (ch->exec) cudaMemsetAsync(ch->exec, 0, 4 * sizeof(unsigned long long), pb->stream);
     ch->jT = chains_alloc<double>(ch, nB * 16);
     ch->jnew = chains_alloc<double>(ch, nB * 4);
     if (!ch->par || !ch->par_alt || !ch->origin || !ch->A || !ch->L || !ch->ode || !ch->betaN || !ch->latent || !ch->coalLog ||
@@ -1750,11 +1785,11 @@ extern "C" int lna_chains_exec_counts(lna_chains *ch, uint64_t *evals, uint64_t 
     for (int g = 0; g < ch->G; ++g) {
         ChainPart *pt = ch->part[g];
         cudaSetDevice(pt->pb->device);
-        unsigned long long h[2] = {0, 0};
+        unsigned long long h[4] = {0, 0, 0, 0};
         CK(cudaStreamSynchronize(pt->pb->stream));
         CK(cudaMemcpy(h, pt->exec, sizeof h, cudaMemcpyDeviceToHost));
         tot[0] += h[0];
-        tot[1] += h[1];
+        tot[1] += h[1] + (h[2] + (unsigned long long)pt->pb->dp.k / 2) / (unsigned long long)pt->pb->dp.k;  // warp-ticks -> evaluations
     }
     if (evals) *evals = tot[0];
     if (warp_evals) *warp_evals = tot[1];

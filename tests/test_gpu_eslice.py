@@ -669,3 +669,41 @@ def test_metropolis_tree_general_entries_bit_identical(api, changepoint, monkeyp
     for key in ("par", "OriginTraj", "LatentTraj", "coalLog", "logOrigin", "n_full_evals", "n_cheap_evals", "n_mh_accept"):
         assert np.array_equal(runs["0"][key], runs["1"][key]), key
     assert len(np.unique(runs["1"]["par"][:, 0])) > 1  # S0 moved in some chains
+
+
+def test_slice_kernel_variants_give_the_same_chains(changepoint):
+    """The parameter slice update has three device schedules -- speculative waves (lna_eslice.cuh), barrier-free lanes with
+    early rejection (lna_async.cuh), sequential candidates with early rejection, parked state and compaction (lna_seg.cuh).
+    Whatever the schedule, the accepted candidate is the one the sequential rule picks: 8 iterations of 96 chains end in the
+    same state (decisions identical; values to the last bits of the per-interval dt operands)."""
+    import os
+    from lnaphylodyn_b200 import api, chains as chm
+    g = changepoint
+    B = 96
+    par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"),
+                           g.setting("control.hyper")])
+    pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
+    keys = ("LNA_ESS_ASYNC", "LNA_ESS_ASYNC_W", "LNA_ESS_SEG", "LNA_ESS_SEG_T", "LNA_GRAPH")
+    saved = {k: os.environ.get(k) for k in keys}
+    results = {}
+    try:
+        for name, env in (("waves", {"LNA_ESS_ASYNC": "0"}), ("barrier-free", {"LNA_ESS_ASYNC_W": "8"}),
+                          ("barrier-free-4", {"LNA_ESS_ASYNC_W": "4"}), ("sequential", {"LNA_ESS_SEG": "1", "LNA_ESS_SEG_T": "7"})):
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            os.environ["LNA_GRAPH"] = "0"  # (a captured graph would freeze the first variant's launches)
+            ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+            for it in range(8):
+                ch.step_rng(chm.vignette_opts(g, update_traj=it >= 2), 99, it)
+            results[name] = ch.get()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    ref = results["waves"]
+    for name, r in results.items():
+        assert np.array_equal(r["n_full_evals"], ref["n_full_evals"]) and np.array_equal(r["n_mh_accept"], ref["n_mh_accept"]), name
+        assert relerr(r["par"], ref["par"]) < 1e-12 and relerr(r["coalLog"], ref["coalLog"]) < 1e-12, name
