@@ -10,7 +10,7 @@
 //   lane holds exactly the double the sequential loop would hold), each lane looks up its own grid cell, and a ballot finds
 //   the first proposal that is an event (a coalescence or the next sampling time).  Proposals after it are discarded and
 //   drawn again in the next round under the new lineage count -- the stream is indexed by proposal number, so the result is
-//   bit-identical to the sequential loop consuming the same stream (oracle/lna_oracle.c: orc_volz_thin_sir).
+//   bit-identical to the sequential loop consuming the same stream (checked in tests/test_gpu_thin.py).
 #pragma once
 #include "lna_eslice.cuh"
 
