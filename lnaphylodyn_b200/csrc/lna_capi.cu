@@ -596,6 +596,30 @@ static int pick_block(const lna_problem *pb, long long B) {
     return per_sm >= 128 ? 64 : 32;
 }
 
+// Balanced FULL kernel (k_full_loglik_bal): worth it when the warp-loads per SM sub-partition are few and not whole -- the
+// plain kernel then lasts ceil(loads per sub-partition) loads, the balanced one loads / 4 per SM.  Needs at most four pieces
+// per sub-partition (512-thread blocks keep the 100-register evaluation unspilled).  LNA_BAL=0 / 1 forces it off / on
+// (1: whenever the piece count allows it -- tests run it on small batches, where a load is cut three times).
+static bool use_balanced_full(const lna_problem *pb, long long B, int *block) {
+    const char *e = getenv("LNA_BAL");
+    const int mode = e ? atoi(e) : -1;
+    if (mode == 0 || pb->sm_count <= 0) return false;
+    const long long L = (B + 31) / 32, nmax = (L + pb->sm_count - 1) / pb->sm_count;
+    int pieces = 0;
+    for (int j : {0, pb->sm_count - 1})  // blocks 0 and nblocks-1 carry the two load counts that occur
+        for (int sp = 0; sp < 4; ++sp) {
+            int n = 0;
+            while (lna::bal_piece(L, pb->sm_count, j, pb->dp.k, sp, n).valid) ++n;
+            pieces = std::max(pieces, n);
+        }
+    if (pieces < 1 || pieces > 4) return false;
+    *block = 128 * pieces;
+    if (mode == 1) return true;
+    if (pb->parent) return false;  // one of several concurrent stream groups: their launches already fill each other's tails
+    // plain kernel: ceil(nmax / 4) loads deep; balanced: nmax / 4 (+ the hand-over).  Take it from 1/8 load of gain upwards.
+    return nmax >= 4 && 4 * ((nmax + 3) / 4) - nmax >= 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // FULL evaluation
 // ------------------------------------------------------------------------------------------------
@@ -688,6 +712,7 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
     const int block = pick_block(pb, B);
     const unsigned grid = nblk(B, block);
     const View vp = item_view(param, P.npt), vi = item_view(initial, p), vo = item_view(origin, (long long)P.k * p);
+    int bal_block = 0;
 #define LAUNCH(MODEL, STORE)                                                                                     \
     k_full_loglik<MODEL, STORE><<<grid, block, full_eval_smem_bytes(pb->tab_bytes, block), pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status, group)
     if (P.model == LNA_MODEL_SIR && use_split_eval(pb, B, 1)) {
@@ -701,6 +726,16 @@ static int full_loglik_dev_impl(lna_problem *pb, int64_t B, const double *param,
         } else {
             big_smem_attr(k_full_loglik_split<false>, pb->device);
             k_full_loglik_split<false><<<nblk(B, 32), blk, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status, group);
+        }
+    } else if (P.model == LNA_MODEL_SIR && use_balanced_full(pb, B, &bal_block)) {
+        // one persistent block per SM, the SM's warp-loads cut into four equal shares (k_full_loglik_bal)
+        const size_t sm = lna::bal_smem_bytes(pb->tab_bytes, bal_block);
+        if (store) {
+            big_smem_attr(k_full_loglik_bal<true>, pb->device);
+            k_full_loglik_bal<true><<<pb->sm_count, bal_block, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status, group);
+        } else {
+            big_smem_attr(k_full_loglik_bal<false>, pb->device);
+            k_full_loglik_bal<false><<<pb->sm_count, bal_block, sm, pb->stream>>>(P, pb->seg, B, vp, vi, vo, out, coalLog, status, group);
         }
     } else if (P.model == LNA_MODEL_SIR) {
         if (store) LAUNCH(0, true);

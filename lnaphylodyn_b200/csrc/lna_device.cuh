@@ -220,16 +220,37 @@ struct VolzAcc {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Partial evaluations: a FULL evaluation cut at LNA-interval boundaries into pieces that different warps run one after the
+// other (k_full_loglik_bal: the pieces of one warp-load go to two SM sub-partitions so that all four finish together).
+// Everything that crosses a cut is the trajectory's running state -- 6 doubles and 3 ints per trajectory; beta and the
+// change-point cursor are rebuilt from (R0cum, nxt) with the expressions the uncut evaluation uses, so a cut changes no bit.
+// ------------------------------------------------------------------------------------------------
+struct PartState {
+    double S, I, X0, X1, R0cum, acc;
+    int nxt, flags, st, pad;
+};
+struct NoPart {  // the whole evaluation (every kernel but k_full_loglik_bal)
+    static constexpr bool kOn = false;
+};
+struct PartRange {
+    static constexpr bool kOn = true;
+    int seg_begin, seg_end;  // intervals [seg_begin, seg_end) of 0..k
+    PartState *in;           // this trajectory's state at seg_begin (seg_begin > 0)
+    PartState *out;          // where it goes at seg_end (seg_end < k)
+};
+
+// ------------------------------------------------------------------------------------------------
 // SIR (p = 2) FULL evaluation.
 //   param = (R0, gamma, ch_1..ch_nch, hyper); theta0 = beta(t) = R0*prod(ch)*gamma/N, theta1 = param[1].
 // Per fine step: one Euler step of F0 and Sigma at the left endpoint, then the reference's RK4
 // variant.  F's second row is -(first row) - (0, gamma), which removes a third of the multiplies;
 // the hazards h = (beta S I, gamma I) are shared between the covariance step and RK stage 1.
 // ------------------------------------------------------------------------------------------------
-template <bool kStore, class ChSrc, class EpsSrc>
+template <bool kStore, class ChSrc, class EpsSrc, class Part = NoPart>
 __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD, const Tables &T, const ChSrc &chs,
                                               const EpsSrc &eps, double R0, double gam, double S, double I,
-                                              const FullOut &out, long long b, double &loglik, int &status) {
+                                              const FullOut &out, long long b, double &loglik, int &status,
+                                              const Part part = Part{}) {
     const double h2 = P.h2, dt6 = P.dt6;
     const double hg = h2 * gam, dg6 = dt6 * gam;
     const double invN = P.invN;
@@ -242,24 +263,49 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
     double X0 = 0.0, X1 = 0.0;
     VolzAcc va;
     int st = 0;
+    int seg_begin = 0, seg_end = k;
+    bool resumed = false;
+    if constexpr (Part::kOn) {
+        seg_begin = part.seg_begin;
+        seg_end = part.seg_end;
+        resumed = seg_begin > 0;
+        if (resumed) {  // the state the previous piece left at this cut
+            const PartState ps = *part.in;
+            S = ps.S;
+            I = ps.I;
+            X0 = ps.X0;
+            X1 = ps.X1;
+            R0cum = ps.R0cum;
+            va.acc = ps.acc;
+            va.flags = ps.flags;
+            st = ps.st;
+            cur.nxt = ps.nxt;
+            cur.next_s = cur.nxt < cur.nch ? cur.chidx[cur.nxt] : 0x7fffffff;
+            cur.pre = chs.raw(cur.nxt < cur.nch ? cur.nxt : 0);
+            beta = (R0cum * gam) * invN;
+            hb = h2 * beta;
+        }
+    }
 
     // coarse row 0 = initial state
-    if (kStore) {
-        if (out.ode.ok()) {
-            out.ode.put(b, 0, T.ctimes[0]);
-            out.ode.put(b, nrow, S);
-            out.ode.put(b, 2 * nrow, I);
+    if (!resumed) {
+        if (kStore) {
+            if (out.ode.ok()) {
+                out.ode.put(b, 0, T.ctimes[0]);
+                out.ode.put(b, nrow, S);
+                out.ode.put(b, 2 * nrow, I);
+            }
+            if (out.latent.ok()) {
+                out.latent.put(b, 0, T.ctimes[0]);
+                out.latent.put(b, nrow, S);
+                out.latent.put(b, 2 * nrow, I);
+            }
+            if (out.betaN.ok()) out.betaN.put(b, 0, beta);
         }
-        if (out.latent.ok()) {
-            out.latent.put(b, 0, T.ctimes[0]);
-            out.latent.put(b, nrow, S);
-            out.latent.put(b, 2 * nrow, I);
-        }
-        if (out.betaN.ok()) out.betaN.put(b, 0, beta);
+        if (P.has_init) va.row(P, T, 0, S, I, beta, (S < 0.0) | (I < 0.0));
     }
-    if (P.has_init) va.row(P, T, 0, S, I, beta, (S < 0.0) | (I < 0.0));
 
-    for (int seg = 0; seg < k; ++seg) {
+    for (int seg = seg_begin; seg < seg_end; ++seg) {
         double p00 = 1.0, p01 = 0.0, p10 = 0.0, p11 = 1.0;  // F0
         double s00 = 0.0, s01 = 0.0, s11 = 0.0;              // Sigma (symmetric)
         // latent increments of this interval: asynchronous copy into the thread's shared-memory slot now, read at
@@ -387,6 +433,23 @@ __device__ __forceinline__ void sir_full_eval(const DevProb &P, const SegDt &SD,
             if (out.betaN.ok()) out.betaN.put(b, r, beta);
         }
         if (P.has_init) va.row(P, T, r, lS, lI, beta, (lS < 0.0) | (lI < 0.0));
+    }
+    if constexpr (Part::kOn) {
+        if (seg_end < k) {  // hand the running state to the piece that continues at this cut
+            PartState ps;
+            ps.S = S;
+            ps.I = I;
+            ps.X0 = X0;
+            ps.X1 = X1;
+            ps.R0cum = R0cum;
+            ps.acc = va.acc;
+            ps.nxt = cur.nxt;
+            ps.flags = va.flags;
+            ps.st = st;
+            ps.pad = 0;
+            *part.out = ps;
+            return;
+        }
     }
     if (st & ST_CHOL_FAIL) {
         status |= ST_CHOL_FAIL;

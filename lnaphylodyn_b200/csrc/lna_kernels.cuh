@@ -47,6 +47,90 @@ k_full_loglik(const __grid_constant__ DevProb P, const __grid_constant__ SegDt S
     if (status) status[b] = st;
 }
 
+// ================================================================================================
+// BALANCED FULL kernel (SIR): one persistent block per SM, warp w on SM sub-partition w % 4.
+// k_full_loglik's unit of work is a warp-load (32 evaluations x 2000 dependent steps) and a sub-partition's FP64 pipe is
+// saturated by three of them, so a launch lasts ceil(warp-loads per sub-partition) x one load: the headline batch (65 536
+// evaluations = 2048 loads on 592 sub-partitions = 3.46 each) runs 4 deep on 272 sub-partitions while 320 idle for a quarter
+// of the launch.  Here the n loads of an SM are laid on a line of n x k LNA intervals and the line is cut into four equal
+// segments, one per sub-partition; a load that a cut falls into is evaluated in two pieces by two warps on neighbouring
+// sub-partitions, the running state (PartState, 64 B per trajectory) handed over through shared memory.  All four pipes of
+// the SM then carry n / 4 loads.  Same expressions in the same order as the uncut evaluation: same bits.
+// ================================================================================================
+struct BalPiece {
+    long long load;          // warp-load: items 32 load .. 32 load + 31
+    int seg_begin, seg_end;  // LNA intervals of that load
+    bool valid;
+};
+// piece `pidx` of sub-partition `sp` in block `j` of `nblocks`, L warp-loads in all
+__host__ __device__ inline BalPiece bal_piece(long long L, int nblocks, int j, int k, int sp, int pidx) {
+    const long long base = L / nblocks, rem = L % nblocks;
+    const long long n = base + (j < rem ? 1 : 0), l0 = (long long)j * base + (j < rem ? j : rem);
+    const long long c0 = ((long long)sp * n * k + 2) / 4, c1 = ((long long)(sp + 1) * n * k + 2) / 4;
+    const long long start = pidx == 0 ? c0 : (c0 / k + pidx) * k;
+    BalPiece pc{0, 0, 0, false};
+    if (start >= c1) return pc;
+    const long long ld = start / k, end = (ld + 1) * k < c1 ? (ld + 1) * k : c1;
+    pc.load = l0 + ld;
+    pc.seg_begin = (int)(start - ld * k);
+    pc.seg_end = (int)(end - ld * k);
+    pc.valid = true;
+    return pc;
+}
+constexpr int kBalCuts = 3;
+__host__ __device__ inline size_t bal_smem_bytes(size_t tab_bytes, int block) {
+    return ((full_eval_smem_bytes(tab_bytes, block) + 15) & ~(size_t)15) + sizeof(PartState) * 32 * kBalCuts + 16;
+}
+
+template <bool kStore>
+__global__ void __launch_bounds__(512, 1)
+k_full_loglik_bal(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, View param,
+                  View initial, View origin, FullOut out, double *coalLog, int *status, int group) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    PartState *hand = reinterpret_cast<PartState *>(
+        smem + ((full_eval_smem_bytes(tables_bytes(P.nch, P.k, P.n0), blockDim.x) + 15) & ~(size_t)15));
+    volatile int *flag = reinterpret_cast<volatile int *>(hand + 32 * kBalCuts);
+    if (threadIdx.x < kBalCuts) flag[threadIdx.x] = 0;
+    const Tables T = stage_tables(P, smem, true);  // (ends with __syncthreads)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sp = warp & 3;
+    const BalPiece pc = bal_piece((B + 31) / 32, gridDim.x, blockIdx.x, P.k, sp, warp >> 2);
+    if (!pc.valid) return;
+    const long long b = pc.load * 32 + lane;
+    const bool live = b < B;
+    const bool waits = pc.seg_begin > 0, hands = pc.seg_end < P.k;
+    if (waits) {  // the first piece of this load runs on sub-partition sp - 1
+        if (lane == 0)
+            while (flag[sp - 1] == 0) __nanosleep(400);
+        __syncwarp();
+        __threadfence_block();
+    }
+    if (live) {
+        const long long bc = group > 1 ? b / group : b;
+        int st = 0;
+        double ll = 0.0;
+        ChFromParam chs{param, b, P.nparam};
+        const PartRange part{pc.seg_begin, pc.seg_end, hand + (sp > 0 ? sp - 1 : 0) * 32 + lane,
+                             hand + (sp < kBalCuts ? sp : kBalCuts - 1) * 32 + lane};
+        const double R0 = param.at(b, P.iR0), gam = param.at(b, 1);
+        if (origin.ok()) {
+            EpsFromView eps{origin, bc, P.k};
+            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(bc, 0), initial.at(bc, 1), out, b, ll, st, part);
+        } else {
+            EpsZero eps;
+            sir_full_eval<kStore>(P, SD, T, chs, eps, R0, gam, initial.at(bc, 0), initial.at(bc, 1), out, b, ll, st, part);
+        }
+        if (!hands) {
+            if (coalLog) coalLog[b] = ll;
+            if (status) status[b] = st;
+        }
+    }
+    if (hands) {
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) flag[sp] = 1;
+    }
+}
+
 // MH decision of Update_Param (LNA_functional.cpp:1228-1241) on top of a finished FULL evaluation.
 __global__ void k_mh_accept(long long B, const double *coalLog_new, const double *coal_log, const double *offset,
                             const double *unif, const int *status, int *accept) {

@@ -182,3 +182,58 @@ def test_problem_create_rejects_layouts_the_reference_cannot_run(api, changepoin
     par = g.final["par"].ravel()
     with pytest.raises(LnaError, match="must be"):
         pb.full_loglik(par[2:], par[:2], g.final["OriginTraj"])
+
+
+@pytest.mark.parametrize("gridsize,nch", [(50, 39), (8, 5), (40, 0), (1, 2)])
+def test_balanced_full_kernel_returns_the_plain_kernels_bits(changepoint, monkeypatch, gridsize, nch):
+    """csrc/lna_kernels.cuh k_full_loglik_bal: the warp-loads of an SM are cut into four equal shares at LNA-interval
+    boundaries and a cut load is evaluated in pieces by warps on neighbouring sub-partitions, the running state handed over
+    through shared memory.  Small batches (a load cut three times: every warp waits for and hands to a neighbour), ragged
+    ones, batches where the two load counts per SM differ, with and without stored outputs, change points inside a piece:
+    every output must carry the plain kernel's bits; with the vignette's genealogy the likelihood and its sentinels too."""
+    from lnaphylodyn_b200 import api
+    g = changepoint
+    rng = np.random.default_rng(gridsize * 1000 + nch)
+    vignette = (gridsize, nch) == (50, 39)
+    nt = 2001 if gridsize > 1 else 501
+    times = g.times[:nt]
+    if vignette:
+        x_r, x_i, init, tc = g.x_r, g.x_i, g.init, g.t_correct
+    else:
+        cht = np.sort(rng.uniform(times[0], times[-1], nch))
+        x_r, x_i, init, tc = np.concatenate([[1e6], cht]), [nch, 2, 0, 1], None, 0.0
+    k = (nt - 1) // gridsize
+    pb = api.problem_for(times, x_r, x_i, gridsize, tc, init)
+    monkeypatch.setenv("LNA_SPLIT", "0")
+    for B in (1, 37, 4737, 9489) if vignette else (3, 700):
+        par, ini, eps = draws(rng, B, nch, k, eps_scale=0.5)
+        if vignette:
+            fp = g.final["par"].ravel()
+            par[:, 0], par[:, 1], ini = fp[2] * np.exp(0.05 * rng.standard_normal(B)), fp[3], np.tile(fp[:2], (B, 1))
+        want = ("coalLog", "FT", "Ode", "betaN", "LatentTraj") if vignette else ("FT", "Ode", "betaN", "LatentTraj")
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("LNA_BAL", mode)
+            out[mode] = pb.full_loglik(par, ini, eps, want=want if B < 5000 else want[:1])
+        for key in out["0"]:
+            if key == "FT":
+                assert np.array_equal(out["0"]["FT"]["A"], out["1"]["FT"]["A"]) and np.array_equal(out["0"]["FT"]["Sigma"], out["1"]["FT"]["Sigma"])
+            else:
+                assert np.array_equal(out["0"][key], out["1"][key]), (key, B)
+        if vignette:
+            assert np.sum(out["1"]["coalLog"] > orc.SENTINEL) >= B // 4
+
+
+def test_balanced_full_kernel_against_the_oracle(api, changepoint, monkeypatch):
+    """The balanced kernel forced on (LNA_BAL=1, pipeline off) on a batch where every load is cut: oracle parity at 1e-10."""
+    g = changepoint
+    rng = np.random.default_rng(77)
+    monkeypatch.setenv("LNA_SPLIT", "0")
+    monkeypatch.setenv("LNA_BAL", "1")
+    B = 48
+    par = np.tile(g.final["par"].ravel()[2:], (B, 1))
+    par[:, 0] *= np.exp(0.05 * rng.standard_normal(B))
+    par[:, 2:-1] *= np.exp(0.03 * rng.standard_normal((B, par.shape[1] - 3)))
+    ini = np.tile(g.final["par"].ravel()[:2], (B, 1))
+    eps = np.tile(g.final["OriginTraj"], (B, 1, 1)) + 0.1 * rng.standard_normal((B, 40, 2))
+    compare(api, g.times, g.x_r, g.x_i, g.init, g.gridsize, g.t_correct, par, ini, eps)

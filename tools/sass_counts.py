@@ -16,6 +16,7 @@ SO = os.path.join(ROOT, "lnaphylodyn_b200", "liblnaphylodyn_b200.so")
 KERNELS = {
     "sir_full_nostore": "void lna::k_full_loglik<0, false>",
     "sir_full_store": "void lna::k_full_loglik<0, true>",
+    "sir_full_balanced_nostore": "void lna::k_full_loglik_bal<false>",
     "seir_full_nostore": "void lna::k_full_loglik<1, false>",
     "sirs_full_nostore": "void lna::k_sirs_full<false>",
     "cand_ess_par_w8": "void lna::k_cand_eval<3, 8, false>",
