@@ -12,8 +12,9 @@
 //      as the reference would reject it after evaluating it to the end (a Cholesky failure or a negative state later on is
 //      a rejection too in ESlice_par_General, :1641-1651).  Wide-angle candidates are thrown out after a quarter of the
 //      trajectory on the vignette problems (tools/early_exit_probe.py).
-// The wave kernel cannot use (2): a wave lasts as long as its slowest lane.  Here every chain owns W lanes of a warp and lane
-// w walks its own candidates w+1, w+1+W, w+1+2W, .. -- it starts the next one the moment the current one is rejected.  All
+// The wave kernel cannot use (2): a wave lasts as long as its slowest lane.  Here every chain owns W lanes of a warp; a lane
+// whose candidate is rejected takes the chain's next unstarted candidate in the same tick (so the candidate that will be
+// accepted never queues behind one particular lane's slow rejection).  All
 // lanes of the warp advance in lockstep by ONE LNA INTERVAL (g fine steps + the interval epilogue) per tick, each on its own
 // (candidate, interval); the chain is resolved when some lane has accepted candidate i and every lane is past i.  Same
 // decisions, same accepted candidate, same stored outputs as the sequential loop.
@@ -28,6 +29,10 @@
 
 namespace lna {
 
+constexpr int kAsyncCandDoubles = 7;
+// doubles of shared memory per group of W lanes (host and device)
+__host__ __device__ inline int async_group_doubles(int nch) { return kMaxUnif + 5 + 4 + 3 * nch + 20 * kAsyncCandDoubles; }
+
 template <int W>
 __global__ void __launch_bounds__(128, 3)
 k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt SD, long long B, CandArgs a) {
@@ -37,10 +42,15 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
     // per-group copy of what every candidate START needs -- the call's uniforms, the chain's scalars and its change ratios
     // with their normals -- so that starting a candidate touches no global memory (a start happens in almost every tick of a
     // warp; its latency would be paid by all 32 lanes):  u[22] | S0 I0 R0 gamma hyper | nu_I0 nu_R0 nu_gamma nu_hyper | ch[nch] | nu[nch]
-    const int gs_len = kMaxUnif + 5 + 4 + 2 * P.nch;
+    // ... | z[nch] = log(ch) hyper (the chain's part of every proposed change ratio) | cs[20][7] = (theta, cos, sin, I0, R0,
+    // gamma, hyper') of candidates 1..20, computed ONCE per chain by the group's lanes in parallel: a candidate start -- which
+    // happens in a third of a warp's ticks and is paid by all 32 lanes -- is seven shared-memory loads instead of a sincos and
+    // four exponentials
+    const int gs_stage = kMaxUnif + 5 + 4 + 2 * P.nch, gs_len = async_group_doubles(P.nch);
     double *gs = reinterpret_cast<double *>(smem + full_eval_smem_bytes(tables_bytes(P.nch, P.k, P.n0), blockDim.x)) +
                  (size_t)(threadIdx.x / W) * gs_len;
-    double *g_par = gs + kMaxUnif, *g_nrm = g_par + 5, *g_ch = g_nrm + 4, *g_nu = g_ch + P.nch;
+    double *g_par = gs + kMaxUnif, *g_nrm = g_par + 5, *g_ch = g_nrm + 4, *g_nu = g_ch + P.nch, *g_z = g_nu + P.nch,
+           *g_cs = g_z + P.nch;
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const unsigned gmask = (W >= 32) ? full : (((1u << W) - 1u) << (lane & ~(W - 1)));
@@ -54,13 +64,11 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
     EpsFromView eps{a.origin, 0, P.k};
     EssParPre zpre{};
     double logy = 0.0, logy_lo = 0.0;
-    ThetaSeq ts;
-    ts.init();
     bool have_chain = false, exhausted = false;
 
     // ---- lane state -------------------------------------------------------------------------------------------------
     int cand = 0;             // candidate being evaluated (0 = none)
-    int next = w + 1;         // next candidate of this lane
+    int gnext = 1;            // the chain's next unstarted candidate (uniform within the group)
     int seg = 0;              // interval the current candidate is in
     int accepted = 0;         // candidate this lane accepted (0 = none); the lane stops there
     bool resolved = true;     // the chain is decided (or the group has no chain yet)
@@ -69,13 +77,14 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
     int flags = 0, st = 0, nxt = 0, st_acc = 0, ticks = 0;
     bool revert_cur = false;
     PropScalars x{};
-    ChProp<PROP_ESS_PAR> chs{a.par, a.normals, c, 4, x};
 
     auto apply_changes = [&](int s) {  // every change point with fine index <= s (they sit on interval boundaries)
         bool any = false;
         while (nxt < P.nch && T.chidx[nxt] <= s) {
-            const typename ChProp<PROP_ESS_PAR>::Raw pre{g_ch[nxt], g_nu[nxt]};
-            R0cum *= chs.eval(pre);
+            // ChProp<PROP_ESS_PAR>::eval with log(ch) hyper taken from the per-chain table
+            double f = g_ch[nxt];
+            if (x.rot_ch) f = exp(__ddiv_rn(rot(g_z[nxt], x.ct, g_nu[nxt], x.sn), x.hyper_new));  // :1299, :1310
+            R0cum *= f;
             ++nxt;
             any = true;
         }
@@ -108,9 +117,8 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
                         c = nc;
                         slot = c * W + w;
                         eps.b = c;
-                        chs.c = c;
                         __syncwarp(gmask);  // (the group's previous chain is not read any more)
-                        for (int q = w; q < gs_len; q += W) {
+                        for (int q = w; q < gs_stage; q += W) {
                             double v;
                             if (q < kMaxUnif) v = a.uniforms.at(c, q);
                             else if (q < kMaxUnif + 4) v = a.par.at(c, q - kMaxUnif);
@@ -130,8 +138,26 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
                         logy = a.coal_log[c] + log(unif(0));
                         // (rounding head-room of the bound test: the partial sum carries ~1e-13 relative error)
                         logy_lo = logy - 1e-9 * (fabs(logy) + 1.0);
-                        ts.init();
-                        next = w + 1;
+                        for (int q = w; q < P.nch; q += W) g_z[q] = __dmul_rn(log(g_ch[q]), g_par[4]);  // :1296
+                        {   // candidates w+1, w+1+W, ..: ess_par_scalars on the staged copy (same expressions)
+                            ThetaSeq ts;
+                            ts.init();
+                            for (int j = w + 1; j <= kMaxCand; j += W) {
+                                ts.advance(j, unif);
+                                double sn, ct;
+                                sincos(ts.th, &sn, &ct);
+                                double *cs = g_cs + (j - 1) * kAsyncCandDoubles;
+                                cs[0] = ts.th;
+                                cs[1] = ct;
+                                cs[2] = sn;
+                                cs[3] = a.ess[0] ? exp(__dadd_rn(__dmul_rn(rot(zpre.z0, ct, g_nrm[0], sn), a.pr[1]), a.pr[0])) : g_par[1];
+                                cs[4] = a.ess[1] ? exp(__dadd_rn(__dmul_rn(rot(zpre.z1, ct, g_nrm[1], sn), a.pr[3]), a.pr[2])) : g_par[2];
+                                cs[5] = a.ess[2] ? exp(__dadd_rn(__dmul_rn(rot(zpre.z2, ct, g_nrm[2], sn), a.pr[5]), a.pr[4])) : g_par[3];
+                                cs[6] = a.ess[4] ? exp(__dadd_rn(__dmul_rn(rot(zpre.zh, ct, g_nrm[3], sn), a.pr[7]), a.pr[6])) : g_par[4];
+                            }
+                        }
+                        __syncwarp(gmask);
+                        gnext = 1;
                         cand = 0;
                         accepted = 0;
                         resolved = false;
@@ -148,38 +174,42 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
         int first_acc = accepted ? accepted : 0x7fffffff;
 #pragma unroll
         for (int o = 1; o < W; o <<= 1) first_acc = min(first_acc, __shfl_xor_sync(full, first_acc, o));
-        const bool start = !resolved && cand == 0 && !accepted && next <= kMaxCand + 1 && next < first_acc;
+        // free lanes take the chain's next unstarted candidates in lane order (candidates start in increasing order, so a
+        // lane's bracket replay only ever moves forward and everything below an accepted candidate has been started)
+        const bool want = !resolved && cand == 0 && !accepted;
+        const unsigned wm = __ballot_sync(full, want) & gmask;
+        const int mine = gnext + __popc(wm & ((1u << lane) - 1u));
+        const int lim = min(kMaxCand + 2, first_acc);  // candidates < lim are worth starting
+        const bool start = want && mine < lim;
+        if (!resolved) gnext += max(0, min(__popc(wm), lim - gnext));
         if (a.exec_count) {
             const unsigned sm_ = __ballot_sync(full, start);
             if (sm_ && lane == 0) atomicAdd(a.exec_count, (unsigned long long)__popc(sm_));
         }
         if (start) {
-            cand = next;
-            next += W;
+            cand = mine;
             revert_cur = cand == kMaxCand + 1;  // the cap: back to the current parameters (:1609-1622)
-            if (!revert_cur) ts.advance(cand, unif);
-            th_cur = revert_cur ? 0.0 : ts.th;
-            {  // ess_par_scalars on the staged copy (same expressions)
-                double sn, ct;
-                sincos(th_cur, &sn, &ct);
-                x.ct = ct;
-                x.sn = sn;
+            {
+                const double *cs = g_cs + (revert_cur ? 0 : cand - 1) * kAsyncCandDoubles;
+                th_cur = cs[0];
+                x.ct = cs[1];
+                x.sn = cs[2];
+                x.I0 = cs[3];
+                x.R0 = cs[4];
+                x.gam = cs[5];
+                x.hyper_new = cs[6];
                 x.hyper_old = g_par[4];
-                x.I0 = a.ess[0] ? exp(__dadd_rn(__dmul_rn(rot(zpre.z0, ct, g_nrm[0], sn), a.pr[1]), a.pr[0])) : g_par[1];
-                x.R0 = a.ess[1] ? exp(__dadd_rn(__dmul_rn(rot(zpre.z1, ct, g_nrm[1], sn), a.pr[3]), a.pr[2])) : g_par[2];
-                x.gam = a.ess[2] ? exp(__dadd_rn(__dmul_rn(rot(zpre.z2, ct, g_nrm[2], sn), a.pr[5]), a.pr[4])) : g_par[3];
-                x.hyper_new = a.ess[4] ? exp(__dadd_rn(__dmul_rn(rot(zpre.zh, ct, g_nrm[3], sn), a.pr[7]), a.pr[6])) : g_par[4];
                 x.rot_ch = a.ess[5];
             }
             x.S0 = g_par[0];
             if (revert_cur) {  // current parameters, bit for bit
+                th_cur = 0.0;
                 x.I0 = g_par[1];
                 x.R0 = g_par[2];
                 x.gam = g_par[3];
                 x.rot_ch = 0;
             }
             x.noop = 0;
-            chs.x = x;
             gam = x.gam;
             hg = h2 * gam;
             dg6 = dt6 * gam;
@@ -337,8 +367,8 @@ k_ess_par_async(const __grid_constant__ DevProb P, const __grid_constant__ SegDt
         int gacc = accepted ? accepted : 0x7fffffff;
 #pragma unroll
         for (int o = 1; o < W; o <<= 1) gacc = min(gacc, __shfl_xor_sync(full, gacc, o));
-        // a lane is "below" the accepted candidate if it is evaluating, or still has to start, a candidate < gacc
-        const bool below = !resolved && !accepted && ((cand != 0 && cand < gacc) || (cand == 0 && next < gacc && next <= kMaxCand + 1));
+        // a lane is "below" the accepted candidate if it is evaluating a candidate < gacc (all of those have been started)
+        const bool below = !resolved && !accepted && cand != 0 && cand < gacc;
         const unsigned pend = __ballot_sync(full, below) & gmask;
         if (!resolved && gacc != 0x7fffffff && pend == 0) {
             if (accepted == gacc) {  // the winner writes the chain's result

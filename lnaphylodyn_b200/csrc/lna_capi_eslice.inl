@@ -187,23 +187,36 @@ static bool ess_seg_on(const lna_problem *pb, long long planB, const CandArgs &a
 }
 
 // ESlice_par_General of resident chains without wave barriers and with provable early rejection (lna_async.cuh):
-// W lanes per chain, lane w walks candidates w+1, w+1+W, ..  LNA_ESS_ASYNC=0 keeps the wave kernels, LNA_ESS_ASYNC_W forces W.
-static int ess_async_width(const lna_problem *pb, long long planB, const CandArgs &a0, int W_req, const CandBuf &cb, long long B) {
+// W lanes per chain, a free lane takes the chain's next unstarted candidate.  LNA_ESS_ASYNC=0 keeps the wave kernels,
+// LNA_ESS_ASYNC_W / LNA_ESS_ASYNC_WPS force the lanes per chain / the resident warps per SM sub-partition.
+// Measured with dynamic candidate assignment (tools/async_sweep2.sh, profiles/r2_async_slice.md; ms per iteration, wave kernels
+// against the best barrier-free setting): 512 chains 0.376 / 0.466 (the three-warp pipeline wins), 1024: 0.510 / 0.485 (W = 16),
+// 2048: 0.839 / 0.664 (16), 3072: 0.915 / 0.833 (16), 4096: 1.085 / 0.941 (8, two warps per sub-partition), 6144: 1.436 / 1.331
+// (8, three), 16 384: 2.830 / 2.619 (8, three), 32 768: 4.39 / 4.82 and 65 536: 8.13 / 9.25 (throughput-bound: the wave kernels'
+// cheaper ticks win).
+static int ess_async_width(const lna_problem *pb, long long planB, const CandArgs &a0, int W_req, const CandBuf &cb, long long B,
+                           int *wps) {
     const DevProb &P = pb->dp;
     if (!P.async_ok || !P.has_init || a0.ess[6] || W_req != 0) return 0;  // (an explicit speculation width asks for the wave kernel)
     if (const char *e = getenv("LNA_ESS_ASYNC"))
         if (atoi(e) == 0) return 0;
     int w = 8;
+    *wps = 2;
+    const long long subp = (long long)pb->sm_count * 4, warps8 = planB * 8 / 32, warps16 = planB * 16 / 32;
     if (const char *e = getenv("LNA_ESS_ASYNC_W")) {
         w = atoi(e);
+    } else if (warps16 * 100 >= subp * 85 && warps8 * 10 < subp * 15) {
+        w = 16;  // 1007 .. 3551 chains on 148 SMs: every candidate the chain is likely to need starts in the first tick
+        *wps = 3;
+    } else if (warps8 * 10 >= subp * 15 && warps8 * 10 <= subp * 22) {
+        w = 8;   // 3552 .. 5209 chains
+    } else if (warps8 * 10 > subp * 22 && warps8 * 10 <= subp * 87) {
+        w = 8;   // .. 20 601 chains: persistent, three warps per sub-partition, groups refill from the batch
+        *wps = 3;
     } else {
-        // measured (tools/async_sweep.sh, profiles/r2_async_slice.md): 8 lanes per chain win where they make 1.5-2.2 warps per
-        // SM sub-partition (4096 chains: 1.08 -> 0.98 ms per iteration; 3072: 0.915 wave / 0.939; 6144: 1.426 / 1.430);
-        // smaller batches are faster with all candidates of a chain in flight at once (wave kernels), larger ones are
-        // throughput-bound either way
-        const long long warps = planB * 8 / 32, subp = (long long)pb->sm_count * 4;
-        if (warps * 10 < subp * 15 || warps * 10 > subp * 22) return 0;
+        return 0;
     }
+    if (const char *e = getenv("LNA_ESS_ASYNC_WPS")) *wps = std::max(1, atoi(e));
     if (w != 1 && w != 2 && w != 4 && w != 8 && w != 16 && w != 32) return 0;
     if (cb.NC < B * w) return 0;
     return w;
@@ -232,22 +245,24 @@ static int launch_cand(lna_problem *pb, long long B, int W, const CandArgs &a0, 
             }
             return 0;
         }
-        const int wa = ess_async_width(pb, planB, a0, W, cb, B);
+        int wps = 2;
+        const int wa = ess_async_width(pb, planB, a0, W, cb, B, &wps);
         if (wa) {
-            // persistent: at most `wps` warps per SM sub-partition (LNA_ESS_ASYNC_WPS, default 2), groups of wa lanes pull chains
-            int wps = 2;
-            if (const char *e = getenv("LNA_ESS_ASYNC_WPS")) wps = std::max(1, atoi(e));
+            // persistent: at most `wps` warps per SM sub-partition, groups of wa lanes pull chains from a counter
             const long long warps_needed = (B * wa + 31) / 32, warps_cap = (long long)pb->sm_count * 4 * wps;
             const long long warps = std::min(warps_needed, warps_cap);
             const unsigned grid = (unsigned)((warps + 3) / 4);
             // tables + per-thread eps slots + per-group staging of the chain's scalars, uniforms and change ratios
             const size_t sm = full_eval_smem_bytes(pb->tab_bytes, 128) +
-                              sizeof(double) * (size_t)(128 / wa) * (size_t)(kMaxUnif + 9 + 2 * pb->dp.nch);
+                              sizeof(double) * (size_t)(128 / wa) * (size_t)lna::async_group_doubles(pb->dp.nch);
             if (sm > 48 * 1024) {
                 if (sm > 200 * 1024) return fail("k_ess_par_async: %d change points do not fit in shared memory", pb->dp.nch);
                 big_smem_attr(k_ess_par_async<1>, pb->device);
                 big_smem_attr(k_ess_par_async<2>, pb->device);
                 big_smem_attr(k_ess_par_async<4>, pb->device);
+                big_smem_attr(k_ess_par_async<8>, pb->device);
+                big_smem_attr(k_ess_par_async<16>, pb->device);
+                big_smem_attr(k_ess_par_async<32>, pb->device);
             }
             CandArgs aa = a0;
             aa.work_counter = cb.count + 31;
