@@ -194,6 +194,7 @@ static bool ess_seg_on(const lna_problem *pb, long long planB, const CandArgs &a
 // 2048: 0.839 / 0.664 (16), 3072: 0.915 / 0.833 (16), 4096: 1.085 / 0.941 (8, two warps per sub-partition), 6144: 1.436 / 1.331
 // (8, three), 16 384: 2.830 / 2.619 (8, three), 32 768: 4.39 / 4.82 and 65 536: 8.13 / 9.25 (throughput-bound: the wave kernels'
 // cheaper ticks win).
+constexpr long long kAsyncMaxWarps10 = 118;  // barrier-free kernel up to 11.8 eight-lane warps per SM sub-partition
 static int ess_async_width(const lna_problem *pb, long long planB, const CandArgs &a0, int W_req, const CandBuf &cb, long long B,
                            int *wps) {
     const DevProb &P = pb->dp;
@@ -210,9 +211,13 @@ static int ess_async_width(const lna_problem *pb, long long planB, const CandArg
         *wps = 3;
     } else if (warps8 * 10 >= subp * 15 && warps8 * 10 <= subp * 22) {
         w = 8;   // 3552 .. 5209 chains
-    } else if (warps8 * 10 > subp * 22 && warps8 * 10 <= subp * 87) {
-        w = 8;   // .. 20 601 chains: persistent, three warps per sub-partition, groups refill from the batch
-        *wps = 3;
+    } else if (warps8 * 10 > subp * 22 && warps8 * 10 <= subp * kAsyncMaxWarps10) {
+        // .. 27 942 chains, ONE stream group (lna_chains_create): all warps resident while three per sub-partition hold them
+        // (6144 chains: 1.331 against 1.421 ms), else persistent with two per sub-partition and groups refilling from the
+        // batch (8192: 1.495 / 1.558 with three; 12 288: 2.046; 16 384: 2.603; 24 576: 3.547 against 3.645 for the wave kernels
+        // on two stream groups)
+        w = 8;
+        *wps = warps8 <= subp * 3 ? 3 : 2;
     } else {
         return 0;
     }
@@ -1566,6 +1571,8 @@ extern "C" lna_chains *lna_chains_create(lna_problem *pb, int64_t B) {
     // two stream groups from 8192 chains on (measured with the iterations replayed from CUDA graphs: one group is faster up
     // to 4096 chains, 1.08 vs 1.16 ms per iteration there; two win from 8192, profiles/r2_eslice_timeline.md)
     ch->G = B >= 8192 ? 2 : 1;
+    // the barrier-free slice kernel keeps the machine busy from one stream (persistent groups refill from the batch)
+    if (pb->dp.async_ok && pb->dp.has_init && (long long)B * 8 / 32 * 10 <= (long long)pb->sm_count * 4 * kAsyncMaxWarps10) ch->G = 1;
     if (const char *e = getenv("LNA_CHAIN_GROUPS")) ch->G = std::max(1, std::min(8, atoi(e)));
     if (ch->G > B) ch->G = 1;
     const DevProb &P = pb->dp;
