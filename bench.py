@@ -56,9 +56,9 @@ WORKLOADS = {
 }
 # DRAM bytes per launch of the hot kernel at the default batch: dram__bytes_read.sum + dram__bytes_write.sum of ONE
 # `ncu --set full` capture (a constant from that capture, not measured by this run)
-NCU_TRAFFIC = {"bytes": 65065472 + 565760, "source": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture "
-               "profiles/r2_ncu_kernels.md (k_full_loglik<0,0>, B = 65536, 1024 x 64 threads; tools/headline_kernel.py): ncu cannot "
-               "run inside the timed bench, so the figure is the capture's, not this run's"}
+NCU_TRAFFIC = {"bytes": 65071360 + 579840, "source": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture "
+               "profiles/r2b_ncu_kernels.md (k_full_loglik_bal<false>, B = 65536, 148 x 512 threads; tools/headline_kernel.py): ncu "
+               "cannot run inside the timed bench, so the figure is the capture's, not this run's"}
 SMSP = 4  # FP64 pipes (SM sub-partitions) per SM
 P3_NOTE = ("`achieved` uses SURVEY.md 8d's dense small-matrix ESTIMATE for p = 3 (~277 flops per fine step); the evidence is "
            "`achieved_executed` (flops of the instructions the kernel executes, counted in the SASS) and `pipe_util`")
@@ -701,8 +701,9 @@ def main():
     value_shared = world * B * args.steps / (ms_shared * 1e-3)
 
     # ---- supplemental: the same launches with TWO batches in flight (two problem handles, two streams) ----
-    # The headline batch is 2048 warp-loads on 592 SM sub-partitions (3.46 each): alone, a launch lasts as long as the
-    # sub-partitions that got 4.  With the next batch's launch overlapping the tail the quantisation loss disappears.
+    # The headline batch is 2048 warp-loads on 592 SM sub-partitions (3.46 each).  The plain kernel lasted as long as the
+    # sub-partitions that got 4 (0.510 ms); the balanced kernel (k_full_loglik_bal: each SM's loads cut into four equal shares)
+    # brings a lone launch to 3.5 (0.455 ms).  What a second batch in flight still adds: its launch fills the 13-load SMs' tails.
     pipelined = None
     try:
         pb2 = w.problem(api, cx.local_rank)
@@ -871,7 +872,7 @@ def main():
         W = w.flops_per_eval()
         achieved = (value / world) * W / 1e12
         peak = cx.peak
-        cnt = cx.sass.get("sir_full_nostore", {})
+        cnt = cx.sass.get("sir_full_balanced_nostore", cx.sass.get("sir_full_nostore", {}))
         n = len(w.times) - 1
         per_item_bytes = sum(x.numel() * x.element_size() for x in bufs[0]) + B * 12
         line = {
