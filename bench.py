@@ -333,6 +333,13 @@ class Ctx:
             raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        # one process per GPU: stay on the GPU's NUMA node before any pinned host buffer is allocated (e2e legs)
+        self.host_binding = {"bound": False}
+        if self.world > 1 and not os.environ.get("LNA_NO_NUMA_BIND"):
+            from lnaphylodyn_b200 import comm as _comm
+            pr = torch.cuda.get_device_properties(self.dev)
+            self.host_binding = _comm.bind_host_to_device_numa(getattr(pr, "pci_domain_id", 0), getattr(pr, "pci_bus_id", -1),
+                                                               getattr(pr, "pci_device_id", 0))
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=self.dev)
@@ -868,6 +875,12 @@ def main():
         except Exception as e:  # noqa: BLE001
             gather = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
+    host_binding = cx.host_binding
+    if world > 1:  # every rank's NUMA node, for the record
+        allb = [None] * world
+        cx.dist.all_gather_object(allb, cx.host_binding)
+        host_binding = {"what": "each rank bound to the CPUs of its GPU's NUMA node before allocating pinned host buffers "
+                                "(lnaphylodyn_b200.comm.bind_host_to_device_numa)", "ranks": allb}
     if rank == 0:
         W = w.flops_per_eval()
         achieved = (value / world) * W / 1e12
@@ -886,7 +899,7 @@ def main():
                             "proposals of a chain share the chain's initial state and OriginTraj: 377 B per evaluation, the "
                             "per-item call ships 992)",
                     "frac_of_device_resident": e2e_val / value, "value_synchronous_calls": e2e_sync_val},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_binding": host_binding,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak > 0 else None,
                          "pipe_util": pipe_util(cnt.get("fp64_per_step"), n, B * args.steps, ms_total * 1e-3, cx.sm_count, cx.sm_mhz),

@@ -15,6 +15,40 @@ from ._lib import LnaError, check
 from .api import _d, _ptr
 
 
+def _parse_cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_device_numa(pci_domain, pci_bus, pci_device, sysfs="/sys"):
+    """One process per GPU: keep this process (and so the pinned host buffers it is about to allocate and first-touch) on the
+    NUMA node the GPU hangs off.  Eight ranks streaming proposals to eight GPUs otherwise share whichever memory controllers
+    and PCIe root complexes the scheduler happened to put them on.  Returns a dict describing what was done; a host without
+    NUMA information (numa_node = -1, no sysfs) is left alone."""
+    import os
+    info = {"numa_node": None, "bound": False}
+    try:
+        dev = f"{pci_domain:04x}:{pci_bus:02x}:{pci_device:02x}.0"
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", dev, "numa_node")).read())
+        info.update(pci=dev, numa_node=node)
+        if node < 0:
+            return info
+        cpus = _parse_cpulist(open(os.path.join(sysfs, f"devices/system/node/node{node}/cpulist")).read())
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return info
+        os.sched_setaffinity(0, allowed)
+        info.update(bound=True, cpus=len(allowed))
+    except (OSError, ValueError, AttributeError) as e:
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 class Comm:
     """Wraps lna_comm (an NCCL communicator owned by the library)."""
 

@@ -46,3 +46,28 @@ def test_two_rank_shards_and_gather(tmp_path):
     assert np.array_equal(g[:, 1], ref_n[:, 0]) and np.array_equal(g[:, 2], ref_u[:, 0])  # rank-independent streams
     assert np.array_equal(np.concatenate([np.load(tmp_path / f"n{r}.npy") for r in range(world)]), ref_n)
     assert (g[:, 3] == 0).sum() == 51 and (g[:, 3] == 1).sum() == 50
+
+
+def test_bind_host_to_device_numa_on_a_fake_sysfs(tmp_path):
+    """One process per GPU stays on its GPU's NUMA node (bench.py e2e legs at N > 1): the helper reads the PCI device's
+    numa_node and the node's cpulist, intersects with the allowed CPUs, and leaves hosts without NUMA information alone."""
+    import os
+    from lnaphylodyn_b200 import comm
+    pci = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    pci.mkdir(parents=True)
+    (pci / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    before = os.sched_getaffinity(0)
+    first = min(before)
+    (node / "cpulist").write_text(f"{first},100000-100003\n")
+    try:
+        info = comm.bind_host_to_device_numa(0, 0x1b, 0, sysfs=str(tmp_path))
+        assert info["bound"] and info["numa_node"] == 1 and os.sched_getaffinity(0) == {first}
+    finally:
+        os.sched_setaffinity(0, before)
+    (pci / "numa_node").write_text("-1\n")
+    assert not comm.bind_host_to_device_numa(0, 0x1b, 0, sysfs=str(tmp_path))["bound"]
+    assert not comm.bind_host_to_device_numa(0, 0x1c, 0, sysfs=str(tmp_path))["bound"]   # unknown device: no-op, no raise
+    assert os.sched_getaffinity(0) == before
+    assert comm._parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11}
