@@ -86,10 +86,16 @@ __device__ __forceinline__ void sirs_full_eval(const DevProb &P, const double *_
             x2 = sde.at(bx, 3 * nrow + r);
         }
         const int s_end = (seg + 1) * g;
+        // the two table entries of a step are loaded one step ahead (the tables hold nt = last step + 1 entries): with one warp
+        // per SM sub-partition -- the 16 384-draw sweep -- nothing else hides a load that the whole step depends on
+        // (ncu: 40 % of the kernel's stall samples sat on these two loads)
+        double so = __ldg(sinO + seg * g), sf = __ldg(sinF + seg * g);
         LNA_DO_PRAGMA(unroll LNA_UNROLL)
         for (int s = seg * g; s < s_end; ++s) {
-            const double bo = fma(ba, __ldg(sinO + s), beta);  // rhs:    beta (1 + alpha sin(2 pi t / period))
-            const double bf = fma(ba, __ldg(sinF + s), beta);  // moments: beta (1 + alpha sin(t / period * 2 pi))
+            const double bo = fma(ba, so, beta);  // rhs:    beta (1 + alpha sin(2 pi t / period))
+            const double bf = fma(ba, sf, beta);  // moments: beta (1 + alpha sin(t / period * 2 pi))
+            so = __ldg(sinO + s + 1);
+            sf = __ldg(sinF + s + 1);
             // ---- Euler step of F0 and Sigma at the left endpoint --------------------------------------------------
             {
                 const double bI = bf * I, bS = bf * S;
