@@ -755,7 +755,7 @@ def main():
     # Every step copies its inputs from pinned host memory (chain-shared layout) and reads its B likelihoods + statuses back.
     # Steps are issued with the asynchronous form of the call (the H2D copies of step i+1 overlap the kernel of step i) and
     # the region ends when the last result has landed in host memory (lna_problem_sync).
-    n_e2e = max(args.steps, 20)
+    n_e2e = max(args.steps, 50)  # (the region also holds one pipeline fill and drain: ~1 step)
     cx.barrier()
     t0 = time.perf_counter()
     for i in range(n_e2e):

@@ -109,10 +109,10 @@ struct lna_problem {
     std::vector<double> iC, iD, iy, igridrep;
     int iE = 0, ing = 0, has_init = 0;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t chunk_ev[8] = {}, kern_ev[8] = {}, d2h_ev[2] = {};
+    cudaEvent_t chunk_ev[12] = {}, kern_ev[12] = {}, d2h_ev[3] = {};
     bool d2h_pending = false;  // asynchronous result copies in flight on d2h_stream (lna_problem_sync waits for them)
     cudaEvent_t done_ev = nullptr;
-    cudaEvent_t async_done[2] = {};  // lna_full_loglik_async: last use of staging set 0 / 1
+    cudaEvent_t async_done[3] = {};  // lna_full_loglik_async: last use of staging set 0 / 1 / 2
     int async_parity = 0;
 };
 
@@ -761,8 +761,10 @@ extern "C" int lna_full_loglik_dev(lna_problem *pb, int64_t B, const double *par
 // stream) overlaps the kernel of chunk i (compute stream); results return on a third stream so that a D2H copy never sits
 // between two kernels.
 // async: no synchronisation at the end -- the caller reads the outputs after lna_problem_sync() and keeps all host buffers
-// alive until then; consecutive asynchronous calls alternate between two staging sets, so the copies of call n+1 overlap
-// the kernel of call n (they wait only for call n-1, the previous user of their staging set).
+// alive until then; consecutive asynchronous calls rotate over THREE staging sets, so the copies of call n+1 overlap the
+// kernel of call n and wait only for call n-2, the previous user of their staging set -- with two sets the copy engine idled
+// until kernel n-1 and its result copy were done, and since the balanced kernel a 65 536-evaluation step's copy (24.7 MB over
+// PCIe) takes as long as its kernel, so that bubble was the step time.
 // group > 1: chain-shared inputs (lna_full_loglik_shared): B = n_chains * group evaluations, `initial` / `OriginTraj` per
 // chain -- 336 + (16 + 640) / group bytes per evaluation instead of 992.
 static int full_loglik_chunked(lna_problem *pb, int64_t B, const double *param, const double *initial,
@@ -774,7 +776,7 @@ static int full_loglik_chunked(lna_problem *pb, int64_t B, const double *param, 
     // pipelines against its neighbours, so it is not split at all unless it is very large
     int nchunk = async ? (int)std::min<size_t>(4, std::max<size_t>(1, nB / 131072)) : (int)std::min<size_t>(4, std::max<size_t>(1, nB / 32768));
     if (const char *e = getenv("LNA_H2D_CHUNKS")) nchunk = std::max(1, std::min(4, atoi(e)));
-    const int q = async ? (pb->async_parity ^= 1) : 0;
+    const int q = async ? (pb->async_parity = (pb->async_parity + 1) % 3) : 0;
     const size_t base = async ? 32 + 5 * (size_t)q : 0;
     double *dpar = (double *)pb->scratch.get(base + 0, nB * P.npt * sizeof(double));
     double *dini = (double *)pb->scratch.get(base + 1, nC * p * sizeof(double));

@@ -10,12 +10,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     g = Golden("changepoint_sim")
     par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"), g.setting("control.hyper")])
     pb = api.Problem(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
-    ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+    free = os.environ.get("LNA_FREE", "0") != "0"   # stream groups not joined after every step, started staggered
+    iters = int(os.environ.get("LNA_ITERS", iters))
+    ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"), free_running=free)
     opts = chm.vignette_opts(g, update_traj=True)
     for it in range(6): ch.step_rng(opts, 1, it)
-    pb.sync(); t0 = time.perf_counter()
+    ch.sync(); pb.sync(); t0 = time.perf_counter()
     for it in range(6, 6 + iters): ch.step_rng(opts, 1, it)
-    pb.sync(); dt = time.perf_counter() - t0
+    ch.sync(); pb.sync(); dt = time.perf_counter() - t0
     s = ch.get()
     print(f"{1e3*dt/iters:.3f} ms/iter {B*iters/dt/1e6:.2f} M chain-iter/s  evals/iter {s['n_full_evals'].mean()/(6+iters):.2f} coalLog {s['coalLog'].mean():.3f}")
     sys.exit(0)
