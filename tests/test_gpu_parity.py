@@ -482,8 +482,8 @@ def test_traj_sim_sirs_reports_cholesky_outcome_per_item(api):
 
 
 def test_async_host_buffer_evaluation(changepoint):
-    """lna_full_loglik_async: several calls in flight on alternating staging sets give, after lna_problem_sync, exactly what
-    the synchronous call gives -- including when the same staging set is reused (4 calls) and for a batch below the
+    """lna_full_loglik_async: several calls in flight on the three rotating staging sets give, after lna_problem_sync, exactly
+    what the synchronous call gives -- including when every staging set is reused (7 calls) and for a batch below the
     chunking threshold (falls back to the synchronous path)."""
     import ctypes as C
     from lnaphylodyn_b200 import _lib, api
@@ -493,7 +493,7 @@ def test_async_host_buffer_evaluation(changepoint):
     rng = np.random.default_rng(4)
     for B in (20000, 300):
         sets = []
-        for s in range(4):
+        for s in range(7):
             par = np.tile(g.final["par"].ravel(), (B, 1))
             par[:, 2] *= np.exp(0.05 * rng.standard_normal(B))
             par[:, 3] *= np.exp(0.05 * rng.standard_normal(B))
@@ -507,4 +507,4 @@ def test_async_host_buffer_evaluation(changepoint):
             _lib.check(L.lna_full_loglik(pb.h, B, api._ptr(prm), api._ptr(ini), api._ptr(eps), api._ptr(cl2), api._ptr(st2),
                                          None, None, None, None, None), "sync call")
             assert np.array_equal(cl, cl2) and np.array_equal(st, st2)
-        assert len(np.unique(np.stack([s[3] for s in sets]), axis=0)) == 4
+        assert len(np.unique(np.stack([s[3] for s in sets]), axis=0)) == 7
