@@ -68,3 +68,16 @@ for B in (18944, 28416, 37888, 47360, 56832, 60000, 65536, 66304, 70000, 75776):
                 ts.append(e0.elapsed_time(e1))
         res[bal] = float(np.median(ts))
     print(f"{B:6d}  {B / 32 / 592:5.2f}  {res['0']:.4f}  {res['1']:.4f}  {res['0'] / res['1']:.3f}   balanced: {B / res['1'] / 1e3:.4g} evals/s  W-frac {B * 227200 / (res['1'] * 1e-3) / 37.13e12:.3f}", flush=True)
+
+# stress: the shared-memory hand-over (state, fence, flag / flag, fence, state) under repetition -- a lost or early hand-over
+# would change bits in the cut loads
+if len(sys.argv) > 2 and sys.argv[2] == "stress":
+    n_bad, n_run = 0, 0
+    for B in (65536, 60000, 47360, 28416, 9489, 700):
+        ref = run(B, "0", False)
+        for rep in range(60):
+            got = run(B, "1", False)
+            n_run += 1
+            if not all(torch.equal(x, y) for x, y in zip(ref, got)):
+                n_bad += 1
+    print(f"stress: {n_run} balanced launches compared with the plain kernel's results, {n_bad} mismatching", flush=True)
