@@ -1,5 +1,7 @@
+"""Experiment (GPU box): General_MCMC2 iteration (constant_sim vignette) with one against two stream groups at 8192 / 16 384 chains
+(measured: one group wins, 1.90 / 2.10 and 3.01 / 3.18 ms per iteration)."""
 import os, sys, time, ctypes as C
-ROOT = "/root/repo" if os.path.isdir("/root/repo/tests") else os.getcwd()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from conftest import Golden
