@@ -325,8 +325,9 @@ static int launch_commit_fields(lna_problem *pb, long long B, const CandBuf &cb,
     CommitArgs ca{cb.win_slot, cb.NC, cb.cA, cb.cL, cb.cOde, cb.cBeta, cb.cLat, A, L, ode, betaN, latent,
                   P.p * P.p * P.k, P.nrow * (P.p + 1), P.nrow, 0};
     const int per = 2 * ca.nA + 2 * ca.nOde + ca.nBeta;
-    if (per > 65535) return fail("k_commit_fields: %d elements per chain exceed the grid.y limit", per);
-    k_commit_fields<<<dim3(nblk(B, 128), per), 128, 0, pb->stream>>>(B, ca);
+    const int ny = (per + lna::kCommitPer - 1) / lna::kCommitPer;
+    if (ny > 65535) return fail("k_commit_fields: %d elements per chain exceed the grid.y limit", per);
+    k_commit_fields<<<dim3(nblk(B, 128), ny), 128, 0, pb->stream>>>(B, ca);
     return launch_check(pb, "k_commit_fields");
 }
 

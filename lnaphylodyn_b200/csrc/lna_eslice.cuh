@@ -630,34 +630,62 @@ struct CommitArgs {
     int copy_when_rejected;            // standalone entry points also want the evaluated candidate back
 };
 
+constexpr int kCommitPer = 8;  // elements per thread
 __global__ void k_commit_fields(long long B, CommitArgs a) {
-    // grid.y = element, grid.x covers the chains: no 64-bit div/mod per thread
+    // grid.y = block of kCommitPer consecutive elements, grid.x covers the chains (no 64-bit div/mod per thread).  A thread
+    // first issues its kCommitPer gather loads -- independent, all in flight together -- then stores: one element per thread
+    // left the copy launch- and latency-bound (29 us for 4096 chains, 203 us for 65 536: a third of the HBM rate).
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= B) return;
-    int e = blockIdx.y;
     const int slot = a.win_slot[c];
     if (slot < 0) return;
-    if (e < a.nA) {
-        if (a.A.ok()) a.A.put(c, e, a.cA[(long long)e * a.NC + slot]);
-        return;
+    const int per = 2 * a.nA + 2 * a.nOde + a.nBeta, e0 = blockIdx.y * kCommitPer;
+    // field of flat element e: A | L | ode | latent | betaN
+    auto src = [&](int e) -> const double * {
+        if (e < a.nA) return a.A.ok() ? a.cA + (long long)e * a.NC + slot : nullptr;
+        e -= a.nA;
+        if (e < a.nA) return a.L.ok() ? a.cL + (long long)e * a.NC + slot : nullptr;
+        e -= a.nA;
+        if (e < a.nOde) return a.ode.ok() ? a.cOde + (long long)e * a.NC + slot : nullptr;
+        e -= a.nOde;
+        if (e < a.nOde) return a.latent.ok() ? a.cLat + (long long)e * a.NC + slot : nullptr;
+        e -= a.nOde;
+        return a.betaN.ok() ? a.cBeta + (long long)e * a.NC + slot : nullptr;
+    };
+    double v[kCommitPer];
+    bool have[kCommitPer];
+#pragma unroll
+    for (int i = 0; i < kCommitPer; ++i) {
+        const double *q = e0 + i < per ? src(e0 + i) : nullptr;
+        have[i] = q != nullptr;
+        v[i] = have[i] ? __ldcs(q) : 0.0;  // (scratch is read once: streaming load)
     }
-    e -= a.nA;
-    if (e < a.nA) {
-        if (a.L.ok()) a.L.put(c, e, a.cL[(long long)e * a.NC + slot]);
-        return;
+#pragma unroll
+    for (int i = 0; i < kCommitPer; ++i) {
+        if (!have[i]) continue;
+        int e = e0 + i;
+        if (e < a.nA) {
+            a.A.put(c, e, v[i]);
+            continue;
+        }
+        e -= a.nA;
+        if (e < a.nA) {
+            a.L.put(c, e, v[i]);
+            continue;
+        }
+        e -= a.nA;
+        if (e < a.nOde) {
+            a.ode.put(c, e, v[i]);
+            continue;
+        }
+        e -= a.nOde;
+        if (e < a.nOde) {
+            a.latent.put(c, e, v[i]);
+            continue;
+        }
+        e -= a.nOde;
+        a.betaN.put(c, e, v[i]);
     }
-    e -= a.nA;
-    if (e < a.nOde) {
-        if (a.ode.ok()) a.ode.put(c, e, a.cOde[(long long)e * a.NC + slot]);
-        return;
-    }
-    e -= a.nOde;
-    if (e < a.nOde) {
-        if (a.latent.ok()) a.latent.put(c, e, a.cLat[(long long)e * a.NC + slot]);
-        return;
-    }
-    e -= a.nOde;
-    if (a.betaN.ok()) a.betaN.put(c, e, a.cBeta[(long long)e * a.NC + slot]);
 }
 
 // logOrigin of ESlice_par_General: -1/2 sum over ALL rows of OriginTraj (:1673-1678); one warp per chain.
