@@ -683,27 +683,36 @@ def test_slice_kernel_variants_give_the_same_chains(changepoint):
     par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"),
                            g.setting("control.hyper")])
     pb = api.problem_for(g.times, g.x_r, g.x_i, g.gridsize, g.t_correct, g.init)
-    keys = ("LNA_ESS_ASYNC", "LNA_ESS_ASYNC_W", "LNA_ESS_SEG", "LNA_ESS_SEG_T", "LNA_GRAPH")
+    keys = ("LNA_ESS_ASYNC", "LNA_ESS_ASYNC_W", "LNA_ESS_ASYNC_WPS", "LNA_ESS_SEG", "LNA_ESS_SEG_T", "LNA_GRAPH")
     saved = {k: os.environ.get(k) for k in keys}
-    results = {}
+    # second batch: more chains than a persistent launch of one 32-lane group per warp and one warp per SM sub-partition holds
+    # (592 on a B200), so that groups REFILL from the batch counter; 16 lanes per chain is the default from 1007 chains on
+    cases = ((96, (("waves", {"LNA_ESS_ASYNC": "0"}), ("barrier-free", {"LNA_ESS_ASYNC_W": "8"}),
+                   ("barrier-free-4", {"LNA_ESS_ASYNC_W": "4"}), ("barrier-free-16", {"LNA_ESS_ASYNC_W": "16"}),
+                   ("sequential", {"LNA_ESS_SEG": "1", "LNA_ESS_SEG_T": "7"}))),
+             (1100, (("waves", {"LNA_ESS_ASYNC": "0"}), ("default", {}),
+                     ("barrier-free-32-refill", {"LNA_ESS_ASYNC_W": "32", "LNA_ESS_ASYNC_WPS": "1"}),
+                     ("barrier-free-8-refill", {"LNA_ESS_ASYNC_W": "8", "LNA_ESS_ASYNC_WPS": "1"}))))
     try:
-        for name, env in (("waves", {"LNA_ESS_ASYNC": "0"}), ("barrier-free", {"LNA_ESS_ASYNC_W": "8"}),
-                          ("barrier-free-4", {"LNA_ESS_ASYNC_W": "4"}), ("sequential", {"LNA_ESS_SEG": "1", "LNA_ESS_SEG_T": "7"})):
-            for k in keys:
-                os.environ.pop(k, None)
-            os.environ.update(env)
-            os.environ["LNA_GRAPH"] = "0"  # (a captured graph would freeze the first variant's launches)
-            ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
-            for it in range(8):
-                ch.step_rng(chm.vignette_opts(g, update_traj=it >= 2), 99, it)
-            results[name] = ch.get()
+        for B, variants in cases:
+            results = {}
+            for name, env in variants:
+                for k in keys:
+                    os.environ.pop(k, None)
+                os.environ.update(env)
+                os.environ["LNA_GRAPH"] = "0"  # (a captured graph would freeze the first variant's launches)
+                ch = chm.Chains(pb, np.tile(par0, (B, 1)), g.setting("control.traj"))
+                for it in range(8 if B < 1000 else 5):
+                    ch.step_rng(chm.vignette_opts(g, update_traj=it >= 2), 99, it)
+                results[name] = ch.get()
+            ref = results["waves"]
+            for name, r in results.items():
+                assert np.array_equal(r["n_full_evals"], ref["n_full_evals"]) and np.array_equal(r["n_mh_accept"], ref["n_mh_accept"]), (B, name)
+                assert relerr(r["par"], ref["par"]) < 1e-12 and relerr(r["coalLog"], ref["coalLog"]) < 1e-12, (B, name)
+                assert relerr(r["LatentTraj"], ref["LatentTraj"]) < 1e-10 and np.array_equal(r["status"], ref["status"]), (B, name)
     finally:
         for k, v in saved.items():
             if v is None:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    ref = results["waves"]
-    for name, r in results.items():
-        assert np.array_equal(r["n_full_evals"], ref["n_full_evals"]) and np.array_equal(r["n_mh_accept"], ref["n_mh_accept"]), name
-        assert relerr(r["par"], ref["par"]) < 1e-12 and relerr(r["coalLog"], ref["coalLog"]) < 1e-12, name
