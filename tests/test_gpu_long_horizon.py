@@ -58,10 +58,15 @@ def _osnap(st):
             "n_mh_accept": st["n_mh_accept"]}
 
 
-def test_general_mcmc_with_eslice_200_iterations(changepoint):
+@pytest.mark.parametrize("schedule", ["auto", "barrier-free"])
+def test_general_mcmc_with_eslice_200_iterations(changepoint, monkeypatch, schedule):
     """Changpoint_sim vignette body (gamma walk + no-op hyper entry, parameter slice update, trajectory slice update from
-    iteration 20 on)."""
+    iteration 20 on).  `auto` is what 64 chains select (speculative waves, three-warp pipeline); `barrier-free` forces the
+    kernel that batches of 1007 to ~28 000 chains select (lna_async.cuh: dynamic candidate assignment, early rejection), with 16
+    lanes per chain as in the lower half of that range."""
     from lnaphylodyn_b200 import api, chains as chm
+    if schedule == "barrier-free":
+        monkeypatch.setenv("LNA_ESS_ASYNC_W", "16")
     g = changepoint
     B, seed, burn1 = CHAINS, 2024, 20
     par0 = np.concatenate([[g.x_r[0], 1.0], g.setting("control.R0"), g.setting("control.gamma"), g.setting("control.ch"),
